@@ -1,0 +1,139 @@
+"""Uniform MeshBlock lattice: the geometry/index bookkeeping Parthenon hands the hot path.
+
+Host-side only (numpy).  Mirrors:
+  * block domains -- P:mesh/forest/tree.cpp:297-320, P:mesh/forest/logical_location.cpp:61-74,
+    P:defs.hpp:98-101 (symmetrized logical -> actual position);
+  * per-block coordinates -- P:coordinates/uniform_cartesian.hpp:30-36
+    (dx = (xmax-xmin)/nx, xmin_ = xmin - nghost*dx for non-symmetry directions);
+  * index shapes -- interior [ng, ng+nx-1], entire [0, nx+2ng-1]; symmetry (nx==1)
+    directions carry no ghosts.
+Block ids are lexicographic (x1 fastest) over the nbx x nby x nbz lattice.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .enums import BoundaryFlag, Coordinates, CoordSelect
+from .params import ParameterInput
+
+
+def _symm_coord(index: int, side: int, nrange: int) -> float:
+    """LogicalLocation::IndexToSymmetrizedCoordinate (logical_location.cpp:61-74)."""
+    noffset = index - nrange // 2
+    noffset_ceil = index - (nrange + 1) // 2
+    return float(noffset + noffset_ceil + side) / (2.0 * nrange)
+
+
+@dataclass
+class UniformMesh:
+    nx: tuple            # mesh zones (nx1, nx2, nx3)
+    xmin: tuple
+    xmax: tuple
+    block_nx: tuple      # zones per MeshBlock
+    nghost: int = 2
+    bcs: tuple = (BoundaryFlag.periodic,) * 6   # ix1, ox1, ix2, ox2, ix3, ox3
+    coords: Coordinates = Coordinates.cartesian
+    # optional sub-lattice owned by this rank (block-spatial partition)
+    lattice_lo: tuple = (0, 0, 0)
+    lattice_n: tuple | None = None
+    ndim: int = field(init=False)
+
+    def __post_init__(self):
+        self.nx = tuple(int(v) for v in self.nx)
+        self.block_nx = tuple(int(v) for v in self.block_nx)
+        self.ndim = 1 + (self.nx[1] > 1) + (self.nx[2] > 1)
+        for d in range(3):
+            if self.nx[d] % self.block_nx[d]:
+                raise ValueError("mesh size must be a multiple of the MeshBlock size")
+        self.nrb = tuple(self.nx[d] // self.block_nx[d] for d in range(3))
+        if self.lattice_n is None:
+            self.lattice_n = self.nrb
+        ng = self.nghost
+        self.ngd = tuple(ng if self.nx[d] > 1 else 0 for d in range(3))
+        self.ni, self.nj, self.nk = (self.block_nx[d] + 2 * self.ngd[d] for d in range(3))
+        self.is_, self.js, self.ks = self.ngd
+        self.ie = self.is_ + self.block_nx[0] - 1
+        self.je = self.js + self.block_nx[1] - 1
+        self.ke = self.ks + self.block_nx[2] - 1
+        # gas.face.velocity is a plain Face field: +1 in every non-trivial direction
+        # (P:interface/metadata.cpp:378-387)
+        self.fni = self.ni + (1 if self.ni > 1 else 0)
+        self.fnj = self.nj + (1 if self.nj > 1 else 0)
+        self.fnk = self.nk + (1 if self.nk > 1 else 0)
+        nbx, nby, nbz = self.lattice_n
+        self.nb = nbx * nby * nbz
+        self.blk_xmin = np.zeros((self.nb, 3))   # Coordinates_t::xmin_ (ghost shifted)
+        self.blk_dx = np.zeros((self.nb, 3))
+        self.blk_lo = np.zeros((self.nb, 3))     # physical block lower corner
+        self.blk_loc = np.zeros((self.nb, 3), dtype=np.int64)
+        for b in range(self.nb):
+            l = (b % nbx, (b // nbx) % nby, b // (nbx * nby))
+            for d in range(3):
+                lx = l[d] + self.lattice_lo[d]
+                self.blk_loc[b, d] = lx
+                if self.nx[d] > 1:
+                    ul = _symm_coord(lx, 0, self.nrb[d])
+                    ur = _symm_coord(lx, 2, self.nrb[d])  # BlockLocation::Right == 2
+                    mid = 0.5 * (self.xmin[d] + self.xmax[d])
+                    lo = mid + (ul * self.xmax[d] - ul * self.xmin[d])
+                    hi = mid + (ur * self.xmax[d] - ur * self.xmin[d])
+                else:
+                    lo, hi = self.xmin[d], self.xmax[d]
+                dx = (hi - lo) / self.block_nx[d]
+                self.blk_lo[b, d] = lo
+                self.blk_dx[b, d] = dx
+                self.blk_xmin[b, d] = lo - self.ngd[d] * dx
+
+    # ---- convenience -------------------------------------------------------------
+    @property
+    def cells_per_block(self):
+        return self.ni * self.nj * self.nk
+
+    @property
+    def interior_zones(self):
+        return self.nb * self.block_nx[0] * self.block_nx[1] * self.block_nx[2]
+
+    @property
+    def global_nrb(self):
+        return self.nrb
+
+    def shape(self, nvar):
+        return (self.nb, nvar, self.nk, self.nj, self.ni)
+
+    def face_shape(self, ns):
+        return (self.nb, ns, self.fnk, self.fnj, self.fni)
+
+    def interior(self):
+        return (slice(self.ks, self.ke + 1), slice(self.js, self.je + 1),
+                slice(self.is_, self.ie + 1))
+
+    def face_positions(self, b, d):
+        n = (self.ni, self.nj, self.nk)[d]
+        return self.blk_xmin[b, d] + np.arange(n + 1) * self.blk_dx[b, d]
+
+    def bc_ints(self):
+        return np.array([int(v) for v in self.bcs], dtype=np.int32)
+
+    @classmethod
+    def from_input(cls, pin: ParameterInput, **kw):
+        g = lambda k, dflt=None: (pin.GetOrAddInteger("parthenon/mesh", k, dflt)
+                                  if dflt is not None else pin.GetInteger("parthenon/mesh", k))
+        nx = (g("nx1"), g("nx2", 1), g("nx3", 1))
+        xmin = tuple(pin.GetOrAddReal("parthenon/mesh", f"x{d}min", -0.5) for d in (1, 2, 3))
+        xmax = tuple(pin.GetOrAddReal("parthenon/mesh", f"x{d}max", 0.5) for d in (1, 2, 3))
+        bnx = tuple(pin.GetOrAddInteger("parthenon/meshblock", f"nx{d}", nx[d - 1])
+                    for d in (1, 2, 3))
+        bcs = []
+        for d in (1, 2, 3):
+            for side in ("i", "o"):
+                name = pin.GetOrAddString("parthenon/mesh", f"{side}x{d}_bc", "outflow")
+                if name not in BoundaryFlag.__members__:
+                    raise ValueError(f"boundary flag {name!r} is outside the hot-path scope")
+                bcs.append(BoundaryFlag[name])
+        ndim = 1 + (nx[1] > 1) + (nx[2] > 1)
+        coords = CoordSelect(pin.GetOrAddString("artemis", "coordinates", "cartesian"), ndim)
+        return cls(nx=nx, xmin=xmin, xmax=xmax, block_nx=bnx,
+                   nghost=pin.GetOrAddInteger("parthenon/mesh", "nghost", 2),
+                   bcs=tuple(bcs), coords=coords, **kw)

@@ -1,0 +1,1068 @@
+/*
+ * artemis_oracle.c -- CPU restatement of the Artemis finite-volume gas/dust stage update.
+ *
+ * TEST INFRASTRUCTURE ONLY (see artemis_oracle.h).  Never linked into the product.
+ *
+ * Compile WITHOUT FMA contraction: gcc -O2 -ffp-contract=off -fopenmp (oracle/Makefile).
+ * All citations are file:line in lanl/artemis @ 6c2a7a8 ("P:" = external/parthenon/src/).
+ */
+#include "artemis_oracle.h"
+
+#include <math.h>
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define SQR(x) ((x) * (x))
+#define IDX(g, nvar, b, n, k, j, i)                                                      \
+  (((((size_t)(b) * (nvar) + (n)) * (g)->nk + (k)) * (g)->nj + (j)) * (g)->ni + (i))
+#define FIDX(g, S, b, n, k, j, i)                                                        \
+  (((((size_t)(b) * (S) + (n)) * (g)->fnk + (k)) * (g)->fnj + (j)) * (g)->fni + (i))
+
+static inline double dmax(double a, double b) { return a > b ? a : b; } /* std::max */
+static inline double dmin(double a, double b) { return b < a ? b : a; } /* std::min */
+
+int ao_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* ===================================================================================== */
+/* Geometry: src/geometry/{geometry,cylindrical,spherical,axisymmetric}.hpp               */
+/* ===================================================================================== */
+typedef struct {
+  double x1[2], x2[2], x3[2];
+} bbox_t;
+
+/* geometry.hpp:61-79 (BBox) with P:coordinates/uniform_cartesian.hpp:153-157 (Xf) */
+static inline bbox_t make_bbox(const double *xmin, const double *dx, int k, int j, int i) {
+  bbox_t b;
+  b.x1[0] = xmin[0] + i * dx[0];
+  b.x1[1] = xmin[0] + (i + 1) * dx[0];
+  b.x2[0] = xmin[1] + j * dx[1];
+  b.x2[1] = xmin[1] + (j + 1) * dx[1];
+  b.x3[0] = xmin[2] + k * dx[2];
+  b.x3[1] = xmin[2] + (k + 1) * dx[2];
+  return b;
+}
+
+static inline int is_sph(int geom) {
+  return geom == AO_SPHERICAL1D || geom == AO_SPHERICAL2D || geom == AO_SPHERICAL3D;
+}
+/* geometry.hpp:102-113 */
+static inline int g_x1dep(int geom) { return geom != AO_CARTESIAN; }
+static inline int g_x2dep(int geom) {
+  return geom == AO_SPHERICAL3D || geom == AO_SPHERICAL2D;
+}
+
+/* <r> = d(r^3/3)/d(r^2/2): cylindrical.hpp:52-56, axisymmetric.hpp:48-52 */
+static inline double rface_avg(const bbox_t *b) {
+  return 2.0 / 3.0 * (b->x1[0] * b->x1[0] + b->x1[0] * b->x1[1] + b->x1[1] * b->x1[1]) /
+         (b->x1[0] + b->x1[1]);
+}
+
+static inline double g_x1v(int geom, const bbox_t *b) {
+  if (geom == AO_CYLINDRICAL || geom == AO_AXISYMMETRIC) return rface_avg(b);
+  if (is_sph(geom)) { /* spherical.hpp:57-60, 261-264, 448-451 */
+    const double dr2 = b->x1[0] * b->x1[0] + b->x1[1] * b->x1[1];
+    return 0.75 * (b->x1[0] + b->x1[1]) * dr2 / (dr2 + b->x1[0] * b->x1[1]);
+  }
+  return 0.5 * (b->x1[0] + b->x1[1]); /* geometry.hpp:166 */
+}
+static inline double g_x2v(int geom, const bbox_t *b) {
+  if (geom == AO_SPHERICAL3D || geom == AO_SPHERICAL2D) { /* spherical.hpp:61-68 */
+    const double ctm = cos(b->x2[0]);
+    const double ctp = cos(b->x2[1]);
+    const double dst = sin(b->x2[1]) - sin(b->x2[0]);
+    return (dst - b->x2[1] * ctp + b->x2[0] * ctm) / fabs(ctm - ctp);
+  }
+  return 0.5 * (b->x2[0] + b->x2[1]);
+}
+static inline double g_x3v(int geom, const bbox_t *b) {
+  (void)geom;
+  return 0.5 * (b->x3[0] + b->x3[1]);
+}
+
+/* scale factors h_i(x): geometry.hpp:172-180 + overrides */
+static inline double g_hx1(int geom, double x1, double x2, double x3) {
+  (void)geom; (void)x1; (void)x2; (void)x3;
+  return 1.0;
+}
+static inline double g_hx2(int geom, double x1, double x2, double x3) {
+  (void)x2; (void)x3;
+  if (geom == AO_CYLINDRICAL || is_sph(geom)) return x1; /* cyl:58, sph:49,253,444 */
+  return 1.0;
+}
+static inline double g_hx3(int geom, double x1, double x2, double x3) {
+  (void)x3;
+  if (geom == AO_AXISYMMETRIC) return x1; /* axisymmetric.hpp:54 */
+  if (geom == AO_SPHERICAL3D || geom == AO_SPHERICAL2D) return x1 * sin(x2); /* sph:53 */
+  return 1.0; /* NB spherical1D does NOT override hx3 */
+}
+/* volume-averaged scale factors: geometry.hpp:182-184 + overrides */
+static inline double g_hx1v(int geom, const bbox_t *b) {
+  (void)geom; (void)b;
+  return 1.0;
+}
+static inline double g_hx2v(int geom, const bbox_t *b) {
+  if (geom == AO_CYLINDRICAL || geom == AO_SPHERICAL3D || geom == AO_SPHERICAL2D)
+    return g_x1v(geom, b); /* cyl:62, sph:70,274 ; spherical1D keeps the default 1.0 */
+  return 1.0;
+}
+static inline double g_hx3v(int geom, const bbox_t *b) {
+  if (geom == AO_AXISYMMETRIC) return g_x1v(geom, b); /* axisymmetric.hpp:58 */
+  if (geom == AO_SPHERICAL3D || geom == AO_SPHERICAL2D) { /* spherical.hpp:71-85 */
+    const double ctm = cos(b->x2[0]);
+    const double ctp = cos(b->x2[1]);
+    const double stm = sin(b->x2[0]);
+    const double stp = sin(b->x2[1]);
+    const double dsc = stp * ctp - stm * ctm;
+    const double dx2 = b->x2[1] - b->x2[0];
+    return g_x1v(geom, b) * 0.5 * (dx2 - dsc) / fabs(ctm - ctp);
+  }
+  return 1.0;
+}
+
+/* face centroids: geometry.hpp:186-201 + overrides */
+static inline void g_facecen1(int geom, const bbox_t *b, int f, double xf[3]) {
+  xf[0] = b->x1[f];
+  xf[1] = g_x2v(geom, b);
+  xf[2] = g_x3v(geom, b);
+}
+static inline void g_facecen2(int geom, const bbox_t *b, int f, double xf[3]) {
+  if (geom == AO_AXISYMMETRIC || geom == AO_SPHERICAL3D) { /* axi:60-67, sph:87-94 */
+    xf[0] = rface_avg(b);
+    xf[1] = b->x2[f];
+    xf[2] = 0.5 * (b->x3[0] + b->x3[1]);
+  } else if (geom == AO_SPHERICAL2D) { /* spherical.hpp:291-298 */
+    xf[0] = rface_avg(b);
+    xf[1] = b->x2[f];
+    xf[2] = 0.0;
+  } else if (geom == AO_SPHERICAL1D) { /* spherical.hpp:453-460 */
+    xf[0] = rface_avg(b);
+    xf[1] = M_PI * 0.5;
+    xf[2] = 0.0;
+  } else {
+    xf[0] = g_x1v(geom, b);
+    xf[1] = b->x2[f];
+    xf[2] = g_x3v(geom, b);
+  }
+}
+static inline void g_facecen3(int geom, const bbox_t *b, int f, double xf[3]) {
+  if (geom == AO_CYLINDRICAL || geom == AO_SPHERICAL3D) { /* cyl:64-71, sph:96-103 */
+    xf[0] = rface_avg(b);
+    xf[1] = 0.5 * (b->x2[0] + b->x2[1]);
+    xf[2] = b->x3[f];
+  } else if (geom == AO_SPHERICAL2D) { /* spherical.hpp:300-307 */
+    xf[0] = rface_avg(b);
+    xf[1] = 0.5 * (b->x2[0] + b->x2[1]);
+    xf[2] = 0.0;
+  } else if (geom == AO_SPHERICAL1D) { /* spherical.hpp:462-469 */
+    xf[0] = rface_avg(b);
+    xf[1] = M_PI * 0.5;
+    xf[2] = 0.0;
+  } else {
+    xf[0] = g_x1v(geom, b);
+    xf[1] = g_x2v(geom, b);
+    xf[2] = b->x3[f];
+  }
+}
+
+/* face areas: geometry.hpp:203-220 + overrides */
+static inline double g_area1(int geom, const bbox_t *b, double x1f) {
+  const double dx2 = b->x2[1] - b->x2[0];
+  const double dx3 = b->x3[1] - b->x3[0];
+  switch (geom) {
+  case AO_CYLINDRICAL:
+  case AO_AXISYMMETRIC: return x1f * dx2 * dx3; /* cyl:73-78, axi:69-74 */
+  case AO_SPHERICAL3D:                          /* spherical.hpp:105-109 */
+    return x1f * x1f * fabs(cos(b->x2[0]) - cos(b->x2[1])) * dx3;
+  case AO_SPHERICAL2D: return x1f * x1f * fabs(cos(b->x2[0]) - cos(b->x2[1])); /* :309 */
+  case AO_SPHERICAL1D: return x1f * x1f;                                       /* :471 */
+  default: return dx2 * dx3;
+  }
+}
+static inline double g_area2(int geom, const bbox_t *b, double x2f) {
+  const double dx1 = b->x1[1] - b->x1[0];
+  const double dx3 = b->x3[1] - b->x3[0];
+  switch (geom) {
+  case AO_AXISYMMETRIC: return (b->x1[0] + b->x1[1]) * 0.5 * dx1 * dx3; /* axi:75-80 */
+  case AO_SPHERICAL3D: return 0.5 * (b->x1[1] + b->x1[0]) * sin(x2f) * dx1 * dx3; /*:110*/
+  case AO_SPHERICAL2D: return 0.5 * (b->x1[1] + b->x1[0]) * sin(x2f) * dx1;       /*:313*/
+  case AO_SPHERICAL1D: return 0.5 * (b->x1[1] + b->x1[0]) * dx1;                  /*:475*/
+  default: return dx1 * dx3;
+  }
+}
+static inline double g_area3(int geom, const bbox_t *b, double x3f) {
+  (void)x3f;
+  const double dx1 = b->x1[1] - b->x1[0];
+  const double dx2 = b->x2[1] - b->x2[0];
+  switch (geom) {
+  case AO_CYLINDRICAL:
+  case AO_SPHERICAL3D:
+  case AO_SPHERICAL2D: return 0.5 * (b->x1[0] + b->x1[1]) * dx1 * dx2; /* cyl:79, sph:116 */
+  case AO_SPHERICAL1D: return 0.5 * (b->x1[0] + b->x1[1]) * dx1;       /* sph:480 */
+  default: return dx1 * dx2;
+  }
+}
+/* geometry.hpp:222-228 + overrides */
+static inline double g_volume(int geom, const bbox_t *b) {
+  const double dx1 = b->x1[1] - b->x1[0];
+  const double dx2 = b->x2[1] - b->x2[0];
+  const double dx3 = b->x3[1] - b->x3[0];
+  if (geom == AO_CYLINDRICAL || geom == AO_AXISYMMETRIC)
+    return (b->x1[0] + b->x1[1]) * 0.5 * dx1 * dx2 * dx3; /* cyl:85-90, axi:82-87 */
+  if (is_sph(geom)) {                                     /* sph:123-132,327-335,486 */
+    const double rfac =
+        (b->x1[0] * b->x1[0] + b->x1[0] * b->x1[1] + b->x1[1] * b->x1[1]) / 3.0;
+    if (geom == AO_SPHERICAL1D) return rfac * dx1;
+    const double dc = fabs(cos(b->x2[0]) - cos(b->x2[1]));
+    if (geom == AO_SPHERICAL2D) return rfac * dx1 * dc;
+    return rfac * dx1 * dc * dx3;
+  }
+  return dx1 * dx2 * dx3;
+}
+/* connection terms {dh1/dxd, dh2/dxd, dh3/dxd}: geometry.hpp:238-248 + overrides */
+static inline void g_conn1(int geom, const bbox_t *b, double c[3]) {
+  c[0] = c[1] = c[2] = 0.0;
+  if (geom == AO_CYLINDRICAL) c[1] = 1.0 / (0.5 * (b->x1[0] + b->x1[1])); /* cyl:92 */
+  if (geom == AO_AXISYMMETRIC) c[2] = 1.0 / (0.5 * (b->x1[0] + b->x1[1])); /* axi:89 */
+  if (is_sph(geom)) { /* spherical.hpp:134-141 */
+    const double v =
+        3.0 / 2.0 * (b->x1[0] + b->x1[1]) /
+        (b->x1[0] * b->x1[0] + b->x1[0] * b->x1[1] + b->x1[1] * b->x1[1]);
+    c[1] = v;
+    c[2] = v;
+  }
+}
+static inline void g_conn2(int geom, const bbox_t *b, double c[3]) {
+  c[0] = c[1] = c[2] = 0.0;
+  if (geom == AO_SPHERICAL3D || geom == AO_SPHERICAL2D) /* spherical.hpp:142-145 */
+    c[2] = (sin(b->x2[1]) - sin(b->x2[0])) / fabs(cos(b->x2[0]) - cos(b->x2[1]));
+}
+/* geometry.hpp:330-357 cell widths h_d(xv) * dx_d */
+static inline void g_cell_widths(int geom, const bbox_t *b, double w[3]) {
+  const double xv[3] = {g_x1v(geom, b), g_x2v(geom, b), g_x3v(geom, b)};
+  w[0] = g_hx1(geom, xv[0], xv[1], xv[2]) * (b->x1[1] - b->x1[0]);
+  w[1] = g_hx2(geom, xv[0], xv[1], xv[2]) * (b->x2[1] - b->x2[0]);
+  w[2] = g_hx3(geom, xv[0], xv[1], xv[2]) * (b->x3[1] - b->x3[0]);
+}
+/* src/rotating_frame/rotating_frame.hpp:32-49 with the ConvertToCylWithVec of each geom */
+static inline void g_rotation_velocity(int geom, const double xv[3], double omf,
+                                       double vf[3]) {
+  vf[0] = vf[1] = vf[2] = 0.0;
+  switch (geom) {
+  case AO_CARTESIAN: vf[1] = omf; break;
+  case AO_CYLINDRICAL: vf[1] = 1.0 * (omf * xv[0]); break; /* cyl:134-141 ex2[1]=1 */
+  case AO_AXISYMMETRIC: vf[2] = 1.0 * (omf * xv[0]); break; /* axi:137-147 ex3[1]=1 */
+  case AO_SPHERICAL3D:
+  case AO_SPHERICAL2D: vf[2] = 1.0 * (omf * (xv[0] * sin(xv[1]))); break; /* sph:208-230 */
+  case AO_SPHERICAL1D: vf[2] = 1.0 * (omf * (xv[0] * 1.0)); break;
+  }
+}
+
+void ao_geom_cell(int geom, const double *xmin, const double *dx, int k, int j, int i,
+                  double *out) {
+  bbox_t b = make_bbox(xmin, dx, k, j, i);
+  double c[3], w[3], xf[3];
+  out[0] = g_x1v(geom, &b);
+  out[1] = g_x2v(geom, &b);
+  out[2] = g_x3v(geom, &b);
+  out[3] = g_hx1v(geom, &b);
+  out[4] = g_hx2v(geom, &b);
+  out[5] = g_hx3v(geom, &b);
+  out[6] = g_volume(geom, &b);
+  out[7] = g_area1(geom, &b, b.x1[0]);
+  out[8] = g_area1(geom, &b, b.x1[1]);
+  out[9] = g_area2(geom, &b, b.x2[0]);
+  out[10] = g_area2(geom, &b, b.x2[1]);
+  out[11] = g_area3(geom, &b, b.x3[0]);
+  out[12] = g_area3(geom, &b, b.x3[1]);
+  g_conn1(geom, &b, c);
+  out[13] = c[0]; out[14] = c[1]; out[15] = c[2];
+  g_conn2(geom, &b, c);
+  out[16] = c[0]; out[17] = c[1]; out[18] = c[2];
+  g_cell_widths(geom, &b, w);
+  out[19] = w[0]; out[20] = w[1]; out[21] = w[2];
+  g_facecen1(geom, &b, 0, xf);
+  out[22] = g_hx1(geom, xf[0], xf[1], xf[2]);
+  out[23] = g_hx2(geom, xf[0], xf[1], xf[2]);
+  out[24] = g_hx3(geom, xf[0], xf[1], xf[2]);
+  g_facecen2(geom, &b, 0, xf);
+  out[25] = g_hx1(geom, xf[0], xf[1], xf[2]);
+  out[26] = g_hx2(geom, xf[0], xf[1], xf[2]);
+  out[27] = g_hx3(geom, xf[0], xf[1], xf[2]);
+  g_facecen3(geom, &b, 0, xf);
+  out[28] = g_hx1(geom, xf[0], xf[1], xf[2]);
+  out[29] = g_hx2(geom, xf[0], xf[1], xf[2]);
+  out[30] = g_hx3(geom, xf[0], xf[1], xf[2]);
+  out[31] = 0.0;
+}
+
+/* ===================================================================================== */
+/* Reconstruction: src/utils/fluxes/reconstruction/{plm,ppm}.hpp                          */
+/* ===================================================================================== */
+/* plm.hpp:31-47 */
+void ao_plm(double q_im1, double q_i, double q_ip1, double *ql_ip1, double *qr_i) {
+  double dql = (q_i - q_im1);
+  double dqr = (q_ip1 - q_i);
+  double dq2 = dql * dqr;
+  double dqm = dq2 / (dql + dqr);
+  if (dq2 <= 0.0) dqm = 0.0;
+  *ql_ip1 = q_i + dqm;
+  *qr_i = q_i - dqm;
+}
+/* plm.hpp:53-73 */
+void ao_plm_g(double q_im1, double q_i, double q_ip1, double x_im1, double x_i,
+              double x_ip1, double xf0, double xf1, double dx, double *ql_ip1,
+              double *qr_i) {
+  const double dql = (q_i - q_im1) * dx / (x_i - x_im1);
+  const double dqr = (q_ip1 - q_i) * dx / (x_ip1 - x_i);
+  const double dq2 = dql * dqr;
+  const double cr = (x_ip1 - x_i) / (xf1 - x_i);
+  const double cl = (x_i - x_im1) / (x_i - xf0);
+  const double dqm = (dq2 <= 0.0) ? 0.0
+                                  : dq2 * (cr * dql + cl * dqr) /
+                                        (dql * dql + dqr * dqr + dq2 * (cl + cr - 2.0));
+  *ql_ip1 = q_i + dqm * (xf1 - x_i) / dx;
+  *qr_i = q_i - dqm * (x_i - xf0) / dx;
+}
+/* ppm.hpp:32-66 */
+void ao_ppm4(double q_im2, double q_im1, double q_i, double q_ip1, double q_ip2,
+             double *ql_ip1, double *qr_i) {
+  double qlv = (7. * (q_i + q_im1) - (q_im2 + q_ip1)) / 12.0;
+  double qrv = (7. * (q_i + q_ip1) - (q_im1 + q_ip2)) / 12.0;
+  qlv = dmax(qlv, dmin(q_i, q_im1));
+  qlv = dmin(qlv, dmax(q_i, q_im1));
+  qrv = dmax(qrv, dmin(q_i, q_ip1));
+  qrv = dmin(qrv, dmax(q_i, q_ip1));
+  double qc = qrv - q_i;
+  double qd = qlv - q_i;
+  if ((qc * qd) >= 0.0) {
+    qlv = q_i;
+    qrv = q_i;
+  } else {
+    if (fabs(qc) >= 2.0 * fabs(qd)) qrv = q_i - 2.0 * qd;
+    if (fabs(qd) >= 2.0 * fabs(qc)) qlv = q_i - 2.0 * qc;
+  }
+  *ql_ip1 = qrv;
+  *qr_i = qlv;
+}
+
+/* Reconstruction<R,DIR,GEOM>::apply (pcm.hpp:30-88, plm.hpp:78-175, ppm.hpp:71-129):
+ * reconstruct cells (k,j,i), i in [il,iu], along `dir`; cell i's upper-face value goes to
+ * ql[n][i + (dir==1)] and its lower-face value to qr[n][i].  Scratch rows are ni+1 wide. */
+static void recon_row(const ao_grid *g, int recon, int dir, int nvar, const double *prim,
+                      int b, int k, int j, int il, int iu, double *ql, double *qr) {
+  const int W = g->ni + 1;
+  const ptrdiff_t s1 = 1, s2 = (ptrdiff_t)g->ni, s3 = (ptrdiff_t)g->ni * g->nj;
+  const ptrdiff_t st = dir == 1 ? s1 : (dir == 2 ? s2 : s3);
+  const int sh = (dir == 1) ? 1 : 0;
+  const double *xmin = g->xmin + 3 * b, *dx = g->dx + 3 * b;
+  for (int n = 0; n < nvar; ++n) {
+    const double *q = prim + IDX(g, nvar, b, n, k, j, 0);
+    double *qln = ql + (size_t)n * W, *qrn = qr + (size_t)n * W;
+    for (int i = il; i <= iu; ++i) {
+      if (recon == AO_PCM) {
+        qln[i + sh] = q[i];
+        qrn[i] = q[i];
+      } else if (recon == AO_PLM) {
+        if (g->geom == AO_CARTESIAN) {
+          ao_plm(q[i - st], q[i], q[i + st], &qln[i + sh], &qrn[i]);
+        } else {
+          const int dk = (dir == 3), dj = (dir == 2), di = (dir == 1);
+          bbox_t bm = make_bbox(xmin, dx, k - dk, j - dj, i - di);
+          bbox_t bc = make_bbox(xmin, dx, k, j, i);
+          bbox_t bp = make_bbox(xmin, dx, k + dk, j + dj, i + di);
+          double xvm, xvc, xvp, w[3];
+          const double *xf;
+          g_cell_widths(g->geom, &bc, w);
+          if (dir == 1) {
+            xvm = g_x1v(g->geom, &bm); xvc = g_x1v(g->geom, &bc); xvp = g_x1v(g->geom, &bp);
+            xf = bc.x1;
+          } else if (dir == 2) {
+            xvm = g_x2v(g->geom, &bm); xvc = g_x2v(g->geom, &bc); xvp = g_x2v(g->geom, &bp);
+            xf = bc.x2;
+          } else {
+            xvm = g_x3v(g->geom, &bm); xvc = g_x3v(g->geom, &bc); xvp = g_x3v(g->geom, &bp);
+            xf = bc.x3;
+          }
+          ao_plm_g(q[i - st], q[i], q[i + st], xvm, xvc, xvp, xf[0], xf[1], w[dir - 1],
+                   &qln[i + sh], &qrn[i]);
+        }
+      } else {
+        ao_ppm4(q[i - 2 * st], q[i - st], q[i], q[i + st], q[i + 2 * st], &qln[i + sh],
+                &qrn[i]);
+      }
+    }
+  }
+}
+
+/* ===================================================================================== */
+/* Riemann solvers: src/utils/fluxes/riemann/{hllc,hlle,llf}.hpp                          */
+/* wl/wr = {rho, vx(normal), vy, vz, P, sie}; out = {Frho,Fmx,Fmy,Fmz,FE,Fu,pface,vface}   */
+/* ===================================================================================== */
+/* hllc.hpp:76-180 */
+static void solve_hllc(double gm1, const double *wl, const double *wr, double *out) {
+  const double wl_idn = wl[0], wl_ivx = wl[1], wl_ivy = wl[2], wl_ivz = wl[3],
+               wl_ipr = wl[4], wl_ise = wl[5];
+  const double wr_idn = wr[0], wr_ivx = wr[1], wr_ivy = wr[2], wr_ivz = wr[3],
+               wr_ipr = wr[4], wr_ise = wr[5];
+  double igm1 = 1.0 / gm1;
+  double gamma = gm1 + 1.0;
+  double alpha = (gamma + 1.0) / (2.0 * gamma);
+  double qa, qb, qc, qd, qe, qf;
+  qa = sqrt(gamma * wl_ipr / wl_idn);
+  qb = sqrt(gamma * wr_ipr / wr_idn);
+  double el = wl_ipr * igm1 + 0.5 * wl_idn * (SQR(wl_ivx) + SQR(wl_ivy) + SQR(wl_ivz));
+  double er = wr_ipr * igm1 + 0.5 * wr_idn * (SQR(wr_ivx) + SQR(wr_ivy) + SQR(wr_ivz));
+  qc = 0.25 * (wl_idn + wr_idn) * (qa + qb);
+  qd = 0.5 * (wl_ipr + wr_ipr + (wl_ivx - wr_ivx) * qc);
+  qe = (qd <= wl_ipr) ? 1.0 : sqrt(1.0 + alpha * ((qd / wl_ipr) - 1.0));
+  qf = (qd <= wr_ipr) ? 1.0 : sqrt(1.0 + alpha * ((qd / wr_ipr) - 1.0));
+  double sl = wl_ivx - qa * qe;
+  double sr = wr_ivx + qb * qf;
+  qa = sr > 0.0 ? sr : 1.0e-20;
+  qb = sl < 0.0 ? sl : -1.0e-20;
+  qe = wl_ivx - sl;
+  qf = wr_ivx - sr;
+  qc = wl_ipr + qe * wl_idn * wl_ivx;
+  qd = wr_ipr + qf * wr_idn * wr_ivx;
+  double ml = wl_idn * qe;
+  double mr = -(wr_idn * qf);
+  double am = (qc - qd) / (ml + mr);
+  double cp = (ml * qd + mr * qc) / (ml + mr);
+  cp = cp > 0.0 ? cp : 0.0;
+  qe = wl_idn * (wl_ivx - qb);
+  qf = wr_idn * (wr_ivx - qa);
+  double fld = qe, frd = qf;
+  double flmx = qe * wl_ivx, frmx = qf * wr_ivx;
+  double flmy = qe * wl_ivy, frmy = qf * wr_ivy;
+  double flmz = qe * wl_ivz, frmz = qf * wr_ivz;
+  double fle = el * (wl_ivx - qb) + wl_ipr * wl_ivx;
+  double fre = er * (wr_ivx - qa) + wr_ipr * wr_ivx;
+  if (am >= 0.0) {
+    qc = am / (am - qb);
+    qd = 0.0;
+    qe = -qb / (am - qb);
+  } else {
+    qc = 0.0;
+    qd = -am / (qa - am);
+    qe = qa / (qa - am);
+  }
+  out[6] = qc * wl_ipr + qd * wr_ipr + qe * cp;
+  const double frho = qc * fld + qd * frd;
+  out[0] = frho;
+  out[1] = qc * flmx + qd * frmx;
+  out[2] = qc * flmy + qd * frmy;
+  out[3] = qc * flmz + qd * frmz;
+  out[4] = qc * fle + qd * fre + qe * cp * am;
+  out[5] = frho * ((frho >= 0.0) ? wl_ise : wr_ise);
+  out[7] = frho / ((frho >= 0.0) ? wl_idn : wr_idn);
+}
+
+/* hlle.hpp:92-220 */
+static void solve_hlle(int fluid, double gm1, const double *wl, const double *wr,
+                       double *out) {
+  const int gas = (fluid == AO_GAS);
+  const double wl_idn = wl[0], wl_ivx = wl[1], wl_ivy = wl[2], wl_ivz = wl[3];
+  const double wr_idn = wr[0], wr_ivx = wr[1], wr_ivy = wr[2], wr_ivz = wr[3];
+  double wl_ipr = 0, wr_ipr = 0, wl_ise = 0, wr_ise = 0, igm1 = 0, gamma = 0;
+  if (gas) {
+    wl_ipr = wl[4]; wl_ise = wl[5]; wr_ipr = wr[4]; wr_ise = wr[5];
+    igm1 = 1.0 / gm1;
+    gamma = gm1 + 1.0;
+  }
+  double sqrtdl = sqrt(wl_idn);
+  double sqrtdr = sqrt(wr_idn);
+  double isdlpdr = 1.0 / (sqrtdl + sqrtdr);
+  double wroe_ivx = (sqrtdl * wl_ivx + sqrtdr * wr_ivx) * isdlpdr;
+  double wroe_ivy = (sqrtdl * wl_ivy + sqrtdr * wr_ivy) * isdlpdr;
+  double wroe_ivz = (sqrtdl * wl_ivz + sqrtdr * wr_ivz) * isdlpdr;
+  double el = 0, er = 0, hroe = 0;
+  if (gas) {
+    el = wl_ipr * igm1 + 0.5 * wl_idn * (SQR(wl_ivx) + SQR(wl_ivy) + SQR(wl_ivz));
+    er = wr_ipr * igm1 + 0.5 * wr_idn * (SQR(wr_ivx) + SQR(wr_ivy) + SQR(wr_ivz));
+    hroe = ((el + wl_ipr) / sqrtdl + (er + wr_ipr) / sqrtdr) * isdlpdr;
+  }
+  double qa = 0, qb = 0, sl, sr;
+  if (gas) {
+    qa = sqrt(gamma * wl_ipr / wl_idn);
+    qb = sqrt(gamma * wr_ipr / wr_idn);
+    double a = hroe - 0.5 * (SQR(wroe_ivx) + SQR(wroe_ivy) + SQR(wroe_ivz));
+    a = (a < 0.0) ? 0.0 : sqrt(gm1 * a);
+    double sla = wroe_ivx - a;
+    double slb = wl_ivx - qa;
+    double sra = wroe_ivx + a;
+    double srb = wr_ivx + qb;
+    sl = dmin(sla, slb);
+    sr = dmax(sra, srb);
+  } else {
+    sl = dmin(wroe_ivx, wl_ivx);
+    sr = dmax(wroe_ivx, wr_ivx);
+  }
+  double bp = (sr > 0.0) ? sr : 1.0e-20;
+  double bm = (sl < 0.0) ? sl : -1.0e-20;
+  qa = wl_ivx - bm;
+  qb = wr_ivx - bp;
+  double fl_d = wl_idn * qa, fr_d = wr_idn * qb;
+  double fl_mx = wl_idn * wl_ivx * qa, fr_mx = wr_idn * wr_ivx * qb;
+  double fl_my = wl_idn * wl_ivy * qa, fr_my = wr_idn * wr_ivy * qb;
+  double fl_mz = wl_idn * wl_ivz * qa, fr_mz = wr_idn * wr_ivz * qb;
+  double fl_e = 0, fr_e = 0;
+  if (gas) {
+    fl_e = el * qa + wl_ipr * wl_ivx;
+    fr_e = er * qb + wr_ipr * wr_ivx;
+  }
+  qa = 0.0;
+  if (bp != bm) qa = 0.5 * (bp + bm) / (bp - bm);
+  if (gas) out[6] = 0.5 * (wl_ipr + wr_ipr) + qa * (wl_ipr - wr_ipr);
+  const double frho = 0.5 * (fl_d + fr_d) + qa * (fl_d - fr_d);
+  out[0] = frho;
+  out[1] = 0.5 * (fl_mx + fr_mx) + qa * (fl_mx - fr_mx);
+  out[2] = 0.5 * (fl_my + fr_my) + qa * (fl_my - fr_my);
+  out[3] = 0.5 * (fl_mz + fr_mz) + qa * (fl_mz - fr_mz);
+  if (gas) {
+    out[4] = 0.5 * (fl_e + fr_e) + qa * (fl_e - fr_e);
+    out[5] = frho * ((frho >= 0.0) ? wl_ise : wr_ise);
+    out[7] = frho / ((frho >= 0.0) ? wl_idn : wr_idn);
+  }
+}
+
+/* llf.hpp:87-168 */
+static void solve_llf(int fluid, double gm1, const double *wl, const double *wr,
+                      double *out) {
+  const int gas = (fluid == AO_GAS);
+  const double wl_idn = wl[0], wl_ivx = wl[1], wl_ivy = wl[2], wl_ivz = wl[3];
+  const double wr_idn = wr[0], wr_ivx = wr[1], wr_ivy = wr[2], wr_ivz = wr[3];
+  double wl_ipr = 0, wr_ipr = 0, wl_ise = 0, wr_ise = 0, igm1 = 0, gamma = 0;
+  if (gas) {
+    wl_ipr = wl[4]; wl_ise = wl[5]; wr_ipr = wr[4]; wr_ise = wr[5];
+    igm1 = 1.0 / gm1;
+    gamma = gm1 + 1.0;
+  }
+  double qa = wl_idn * wl_ivx;
+  double qb = wr_idn * wr_ivx;
+  double fsum_d = qa + qb;
+  double fsum_mx = qa * wl_ivx + qb * wr_ivx;
+  double fsum_my = qa * wl_ivy + qb * wr_ivy;
+  double fsum_mz = qa * wl_ivz + qb * wr_ivz;
+  double el = 0, er = 0, fsum_e = 0;
+  if (gas) {
+    el = wl_ipr * igm1 + 0.5 * wl_idn * (SQR(wl_ivx) + SQR(wl_ivy) + SQR(wl_ivz));
+    er = wr_ipr * igm1 + 0.5 * wr_idn * (SQR(wr_ivx) + SQR(wr_ivy) + SQR(wr_ivz));
+    fsum_e = (el + wl_ipr) * wl_ivx + (er + wr_ipr) * wr_ivx;
+  }
+  double a;
+  if (gas) {
+    qa = sqrt(gamma * wl_ipr / wl_idn);
+    qb = sqrt(gamma * wr_ipr / wr_idn);
+    a = dmax((fabs(wl_ivx) + qa), (fabs(wr_ivx) + qb));
+  } else {
+    a = dmax(fabs(wl_ivx), fabs(wr_ivx));
+  }
+  double du_d = a * (wr_idn - wl_idn);
+  double du_mx = a * (wr_idn * wr_ivx - wl_idn * wl_ivx);
+  double du_my = a * (wr_idn * wr_ivy - wl_idn * wl_ivy);
+  double du_mz = a * (wr_idn * wr_ivz - wl_idn * wl_ivz);
+  double du_e = 0;
+  if (gas) du_e = a * (er - el);
+  if (gas) out[6] = 0.5 * (wl_ipr + wr_ipr);
+  const double frho = 0.5 * (fsum_d - du_d);
+  out[0] = frho;
+  out[1] = 0.5 * (fsum_mx - du_mx);
+  out[2] = 0.5 * (fsum_my - du_my);
+  out[3] = 0.5 * (fsum_mz - du_mz);
+  if (gas) {
+    out[4] = 0.5 * (fsum_e - du_e);
+    out[5] = frho * ((frho >= 0.0) ? wl_ise : wr_ise);
+    out[7] = frho / ((frho >= 0.0) ? wl_idn : wr_idn);
+  }
+}
+
+void ao_riemann(int solver, int fluid, double gm1, const double *wl, const double *wr,
+                double *out) {
+  if (solver == AO_HLLC)
+    solve_hllc(gm1, wl, wr, out);
+  else if (solver == AO_HLLE)
+    solve_hlle(fluid, gm1, wl, wr, out);
+  else
+    solve_llf(fluid, gm1, wl, wr, out);
+}
+
+/* RiemannSolver::solve over one row of faces + ScaleMomentumFlux (fluid_fluxes.hpp:32-70) */
+static void riemann_row(const ao_grid *g, const ao_fluid *f, int dir, int b, int k, int j,
+                        int il, int iu, const double *wl, const double *wr, double *flux,
+                        double *pflux, double *vface) {
+  const int S = f->nspecies;
+  const int gas = (f->fluid == AO_GAS);
+  const int nvar = gas ? 6 * S : 4 * S;
+  const int W = g->ni + 1;
+  const double *xmin = g->xmin + 3 * b, *dx = g->dx + 3 * b;
+  for (int n = 0; n < S; ++n) {
+    const int IDN = n;
+    const int ivx = S + (n * 3) + ((dir - 1));
+    const int ivy = S + (n * 3) + ((dir - 1) + 1) % 3;
+    const int ivz = S + (n * 3) + ((dir - 1) + 2) % 3;
+    const int IPR = S * 4 + n, ISE = S * 5 + n;
+    for (int i = il; i <= iu; ++i) {
+      double l[6], r[6], out[8];
+      l[0] = wl[(size_t)IDN * W + i]; r[0] = wr[(size_t)IDN * W + i];
+      l[1] = wl[(size_t)ivx * W + i]; r[1] = wr[(size_t)ivx * W + i];
+      l[2] = wl[(size_t)ivy * W + i]; r[2] = wr[(size_t)ivy * W + i];
+      l[3] = wl[(size_t)ivz * W + i]; r[3] = wr[(size_t)ivz * W + i];
+      if (gas) {
+        l[4] = wl[(size_t)IPR * W + i]; r[4] = wr[(size_t)IPR * W + i];
+        l[5] = wl[(size_t)ISE * W + i]; r[5] = wr[(size_t)ISE * W + i];
+      }
+      ao_riemann(f->riemann, f->fluid, f->gm1, l, r, out);
+      flux[IDX(g, nvar, b, IDN, k, j, i)] = out[0];
+      flux[IDX(g, nvar, b, ivx, k, j, i)] = out[1];
+      flux[IDX(g, nvar, b, ivy, k, j, i)] = out[2];
+      flux[IDX(g, nvar, b, ivz, k, j, i)] = out[3];
+      if (gas) {
+        flux[IDX(g, nvar, b, IPR, k, j, i)] = out[4];
+        flux[IDX(g, nvar, b, ISE, k, j, i)] = out[5];
+        pflux[IDX(g, S, b, n, k, j, i)] = out[6];
+        vface[FIDX(g, S, b, n, k, j, i)] = out[7];
+      }
+    }
+    /* ScaleMomentumFlux: fluid_fluxes.hpp:49-68 */
+    if (g->geom != AO_CARTESIAN) {
+      const int IVX = S + 3 * n, IVY = IVX + 1, IVZ = IVX + 2;
+      for (int i = il; i <= iu; ++i) {
+        bbox_t bb = make_bbox(xmin, dx, k, j, i);
+        double xf[3];
+        if (dir == 1) g_facecen1(g->geom, &bb, 0, xf);
+        else if (dir == 2) g_facecen2(g->geom, &bb, 0, xf);
+        else g_facecen3(g->geom, &bb, 0, xf);
+        flux[IDX(g, nvar, b, IVX, k, j, i)] *= g_hx1(g->geom, xf[0], xf[1], xf[2]);
+        flux[IDX(g, nvar, b, IVY, k, j, i)] *= g_hx2(g->geom, xf[0], xf[1], xf[2]);
+        flux[IDX(g, nvar, b, IVZ, k, j, i)] *= g_hx3(g->geom, xf[0], xf[1], xf[2]);
+      }
+    }
+  }
+}
+
+/* CalculateFluxesImpl: src/utils/fluxes/fluid_fluxes.hpp:76-213 */
+void ao_calculate_fluxes(const ao_grid *g, const ao_fluid *f, int pcm, const double *prim,
+                         double *flux1, double *flux2, double *flux3, double *pflux1,
+                         double *pflux2, double *pflux3, double *vface1, double *vface2,
+                         double *vface3) {
+  const int S = f->nspecies;
+  const int nvar = (f->fluid == AO_GAS) ? 6 * S : 4 * S;
+  const int recon = pcm ? AO_PCM : f->recon; /* fluid_fluxes.hpp:225 */
+  const int W = g->ni + 1;
+  const size_t row = (size_t)nvar * W;
+  const int nkr = g->ke - g->ks + 1, njr = g->je - g->js + 1;
+
+  /* X1: fluid_fluxes.hpp:105-126 */
+#pragma omp parallel
+  {
+    double *scr = (double *)malloc(sizeof(double) * row * 3);
+    double *s1 = scr, *s2 = scr + row, *s3 = scr + 2 * row;
+#pragma omp for collapse(2) schedule(static)
+    for (int b = 0; b < g->nb; ++b)
+      for (int kj = 0; kj < nkr * njr; ++kj) {
+        const int k = g->ks + kj / njr, j = g->js + kj % njr;
+        recon_row(g, recon, 1, nvar, prim, b, k, j, g->is - 1, g->ie + 1, s1, s2);
+        riemann_row(g, f, 1, b, k, j, g->is, g->ie + 1, s1, s2, flux1, pflux1, vface1);
+      }
+    /* X2: fluid_fluxes.hpp:129-168 */
+    if (g->ndim > 1) {
+#pragma omp for collapse(2) schedule(static)
+      for (int b = 0; b < g->nb; ++b)
+        for (int k = g->ks; k <= g->ke; ++k) {
+          const int jl = g->js - 1, ju = g->je + 1;
+          for (int j = jl; j <= ju; ++j) {
+            double *wl = s1, *wl_jp1 = s2, *wr = s3;
+            if ((j % 2) == 0) { wl = s2; wl_jp1 = s1; }
+            recon_row(g, recon, 2, nvar, prim, b, k, j, g->is, g->ie, wl_jp1, wr);
+            if (j > jl)
+              riemann_row(g, f, 2, b, k, j, g->is, g->ie, wl, wr, flux2, pflux2, vface2);
+          }
+        }
+    }
+    /* X3: fluid_fluxes.hpp:171-210 */
+    if (g->ndim > 2) {
+#pragma omp for collapse(2) schedule(static)
+      for (int b = 0; b < g->nb; ++b)
+        for (int j = g->js; j <= g->je; ++j) {
+          const int kl = g->ks - 1, ku = g->ke + 1;
+          for (int k = kl; k <= ku; ++k) {
+            double *wl = s1, *wl_kp1 = s2, *wr = s3;
+            if ((k % 2) == 0) { wl = s2; wl_kp1 = s1; }
+            recon_row(g, recon, 3, nvar, prim, b, k, j, g->is, g->ie, wl_kp1, wr);
+            if (k > kl)
+              riemann_row(g, f, 3, b, k, j, g->is, g->ie, wl, wr, flux3, pflux3, vface3);
+          }
+        }
+    }
+    free(scr);
+  }
+}
+
+/* ===================================================================================== */
+/* ApplyUpdate: src/utils/integrators/artemis_integrator.hpp:56-110                        */
+/* ===================================================================================== */
+void ao_apply_update(const ao_grid *g, int nvar, double *u0, const double *u1,
+                     const double *flux1, const double *flux2, const double *flux3,
+                     double gam0, double gam1, double beta_dt) {
+  const int multi_d = g->ndim > 1, three_d = g->ndim > 2;
+  const size_t sj = (size_t)g->ni, sk = (size_t)g->ni * g->nj;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < g->nb; ++b)
+    for (int k = g->ks; k <= g->ke; ++k)
+      for (int j = g->js; j <= g->je; ++j)
+        for (int i = g->is; i <= g->ie; ++i) {
+          bbox_t bb = make_bbox(g->xmin + 3 * b, g->dx + 3 * b, k, j, i);
+          const double ax1[2] = {g_area1(g->geom, &bb, bb.x1[0]),
+                                 g_area1(g->geom, &bb, bb.x1[1])};
+          double ax2[2] = {0.0, 0.0}, ax3[2] = {0.0, 0.0};
+          if (multi_d) {
+            ax2[0] = g_area2(g->geom, &bb, bb.x2[0]);
+            ax2[1] = g_area2(g->geom, &bb, bb.x2[1]);
+          }
+          if (three_d) {
+            ax3[0] = g_area3(g->geom, &bb, bb.x3[0]);
+            ax3[1] = g_area3(g->geom, &bb, bb.x3[1]);
+          }
+          const double vol = g_volume(g->geom, &bb);
+          for (int n = 0; n < nvar; ++n) {
+            const size_t c = IDX(g, nvar, b, n, k, j, i);
+            double divf = (ax1[0] * flux1[c] - ax1[1] * flux1[c + 1]);
+            if (multi_d) divf += (ax2[0] * flux2[c] - ax2[1] * flux2[c + sj]);
+            if (three_d) divf += (ax3[0] * flux3[c] - ax3[1] * flux3[c + sk]);
+            u0[c] = gam0 * u0[c] + gam1 * u1[c] + divf * beta_dt / vol;
+          }
+        }
+}
+
+/* DeepCopyConservedData: artemis_integrator.hpp:30-51 */
+void ao_deep_copy(const ao_grid *g, int nvar, double *to, const double *from) {
+  memcpy(to, from, sizeof(double) * (size_t)g->nb * nvar * g->nk * g->nj * g->ni);
+}
+
+/* ===================================================================================== */
+/* FluxSourceImpl: src/utils/fluxes/fluid_fluxes.hpp:298-420                               */
+/* NB the reference loops i over [is-2, ie+1]; rows outside the interior only touch ghost   */
+/* conserved values that PrimToCons overwrites.  We restate the interior part and apply     */
+/* the same update to ghost columns only where every operand exists (i >= 0, i+1 < ni).    */
+/* ===================================================================================== */
+void ao_flux_source(const ao_grid *g, const ao_fluid *f, const double *prim, double *cons,
+                    const double *pflux1, const double *pflux2, const double *pflux3,
+                    const double *vface1, const double *vface2, const double *vface3,
+                    double omf, double dt) {
+  const int S = f->nspecies;
+  const int gas = (f->fluid == AO_GAS);
+  const int nvar = gas ? 6 * S : 4 * S;
+  const int multi_d = g->ndim >= 2, three_d = g->ndim == 3;
+  const int x1dep = g_x1dep(g->geom);
+  const int x2dep = g_x2dep(g->geom) && multi_d;
+  const size_t sj = (size_t)g->ni, sk = (size_t)g->ni * g->nj;
+  const size_t fsj = (size_t)g->fni, fsk = (size_t)g->fni * g->fnj;
+  /* Dust::FluxSource early-out: src/dust/dust.cpp:311-312 */
+  if (!gas && !(x1dep || x2dep)) return;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < g->nb; ++b)
+    for (int k = g->ks; k <= g->ke; ++k)
+      for (int j = g->js; j <= g->je; ++j)
+        for (int i = g->is; i <= g->ie; ++i) {
+          bbox_t bb = make_bbox(g->xmin + 3 * b, g->dx + 3 * b, k, j, i);
+          double dhdx1[3] = {0, 0, 0}, dhdx2[3] = {0, 0, 0};
+          if (x1dep) g_conn1(g->geom, &bb, dhdx1);
+          if (x2dep) g_conn2(g->geom, &bb, dhdx2);
+          const double ax1[2] = {g_area1(g->geom, &bb, bb.x1[0]),
+                                 g_area1(g->geom, &bb, bb.x1[1])};
+          double ax2[2] = {0.0, 0.0}, ax3[2] = {0.0, 0.0};
+          if (multi_d) {
+            ax2[0] = g_area2(g->geom, &bb, bb.x2[0]);
+            ax2[1] = g_area2(g->geom, &bb, bb.x2[1]);
+          }
+          if (three_d) {
+            ax3[0] = g_area3(g->geom, &bb, bb.x3[0]);
+            ax3[1] = g_area3(g->geom, &bb, bb.x3[1]);
+          }
+          const double vol = g_volume(g->geom, &bb);
+          const double dx[3] = {bb.x1[1] - bb.x1[0], bb.x2[1] - bb.x2[0],
+                                bb.x3[1] - bb.x3[0]};
+          const double xv[3] = {g_x1v(g->geom, &bb), g_x2v(g->geom, &bb),
+                                g_x3v(g->geom, &bb)};
+          double vf[3];
+          g_rotation_velocity(g->geom, xv, omf, vf);
+          for (int n = 0; n < S; ++n) {
+            const size_t cmx = IDX(g, nvar, b, S + 3 * n + 0, k, j, i);
+            const size_t cmy = IDX(g, nvar, b, S + 3 * n + 1, k, j, i);
+            const size_t cmz = IDX(g, nvar, b, S + 3 * n + 2, k, j, i);
+            if (gas) {
+              const size_t ceg = IDX(g, nvar, b, 5 * S + n, k, j, i);
+              const size_t p = IDX(g, S, b, n, k, j, i);
+              const size_t v = FIDX(g, S, b, n, k, j, i);
+              cons[cmx] += dt / dx[0] * (pflux1[p] - pflux1[p + 1]);
+              cons[ceg] -= dt / vol * 0.5 * (pflux1[p] + pflux1[p + 1]) *
+                           (ax1[1] * vface1[v + 1] - ax1[0] * vface1[v]);
+              if (multi_d) {
+                cons[cmy] += dt / dx[1] * (pflux2[p] - pflux2[p + sj]);
+                cons[ceg] -= dt / vol * 0.5 * (pflux2[p] + pflux2[p + sj]) *
+                             (ax2[1] * vface2[v + fsj] - ax2[0] * vface2[v]);
+              }
+              if (three_d) {
+                cons[cmz] += dt / dx[2] * (pflux3[p] - pflux3[p + sk]);
+                cons[ceg] -= dt / vol * 0.5 * (pflux3[p] + pflux3[p + sk]) *
+                             (ax3[1] * vface3[v + fsk] - ax3[0] * vface3[v]);
+              }
+            }
+            const double dens = prim[IDX(g, nvar, b, n, k, j, i)];
+            const double rdt = dens * dt;
+            const double vx = prim[IDX(g, nvar, b, S + 3 * n + 0, k, j, i)];
+            const double vy = prim[IDX(g, nvar, b, S + 3 * n + 1, k, j, i)];
+            const double vz = prim[IDX(g, nvar, b, S + 3 * n + 2, k, j, i)];
+            if (x1dep)
+              cons[cmx] += rdt * (dhdx1[0] * SQR(vx + vf[0]) + dhdx1[1] * SQR(vy + vf[1]) +
+                                  dhdx1[2] * SQR(vz + vf[2]));
+            if (x2dep)
+              cons[cmy] += rdt * (dhdx2[0] * SQR(vx + vf[0]) + dhdx2[1] * SQR(vy + vf[1]) +
+                                  dhdx2[2] * SQR(vz + vf[2]));
+          }
+        }
+}
+
+/* ===================================================================================== */
+/* src/derived/fill_derived.cpp + src/utils/artemis_utils.hpp:42-78                        */
+/* ===================================================================================== */
+/* SetAuxillaryFields: fill_derived.cpp:29-75 */
+void ao_set_aux(const ao_grid *g, const ao_fluid *f, double *cons) {
+  if (f->fluid != AO_GAS) return;
+  const int S = f->nspecies, nvar = 6 * S;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < g->nb; ++b)
+    for (int k = g->ks; k <= g->ke; ++k)
+      for (int j = g->js; j <= g->je; ++j)
+        for (int i = g->is; i <= g->ie; ++i) {
+          bbox_t bb = make_bbox(g->xmin + 3 * b, g->dx + 3 * b, k, j, i);
+          const double hx[3] = {g_hx1v(g->geom, &bb), g_hx2v(g->geom, &bb),
+                                g_hx3v(g->geom, &bb)};
+          for (int n = 0; n < S; ++n) {
+            double u_d = cons[IDX(g, nvar, b, n, k, j, i)];
+            u_d = (u_d > f->dfloor) ? u_d : f->dfloor;
+            /* GetSpecificInternalEnergy: artemis_utils.hpp:50-66 */
+            const double ud2 = dmax(cons[IDX(g, nvar, b, n, k, j, i)], f->dfloor);
+            const double rv1 = cons[IDX(g, nvar, b, S + 3 * n + 0, k, j, i)] / hx[0];
+            const double rv2 = cons[IDX(g, nvar, b, S + 3 * n + 1, k, j, i)] / hx[1];
+            const double rv3 = cons[IDX(g, nvar, b, S + 3 * n + 2, k, j, i)] / hx[2];
+            const double ke = 0.5 * (SQR(rv1) + SQR(rv2) + SQR(rv3)) / ud2;
+            const double e_cons = cons[IDX(g, nvar, b, 4 * S + n, k, j, i)];
+            const double ue_cons = e_cons - ke;
+            double *u_u = &cons[IDX(g, nvar, b, 5 * S + n, k, j, i)];
+            double sie = (ue_cons > f->de_switch * e_cons) ? ue_cons / ud2 : *u_u / ud2;
+            sie = dmax(sie, f->siefloor);
+            *u_u = sie * u_d;
+            const double uflr = f->siefloor * u_d;
+            *u_u = (*u_u > uflr) ? *u_u : uflr;
+          }
+        }
+}
+
+/* ConsToPrim: fill_derived.cpp:81-167 (interior) */
+void ao_cons_to_prim(const ao_grid *g, const ao_fluid *f, const double *cons, double *prim) {
+  const int S = f->nspecies;
+  const int gas = (f->fluid == AO_GAS);
+  const int nvar = gas ? 6 * S : 4 * S;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < g->nb; ++b)
+    for (int k = g->ks; k <= g->ke; ++k)
+      for (int j = g->js; j <= g->je; ++j)
+        for (int i = g->is; i <= g->ie; ++i) {
+          bbox_t bb = make_bbox(g->xmin + 3 * b, g->dx + 3 * b, k, j, i);
+          const double hx[3] = {g_hx1v(g->geom, &bb), g_hx2v(g->geom, &bb),
+                                g_hx3v(g->geom, &bb)};
+          for (int n = 0; n < S; ++n) {
+            const double u_d = cons[IDX(g, nvar, b, n, k, j, i)];
+            const double w_d = (u_d > f->dfloor) ? u_d : f->dfloor;
+            prim[IDX(g, nvar, b, n, k, j, i)] = w_d;
+            for (int d = 0; d < 3; ++d)
+              prim[IDX(g, nvar, b, S + 3 * n + d, k, j, i)] =
+                  cons[IDX(g, nvar, b, S + 3 * n + d, k, j, i)] / (w_d * hx[d]);
+            if (gas) {
+              const double w_s = cons[IDX(g, nvar, b, 5 * S + n, k, j, i)] / w_d;
+              prim[IDX(g, nvar, b, 5 * S + n, k, j, i)] =
+                  (w_s > f->siefloor) ? w_s : f->siefloor;
+            }
+          }
+        }
+}
+
+/* PrimToCons: fill_derived.cpp:172-277 (entire domain, ghosts included) */
+void ao_prim_to_cons(const ao_grid *g, const ao_fluid *f, double *prim, double *cons) {
+  const int S = f->nspecies;
+  const int gas = (f->fluid == AO_GAS);
+  const int nvar = gas ? 6 * S : 4 * S;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < g->nb; ++b)
+    for (int k = 0; k < g->nk; ++k)
+      for (int j = 0; j < g->nj; ++j)
+        for (int i = 0; i < g->ni; ++i) {
+          bbox_t bb = make_bbox(g->xmin + 3 * b, g->dx + 3 * b, k, j, i);
+          const double hx[3] = {g_hx1v(g->geom, &bb), g_hx2v(g->geom, &bb),
+                                g_hx3v(g->geom, &bb)};
+          for (int n = 0; n < S; ++n) {
+            double *w_d = &prim[IDX(g, nvar, b, n, k, j, i)];
+            *w_d = (*w_d > f->dfloor) ? *w_d : f->dfloor;
+            const double u_d = *w_d;
+            cons[IDX(g, nvar, b, n, k, j, i)] = u_d;
+            const double vel1 = prim[IDX(g, nvar, b, S + 3 * n + 0, k, j, i)];
+            const double vel2 = prim[IDX(g, nvar, b, S + 3 * n + 1, k, j, i)];
+            const double vel3 = prim[IDX(g, nvar, b, S + 3 * n + 2, k, j, i)];
+            cons[IDX(g, nvar, b, S + 3 * n + 0, k, j, i)] = *w_d * vel1 * hx[0];
+            cons[IDX(g, nvar, b, S + 3 * n + 1, k, j, i)] = *w_d * vel2 * hx[1];
+            cons[IDX(g, nvar, b, S + 3 * n + 2, k, j, i)] = *w_d * vel3 * hx[2];
+            if (gas) {
+              double *w_s = &prim[IDX(g, nvar, b, 5 * S + n, k, j, i)];
+              *w_s = (*w_s > f->siefloor) ? *w_s : f->siefloor;
+              const double u_u = *w_s * u_d;
+              cons[IDX(g, nvar, b, 5 * S + n, k, j, i)] = u_u;
+              /* singularity-eos 1.9.1 eos_ideal.hpp:91-95: MYMAX(0.0, gm1*rho*sie) */
+              prim[IDX(g, nvar, b, 4 * S + n, k, j, i)] = dmax(0.0, f->gm1 * *w_d * *w_s);
+              const double ke = 0.5 * *w_d * (SQR(vel1) + SQR(vel2) + SQR(vel3));
+              cons[IDX(g, nvar, b, 4 * S + n, k, j, i)] = u_u + ke;
+            }
+          }
+        }
+}
+
+/* Gas/Dust::EstimateTimestepMesh: src/gas/gas.cpp:391-468, src/dust/dust.cpp:238-276.
+ * Returns cfl * min_dt (diffusion limits out of scope). */
+double ao_estimate_dt(const ao_grid *g, const ao_fluid *f, const double *prim) {
+  const int S = f->nspecies;
+  const int gas = (f->fluid == AO_GAS);
+  const int nvar = gas ? 6 * S : 4 * S;
+  double min_dt = 1.79769313486231570815e+308; /* Big<Real>() */
+#pragma omp parallel for collapse(2) schedule(static) reduction(min : min_dt)
+  for (int b = 0; b < g->nb; ++b)
+    for (int k = g->ks; k <= g->ke; ++k)
+      for (int j = g->js; j <= g->je; ++j)
+        for (int i = g->is; i <= g->ie; ++i) {
+          bbox_t bb = make_bbox(g->xmin + 3 * b, g->dx + 3 * b, k, j, i);
+          double dx[3];
+          g_cell_widths(g->geom, &bb, dx);
+          for (int n = 0; n < S; ++n) {
+            double cs = 0.0;
+            if (gas) {
+              const double dens = prim[IDX(g, nvar, b, n, k, j, i)];
+              const double sie = prim[IDX(g, nvar, b, 5 * S + n, k, j, i)];
+              /* eos_ideal.hpp:136-140 */
+              const double bulk = dmax(0.0, (f->gm1 + 1) * f->gm1 * dens * sie);
+              cs = sqrt(bulk / dens);
+            }
+            double denom = 0.0;
+            for (int d = 0; d < g->ndim; d++) {
+              const double av = fabs(prim[IDX(g, nvar, b, S + 3 * n + d, k, j, i)]);
+              if (gas) {
+                const double ss = av + cs;
+                denom += ss / dx[d];
+              } else {
+                denom += av / dx[d];
+              }
+            }
+            min_dt = dmin(min_dt, 1.0 / denom);
+          }
+        }
+  return f->cfl * min_dt;
+}
+
+/* ===================================================================================== */
+/* Ghost exchange (same level) + physical BCs.                                             */
+/* Index ranges: P:bvals/comms/bnd_info.cpp:152-213 (same-level branch); pack/unpack        */
+/* P:bvals/comms/boundary_communication.cpp:95-140, 273-334; outflow/reflect                */
+/* P:bvals/boundary_conditions_generic.hpp:178-256 in face order ix1,ox1,ix2,ox2,ix3,ox3.   */
+/* ===================================================================================== */
+static void range_send(int off, int s, int e, int ng, int *lo, int *hi) {
+  if (off == 0) { *lo = s; *hi = e; }
+  else if (off > 0) { *lo = e - ng + 1; *hi = e; }
+  else { *lo = s; *hi = s + ng - 1; }
+}
+static void range_recv(int off, int s, int e, int ng, int *lo, int *hi) {
+  if (off == 0) { *lo = s; *hi = e; }
+  else if (off > 0) { *lo = e + 1; *hi = e + ng; }
+  else { *lo = s - ng; *hi = s - 1; }
+}
+
+void ao_exchange_ghosts(const ao_grid *g, int nbx, int nby, int nbz, const int *bc,
+                        int nvar, double *a, int nv, const int *vars, const int *vec_dir) {
+  const int ng = g->ng;
+  const int nbd[3] = {nbx, nby, nbz};
+  const int ox3 = g->ndim > 2 ? 1 : 0, ox2 = g->ndim > 1 ? 1 : 0;
+  /* 1. neighbour -> ghost copies (receiver-driven; all sources are interior cells) */
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < g->nb; ++b) {
+    const int lb[3] = {b % nbx, (b / nbx) % nby, b / (nbx * nby)};
+    for (int o3 = -ox3; o3 <= ox3; ++o3)
+      for (int o2 = -ox2; o2 <= ox2; ++o2)
+        for (int o1 = -1; o1 <= 1; ++o1) {
+          if (!o1 && !o2 && !o3) continue;
+          const int off[3] = {o1, o2, o3};
+          int ln[3], ok = 1;
+          for (int d = 0; d < 3; ++d) {
+            ln[d] = lb[d] + off[d];
+            if (ln[d] < 0 || ln[d] >= nbd[d]) {
+              if (bc[2 * d + (off[d] > 0)] == AO_BC_PERIODIC)
+                ln[d] = (ln[d] + nbd[d]) % nbd[d];
+              else
+                ok = 0;
+            }
+          }
+          if (!ok) continue;
+          const int nbr = ln[0] + nbx * (ln[1] + nby * ln[2]);
+          int rl[3], rh[3], sl[3], sh[3];
+          range_recv(o1, g->is, g->ie, ng, &rl[0], &rh[0]);
+          range_recv(o2, g->js, g->je, ng, &rl[1], &rh[1]);
+          range_recv(o3, g->ks, g->ke, ng, &rl[2], &rh[2]);
+          /* the sender sees this block at offset -off */
+          range_send(-o1, g->is, g->ie, ng, &sl[0], &sh[0]);
+          range_send(-o2, g->js, g->je, ng, &sl[1], &sh[1]);
+          range_send(-o3, g->ks, g->ke, ng, &sl[2], &sh[2]);
+          (void)sh;
+          for (int v = 0; v < nv; ++v)
+            for (int k = rl[2]; k <= rh[2]; ++k)
+              for (int j = rl[1]; j <= rh[1]; ++j)
+                for (int i = rl[0]; i <= rh[0]; ++i)
+                  a[IDX(g, nvar, b, vars[v], k, j, i)] =
+                      a[IDX(g, nvar, nbr, vars[v], sl[2] + (k - rl[2]), sl[1] + (j - rl[1]),
+                            sl[0] + (i - rl[0]))];
+        }
+  }
+  /* 2. physical boundaries */
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < g->nb; ++b) {
+    const int lb[3] = {b % nbx, (b / nbx) % nby, b / (nbx * nby)};
+    const int s[3] = {g->is, g->js, g->ks}, e[3] = {g->ie, g->je, g->ke};
+    const int nt[3] = {g->ni, g->nj, g->nk};
+    for (int face = 0; face < 2 * g->ndim; ++face) {
+      const int d = face / 2, outer = face % 2;
+      if (bc[face] == AO_BC_PERIODIC) continue;
+      if (outer ? (lb[d] != nbd[d] - 1) : (lb[d] != 0)) continue;
+      const int ref = outer ? e[d] : s[d];
+      const int offset = 2 * ref + (outer ? 1 : -1);
+      int lo[3] = {0, 0, 0}, hi[3] = {nt[0] - 1, nt[1] - 1, nt[2] - 1};
+      if (outer) { lo[d] = e[d] + 1; hi[d] = nt[d] - 1; }
+      else { lo[d] = 0; hi[d] = s[d] - 1; }
+      for (int v = 0; v < nv; ++v) {
+        const double sgn = (bc[face] == AO_BC_REFLECT && vec_dir[v] == d + 1) ? -1.0 : 1.0;
+        for (int k = lo[2]; k <= hi[2]; ++k)
+          for (int j = lo[1]; j <= hi[1]; ++j)
+            for (int i = lo[0]; i <= hi[0]; ++i) {
+              int c[3] = {i, j, k};
+              c[d] = (bc[face] == AO_BC_REFLECT) ? offset - c[d] : ref;
+              a[IDX(g, nvar, b, vars[v], k, j, i)] =
+                  sgn * a[IDX(g, nvar, b, vars[v], c[2], c[1], c[0])];
+            }
+      }
+    }
+  }
+}

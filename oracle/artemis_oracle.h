@@ -1,0 +1,105 @@
+/*
+ * artemis_oracle.h -- CPU restatement of the Artemis finite-volume hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load it, and only as the checker / reported CPU baseline.
+ *
+ * Every function cites the reference file:line (relative to lanl/artemis @ 6c2a7a8)
+ * whose arithmetic it restates, operation for operation, so that the result is
+ * bit-identical to the reference's Kokkos-OpenMP build when compiled without FMA
+ * contraction (gcc -O2 -ffp-contract=off; the reference build uses no -march).
+ *
+ * Pinning: see oracle/README.md -- (1) linear-wave RMS-L1 golden numbers measured from
+ * the real reference, (2) the reference's own regression thresholds
+ * (tst/scripts/hydro/linwave.py), (3) oracle/_ref: the reference's own headers
+ * compiled against a mock Parthenon, compared function by function.
+ *
+ * Data model ("MeshBlockPack layout"): every variable is a dense
+ * array [nb][nvar][nk][nj][ni], i fastest, ghosts included.  Pack index conventions
+ * follow src/utils/fluxes/riemann/hllc.hpp:66-73 (S = nspecies):
+ *   gas  prim: rho n | vel S+3n+d | pressure 4S+n | sie 5S+n          (6S vars)
+ *   gas  cons: rho n | mom S+3n+d | total_energy 4S+n | internal 5S+n (6S vars)
+ *   dust prim: rho n | vel S+3n+d                                     (4S vars)
+ *   dust cons: rho n | mom S+3n+d                                     (4S vars)
+ * Fluxes: flux[d] has the cons layout; flux at index i is the LOWER face of cell i.
+ * pflux[d]: [nb][S][nk][nj][ni] interface pressure (the prim-pressure flux slot).
+ * vface[d]: [nb][S][fnk][fnj][fni] face velocity (gas.face.velocity, el = d).
+ */
+#ifndef ARTEMIS_ORACLE_H_
+#define ARTEMIS_ORACLE_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* src/artemis.hpp:78-105 enum order */
+enum { AO_CARTESIAN = 0, AO_CYLINDRICAL = 1, AO_SPHERICAL1D = 2, AO_SPHERICAL2D = 3,
+       AO_SPHERICAL3D = 4, AO_AXISYMMETRIC = 5 };
+enum { AO_HLLC = 0, AO_HLLE = 1, AO_LLF = 2 };
+enum { AO_PCM = 0, AO_PLM = 1, AO_PPM = 2 };
+enum { AO_GAS = 0, AO_DUST = 1 };
+enum { AO_BC_PERIODIC = 0, AO_BC_OUTFLOW = 1, AO_BC_REFLECT = 2 };
+
+typedef struct {
+  int geom, ndim, ng, nb;
+  int ni, nj, nk;             /* allocated cells per block (ghosts included)      */
+  int is, ie, js, je, ks, ke; /* interior bounds (inclusive)                      */
+  int fni, fnj, fnk;          /* allocated dims of the face-velocity field        */
+  const double *xmin;         /* [nb][3] UniformCartesian::xmin_ (ghost-shifted)  */
+  const double *dx;           /* [nb][3]                                          */
+} ao_grid;
+
+typedef struct {
+  int fluid;    /* AO_GAS / AO_DUST */
+  int nspecies;
+  int recon, riemann;
+  double gm1;   /* gamma - 1 (gas)  */
+  double dfloor, siefloor, de_switch, cfl;
+} ao_fluid;
+
+void ao_calculate_fluxes(const ao_grid *g, const ao_fluid *f, int pcm, const double *prim,
+                         double *flux1, double *flux2, double *flux3, double *pflux1,
+                         double *pflux2, double *pflux3, double *vface1, double *vface2,
+                         double *vface3);
+void ao_apply_update(const ao_grid *g, int nvar, double *u0, const double *u1,
+                     const double *flux1, const double *flux2, const double *flux3,
+                     double gam0, double gam1, double beta_dt);
+void ao_flux_source(const ao_grid *g, const ao_fluid *f, const double *prim, double *cons,
+                    const double *pflux1, const double *pflux2, const double *pflux3,
+                    const double *vface1, const double *vface2, const double *vface3,
+                    double omf, double dt);
+void ao_set_aux(const ao_grid *g, const ao_fluid *f, double *cons);
+void ao_cons_to_prim(const ao_grid *g, const ao_fluid *f, const double *cons, double *prim);
+void ao_prim_to_cons(const ao_grid *g, const ao_fluid *f, double *prim, double *cons);
+double ao_estimate_dt(const ao_grid *g, const ao_fluid *f, const double *prim);
+void ao_deep_copy(const ao_grid *g, int nvar, double *to, const double *from);
+
+/* Same-level ghost exchange on a uniform nbx x nby x nbz block lattice + physical BCs.
+ * vars: list of nv pack indices into `a` ([nb][nvar][nk][nj][ni]) to communicate;
+ * vec_dir[v] = 1,2,3 if var v is that component of a vector (sign flip under reflect),
+ * else 0.  bc[6] = {ix1, ox1, ix2, ox2, ix3, ox3}. */
+void ao_exchange_ghosts(const ao_grid *g, int nbx, int nby, int nbz, const int *bc,
+                        int nvar, double *a, int nv, const int *vars, const int *vec_dir);
+
+/* Geometry probes (used by tests to compare against oracle/_ref and the CUDA tables) */
+void ao_geom_cell(int geom, const double *xmin, const double *dx, int k, int j, int i,
+                  double *out /* [32] */);
+
+/* Single-function probes */
+void ao_plm(double qm, double q, double qp, double *ql_ip1, double *qr_i);
+void ao_plm_g(double qm, double q, double qp, double xm, double xc, double xp,
+              double xf0, double xf1, double dx, double *ql_ip1, double *qr_i);
+void ao_ppm4(double qm2, double qm1, double q, double qp1, double qp2, double *ql_ip1,
+             double *qr_i);
+/* wl/wr: [6] (gas: rho,vx,vy,vz,P,sie) or [4] (dust); out: gas [8] = Frho,Fmx,Fmy,Fmz,
+ * FE, Fu, pface, vface ; dust [4] */
+void ao_riemann(int solver, int fluid, double gm1, const double *wl, const double *wr,
+                double *out);
+
+int ao_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,225 @@
+"""ctypes wrapper + stage driver for the CPU oracle.
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (artemis_b200/) never imports it.
+
+OracleSim restates, independently of the product's host mirror, the per-stage task order of
+ArtemisDriver<GEOM>::StepTasks (src/artemis_driver.cpp:145-270) and Parthenon's
+EvolutionDriver dt logic (P:driver/driver.cpp:210-269) on numpy arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "libartemis_oracle.so")
+_DP = C.POINTER(C.c_double)
+_IP = C.POINTER(C.c_int)
+
+
+class _Grid(C.Structure):
+    _fields_ = [(n, C.c_int) for n in
+                ("geom", "ndim", "ng", "nb", "ni", "nj", "nk", "is_", "ie", "js", "je", "ks",
+                 "ke", "fni", "fnj", "fnk")] + [("xmin", _DP), ("dx", _DP)]
+
+
+class _Fluid(C.Structure):
+    _fields_ = [("fluid", C.c_int), ("nspecies", C.c_int), ("recon", C.c_int),
+                ("riemann", C.c_int), ("gm1", C.c_double), ("dfloor", C.c_double),
+                ("siefloor", C.c_double), ("de_switch", C.c_double), ("cfl", C.c_double)]
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("artemis_oracle.c", "artemis_oracle.h")]
+    if (not force and os.path.exists(_LIB)
+            and all(os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in src)):
+        return _LIB
+    subprocess.check_call(["make", "-C", _HERE, "CC=gcc"], stdout=subprocess.DEVNULL)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            build()
+        _lib = C.CDLL(_LIB)
+        _lib.ao_estimate_dt.restype = C.c_double
+        _lib.ao_num_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(_DP)
+
+
+def make_grid(mesh):
+    g = _Grid(int(mesh.coords), mesh.ndim, mesh.nghost, mesh.nb, mesh.ni, mesh.nj, mesh.nk,
+              mesh.is_, mesh.ie, mesh.js, mesh.je, mesh.ks, mesh.ke, mesh.fni, mesh.fnj,
+              mesh.fnk, _p(mesh.blk_xmin), _p(mesh.blk_dx))
+    g._keep = (mesh.blk_xmin, mesh.blk_dx)
+    return g
+
+
+def make_fluid(fp):
+    return _Fluid(int(fp.fluid_type), fp.nspecies, int(fp.recon), int(fp.rsolver), fp.gm1,
+                  fp.dfloor, fp.siefloor, fp.de_switch, fp.cfl)
+
+
+class FluidState:
+    """All arrays of one fluid in the MeshBlockPack layout (see artemis_oracle.h)."""
+
+    def __init__(self, mesh, fp, with_flux=True):
+        self.fp = fp
+        S = fp.nspecies
+        gas = int(fp.fluid_type) == 0
+        nv = fp.nvar
+        self.prim = np.zeros(mesh.shape(nv))
+        self.u0 = np.zeros(mesh.shape(nv))
+        self.u1 = np.zeros(mesh.shape(nv))
+        self.flux = [np.zeros(mesh.shape(nv)) for _ in range(3)] if with_flux else None
+        self.pflux = [np.zeros(mesh.shape(S)) for _ in range(3)] if gas and with_flux else [None] * 3
+        self.vface = [np.zeros(mesh.face_shape(S)) for _ in range(3)] if gas and with_flux else [None] * 3
+        # FillGhost variables: gas prim rho,v,sie (pressure is NOT exchanged:
+        # src/gas/gas.cpp:243-270); dust prim rho,v (src/dust/dust.cpp:200-212)
+        if gas:
+            self.ghost_vars = list(range(0, 4 * S)) + list(range(5 * S, 6 * S))
+        else:
+            self.ghost_vars = list(range(0, 4 * S))
+        self.vec_dir = [((v - S) % 3 + 1) if S <= v < 4 * S else 0 for v in self.ghost_vars]
+
+
+class OracleSim:
+    """Mini driver: same task order as the reference, one numpy-backed MeshData."""
+
+    def __init__(self, mesh, gas=None, dust=None, integrator="rk2", omf=0.0):
+        from artemis_b200.enums import INTEGRATORS  # plain data table, no product code path
+        self.mesh = mesh
+        self.g = make_grid(mesh)
+        self.L = lib()
+        self.fluids = []
+        self.gas = FluidState(mesh, gas) if gas is not None else None
+        self.dust = FluidState(mesh, dust) if dust is not None else None
+        self.fluids = [f for f in (self.gas, self.dust) if f is not None]
+        self.integrator = integrator
+        self.stages = INTEGRATORS[integrator]
+        self.omf = omf
+        self.time = 0.0
+        self.ncycle = 0
+        self.dt = np.finfo(np.float64).max
+        self.tlim = np.inf
+        self.nlim = -1
+
+    # ---- task functions (names follow the reference) ---------------------------------
+    def CalculateFluxes(self, fs, pcm):
+        f = make_fluid(fs.fp)
+        self.L.ao_calculate_fluxes(C.byref(self.g), C.byref(f), int(pcm), _p(fs.prim),
+                                   *[_p(a) for a in fs.flux], *[_p(a) for a in fs.pflux],
+                                   *[_p(a) for a in fs.vface])
+
+    def ApplyUpdate(self, fs, gam0, gam1, beta_dt):
+        self.L.ao_apply_update(C.byref(self.g), fs.fp.nvar, _p(fs.u0), _p(fs.u1),
+                               *[_p(a) for a in fs.flux], C.c_double(gam0), C.c_double(gam1),
+                               C.c_double(beta_dt))
+
+    def FluxSource(self, fs, dt):
+        f = make_fluid(fs.fp)
+        self.L.ao_flux_source(C.byref(self.g), C.byref(f), _p(fs.prim), _p(fs.u0),
+                              *[_p(a) for a in fs.pflux], *[_p(a) for a in fs.vface],
+                              C.c_double(self.omf), C.c_double(dt))
+
+    def SetAuxillaryFields(self, fs):
+        f = make_fluid(fs.fp)
+        self.L.ao_set_aux(C.byref(self.g), C.byref(f), _p(fs.u0))
+
+    def ConsToPrim(self, fs):
+        f = make_fluid(fs.fp)
+        self.L.ao_cons_to_prim(C.byref(self.g), C.byref(f), _p(fs.u0), _p(fs.prim))
+
+    def PrimToCons(self, fs):
+        f = make_fluid(fs.fp)
+        self.L.ao_prim_to_cons(C.byref(self.g), C.byref(f), _p(fs.prim), _p(fs.u0))
+
+    def ExchangeGhosts(self, fs):
+        m = self.mesh
+        vars_ = np.array(fs.ghost_vars, dtype=np.int32)
+        vdir = np.array(fs.vec_dir, dtype=np.int32)
+        bc = m.bc_ints()
+        self.L.ao_exchange_ghosts(C.byref(self.g), *[int(v) for v in m.lattice_n],
+                                  bc.ctypes.data_as(_IP), fs.fp.nvar, _p(fs.prim), len(vars_),
+                                  vars_.ctypes.data_as(_IP), vdir.ctypes.data_as(_IP))
+
+    def EstimateTimestep(self):
+        dts = []
+        for fs in self.fluids:
+            f = make_fluid(fs.fp)
+            dts.append(self.L.ao_estimate_dt(C.byref(self.g), C.byref(f), _p(fs.prim)))
+        return min(dts)
+
+    # ---- Mesh::Initialize sequence after the pgen (P:mesh/mesh.cpp:783-814) -----------
+    def initialize(self):
+        for fs in self.fluids:
+            self.PrimToCons(fs)      # PostInitialization
+            self.ConsToPrim(fs)      # PreCommFillDerived
+            self.ExchangeGhosts(fs)  # CommunicateBoundaries + physical BCs
+            self.PrimToCons(fs)      # FillDerived
+        self.block_dt = self.EstimateTimestep()
+        self.SetGlobalTimeStep()
+
+    def SetGlobalTimeStep(self):
+        """P:driver/driver.cpp:210-269 (dt_factor 2, no user limits)."""
+        big = np.finfo(np.float64).max
+        if self.dt < 0.1 * big:
+            self.dt *= 2.0
+        self.dt = min(self.dt, self.block_dt)
+        if self.time < self.tlim and (self.tlim - self.time) < self.dt:
+            self.dt = self.tlim - self.time
+
+    def stage(self, s):
+        gam0, gam1, beta = self.stages[s]
+        bdt = beta * self.dt
+        pcm = (s == 0 and self.integrator == "vl2")
+        for fs in self.fluids:
+            self.CalculateFluxes(fs, pcm)
+        for fs in self.fluids:
+            self.ApplyUpdate(fs, gam0, gam1, bdt)
+        for fs in self.fluids:
+            self.FluxSource(fs, bdt)
+        for fs in self.fluids:
+            self.SetAuxillaryFields(fs)
+            self.ConsToPrim(fs)
+            self.ExchangeGhosts(fs)
+            self.PrimToCons(fs)
+
+    def step(self):
+        for fs in self.fluids:           # DeepCopyConservedData (artemis_driver.cpp:156-163)
+            np.copyto(fs.u1, fs.u0)
+        for s in range(len(self.stages)):
+            self.stage(s)
+        self.block_dt = self.EstimateTimestep()
+        self.ncycle += 1
+        self.time += self.dt
+        self.SetGlobalTimeStep()
+
+    def keep_going(self):
+        return (self.time < self.tlim) and (self.nlim < 0 or self.ncycle < self.nlim)
+
+    def run(self):
+        while self.keep_going():
+            self.step()
+
+
+if __name__ == "__main__":
+    build(force=True)
+    print(_LIB, "threads:", lib().ao_num_threads(), file=sys.stderr)
