@@ -1,0 +1,89 @@
+"""Builds libartemis_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+Two variants are produced from the same sources:
+  * artemis_b200/lib/libartemis_b200.so         -- default (FMA contraction on)
+  * artemis_b200/lib/libartemis_b200_strict.so  -- --fmad=false, operation-for-operation
+    identical to the reference's CPU arithmetic (used by the bit-exactness tests)
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(HERE, "build")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
+          "--expt-relaxed-constexpr", "-I", os.path.join(HERE, "..", "include")]
+
+# (source, extra defines, object suffix)
+UNITS = [("api.cu", [], ""), ("tasks.cu", [], ""), ("halo.cu", [], ""),
+         ("fused_dispatch.cu", [], ""), ("host_path.cu", [], "")]
+UNITS += [("fused.cu", [f"-DAB_GEOM={g}"], f"_g{g}") for g in range(6)]
+UNITS += [("tasks_flux.cu", [f"-DAB_GEOM={g}"], f"_g{g}") for g in range(6)]
+
+
+def _deps():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [
+        os.path.join(HERE, "..", "include", "ab200.h")]
+
+
+def _stamp(flags):
+    h = hashlib.sha256()
+    for p in _deps():
+        with open(p, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(flags).encode())
+    return h.hexdigest()
+
+
+def _compile(args):
+    src, defs, suffix, variant, flags = args
+    obj = os.path.join(OBJDIR, variant, os.path.splitext(src)[0] + suffix + ".o")
+    os.makedirs(os.path.dirname(obj), exist_ok=True)
+    cmd = [NVCC, *ARCH, *COMMON, *flags, *defs, "-c", os.path.join(CSRC, src), "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}{suffix} [{variant}]:\n{r.stdout}\n{r.stderr}")
+    return obj, r.stderr
+
+
+def build_variant(variant: str, flags, verbose=False, jobs=None):
+    out = os.path.join(LIBDIR, f"libartemis_b200{'' if variant == 'fast' else '_' + variant}.so")
+    stamp_file = out + ".stamp"
+    stamp = _stamp(flags)
+    if os.path.exists(out) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return out
+    os.makedirs(LIBDIR, exist_ok=True)
+    units = [u for u in UNITS if os.path.exists(os.path.join(CSRC, u[0]))]
+    jobs = jobs or min(len(units), os.cpu_count() or 4)
+    with cf.ThreadPoolExecutor(jobs) as ex:
+        res = list(ex.map(_compile, [(s, d, x, variant, flags) for s, d, x in units]))
+    if verbose:
+        for _, err in res:
+            if err.strip():
+                print(err, file=sys.stderr)
+    objs = [o for o, _ in res]
+    cmd = [NVCC, *ARCH, "-shared", "-o", out, *objs, "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(stamp_file, "w") as fh:
+        fh.write(stamp)
+    return out
+
+
+def build_all(verbose=False):
+    fast = build_variant("fast", [], verbose)
+    strict = build_variant("strict", ["--fmad=false"], verbose)
+    return fast, strict
+
+
+if __name__ == "__main__":
+    print(build_all(verbose="-v" in sys.argv))

@@ -1,0 +1,115 @@
+"""ctypes binding of include/ab200.h (the C ABI of libartemis_b200).
+
+This is the only way the Python host mirror reaches the CUDA path.  There is no fallback: if
+the shared library cannot be loaded, or no CUDA device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_DP = C.POINTER(C.c_double)
+_PP = C.POINTER(C.c_void_p)
+
+
+class GridDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in
+                ("geom", "ndim", "nghost", "nblocks", "ni", "nj", "nk", "is_", "ie", "js", "je",
+                 "ks", "ke", "fni", "fnj", "fnk")] + [("xmin", _DP), ("dx", _DP)]
+
+
+class FluidDesc(C.Structure):
+    _fields_ = [("fluid", C.c_int), ("nspecies", C.c_int), ("recon", C.c_int),
+                ("riemann", C.c_int), ("gm1", C.c_double), ("dfloor", C.c_double),
+                ("siefloor", C.c_double), ("de_switch", C.c_double), ("cfl", C.c_double)]
+
+
+class PackDesc(C.Structure):
+    _fields_ = [("prim", _PP), ("cons0", _PP), ("cons1", _PP), ("flux", _PP * 3),
+                ("pflux", _PP * 3), ("vface", _PP * 3)]
+
+
+class BndDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("fluid", "block", "var0", "ncomp", "si", "ei", "sj", "ej",
+                                       "sk", "ek")] + [("buf", C.c_void_p)]
+
+
+class AB200Error(RuntimeError):
+    pass
+
+
+# every symbol include/ab200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "ab200_abi_version", "ab200_last_error", "ab200_device_count", "ab200_create",
+    "ab200_destroy", "ab200_synchronize", "ab200_set_grid", "ab200_bind_pack", "ab200_unbind",
+    "ab200_set_rotating_frame", "ab200_calculate_fluxes", "ab200_apply_update",
+    "ab200_flux_source", "ab200_set_auxillary_fields", "ab200_cons_to_prim",
+    "ab200_prim_to_cons", "ab200_deep_copy_conserved", "ab200_estimate_timestep",
+    "ab200_fused_stage", "ab200_prim_to_cons_ghosts", "ab200_estimate_timestep_device",
+    "ab200_set_global_timestep_device", "ab200_dt_device", "ab200_read_time_state",
+    "ab200_write_time_state", "ab200_halo_pack", "ab200_halo_unpack", "ab200_set_topology",
+    "ab200_exchange_ghosts", "ab200_apply_physical_bcs", "ab200_cycles_host",
+    "ab200_run_cycles", "ab200_malloc", "ab200_free", "ab200_memcpy_h2d", "ab200_memcpy_d2h",
+    "ab200_launch_count", "ab200_timer_begin", "ab200_timer_end",
+]
+
+_libs: dict[str, C.CDLL] = {}
+
+
+def lib_path(variant: str = "fast") -> str:
+    name = "libartemis_b200.so" if variant == "fast" else f"libartemis_b200_{variant}.so"
+    return os.path.join(_HERE, "lib", name)
+
+
+def load(variant: str | None = None) -> C.CDLL:
+    variant = variant or os.environ.get("AB200_VARIANT", "fast")
+    if variant in _libs:
+        return _libs[variant]
+    path = lib_path(variant)
+    if not os.path.exists(path):
+        raise AB200Error(
+            f"{path} not found: build it with `python -m artemis_b200.build` "
+            "(libartemis_b200 is the only compute path; there is no CPU fallback)")
+    L = C.CDLL(path)
+    L.ab200_last_error.restype = C.c_char_p
+    L.ab200_dt_device.restype = C.c_void_p
+    L.ab200_dt_device.argtypes = [C.c_void_p]
+    L.ab200_launch_count.restype = C.c_longlong
+    L.ab200_launch_count.argtypes = [C.c_void_p]
+    vp, i, d = C.c_void_p, C.c_int, C.c_double
+    sig = {
+        "ab200_create": [C.POINTER(vp), i, vp], "ab200_destroy": [vp], "ab200_synchronize": [vp],
+        "ab200_set_grid": [vp, C.POINTER(GridDesc)],
+        "ab200_bind_pack": [vp, C.POINTER(FluidDesc), C.POINTER(PackDesc)],
+        "ab200_unbind": [vp, i], "ab200_set_rotating_frame": [vp, d],
+        "ab200_calculate_fluxes": [vp, i, i], "ab200_apply_update": [vp, d, d, d],
+        "ab200_flux_source": [vp, i, d], "ab200_set_auxillary_fields": [vp],
+        "ab200_cons_to_prim": [vp], "ab200_prim_to_cons": [vp],
+        "ab200_deep_copy_conserved": [vp], "ab200_estimate_timestep": [vp, i, _DP],
+        "ab200_fused_stage": [vp, d, d, d, d, i, i, i], "ab200_prim_to_cons_ghosts": [vp],
+        "ab200_estimate_timestep_device": [vp],
+        "ab200_set_global_timestep_device": [vp, d, i],
+        "ab200_read_time_state": [vp, _DP], "ab200_write_time_state": [vp, _DP],
+        "ab200_halo_pack": [vp, C.POINTER(BndDesc), i],
+        "ab200_halo_unpack": [vp, C.POINTER(BndDesc), i],
+        "ab200_set_topology": [vp, i, i, i, C.POINTER(C.c_int)],
+        "ab200_exchange_ghosts": [vp], "ab200_apply_physical_bcs": [vp],
+        "ab200_cycles_host": [vp, i, i, _DP, _DP, _DP, _DP, _DP],
+        "ab200_run_cycles": [vp, i, i, d],
+        "ab200_malloc": [vp, C.POINTER(vp), C.c_size_t], "ab200_free": [vp, vp],
+        "ab200_memcpy_h2d": [vp, vp, vp, C.c_size_t], "ab200_memcpy_d2h": [vp, vp, vp, C.c_size_t],
+        "ab200_timer_begin": [vp], "ab200_timer_end": [vp, C.POINTER(C.c_float)],
+    }
+    for name, args in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    _libs[variant] = L
+    return L
+
+
+def check(L, rc, what=""):
+    if rc != 0:
+        msg = L.ab200_last_error()
+        raise AB200Error(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

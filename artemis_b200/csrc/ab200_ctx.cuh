@@ -1,0 +1,90 @@
+// ab200_ctx.cuh -- host-side context of libartemis_b200 (internal).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "ab200_dev.cuh"
+
+namespace ab200 {
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define AB_CUDA(call)                                                                    \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) return ab200::cuda_fail(e__, #call, __FILE__, __LINE__);     \
+  } while (0)
+#define AB_REQUIRE(cond, code, msg)                                                      \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      ab200::set_error(msg);                                                             \
+      return (code);                                                                     \
+    }                                                                                    \
+  } while (0)
+#define AB_TRY(call)                                                                     \
+  do {                                                                                   \
+    int rc__ = (call);                                                                   \
+    if (rc__ != AB200_OK) return rc__;                                                   \
+  } while (0)
+
+struct FluidHost {
+  bool bound = false;
+  FluidDev d{};                       // device-visible descriptor (pointer tables on device)
+  std::vector<void *> owned_tables;   // device pointer tables we allocated
+  std::vector<void *> owned_scratch;  // flux/pflux/vface/u1 scratch we allocated
+  // ghost-exchange variable list (FillGhost fields): pack indices + vector component
+  int n_ghost = 0;
+  int *ghost_vars = nullptr;  // device
+  int *ghost_vdir = nullptr;  // device
+};
+
+struct Topology {
+  bool set = false;
+  int nbx = 1, nby = 1, nbz = 1;
+  int bc[6] = {0, 0, 0, 0, 0, 0};
+};
+
+}  // namespace ab200
+
+struct ab200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool grid_set = false;
+  ab200::GridDev g{};
+  std::vector<void *> grid_allocs;
+  std::vector<double> h_xmin, h_dx;
+  ab200::FluidHost fl[2];
+  ab200::Topology topo;
+  double omf = 0.0;
+  double *d_time = nullptr;     // device double[4]: dt, new_dt, time, ncycle
+  double *d_red = nullptr;      // reduction scratch
+  double *h_pinned = nullptr;   // pinned host scratch (8 doubles)
+  long long launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 148;
+  // host-buffer path (ab200_cycles_host) owned device state
+  std::vector<void *> host_path_allocs;
+  bool host_path_ready = false;
+};
+
+namespace ab200 {
+// kernel launch entry points implemented in tasks_*.cu / fused.cu / halo.cu
+int launch_calculate_fluxes(ab200_ctx *c, int fluid, int pcm);
+int launch_apply_update(ab200_ctx *c, int fluid, double gam0, double gam1, double beta_dt);
+int launch_flux_source(ab200_ctx *c, int fluid, double dt);
+int launch_set_aux(ab200_ctx *c);
+int launch_cons_to_prim(ab200_ctx *c, int fluid);
+int launch_prim_to_cons(ab200_ctx *c, int fluid, int ghosts_only);
+int launch_deep_copy(ab200_ctx *c, int fluid);
+int launch_estimate_dt(ab200_ctx *c, int fluid, double *d_out, int combine);
+int launch_fused_stage(ab200_ctx *c, int fluid, double gam0, double gam1, double beta,
+                       double dt, int pcm, int stage1_copy, int use_device_dt);
+int launch_exchange(ab200_ctx *c, int fluid);
+int launch_physical_bcs(ab200_ctx *c, int fluid);
+int launch_halo(ab200_ctx *c, const ab200_bnd_desc *bnd, int n, int unpack);
+int launch_set_global_dt(ab200_ctx *c, double tlim, int advance_time);
+int ensure_scratch(ab200_ctx *c, int fluid, bool need_flux, bool need_u1);
+}  // namespace ab200

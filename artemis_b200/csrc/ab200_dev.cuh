@@ -1,0 +1,477 @@
+// ab200_dev.cuh -- device-side building blocks shared by every kernel of libartemis_b200:
+// descriptors, coordinate geometry, reconstruction and Riemann solvers.
+//
+// All arithmetic follows the reference operation for operation (citations are file:line in
+// lanl/artemis @ 6c2a7a8) so that a build with --fmad=false is bit-identical to the
+// reference's CPU build; transcendental inputs (sin/cos of the theta faces and centroids)
+// come from host-built tables so libm rounding matches as well.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/ab200.h"
+
+namespace ab200 {
+
+#define AB_HD __host__ __device__ __forceinline__
+#define AB_D __device__ __forceinline__
+
+// Per-block 1-D metric tables (host-built).  Everything the
+// Coords<GEOM> algebra needs is separable in (i, j, k).
+struct GeomTab {
+  const double *x1f, *x2f, *x3f;          // [nb][n+1] face positions  Xf(idx)=xmin+idx*dx
+  const double *x1v, *x2v, *x3v;          // [nb][n]   volume centroids (geometry specific)
+  const double *cosf, *sinf;              // [nb][nj+1] cos/sin(x2f)   (spherical)
+  const double *sinv, *sinc;              // [nb][nj]   sin(x2v), sin(0.5*(x2f[j]+x2f[j+1]))
+};
+
+struct GridDev {
+  int geom, ndim, ng, nb;
+  int ni, nj, nk;
+  int is, ie, js, je, ks, ke;
+  int fni, fnj, fnk;
+  GeomTab t;
+};
+
+struct FluidDev {
+  int fluid, S, nvar, recon, riemann;
+  double gm1, dfloor, siefloor, de_switch, cfl;
+  double *const *prim;
+  double *const *u0;
+  double *const *u1;
+  double *const *flux[3];
+  double *const *pflux[3];
+  double *const *vface[3];
+};
+
+AB_D double sqr(double x) { return x * x; }
+// std::max / std::min semantics of the reference (NaN-free inputs)
+AB_D double dmax(double a, double b) { return a > b ? a : b; }
+AB_D double dmin(double a, double b) { return b < a ? b : a; }
+
+// ========================================================================================
+// Geometry: src/geometry/{geometry,cylindrical,spherical,axisymmetric}.hpp
+// ========================================================================================
+template <int GEOM>
+struct Coords {
+  double x1[2], x2[2], x3[2];
+  const GeomTab &t;
+  int b_, k_, j_, i_;
+  int o1, o2, o3;  // table offsets
+
+  AB_D Coords(const GridDev &g, int b, int k, int j, int i)
+      : t(g.t), b_(b), k_(k), j_(j), i_(i) {
+    o1 = b * (g.ni + 1) + i;
+    o2 = b * (g.nj + 1) + j;
+    o3 = b * (g.nk + 1) + k;
+    x1[0] = t.x1f[o1]; x1[1] = t.x1f[o1 + 1];
+    x2[0] = t.x2f[o2]; x2[1] = t.x2f[o2 + 1];
+    x3[0] = t.x3f[o3]; x3[1] = t.x3f[o3 + 1];
+  }
+  static constexpr bool sph = (GEOM == AB200_SPHERICAL1D || GEOM == AB200_SPHERICAL2D ||
+                               GEOM == AB200_SPHERICAL3D);
+  static constexpr bool sph23 = (GEOM == AB200_SPHERICAL2D || GEOM == AB200_SPHERICAL3D);
+  static constexpr bool x1dep = (GEOM != AB200_CARTESIAN);  // geometry.hpp:102-105
+  static constexpr bool x2dep = sph23;                      // geometry.hpp:106-109
+
+  // trig from the host tables
+  AB_D double cosf(int f) const { return t.cosf[o2 + f]; }
+  AB_D double sinf(int f) const { return t.sinf[o2 + f]; }
+  AB_D double sinv() const { return t.sinv[o2 - b_]; }  // [nb][nj] -> offset b*nj + j
+  AB_D double sinc() const { return t.sinc[o2 - b_]; }
+
+  // <r> on a theta/phi/z face: cylindrical.hpp:52-56
+  AB_D double rface() const {
+    return 2.0 / 3.0 * (x1[0] * x1[0] + x1[0] * x1[1] + x1[1] * x1[1]) / (x1[0] + x1[1]);
+  }
+  AB_D double x1v() const {
+    if (GEOM == AB200_CYLINDRICAL || GEOM == AB200_AXISYMMETRIC) return rface();
+    if (sph) {  // spherical.hpp:57-60
+      const double dr2 = x1[0] * x1[0] + x1[1] * x1[1];
+      return 0.75 * (x1[0] + x1[1]) * dr2 / (dr2 + x1[0] * x1[1]);
+    }
+    return 0.5 * (x1[0] + x1[1]);
+  }
+  AB_D double x2v() const {
+    if (sph23) {  // spherical.hpp:61-68
+      const double ctm = cosf(0), ctp = cosf(1);
+      const double dst = sinf(1) - sinf(0);
+      return (dst - x2[1] * ctp + x2[0] * ctm) / fabs(ctm - ctp);
+    }
+    return 0.5 * (x2[0] + x2[1]);
+  }
+  AB_D double x3v() const { return 0.5 * (x3[0] + x3[1]); }
+
+  AB_D double hx1v() const { return 1.0; }
+  AB_D double hx2v() const {  // cyl:62, sph:70,274; spherical1D keeps the default
+    if (GEOM == AB200_CYLINDRICAL || sph23) return x1v();
+    return 1.0;
+  }
+  AB_D double hx3v() const {
+    if (GEOM == AB200_AXISYMMETRIC) return x1v();
+    if (sph23) {  // spherical.hpp:71-85
+      const double ctm = cosf(0), ctp = cosf(1), stm = sinf(0), stp = sinf(1);
+      const double dsc = stp * ctp - stm * ctm;
+      const double dx2 = x2[1] - x2[0];
+      return x1v() * 0.5 * (dx2 - dsc) / fabs(ctm - ctp);
+    }
+    return 1.0;
+  }
+  // h_d at the lower-face centroid of direction DIR (ScaleMomentumFlux,
+  // src/utils/fluxes/fluid_fluxes.hpp:55-66 with FaceCenX{1,2,3}(lower))
+  template <int DIR>
+  AB_D void face_scale(double h[3]) const {
+    h[0] = 1.0; h[1] = 1.0; h[2] = 1.0;
+    if (GEOM == AB200_CARTESIAN) return;
+    double xr, s2;  // radial coordinate and sin(theta) at the face centroid
+    if (DIR == 1) {
+      xr = x1[0];
+      s2 = sph23 ? sinv() : 1.0;        // FaceCenX1 = {x1f, x2v, x3v}
+    } else if (DIR == 2) {
+      xr = (GEOM == AB200_CYLINDRICAL) ? x1v() : rface();  // cyl keeps default FaceCenX2
+      s2 = sph23 ? sinf(0) : 1.0;
+    } else {
+      xr = (GEOM == AB200_AXISYMMETRIC) ? x1v() : rface();
+      s2 = sph23 ? sinc() : 1.0;
+    }
+    if (GEOM == AB200_CYLINDRICAL || sph) h[1] = xr;
+    if (GEOM == AB200_AXISYMMETRIC) h[2] = xr;
+    if (sph23) h[2] = xr * s2;
+  }
+  AB_D double area1(double x1f) const {
+    const double dx2 = x2[1] - x2[0], dx3 = x3[1] - x3[0];
+    if (GEOM == AB200_CYLINDRICAL || GEOM == AB200_AXISYMMETRIC) return x1f * dx2 * dx3;
+    if (GEOM == AB200_SPHERICAL3D) return x1f * x1f * fabs(cosf(0) - cosf(1)) * dx3;
+    if (GEOM == AB200_SPHERICAL2D) return x1f * x1f * fabs(cosf(0) - cosf(1));
+    if (GEOM == AB200_SPHERICAL1D) return x1f * x1f;
+    return dx2 * dx3;
+  }
+  AB_D double area2(int f) const {
+    const double dx1 = x1[1] - x1[0], dx3 = x3[1] - x3[0];
+    if (GEOM == AB200_AXISYMMETRIC) return (x1[0] + x1[1]) * 0.5 * dx1 * dx3;
+    if (GEOM == AB200_SPHERICAL3D) return 0.5 * (x1[1] + x1[0]) * sinf(f) * dx1 * dx3;
+    if (GEOM == AB200_SPHERICAL2D) return 0.5 * (x1[1] + x1[0]) * sinf(f) * dx1;
+    if (GEOM == AB200_SPHERICAL1D) return 0.5 * (x1[1] + x1[0]) * dx1;
+    return dx1 * dx3;
+  }
+  AB_D double area3() const {
+    const double dx1 = x1[1] - x1[0], dx2 = x2[1] - x2[0];
+    if (GEOM == AB200_CYLINDRICAL || sph23) return 0.5 * (x1[0] + x1[1]) * dx1 * dx2;
+    if (GEOM == AB200_SPHERICAL1D) return 0.5 * (x1[0] + x1[1]) * dx1;
+    return dx1 * dx2;
+  }
+  AB_D double volume() const {
+    const double dx1 = x1[1] - x1[0], dx2 = x2[1] - x2[0], dx3 = x3[1] - x3[0];
+    if (GEOM == AB200_CYLINDRICAL || GEOM == AB200_AXISYMMETRIC)
+      return (x1[0] + x1[1]) * 0.5 * dx1 * dx2 * dx3;
+    if (sph) {
+      const double rfac = (x1[0] * x1[0] + x1[0] * x1[1] + x1[1] * x1[1]) / 3.0;
+      if (GEOM == AB200_SPHERICAL1D) return rfac * dx1;
+      const double dc = fabs(cosf(0) - cosf(1));
+      if (GEOM == AB200_SPHERICAL2D) return rfac * dx1 * dc;
+      return rfac * dx1 * dc * dx3;
+    }
+    return dx1 * dx2 * dx3;
+  }
+  AB_D void conn1(double c[3]) const {
+    c[0] = 0.0; c[1] = 0.0; c[2] = 0.0;
+    if (GEOM == AB200_CYLINDRICAL) c[1] = 1.0 / (0.5 * (x1[0] + x1[1]));
+    if (GEOM == AB200_AXISYMMETRIC) c[2] = 1.0 / (0.5 * (x1[0] + x1[1]));
+    if (sph) {  // spherical.hpp:134-141
+      const double v = 3.0 / 2.0 * (x1[0] + x1[1]) /
+                       (x1[0] * x1[0] + x1[0] * x1[1] + x1[1] * x1[1]);
+      c[1] = v; c[2] = v;
+    }
+  }
+  AB_D void conn2(double c[3]) const {
+    c[0] = 0.0; c[1] = 0.0; c[2] = 0.0;
+    if (sph23) c[2] = (sinf(1) - sinf(0)) / fabs(cosf(0) - cosf(1));  // spherical.hpp:142
+  }
+  // GetCellWidths: geometry.hpp:347-354
+  AB_D void widths(double w[3]) const {
+    const double xv1 = x1v();
+    double h2 = 1.0, h3 = 1.0;
+    if (GEOM == AB200_CYLINDRICAL || sph) h2 = xv1;
+    if (GEOM == AB200_AXISYMMETRIC) h3 = xv1;
+    if (sph23) h3 = xv1 * sinv();
+    w[0] = 1.0 * (x1[1] - x1[0]);
+    w[1] = h2 * (x2[1] - x2[0]);
+    w[2] = h3 * (x3[1] - x3[0]);
+  }
+  // RotatingFrame::RotationVelocity: src/rotating_frame/rotating_frame.hpp:32-49
+  AB_D void rotation_velocity(double omf, double vf[3]) const {
+    vf[0] = 0.0; vf[1] = 0.0; vf[2] = 0.0;
+    if (GEOM == AB200_CARTESIAN) { vf[1] = omf; return; }
+    const double xv1 = x1v();
+    if (GEOM == AB200_CYLINDRICAL) vf[1] = 1.0 * (omf * xv1);
+    if (GEOM == AB200_AXISYMMETRIC) vf[2] = 1.0 * (omf * xv1);
+    if (sph23) vf[2] = 1.0 * (omf * (xv1 * sinv()));
+    if (GEOM == AB200_SPHERICAL1D) vf[2] = 1.0 * (omf * (xv1 * 1.0));
+  }
+};
+
+// ========================================================================================
+// Reconstruction: src/utils/fluxes/reconstruction/{plm,ppm}.hpp
+// ========================================================================================
+AB_D void plm(double q_im1, double q_i, double q_ip1, double &ql_ip1, double &qr_i) {
+  const double dql = (q_i - q_im1);
+  const double dqr = (q_ip1 - q_i);
+  const double dq2 = dql * dqr;
+  double dqm = dq2 / (dql + dqr);
+  if (dq2 <= 0.0) dqm = 0.0;
+  ql_ip1 = q_i + dqm;
+  qr_i = q_i - dqm;
+}
+// plm.hpp:53-73 (Mignone 2013)
+AB_D void plm_g(double q_im1, double q_i, double q_ip1, double &ql_ip1, double &qr_i,
+                double x_im1, double x_i, double x_ip1, double xf0, double xf1, double dx) {
+  const double dql = (q_i - q_im1) * dx / (x_i - x_im1);
+  const double dqr = (q_ip1 - q_i) * dx / (x_ip1 - x_i);
+  const double dq2 = dql * dqr;
+  const double cr = (x_ip1 - x_i) / (xf1 - x_i);
+  const double cl = (x_i - x_im1) / (x_i - xf0);
+  const double dqm = (dq2 <= 0.0) ? 0.0
+                                  : dq2 * (cr * dql + cl * dqr) /
+                                        (dql * dql + dqr * dqr + dq2 * (cl + cr - 2.0));
+  ql_ip1 = q_i + dqm * (xf1 - x_i) / dx;
+  qr_i = q_i - dqm * (x_i - xf0) / dx;
+}
+// ppm.hpp:32-66
+AB_D void ppm4(double q_im2, double q_im1, double q_i, double q_ip1, double q_ip2,
+               double &ql_ip1, double &qr_i) {
+  double qlv = (7. * (q_i + q_im1) - (q_im2 + q_ip1)) / 12.0;
+  double qrv = (7. * (q_i + q_ip1) - (q_im1 + q_ip2)) / 12.0;
+  qlv = dmax(qlv, dmin(q_i, q_im1));
+  qlv = dmin(qlv, dmax(q_i, q_im1));
+  qrv = dmax(qrv, dmin(q_i, q_ip1));
+  qrv = dmin(qrv, dmax(q_i, q_ip1));
+  const double qc = qrv - q_i;
+  const double qd = qlv - q_i;
+  if ((qc * qd) >= 0.0) {
+    qlv = q_i;
+    qrv = q_i;
+  } else {
+    if (fabs(qc) >= 2.0 * fabs(qd)) qrv = q_i - 2.0 * qd;
+    if (fabs(qd) >= 2.0 * fabs(qc)) qlv = q_i - 2.0 * qc;
+  }
+  ql_ip1 = qrv;
+  qr_i = qlv;
+}
+
+// Reconstruct one variable of one cell along a stride. q points at the cell; st = element
+// stride along the reconstruction direction.  xm/xc/xp, xf0/xf1, w: PLM_G geometry.
+template <int RC, bool CART>
+AB_D void recon_cell(const double *__restrict__ q, ptrdiff_t st, double &ql_ip1, double &qr_i,
+                     double xm, double xc, double xp, double xf0, double xf1, double w) {
+  if (RC == AB200_PCM) {
+    const double v = q[0];
+    ql_ip1 = v;
+    qr_i = v;
+  } else if (RC == AB200_PLM) {
+    if (CART) plm(q[-st], q[0], q[st], ql_ip1, qr_i);
+    else plm_g(q[-st], q[0], q[st], ql_ip1, qr_i, xm, xc, xp, xf0, xf1, w);
+  } else {
+    ppm4(q[-2 * st], q[-st], q[0], q[st], q[2 * st], ql_ip1, qr_i);
+  }
+}
+
+// ========================================================================================
+// Riemann solvers: src/utils/fluxes/riemann/{hllc,hlle,llf}.hpp
+// State order {rho, vx(normal), vy, vz, P, sie}; out {Frho,Fmx,Fmy,Fmz,FE,Fu,pface,vface}.
+// Momentum fluxes are pressure-free; pface is the interface pressure.
+// ========================================================================================
+template <int RS, int FLUID>
+struct Riemann;
+
+template <>
+struct Riemann<AB200_HLLC, AB200_GAS> {  // hllc.hpp:76-180
+  static AB_D void solve(double gm1, const double *wl, const double *wr, double *out) {
+    const double wl_idn = wl[0], wl_ivx = wl[1], wl_ivy = wl[2], wl_ivz = wl[3],
+                 wl_ipr = wl[4], wl_ise = wl[5];
+    const double wr_idn = wr[0], wr_ivx = wr[1], wr_ivy = wr[2], wr_ivz = wr[3],
+                 wr_ipr = wr[4], wr_ise = wr[5];
+    const double igm1 = 1.0 / gm1;
+    const double gamma = gm1 + 1.0;
+    const double alpha = (gamma + 1.0) / (2.0 * gamma);
+    double qa, qb, qc, qd, qe, qf;
+    qa = sqrt(gamma * wl_ipr / wl_idn);
+    qb = sqrt(gamma * wr_ipr / wr_idn);
+    const double el =
+        wl_ipr * igm1 + 0.5 * wl_idn * (sqr(wl_ivx) + sqr(wl_ivy) + sqr(wl_ivz));
+    const double er =
+        wr_ipr * igm1 + 0.5 * wr_idn * (sqr(wr_ivx) + sqr(wr_ivy) + sqr(wr_ivz));
+    qc = 0.25 * (wl_idn + wr_idn) * (qa + qb);
+    qd = 0.5 * (wl_ipr + wr_ipr + (wl_ivx - wr_ivx) * qc);
+    qe = (qd <= wl_ipr) ? 1.0 : sqrt(1.0 + alpha * ((qd / wl_ipr) - 1.0));
+    qf = (qd <= wr_ipr) ? 1.0 : sqrt(1.0 + alpha * ((qd / wr_ipr) - 1.0));
+    const double sl = wl_ivx - qa * qe;
+    const double sr = wr_ivx + qb * qf;
+    qa = sr > 0.0 ? sr : 1.0e-20;
+    qb = sl < 0.0 ? sl : -1.0e-20;
+    qe = wl_ivx - sl;
+    qf = wr_ivx - sr;
+    qc = wl_ipr + qe * wl_idn * wl_ivx;
+    qd = wr_ipr + qf * wr_idn * wr_ivx;
+    const double ml = wl_idn * qe;
+    const double mr = -(wr_idn * qf);
+    const double am = (qc - qd) / (ml + mr);
+    double cp = (ml * qd + mr * qc) / (ml + mr);
+    cp = cp > 0.0 ? cp : 0.0;
+    qe = wl_idn * (wl_ivx - qb);
+    qf = wr_idn * (wr_ivx - qa);
+    const double fld = qe, frd = qf;
+    const double flmx = qe * wl_ivx, frmx = qf * wr_ivx;
+    const double flmy = qe * wl_ivy, frmy = qf * wr_ivy;
+    const double flmz = qe * wl_ivz, frmz = qf * wr_ivz;
+    const double fle = el * (wl_ivx - qb) + wl_ipr * wl_ivx;
+    const double fre = er * (wr_ivx - qa) + wr_ipr * wr_ivx;
+    if (am >= 0.0) {
+      qc = am / (am - qb);
+      qd = 0.0;
+      qe = -qb / (am - qb);
+    } else {
+      qc = 0.0;
+      qd = -am / (qa - am);
+      qe = qa / (qa - am);
+    }
+    out[6] = qc * wl_ipr + qd * wr_ipr + qe * cp;
+    const double frho = qc * fld + qd * frd;
+    out[0] = frho;
+    out[1] = qc * flmx + qd * frmx;
+    out[2] = qc * flmy + qd * frmy;
+    out[3] = qc * flmz + qd * frmz;
+    out[4] = qc * fle + qd * fre + qe * cp * am;
+    out[5] = frho * ((frho >= 0.0) ? wl_ise : wr_ise);
+    out[7] = frho / ((frho >= 0.0) ? wl_idn : wr_idn);
+  }
+};
+
+template <int FLUID>
+struct Riemann<AB200_HLLE, FLUID> {  // hlle.hpp:92-220
+  static AB_D void solve(double gm1, const double *wl, const double *wr, double *out) {
+    constexpr bool gas = (FLUID == AB200_GAS);
+    const double wl_idn = wl[0], wl_ivx = wl[1], wl_ivy = wl[2], wl_ivz = wl[3];
+    const double wr_idn = wr[0], wr_ivx = wr[1], wr_ivy = wr[2], wr_ivz = wr[3];
+    double wl_ipr = 0, wr_ipr = 0, wl_ise = 0, wr_ise = 0, igm1 = 0, gamma = 0;
+    if (gas) {
+      wl_ipr = wl[4]; wl_ise = wl[5]; wr_ipr = wr[4]; wr_ise = wr[5];
+      igm1 = 1.0 / gm1;
+      gamma = gm1 + 1.0;
+    }
+    const double sqrtdl = sqrt(wl_idn);
+    const double sqrtdr = sqrt(wr_idn);
+    const double isdlpdr = 1.0 / (sqrtdl + sqrtdr);
+    const double wroe_ivx = (sqrtdl * wl_ivx + sqrtdr * wr_ivx) * isdlpdr;
+    const double wroe_ivy = (sqrtdl * wl_ivy + sqrtdr * wr_ivy) * isdlpdr;
+    const double wroe_ivz = (sqrtdl * wl_ivz + sqrtdr * wr_ivz) * isdlpdr;
+    double el = 0, er = 0, hroe = 0;
+    if (gas) {
+      el = wl_ipr * igm1 + 0.5 * wl_idn * (sqr(wl_ivx) + sqr(wl_ivy) + sqr(wl_ivz));
+      er = wr_ipr * igm1 + 0.5 * wr_idn * (sqr(wr_ivx) + sqr(wr_ivy) + sqr(wr_ivz));
+      hroe = ((el + wl_ipr) / sqrtdl + (er + wr_ipr) / sqrtdr) * isdlpdr;
+    }
+    double qa = 0, qb = 0, sl, sr;
+    if (gas) {
+      qa = sqrt(gamma * wl_ipr / wl_idn);
+      qb = sqrt(gamma * wr_ipr / wr_idn);
+      double a = hroe - 0.5 * (sqr(wroe_ivx) + sqr(wroe_ivy) + sqr(wroe_ivz));
+      a = (a < 0.0) ? 0.0 : sqrt(gm1 * a);
+      const double sla = wroe_ivx - a;
+      const double slb = wl_ivx - qa;
+      const double sra = wroe_ivx + a;
+      const double srb = wr_ivx + qb;
+      sl = dmin(sla, slb);
+      sr = dmax(sra, srb);
+    } else {
+      sl = dmin(wroe_ivx, wl_ivx);
+      sr = dmax(wroe_ivx, wr_ivx);
+    }
+    const double bp = (sr > 0.0) ? sr : 1.0e-20;
+    const double bm = (sl < 0.0) ? sl : -1.0e-20;
+    qa = wl_ivx - bm;
+    qb = wr_ivx - bp;
+    const double fl_d = wl_idn * qa, fr_d = wr_idn * qb;
+    const double fl_mx = wl_idn * wl_ivx * qa, fr_mx = wr_idn * wr_ivx * qb;
+    const double fl_my = wl_idn * wl_ivy * qa, fr_my = wr_idn * wr_ivy * qb;
+    const double fl_mz = wl_idn * wl_ivz * qa, fr_mz = wr_idn * wr_ivz * qb;
+    double fl_e = 0, fr_e = 0;
+    if (gas) {
+      fl_e = el * qa + wl_ipr * wl_ivx;
+      fr_e = er * qb + wr_ipr * wr_ivx;
+    }
+    qa = 0.0;
+    if (bp != bm) qa = 0.5 * (bp + bm) / (bp - bm);
+    if (gas) out[6] = 0.5 * (wl_ipr + wr_ipr) + qa * (wl_ipr - wr_ipr);
+    const double frho = 0.5 * (fl_d + fr_d) + qa * (fl_d - fr_d);
+    out[0] = frho;
+    out[1] = 0.5 * (fl_mx + fr_mx) + qa * (fl_mx - fr_mx);
+    out[2] = 0.5 * (fl_my + fr_my) + qa * (fl_my - fr_my);
+    out[3] = 0.5 * (fl_mz + fr_mz) + qa * (fl_mz - fr_mz);
+    if (gas) {
+      out[4] = 0.5 * (fl_e + fr_e) + qa * (fl_e - fr_e);
+      out[5] = frho * ((frho >= 0.0) ? wl_ise : wr_ise);
+      out[7] = frho / ((frho >= 0.0) ? wl_idn : wr_idn);
+    }
+  }
+};
+
+template <int FLUID>
+struct Riemann<AB200_LLF, FLUID> {  // llf.hpp:87-168
+  static AB_D void solve(double gm1, const double *wl, const double *wr, double *out) {
+    constexpr bool gas = (FLUID == AB200_GAS);
+    const double wl_idn = wl[0], wl_ivx = wl[1], wl_ivy = wl[2], wl_ivz = wl[3];
+    const double wr_idn = wr[0], wr_ivx = wr[1], wr_ivy = wr[2], wr_ivz = wr[3];
+    double wl_ipr = 0, wr_ipr = 0, wl_ise = 0, wr_ise = 0, igm1 = 0, gamma = 0;
+    if (gas) {
+      wl_ipr = wl[4]; wl_ise = wl[5]; wr_ipr = wr[4]; wr_ise = wr[5];
+      igm1 = 1.0 / gm1;
+      gamma = gm1 + 1.0;
+    }
+    double qa = wl_idn * wl_ivx;
+    double qb = wr_idn * wr_ivx;
+    const double fsum_d = qa + qb;
+    const double fsum_mx = qa * wl_ivx + qb * wr_ivx;
+    const double fsum_my = qa * wl_ivy + qb * wr_ivy;
+    const double fsum_mz = qa * wl_ivz + qb * wr_ivz;
+    double el = 0, er = 0, fsum_e = 0;
+    if (gas) {
+      el = wl_ipr * igm1 + 0.5 * wl_idn * (sqr(wl_ivx) + sqr(wl_ivy) + sqr(wl_ivz));
+      er = wr_ipr * igm1 + 0.5 * wr_idn * (sqr(wr_ivx) + sqr(wr_ivy) + sqr(wr_ivz));
+      fsum_e = (el + wl_ipr) * wl_ivx + (er + wr_ipr) * wr_ivx;
+    }
+    double a;
+    if (gas) {
+      qa = sqrt(gamma * wl_ipr / wl_idn);
+      qb = sqrt(gamma * wr_ipr / wr_idn);
+      a = dmax((fabs(wl_ivx) + qa), (fabs(wr_ivx) + qb));
+    } else {
+      a = dmax(fabs(wl_ivx), fabs(wr_ivx));
+    }
+    const double du_d = a * (wr_idn - wl_idn);
+    const double du_mx = a * (wr_idn * wr_ivx - wl_idn * wl_ivx);
+    const double du_my = a * (wr_idn * wr_ivy - wl_idn * wl_ivy);
+    const double du_mz = a * (wr_idn * wr_ivz - wl_idn * wl_ivz);
+    double du_e = 0;
+    if (gas) du_e = a * (er - el);
+    if (gas) out[6] = 0.5 * (wl_ipr + wr_ipr);
+    const double frho = 0.5 * (fsum_d - du_d);
+    out[0] = frho;
+    out[1] = 0.5 * (fsum_mx - du_mx);
+    out[2] = 0.5 * (fsum_my - du_my);
+    out[3] = 0.5 * (fsum_mz - du_mz);
+    if (gas) {
+      out[4] = 0.5 * (fsum_e - du_e);
+      out[5] = frho * ((frho >= 0.0) ? wl_ise : wr_ise);
+      out[7] = frho / ((frho >= 0.0) ? wl_idn : wr_idn);
+    }
+  }
+};
+
+// HLLC is gas-only (hllc.hpp:63); Dust::Initialize rejects it (src/dust/dust.cpp:76-85).
+template <>
+struct Riemann<AB200_HLLC, AB200_DUST> {
+  static AB_D void solve(double, const double *, const double *, double *) {}
+};
+
+}  // namespace ab200

@@ -1,0 +1,89 @@
+// fused.cu -- instantiations + launcher of the fused directional passes for ONE coordinate
+// system (compiled six times with -DAB_GEOM=0..5).
+#include "fused.cuh"
+
+#ifndef AB_GEOM
+#error "compile with -DAB_GEOM=<0..5>"
+#endif
+
+namespace ab200 {
+
+template <int GEOM, int FLUID, int RS, int RC, int DIR>
+static int launch_pass(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
+  const GridDev &g = c->g;
+  const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
+  const int L = DIR == 1 ? nir : (DIR == 2 ? njr : nkr);
+  AB_REQUIRE(L + 2 <= kFusedMaxThreads, AB200_EINVAL,
+             "ab200_fused_stage: MeshBlock extent exceeds 510 zones; use the task-level path");
+  int np = kFusedMaxThreads / (L + 2);
+  const long long npencils =
+      (long long)g.nb * (DIR == 1 ? (long long)nkr * njr
+                                  : (DIR == 2 ? (long long)nkr * nir : (long long)njr * nir));
+  if (np > npencils) np = (int)npencils;
+  a.np = np;
+  a.npencils = (int)npencils;
+  const int nthreads = ((np * (L + 2) + 31) / 32) * 32;
+  constexpr int NV = FLUID == AB200_GAS ? 6 : 4, NF = FLUID == AB200_GAS ? 8 : 4;
+  const size_t shmem = sizeof(double) * (size_t)(NV + NF) * np * (L + 1);
+  auto kern = k_fused_pass<GEOM, FLUID, RS, RC, DIR>;
+  if (shmem > 48 * 1024)
+    AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+  const unsigned grid = (unsigned)((npencils + np - 1) / np);
+  kern<<<grid, nthreads, shmem, c->stream>>>(g, f, a);
+  c->launches++;
+  AB_CUDA(cudaGetLastError());
+  return AB200_OK;
+}
+
+template <int GEOM, int FLUID, int RS, int RC>
+static int launch_dirs(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
+  const int ndim = c->g.ndim;
+  const int copy = a.copy_u1;
+  a.first = 1; a.last = (ndim == 1); a.copy_u1 = copy;
+  AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 1>(c, f, a)));
+  if (ndim >= 2) {
+    a.first = 0; a.last = (ndim == 2); a.copy_u1 = 0;
+    AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 2>(c, f, a)));
+  }
+  if (ndim >= 3) {
+    a.first = 0; a.last = 1; a.copy_u1 = 0;
+    AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 3>(c, f, a)));
+  }
+  return AB200_OK;
+}
+
+template <int GEOM, int FLUID, int RS>
+static int launch_rc(ab200_ctx *c, const FluidDev &f, int recon, const FusedArgs &a) {
+  switch (recon) {
+  case AB200_PCM: return launch_dirs<GEOM, FLUID, RS, AB200_PCM>(c, f, a);
+  case AB200_PLM: return launch_dirs<GEOM, FLUID, RS, AB200_PLM>(c, f, a);
+  case AB200_PPM: return launch_dirs<GEOM, FLUID, RS, AB200_PPM>(c, f, a);
+  }
+  set_error("Reconstruction method not recognized!");
+  return AB200_EINVAL;
+}
+
+template <int GEOM>
+int launch_fused_geom(ab200_ctx *c, int fluid, const FusedArgs &a, int pcm);
+
+template <>
+int launch_fused_geom<AB_GEOM>(ab200_ctx *c, int fluid, const FusedArgs &a, int pcm) {
+  const FluidDev &f = c->fl[fluid].d;
+  const int recon = pcm ? AB200_PCM : f.recon;
+  if (fluid == AB200_GAS) {
+    switch (f.riemann) {
+    case AB200_HLLC: return launch_rc<AB_GEOM, AB200_GAS, AB200_HLLC>(c, f, recon, a);
+    case AB200_HLLE: return launch_rc<AB_GEOM, AB200_GAS, AB200_HLLE>(c, f, recon, a);
+    case AB200_LLF: return launch_rc<AB_GEOM, AB200_GAS, AB200_LLF>(c, f, recon, a);
+    }
+  } else {
+    switch (f.riemann) {
+    case AB200_HLLE: return launch_rc<AB_GEOM, AB200_DUST, AB200_HLLE>(c, f, recon, a);
+    case AB200_LLF: return launch_rc<AB_GEOM, AB200_DUST, AB200_LLF>(c, f, recon, a);
+    }
+  }
+  set_error("Riemann solver not recognized!");
+  return AB200_EINVAL;
+}
+
+}  // namespace ab200

@@ -1,0 +1,203 @@
+// halo.cu -- ghost-zone kernels: same-GPU neighbour fill, physical boundaries, and the
+// descriptor-driven pack/unpack used for buffers that cross GPUs.
+//
+// Index ranges are the same-level branch of CalcIndices (P:bvals/comms/bnd_info.cpp:152-213):
+// a neighbour at offset o in a direction sends its innermost `ng` interior cells adjacent to
+// the shared face/edge/corner and the receiver fills its `ng` ghost cells.  Copy order inside
+// a buffer is [comp][k][j][i], i fastest (P:utils/indexer.hpp:119-131).
+#include "tasks.cuh"
+
+namespace ab200 {
+
+// ----------------------------------------------------------------------------------------
+// Same-GPU exchange: every ghost cell pulls from the interior of its neighbour block.
+// Replaces pack (K8) + state flip + unpack (K9) for BuffCommType::both buffers.
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_exchange(GridDev g, FluidDev f, int nbx, int nby, int nbz, int bc0, int bc1, int bc2, int bc3,
+           int bc4, int bc5, const int *__restrict__ gvars, int ngv) {
+  const long long total = (long long)g.nb * g.nk * g.nj * g.ni;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const CellIdx c = decode(t, g.ni, g.nj, g.nk, 0, 0, 0);
+  const int o1 = c.i < g.is ? -1 : (c.i > g.ie ? 1 : 0);
+  const int o2 = c.j < g.js ? -1 : (c.j > g.je ? 1 : 0);
+  const int o3 = c.k < g.ks ? -1 : (c.k > g.ke ? 1 : 0);
+  if (!o1 && !o2 && !o3) return;
+  const int bc[6] = {bc0, bc1, bc2, bc3, bc4, bc5};
+  const int nbd[3] = {nbx, nby, nbz};
+  int l[3] = {c.b % nbx, (c.b / nbx) % nby, c.b / (nbx * nby)};
+  const int off[3] = {o1, o2, o3};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    l[d] += off[d];
+    if (l[d] < 0 || l[d] >= nbd[d]) {
+      if (bc[2 * d + (off[d] > 0)] != AB200_BC_PERIODIC) return;  // physical or remote face
+      l[d] = (l[d] + nbd[d]) % nbd[d];
+    }
+  }
+  const int nbr = l[0] + nbx * (l[1] + nby * l[2]);
+  const int si = c.i - o1 * (g.ie - g.is + 1);
+  const int sj = c.j - o2 * (g.je - g.js + 1);
+  const int sk = c.k - o3 * (g.ke - g.ks + 1);
+  const size_t doff = ((size_t)c.k * g.nj + c.j) * g.ni + c.i;
+  const size_t soff = ((size_t)sk * g.nj + sj) * g.ni + si;
+  for (int v = 0; v < ngv; ++v) {
+    const int n = gvars[v];
+    f.prim[(size_t)c.b * f.nvar + n][doff] = f.prim[(size_t)nbr * f.nvar + n][soff];
+  }
+}
+
+int launch_exchange(ab200_ctx *c, int fluid) {
+  const GridDev &g = c->g;
+  const FluidHost &fh = c->fl[fluid];
+  const Topology &tp = c->topo;
+  const long long total = (long long)g.nb * g.nk * g.nj * g.ni;
+  const unsigned grid = (unsigned)((total + kThreads - 1) / kThreads);
+  k_exchange<<<grid, kThreads, 0, c->stream>>>(g, fh.d, tp.nbx, tp.nby, tp.nbz, tp.bc[0],
+                                               tp.bc[1], tp.bc[2], tp.bc[3], tp.bc[4], tp.bc[5],
+                                               fh.ghost_vars, fh.n_ghost);
+  c->launches++;
+  AB_CUDA(cudaGetLastError());
+  return AB200_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// Physical boundaries: GenericBC Outflow / Reflect
+// (P:bvals/boundary_conditions_generic.hpp:178-256).  One launch per mesh face, in the
+// reference's order, over the blocks that touch that face; the tangential ranges are the
+// *entire* index range so corners inherit the previous faces' fills.
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_physical_bc(GridDev g, FluidDev f, int nbx, int nby, int nbz, int face, int type,
+              const int *__restrict__ gvars, const int *__restrict__ gvdir, int ngv) {
+  const int d = face >> 1, outer = face & 1;
+  const int nt[3] = {g.ni, g.nj, g.nk};
+  const int s[3] = {g.is, g.js, g.ks}, e[3] = {g.ie, g.je, g.ke};
+  const int nbd[3] = {nbx, nby, nbz};
+  int ext[3] = {nt[0], nt[1], nt[2]};
+  const int ngd = outer ? nt[d] - 1 - e[d] : s[d];
+  ext[d] = ngd;
+  // blocks on this face: lattice coordinate along d fixed
+  int nbf[3] = {nbx, nby, nbz};
+  nbf[d] = 1;
+  const long long per_block = (long long)ext[0] * ext[1] * ext[2];
+  const long long total = per_block * nbf[0] * nbf[1] * nbf[2];
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  long long r = t;
+  int cidx[3];
+  cidx[0] = (int)(r % ext[0]); r /= ext[0];
+  cidx[1] = (int)(r % ext[1]); r /= ext[1];
+  cidx[2] = (int)(r % ext[2]); r /= ext[2];
+  int lb[3];
+  lb[0] = (int)(r % nbf[0]); r /= nbf[0];
+  lb[1] = (int)(r % nbf[1]); r /= nbf[1];
+  lb[2] = (int)r;
+  lb[d] = outer ? nbd[d] - 1 : 0;
+  const int b = lb[0] + nbx * (lb[1] + nby * lb[2]);
+  cidx[d] += outer ? e[d] + 1 : 0;
+  const int ref = outer ? e[d] : s[d];
+  const int offset = 2 * ref + (outer ? 1 : -1);
+  int sidx[3] = {cidx[0], cidx[1], cidx[2]};
+  sidx[d] = (type == AB200_BC_REFLECT) ? offset - cidx[d] : ref;
+  const size_t doff = ((size_t)cidx[2] * g.nj + cidx[1]) * g.ni + cidx[0];
+  const size_t soff = ((size_t)sidx[2] * g.nj + sidx[1]) * g.ni + sidx[0];
+  for (int v = 0; v < ngv; ++v) {
+    double *a = f.prim[(size_t)b * f.nvar + gvars[v]];
+    const double sgn = (type == AB200_BC_REFLECT && gvdir[v] == d + 1) ? -1.0 : 1.0;
+    a[doff] = sgn * a[soff];
+  }
+}
+
+int launch_physical_bcs(ab200_ctx *c, int fluid) {
+  const GridDev &g = c->g;
+  const FluidHost &fh = c->fl[fluid];
+  const Topology &tp = c->topo;
+  const int nt[3] = {g.ni, g.nj, g.nk};
+  const int s[3] = {g.is, g.js, g.ks}, e[3] = {g.ie, g.je, g.ke};
+  const int nbd[3] = {tp.nbx, tp.nby, tp.nbz};
+  for (int face = 0; face < 2 * g.ndim; ++face) {
+    const int type = tp.bc[face];
+    if (type != AB200_BC_OUTFLOW && type != AB200_BC_REFLECT) continue;
+    const int d = face >> 1, outer = face & 1;
+    long long ext[3] = {nt[0], nt[1], nt[2]};
+    ext[d] = outer ? nt[d] - 1 - e[d] : s[d];
+    if (ext[d] <= 0) continue;
+    long long nbf = (long long)nbd[0] * nbd[1] * nbd[2] / nbd[d];
+    const long long total = ext[0] * ext[1] * ext[2] * nbf;
+    const unsigned grid = (unsigned)((total + kThreads - 1) / kThreads);
+    k_physical_bc<<<grid, kThreads, 0, c->stream>>>(g, fh.d, tp.nbx, tp.nby, tp.nbz, face, type,
+                                                    fh.ghost_vars, fh.ghost_vdir, fh.n_ghost);
+    c->launches++;
+  }
+  AB_CUDA(cudaGetLastError());
+  return AB200_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// Descriptor-driven pack (K8) / unpack (K9) for buffers that leave the GPU.
+// grid.y = buffer, grid.x strides over the buffer's elements.
+// ----------------------------------------------------------------------------------------
+struct BndDev {
+  int fluid, block, var0, ncomp;
+  int si, ei, sj, ej, sk, ek;
+  double *buf;
+};
+
+template <bool UNPACK>
+__global__ void __launch_bounds__(kThreads)
+k_halo(GridDev g, FluidDev f0, FluidDev f1, const BndDev *__restrict__ bnd) {
+  const BndDev d = bnd[blockIdx.y];
+  const FluidDev &f = d.fluid == AB200_GAS ? f0 : f1;
+  const int ni = d.ei - d.si + 1, nj = d.ej - d.sj + 1, nk = d.ek - d.sk + 1;
+  const long long total = (long long)d.ncomp * nk * nj * ni;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    long long r = t;
+    const int i = (int)(r % ni) + d.si; r /= ni;
+    const int j = (int)(r % nj) + d.sj; r /= nj;
+    const int k = (int)(r % nk) + d.sk; r /= nk;
+    const int n = (int)r + d.var0;
+    double *a = f.prim[(size_t)d.block * f.nvar + n] + ((size_t)k * g.nj + j) * g.ni + i;
+    if (UNPACK) *a = d.buf[t];
+    else d.buf[t] = *a;
+  }
+}
+
+int launch_halo(ab200_ctx *c, const ab200_bnd_desc *bnd, int n, int unpack) {
+  const GridDev &g = c->g;
+  std::vector<BndDev> h(n);
+  long long maxel = 0;
+  for (int i = 0; i < n; ++i) {
+    const ab200_bnd_desc &b = bnd[i];
+    AB_REQUIRE(b.fluid == 0 || b.fluid == 1, AB200_EINVAL, "halo: bad fluid in descriptor");
+    AB_REQUIRE(c->fl[b.fluid].bound, AB200_ESTATE, "halo: descriptor names an unbound fluid");
+    AB_REQUIRE(b.block >= 0 && b.block < g.nb && b.var0 >= 0 && b.ncomp > 0 &&
+                   b.var0 + b.ncomp <= c->fl[b.fluid].d.nvar,
+               AB200_EINVAL, "halo: descriptor block/variable out of range");
+    AB_REQUIRE(b.si >= 0 && b.ei < g.ni && b.sj >= 0 && b.ej < g.nj && b.sk >= 0 && b.ek < g.nk &&
+                   b.si <= b.ei && b.sj <= b.ej && b.sk <= b.ek,
+               AB200_EINVAL, "halo: descriptor index range outside the block");
+    AB_REQUIRE(b.buf != nullptr, AB200_EINVAL, "halo: null buffer");
+    h[i] = {b.fluid, b.block, b.var0, b.ncomp, b.si, b.ei, b.sj, b.ej, b.sk, b.ek, b.buf};
+    const long long el = (long long)b.ncomp * (b.ei - b.si + 1) * (b.ej - b.sj + 1) * (b.ek - b.sk + 1);
+    if (el > maxel) maxel = el;
+  }
+  BndDev *d;
+  AB_CUDA(cudaMallocAsync((void **)&d, sizeof(BndDev) * n, c->stream));
+  AB_CUDA(cudaMemcpyAsync(d, h.data(), sizeof(BndDev) * n, cudaMemcpyHostToDevice, c->stream));
+  AB_CUDA(cudaStreamSynchronize(c->stream));  // h goes out of scope
+  unsigned gx = (unsigned)((maxel + kThreads - 1) / kThreads);
+  if (gx > 64) gx = 64;
+  dim3 grid(gx, (unsigned)n);
+  const FluidDev &f0 = c->fl[0].d, &f1 = c->fl[1].d;
+  if (unpack) k_halo<true><<<grid, kThreads, 0, c->stream>>>(g, f0, f1, d);
+  else k_halo<false><<<grid, kThreads, 0, c->stream>>>(g, f0, f1, d);
+  c->launches++;
+  AB_CUDA(cudaGetLastError());
+  AB_CUDA(cudaFreeAsync(d, c->stream));
+  return AB200_OK;
+}
+
+}  // namespace ab200

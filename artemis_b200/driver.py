@@ -1,0 +1,224 @@
+"""Host mirror of the reference's task functions and stage driver for the hot path.
+
+Same names, argument meaning and error behaviour as the reference:
+every task function takes the MeshData it acts on and returns a TaskStatus; failures of the
+C ABI surface as ``TaskStatus.fail`` from the task (and raise from the driver, the analogue
+of PARTHENON_FAIL).  All compute goes through libartemis_b200 -- there is no CPU path here.
+
+  Gas.CalculateFluxes / Gas.FluxSource / Gas.EstimateTimestepMesh   src/gas/gas.cpp:391-519
+  Dust.CalculateFluxes / Dust.FluxSource / Dust.EstimateTimestepMesh src/dust/dust.cpp:238-326
+  ArtemisUtils.ApplyUpdate / DeepCopyConservedData   src/utils/integrators/artemis_integrator.hpp
+  ArtemisDerived.SetAuxillaryFields / ConsToPrim / PrimToCons        src/derived/fill_derived.cpp
+  ArtemisDriver.Step / StepTasks / PostStepTasks                     src/artemis_driver.cpp:101-297
+"""
+from __future__ import annotations
+
+import ctypes as C
+from enum import Enum
+
+import numpy as np
+
+from . import capi
+from .enums import INTEGRATORS, Fluid
+from .meshdata import MeshData
+
+_DP = C.POINTER(C.c_double)
+_BIG = float(np.finfo(np.float64).max)
+
+
+class TaskStatus(Enum):  # P:basic_types.hpp:59
+    complete = 0
+    incomplete = 1
+    iterate = 2
+    fail = 3
+
+
+def _task(md: MeshData, name, *args) -> TaskStatus:
+    rc = getattr(md.L, name)(md.ctx, *args)
+    if rc != 0:
+        md.last_error = md.L.ab200_last_error().decode()
+        return TaskStatus.fail
+    return TaskStatus.complete
+
+
+class LowStorageIntegrator:
+    """gam0/gam1/beta tables of P:time_integration/low_storage_integrator.cpp."""
+
+    def __init__(self, name: str):
+        if name not in INTEGRATORS:
+            raise ValueError(f"integrator {name!r} not supported on the hot path")
+        self._name = name
+        st = INTEGRATORS[name]
+        self.nstages = len(st)
+        self.gam0 = [s[0] for s in st]
+        self.gam1 = [s[1] for s in st]
+        self.beta = [s[2] for s in st]
+        self.dt = 0.0
+
+    def GetName(self):
+        return self._name
+
+
+class _FluidPkg:
+    fluid = Fluid.gas
+
+    @classmethod
+    def CalculateFluxes(cls, md: MeshData, pcm: bool) -> TaskStatus:
+        return _task(md, "ab200_calculate_fluxes", int(cls.fluid), int(bool(pcm)))
+
+    @classmethod
+    def FluxSource(cls, md: MeshData, dt: float) -> TaskStatus:
+        return _task(md, "ab200_flux_source", int(cls.fluid), float(dt))
+
+    @classmethod
+    def EstimateTimestepMesh(cls, md: MeshData) -> float:
+        out = C.c_double()
+        capi.check(md.L, md.L.ab200_estimate_timestep(md.ctx, int(cls.fluid), C.byref(out)),
+                   f"{cls.__name__}::EstimateTimestepMesh")
+        return out.value
+
+
+class Gas(_FluidPkg):
+    fluid = Fluid.gas
+
+
+class Dust(_FluidPkg):
+    fluid = Fluid.dust
+
+
+class ArtemisUtils:
+    @staticmethod
+    def DeepCopyConservedData(md: MeshData) -> TaskStatus:
+        return _task(md, "ab200_deep_copy_conserved")
+
+    @staticmethod
+    def ApplyUpdate(md: MeshData, stage: int, integrator: LowStorageIntegrator) -> TaskStatus:
+        gam0 = integrator.gam0[stage - 1]
+        gam1 = integrator.gam1[stage - 1]
+        beta_dt = integrator.beta[stage - 1] * integrator.dt
+        return _task(md, "ab200_apply_update", gam0, gam1, beta_dt)
+
+
+class ArtemisDerived:
+    @staticmethod
+    def SetAuxillaryFields(md: MeshData) -> TaskStatus:
+        return _task(md, "ab200_set_auxillary_fields")
+
+    @staticmethod
+    def ConsToPrim(md: MeshData) -> TaskStatus:
+        return _task(md, "ab200_cons_to_prim")
+
+    @staticmethod
+    def PrimToCons(md: MeshData) -> TaskStatus:
+        return _task(md, "ab200_prim_to_cons")
+
+
+def AddBoundaryExchangeTasks(md: MeshData, comm=None) -> TaskStatus:
+    """parthenon::AddBoundaryExchangeTasks (P:bvals/comms/boundary_communication.cpp:433-444):
+    same-GPU neighbours in one kernel, remote neighbours through `comm`, then physical BCs."""
+    st = _task(md, "ab200_exchange_ghosts")
+    if st != TaskStatus.complete:
+        return st
+    if comm is not None:
+        comm.exchange(md)
+    return _task(md, "ab200_apply_physical_bcs")
+
+
+class ArtemisDriver:
+    """Stage driver for the hot path (uniform mesh; out-of-scope source terms absent).
+
+    mode = "tasks": one C-ABI call per reference task, in the reference's order.
+    mode = "fused": ab200_fused_stage + ghost-zone PrimToCons (the fast path).
+    """
+
+    def __init__(self, md: MeshData, integrator: str = "rk2", mode: str = "tasks",
+                 tlim: float = np.inf, nlim: int = -1, comm=None):
+        self.md = md
+        self.integrator = LowStorageIntegrator(integrator)
+        self.mode = mode
+        self.comm = comm
+        self.time = 0.0
+        self.ncycle = 0
+        self.dt = _BIG
+        self.tlim = tlim
+        self.nlim = nlim
+        self.do_gas = md.gas is not None
+        self.do_dust = md.dust is not None
+
+    @staticmethod
+    def _require(st: TaskStatus, md, what):
+        if st != TaskStatus.complete:
+            raise capi.AB200Error(f"{what}: {getattr(md, 'last_error', '')}")
+
+    # Mesh::Initialize after the pgen (P:mesh/mesh.cpp:783-814)
+    def Initialize(self):
+        md = self.md
+        self._require(ArtemisDerived.PrimToCons(md), md, "PostInitialization")
+        self._require(ArtemisDerived.ConsToPrim(md), md, "PreCommFillDerived")
+        self._require(AddBoundaryExchangeTasks(md, self.comm), md, "CommunicateBoundaries")
+        self._require(ArtemisDerived.PrimToCons(md), md, "FillDerived")
+        self.block_dt = self.EstimateTimestep()
+        self.SetGlobalTimeStep()
+
+    def EstimateTimestep(self) -> float:
+        dts = []
+        if self.do_gas:
+            dts.append(Gas.EstimateTimestepMesh(self.md))
+        if self.do_dust:
+            dts.append(Dust.EstimateTimestepMesh(self.md))
+        dt = min(dts)
+        if self.comm is not None:
+            dt = self.comm.allreduce_min(dt)
+        return dt
+
+    def SetGlobalTimeStep(self):
+        """EvolutionDriver::SetGlobalTimeStep, P:driver/driver.cpp:210-269."""
+        if self.dt < 0.1 * _BIG:
+            self.dt *= 2.0
+        self.dt = min(self.dt, self.block_dt)
+        if self.time < self.tlim and (self.tlim - self.time) < self.dt:
+            self.dt = self.tlim - self.time
+
+    def StepTasks(self):
+        md, integ = self.md, self.integrator
+        req = self._require
+        if self.mode == "tasks":
+            req(ArtemisUtils.DeepCopyConservedData(md), md, "DeepCopyConservedData")
+        for stage in range(1, integ.nstages + 1):
+            bdt = integ.beta[stage - 1] * integ.dt
+            do_pcm = (stage == 1) and (integ.GetName() == "vl2")
+            if self.mode == "tasks":
+                if self.do_gas:
+                    req(Gas.CalculateFluxes(md, do_pcm), md, "Gas::CalculateFluxes")
+                if self.do_dust:
+                    req(Dust.CalculateFluxes(md, do_pcm), md, "Dust::CalculateFluxes")
+                req(ArtemisUtils.ApplyUpdate(md, stage, integ), md, "ApplyUpdate")
+                if self.do_gas:
+                    req(Gas.FluxSource(md, bdt), md, "Gas::FluxSource")
+                if self.do_dust:
+                    req(Dust.FluxSource(md, bdt), md, "Dust::FluxSource")
+                req(ArtemisDerived.SetAuxillaryFields(md), md, "SetAuxillaryFields")
+                req(ArtemisDerived.ConsToPrim(md), md, "ConsToPrim")
+                req(AddBoundaryExchangeTasks(md, self.comm), md, "AddBoundaryExchangeTasks")
+                req(ArtemisDerived.PrimToCons(md), md, "PrimToCons")
+            else:
+                req(_task(md, "ab200_fused_stage", integ.gam0[stage - 1], integ.gam1[stage - 1],
+                          integ.beta[stage - 1], integ.dt, int(do_pcm), int(stage == 1), 0),
+                    md, "ab200_fused_stage")
+                req(AddBoundaryExchangeTasks(md, self.comm), md, "AddBoundaryExchangeTasks")
+                req(_task(md, "ab200_prim_to_cons_ghosts"), md, "PrimToCons(ghosts)")
+
+    def Step(self):
+        self.integrator.dt = self.dt        # PreStepTasks, artemis_driver.cpp:128-130
+        self.StepTasks()
+        self.block_dt = self.EstimateTimestep()   # PostStepTasks, :277-297
+        self.ncycle += 1
+        self.time += self.dt
+        self.SetGlobalTimeStep()
+
+    def KeepGoing(self):
+        return (self.time < self.tlim) and (self.nlim < 0 or self.ncycle < self.nlim)
+
+    def Execute(self):
+        while self.KeepGoing():
+            self.Step()

@@ -1,0 +1,214 @@
+/*
+ * ab200.h -- C ABI of libartemis_b200: the B200-native (sm_100a, hand-written fp64 CUDA)
+ * replacement for the data-parallel hot path of lanl/artemis.
+ *
+ * The reference has no FFI today: its hot path is a set of Parthenon *task functions*
+ * (TaskStatus f(MeshData<Real>*, ...)) added to the per-stage TaskList in
+ * src/artemis_driver.cpp:166-270.  Each entry point below replaces the body of one of those
+ * task functions; the file:line it replaces is cited on every declaration.  A ~150-line
+ * glue TU compiled inside Artemis flattens the SparsePack it already
+ * builds into the pointer tables of ab200_pack_desc and calls these functions.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no C++/torch/Kokkos types.
+ *  - Every function returns 0 on success, non-zero on failure (AB200_E*); the message is
+ *    available from ab200_last_error().  The glue maps non-zero to TaskStatus::fail /
+ *    PARTHENON_FAIL (P:basic_types.hpp:59).  Nothing throws across the boundary.
+ *  - The library BORROWS every state array (Parthenon owns them); it owns only its pointer
+ *    tables, metric tables, halo slabs and reduction scratch.
+ *  - All work is enqueued on the stream given at ab200_create (pass the raw cudaStream_t of
+ *    Kokkos::Cuda().cuda_stream(), or NULL for the legacy default stream) and is
+ *    asynchronous unless the function returns a host scalar.  Callable from any host
+ *    thread: every entry point does cudaSetDevice(ctx->device).
+ *  - There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Variable layout ("MeshBlockPack layout", P:interface/variable.cpp:112-128): each
+ * (block, pack-index) entry of a pointer table addresses one dense 3-D array
+ * [nk][nj][ni] (i fastest, ghosts included) in DEVICE memory.  Pack index conventions are
+ * the reference's (src/utils/fluxes/riemann/hllc.hpp:66-73), S = nspecies:
+ *    gas  prim: rho n | vel S+3n+d | pressure 4S+n | sie 5S+n            (6S entries)
+ *    gas  cons: rho n | mom S+3n+d | total_energy 4S+n | internal 5S+n   (6S entries)
+ *    dust prim: rho n | vel S+3n+d        dust cons: rho n | mom S+3n+d  (4S entries)
+ * flux[d] uses the cons numbering; flux(i) is the LOWER face of cell i
+ * (src/utils/fluxes/fluid_fluxes.hpp:114-121).  pflux[d] is the flux slot of
+ * gas.prim.pressure (interface pressure), vface[d] is gas.face.velocity element d with
+ * allocated dims fnk x fnj x fni (P:interface/metadata.cpp:378-387).
+ */
+#ifndef AB200_H_
+#define AB200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AB200_ABI_VERSION 1
+
+/* src/artemis.hpp:78-105 */
+enum { AB200_CARTESIAN = 0, AB200_CYLINDRICAL = 1, AB200_SPHERICAL1D = 2,
+       AB200_SPHERICAL2D = 3, AB200_SPHERICAL3D = 4, AB200_AXISYMMETRIC = 5 };
+enum { AB200_HLLC = 0, AB200_HLLE = 1, AB200_LLF = 2 };
+enum { AB200_PCM = 0, AB200_PLM = 1, AB200_PPM = 2 };
+enum { AB200_GAS = 0, AB200_DUST = 1 };
+enum { AB200_BC_PERIODIC = 0, AB200_BC_OUTFLOW = 1, AB200_BC_REFLECT = 2,
+       AB200_BC_NONE = 3 /* face handled by the caller (remote rank / user BC) */ };
+
+enum { AB200_OK = 0, AB200_EINVAL = 1, AB200_ECUDA = 2, AB200_ESTATE = 3, AB200_ENOMEM = 4 };
+
+typedef struct ab200_ctx ab200_ctx;
+
+/* Mesh/index description of one MeshData partition (all blocks share one shape).
+ * xmin/dx are Parthenon's UniformCartesian xmin_/dx_ per block
+ * (P:coordinates/uniform_cartesian.hpp:30-36): Xf(idx) = xmin + idx*dx. */
+typedef struct ab200_grid_desc {
+  int geom, ndim, nghost, nblocks;
+  int ni, nj, nk;             /* allocated cells per block, ghosts included */
+  int is, ie, js, je, ks, ke; /* interior bounds, inclusive                 */
+  int fni, fnj, fnk;          /* allocated dims of gas.face.velocity        */
+  const double *xmin;         /* HOST [nblocks][3]                          */
+  const double *dx;           /* HOST [nblocks][3]                          */
+} ab200_grid_desc;
+
+/* StateDescriptor params read by the hot path (src/gas/gas.cpp:59-208,
+ * src/dust/dust.cpp:44-100). */
+typedef struct ab200_fluid_desc {
+  int fluid, nspecies, recon, riemann;
+  double gm1, dfloor, siefloor, de_switch, cfl;
+} ab200_fluid_desc;
+
+/* HOST arrays of DEVICE pointers; entry [b*nvar + n] (or [b*S + n]). NULL tables are
+ * allowed for cons1/flux/pflux/vface: the library then allocates its own scratch when an
+ * entry point needs them. */
+typedef struct ab200_pack_desc {
+  double *const *prim;
+  double *const *cons0; /* u0 */
+  double *const *cons1; /* u1 */
+  double *const *flux[3];
+  double *const *pflux[3];
+  double *const *vface[3];
+} ab200_pack_desc;
+
+/* One ghost-zone buffer, the analogue of parthenon::BndInfo (P:bvals/comms/bnd_info.hpp,
+ * index ranges from CalcIndices P:bvals/comms/bnd_info.cpp:105-252).  The sub-box
+ * [sk..ek][sj..ej][si..ei] of `ncomp` consecutive pack entries starting at `var0` of block
+ * `block` is (un)packed to/from `buf` in [comp][k][j][i] order (i fastest,
+ * P:utils/indexer.hpp:119-131). */
+typedef struct ab200_bnd_desc {
+  int fluid, block, var0, ncomp;
+  int si, ei, sj, ej, sk, ek;
+  double *buf; /* DEVICE */
+} ab200_bnd_desc;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int ab200_abi_version(void);
+const char *ab200_last_error(void);
+int ab200_device_count(void);
+int ab200_create(ab200_ctx **ctx, int device, void *cuda_stream);
+int ab200_destroy(ab200_ctx *ctx);
+int ab200_synchronize(ab200_ctx *ctx);
+
+/* ---- binding (rebuilt when the SparsePack cache is invalidated,
+ *      P:interface/sparse_pack_base.cpp:320-344) ------------------------------------------ */
+int ab200_set_grid(ab200_ctx *ctx, const ab200_grid_desc *grid);
+int ab200_bind_pack(ab200_ctx *ctx, const ab200_fluid_desc *fluid, const ab200_pack_desc *pack);
+int ab200_unbind(ab200_ctx *ctx, int fluid);
+/* rotating_frame "omega" used by FluxSource (src/utils/fluxes/fluid_fluxes.hpp:433-437) */
+int ab200_set_rotating_frame(ab200_ctx *ctx, double omega);
+
+/* ---- task functions ---------------------------------------------------------------------- */
+/* Gas::CalculateFluxes / Dust::CalculateFluxes -> ArtemisUtils::CalculateFluxesImpl
+ * (src/gas/gas.cpp:473-494, src/dust/dust.cpp:281-298, fluid_fluxes.hpp:76-213) */
+int ab200_calculate_fluxes(ab200_ctx *ctx, int fluid, int pcm);
+/* ArtemisUtils::ApplyUpdate<GEOM> over every bound fluid
+ * (src/utils/integrators/artemis_integrator.hpp:56-110) */
+int ab200_apply_update(ab200_ctx *ctx, double gam0, double gam1, double beta_dt);
+/* Gas::FluxSource / Dust::FluxSource -> FluxSourceImpl
+ * (src/gas/gas.cpp:499-519, src/dust/dust.cpp:303-326, fluid_fluxes.hpp:298-420) */
+int ab200_flux_source(ab200_ctx *ctx, int fluid, double dt);
+/* ArtemisDerived::SetAuxillaryFields<GEOM> (src/derived/fill_derived.cpp:29-75) */
+int ab200_set_auxillary_fields(ab200_ctx *ctx);
+/* ArtemisDerived::ConsToPrim<GEOM> (fill_derived.cpp:81-167), interior */
+int ab200_cons_to_prim(ab200_ctx *ctx);
+/* ArtemisDerived::PrimToCons<T,GEOM> (fill_derived.cpp:172-277), entire domain */
+int ab200_prim_to_cons(ab200_ctx *ctx);
+/* ArtemisUtils::DeepCopyConservedData u1 <- u0 (artemis_integrator.hpp:30-51) */
+int ab200_deep_copy_conserved(ab200_ctx *ctx);
+/* Gas/Dust::EstimateTimestepMesh<GEOM> (src/gas/gas.cpp:391-468, src/dust/dust.cpp:238-276):
+ * returns cfl * min over the partition in *dt_host (synchronises the stream). */
+int ab200_estimate_timestep(ab200_ctx *ctx, int fluid, double *dt_host);
+
+/* ---- fused fast path ----------------------------------------------------------------------
+ * One call == CalculateFluxes + ApplyUpdate + FluxSource + SetAuxillaryFields + ConsToPrim +
+ * (interior part of) PrimToCons for every bound fluid, i.e. tasks
+ * src/artemis_driver.cpp:184-255 plus the interior of :261, valid when no out-of-scope
+ * source term (drag/gravity/rotating-frame/cooling/diffusion, :217-248) sits in between.
+ * One fused pass per direction: reconstruct -> Riemann -> flux difference -> update; flux
+ * arrays are never materialised.  If stage1_copy != 0 the pass also writes u1 <- u0
+ * (DeepCopyConservedData folded in; requires gam0 == 0, gam1 == 1).
+ * dt is read from the device scalar ab200_dt_device() when use_device_dt != 0. */
+int ab200_fused_stage(ab200_ctx *ctx, double gam0, double gam1, double beta, double dt,
+                      int pcm, int stage1_copy, int use_device_dt);
+/* PrimToCons restricted to ghost zones (completes :261 after the exchange). */
+int ab200_prim_to_cons_ghosts(ab200_ctx *ctx);
+
+/* ---- timestep on the device (replaces the per-cycle host round trip of
+ *      P:driver/driver.cpp:210-269 + MPI_Allreduce :237) ------------------------------------ */
+/* min over all bound fluids of cfl*min_dt -> device scalar new_dt (no sync) */
+int ab200_estimate_timestep_device(ab200_ctx *ctx);
+/* dt = min(2*dt, new_dt); clamp to tlim - time; time += old dt handled by caller flag.
+ * Mirrors EvolutionDriver::SetGlobalTimeStep; runs on the device, no sync. */
+int ab200_set_global_timestep_device(ab200_ctx *ctx, double tlim, int advance_time);
+double *ab200_dt_device(ab200_ctx *ctx);     /* device double[4]: dt, new_dt, time, ncycle */
+int ab200_read_time_state(ab200_ctx *ctx, double *host4); /* syncs */
+int ab200_write_time_state(ab200_ctx *ctx, const double *host4);
+
+/* ---- ghost zones --------------------------------------------------------------------------
+ * Pack / unpack kernels of SendBoundBufs / SetBounds
+ * (P:bvals/comms/boundary_communication.cpp:95-140, 273-334) driven by the caller's BndInfo. */
+int ab200_halo_pack(ab200_ctx *ctx, const ab200_bnd_desc *bnd, int n);
+int ab200_halo_unpack(ab200_ctx *ctx, const ab200_bnd_desc *bnd, int n);
+/* Library-managed same-level exchange for a uniform nbx*nby*nbz lattice of the bound blocks
+ * (block id = lx + nbx*(ly + nby*lz)).
+ *  ab200_exchange_ghosts: same-GPU neighbours are filled ghost<-interior in ONE kernel (no
+ *    intermediate buffer; the reference's BuffCommType::both case,
+ *    P:bvals/comms/build_boundary_buffers.cpp:148-151).  Neighbours across a face flagged
+ *    AB200_BC_NONE (another rank) are left to ab200_halo_pack/unpack.
+ *  ab200_apply_physical_bcs: outflow / reflect (P:bvals/boundary_conditions_generic.hpp:
+ *    178-256) on lattice faces flagged OUTFLOW/REFLECT, in the reference's face order
+ *    ix1, ox1, ix2, ox2, ix3, ox3; call it after every neighbour (local and remote) is set. */
+int ab200_set_topology(ab200_ctx *ctx, int nbx, int nby, int nbz, const int bc[6]);
+int ab200_exchange_ghosts(ab200_ctx *ctx);
+int ab200_apply_physical_bcs(ab200_ctx *ctx);
+
+/* ---- host-buffer entry point (a CPU-resident Parthenon build, and bench.py's e2e leg) ----
+ * Runs `ncycles` full rk/vl cycles on state held in HOST memory: uploads the gas (and dust)
+ * primitives [nblocks][nvar][nk][nj][ni], rebuilds conserved state with PrimToCons, advances
+ * (fused path + library exchange + device dt), downloads primitives and conserved u0.
+ * integrator: 0 rk1, 1 rk2, 2 vl2, 3 rk3.  dt_io: in = current dt (<=0: estimate), out = next. */
+int ab200_cycles_host(ab200_ctx *ctx, int integrator, int ncycles, double *dt_io,
+                      double *gas_prim_host, double *gas_cons_host, double *dust_prim_host,
+                      double *dust_cons_host);
+
+/* Device-resident driver loop: `ncycles` cycles of {per stage: ab200_fused_stage ->
+ * ab200_exchange_ghosts -> ab200_apply_physical_bcs -> ab200_prim_to_cons_ghosts} followed by
+ * ab200_estimate_timestep_device + ab200_set_global_timestep_device, i.e.
+ * ArtemisDriver::Step (src/artemis_driver.cpp:101-121) for a single-rank uniform mesh with
+ * no host round trip.  State must already be bound; dt/time live in ab200_dt_device(). */
+int ab200_run_cycles(ab200_ctx *ctx, int integrator, int ncycles, double tlim);
+
+/* ---- utilities ---------------------------------------------------------------------------- */
+int ab200_malloc(ab200_ctx *ctx, void **dptr, size_t bytes);
+int ab200_free(ab200_ctx *ctx, void *dptr);
+int ab200_memcpy_h2d(ab200_ctx *ctx, void *dst, const void *src, size_t bytes);
+int ab200_memcpy_d2h(ab200_ctx *ctx, void *dst, const void *src, size_t bytes);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+long long ab200_launch_count(ab200_ctx *ctx);
+/* CUDA-event timing of the work enqueued between begin/end on the context's stream (ms) */
+int ab200_timer_begin(ab200_ctx *ctx);
+int ab200_timer_end(ab200_ctx *ctx, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AB200_H_ */

@@ -1,0 +1,8 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,memory.total --format=csv > gpurun_out/gpu.txt
+python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/smoke.log 2>&1
+echo "smoke rc=$?" >> gpurun_out/smoke.log
+tail -5 gpurun_out/smoke.log
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+tail -40 gpurun_out/pytest_gpu.log

@@ -1,0 +1,185 @@
+"""GPU parity over whole integrator cycles, through the host mirror of ArtemisDriver.
+
+north_star tolerances: per-zone relative difference <= 1e-12 after one cycle and <= 1e-9
+after 100 cycles against the reference's implementation (the pinned oracle), and identical
+linear-wave L1 error / convergence order."""
+import numpy as np
+import pytest
+
+from artemis_b200 import pgen
+from artemis_b200.driver import ArtemisDriver
+from artemis_b200.enums import BoundaryFlag, Coordinates, Fluid, ReconstructionMethod, RSolver
+from artemis_b200.mesh import UniformMesh
+from artemis_b200.meshdata import MeshData
+from artemis_b200.params import FluidParams
+from oracle.oracle_py import OracleSim
+from tests.helpers import dust_params, gas_params, make_mesh, random_prim, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_1 = 1e-12    # one cycle
+TOL_100 = 1e-9   # hundred cycles
+
+# golden RMS-L1 numbers measured from the real reference
+GOLDEN = {("plm", 16): 6.727418e-07, ("plm", 32): 1.875944e-07,
+          ("ppm", 16): 3.780974e-07, ("ppm", 32): 1.620378e-07}
+
+
+def _linwave_mesh(res, ng=4):
+    return UniformMesh(nx=(res, res // 2, res // 2), xmin=(0, 0, 0), xmax=(3.0, 1.5, 1.5),
+                       block_nx=(res // 4,) * 3, nghost=ng)
+
+
+def _linwave_gas(recon, rs="hllc"):
+    return FluidParams(Fluid.gas, Coordinates.cartesian, ReconstructionMethod[recon],
+                       RSolver[rs], cfl=0.9, nspecies=1, dfloor=1e-20, gamma=1.66666666667)
+
+
+def _run_linwave(res, recon, mode, variant, wave_flag=0, rs="hllc"):
+    mesh = _linwave_mesh(res)
+    gp = _linwave_gas(recon, rs)
+    prim, lw = pgen.linear_wave(mesh, gp.gamma, wave_flag, 1e-6, 0.0)
+    md = MeshData(mesh, gas=gp, variant=variant, materialize_fluxes=(mode == "tasks"))
+    md.gas.prim.set(prim)
+    drv = ArtemisDriver(md, "rk2", mode=mode, tlim=lw.tlim, nlim=1000)
+    drv.Initialize()
+    drv.Execute()
+    u0 = md.gas.u0.get()
+    rms, l1 = pgen.linear_wave_errors(mesh, lw, u0)
+    md.close()
+    return rms, l1, drv.ncycle, u0
+
+
+@pytest.mark.parametrize("recon", ["plm", "ppm"])
+def test_linwave_tasks_strict_is_bit_identical_to_oracle(recon):
+    res = 16
+    mesh = _linwave_mesh(res)
+    gp = _linwave_gas(recon)
+    prim, lw = pgen.linear_wave(mesh, gp.gamma, 0, 1e-6, 0.0)
+    osim = OracleSim(mesh, gas=gp)
+    osim.gas.prim[:] = prim
+    osim.tlim, osim.nlim = lw.tlim, 1000
+    osim.initialize()
+    osim.run()
+    rms, l1, ncycle, u0 = _run_linwave(res, recon, "tasks", "strict")
+    assert ncycle == osim.ncycle == 18
+    assert np.array_equal(u0, osim.gas.u0)
+    assert f"{rms:.6e}" == f"{GOLDEN[(recon, res)]:.6e}"
+
+
+@pytest.mark.parametrize("mode,variant", [("tasks", "fast"), ("fused", "fast"), ("fused", "strict")])
+@pytest.mark.parametrize("recon", ["plm", "ppm"])
+def test_linwave_l1_error_and_order_match_reference(recon, mode, variant):
+    errs = {}
+    for res in (16, 32):
+        rms, l1, ncycle, _ = _run_linwave(res, recon, mode, variant)
+        assert ncycle == (18 if res == 16 else 36)
+        # identical L1 error: all 7 published digits of the reference's number
+        assert abs(rms - GOLDEN[(recon, res)]) <= 0.6e-6 * GOLDEN[(recon, res)], (rms, res)
+        errs[res] = rms
+    ratio = errs[32] / errs[16]
+    assert abs(ratio - GOLDEN[(recon, 32)] / GOLDEN[(recon, 16)]) < 1e-6
+    # the reference's own regression thresholds, tst/scripts/hydro/linwave.py:96-106
+    assert errs[32] <= (2.23e-7 if recon == "plm" else 1.75e-7)
+    assert ratio <= (0.29 if recon == "plm" else 0.44)
+
+
+def test_linwave_left_right_sound_waves_identical_errors():
+    """tst/scripts/hydro/linwave.py:135-143: L- and R-going errors must be bit-identical."""
+    # the reference compares the "%e"-formatted numbers of <id>-errs.dat
+    # (src/pgen/linear_wave.hpp:365-369); the strict build is identical to the last bit.
+    for mode, variant in (("fused", "fast"), ("tasks", "fast")):
+        l = _run_linwave(16, "ppm", mode, variant, wave_flag=0)[0]
+        r = _run_linwave(16, "ppm", mode, variant, wave_flag=4)[0]
+        assert "%e" % l == "%e" % r
+    l = _run_linwave(16, "ppm", "tasks", "strict", wave_flag=0)[0]
+    r = _run_linwave(16, "ppm", "tasks", "strict", wave_flag=4)[0]
+    assert l == r
+
+
+def _twin_run(mesh, gp, dp, mode, variant, ncycles, integrator="rk2", seed=3, prim=None):
+    osim = OracleSim(mesh, gas=gp, dust=dp, integrator=integrator)
+    md = MeshData(mesh, gas=gp, dust=dp, variant=variant, materialize_fluxes=(mode == "tasks"))
+    for which, fp in ((Fluid.gas, gp), (Fluid.dust, dp)):
+        if fp is None:
+            continue
+        p = prim if (prim is not None and which == Fluid.gas) else random_prim(
+            mesh, fp, seed=seed + int(which), shocks=False)
+        (osim.gas if which == Fluid.gas else osim.dust).prim[:] = p
+        md.fluid(which).prim.set(p)
+    osim.nlim = ncycles
+    osim.initialize()
+    drv = ArtemisDriver(md, integrator, mode=mode, nlim=ncycles)
+    drv.Initialize()
+    assert drv.dt == osim.dt or abs(drv.dt - osim.dt) < 1e-14 * osim.dt
+    osim.run()
+    drv.Execute()
+    out = []
+    for of, df in zip(osim.fluids, md.fluids):
+        out.append((rel_err(df.u0.get(), of.u0), rel_err(df.prim.get(), of.prim)))
+    md.close()
+    return out, drv, osim
+
+
+CYCLE_CASES = [
+    (Coordinates.cartesian, 3, "ppm", "hllc", "rk2"),
+    (Coordinates.cartesian, 3, "plm", "hlle", "vl2"),
+    (Coordinates.cartesian, 2, "ppm", "llf", "rk3"),
+    (Coordinates.cylindrical, 3, "plm", "hllc", "rk2"),
+    (Coordinates.axisymmetric, 2, "plm", "hlle", "rk2"),
+    (Coordinates.spherical3D, 3, "ppm", "hlle", "rk2"),
+    (Coordinates.spherical2D, 2, "plm", "hllc", "vl2"),
+    (Coordinates.spherical1D, 1, "ppm", "hllc", "rk2"),
+]
+
+
+@pytest.mark.parametrize("mode", ["tasks", "fused"])
+@pytest.mark.parametrize("coords,ndim,recon,rs,integ", CYCLE_CASES)
+def test_one_cycle_within_1e12(coords, ndim, recon, rs, integ, mode):
+    bcs = (BoundaryFlag.outflow,) * 6 if coords != Coordinates.cartesian else None
+    mesh = make_mesh(coords, ndim, bcs=bcs)
+    gp = gas_params(coords, recon, rs)
+    dp = dust_params(coords, recon, "hlle", S=2)
+    errs, drv, osim = _twin_run(mesh, gp, dp, mode, "fast", 1, integ)
+    for eu, ep in errs:
+        assert eu <= TOL_1 and ep <= TOL_1, (errs, coords, mode)
+
+
+@pytest.mark.parametrize("mode", ["tasks", "fused"])
+def test_hundred_cycles_blast_within_1e9(mode):
+    """3D Sedov blast (config 2 numerics: PPM+HLLC, rk2, outflow) at 32^3, 100 cycles."""
+    mesh = UniformMesh(nx=(32, 32, 32), xmin=(-1, -1, -1), xmax=(1, 1, 1), block_nx=(16, 16, 16),
+                       nghost=4, bcs=(BoundaryFlag.outflow,) * 6)
+    gp = FluidParams(Fluid.gas, Coordinates.cartesian, ReconstructionMethod.ppm, RSolver.hllc,
+                     cfl=0.3, nspecies=1, dfloor=1e-10, gamma=1.4, siefloor=1e-10)
+    prim = pgen.blast(mesh, gp.gamma, d0=1.0, p0=1e-5, internal_energy=1.0, radius=0.2,
+                      samples=0)
+    errs, drv, osim = _twin_run(mesh, gp, None, mode, "fast", 100, prim=prim)
+    assert drv.ncycle == osim.ncycle == 100
+    assert abs(drv.time - osim.time) <= 1e-12 * osim.time
+    for eu, ep in errs:
+        assert eu <= TOL_100 and ep <= TOL_100, errs
+
+
+def test_device_resident_driver_matches_host_driven():
+    """ab200_run_cycles (dt on the device, no host round trip) == the host-driven fused loop."""
+    mesh = make_mesh(Coordinates.cartesian, 3, bcs=(BoundaryFlag.outflow,) * 6)
+    gp = gas_params(Coordinates.cartesian, "ppm", "hllc")
+    prim = random_prim(mesh, gp, seed=11, shocks=False)
+    md1 = MeshData(mesh, gas=gp, materialize_fluxes=False)
+    md1.gas.prim.set(prim)
+    d1 = ArtemisDriver(md1, "rk2", mode="fused", nlim=5)
+    d1.Initialize()
+    d1.Execute()
+    md2 = MeshData(mesh, gas=gp, materialize_fluxes=False)
+    md2.gas.prim.set(prim)
+    d2 = ArtemisDriver(md2, "rk2", mode="fused")
+    d2.Initialize()
+    md2.set_time_state(d2.dt)
+    md2.call("ab200_run_cycles", 1, 5, float(np.finfo(np.float64).max))
+    ts = md2.time_state()
+    assert ts[3] == 5 and abs(ts[2] - d1.time) <= 1e-15 * d1.time
+    assert np.array_equal(md1.gas.u0.get(), md2.gas.u0.get())
+    assert np.array_equal(md1.gas.prim.get(), md2.gas.prim.get())
+    md1.close()
+    md2.close()
