@@ -24,7 +24,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 
 # (source, extra defines, object suffix)
 UNITS = [("api.cu", [], ""), ("tasks.cu", [], ""), ("halo.cu", [], ""),
-         ("fused_dispatch.cu", [], ""), ("host_path.cu", [], "")]
+         ("fused_dispatch.cu", [], ""), ("host_path.cu", [], ""), ("tma_maps.cu", [], "")]
 UNITS += [("fused.cu", [f"-DAB_GEOM={g}"], f"_g{g}") for g in range(6)]
 UNITS += [("tasks_flux.cu", [f"-DAB_GEOM={g}"], f"_g{g}") for g in range(6)]
 
@@ -80,7 +80,7 @@ def build_variant(variant: str, flags, verbose=False, jobs=None):
 
 
 def build_all(verbose=False):
-    fast = build_variant("fast", [], verbose)
+    fast = build_variant("fast", ["-DAB200_FAST_MATH"], verbose)
     strict = build_variant("strict", ["--fmad=false"], verbose)
     return fast, strict
 

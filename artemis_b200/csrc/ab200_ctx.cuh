@@ -39,7 +39,13 @@ struct FluidHost {
   int n_ghost = 0;
   int *ghost_vars = nullptr;  // device
   int *ghost_vdir = nullptr;  // device
+  // TMA staging of the fused passes: CUtensorMap[3 kinds][nb*nvar] per direction (device)
+  bool tma_tried = false, tma_ready = false;
+  void *tma_maps[3] = {nullptr, nullptr, nullptr};
+  int tma_np[3] = {0, 0, 0};
 };
+int ensure_tma(ab200_ctx *c, int fluid, int max_threads);
+void release_tma(FluidHost &fh);
 
 struct Topology {
   bool set = false;

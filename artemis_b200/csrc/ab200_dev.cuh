@@ -37,6 +37,7 @@ struct GridDev {
 struct FluidDev {
   int fluid, S, nvar, recon, riemann;
   double gm1, dfloor, siefloor, de_switch, cfl;
+  double igm1, gamma, alpha;  // host-computed: 1/gm1, gm1+1, (gamma+1)/(2 gamma)
   double *const *prim;
   double *const *u0;
   double *const *u1;
@@ -46,6 +47,38 @@ struct FluidDev {
 };
 
 AB_D double sqr(double x) { return x * x; }
+
+// Division.  The strict build keeps IEEE division (bit-identical to the reference).  The
+// default build uses a branch-free reciprocal (MUFU.RCP64H seed + 2 Newton steps) and one
+// residual correction: <= 1 ulp from the IEEE quotient for normal operands, no slow-path
+// CALL (nvcc's IEEE sequence branches to a subroutine whenever the numerator is zero or tiny,
+// which is every face of a quiescent region), and 0/0 or x/0 still produce NaN/Inf-class
+// values that the callers' selects discard exactly like the reference does.
+#ifdef AB200_FAST_MATH
+AB_D double drcp(double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+AB_D double ddiv(double a, double b) {
+  const double r = drcp(b);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
+#else
+AB_D double drcp(double b) { return 1.0 / b; }
+AB_D double ddiv(double a, double b) { return a / b; }
+#endif
+
+// Uniform EOS constants, computed once on the host with the reference's expressions
+// (hllc.hpp:76-78: igm1 = 1/gm1, gamma = gm1+1, alpha = (gamma+1)/(2 gamma)).
+struct EosConsts {
+  double gm1, igm1, gamma, alpha;
+};
 // std::max / std::min semantics of the reference (NaN-free inputs)
 AB_D double dmax(double a, double b) { return a > b ? a : b; }
 AB_D double dmin(double a, double b) { return b < a ? b : a; }
@@ -218,7 +251,7 @@ AB_D void plm(double q_im1, double q_i, double q_ip1, double &ql_ip1, double &qr
   const double dql = (q_i - q_im1);
   const double dqr = (q_ip1 - q_i);
   const double dq2 = dql * dqr;
-  double dqm = dq2 / (dql + dqr);
+  double dqm = ddiv(dq2, dql + dqr);
   if (dq2 <= 0.0) dqm = 0.0;
   ql_ip1 = q_i + dqm;
   qr_i = q_i - dqm;
@@ -240,8 +273,13 @@ AB_D void plm_g(double q_im1, double q_i, double q_ip1, double &ql_ip1, double &
 // ppm.hpp:32-66
 AB_D void ppm4(double q_im2, double q_im1, double q_i, double q_ip1, double q_ip2,
                double &ql_ip1, double &qr_i) {
+#ifdef AB200_FAST_MATH
+  double qlv = (7. * (q_i + q_im1) - (q_im2 + q_ip1)) * (1.0 / 12.0);
+  double qrv = (7. * (q_i + q_ip1) - (q_im1 + q_ip2)) * (1.0 / 12.0);
+#else
   double qlv = (7. * (q_i + q_im1) - (q_im2 + q_ip1)) / 12.0;
   double qrv = (7. * (q_i + q_ip1) - (q_im1 + q_ip2)) / 12.0;
+#endif
   qlv = dmax(qlv, dmin(q_i, q_im1));
   qlv = dmin(qlv, dmax(q_i, q_im1));
   qrv = dmax(qrv, dmin(q_i, q_ip1));
@@ -286,25 +324,25 @@ struct Riemann;
 
 template <>
 struct Riemann<AB200_HLLC, AB200_GAS> {  // hllc.hpp:76-180
-  static AB_D void solve(double gm1, const double *wl, const double *wr, double *out) {
+  static AB_D void solve(const EosConsts &eos, const double *wl, const double *wr, double *out) {
     const double wl_idn = wl[0], wl_ivx = wl[1], wl_ivy = wl[2], wl_ivz = wl[3],
                  wl_ipr = wl[4], wl_ise = wl[5];
     const double wr_idn = wr[0], wr_ivx = wr[1], wr_ivy = wr[2], wr_ivz = wr[3],
                  wr_ipr = wr[4], wr_ise = wr[5];
-    const double igm1 = 1.0 / gm1;
-    const double gamma = gm1 + 1.0;
-    const double alpha = (gamma + 1.0) / (2.0 * gamma);
+    const double igm1 = eos.igm1;
+    const double gamma = eos.gamma;
+    const double alpha = eos.alpha;
     double qa, qb, qc, qd, qe, qf;
-    qa = sqrt(gamma * wl_ipr / wl_idn);
-    qb = sqrt(gamma * wr_ipr / wr_idn);
+    qa = sqrt(ddiv(gamma * wl_ipr, wl_idn));
+    qb = sqrt(ddiv(gamma * wr_ipr, wr_idn));
     const double el =
         wl_ipr * igm1 + 0.5 * wl_idn * (sqr(wl_ivx) + sqr(wl_ivy) + sqr(wl_ivz));
     const double er =
         wr_ipr * igm1 + 0.5 * wr_idn * (sqr(wr_ivx) + sqr(wr_ivy) + sqr(wr_ivz));
     qc = 0.25 * (wl_idn + wr_idn) * (qa + qb);
     qd = 0.5 * (wl_ipr + wr_ipr + (wl_ivx - wr_ivx) * qc);
-    qe = (qd <= wl_ipr) ? 1.0 : sqrt(1.0 + alpha * ((qd / wl_ipr) - 1.0));
-    qf = (qd <= wr_ipr) ? 1.0 : sqrt(1.0 + alpha * ((qd / wr_ipr) - 1.0));
+    qe = (qd <= wl_ipr) ? 1.0 : sqrt(1.0 + alpha * (ddiv(qd, wl_ipr) - 1.0));
+    qf = (qd <= wr_ipr) ? 1.0 : sqrt(1.0 + alpha * (ddiv(qd, wr_ipr) - 1.0));
     const double sl = wl_ivx - qa * qe;
     const double sr = wr_ivx + qb * qf;
     qa = sr > 0.0 ? sr : 1.0e-20;
@@ -315,8 +353,14 @@ struct Riemann<AB200_HLLC, AB200_GAS> {  // hllc.hpp:76-180
     qd = wr_ipr + qf * wr_idn * wr_ivx;
     const double ml = wl_idn * qe;
     const double mr = -(wr_idn * qf);
+#ifdef AB200_FAST_MATH
+    const double rm = drcp(ml + mr);
+    const double am = (qc - qd) * rm;
+    double cp = (ml * qd + mr * qc) * rm;
+#else
     const double am = (qc - qd) / (ml + mr);
     double cp = (ml * qd + mr * qc) / (ml + mr);
+#endif
     cp = cp > 0.0 ? cp : 0.0;
     qe = wl_idn * (wl_ivx - qb);
     qf = wr_idn * (wr_ivx - qa);
@@ -326,6 +370,15 @@ struct Riemann<AB200_HLLC, AB200_GAS> {  // hllc.hpp:76-180
     const double flmz = qe * wl_ivz, frmz = qf * wr_ivz;
     const double fle = el * (wl_ivx - qb) + wl_ipr * wl_ivx;
     const double fre = er * (wr_ivx - qa) + wr_ipr * wr_ivx;
+#ifdef AB200_FAST_MATH
+    {
+      const bool pos = (am >= 0.0);
+      const double rw = drcp(pos ? (am - qb) : (qa - am));
+      qc = pos ? am * rw : 0.0;
+      qd = pos ? 0.0 : -am * rw;
+      qe = pos ? -qb * rw : qa * rw;
+    }
+#else
     if (am >= 0.0) {
       qc = am / (am - qb);
       qd = 0.0;
@@ -335,6 +388,7 @@ struct Riemann<AB200_HLLC, AB200_GAS> {  // hllc.hpp:76-180
       qd = -am / (qa - am);
       qe = qa / (qa - am);
     }
+#endif
     out[6] = qc * wl_ipr + qd * wr_ipr + qe * cp;
     const double frho = qc * fld + qd * frd;
     out[0] = frho;
@@ -343,25 +397,25 @@ struct Riemann<AB200_HLLC, AB200_GAS> {  // hllc.hpp:76-180
     out[3] = qc * flmz + qd * frmz;
     out[4] = qc * fle + qd * fre + qe * cp * am;
     out[5] = frho * ((frho >= 0.0) ? wl_ise : wr_ise);
-    out[7] = frho / ((frho >= 0.0) ? wl_idn : wr_idn);
+    out[7] = ddiv(frho, (frho >= 0.0) ? wl_idn : wr_idn);
   }
 };
 
 template <int FLUID>
 struct Riemann<AB200_HLLE, FLUID> {  // hlle.hpp:92-220
-  static AB_D void solve(double gm1, const double *wl, const double *wr, double *out) {
+  static AB_D void solve(const EosConsts &eos, const double *wl, const double *wr, double *out) {
     constexpr bool gas = (FLUID == AB200_GAS);
     const double wl_idn = wl[0], wl_ivx = wl[1], wl_ivy = wl[2], wl_ivz = wl[3];
     const double wr_idn = wr[0], wr_ivx = wr[1], wr_ivy = wr[2], wr_ivz = wr[3];
     double wl_ipr = 0, wr_ipr = 0, wl_ise = 0, wr_ise = 0, igm1 = 0, gamma = 0;
     if (gas) {
       wl_ipr = wl[4]; wl_ise = wl[5]; wr_ipr = wr[4]; wr_ise = wr[5];
-      igm1 = 1.0 / gm1;
-      gamma = gm1 + 1.0;
+      igm1 = eos.igm1;
+      gamma = eos.gamma;
     }
     const double sqrtdl = sqrt(wl_idn);
     const double sqrtdr = sqrt(wr_idn);
-    const double isdlpdr = 1.0 / (sqrtdl + sqrtdr);
+    const double isdlpdr = drcp(sqrtdl + sqrtdr);
     const double wroe_ivx = (sqrtdl * wl_ivx + sqrtdr * wr_ivx) * isdlpdr;
     const double wroe_ivy = (sqrtdl * wl_ivy + sqrtdr * wr_ivy) * isdlpdr;
     const double wroe_ivz = (sqrtdl * wl_ivz + sqrtdr * wr_ivz) * isdlpdr;
@@ -369,14 +423,14 @@ struct Riemann<AB200_HLLE, FLUID> {  // hlle.hpp:92-220
     if (gas) {
       el = wl_ipr * igm1 + 0.5 * wl_idn * (sqr(wl_ivx) + sqr(wl_ivy) + sqr(wl_ivz));
       er = wr_ipr * igm1 + 0.5 * wr_idn * (sqr(wr_ivx) + sqr(wr_ivy) + sqr(wr_ivz));
-      hroe = ((el + wl_ipr) / sqrtdl + (er + wr_ipr) / sqrtdr) * isdlpdr;
+      hroe = (ddiv(el + wl_ipr, sqrtdl) + ddiv(er + wr_ipr, sqrtdr)) * isdlpdr;
     }
     double qa = 0, qb = 0, sl, sr;
     if (gas) {
-      qa = sqrt(gamma * wl_ipr / wl_idn);
-      qb = sqrt(gamma * wr_ipr / wr_idn);
+      qa = sqrt(ddiv(gamma * wl_ipr, wl_idn));
+      qb = sqrt(ddiv(gamma * wr_ipr, wr_idn));
       double a = hroe - 0.5 * (sqr(wroe_ivx) + sqr(wroe_ivy) + sqr(wroe_ivz));
-      a = (a < 0.0) ? 0.0 : sqrt(gm1 * a);
+      a = (a < 0.0) ? 0.0 : sqrt(eos.gm1 * a);
       const double sla = wroe_ivx - a;
       const double slb = wl_ivx - qa;
       const double sra = wroe_ivx + a;
@@ -401,7 +455,7 @@ struct Riemann<AB200_HLLE, FLUID> {  // hlle.hpp:92-220
       fr_e = er * qb + wr_ipr * wr_ivx;
     }
     qa = 0.0;
-    if (bp != bm) qa = 0.5 * (bp + bm) / (bp - bm);
+    if (bp != bm) qa = ddiv(0.5 * (bp + bm), bp - bm);
     if (gas) out[6] = 0.5 * (wl_ipr + wr_ipr) + qa * (wl_ipr - wr_ipr);
     const double frho = 0.5 * (fl_d + fr_d) + qa * (fl_d - fr_d);
     out[0] = frho;
@@ -411,22 +465,22 @@ struct Riemann<AB200_HLLE, FLUID> {  // hlle.hpp:92-220
     if (gas) {
       out[4] = 0.5 * (fl_e + fr_e) + qa * (fl_e - fr_e);
       out[5] = frho * ((frho >= 0.0) ? wl_ise : wr_ise);
-      out[7] = frho / ((frho >= 0.0) ? wl_idn : wr_idn);
+      out[7] = ddiv(frho, (frho >= 0.0) ? wl_idn : wr_idn);
     }
   }
 };
 
 template <int FLUID>
 struct Riemann<AB200_LLF, FLUID> {  // llf.hpp:87-168
-  static AB_D void solve(double gm1, const double *wl, const double *wr, double *out) {
+  static AB_D void solve(const EosConsts &eos, const double *wl, const double *wr, double *out) {
     constexpr bool gas = (FLUID == AB200_GAS);
     const double wl_idn = wl[0], wl_ivx = wl[1], wl_ivy = wl[2], wl_ivz = wl[3];
     const double wr_idn = wr[0], wr_ivx = wr[1], wr_ivy = wr[2], wr_ivz = wr[3];
     double wl_ipr = 0, wr_ipr = 0, wl_ise = 0, wr_ise = 0, igm1 = 0, gamma = 0;
     if (gas) {
       wl_ipr = wl[4]; wl_ise = wl[5]; wr_ipr = wr[4]; wr_ise = wr[5];
-      igm1 = 1.0 / gm1;
-      gamma = gm1 + 1.0;
+      igm1 = eos.igm1;
+      gamma = eos.gamma;
     }
     double qa = wl_idn * wl_ivx;
     double qb = wr_idn * wr_ivx;
@@ -442,8 +496,8 @@ struct Riemann<AB200_LLF, FLUID> {  // llf.hpp:87-168
     }
     double a;
     if (gas) {
-      qa = sqrt(gamma * wl_ipr / wl_idn);
-      qb = sqrt(gamma * wr_ipr / wr_idn);
+      qa = sqrt(ddiv(gamma * wl_ipr, wl_idn));
+      qb = sqrt(ddiv(gamma * wr_ipr, wr_idn));
       a = dmax((fabs(wl_ivx) + qa), (fabs(wr_ivx) + qb));
     } else {
       a = dmax(fabs(wl_ivx), fabs(wr_ivx));
@@ -463,7 +517,7 @@ struct Riemann<AB200_LLF, FLUID> {  // llf.hpp:87-168
     if (gas) {
       out[4] = 0.5 * (fsum_e - du_e);
       out[5] = frho * ((frho >= 0.0) ? wl_ise : wr_ise);
-      out[7] = frho / ((frho >= 0.0) ? wl_idn : wr_idn);
+      out[7] = ddiv(frho, (frho >= 0.0) ? wl_idn : wr_idn);
     }
   }
 };
@@ -471,7 +525,7 @@ struct Riemann<AB200_LLF, FLUID> {  // llf.hpp:87-168
 // HLLC is gas-only (hllc.hpp:63); Dust::Initialize rejects it (src/dust/dust.cpp:76-85).
 template <>
 struct Riemann<AB200_HLLC, AB200_DUST> {
-  static AB_D void solve(double, const double *, const double *, double *) {}
+  static AB_D void solve(const EosConsts &, const double *, const double *, double *) {}
 };
 
 }  // namespace ab200

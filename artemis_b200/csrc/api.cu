@@ -237,6 +237,7 @@ int ab200_unbind(ab200_ctx *c, int fluid) {
   free_all(f.owned_scratch);
   if (f.ghost_vars) cudaFree(f.ghost_vars);
   if (f.ghost_vdir) cudaFree(f.ghost_vdir);
+  release_tma(f);
   f = FluidHost();
   return AB200_OK;
 }
@@ -268,6 +269,9 @@ int ab200_bind_pack(ab200_ctx *c, const ab200_fluid_desc *fd, const ab200_pack_d
   d.recon = fd->recon; d.riemann = fd->riemann;
   d.gm1 = fd->gm1; d.dfloor = fd->dfloor; d.siefloor = fd->siefloor;
   d.de_switch = fd->de_switch; d.cfl = fd->cfl;
+  d.igm1 = 1.0 / fd->gm1;  // hllc.hpp:76-78
+  d.gamma = fd->gm1 + 1.0;
+  d.alpha = (d.gamma + 1.0) / (2.0 * d.gamma);
   const size_t nent = (size_t)c->g.nb * d.nvar, sent = (size_t)c->g.nb * d.S;
   auto up = [&](double *const **slot, double *const *src, size_t n) -> int {
     *slot = nullptr;

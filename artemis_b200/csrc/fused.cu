@@ -1,5 +1,7 @@
 // fused.cu -- instantiations + launcher of the fused directional passes for ONE coordinate
 // system (compiled six times with -DAB_GEOM=0..5).
+#include <cstdlib>
+
 #include "fused.cuh"
 
 #ifndef AB_GEOM
@@ -11,25 +13,52 @@ namespace ab200 {
 template <int GEOM, int FLUID, int RS, int RC, int DIR>
 static int launch_pass(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
   const GridDev &g = c->g;
+  const FluidHost &fh = c->fl[FLUID];
   const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
   const int L = DIR == 1 ? nir : (DIR == 2 ? njr : nkr);
+  const int nL = DIR == 1 ? g.ni : (DIR == 2 ? g.nj : g.nk);
   AB_REQUIRE(L + 2 <= kFusedMaxThreads, AB200_EINVAL,
              "ab200_fused_stage: MeshBlock extent exceeds 510 zones; use the task-level path");
-  int np = kFusedMaxThreads / (L + 2);
-  const long long npencils =
-      (long long)g.nb * (DIR == 1 ? (long long)nkr * njr
-                                  : (DIR == 2 ? (long long)nkr * nir : (long long)njr * nir));
-  if (np > npencils) np = (int)npencils;
-  a.np = np;
-  a.npencils = (int)npencils;
-  const int nthreads = ((np * (L + 2) + 31) / 32) * 32;
   constexpr int NV = FLUID == AB200_GAS ? 6 : 4, NF = FLUID == AB200_GAS ? 8 : 4;
-  const size_t shmem = sizeof(double) * (size_t)(NV + NF) * np * (L + 1);
-  auto kern = k_fused_pass<GEOM, FLUID, RS, RC, DIR>;
-  if (shmem > 48 * 1024)
-    AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-  const unsigned grid = (unsigned)((npencils + np - 1) / np);
-  kern<<<grid, nthreads, shmem, c->stream>>>(g, f, a);
+  const int npencils = DIR == 1 ? nkr * njr : (DIR == 2 ? nkr * nir : njr * nir);  // per block
+  if (fh.tma_ready && fh.tma_np[DIR - 1] > 0) {
+    // ---- TMA-staged kernel ---------------------------------------------------------------
+    const int np = fh.tma_np[DIR - 1];
+    const int tiled = DIR == 1 ? njr : nir, rows = DIR == 3 ? njr : nkr;
+    a.np = np;
+    a.npencils = npencils;
+    a.tiles_per_row = (tiled + np - 1) / np;
+    a.maps = reinterpret_cast<const CUtensorMap *>(fh.tma_maps[DIR - 1]);
+    const int nthreads = ((np * (L + 2) + 31) / 32) * 32;
+    const bool need_u1 = a.first && !a.copy_u1;
+    const size_t tile_stride = (((size_t)np * nL * 8 + 127) / 128) * 128;
+    const size_t shmem = 128 + (need_u1 ? 3 : 2) * NV * tile_stride +
+                         sizeof(double) * ((size_t)(NV + NF) * np * (L + 1) + 3 * (size_t)f.nvar);
+    auto kern = k_fused_pass<GEOM, FLUID, RS, RC, DIR, true>;
+    if (shmem > 48 * 1024)
+      AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    dim3 grid((unsigned)(a.tiles_per_row * rows), (unsigned)g.nb);
+    kern<<<grid, nthreads, shmem, c->stream>>>(g, f, a);
+  } else {
+    // ---- fallback: stencil straight from global memory through L1 -------------------------
+    int np = kFusedMaxThreads / (L + 2);
+    if (const char *env = getenv("AB200_FUSED_NP")) {  // tuning knob: pencils per CTA
+      const int v = atoi(env);
+      if (v >= 1 && v <= np) np = v;
+    }
+    if (np > npencils) np = npencils;
+    a.np = np;
+    a.npencils = npencils;
+    a.tiles_per_row = 0;
+    a.maps = nullptr;
+    const int nthreads = ((np * (L + 2) + 31) / 32) * 32;
+    const size_t shmem = sizeof(double) * ((size_t)(NV + NF) * np * (L + 1) + 3 * (size_t)f.nvar);
+    auto kern = k_fused_pass<GEOM, FLUID, RS, RC, DIR, false>;
+    if (shmem > 48 * 1024)
+      AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    dim3 grid((unsigned)((npencils + np - 1) / np), (unsigned)g.nb);
+    kern<<<grid, nthreads, shmem, c->stream>>>(g, f, a);
+  }
   c->launches++;
   AB_CUDA(cudaGetLastError());
   return AB200_OK;
@@ -68,6 +97,7 @@ int launch_fused_geom(ab200_ctx *c, int fluid, const FusedArgs &a, int pcm);
 
 template <>
 int launch_fused_geom<AB_GEOM>(ab200_ctx *c, int fluid, const FusedArgs &a, int pcm) {
+  AB_TRY(ensure_tma(c, fluid, kTmaMaxThreads));
   const FluidDev &f = c->fl[fluid].d;
   const int recon = pcm ? AB200_PCM : f.recon;
   if (fluid == AB200_GAS) {

@@ -92,7 +92,7 @@ k_calculate_fluxes(GridDev g, FluidDev f) {
       recon_cell<RC, CART>(q - st, st, wl[v], dummy, gl[0], gl[1], gl[2], gl[3], gl[4], gl[5]);
       recon_cell<RC, CART>(q, st, dummy, wr[v], gr[0], gr[1], gr[2], gr[3], gr[4], gr[5]);
     }
-    Riemann<RS, FLUID>::solve(f.gm1, wl, wr, out);
+    Riemann<RS, FLUID>::solve(EosConsts{f.gm1, f.igm1, f.gamma, f.alpha}, wl, wr, out);
     // ScaleMomentumFlux: component IVX*=hx1, IVY*=hx2, IVZ*=hx3 (fluid_fluxes.hpp:64-66)
     if (!CART) {
 #pragma unroll
@@ -233,10 +233,10 @@ AB_D double set_aux_cell(double dens, double m1, double m2, double m3, double e_
   double u_d = dens;
   u_d = (u_d > dflr) ? u_d : dflr;
   const double ud2 = dmax(dens, dflr);
-  const double rv1 = m1 / hx[0], rv2 = m2 / hx[1], rv3 = m3 / hx[2];
-  const double ke = 0.5 * (sqr(rv1) + sqr(rv2) + sqr(rv3)) / ud2;
+  const double rv1 = ddiv(m1, hx[0]), rv2 = ddiv(m2, hx[1]), rv3 = ddiv(m3, hx[2]);
+  const double ke = ddiv(0.5 * (sqr(rv1) + sqr(rv2) + sqr(rv3)), ud2);
   const double ue_cons = e_cons - ke;
-  double sie = (ue_cons > de_switch * e_cons) ? ue_cons / ud2 : u_u / ud2;
+  double sie = ddiv((ue_cons > de_switch * e_cons) ? ue_cons : u_u, ud2);
   sie = dmax(sie, sieflr);
   double r = sie * u_d;
   const double uflr = sieflr * u_d;

@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- zone-cycles/s of the Artemis gas stage update on B200 (config 2 of BASELINE.json).
+
+Workload (N=1): 3-D Sedov blast, 256^3 zones per GPU as 64 MeshBlocks of 64^3, nghost=4,
+PPM + HLLC, fp64, rk2, gamma=1.4, cfl=0.3, outflow boundaries (inputs/blast/blast.in with the
+SURVEY 8d overrides).  N>1: weak scaling, one 256^3 tile per rank (block-spatial partition),
+halo exchange + dt all-reduce over NCCL.  A "step" is one full integrator cycle
+(2 stages + CFL reduction).  State (3.4 GB/GPU) is far larger than L2, so no flush is needed.
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_ZONE_STAGE = 240.0   # R W6 + u0 6 + u1 6, W u0 6 + W 6 doubles
+METRIC = "zone-cycles/sec, 3D PPM+HLLC fp64, 1/2/4/8 B200; % HBM roofline"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tile", type=int, default=256, help="zones per GPU per direction")
+    ap.add_argument("--block", type=int, default=64)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample", type=int, default=128, help="CPU baseline mesh size")
+    ap.add_argument("--cpu-cycles", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def rank_layout(n):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n]
+
+
+def make_problem(args, rank, world):
+    from artemis_b200.enums import BoundaryFlag, Coordinates, Fluid, ReconstructionMethod, RSolver
+    from artemis_b200.mesh import UniformMesh
+    from artemis_b200.params import FluidParams
+    lay = rank_layout(world)
+    T, B = args.tile, args.block
+    nx = tuple(T * lay[d] for d in range(3))
+    nbt = T // B
+    rl = (rank % lay[0], (rank // lay[0]) % lay[1], rank // (lay[0] * lay[1]))
+    mesh = UniformMesh(nx=nx, xmin=tuple(-1.0 * lay[d] for d in range(3)),
+                       xmax=tuple(1.0 * lay[d] for d in range(3)), block_nx=(B, B, B), nghost=4,
+                       bcs=(BoundaryFlag.outflow,) * 6,
+                       lattice_lo=tuple(rl[d] * nbt for d in range(3)), lattice_n=(nbt,) * 3)
+    gp = FluidParams(Fluid.gas, Coordinates.cartesian, ReconstructionMethod.ppm, RSolver.hllc,
+                     cfl=0.3, nspecies=1, dfloor=1e-10, gamma=1.4, siefloor=1e-10)
+    return mesh, gp, lay, rl
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.idx = gpu_index
+        self.stop_evt = threading.Event()
+        self.rows = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+            if self.stop_evt.is_set():
+                break
+        self.proc.terminate()
+
+    def finish(self):
+        self.stop_evt.set()
+        time.sleep(0.15)
+        try:
+            self.proc.terminate()
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        # under load = the upper half of the samples
+        sm_sorted = sorted(sm)
+        return {"sm_mhz": float(np.median(sm_sorted[len(sm_sorted) // 2:])),
+                "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(args, steps=None):
+    """The oracle (CPU restatement of the reference path) timed on the host cores: a bounded
+    sample of the same workload (same numerics, smaller mesh)."""
+    from artemis_b200 import pgen
+    from artemis_b200.enums import BoundaryFlag, Coordinates, Fluid, ReconstructionMethod, RSolver
+    from artemis_b200.mesh import UniformMesh
+    from artemis_b200.params import FluidParams
+    from oracle import oracle_py
+    n = args.cpu_sample
+    mesh = UniformMesh(nx=(n, n, n), xmin=(-1, -1, -1), xmax=(1, 1, 1),
+                       block_nx=(min(64, n),) * 3, nghost=4, bcs=(BoundaryFlag.outflow,) * 6)
+    gp = FluidParams(Fluid.gas, Coordinates.cartesian, ReconstructionMethod.ppm, RSolver.hllc,
+                     cfl=0.3, nspecies=1, dfloor=1e-10, gamma=1.4, siefloor=1e-10)
+    sim = oracle_py.OracleSim(mesh, gas=gp, integrator="rk2")
+    sim.gas.prim[:] = pgen.blast(mesh, gp.gamma, d0=1.0, p0=1e-5, internal_energy=1.0, radius=0.1,
+                                 samples=0)
+    sim.initialize()
+    sim.step()  # warm-up (page faults, OpenMP pool)
+    ncyc = steps or args.cpu_cycles
+    times = []
+    for _ in range(ncyc):
+        t0 = time.perf_counter()
+        sim.step()
+        times.append(time.perf_counter() - t0)
+    tot = sum(times)
+    zc = mesh.interior_zones * ncyc / tot
+    return {"value": zc, "unit": "zone-cycles/s", "cores": int(oracle_py.lib().ao_num_threads()),
+            "kind": "port",
+            "sample": f"{ncyc} rk2 cycles of the {n}^3 blast ({mesh.nb} blocks of "
+                      f"{mesh.block_nx[0]}^3, PPM+HLLC fp64) with the OpenMP oracle"}, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, times = cpu_baseline(args, steps=max(1, args.steps))
+    ms = 1e3 * float(np.mean(times))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"],
+            "unit": "zone-cycles/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"3D Sedov blast PPM+HLLC rk2 fp64, bounded sample "
+                                   f"{args.cpu_sample}^3 per step on host cores (GPU arm: "
+                                   f"{args.tile}^3 per GPU, 64^3 MeshBlocks)",
+                       "note": "the reference's Kokkos build needs cmake+Kokkos and is not "
+                               "buildable on the GPU box; this times the oracle port of the "
+                               "same path with all host threads"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "zone-cycles/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    from artemis_b200 import pgen
+    from artemis_b200.driver import ArtemisDriver
+    from artemis_b200.meshdata import MeshData
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    mesh, gp, lay, rl = make_problem(args, rank, world)
+    bcs = list(mesh.bcs)
+    if world > 1:
+        from artemis_b200.comm import HaloComm
+        for d in range(3):
+            if rl[d] > 0:
+                bcs[2 * d] = 3            # AB200_BC_NONE: neighbour rank
+            if rl[d] < lay[d] - 1:
+                bcs[2 * d + 1] = 3
+    md = MeshData(mesh, gas=gp, device=local, materialize_fluxes=False, bcs=bcs)
+    if world > 1:
+        comm = HaloComm(md, lay, rl, rank, world)
+    prim = pgen.blast(mesh, gp.gamma, d0=1.0, p0=1e-5, internal_energy=1.0, radius=0.1, samples=0)
+    md.gas.prim.set(prim)
+    drv = ArtemisDriver(md, "rk2", mode="fused", comm=comm)
+    drv.Initialize()
+    zones = mesh.interior_zones * world
+    integ = 1  # rk2
+
+    def sync_all():
+        md.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def one_step():
+        if world == 1:
+            md.call("ab200_run_cycles", integ, 1, float(np.finfo(np.float64).max))
+        else:
+            drv.Step()
+
+    if world == 1:
+        md.set_time_state(drv.dt)
+    for _ in range(args.warmup):
+        one_step()
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = md.launch_count()
+    sync_all()
+    md.call("ab200_timer_begin")
+    for _ in range(args.steps):
+        one_step()
+    ms = __import__("ctypes").c_float()
+    md.call("ab200_timer_end", __import__("ctypes").byref(ms))
+    sync_all()
+    launches = md.launch_count() - l0
+    clocks = sampler.finish() if sampler else None
+    t_ms = float(ms.value)
+    if world > 1:
+        tt = torch.tensor([t_ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_ms = float(tt.item())
+        lt = torch.tensor([launches], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    value = zones * args.steps / (t_ms * 1e-3)
+    ts = md.time_state() if world == 1 else None
+
+    # ---- per-kernel timing of the dominant kernels (fused directional passes) -------------
+    import ctypes as C
+    peak, peak_src = measured_peaks()
+    kms = []
+    reps = 3
+    for stage, (g0, g1, b) in enumerate(((0.0, 1.0, 1.0), (0.5, 0.5, 0.5))):
+        acc = 0.0
+        for _ in range(reps):
+            md.synchronize()
+            md.call("ab200_timer_begin")
+            md.call("ab200_fused_stage", g0, g1, b, 0.0, 0, int(stage == 0), 0)  # dt=0: state kept
+            k = C.c_float()
+            md.call("ab200_timer_end", C.byref(k))
+            acc += k.value
+        kms.append(acc / reps)
+    stage_ms = float(np.mean(kms))
+    zones_local = mesh.interior_zones
+    achieved = ALG_BYTES_PER_ZONE_STAGE * zones_local / (stage_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as fh:
+            traffic = json.load(fh).get("fused_stage_dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "kernel": "k_fused_pass x3 (one fused stage = x, y, z directional passes)",
+                "stage_ms": kms, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ALG_BYTES_PER_ZONE_STAGE * zones_local,
+                "whole_cycle_frac": value / world * 2 * ALG_BYTES_PER_ZONE_STAGE / (peak * 1e9)}
+
+    # ---- end to end through the host-buffer C-ABI entry point ------------------------------
+    e2e = None
+    if not args.no_e2e and world == 1:
+        nv = gp.nvar
+        shape = mesh.shape(nv)
+        hp = torch.empty(shape, dtype=torch.float64).pin_memory()
+        hc = torch.empty(shape, dtype=torch.float64).pin_memory()
+        hp.numpy()[:] = md.gas.prim.get()
+        dt_io = C.c_double(drv.dt)
+        DP = C.POINTER(C.c_double)
+        php, phc = C.cast(hp.data_ptr(), DP), C.cast(hc.data_ptr(), DP)
+        md.call("ab200_cycles_host", integ, 1, C.byref(dt_io), php, phc, None, None)  # warm-up
+        md.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            md.call("ab200_cycles_host", integ, 1, C.byref(dt_io), php, phc, None, None)
+        md.synchronize()
+        te = (time.perf_counter() - t0) / args.e2e_steps
+        nbytes = int(np.prod(shape)) * 8
+        e2e = {"value": mesh.interior_zones / te, "unit": "zone-cycles/s",
+               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 2 * nbytes,
+               "ms_per_step": te * 1e3,
+               "api": "ab200_cycles_host (pinned host prim in; prim + cons out)"}
+    elif world > 1:
+        e2e = {"value": None, "unit": "zone-cycles/s", "h2d_bytes_per_step": 0,
+               "d2h_bytes_per_step": 0, "note": "host-buffer entry point is measured at N=1"}
+
+    base = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        base, _ = cpu_baseline(args)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "zone-cycles/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"3D Sedov blast (inputs/blast + 3D overrides), PPM+HLLC, "
+                                       f"rk2, {args.tile}^3 zones per GPU in {args.block}^3 "
+                                       f"MeshBlocks, nghost=4, outflow",
+                           "zones_total": zones, "ranks": list(lay),
+                           "l2": "state 3.4 GB/GPU >> 126 MB L2, no flush needed",
+                           "path": "fused stage kernels + device-resident dt"
+                                   if world == 1 else "fused stage kernels + NCCL halo exchange"},
+                "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
+                "gpu_launches": launches, "clocks": clocks}
+        if ts is not None:
+            line["config"]["sim_time"] = float(ts[2])
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    md.close()
+
+
+if __name__ == "__main__":
+    main()
