@@ -28,16 +28,22 @@ static int launch_pass(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
     a.np = np;
     a.npencils = npencils;
     a.tiles_per_row = (tiled + np - 1) / np;
+    a.tiles_per_block = a.tiles_per_row * rows;
+    a.nwork = g.nb * a.tiles_per_block * f.S;
     a.maps = reinterpret_cast<const CUtensorMap *>(fh.tma_maps[DIR - 1]);
     const int nthreads = ((np * (L + 2) + 31) / 32) * 32;
     const bool need_u1 = a.first && !a.copy_u1;
     const size_t tile_stride = (((size_t)np * nL * 8 + 127) / 128) * 128;
-    const size_t shmem = 128 + (need_u1 ? 3 : 2) * NV * tile_stride +
+    const size_t shmem = 128 + 2 * (need_u1 ? 3 : 2) * NV * tile_stride +
                          sizeof(double) * ((size_t)(NV + NF) * np * (L + 1) + 3 * (size_t)f.nvar);
     auto kern = k_fused_pass<GEOM, FLUID, RS, RC, DIR, true>;
     if (shmem > 48 * 1024)
       AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-    dim3 grid((unsigned)(a.tiles_per_row * rows), (unsigned)g.nb);
+    // persistent CTAs: 2 per SM, each streams work items through a 2-stage TMA pipeline
+    int ncta = 2 * c->sm_count;
+    if (const char *env = getenv("AB200_FUSED_CTAS")) ncta = atoi(env) > 0 ? atoi(env) : ncta;
+    if (ncta > a.nwork) ncta = a.nwork;
+    dim3 grid((unsigned)ncta, 1);
     kern<<<grid, nthreads, shmem, c->stream>>>(g, f, a);
   } else {
     // ---- fallback: stencil straight from global memory through L1 -------------------------

@@ -39,7 +39,9 @@ struct FusedArgs {
   int first, last, copy_u1;
   int np;        // pencils per CTA
   int npencils;  // pencils per MeshBlock
-  int tiles_per_row;  // TMA: tiles along the transverse index that is tiled
+  int tiles_per_row;    // TMA: tiles along the transverse index that is tiled
+  int tiles_per_block;  // TMA: tiles per MeshBlock
+  int nwork;            // TMA: nb * tiles_per_block * nspecies
   const CUtensorMap *maps;  // TMA: [3 kinds][nb*nvar] for this direction
 };
 
@@ -91,52 +93,26 @@ k_fused_pass(GridDev g, FluidDev f, FusedArgs a) {
   const int NP = a.np;
   const int nslots = NP * (L + 1);
   const bool need_u1 = a.first && !a.copy_u1;
-  // ---- shared-memory carve-up -----------------------------------------------------------
-  const int tile_stride = TMA ? ((NP * nL * 8 + 127) / 128) * 16 : 0;  // doubles per variable
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-  double *s_prim = reinterpret_cast<double *>(smem_raw + (TMA ? 128 : 0));
-  double *s_u0 = s_prim + NV * tile_stride;
-  double *s_u1 = s_u0 + NV * tile_stride;
-  double *s_ql = s_u1 + (need_u1 ? NV * tile_stride : 0);  // [NV][nslots]
-  double *s_fx = s_ql + NV * nslots;                       // [NF][nslots]
-  // CTA-uniform array base pointers of this block: prim | u0 | u1, nvar each
-  double **s_ptr = reinterpret_cast<double **>(s_fx + NF * nslots);
-  const int b = blockIdx.y;
+  const int S = f.S;
   const int nvar = f.nvar;
-  for (int q = threadIdx.x; q < 3 * nvar; q += blockDim.x) {
-    const int w = q / nvar, n = q - w * nvar;
-    double *const *tab = w == 0 ? f.prim : (w == 1 ? f.u0 : f.u1);
-    s_ptr[q] = tab ? tab[(size_t)b * nvar + n] : nullptr;
-  }
+  // ---- shared-memory carve-up -----------------------------------------------------------
+  // TMA: [2 mbarriers | 2 stages x {prim, u0, (u1)} tiles | ql | fx | pointers]
+  const int tile_stride = TMA ? ((NP * nL * 8 + 127) / 128) * 16 : 0;  // doubles per variable
+  const int stage_stride = (need_u1 ? 3 : 2) * NV * tile_stride;        // doubles per stage
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+  double *s_tiles = reinterpret_cast<double *>(smem_raw + (TMA ? 128 : 0));
+  double *s_ql = s_tiles + 2 * stage_stride;  // [NV][nslots]
+  double *s_fx = s_ql + NV * nslots;          // [NF][nslots]
+  // CTA-uniform array base pointers of the current block: prim | u0 | u1, nvar each
+  double **s_ptr = reinterpret_cast<double **>(s_fx + NF * nslots);
 
-  // ---- thread -> (pencil p, cell c) ---------------------------------------------------
+  // ---- thread -> (pencil p, cell c): fixed for the lifetime of the CTA ----------------------
   const int t = threadIdx.x;
   int p, c;
   if (DIR == 1) { p = t / (L + 2); c = t % (L + 2) - 1; }
   else { p = t % NP; c = t / NP - 1; }
-  int k = g.ks, j = g.js, i = g.is;
-  bool active = (t < NP * (L + 2));
-  int bc0 = 0, bc1 = 0, bc2 = 0;  // TMA box start coordinates (i, j, k)
-  if (TMA) {
-    // tiles never straddle a row of the tiled transverse index
-    const int tr = blockIdx.x % a.tiles_per_row, row = blockIdx.x / a.tiles_per_row;
-    if (DIR == 1) { j = g.js + tr * NP + p; k = g.ks + row; i = g.is + c; active = active && j <= g.je;
-                    bc0 = 0; bc1 = g.js + tr * NP; bc2 = k; }
-    if (DIR == 2) { i = g.is + tr * NP + p; k = g.ks + row; j = g.js + c; active = active && i <= g.ie;
-                    bc0 = g.is + tr * NP; bc1 = 0; bc2 = k; }
-    if (DIR == 3) { i = g.is + tr * NP + p; j = g.js + row; k = g.ks + c; active = active && i <= g.ie;
-                    bc0 = g.is + tr * NP; bc1 = j; bc2 = 0; }
-  } else {
-    const int pid = blockIdx.x * NP + p;
-    active = active && (pid < a.npencils);
-    if (active) {
-      if (DIR == 1) { j = pid % njr + g.js; k = pid / njr + g.ks; i = g.is + c; }
-      if (DIR == 2) { i = pid % nir + g.is; k = pid / nir + g.ks; j = g.js + c; }
-      if (DIR == 3) { i = pid % nir + g.is; j = pid / nir + g.js; k = g.ks + c; }
-    }
-  }
+  const bool in_tile = (t < NP * (L + 2));
   const int st = DIR == 1 ? 1 : (DIR == 2 ? g.ni : g.ni * g.nj);
-  const int off = (k * g.nj + j) * g.ni + i;
   // position of this cell inside a staged tile, and the stride along DIR there
   const int tctr = DIR == 1 ? p * nL + (s0 + c) : (s0 + c) * NP + p;
   const int tst = DIR == 1 ? 1 : NP;
@@ -145,18 +121,105 @@ k_fused_pass(GridDev g, FluidDev f, FusedArgs a) {
 
   const double dt = a.dt_dev ? *a.dt_dev : a.dt;
   const double bdt = a.beta * dt;
-  const int S = f.S;
   const EosConsts eos{f.gm1, f.igm1, f.gamma, f.alpha};
-  const bool interior = active && c >= 0 && c < L;
 
-  // PLM_G geometry of this cell along DIR
-  double gx[6] = {0, 0, 0, 0, 0, 0};
-  if (!CART && RC == AB200_PLM && active)
-    plmg_geom<GEOM, DIR>(g, b, k, j, i, gx[0], gx[1], gx[2], gx[3], gx[4], gx[5]);
-  if (TMA && t == 0) mbar_init(bar, 1);
-  __syncthreads();  // s_ptr + mbarrier ready
+  // ---- work items ---------------------------------------------------------------------------
+  // TMA: persistent CTAs; item w = (tile, species), tiles enumerated block-major.
+  // fallback: one tile per CTA (blockIdx), items = species.
+  const int nwork = TMA ? a.nwork : S;
+  const int wstep = TMA ? (int)gridDim.x : 1;
+  auto tile_of = [&](int w, int &b, int &n, int &tr, int &row) {
+    if (TMA) {
+      n = w % S;
+      const int tile = w / S;
+      b = tile / a.tiles_per_block;
+      const int tb = tile - b * a.tiles_per_block;
+      row = tb / a.tiles_per_row;
+      tr = tb - row * a.tiles_per_row;
+    } else {
+      n = w; b = blockIdx.y; tr = 0; row = 0;
+    }
+  };
+  // elected thread: launch the TMA loads of work item w into pipeline stage `stg`
+  auto issue = [&](int w, int stg) {
+    int b, n, tr, row;
+    tile_of(w, b, n, tr, row);
+    int bc0, bc1, bc2;  // box start (i, j, k); tiles never straddle a transverse row
+    if (DIR == 1) { bc0 = 0; bc1 = g.js + tr * NP; bc2 = g.ks + row; }
+    if (DIR == 2) { bc0 = g.is + tr * NP; bc1 = 0; bc2 = g.ks + row; }
+    if (DIR == 3) { bc0 = g.is + tr * NP; bc1 = g.js + row; bc2 = 0; }
+    const int idx[6] = {n, S + 3 * n + (DIR - 1), S + 3 * n + ((DIR - 1) + 1) % 3,
+                        S + 3 * n + ((DIR - 1) + 2) % 3, 4 * S + n, 5 * S + n};
+    const int ci[6] = {n, S + 3 * n, S + 3 * n + 1, S + 3 * n + 2, 4 * S + n, 5 * S + n};
+    const uint32_t bytes = (uint32_t)(NP * nL * 8) * NV * (need_u1 ? 3 : 2);
+    mbar_expect_tx(bar + stg, bytes);
+    const CUtensorMap *mp = a.maps + (size_t)b * nvar;
+    const size_t kind = (size_t)g.nb * nvar;
+    double *dst = s_tiles + stg * stage_stride;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      tma_load_3d(dst + v * tile_stride, mp + idx[v], bar + stg, bc0, bc1, bc2);
+#pragma unroll
+    for (int m = 0; m < NV; ++m)
+      tma_load_3d(dst + (NV + m) * tile_stride, mp + kind + ci[m], bar + stg, bc0, bc1, bc2);
+    if (need_u1) {
+#pragma unroll
+      for (int m = 0; m < NV; ++m)
+        tma_load_3d(dst + (2 * NV + m) * tile_stride, mp + 2 * kind + ci[m], bar + stg, bc0, bc1,
+                    bc2);
+    }
+  };
 
-  for (int n = 0; n < S; ++n) {
+  int w = TMA ? (int)blockIdx.x : 0;
+  if (TMA) {
+    if (t == 0) {
+      mbar_init(bar, 1);
+      mbar_init(bar + 1, 1);
+    }
+    __syncthreads();
+    if (t == 0 && w < nwork) issue(w, 0);
+  }
+  int cur_b = -1;
+  for (int it = 0; w < nwork; w += wstep, ++it) {
+    int b, n, tr, row;
+    tile_of(w, b, n, tr, row);
+    const int stg = it & 1;
+    if (TMA && t == 0 && w + wstep < nwork) issue(w + wstep, stg ^ 1);  // prefetch next item
+    if (b != cur_b) {  // (re)load the block's array base pointers (CTA-uniform branch)
+      cur_b = b;
+      for (int q = threadIdx.x; q < 3 * nvar; q += blockDim.x) {
+        const int kind = q / nvar, e = q - kind * nvar;
+        double *const *tab = kind == 0 ? f.prim : (kind == 1 ? f.u0 : f.u1);
+        s_ptr[q] = tab ? tab[(size_t)b * nvar + e] : nullptr;
+      }
+      __syncthreads();
+    }
+    // ---- cell indices of this thread for this item ------------------------------------------
+    int k = g.ks, j = g.js, i = g.is;
+    bool active = in_tile;
+    if (TMA) {
+      if (DIR == 1) { j = g.js + tr * NP + p; k = g.ks + row; i = g.is + c; active = active && j <= g.je; }
+      if (DIR == 2) { i = g.is + tr * NP + p; k = g.ks + row; j = g.js + c; active = active && i <= g.ie; }
+      if (DIR == 3) { i = g.is + tr * NP + p; j = g.js + row; k = g.ks + c; active = active && i <= g.ie; }
+    } else {
+      const int pid = blockIdx.x * NP + p;
+      active = active && (pid < a.npencils);
+      if (active) {
+        if (DIR == 1) { j = pid % njr + g.js; k = pid / njr + g.ks; i = g.is + c; }
+        if (DIR == 2) { i = pid % nir + g.is; k = pid / nir + g.ks; j = g.js + c; }
+        if (DIR == 3) { i = pid % nir + g.is; j = pid / nir + g.js; k = g.ks + c; }
+      }
+    }
+    const int off = (k * g.nj + j) * g.ni + i;
+    const bool interior = active && c >= 0 && c < L;
+    const double *s_prim = s_tiles + stg * stage_stride;
+    const double *s_u0 = s_prim + NV * tile_stride;
+    const double *s_u1 = s_u0 + NV * tile_stride;
+    // PLM_G geometry of this cell along DIR
+    double gx[6] = {0, 0, 0, 0, 0, 0};
+    if (!CART && RC == AB200_PLM && active)
+      plmg_geom<GEOM, DIR>(g, b, k, j, i, gx[0], gx[1], gx[2], gx[3], gx[4], gx[5]);
+
     int idx[6];
     idx[0] = n;
     idx[1] = S + 3 * n + (DIR - 1);
@@ -167,27 +230,8 @@ k_fused_pass(GridDev g, FluidDev f, FusedArgs a) {
     // conserved values in pack order: rho, m1, m2, m3, (E, u)
     const int ci[6] = {n, S + 3 * n, S + 3 * n + 1, S + 3 * n + 2, 4 * S + n, 5 * S + n};
 
-    // ---- stage-in: TMA loads of the prim / u0 / u1 pencil tiles ---------------------------
-    if (TMA) {
-      if (t == 0) {
-        const uint32_t bytes = (uint32_t)(NP * nL * 8) * NV * (need_u1 ? 3 : 2);
-        mbar_expect_tx(bar, bytes);
-        const CUtensorMap *mp = a.maps + (size_t)b * nvar;
-        const size_t kind = (size_t)gridDim.y * nvar;
-#pragma unroll
-        for (int v = 0; v < NV; ++v)
-          tma_load_3d(s_prim + v * tile_stride, mp + idx[v], bar, bc0, bc1, bc2);
-#pragma unroll
-        for (int m = 0; m < NV; ++m)
-          tma_load_3d(s_u0 + m * tile_stride, mp + kind + ci[m], bar, bc0, bc1, bc2);
-        if (need_u1) {
-#pragma unroll
-          for (int m = 0; m < NV; ++m)
-            tma_load_3d(s_u1 + m * tile_stride, mp + 2 * kind + ci[m], bar, bc0, bc1, bc2);
-        }
-      }
-      mbar_wait(bar, (uint32_t)(n & 1));
-    }
+    // ---- stage-in: wait for this item's TMA loads --------------------------------------------
+    if (TMA) mbar_wait(bar + stg, (uint32_t)((it >> 1) & 1));
 
     // ---- phase A: reconstruct this cell ------------------------------------------------
     double qr[NV], wc0 = 0.0, wcv[3] = {0.0, 0.0, 0.0};
@@ -357,7 +401,8 @@ k_fused_pass(GridDev g, FluidDev f, FusedArgs a) {
         }
       }
     }
-    if (n + 1 < S) __syncthreads();
+    // exchange buffers and (TMA) this stage's tiles are free for the next item
+    if (w + wstep < nwork) __syncthreads();
   }
 }
 
