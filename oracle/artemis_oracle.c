@@ -993,14 +993,17 @@ static void range_recv(int off, int s, int e, int ng, int *lo, int *hi) {
   else { *lo = s - ng; *hi = s - 1; }
 }
 
-void ao_exchange_ghosts(const ao_grid *g, int nbx, int nby, int nbz, const int *bc,
-                        int nvar, double *a, int nv, const int *vars, const int *vec_dir) {
+/* phases: bit 0 = neighbour -> ghost copies, bit 1 = physical boundaries.  Faces flagged
+ * AO_BC_NONE belong to another rank: neither copied across nor filled (multi-rank tests). */
+void ao_exchange_ghosts_phase(const ao_grid *g, int nbx, int nby, int nbz, const int *bc,
+                              int nvar, double *a, int nv, const int *vars,
+                              const int *vec_dir, int phases) {
   const int ng = g->ng;
   const int nbd[3] = {nbx, nby, nbz};
   const int ox3 = g->ndim > 2 ? 1 : 0, ox2 = g->ndim > 1 ? 1 : 0;
   /* 1. neighbour -> ghost copies (receiver-driven; all sources are interior cells) */
 #pragma omp parallel for schedule(static)
-  for (int b = 0; b < g->nb; ++b) {
+  for (int b = 0; b < ((phases & 1) ? g->nb : 0); ++b) {
     const int lb[3] = {b % nbx, (b / nbx) % nby, b / (nbx * nby)};
     for (int o3 = -ox3; o3 <= ox3; ++o3)
       for (int o2 = -ox2; o2 <= ox2; ++o2)
@@ -1039,13 +1042,13 @@ void ao_exchange_ghosts(const ao_grid *g, int nbx, int nby, int nbz, const int *
   }
   /* 2. physical boundaries */
 #pragma omp parallel for schedule(static)
-  for (int b = 0; b < g->nb; ++b) {
+  for (int b = 0; b < ((phases & 2) ? g->nb : 0); ++b) {
     const int lb[3] = {b % nbx, (b / nbx) % nby, b / (nbx * nby)};
     const int s[3] = {g->is, g->js, g->ks}, e[3] = {g->ie, g->je, g->ke};
     const int nt[3] = {g->ni, g->nj, g->nk};
     for (int face = 0; face < 2 * g->ndim; ++face) {
       const int d = face / 2, outer = face % 2;
-      if (bc[face] == AO_BC_PERIODIC) continue;
+      if (bc[face] == AO_BC_PERIODIC || bc[face] == AO_BC_NONE) continue;
       if (outer ? (lb[d] != nbd[d] - 1) : (lb[d] != 0)) continue;
       const int ref = outer ? e[d] : s[d];
       const int offset = 2 * ref + (outer ? 1 : -1);
@@ -1065,4 +1068,9 @@ void ao_exchange_ghosts(const ao_grid *g, int nbx, int nby, int nbz, const int *
       }
     }
   }
+}
+
+void ao_exchange_ghosts(const ao_grid *g, int nbx, int nby, int nbz, const int *bc,
+                        int nvar, double *a, int nv, const int *vars, const int *vec_dir) {
+  ao_exchange_ghosts_phase(g, nbx, nby, nbz, bc, nvar, a, nv, vars, vec_dir, 3);
 }

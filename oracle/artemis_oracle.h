@@ -39,7 +39,7 @@ enum { AO_CARTESIAN = 0, AO_CYLINDRICAL = 1, AO_SPHERICAL1D = 2, AO_SPHERICAL2D 
 enum { AO_HLLC = 0, AO_HLLE = 1, AO_LLF = 2 };
 enum { AO_PCM = 0, AO_PLM = 1, AO_PPM = 2 };
 enum { AO_GAS = 0, AO_DUST = 1 };
-enum { AO_BC_PERIODIC = 0, AO_BC_OUTFLOW = 1, AO_BC_REFLECT = 2 };
+enum { AO_BC_PERIODIC = 0, AO_BC_OUTFLOW = 1, AO_BC_REFLECT = 2, AO_BC_NONE = 3 };
 
 typedef struct {
   int geom, ndim, ng, nb;
@@ -81,6 +81,12 @@ void ao_deep_copy(const ao_grid *g, int nvar, double *to, const double *from);
  * else 0.  bc[6] = {ix1, ox1, ix2, ox2, ix3, ox3}. */
 void ao_exchange_ghosts(const ao_grid *g, int nbx, int nby, int nbz, const int *bc,
                         int nvar, double *a, int nv, const int *vars, const int *vec_dir);
+
+/* Same, split in phases (bit 0: neighbour copies, bit 1: physical BCs); faces flagged
+ * AO_BC_NONE (owned by another rank) are left untouched. */
+void ao_exchange_ghosts_phase(const ao_grid *g, int nbx, int nby, int nbz, const int *bc,
+                              int nvar, double *a, int nv, const int *vars,
+                              const int *vec_dir, int phases);
 
 /* Geometry probes (used by tests to compare against oracle/_ref and the CUDA tables) */
 void ao_geom_cell(int geom, const double *xmin, const double *dx, int k, int j, int i,
