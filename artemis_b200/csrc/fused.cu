@@ -3,6 +3,7 @@
 #include <cstdlib>
 
 #include "fused.cuh"
+#include "march.cuh"
 
 #ifndef AB_GEOM
 #error "compile with -DAB_GEOM=<0..5>"
@@ -70,6 +71,26 @@ static int launch_pass(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
   return AB200_OK;
 }
 
+// x2 / x3 passes as marching kernels (march.cuh): one thread per pencil, register window.
+template <int GEOM, int FLUID, int RS, int RC, int DIR>
+static int launch_march(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
+  const GridDev &g = c->g;
+  const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
+  const int ncols = nir * (DIR == 2 ? nkr : njr);
+  dim3 grid((unsigned)((ncols + kMarchThreads - 1) / kMarchThreads), (unsigned)g.nb,
+            (unsigned)f.S);
+  k_march_pass<GEOM, FLUID, RS, RC, DIR><<<grid, kMarchThreads, 0, c->stream>>>(g, f, a);
+  c->launches++;
+  AB_CUDA(cudaGetLastError());
+  return AB200_OK;
+}
+
+static bool use_march() {
+  static int v = -1;
+  if (v < 0) v = getenv("AB200_NO_MARCH") ? 0 : 1;
+  return v == 1;
+}
+
 template <int GEOM, int FLUID, int RS, int RC>
 static int launch_dirs(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
   const int ndim = c->g.ndim;
@@ -78,11 +99,13 @@ static int launch_dirs(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
   AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 1>(c, f, a)));
   if (ndim >= 2) {
     a.first = 0; a.last = (ndim == 2); a.copy_u1 = 0;
-    AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 2>(c, f, a)));
+    if (use_march()) AB_TRY((launch_march<GEOM, FLUID, RS, RC, 2>(c, f, a)));
+    else AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 2>(c, f, a)));
   }
   if (ndim >= 3) {
     a.first = 0; a.last = 1; a.copy_u1 = 0;
-    AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 3>(c, f, a)));
+    if (use_march()) AB_TRY((launch_march<GEOM, FLUID, RS, RC, 3>(c, f, a)));
+    else AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 3>(c, f, a)));
   }
   return AB200_OK;
 }
