@@ -87,9 +87,15 @@ int launch_prim_to_cons(ab200_ctx *c, int fluid, int ghosts_only);
 int launch_deep_copy(ab200_ctx *c, int fluid);
 int launch_estimate_dt(ab200_ctx *c, int fluid, double *d_out, int combine);
 int launch_fused_stage(ab200_ctx *c, int fluid, double gam0, double gam1, double beta,
-                       double dt, int pcm, int stage1_copy, int use_device_dt);
+                       double dt, int pcm, int stage1_copy, int use_device_dt,
+                       unsigned long long *dt_min);
+bool fused_folds_dt(const ab200_ctx *c);
+int launch_finish_dt(ab200_ctx *c, const double *partial, int n, double cfl, double *d_out,
+                     int combine);
 int launch_exchange(ab200_ctx *c, int fluid);
 int launch_physical_bcs(ab200_ctx *c, int fluid);
+int launch_fill_ghosts(ab200_ctx *c, int fluid);
+bool topology_is_local(const ab200_ctx *c);
 int launch_halo(ab200_ctx *c, const ab200_bnd_desc *bnd, int n, int unpack);
 int launch_set_global_dt(ab200_ctx *c, double tlim, int advance_time);
 int ensure_scratch(ab200_ctx *c, int fluid, bool need_flux, bool need_u1);

@@ -436,15 +436,31 @@ int ab200_write_time_state(ab200_ctx *c, const double *host4) {
 }
 
 int ab200_fused_stage(ab200_ctx *c, double gam0, double gam1, double beta, double dt, int pcm,
-                      int stage1_copy, int use_device_dt) {
+                      int stage1_copy, int flags) {
   AB_ENTER(c)
   AB_REQUIRE(!stage1_copy || (gam0 == 0.0 && gam1 == 1.0), AB200_EINVAL,
              "ab200_fused_stage: stage1_copy requires gam0 == 0 and gam1 == 1");
+  AB_REQUIRE((flags & ~(AB200_STAGE_DEVICE_DT | AB200_STAGE_REDUCE_DT)) == 0, AB200_EINVAL,
+             "ab200_fused_stage: unknown flag");
+  const int use_device_dt = (flags & AB200_STAGE_DEVICE_DT) != 0;
+  const int reduce_dt = (flags & AB200_STAGE_REDUCE_DT) != 0;
+  const bool fold = reduce_dt && fused_folds_dt(c);
+  // per-fluid raw minimum (bit pattern of a positive double), reset to a huge finite value
+  unsigned long long *slots = reinterpret_cast<unsigned long long *>(c->d_red + 3072);
+  if (fold) AB_CUDA(cudaMemsetAsync(slots, 0x7f, 2 * sizeof(unsigned long long), c->stream));
   int any = 0;
   for (int f = 0; f < 2; ++f) {
     if (!c->fl[f].bound) continue;
     AB_TRY(ensure_scratch(c, f, false, true));
-    AB_TRY(launch_fused_stage(c, f, gam0, gam1, beta, dt, pcm, stage1_copy, use_device_dt));
+    AB_TRY(launch_fused_stage(c, f, gam0, gam1, beta, dt, pcm, stage1_copy, use_device_dt,
+                              fold ? slots + f : nullptr));
+    if (reduce_dt) {  // new_dt = min over fluids of cfl * min dt  (EstimateTimestepMesh)
+      if (fold)
+        AB_TRY(launch_finish_dt(c, reinterpret_cast<const double *>(slots + f), 1, c->fl[f].d.cfl,
+                                c->d_time + 1, any));
+      else
+        AB_TRY(launch_estimate_dt(c, f, c->d_time + 1, any));
+    }
     any = 1;
   }
   AB_REQUIRE(any, AB200_ESTATE, "ab200_fused_stage: no fluid bound");
@@ -482,6 +498,17 @@ int ab200_exchange_ghosts(ab200_ctx *c) {
   AB_REQUIRE(c->topo.set, AB200_ESTATE, "ab200_exchange_ghosts: call ab200_set_topology first");
   for (int f = 0; f < 2; ++f)
     if (c->fl[f].bound) AB_TRY(launch_exchange(c, f));
+  return AB200_OK;
+}
+
+int ab200_fill_ghosts(ab200_ctx *c) {
+  AB_ENTER(c)
+  AB_REQUIRE(c->topo.set, AB200_ESTATE, "ab200_fill_ghosts: call ab200_set_topology first");
+  AB_REQUIRE(topology_is_local(c), AB200_ESTATE,
+             "ab200_fill_ghosts: a face is flagged AB200_BC_NONE (neighbour on another rank); "
+             "use ab200_exchange_ghosts + halo pack/unpack + ab200_apply_physical_bcs");
+  for (int f = 0; f < 2; ++f)
+    if (c->fl[f].bound) AB_TRY(launch_fill_ghosts(c, f));
   return AB200_OK;
 }
 

@@ -95,15 +95,19 @@ template <int GEOM, int FLUID, int RS, int RC>
 static int launch_dirs(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
   const int ndim = c->g.ndim;
   const int copy = a.copy_u1;
+  unsigned long long *dt_min = a.dt_min;
+  a.dt_min = nullptr;  // only the marching kernel of the last direction folds the dt reduction
   a.first = 1; a.last = (ndim == 1); a.copy_u1 = copy;
   AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 1>(c, f, a)));
   if (ndim >= 2) {
     a.first = 0; a.last = (ndim == 2); a.copy_u1 = 0;
+    a.dt_min = (ndim == 2) ? dt_min : nullptr;
     if (use_march()) AB_TRY((launch_march<GEOM, FLUID, RS, RC, 2>(c, f, a)));
     else AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 2>(c, f, a)));
   }
   if (ndim >= 3) {
     a.first = 0; a.last = 1; a.copy_u1 = 0;
+    a.dt_min = dt_min;
     if (use_march()) AB_TRY((launch_march<GEOM, FLUID, RS, RC, 3>(c, f, a)));
     else AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 3>(c, f, a)));
   }
@@ -125,7 +129,9 @@ template <int GEOM>
 int launch_fused_geom(ab200_ctx *c, int fluid, const FusedArgs &a, int pcm);
 
 template <>
-int launch_fused_geom<AB_GEOM>(ab200_ctx *c, int fluid, const FusedArgs &a, int pcm) {
+int launch_fused_geom<AB_GEOM>(ab200_ctx *c, int fluid, const FusedArgs &a_in, int pcm) {
+  FusedArgs a = a_in;
+  if (!(use_march() && c->g.ndim >= 2)) a.dt_min = nullptr;
   AB_TRY(ensure_tma(c, fluid, kTmaMaxThreads));
   const FluidDev &f = c->fl[fluid].d;
   const int recon = pcm ? AB200_PCM : f.recon;

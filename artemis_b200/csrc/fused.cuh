@@ -43,6 +43,9 @@ struct FusedArgs {
   int tiles_per_block;  // TMA: tiles per MeshBlock
   int nwork;            // TMA: nb * tiles_per_block * nspecies
   const CUtensorMap *maps;  // TMA: [3 kinds][nb*nvar] for this direction
+  // last pass of the last stage: min over zones of the CFL timestep (positive doubles order
+  // like unsigned integers), folded into the kernel that writes the new primitives
+  unsigned long long *dt_min;
 };
 
 AB_D void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }

@@ -1,4 +1,6 @@
 // fused_dispatch.cu -- runtime coordinate-system dispatch for the fused directional passes.
+#include <cstdlib>
+
 #include "fused.cuh"
 
 namespace ab200 {
@@ -12,9 +14,14 @@ template <> int launch_fused_geom<3>(ab200_ctx *, int, const FusedArgs &, int);
 template <> int launch_fused_geom<4>(ab200_ctx *, int, const FusedArgs &, int);
 template <> int launch_fused_geom<5>(ab200_ctx *, int, const FusedArgs &, int);
 
+bool fused_folds_dt(const ab200_ctx *c) {
+  return c->g.ndim >= 2 && !getenv("AB200_NO_MARCH");
+}
+
 int launch_fused_stage(ab200_ctx *c, int fluid, double gam0, double gam1, double beta, double dt,
-                       int pcm, int stage1_copy, int use_device_dt) {
+                       int pcm, int stage1_copy, int use_device_dt, unsigned long long *dt_min) {
   FusedArgs a{};
+  a.dt_min = dt_min;
   a.gam0 = gam0; a.gam1 = gam1; a.beta = beta; a.dt = dt; a.omf = c->omf;
   a.dt_dev = use_device_dt ? c->d_time : nullptr;
   a.copy_u1 = stage1_copy;

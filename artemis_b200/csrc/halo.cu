@@ -5,6 +5,8 @@
 // a neighbour at offset o in a direction sends its innermost `ng` interior cells adjacent to
 // the shared face/edge/corner and the receiver fills its `ng` ghost cells.  Copy order inside
 // a buffer is [comp][k][j][i], i fastest (P:utils/indexer.hpp:119-131).
+#include <type_traits>
+
 #include "tasks.cuh"
 
 namespace ab200 {
@@ -60,6 +62,157 @@ int launch_exchange(ab200_ctx *c, int fluid) {
   c->launches++;
   AB_CUDA(cudaGetLastError());
   return AB200_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// Fused ghost fill (single-rank fast path): ONE kernel == same-GPU exchange (K8+K9) +
+// physical boundaries (K11, outflow / reflect, in the reference's face order) + PrimToCons on
+// the ghost zones (ghost part of K12).  One thread per GHOST cell.  The sequential process
+//   neighbour copies -> BC ix1, ox1 (entire tangential range) -> ix2, ox2 -> ix3, ox3
+// composes per direction: whichever of {neighbour shift, periodic wrap, outflow clamp, reflect
+// mirror} applies along x1, x2, x3 is independent of the other two directions, so the final
+// value of every ghost cell is the value of ONE interior cell of one block (times -1 for the
+// normal velocity under each reflection).  Sources are interior cells only, which this kernel
+// never writes, so there is no ordering hazard.
+// ----------------------------------------------------------------------------------------
+template <int GEOM, int FLUID>
+__global__ void __launch_bounds__(kThreads)
+k_fill_ghosts(GridDev g, FluidDev f, int nbx, int nby, int nbz, int bc0, int bc1, int bc2,
+              int bc3, int bc4, int bc5) {
+  constexpr bool gas = (FLUID == AB200_GAS);
+  const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
+  const int gk = g.nk - nkr, gj = g.nj - njr, gi = g.ni - nir;
+  const int nK = gk * g.nj * g.ni, nJ = nkr * gj * g.ni, nI = nkr * njr * gi;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nK + nJ + nI) return;
+  const int b = blockIdx.y;
+  int i, j, k;
+  if (t < nK) {  // k-ghost planes: all j, all i
+    i = t % g.ni; t /= g.ni;
+    j = t % g.nj; t /= g.nj;
+    k = t < g.ks ? t : t - g.ks + g.ke + 1;
+  } else if (t < nK + nJ) {  // j-ghost rows of the interior planes
+    t -= nK;
+    i = t % g.ni; t /= g.ni;
+    const int jj = t % gj; t /= gj;
+    j = jj < g.js ? jj : jj - g.js + g.je + 1;
+    k = g.ks + t;
+  } else {  // i-ghost columns of the interior rows
+    t -= nK + nJ;
+    const int ii = t % gi; t /= gi;
+    i = ii < g.is ? ii : ii - g.is + g.ie + 1;
+    j = g.js + t % njr;
+    k = g.ks + t / njr;
+  }
+  const int bc[6] = {bc0, bc1, bc2, bc3, bc4, bc5};
+  const int nbd[3] = {nbx, nby, nbz};
+  const int s[3] = {g.is, g.js, g.ks}, e[3] = {g.ie, g.je, g.ke};
+  int l[3] = {b % nbx, (b / nbx) % nby, b / (nbx * nby)};
+  int src[3] = {i, j, k};
+  bool flip[3] = {false, false, false};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const int o = src[d] < s[d] ? -1 : (src[d] > e[d] ? 1 : 0);
+    if (!o) continue;
+    const int ln = l[d] + o;
+    if (ln < 0 || ln >= nbd[d]) {
+      const int type = bc[2 * d + (o > 0)];
+      if (type == AB200_BC_PERIODIC) {
+        l[d] = (ln + nbd[d]) % nbd[d];
+        src[d] -= o * (e[d] - s[d] + 1);
+      } else if (type == AB200_BC_OUTFLOW) {
+        src[d] = o > 0 ? e[d] : s[d];
+      } else if (type == AB200_BC_REFLECT) {
+        const int ref = o > 0 ? e[d] : s[d];
+        src[d] = 2 * ref + (o > 0 ? 1 : -1) - src[d];
+        flip[d] = true;
+      } else {
+        return;  // AB200_BC_NONE: another rank owns this neighbour
+      }
+    } else {
+      l[d] = ln;
+      src[d] -= o * (e[d] - s[d] + 1);
+    }
+  }
+  const int nbr = l[0] + nbx * (l[1] + nby * l[2]);
+  const size_t doff = ((size_t)k * g.nj + j) * g.ni + i;
+  const size_t soff = ((size_t)src[2] * g.nj + src[1]) * g.ni + src[0];
+  Coords<GEOM> cc(g, b, k, j, i);
+  const double hx[3] = {cc.hx1v(), cc.hx2v(), cc.hx3v()};
+  const int S = f.S;
+  const size_t ed = (size_t)b * f.nvar, es = (size_t)nbr * f.nvar;
+  for (int n = 0; n < S; ++n) {
+    // the FillGhost fields (src/gas/gas.cpp:243-270, src/dust/dust.cpp:200-212) ...
+    double w_d = f.prim[es + n][soff];
+    double vel[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double v = f.prim[es + S + 3 * n + d][soff];
+      vel[d] = flip[d] ? -1.0 * v : v;
+    }
+    // ... then PrimToCons on the ghost cell (fill_derived.cpp:217-274)
+    w_d = (w_d > f.dfloor) ? w_d : f.dfloor;
+    f.prim[ed + n][doff] = w_d;
+    f.u0[ed + n][doff] = w_d;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      f.prim[ed + S + 3 * n + d][doff] = vel[d];
+      f.u0[ed + S + 3 * n + d][doff] = w_d * vel[d] * hx[d];
+    }
+    if (gas) {
+      double w_s = f.prim[es + 5 * S + n][soff];
+      w_s = (w_s > f.siefloor) ? w_s : f.siefloor;
+      f.prim[ed + 5 * S + n][doff] = w_s;
+      const double u_u = w_s * w_d;
+      f.u0[ed + 5 * S + n][doff] = u_u;
+      f.prim[ed + 4 * S + n][doff] = dmax(0.0, f.gm1 * w_d * w_s);
+      const double ke = 0.5 * w_d * (sqr(vel[0]) + sqr(vel[1]) + sqr(vel[2]));
+      f.u0[ed + 4 * S + n][doff] = u_u + ke;
+    }
+  }
+}
+
+template <typename F>
+static int dispatch_geom_h(int geom, F &&fn) {
+  switch (geom) {
+  case 0: return fn(std::integral_constant<int, 0>{});
+  case 1: return fn(std::integral_constant<int, 1>{});
+  case 2: return fn(std::integral_constant<int, 2>{});
+  case 3: return fn(std::integral_constant<int, 3>{});
+  case 4: return fn(std::integral_constant<int, 4>{});
+  case 5: return fn(std::integral_constant<int, 5>{});
+  }
+  set_error("Coordinate type not recognized!");
+  return AB200_EINVAL;
+}
+
+bool topology_is_local(const ab200_ctx *c) {
+  for (int q = 0; q < 6; ++q)
+    if (c->topo.bc[q] == AB200_BC_NONE) return false;
+  return true;
+}
+
+int launch_fill_ghosts(ab200_ctx *c, int fluid) {
+  const GridDev &g = c->g;
+  const FluidHost &fh = c->fl[fluid];
+  const Topology &tp = c->topo;
+  const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
+  const long long nghost = (long long)g.ni * g.nj * g.nk - (long long)nir * njr * nkr;
+  if (nghost <= 0) return AB200_OK;
+  dim3 grid((unsigned)((nghost + kThreads - 1) / kThreads), (unsigned)g.nb);
+  int rc = dispatch_geom_h(g.geom, [&](auto G) {
+    constexpr int GG = decltype(G)::value;
+    if (fluid == AB200_GAS)
+      k_fill_ghosts<GG, AB200_GAS><<<grid, kThreads, 0, c->stream>>>(
+          g, fh.d, tp.nbx, tp.nby, tp.nbz, tp.bc[0], tp.bc[1], tp.bc[2], tp.bc[3], tp.bc[4], tp.bc[5]);
+    else
+      k_fill_ghosts<GG, AB200_DUST><<<grid, kThreads, 0, c->stream>>>(
+          g, fh.d, tp.nbx, tp.nby, tp.nbz, tp.bc[0], tp.bc[1], tp.bc[2], tp.bc[3], tp.bc[4], tp.bc[5]);
+    return AB200_OK;
+  });
+  c->launches++;
+  AB_CUDA(cudaGetLastError());
+  return rc;
 }
 
 // ----------------------------------------------------------------------------------------

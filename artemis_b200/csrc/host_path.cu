@@ -26,12 +26,16 @@ extern "C" int ab200_run_cycles(ab200_ctx *c, int integrator, int ncycles, doubl
   for (int cyc = 0; cyc < ncycles; ++cyc) {
     for (int s = 0; s < nst; ++s) {
       const int pcm = (s == 0 && integrator == 2);  // vl2 stage 1: artemis_driver.cpp:182
-      AB_TRY(ab200_fused_stage(c, st[s].g0, st[s].g1, st[s].b, 0.0, pcm, s == 0, 1));
-      AB_TRY(ab200_exchange_ghosts(c));
-      AB_TRY(ab200_apply_physical_bcs(c));
-      AB_TRY(ab200_prim_to_cons_ghosts(c));
+      const int flags = AB200_STAGE_DEVICE_DT | (s == nst - 1 ? AB200_STAGE_REDUCE_DT : 0);
+      AB_TRY(ab200_fused_stage(c, st[s].g0, st[s].g1, st[s].b, 0.0, pcm, s == 0, flags));
+      if (topology_is_local(c)) {
+        AB_TRY(ab200_fill_ghosts(c));
+      } else {
+        AB_TRY(ab200_exchange_ghosts(c));
+        AB_TRY(ab200_apply_physical_bcs(c));
+        AB_TRY(ab200_prim_to_cons_ghosts(c));
+      }
     }
-    AB_TRY(ab200_estimate_timestep_device(c));
     AB_TRY(ab200_set_global_timestep_device(c, tlim, 1));
   }
   return AB200_OK;

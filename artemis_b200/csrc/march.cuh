@@ -137,6 +137,7 @@ k_march_pass(GridDev g, FluidDev f, FusedArgs a) {
 #pragma unroll
   for (int m = 0; m < 8; ++m) acc[m] = 0.0;
   const int cend = s0 + L;
+  double tmin = 1.79769313486231570815e+308;
 
   // one marching step for cell c; Wa..Wd = q(c-1), q(c), q(c+1), q(c+2)
   auto step = [&](const int c, double(&Wa)[NV], double(&Wb)[NV], double(&Wc)[NV],
@@ -275,6 +276,13 @@ k_march_pass(GridDev g, FluidDev f, FusedArgs a) {
           __stcg(pu[5] + off, u_u);
           const double ke = 0.5 * w_d * (sqr(v1) + sqr(v2) + sqr(v3));
           __stcg(pu[4] + off, u_u + ke);
+          if (a.dt_min) {  // EstimateTimestepMesh folded in (src/gas/gas.cpp:411-433)
+            const double vel[3] = {v1, v2, v3};
+            tmin = dmin(tmin, cell_dt<GEOM, FLUID>(g, f, cc, w_d, vel, w_s));
+          }
+        } else if (a.dt_min) {
+          const double vel[3] = {v1, v2, v3};
+          tmin = dmin(tmin, cell_dt<GEOM, FLUID>(g, f, cc, w_d, vel, 0.0));
         }
       }
     }
@@ -299,6 +307,16 @@ k_march_pass(GridDev g, FluidDev f, FusedArgs a) {
     step(c + 1, W1, W2, W3, W0, IB, IA, QB, QA, UB, UA);
     step(c + 2, W2, W3, W0, W1, IA, IB, QA, QB, UA, UB);
     step(c + 3, W3, W0, W1, W2, IB, IA, QB, QA, UB, UA);
+  }
+  if (a.dt_min) {  // warp-shuffle min, one atomic per warp
+    if (__activemask() == 0xffffffffu) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tmin = dmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+      if ((threadIdx.x & 31) == 0)
+        atomicMin(a.dt_min, (unsigned long long)__double_as_longlong(tmin));
+    } else {
+      atomicMin(a.dt_min, (unsigned long long)__double_as_longlong(tmin));
+    }
   }
 }
 

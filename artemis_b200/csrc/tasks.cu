@@ -161,6 +161,14 @@ __global__ void k_finish_dt(const double *partial, int n, double cfl, double *ou
   }
 }
 
+int launch_finish_dt(ab200_ctx *c, const double *partial, int n, double cfl, double *d_out,
+                     int combine) {
+  k_finish_dt<<<1, 256, 0, c->stream>>>(partial, n, cfl, d_out, combine);
+  c->launches++;
+  AB_CUDA(cudaGetLastError());
+  return AB200_OK;
+}
+
 int launch_estimate_dt(ab200_ctx *c, int fluid, double *d_out, int combine) {
   const GridDev &g = c->g;
   const FluidDev &f = c->fl[fluid].d;

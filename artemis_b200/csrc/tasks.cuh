@@ -343,6 +343,27 @@ k_prim_to_cons(GridDev g, FluidDev f, int ghosts_only) {
 __global__ void __launch_bounds__(kThreads) k_deep_copy(GridDev g, FluidDev f);
 
 // K13/K14: EstimateTimestepMesh (src/gas/gas.cpp:411-433, src/dust/dust.cpp:256-272)
+// one zone: 1 / sum_d (|v_d| + c_s) / dl_d   (dust: c_s = 0)
+template <int GEOM, int FLUID>
+AB_D double cell_dt(const GridDev &g, const FluidDev &f, const Coords<GEOM> &cc, double dens,
+                    const double vel[3], double sie) {
+  constexpr bool gas = (FLUID == AB200_GAS);
+  double dx[3];
+  cc.widths(dx);
+  double cs = 0.0;
+  if (gas) {
+    // eos_ideal.hpp:136-140 BulkModulusFromDensityInternalEnergy
+    const double bulk = dmax(0.0, (f.gm1 + 1) * f.gm1 * dens * sie);
+    cs = sqrt(bulk / dens);
+  }
+  double denom = 0.0;
+  for (int d = 0; d < g.ndim; d++) {
+    const double av = fabs(vel[d]);
+    denom += gas ? (av + cs) / dx[d] : av / dx[d];
+  }
+  return 1.0 / denom;
+}
+
 template <int GEOM, int FLUID>
 __global__ void __launch_bounds__(kThreads)
 k_estimate_dt(GridDev g, FluidDev f, double *partial) {
@@ -354,26 +375,15 @@ k_estimate_dt(GridDev g, FluidDev f, double *partial) {
        t += (long long)gridDim.x * blockDim.x) {
     const CellIdx c = decode(t, nir, njr, nkr, g.is, g.js, g.ks);
     Coords<GEOM> cc(g, c.b, c.k, c.j, c.i);
-    double dx[3];
-    cc.widths(dx);
     const size_t off = ((size_t)c.k * g.nj + c.j) * g.ni + c.i;
     const size_t e = (size_t)c.b * f.nvar;
     const int S = f.S;
     for (int n = 0; n < S; ++n) {
-      double cs = 0.0;
-      if (gas) {
-        const double dens = f.prim[e + n][off];
-        const double sie = f.prim[e + 5 * S + n][off];
-        // eos_ideal.hpp:136-140 BulkModulusFromDensityInternalEnergy
-        const double bulk = dmax(0.0, (f.gm1 + 1) * f.gm1 * dens * sie);
-        cs = sqrt(bulk / dens);
-      }
-      double denom = 0.0;
-      for (int d = 0; d < g.ndim; d++) {
-        const double av = fabs(f.prim[e + S + 3 * n + d][off]);
-        denom += gas ? (av + cs) / dx[d] : av / dx[d];
-      }
-      ldt = dmin(ldt, 1.0 / denom);
+      const double dens = f.prim[e + n][off];
+      const double sie = gas ? f.prim[e + 5 * S + n][off] : 0.0;
+      const double vel[3] = {f.prim[e + S + 3 * n + 0][off], f.prim[e + S + 3 * n + 1][off],
+                             f.prim[e + S + 3 * n + 2][off]};
+      ldt = dmin(ldt, cell_dt<GEOM, FLUID>(g, f, cc, dens, vel, sie));
     }
   }
   // warp-shuffle min reduction, then one value per CTA

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AB200_ABI_VERSION 1
+#define AB200_ABI_VERSION 2
 
 /* src/artemis.hpp:78-105 */
 enum { AB200_CARTESIAN = 0, AB200_CYLINDRICAL = 1, AB200_SPHERICAL1D = 2,
@@ -146,9 +146,15 @@ int ab200_estimate_timestep(ab200_ctx *ctx, int fluid, double *dt_host);
  * One fused pass per direction: reconstruct -> Riemann -> flux difference -> update; flux
  * arrays are never materialised.  If stage1_copy != 0 the pass also writes u1 <- u0
  * (DeepCopyConservedData folded in; requires gam0 == 0, gam1 == 1).
- * dt is read from the device scalar ab200_dt_device() when use_device_dt != 0. */
+ * flags: AB200_STAGE_DEVICE_DT  dt is read from the device scalar ab200_dt_device()[0];
+ *        AB200_STAGE_REDUCE_DT  (last stage of a cycle) also leave cfl * min(dt) of every bound
+ *                               fluid in ab200_dt_device()[1], i.e. Gas/Dust::
+ *                               EstimateTimestepMesh (src/gas/gas.cpp:391-468) over the new
+ *                               interior primitives; folded into the kernel that writes them. */
+#define AB200_STAGE_DEVICE_DT 1
+#define AB200_STAGE_REDUCE_DT 2
 int ab200_fused_stage(ab200_ctx *ctx, double gam0, double gam1, double beta, double dt,
-                      int pcm, int stage1_copy, int use_device_dt);
+                      int pcm, int stage1_copy, int flags);
 /* PrimToCons restricted to ghost zones (completes :261 after the exchange). */
 int ab200_prim_to_cons_ghosts(ab200_ctx *ctx);
 
@@ -180,6 +186,11 @@ int ab200_halo_unpack(ab200_ctx *ctx, const ab200_bnd_desc *bnd, int n);
 int ab200_set_topology(ab200_ctx *ctx, int nbx, int nby, int nbz, const int bc[6]);
 int ab200_exchange_ghosts(ab200_ctx *ctx);
 int ab200_apply_physical_bcs(ab200_ctx *ctx);
+/* Single-rank fast path: ab200_exchange_ghosts + ab200_apply_physical_bcs +
+ * ab200_prim_to_cons_ghosts in ONE kernel over the ghost cells only (tasks
+ * src/artemis_driver.cpp:258-261 for a partition with no remote neighbour).  Fails with
+ * AB200_ESTATE when a lattice face is flagged AB200_BC_NONE. */
+int ab200_fill_ghosts(ab200_ctx *ctx);
 
 /* ---- host-buffer entry point (a CPU-resident Parthenon build, and bench.py's e2e leg) ----
  * Runs `ncycles` full rk/vl cycles on state held in HOST memory: uploads the gas (and dust)

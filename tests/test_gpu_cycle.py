@@ -161,25 +161,58 @@ def test_hundred_cycles_blast_within_1e9(mode):
         assert eu <= TOL_100 and ep <= TOL_100, errs
 
 
-def test_device_resident_driver_matches_host_driven():
-    """ab200_run_cycles (dt on the device, no host round trip) == the host-driven fused loop."""
-    mesh = make_mesh(Coordinates.cartesian, 3, bcs=(BoundaryFlag.outflow,) * 6)
-    gp = gas_params(Coordinates.cartesian, "ppm", "hllc")
+@pytest.mark.parametrize("coords,bc,with_dust,integ", [
+    (Coordinates.cartesian, "outflow", False, "rk2"),
+    (Coordinates.cartesian, "periodic", True, "vl2"),
+    (Coordinates.cartesian, "reflect", True, "rk3"),
+    (Coordinates.cylindrical, "mixed", True, "rk2"),
+    (Coordinates.spherical3D, "mixed", False, "rk2"),
+    (Coordinates.axisymmetric, "reflect", False, "rk2"),
+])
+def test_device_resident_driver_matches_host_driven(coords, bc, with_dust, integ):
+    """ab200_run_cycles (fused ghost fill, dt reduction folded into the last pass, dt on the
+    device, no host round trip) == the host-driven fused loop built from the per-task entry
+    points, bit for bit."""
+    B = BoundaryFlag
+    bcs = {"outflow": (B.outflow,) * 6, "periodic": (B.periodic,) * 6, "reflect": (B.reflect,) * 6,
+           "mixed": (B.reflect, B.outflow, B.periodic, B.periodic, B.outflow, B.reflect)}[bc]
+    mesh = make_mesh(coords, 3, bcs=bcs)
+    gp = gas_params(coords, "ppm", "hllc")
+    dp = dust_params(coords, "plm", "hlle", S=2) if with_dust else None
     prim = random_prim(mesh, gp, seed=11, shocks=False)
-    md1 = MeshData(mesh, gas=gp, materialize_fluxes=False)
+    dprim = random_prim(mesh, dp, seed=12, shocks=False) if with_dust else None
+    ncyc = 4
+    md1 = MeshData(mesh, gas=gp, dust=dp, materialize_fluxes=False)
     md1.gas.prim.set(prim)
-    d1 = ArtemisDriver(md1, "rk2", mode="fused", nlim=5)
+    if with_dust:
+        md1.dust.prim.set(dprim)
+    d1 = ArtemisDriver(md1, integ, mode="fused", nlim=ncyc)
     d1.Initialize()
     d1.Execute()
-    md2 = MeshData(mesh, gas=gp, materialize_fluxes=False)
+    md2 = MeshData(mesh, gas=gp, dust=dp, materialize_fluxes=False)
     md2.gas.prim.set(prim)
-    d2 = ArtemisDriver(md2, "rk2", mode="fused")
+    if with_dust:
+        md2.dust.prim.set(dprim)
+    d2 = ArtemisDriver(md2, integ, mode="fused")
     d2.Initialize()
     md2.set_time_state(d2.dt)
-    md2.call("ab200_run_cycles", 1, 5, float(np.finfo(np.float64).max))
+    code = {"rk1": 0, "rk2": 1, "vl2": 2, "rk3": 3}[integ]
+    md2.call("ab200_run_cycles", code, ncyc, float(np.finfo(np.float64).max))
     ts = md2.time_state()
-    assert ts[3] == 5 and abs(ts[2] - d1.time) <= 1e-15 * d1.time
-    assert np.array_equal(md1.gas.u0.get(), md2.gas.u0.get())
-    assert np.array_equal(md1.gas.prim.get(), md2.gas.prim.get())
+    assert ts[3] == ncyc and abs(ts[2] - d1.time) <= 1e-15 * d1.time
+    assert ts[0] == d1.dt
+    for f1, f2 in zip(md1.fluids, md2.fluids):
+        assert np.array_equal(f1.u0.get(), f2.u0.get())
+        assert np.array_equal(f1.prim.get(), f2.prim.get())
     md1.close()
     md2.close()
+
+
+def test_fill_ghosts_refuses_remote_faces():
+    from artemis_b200 import capi
+    mesh = make_mesh(Coordinates.cartesian, 3, bcs=(BoundaryFlag.outflow,) * 6)
+    gp = gas_params(Coordinates.cartesian, "ppm", "hllc")
+    md = MeshData(mesh, gas=gp, materialize_fluxes=False, bcs=[3, 1, 1, 1, 1, 1])
+    with pytest.raises(capi.AB200Error, match="AB200_BC_NONE"):
+        md.call("ab200_fill_ghosts")
+    md.close()
