@@ -43,21 +43,44 @@ def _stamp(flags):
     return h.hexdigest()
 
 
+def _closure(path, seen=None):
+    """Transitive set of quoted #include files of a source (for per-object rebuild stamps)."""
+    import re
+    seen = seen if seen is not None else set()
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    with open(path) as fh:
+        for inc in re.findall(r'#include\s+"([^"]+)"', fh.read()):
+            _closure(os.path.normpath(os.path.join(os.path.dirname(path), inc)), seen)
+    return seen
+
+
 def _compile(args):
     src, defs, suffix, variant, flags = args
     obj = os.path.join(OBJDIR, variant, os.path.splitext(src)[0] + suffix + ".o")
     os.makedirs(os.path.dirname(obj), exist_ok=True)
-    cmd = [NVCC, *ARCH, *COMMON, *flags, *defs, "-c", os.path.join(CSRC, src), "-o", obj]
+    extra = os.environ.get("AB200_EXTRA_NVCC_FLAGS", "").split()
+    cmd = [NVCC, *ARCH, *COMMON, *flags, *extra, *defs, "-c", os.path.join(CSRC, src), "-o", obj]
+    h = hashlib.sha256(" ".join(cmd).encode())
+    for dep in sorted(_closure(os.path.join(CSRC, src))):
+        with open(dep, "rb") as fh:
+            h.update(fh.read())
+    stamp = h.hexdigest()
+    if os.path.exists(obj) and os.path.exists(obj + ".stamp") and open(obj + ".stamp").read() == stamp:
+        return obj, ""
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}{suffix} [{variant}]:\n{r.stdout}\n{r.stderr}")
+    with open(obj + ".stamp", "w") as fh:
+        fh.write(stamp)
     return obj, r.stderr
 
 
 def build_variant(variant: str, flags, verbose=False, jobs=None):
     out = os.path.join(LIBDIR, f"libartemis_b200{'' if variant == 'fast' else '_' + variant}.so")
     stamp_file = out + ".stamp"
-    stamp = _stamp(flags)
+    stamp = _stamp(flags + os.environ.get("AB200_EXTRA_NVCC_FLAGS", "").split())
     if os.path.exists(out) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return out
     os.makedirs(LIBDIR, exist_ok=True)
@@ -81,6 +104,8 @@ def build_variant(variant: str, flags, verbose=False, jobs=None):
 
 def build_all(verbose=False):
     fast = build_variant("fast", ["-DAB200_FAST_MATH"], verbose)
+    if os.environ.get("AB200_BUILD_ONLY_FAST"):
+        return fast, None
     strict = build_variant("strict", ["--fmad=false"], verbose)
     return fast, strict
 

@@ -79,7 +79,8 @@ static int launch_march(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
   const int ncols = nir * (DIR == 2 ? nkr : njr);
   dim3 grid((unsigned)((ncols + kMarchThreads - 1) / kMarchThreads), (unsigned)g.nb,
             (unsigned)f.S);
-  k_march_pass<GEOM, FLUID, RS, RC, DIR><<<grid, kMarchThreads, 0, c->stream>>>(g, f, a);
+  if (a.last) k_march_pass<GEOM, FLUID, RS, RC, DIR, true><<<grid, kMarchThreads, 0, c->stream>>>(g, f, a);
+  else k_march_pass<GEOM, FLUID, RS, RC, DIR, false><<<grid, kMarchThreads, 0, c->stream>>>(g, f, a);
   c->launches++;
   AB_CUDA(cudaGetLastError());
   return AB200_OK;

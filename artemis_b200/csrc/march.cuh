@@ -25,6 +25,11 @@
 namespace ab200 {
 
 constexpr int kMarchThreads = 128;
+#ifndef AB200_MARCH_PREFETCH
+#define AB200_MARCH_PREFETCH 6
+#endif
+constexpr int kMarchPrefetch = AB200_MARCH_PREFETCH;  // steps ahead of the register window
+AB_D void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #ifndef AB200_MARCH_MIN_BLOCKS
 #define AB200_MARCH_MIN_BLOCKS 2
 #endif
@@ -56,7 +61,7 @@ AB_D void ppm_mono(double qlv, double q_i, double qrv, double &ql_ip1, double &q
   qr_i = qlv;
 }
 
-template <int GEOM, int FLUID, int RS, int RC, int DIR>
+template <int GEOM, int FLUID, int RS, int RC, int DIR, bool LAST>
 __global__ void __launch_bounds__(kMarchThreads, AB200_MARCH_MIN_BLOCKS)
 k_march_pass(GridDev g, FluidDev f, FusedArgs a) {
   static_assert(DIR == 2 || DIR == 3, "marching passes cover x2 and x3");
@@ -84,7 +89,6 @@ k_march_pass(GridDev g, FluidDev f, FusedArgs a) {
   const double dt = a.dt_dev ? *a.dt_dev : a.dt;
   const double bdt = a.beta * dt;
   const EosConsts eos{f.gm1, f.igm1, f.gamma, f.alpha};
-  const bool last = a.last;
 
   // primitives in reconstruction order (rho, v_normal, v_t1, v_t2, P, sie), hllc.hpp:66-73;
   // conserved in pack order (rho, m1, m2, m3, E, u)
@@ -125,7 +129,7 @@ k_march_pass(GridDev g, FluidDev f, FusedArgs a) {
   double IA[NV], IB[NV];                  // PPM interface values (lower / upper), alternating
   double QA[NV], QB[NV];                  // upper-edge state of the previous / current cell
   double UA[NV], UB[NV];                  // u0 of the cell being finished / prefetched
-  double acc[8];                          // lower-face contributions of the open cell
+  double AA[8], AB[8];                    // lower-face contributions of the open cell, alternating
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     W0[v] = ldq(v, s0 - 3);
@@ -135,14 +139,15 @@ k_march_pass(GridDev g, FluidDev f, FusedArgs a) {
     IA[v] = IB[v] = QA[v] = QB[v] = UA[v] = UB[v] = 0.0;
   }
 #pragma unroll
-  for (int m = 0; m < 8; ++m) acc[m] = 0.0;
+  for (int m = 0; m < 8; ++m) AA[m] = AB[m] = 0.0;
   const int cend = s0 + L;
   double tmin = 1.79769313486231570815e+308;
 
   // one marching step for cell c; Wa..Wd = q(c-1), q(c), q(c+1), q(c+2)
   auto step = [&](const int c, double(&Wa)[NV], double(&Wb)[NV], double(&Wc)[NV],
                   double(&Wd)[NV], double(&Ilo)[NV], double(&Iup)[NV], double(&Qprev)[NV],
-                  double(&Qcur)[NV], double(&Ucur)[NV], double(&Unext)[NV]) {
+                  double(&Qcur)[NV], double(&Ucur)[NV], double(&Unext)[NV],
+                  double(&acc)[8], double(&Anext)[8]) {
     if (c > cend) return;
     const int j = DIR == 2 ? c : jfix, k = DIR == 3 ? c : kfix;
     double qr[NV];
@@ -169,6 +174,14 @@ k_march_pass(GridDev g, FluidDev f, FusedArgs a) {
     }
     // q(c-1) is dead: its slot receives q(c+3); u0(c) is fetched one step ahead of its use
     if (c < cend) {
+      if (c + kMarchPrefetch < nL) {  // pull the lines of a later step into L2 now
+#pragma unroll
+        for (int v = 0; v < NV; ++v) prefetch_l2(pq[v] + (c + kMarchPrefetch) * st);
+        if (c + kMarchPrefetch - 3 < cend) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) prefetch_l2(pu[v] + (c + kMarchPrefetch - 3) * st);
+        }
+      }
 #pragma unroll
       for (int v = 0; v < NV; ++v) Wa[v] = ldq(v, c + 3);
       if (c >= s0) {
@@ -178,7 +191,8 @@ k_march_pass(GridDev g, FluidDev f, FusedArgs a) {
     }
     if (c < s0) return;
     // ---- Riemann at the lower face of cell c ------------------------------------------------
-    double lo[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double lo_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double(&lo)[8] = HOIST ? Anext : lo_;  // Cartesian fast path: F(c) IS the next step's acc
     Riemann<RS, FLUID>::solve(eos, Qprev, qr, lo);
     if (!CART) {  // ScaleMomentumFlux, fluid_fluxes.hpp:32-70
       Coords<GEOM> cf(g, b, k, j, i);
@@ -234,7 +248,7 @@ k_march_pass(GridDev g, FluidDev f, FusedArgs a) {
         }
 #undef AB_UPD
       }
-      if (!last) {
+      if (!LAST) {
 #pragma unroll
         for (int m = 0; m < NV; ++m) __stcg(pu[m] + off, u[m]);
       } else {
@@ -287,26 +301,21 @@ k_march_pass(GridDev g, FluidDev f, FusedArgs a) {
       }
     }
     // ---- start cell c: its lower-face contributions --------------------------------------------
-    if (c < cend) {
-      if (HOIST) {
+    if (!HOIST && c < cend) {
+      Coords<GEOM> cs(g, b, k, j, i);
+      const double a0 = DIR == 2 ? cs.area2(0) : cs.area3();
 #pragma unroll
-        for (int m = 0; m < 8; ++m) acc[m] = lo[m];
-      } else {
-        Coords<GEOM> cs(g, b, k, j, i);
-        const double a0 = DIR == 2 ? cs.area2(0) : cs.area3();
-#pragma unroll
-        for (int m = 0; m < 6; ++m) acc[m] = a0 * lo[m];
-        acc[6] = lo[6];
-        acc[7] = a0 * lo[7];
-      }
+      for (int m = 0; m < 6; ++m) Anext[m] = a0 * lo[m];
+      Anext[6] = lo[6];
+      Anext[7] = a0 * lo[7];
     }
   };
 
   for (int c = s0 - 2; c <= cend; c += 4) {
-    step(c + 0, W0, W1, W2, W3, IA, IB, QA, QB, UA, UB);
-    step(c + 1, W1, W2, W3, W0, IB, IA, QB, QA, UB, UA);
-    step(c + 2, W2, W3, W0, W1, IA, IB, QA, QB, UA, UB);
-    step(c + 3, W3, W0, W1, W2, IB, IA, QB, QA, UB, UA);
+    step(c + 0, W0, W1, W2, W3, IA, IB, QA, QB, UA, UB, AA, AB);
+    step(c + 1, W1, W2, W3, W0, IB, IA, QB, QA, UB, UA, AB, AA);
+    step(c + 2, W2, W3, W0, W1, IA, IB, QA, QB, UA, UB, AA, AB);
+    step(c + 3, W3, W0, W1, W2, IB, IA, QB, QA, UB, UA, AB, AA);
   }
   if (a.dt_min) {  // warp-shuffle min, one atomic per warp
     if (__activemask() == 0xffffffffu) {

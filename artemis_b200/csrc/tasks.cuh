@@ -354,14 +354,17 @@ AB_D double cell_dt(const GridDev &g, const FluidDev &f, const Coords<GEOM> &cc,
   if (gas) {
     // eos_ideal.hpp:136-140 BulkModulusFromDensityInternalEnergy
     const double bulk = dmax(0.0, (f.gm1 + 1) * f.gm1 * dens * sie);
-    cs = sqrt(bulk / dens);
+    cs = dsqrt(ddiv(bulk, dens));
   }
   double denom = 0.0;
-  for (int d = 0; d < g.ndim; d++) {
-    const double av = fabs(vel[d]);
-    denom += gas ? (av + cs) / dx[d] : av / dx[d];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    if (d < g.ndim) {
+      const double av = fabs(vel[d]);
+      denom += gas ? ddiv(av + cs, dx[d]) : ddiv(av, dx[d]);
+    }
   }
-  return 1.0 / denom;
+  return drcp(denom);
 }
 
 template <int GEOM, int FLUID>
