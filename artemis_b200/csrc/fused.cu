@@ -4,6 +4,7 @@
 
 #include "fused.cuh"
 #include "march.cuh"
+#include "xchunk.cuh"
 
 #ifndef AB_GEOM
 #error "compile with -DAB_GEOM=<0..5>"
@@ -86,6 +87,31 @@ static int launch_march(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
   return AB200_OK;
 }
 
+// x1 pass as the warp-autonomous streaming kernel (xchunk.cuh); first pass of a >= 2-D stage.
+template <int GEOM, int FLUID, int RS, int RC>
+static int launch_xchunk(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
+  const GridDev &g = c->g;
+  const int njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
+  int nseg = njr >= 32 ? 2 : 1;
+  if (const char *env = getenv("AB200_XC_NSEG")) nseg = atoi(env) > 0 ? atoi(env) : nseg;
+  if (nseg > njr) nseg = njr;
+  a.np = nseg;
+  constexpr int NV = FLUID == AB200_GAS ? 6 : 4, NF = FLUID == AB200_GAS ? 8 : 4;
+  const long long nwarps = (long long)g.nb * f.S * nkr * nseg;
+  const size_t shmem = sizeof(double) * kXcWarps * (2 * NV + NF) * 64;
+  const unsigned grid = (unsigned)((nwarps + kXcWarps - 1) / kXcWarps);
+  k_xchunk_pass<GEOM, FLUID, RS, RC><<<grid, kXcWarps * 32, shmem, c->stream>>>(g, f, a);
+  c->launches++;
+  AB_CUDA(cudaGetLastError());
+  return AB200_OK;
+}
+
+static bool use_xchunk() {
+  static int v = -1;
+  if (v < 0) v = getenv("AB200_NO_XCHUNK") ? 0 : 1;
+  return v == 1;
+}
+
 static bool use_march() {
   static int v = -1;
   if (v < 0) v = getenv("AB200_NO_MARCH") ? 0 : 1;
@@ -99,7 +125,8 @@ static int launch_dirs(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
   unsigned long long *dt_min = a.dt_min;
   a.dt_min = nullptr;  // only the marching kernel of the last direction folds the dt reduction
   a.first = 1; a.last = (ndim == 1); a.copy_u1 = copy;
-  AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 1>(c, f, a)));
+  if (ndim >= 2 && use_xchunk()) AB_TRY((launch_xchunk<GEOM, FLUID, RS, RC>(c, f, a)));
+  else AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 1>(c, f, a)));
   if (ndim >= 2) {
     a.first = 0; a.last = (ndim == 2); a.copy_u1 = 0;
     a.dt_min = (ndim == 2) ? dt_min : nullptr;
