@@ -49,7 +49,8 @@ SYMBOLS = [
     "ab200_fused_stage", "ab200_prim_to_cons_ghosts", "ab200_estimate_timestep_device",
     "ab200_set_global_timestep_device", "ab200_dt_device", "ab200_read_time_state",
     "ab200_write_time_state", "ab200_halo_pack", "ab200_halo_unpack", "ab200_set_topology",
-    "ab200_exchange_ghosts", "ab200_apply_physical_bcs", "ab200_fill_ghosts", "ab200_cycles_host",
+    "ab200_exchange_ghosts", "ab200_apply_physical_bcs", "ab200_fill_ghosts",
+    "ab200_fill_ghosts_local", "ab200_finish_remote_ghosts", "ab200_cycles_host",
     "ab200_run_cycles", "ab200_malloc", "ab200_free", "ab200_memcpy_h2d", "ab200_memcpy_d2h",
     "ab200_launch_count", "ab200_timer_begin", "ab200_timer_end",
 ]
@@ -95,7 +96,8 @@ def load(variant: str | None = None) -> C.CDLL:
         "ab200_halo_unpack": [vp, C.POINTER(BndDesc), i],
         "ab200_set_topology": [vp, i, i, i, C.POINTER(C.c_int)],
         "ab200_exchange_ghosts": [vp], "ab200_apply_physical_bcs": [vp],
-        "ab200_fill_ghosts": [vp],
+        "ab200_fill_ghosts": [vp], "ab200_fill_ghosts_local": [vp],
+        "ab200_finish_remote_ghosts": [vp],
         "ab200_cycles_host": [vp, i, i, _DP, _DP, _DP, _DP, _DP],
         "ab200_run_cycles": [vp, i, i, d],
         "ab200_malloc": [vp, C.POINTER(vp), C.c_size_t], "ab200_free": [vp, vp],

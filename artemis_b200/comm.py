@@ -133,15 +133,21 @@ class DeviceBackend:
         self.torch = torch
         self.md = md
         self.device = torch.device(f"cuda:{md.device}")
+        self._desc_cache = {}
 
     def alloc(self, n):
         return self.torch.empty(max(n, 1), dtype=self.torch.float64, device=self.device)
 
     def _descs(self, items, tensor):
-        arr = (capi.BndDesc * len(items))()
-        base = tensor.data_ptr()
-        for q, it in enumerate(items):
-            arr[q] = capi.BndDesc(*it[:10], base + 8 * it[10])
+        # plans and message buffers are persistent: build each ctypes descriptor array once
+        key = (id(items), tensor.data_ptr())
+        arr = self._desc_cache.get(key)
+        if arr is None:
+            arr = (capi.BndDesc * len(items))()
+            base = tensor.data_ptr()
+            for q, it in enumerate(items):
+                arr[q] = capi.BndDesc(*it[:10], base + 8 * it[10])
+            self._desc_cache[key] = arr
         return arr
 
     def pack(self, items, tensor):
@@ -156,6 +162,23 @@ class DeviceBackend:
         t = self.torch.tensor([value], dtype=self.torch.float64, device=self.device)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return float(t.item())
+
+    def time_state_tensor(self):
+        """Zero-copy torch view of the library's device time state (dt, new_dt, time, ncycle)
+        so the dt all-reduce runs on the device scalar with no host round trip."""
+        if getattr(self, "_ts", None) is None:
+            ptr = int(self.md.L.ab200_dt_device(self.md.ctx))
+
+            class _View:
+                __cuda_array_interface__ = {"shape": (4,), "typestr": "<f8", "data": (ptr, False),
+                                            "version": 2, "strides": None}
+
+            self._ts = self.torch.as_tensor(_View(), device=self.device)
+        return self._ts
+
+    def allreduce_min_device(self, dist):
+        """new_dt <- min over ranks, in place on the device (P:driver/driver.cpp:237)."""
+        dist.all_reduce(self.time_state_tensor()[1:2], op=dist.ReduceOp.MIN)
 
 
 class HaloComm:
@@ -180,29 +203,45 @@ class HaloComm:
             self.bufs.append(row)
         self.bytes_per_exchange = 8 * sum(p.nelem for pair in self.plans for p in pair if p)
 
+    def pack_sweep(self, d):
+        """ab200_halo_pack of both sides of direction d into the send buffers."""
+        for side, p in enumerate(self.plans[d]):
+            if p is not None:
+                self.backend.pack(p.send, self.bufs[d][side][0])
+
+    def unpack_sweep(self, d):
+        """ab200_halo_unpack of both sides of direction d from the receive buffers."""
+        for side, p in enumerate(self.plans[d]):
+            if p is not None:
+                self.backend.unpack(p.recv, self.bufs[d][side][1])
+
+    def transfer_sweep(self, d):
+        """One grouped send/recv per peer (NCCL over NVLink on GPUs)."""
+        dist = self.dist
+        pair = self.plans[d]
+        sides = [s for s in (0, 1) if pair[s] is not None]
+        ops = [dist.P2POp(dist.isend, self.bufs[d][side][0], pair[side].peer) for side in sides]
+        # two ranks + periodic: both sides face the same peer, whose lo-side message is
+        # our hi-side ghost data.  P2P ops to one peer match in posting order (NCCL has
+        # no tags), so post the receives in the peer's send order.
+        same_peer = len(sides) == 2 and pair[0].peer == pair[1].peer
+        for side in (reversed(sides) if same_peer else sides):
+            ops.append(dist.P2POp(dist.irecv, self.bufs[d][side][1], pair[side].peer))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
     def exchange(self, md=None):
         """Three sweeps; call after the same-GPU exchange and before the physical BCs."""
-        dist = self.dist
         for d, pair in enumerate(self.plans):
-            ops = []
-            sides = [s for s in (0, 1) if pair[s] is not None]
-            if not sides:
+            if pair[0] is None and pair[1] is None:
                 continue
-            for side in sides:
-                self.backend.pack(pair[side].send, self.bufs[d][side][0])
-                ops.append(dist.P2POp(dist.isend, self.bufs[d][side][0], pair[side].peer))
-            # two ranks + periodic: both sides face the same peer, whose lo-side message is
-            # our hi-side ghost data.  P2P ops to one peer match in posting order (NCCL has
-            # no tags), so post the receives in the peer's send order.
-            same_peer = len(sides) == 2 and pair[0].peer == pair[1].peer
-            for side in (reversed(sides) if same_peer else sides):
-                ops.append(dist.P2POp(dist.irecv, self.bufs[d][side][1], pair[side].peer))
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-            for side, p in enumerate(pair):
-                if p is not None:
-                    self.backend.unpack(p.recv, self.bufs[d][side][1])
+            self.pack_sweep(d)
+            self.transfer_sweep(d)
+            self.unpack_sweep(d)
 
     def allreduce_min(self, value: float) -> float:
         """MPI_Allreduce(&dt, 1, MPI_DOUBLE, MPI_MIN) of P:driver/driver.cpp:237."""
         return self.backend.allreduce_min(self.dist, value)
+
+    def allreduce_min_device(self):
+        self.backend.allreduce_min_device(self.dist)

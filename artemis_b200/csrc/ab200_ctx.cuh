@@ -74,6 +74,13 @@ struct ab200_ctx {
   // host-buffer path (ab200_cycles_host) owned device state
   std::vector<void *> host_path_allocs;
   bool host_path_ready = false;
+  // device copies of halo descriptor lists, keyed by content (ab200_halo_pack / unpack)
+  struct HaloCacheEntry {
+    size_t bytes = 0;
+    std::vector<unsigned char> host;
+    void *dev = nullptr;
+  };
+  std::vector<HaloCacheEntry> halo_cache;
 };
 
 namespace ab200 {
@@ -94,7 +101,7 @@ int launch_finish_dt(ab200_ctx *c, const double *partial, int n, double cfl, dou
                      int combine);
 int launch_exchange(ab200_ctx *c, int fluid);
 int launch_physical_bcs(ab200_ctx *c, int fluid);
-int launch_fill_ghosts(ab200_ctx *c, int fluid);
+int launch_fill_ghosts(ab200_ctx *c, int fluid, int remote_pass);
 bool topology_is_local(const ab200_ctx *c);
 int launch_halo(ab200_ctx *c, const ab200_bnd_desc *bnd, int n, int unpack);
 int launch_set_global_dt(ab200_ctx *c, double tlim, int advance_time);

@@ -183,6 +183,8 @@ int ab200_destroy(ab200_ctx *c) {
   for (int f = 0; f < 2; ++f) ab200_unbind(c, f);
   free_all(c->grid_allocs);
   free_all(c->host_path_allocs);
+  for (auto &e : c->halo_cache) cudaFree(e.dev);
+  c->halo_cache.clear();
   cudaFree(c->d_time);
   cudaFree(c->d_red);
   cudaFreeHost(c->h_pinned);
@@ -508,7 +510,25 @@ int ab200_fill_ghosts(ab200_ctx *c) {
              "ab200_fill_ghosts: a face is flagged AB200_BC_NONE (neighbour on another rank); "
              "use ab200_exchange_ghosts + halo pack/unpack + ab200_apply_physical_bcs");
   for (int f = 0; f < 2; ++f)
-    if (c->fl[f].bound) AB_TRY(launch_fill_ghosts(c, f));
+    if (c->fl[f].bound) AB_TRY(launch_fill_ghosts(c, f, 0));
+  return AB200_OK;
+}
+
+int ab200_fill_ghosts_local(ab200_ctx *c) {
+  AB_ENTER(c)
+  AB_REQUIRE(c->topo.set, AB200_ESTATE, "ab200_fill_ghosts_local: call ab200_set_topology first");
+  for (int f = 0; f < 2; ++f)
+    if (c->fl[f].bound) AB_TRY(launch_fill_ghosts(c, f, 0));
+  return AB200_OK;
+}
+
+int ab200_finish_remote_ghosts(ab200_ctx *c) {
+  AB_ENTER(c)
+  AB_REQUIRE(c->topo.set, AB200_ESTATE,
+             "ab200_finish_remote_ghosts: call ab200_set_topology first");
+  if (topology_is_local(c)) return AB200_OK;  // no face belongs to another rank
+  for (int f = 0; f < 2; ++f)
+    if (c->fl[f].bound) AB_TRY(launch_fill_ghosts(c, f, 1));
   return AB200_OK;
 }
 

@@ -5,6 +5,7 @@
 // a neighbour at offset o in a direction sends its innermost `ng` interior cells adjacent to
 // the shared face/edge/corner and the receiver fills its `ng` ghost cells.  Copy order inside
 // a buffer is [comp][k][j][i], i fastest (P:utils/indexer.hpp:119-131).
+#include <cstring>
 #include <type_traits>
 
 #include "tasks.cuh"
@@ -78,7 +79,7 @@ int launch_exchange(ab200_ctx *c, int fluid) {
 template <int GEOM, int FLUID>
 __global__ void __launch_bounds__(kThreads)
 k_fill_ghosts(GridDev g, FluidDev f, int nbx, int nby, int nbz, int bc0, int bc1, int bc2,
-              int bc3, int bc4, int bc5) {
+              int bc3, int bc4, int bc5, int remote_pass) {
   constexpr bool gas = (FLUID == AB200_GAS);
   const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
   const int gk = g.nk - nkr, gj = g.nj - njr, gi = g.ni - nir;
@@ -110,11 +111,22 @@ k_fill_ghosts(GridDev g, FluidDev f, int nbx, int nby, int nbz, int bc0, int bc1
   int l[3] = {b % nbx, (b / nbx) % nby, b / (nbx * nby)};
   int src[3] = {i, j, k};
   bool flip[3] = {false, false, false};
+  // remote_pass: second half of a multi-rank fill.  Directions that cross onto another rank
+  // (AB200_BC_NONE) keep their ghost index -- those cells were delivered by ab200_halo_unpack --
+  // and only the remaining directions are resolved; cells with no remote direction were
+  // already finished by the first pass.
+  bool remote = false, local_move = false;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const int o = src[d] < s[d] ? -1 : (src[d] > e[d] ? 1 : 0);
     if (!o) continue;
     const int ln = l[d] + o;
+    if ((ln < 0 || ln >= nbd[d]) && bc[2 * d + (o > 0)] == AB200_BC_NONE) {
+      if (!remote_pass) return;  // another rank owns this neighbour
+      remote = true;
+      continue;
+    }
+    local_move = true;
     if (ln < 0 || ln >= nbd[d]) {
       const int type = bc[2 * d + (o > 0)];
       if (type == AB200_BC_PERIODIC) {
@@ -126,14 +138,14 @@ k_fill_ghosts(GridDev g, FluidDev f, int nbx, int nby, int nbz, int bc0, int bc1
         const int ref = o > 0 ? e[d] : s[d];
         src[d] = 2 * ref + (o > 0 ? 1 : -1) - src[d];
         flip[d] = true;
-      } else {
-        return;  // AB200_BC_NONE: another rank owns this neighbour
       }
     } else {
       l[d] = ln;
       src[d] -= o * (e[d] - s[d] + 1);
     }
   }
+  if (remote_pass && !remote) return;
+  (void)local_move;
   const int nbr = l[0] + nbx * (l[1] + nby * l[2]);
   const size_t doff = ((size_t)k * g.nj + j) * g.ni + i;
   const size_t soff = ((size_t)src[2] * g.nj + src[1]) * g.ni + src[0];
@@ -192,7 +204,7 @@ bool topology_is_local(const ab200_ctx *c) {
   return true;
 }
 
-int launch_fill_ghosts(ab200_ctx *c, int fluid) {
+int launch_fill_ghosts(ab200_ctx *c, int fluid, int remote_pass) {
   const GridDev &g = c->g;
   const FluidHost &fh = c->fl[fluid];
   const Topology &tp = c->topo;
@@ -204,10 +216,10 @@ int launch_fill_ghosts(ab200_ctx *c, int fluid) {
     constexpr int GG = decltype(G)::value;
     if (fluid == AB200_GAS)
       k_fill_ghosts<GG, AB200_GAS><<<grid, kThreads, 0, c->stream>>>(
-          g, fh.d, tp.nbx, tp.nby, tp.nbz, tp.bc[0], tp.bc[1], tp.bc[2], tp.bc[3], tp.bc[4], tp.bc[5]);
+          g, fh.d, tp.nbx, tp.nby, tp.nbz, tp.bc[0], tp.bc[1], tp.bc[2], tp.bc[3], tp.bc[4], tp.bc[5], remote_pass);
     else
       k_fill_ghosts<GG, AB200_DUST><<<grid, kThreads, 0, c->stream>>>(
-          g, fh.d, tp.nbx, tp.nby, tp.nbz, tp.bc[0], tp.bc[1], tp.bc[2], tp.bc[3], tp.bc[4], tp.bc[5]);
+          g, fh.d, tp.nbx, tp.nby, tp.nbz, tp.bc[0], tp.bc[1], tp.bc[2], tp.bc[3], tp.bc[4], tp.bc[5], remote_pass);
     return AB200_OK;
   });
   c->launches++;
@@ -337,10 +349,22 @@ int launch_halo(ab200_ctx *c, const ab200_bnd_desc *bnd, int n, int unpack) {
     const long long el = (long long)b.ncomp * (b.ei - b.si + 1) * (b.ej - b.sj + 1) * (b.ek - b.sk + 1);
     if (el > maxel) maxel = el;
   }
-  BndDev *d;
-  AB_CUDA(cudaMallocAsync((void **)&d, sizeof(BndDev) * n, c->stream));
-  AB_CUDA(cudaMemcpyAsync(d, h.data(), sizeof(BndDev) * n, cudaMemcpyHostToDevice, c->stream));
-  AB_CUDA(cudaStreamSynchronize(c->stream));  // h goes out of scope
+  // Descriptor lists are static between remeshes (the caller's BndInfo cache): keep their
+  // device copies, keyed by content, so steady-state calls neither allocate nor synchronise.
+  BndDev *d = nullptr;
+  const size_t bytes = sizeof(BndDev) * (size_t)n;
+  for (auto &e : c->halo_cache)
+    if (e.bytes == bytes && memcmp(e.host.data(), h.data(), bytes) == 0) { d = (BndDev *)e.dev; break; }
+  if (!d) {
+    AB_CUDA(cudaMalloc((void **)&d, bytes));
+    AB_CUDA(cudaMemcpyAsync(d, h.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+    AB_CUDA(cudaStreamSynchronize(c->stream));  // h goes out of scope
+    ab200_ctx::HaloCacheEntry e;
+    e.bytes = bytes;
+    e.host.assign((const unsigned char *)h.data(), (const unsigned char *)h.data() + bytes);
+    e.dev = d;
+    c->halo_cache.push_back(std::move(e));
+  }
   unsigned gx = (unsigned)((maxel + kThreads - 1) / kThreads);
   if (gx > 64) gx = 64;
   dim3 grid(gx, (unsigned)n);
@@ -349,7 +373,6 @@ int launch_halo(ab200_ctx *c, const ab200_bnd_desc *bnd, int n, int unpack) {
   else k_halo<false><<<grid, kThreads, 0, c->stream>>>(g, f0, f1, d);
   c->launches++;
   AB_CUDA(cudaGetLastError());
-  AB_CUDA(cudaFreeAsync(d, c->stream));
   return AB200_OK;
 }
 

@@ -216,6 +216,35 @@ class ArtemisDriver:
         self.time += self.dt
         self.SetGlobalTimeStep()
 
+    # ---- device-resident cycle (fused path; dt, time and ncycle live on the device) ----------
+    def BeginDeviceResident(self):
+        self.md.set_time_state(self.dt, 0.0, self.time, self.ncycle)
+
+    def StepDevice(self, tlim: float = _BIG):
+        """One cycle with no host round trip: per stage ab200_fused_stage (dt read from the
+        device scalar, CFL reduction folded into the last stage) -> ghost fill; then the dt
+        all-reduce on the device scalar and ab200_set_global_timestep_device.  Multi-rank:
+        local ghost fill -> three remote face sweeps (pack / NCCL / unpack) -> finish."""
+        md, integ = self.md, self.integrator
+        for stage in range(1, integ.nstages + 1):
+            do_pcm = (stage == 1) and (integ.GetName() == "vl2")
+            flags = 1 | (2 if stage == integ.nstages else 0)  # DEVICE_DT | REDUCE_DT
+            md.call("ab200_fused_stage", integ.gam0[stage - 1], integ.gam1[stage - 1],
+                    integ.beta[stage - 1], 0.0, int(do_pcm), int(stage == 1), flags)
+            if self.comm is None:
+                md.call("ab200_fill_ghosts")
+            else:
+                md.call("ab200_fill_ghosts_local")
+                self.comm.exchange(md)
+                md.call("ab200_finish_remote_ghosts")
+        if self.comm is not None:
+            self.comm.allreduce_min_device()
+        md.call("ab200_set_global_timestep_device", float(tlim), 1)
+
+    def EndDeviceResident(self):
+        ts = self.md.time_state()
+        self.dt, self.time, self.ncycle = float(ts[0]), float(ts[2]), int(ts[3])
+
     def KeepGoing(self):
         return (self.time < self.tlim) and (self.nlim < 0 or self.ncycle < self.nlim)
 

@@ -234,10 +234,9 @@ def main():
         if world == 1:
             md.call("ab200_run_cycles", integ, 1, float(np.finfo(np.float64).max))
         else:
-            drv.Step()
+            drv.StepDevice()
 
-    if world == 1:
-        md.set_time_state(drv.dt)
+    md.set_time_state(drv.dt)
     for _ in range(args.warmup):
         one_step()
     sync_all()
@@ -338,7 +337,8 @@ def main():
                            "zones_total": zones, "ranks": list(lay),
                            "l2": "state 3.4 GB/GPU >> 126 MB L2, no flush needed",
                            "path": "fused stage kernels + device-resident dt"
-                                   if world == 1 else "fused stage kernels + NCCL halo exchange"},
+                                   if world == 1 else "fused stage kernels + NCCL halo sweeps + "
+                                   "device-resident dt all-reduce"},
                 "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks}
         if ts is not None:

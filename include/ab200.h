@@ -191,6 +191,17 @@ int ab200_apply_physical_bcs(ab200_ctx *ctx);
  * src/artemis_driver.cpp:258-261 for a partition with no remote neighbour).  Fails with
  * AB200_ESTATE when a lattice face is flagged AB200_BC_NONE. */
 int ab200_fill_ghosts(ab200_ctx *ctx);
+/* Multi-rank split of the same fill (one process per GPU, block-spatial partition):
+ *   ab200_fill_ghosts_local      every ghost cell whose neighbour chain stays on this GPU
+ *                                (same-GPU neighbours, physical boundaries) + its PrimToCons;
+ *                                cells that depend on a face flagged AB200_BC_NONE are skipped.
+ *   [caller: ab200_halo_pack -> NCCL send/recv -> ab200_halo_unpack, one sweep per direction]
+ *   ab200_finish_remote_ghosts   the skipped cells: directions that do not cross onto another
+ *                                rank are resolved (neighbour shift / outflow / reflect /
+ *                                periodic) against the just-unpacked ghost data, then
+ *                                PrimToCons.  Together: src/artemis_driver.cpp:258-261. */
+int ab200_fill_ghosts_local(ab200_ctx *ctx);
+int ab200_finish_remote_ghosts(ab200_ctx *ctx);
 
 /* ---- host-buffer entry point (a CPU-resident Parthenon build, and bench.py's e2e leg) ----
  * Runs `ncycles` full rk/vl cycles on state held in HOST memory: uploads the gas (and dust)
