@@ -46,7 +46,7 @@ SYMBOLS = [
     "ab200_set_rotating_frame", "ab200_calculate_fluxes", "ab200_apply_update",
     "ab200_flux_source", "ab200_set_auxillary_fields", "ab200_cons_to_prim",
     "ab200_prim_to_cons", "ab200_deep_copy_conserved", "ab200_estimate_timestep",
-    "ab200_fused_stage", "ab200_prim_to_cons_ghosts", "ab200_estimate_timestep_device",
+    "ab200_fused_stage", "ab200_sync_prim", "ab200_prim_to_cons_ghosts", "ab200_estimate_timestep_device",
     "ab200_set_global_timestep_device", "ab200_dt_device", "ab200_read_time_state",
     "ab200_write_time_state", "ab200_halo_pack", "ab200_halo_unpack", "ab200_set_topology",
     "ab200_exchange_ghosts", "ab200_apply_physical_bcs", "ab200_fill_ghosts",
@@ -88,7 +88,7 @@ def load(variant: str | None = None) -> C.CDLL:
         "ab200_flux_source": [vp, i, d], "ab200_set_auxillary_fields": [vp],
         "ab200_cons_to_prim": [vp], "ab200_prim_to_cons": [vp],
         "ab200_deep_copy_conserved": [vp], "ab200_estimate_timestep": [vp, i, _DP],
-        "ab200_fused_stage": [vp, d, d, d, d, i, i, i], "ab200_prim_to_cons_ghosts": [vp],
+        "ab200_fused_stage": [vp, d, d, d, d, i, i, i], "ab200_prim_to_cons_ghosts": [vp], "ab200_sync_prim": [vp],
         "ab200_estimate_timestep_device": [vp],
         "ab200_set_global_timestep_device": [vp, d, i],
         "ab200_read_time_state": [vp, _DP], "ab200_write_time_state": [vp, _DP],

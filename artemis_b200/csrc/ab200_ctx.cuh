@@ -43,9 +43,18 @@ struct FluidHost {
   bool tma_tried = false, tma_ready = false;
   void *tma_maps[3] = {nullptr, nullptr, nullptr};
   int tma_np[3] = {0, 0, 0};
+  // single-pass sweep kernel (sweep.cuh): the stage reads one primitive set and writes the
+  // other.  prim_tab[0] = the caller's arrays ("home"), prim_tab[1] = library-owned alternate
+  // set; d.prim always points at prim_tab[prim_cur], the set that holds the current state.
+  bool sw_tried = false, sw_ready = false;
+  double *const *prim_tab[2] = {nullptr, nullptr};
+  void *sw_maps[2] = {nullptr, nullptr};  // CUtensorMap[nb*nvar] per set, box {PI, PJ, 1}
+  int prim_cur = 0;
 };
 int ensure_tma(ab200_ctx *c, int fluid, int max_threads);
 void release_tma(FluidHost &fh);
+void release_sweep(FluidHost &fh);
+void *tma_encode_fn();  // cuTensorMapEncodeTiled through the runtime, or nullptr
 
 struct Topology {
   bool set = false;
@@ -97,6 +106,12 @@ int launch_fused_stage(ab200_ctx *c, int fluid, double gam0, double gam1, double
                        double dt, int pcm, int stage1_copy, int use_device_dt,
                        unsigned long long *dt_min);
 bool fused_folds_dt(const ab200_ctx *c);
+// single-pass stage (sweep.cuh / sweep_host.cu)
+bool sweep_eligible(ab200_ctx *c, int fluid);
+int launch_sweep_stage(ab200_ctx *c, int fluid, double gam0, double gam1, double beta, double dt,
+                       int pcm, int stage1_copy, int use_device_dt, unsigned long long *dt_min);
+// bring the current primitives back into the caller's arrays (no-op when already there)
+int sync_prim_home(ab200_ctx *c, int fluid, int interior_only);
 int launch_finish_dt(ab200_ctx *c, const double *partial, int n, double cfl, double *d_out,
                      int combine);
 int launch_exchange(ab200_ctx *c, int fluid);

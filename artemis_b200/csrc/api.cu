@@ -240,6 +240,7 @@ int ab200_unbind(ab200_ctx *c, int fluid) {
   if (f.ghost_vars) cudaFree(f.ghost_vars);
   if (f.ghost_vdir) cudaFree(f.ghost_vdir);
   release_tma(f);
+  release_sweep(f);
   f = FluidHost();
   return AB200_OK;
 }
@@ -325,8 +326,20 @@ int ab200_set_rotating_frame(ab200_ctx *c, double omega) {
   AB_REQUIRE((fluid) == 0 || (fluid) == 1, AB200_EINVAL, "Fluid type not recognized!");  \
   AB_REQUIRE((c)->fl[fluid].bound, AB200_ESTATE, "fluid pack not bound: call ab200_bind_pack");
 
+// Entry points that read or write the caller's primitive arrays directly first bring the
+// current primitives home (no-op unless a ping-pong stage left them in the alternate set).
+#define AB_PRIM_HOME(c)                                                                  \
+  for (int f__ = 0; f__ < 2; ++f__) AB_TRY(sync_prim_home((c), f__, 0));
+
+int ab200_sync_prim(ab200_ctx *c) {
+  AB_ENTER(c)
+  AB_PRIM_HOME(c)
+  return AB200_OK;
+}
+
 int ab200_calculate_fluxes(ab200_ctx *c, int fluid, int pcm) {
   AB_ENTER(c) AB_FLUID(c, fluid)
+  AB_PRIM_HOME(c)
   AB_TRY(ensure_scratch(c, fluid, true, false));
   return launch_calculate_fluxes(c, fluid, pcm);
 }
@@ -345,6 +358,7 @@ int ab200_apply_update(ab200_ctx *c, double gam0, double gam1, double beta_dt) {
 
 int ab200_flux_source(ab200_ctx *c, int fluid, double dt) {
   AB_ENTER(c) AB_FLUID(c, fluid)
+  AB_PRIM_HOME(c)
   if (fluid == AB200_GAS)
     AB_REQUIRE(c->fl[fluid].d.pflux[0] != nullptr, AB200_ESTATE,
                "ab200_flux_source: no interface-pressure arrays (call ab200_calculate_fluxes)");
@@ -359,6 +373,7 @@ int ab200_set_auxillary_fields(ab200_ctx *c) {
 
 int ab200_cons_to_prim(ab200_ctx *c) {
   AB_ENTER(c)
+  AB_PRIM_HOME(c)
   for (int f = 0; f < 2; ++f)
     if (c->fl[f].bound) AB_TRY(launch_cons_to_prim(c, f));
   return AB200_OK;
@@ -366,6 +381,7 @@ int ab200_cons_to_prim(ab200_ctx *c) {
 
 int ab200_prim_to_cons(ab200_ctx *c) {
   AB_ENTER(c)
+  AB_PRIM_HOME(c)
   for (int f = 0; f < 2; ++f)
     if (c->fl[f].bound) AB_TRY(launch_prim_to_cons(c, f, 0));
   return AB200_OK;
@@ -391,6 +407,7 @@ int ab200_deep_copy_conserved(ab200_ctx *c) {
 int ab200_estimate_timestep(ab200_ctx *c, int fluid, double *dt_host) {
   AB_ENTER(c) AB_FLUID(c, fluid)
   AB_REQUIRE(dt_host, AB200_EINVAL, "ab200_estimate_timestep: null output");
+  AB_PRIM_HOME(c)
   AB_TRY(launch_estimate_dt(c, fluid, c->d_red + 2048, 0));
   AB_CUDA(cudaMemcpyAsync(c->h_pinned, c->d_red + 2048, sizeof(double), cudaMemcpyDeviceToHost,
                           c->stream));
@@ -442,20 +459,31 @@ int ab200_fused_stage(ab200_ctx *c, double gam0, double gam1, double beta, doubl
   AB_ENTER(c)
   AB_REQUIRE(!stage1_copy || (gam0 == 0.0 && gam1 == 1.0), AB200_EINVAL,
              "ab200_fused_stage: stage1_copy requires gam0 == 0 and gam1 == 1");
-  AB_REQUIRE((flags & ~(AB200_STAGE_DEVICE_DT | AB200_STAGE_REDUCE_DT)) == 0, AB200_EINVAL,
-             "ab200_fused_stage: unknown flag");
+  AB_REQUIRE((flags & ~(AB200_STAGE_DEVICE_DT | AB200_STAGE_REDUCE_DT | AB200_STAGE_PINGPONG)) == 0,
+             AB200_EINVAL, "ab200_fused_stage: unknown flag");
   const int use_device_dt = (flags & AB200_STAGE_DEVICE_DT) != 0;
   const int reduce_dt = (flags & AB200_STAGE_REDUCE_DT) != 0;
-  const bool fold = reduce_dt && fused_folds_dt(c);
+  const int pingpong = (flags & AB200_STAGE_PINGPONG) != 0;
   // per-fluid raw minimum (bit pattern of a positive double), reset to a huge finite value
   unsigned long long *slots = reinterpret_cast<unsigned long long *>(c->d_red + 3072);
-  if (fold) AB_CUDA(cudaMemsetAsync(slots, 0x7f, 2 * sizeof(unsigned long long), c->stream));
+  if (reduce_dt) AB_CUDA(cudaMemsetAsync(slots, 0x7f, 2 * sizeof(unsigned long long), c->stream));
   int any = 0;
   for (int f = 0; f < 2; ++f) {
     if (!c->fl[f].bound) continue;
     AB_TRY(ensure_scratch(c, f, false, true));
-    AB_TRY(launch_fused_stage(c, f, gam0, gam1, beta, dt, pcm, stage1_copy, use_device_dt,
-                              fold ? slots + f : nullptr));
+    bool fold;
+    if (sweep_eligible(c, f)) {
+      // single-pass stage (sweep.cuh): reads the current primitive set, writes the other one
+      fold = reduce_dt;
+      AB_TRY(launch_sweep_stage(c, f, gam0, gam1, beta, dt, pcm, stage1_copy, use_device_dt,
+                                fold ? slots + f : nullptr));
+      if (!pingpong) AB_TRY(sync_prim_home(c, f, 1));  // interior zones back to the caller
+    } else {
+      AB_TRY(sync_prim_home(c, f, 0));
+      fold = reduce_dt && fused_folds_dt(c);
+      AB_TRY(launch_fused_stage(c, f, gam0, gam1, beta, dt, pcm, stage1_copy, use_device_dt,
+                                fold ? slots + f : nullptr));
+    }
     if (reduce_dt) {  // new_dt = min over fluids of cfl * min dt  (EstimateTimestepMesh)
       if (fold)
         AB_TRY(launch_finish_dt(c, reinterpret_cast<const double *>(slots + f), 1, c->fl[f].d.cfl,

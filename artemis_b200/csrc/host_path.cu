@@ -26,7 +26,8 @@ extern "C" int ab200_run_cycles(ab200_ctx *c, int integrator, int ncycles, doubl
   for (int cyc = 0; cyc < ncycles; ++cyc) {
     for (int s = 0; s < nst; ++s) {
       const int pcm = (s == 0 && integrator == 2);  // vl2 stage 1: artemis_driver.cpp:182
-      const int flags = AB200_STAGE_DEVICE_DT | (s == nst - 1 ? AB200_STAGE_REDUCE_DT : 0);
+      const int flags = AB200_STAGE_DEVICE_DT | AB200_STAGE_PINGPONG |
+                        (s == nst - 1 ? AB200_STAGE_REDUCE_DT : 0);
       AB_TRY(ab200_fused_stage(c, st[s].g0, st[s].g1, st[s].b, 0.0, pcm, s == 0, flags));
       if (topology_is_local(c)) {
         AB_TRY(ab200_fill_ghosts(c));
@@ -38,6 +39,8 @@ extern "C" int ab200_run_cycles(ab200_ctx *c, int integrator, int ncycles, doubl
     }
     AB_TRY(ab200_set_global_timestep_device(c, tlim, 1));
   }
+  // odd number of single-pass stages in total (rk1 / rk3): primitives back to the caller
+  AB_TRY(ab200_sync_prim(c));
   return AB200_OK;
 }
 

@@ -35,6 +35,8 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+void *tma_encode_fn() { return (void *)get_encode(); }
+
 // pencils per CTA for direction `dir` (1..3) given the interior extent L along it
 int tma_pencils(const ab200_ctx *c, int dir, int L, int max_threads) {
   int np = max_threads / (L + 2);

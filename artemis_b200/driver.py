@@ -228,7 +228,8 @@ class ArtemisDriver:
         md, integ = self.md, self.integrator
         for stage in range(1, integ.nstages + 1):
             do_pcm = (stage == 1) and (integ.GetName() == "vl2")
-            flags = 1 | (2 if stage == integ.nstages else 0)  # DEVICE_DT | REDUCE_DT
+            # DEVICE_DT | PINGPONG (primitives may stay in the alternate set) | REDUCE_DT
+            flags = 1 | 4 | (2 if stage == integ.nstages else 0)
             md.call("ab200_fused_stage", integ.gam0[stage - 1], integ.gam1[stage - 1],
                     integ.beta[stage - 1], 0.0, int(do_pcm), int(stage == 1), flags)
             if self.comm is None:
@@ -240,6 +241,7 @@ class ArtemisDriver:
         if self.comm is not None:
             self.comm.allreduce_min_device()
         md.call("ab200_set_global_timestep_device", float(tlim), 1)
+        md.call("ab200_sync_prim")  # no-op after an even number of single-pass stages
 
     def EndDeviceResident(self):
         ts = self.md.time_state()

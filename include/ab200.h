@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AB200_ABI_VERSION 2
+#define AB200_ABI_VERSION 3
 
 /* src/artemis.hpp:78-105 */
 enum { AB200_CARTESIAN = 0, AB200_CYLINDRICAL = 1, AB200_SPHERICAL1D = 2,
@@ -150,11 +150,25 @@ int ab200_estimate_timestep(ab200_ctx *ctx, int fluid, double *dt_host);
  *        AB200_STAGE_REDUCE_DT  (last stage of a cycle) also leave cfl * min(dt) of every bound
  *                               fluid in ab200_dt_device()[1], i.e. Gas/Dust::
  *                               EstimateTimestepMesh (src/gas/gas.cpp:391-468) over the new
- *                               interior primitives; folded into the kernel that writes them. */
+ *                               interior primitives; folded into the kernel that writes them.
+ *        AB200_STAGE_PINGPONG   3-D Cartesian meshes run the stage as ONE kernel (all three
+ *                               directions, primitives and conserved state cross HBM once) that
+ *                               reads one primitive set and writes another, because tiles of a
+ *                               MeshBlock read each other's zones as halo.  Without this flag the
+ *                               new interior primitives are copied back into the caller's arrays
+ *                               before the call returns.  With it they stay in a library-owned
+ *                               alternate set that every ghost-zone / timestep entry point below
+ *                               follows transparently, and the caller's arrays are current again
+ *                               after an even number of stages or after ab200_sync_prim(). */
 #define AB200_STAGE_DEVICE_DT 1
 #define AB200_STAGE_REDUCE_DT 2
+#define AB200_STAGE_PINGPONG 4
 int ab200_fused_stage(ab200_ctx *ctx, double gam0, double gam1, double beta, double dt,
                       int pcm, int stage1_copy, int flags);
+/* Copies the current primitives (interior and ghosts) into the caller's arrays if a
+ * AB200_STAGE_PINGPONG stage left them in the alternate set; no-op otherwise.  Entry points
+ * that hand the caller's primitive arrays to task-level kernels call it implicitly. */
+int ab200_sync_prim(ab200_ctx *ctx);
 /* PrimToCons restricted to ghost zones (completes :261 after the exchange). */
 int ab200_prim_to_cons_ghosts(ab200_ctx *ctx);
 
