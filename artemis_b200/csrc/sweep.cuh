@@ -48,7 +48,10 @@ namespace ab200 {
 #define AB200_SW_HALO_THREADS 64
 #endif
 constexpr int kSwTI = AB200_SW_TI, kSwTJ = AB200_SW_TJ, kSwH = 3;
-constexpr int kSwPI = kSwTI + 2 * kSwH, kSwPJ = kSwTJ + 2 * kSwH;
+// TMA needs a 16-byte aligned global start address along i (an odd fp64 start coordinate is an
+// illegal instruction on sm_100a), so the staged row starts at the even column i0-3 or i0-4
+// and is TI+8 wide; HX (3 or 4, CTA-uniform) is the own tile's column offset inside the row.
+constexpr int kSwPI = kSwTI + 2 * kSwH + 2, kSwPJ = kSwTJ + 2 * kSwH;
 constexpr int kSwMain = kSwTI * kSwTJ;
 constexpr int kSwHalo = AB200_SW_HALO_THREADS;
 constexpr int kSwThreads = kSwMain + kSwHalo;
@@ -56,6 +59,7 @@ constexpr int kSwRing = 4;
 // doubles per staged variable tile (TMA destinations are 128-byte aligned)
 constexpr int kSwTile = ((kSwPI * kSwPJ * 8 + 127) / 128) * 16;
 static_assert(kSwMain % 32 == 0 && kSwHalo % 32 == 0, "whole warps per role");
+static_assert(kSwTI % 2 == 0, "tile origin parity must not depend on the tile index");
 static_assert((kSwPI * 8) % 16 == 0, "TMA inner box extent must be a multiple of 16 bytes");
 
 struct SweepArgs {
@@ -138,6 +142,7 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
   const int b = blockIdx.y, n = blockIdx.z;
   const int S = f.S, nvar = f.nvar;
   const int i0 = g.is + tx * TI, j0 = g.js + ty * TJ;
+  const int HX = H + ((g.is - H) & 1);  // even TMA start column
   const int i = i0 + ci, j = j0 + cj;
   const bool active = is_main && i <= g.ie && j <= g.je;
   const int nkr = g.ke - g.ks + 1;
@@ -167,7 +172,7 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
     const CUtensorMap *mp = a.maps + (size_t)b * nvar;
 #pragma unroll
     for (int v = 0; v < NV; ++v)
-      tma_load_3d(dst + v * kSwTile, mp + pv[v], bar + slot, i0 - H, j0 - H, g.ks - H + p);
+      tma_load_3d(dst + v * kSwTile, mp + pv[v], bar + slot, i0 - HX, j0 - H, g.ks - H + p);
   };
   if (tid == 0) {
     for (int p = 0; p < kSwRing && p < nplanes; ++p) issue(p);
@@ -177,7 +182,7 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
   const double bdt = a.beta * dt;
   const EosConsts eos{f.gm1, f.igm1, f.gamma, f.alpha};
 
-  const int pc = (cj + H) * PI + (ci + H);  // own column inside a staged variable tile
+  const int pc = (cj + H) * PI + (ci + HX);  // own column inside a staged variable tile
   const int h = tid - kSwMain;              // halo-thread index
 
 #ifdef AB200_FAST_MATH
@@ -250,11 +255,11 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
         int p, s, dst, vs;
         if (t < 3 * TJ) {
           const int r = t / 3, e = t - 3 * r, c = e == 0 ? -1 : TI + e - 1;
-          p = (r + H) * PI + c + H; s = 1;
+          p = (r + H) * PI + c + HX; s = 1;
           dst = SM::ix + r * (TI + 3) + c + 1; vs = SM::ix_vs;
         } else {
           const int tt = t - 3 * TJ, c = tt % TI, e = tt / TI, r = e == 0 ? -1 : TJ + e - 1;
-          p = (r + H) * PI + c + H; s = PI;
+          p = (r + H) * PI + c + HX; s = PI;
           dst = SM::iy + (r + 1) * TI + c; vs = SM::iy_vs;
         }
 #pragma unroll
@@ -301,7 +306,7 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
           const int r = t >> 1;
           side = t & 1;
           const int c = side ? TI : -1;
-          p = (r + H) * PI + c + H; s = 1;
+          p = (r + H) * PI + c + HX; s = 1;
           ilo = SM::ix + r * (TI + 3) + c + 1; iup = ilo + 1; ivs = SM::ix_vs;
           out = side ? SM::qhx + r : SM::qlx + r * (TI + 1);
           ovs = side ? SM::qhx_vs : SM::qlx_vs;
@@ -309,7 +314,7 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
           const int tt = t - 2 * TJ, c = tt % TI;
           side = tt / TI;
           const int r = side ? TJ : -1;
-          p = (r + H) * PI + c + H; s = PI;
+          p = (r + H) * PI + c + HX; s = PI;
           ilo = SM::iy + (r + 1) * TI + c; iup = ilo + TI; ivs = SM::iy_vs;
           out = side ? SM::qhy + c : SM::qly + c;
           ovs = side ? SM::qhy_vs : SM::qly_vs;

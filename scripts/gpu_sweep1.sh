@@ -1,13 +1,16 @@
 #!/bin/bash
-# GPU visit for the single-pass sweep kernel: sanitizer on one small case, parity tests, bench,
-# launch list and one full ncu capture.
+# GPU visit for the single-pass sweep kernel: parity tests (sanitizer on one small case only if
+# they fail), bench, launch list and one full ncu capture, then the rest of the GPU suite.
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt
-timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest "tests/test_gpu_sweep.py::test_sweep_fast_within_1e12_one_cycle[periodic-bnx1]" -q -x 2>&1 | tail -40 > gpurun_out/sanitizer.log
-echo "sanitizer:"; tail -12 gpurun_out/sanitizer.log
+nproc >> gpurun_out/gpu.txt; lscpu | grep -E "Model name|^CPU\(s\)|Thread|Core|Socket" >> gpurun_out/gpu.txt
 timeout 1200 python -m pytest tests/test_gpu_sweep.py -q 2>&1 | tail -40 > gpurun_out/pytest_sweep.log
 echo "sweep tests:"; tail -25 gpurun_out/pytest_sweep.log
+if ! grep -q " passed" gpurun_out/pytest_sweep.log || grep -q "failed" gpurun_out/pytest_sweep.log; then
+  timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest "tests/test_gpu_sweep.py::test_sweep_fast_within_1e12_one_cycle[periodic-bnx1]" -q -x 2>&1 | tail -40 > gpurun_out/sanitizer.log
+  echo "sanitizer:"; tail -12 gpurun_out/sanitizer.log
+fi
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench.json 2> gpurun_out/bench.err
 echo "bench rc=$?"
 python - <<'PY'
@@ -19,6 +22,8 @@ except Exception as e:
     print("bench parse failed", e)
 PY
 tail -5 gpurun_out/bench.err
+AB200_NO_SWEEP=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_3pass.json 2>> gpurun_out/bench.err
+echo "3-pass bench:"; cut -c1-400 gpurun_out/bench_3pass.json
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_executed_pipe_fp64.sum,smsp__inst_executed.sum --clock-control none -s 20 -c 16 --csv \
     --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu_bench.log 2>&1
 echo "ncu launches rc=$?"
