@@ -483,7 +483,11 @@ struct Riemann<AB200_HLLE, FLUID> {  // hlle.hpp:92-220
     const double sqrtdl = sqrt(wl_idn);
     const double sqrtdr = sqrt(wr_idn);
     const double isdlpdr = drcp(sqrtdl + sqrtdr);
-    const double wroe_ivx = (sqrtdl * wl_ivx + sqrtdr * wr_ivx) * isdlpdr;
+    // No FMA contraction in the normal Roe velocity: at a reflecting wall (mirrored states) the
+    // two products must cancel EXACTLY like in the reference's build, because the pressureless
+    // wave-speed clamp below (bp/bm = +-1e-20) turns the sign of a rounding residual into an
+    // O(1) change of the flux (hlle.hpp:164-173, 198-199).
+    const double wroe_ivx = __dadd_rn(__dmul_rn(sqrtdl, wl_ivx), __dmul_rn(sqrtdr, wr_ivx)) * isdlpdr;
     const double wroe_ivy = (sqrtdl * wl_ivy + sqrtdr * wr_ivy) * isdlpdr;
     const double wroe_ivz = (sqrtdl * wl_ivz + sqrtdr * wr_ivz) * isdlpdr;
     double el = 0, er = 0, hroe = 0;

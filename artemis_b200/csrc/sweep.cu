@@ -8,11 +8,11 @@
 
 namespace ab200 {
 
-template <int FLUID, int RS, int RC>
-static int launch_one(ab200_ctx *c, const FluidDev &f, const SweepArgs &a) {
+template <int FLUID, int RS, int RC, int MODE>
+static int launch_mode(ab200_ctx *c, const FluidDev &f, const SweepArgs &a) {
   constexpr int NV = FLUID == AB200_GAS ? 6 : 4, NF = FLUID == AB200_GAS ? 8 : 4;
   const size_t shmem = SwSmem<NV, NF>::bytes;
-  auto kern = k_sweep_stage<FLUID, RS, RC>;
+  auto kern = k_sweep_stage<FLUID, RS, RC, MODE>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
@@ -23,6 +23,14 @@ static int launch_one(ab200_ctx *c, const FluidDev &f, const SweepArgs &a) {
   c->launches++;
   AB_CUDA(cudaGetLastError());
   return AB200_OK;
+}
+
+// ApplyUpdate base term resolved at compile time (see k_sweep_stage)
+template <int FLUID, int RS, int RC>
+static int launch_one(ab200_ctx *c, const FluidDev &f, const SweepArgs &a) {
+  if (a.copy_u1) return launch_mode<FLUID, RS, RC, 0>(c, f, a);
+  if (a.gam0 == 0.0) return launch_mode<FLUID, RS, RC, 1>(c, f, a);
+  return launch_mode<FLUID, RS, RC, 2>(c, f, a);
 }
 
 template <int FLUID, int RS>

@@ -34,6 +34,8 @@
 // the stage cannot update the primitives in place.  The host side ping-pongs between the
 // caller's arrays and a library-owned alternate set (sweep.cu).
 #pragma once
+#include <type_traits>
+
 #include "march.cuh"
 
 namespace ab200 {
@@ -81,20 +83,25 @@ struct SwSmem {
   static constexpr int ix_vs = kSwTJ * (kSwTI + 3);       // lower iface of cells -1..TI+1
   static constexpr int iy = ix + NV * ix_vs;
   static constexpr int iy_vs = (kSwTJ + 3) * kSwTI;
+  // Left states at faces 0..TI (P2 -> P3) and, in the SAME slots, the face quantities the
+  // Riemann solve of that face produces (P3 -> P4): a face slot is read and then overwritten
+  // by the one thread that owns the face, so the two generations can share memory.
   static constexpr int qlx = iy + NV * iy_vs;
-  static constexpr int qlx_vs = kSwTJ * (kSwTI + 1);      // left state at faces 0..TI
-  static constexpr int qly = qlx + NV * qlx_vs;
+  static constexpr int qlx_vs = kSwTJ * (kSwTI + 1);
+  static constexpr int fx = qlx, fx_vs = qlx_vs;
+  static constexpr int qly = qlx + NF * qlx_vs;
   static constexpr int qly_vs = (kSwTJ + 1) * kSwTI;
-  static constexpr int qhx = qly + NV * qly_vs;           // right state at face TI
+  static constexpr int fy = qly, fy_vs = qly_vs;
+  static constexpr int qhx = qly + NF * qly_vs;           // right state at face TI
   static constexpr int qhx_vs = kSwTJ;
   static constexpr int qhy = qhx + NV * qhx_vs;
   static constexpr int qhy_vs = kSwTI;
-  static constexpr int fx = qhy + NV * qhy_vs;
-  static constexpr int fx_vs = kSwTJ * (kSwTI + 1);       // face quantities at faces 0..TI
-  static constexpr int fy = fx + NF * fx_vs;
-  static constexpr int fy_vs = (kSwTJ + 1) * kSwTI;
-  static constexpr int ust = fy + NF * fy_vs;             // [2*NV][kSwMain] u0 | u1 of own zone
-  static constexpr int total = ust + 2 * NV * kSwMain;
+  static constexpr int ust = qhy + NV * qhy_vs;           // [2*NV][kSwMain] u0 | u1 of own zone
+  // x3 march state kept out of the register file (private slot per thread): face quantities
+  // at the lower x3 face of the current cell, upper-edge state of the cell below
+  static constexpr int fzs = ust + 2 * NV * kSwMain;      // [NF][kSwMain]
+  static constexpr int qus = fzs + NF * kSwMain;          // [NV][kSwMain]
+  static constexpr int total = qus + NV * kSwMain;
   static constexpr size_t bytes = (size_t)total * 8;
 };
 static_assert(SwSmem<6, 8>::bytes <= 227 * 1024, "sweep tile does not fit shared memory");
@@ -121,13 +128,19 @@ AB_D void sw_recon(const double *q, int s, double ilo, double iup, double &ql_up
   }
 }
 
-template <int FLUID, int RS, int RC>
+// MODE selects the ApplyUpdate base term (artemis_integrator.hpp:95-106) at compile time:
+//   0  stage 1 of every integrator here (gam0 = 0, gam1 = 1, u1 == u0 on entry): base = u0 and
+//      DeepCopyConservedData is folded in (u1 <- u0); u1 is never read
+//   1  gam0 == 0: base = gam1 * u1; u0 is never read
+//   2  general:   base = gam0 * u0 + gam1 * u1
+template <int FLUID, int RS, int RC, int MODE>
 __global__ void __launch_bounds__(kSwThreads, 1)
 k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
   constexpr bool gas = (FLUID == AB200_GAS);
   constexpr int NV = gas ? 6 : 4;   // reconstructed variables per species
   constexpr int NF = gas ? 8 : 4;   // face quantities per species
   constexpr bool PPM = (RC == AB200_PPM);
+  constexpr bool need_u0 = (MODE != 1), need_u1 = (MODE != 0);
   using SM = SwSmem<NV, NF>;
   constexpr int TI = kSwTI, TJ = kSwTJ, H = kSwH, PI = kSwPI;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -150,14 +163,13 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
   const int nsteps = nkr + H;       // k = ks-3 .. ke (the first three steps only warm up x3)
 
   // pack order: rho, v1|m1, v2|m2, v3|m3, (P|E, sie|u)
-  const int pv[6] = {n, S + 3 * n, S + 3 * n + 1, S + 3 * n + 2, 4 * S + n, 5 * S + n};
-  const bool need_u0 = a.copy_u1 || a.gam0 != 0.0;
-  const bool need_u1 = !a.copy_u1 && a.gam1 != 0.0;
+  const int pv0 = n, pv1 = S + 3 * n, pv4 = 4 * S + n, pv5 = 5 * S + n;
+  auto pvx = [&](int m) { return m == 0 ? pv0 : (m < 4 ? pv1 + m - 1 : (m == 4 ? pv4 : pv5)); };
 
   if (tid < 3 * NV) {
     const int kind = tid / NV, m = tid - kind * NV;
     double *const *tab = kind == 0 ? f.u0 : (kind == 1 ? f.u1 : a.prim_out);
-    s_ptr[tid] = tab ? tab[(size_t)b * nvar + pv[m]] : nullptr;
+    s_ptr[tid] = tab ? tab[(size_t)b * nvar + pvx(m)] : nullptr;
   }
   if (tid == 0) {
 #pragma unroll
@@ -172,7 +184,7 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
     const CUtensorMap *mp = a.maps + (size_t)b * nvar;
 #pragma unroll
     for (int v = 0; v < NV; ++v)
-      tma_load_3d(dst + v * kSwTile, mp + pv[v], bar + slot, i0 - HX, j0 - H, g.ks - H + p);
+      tma_load_3d(dst + v * kSwTile, mp + pvx(v), bar + slot, i0 - HX, j0 - H, g.ks - H + p);
   };
   if (tid == 0) {
     for (int p = 0; p < kSwRing && p < nplanes; ++p) issue(p);
@@ -183,53 +195,49 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
   const EosConsts eos{f.gm1, f.igm1, f.gamma, f.alpha};
 
   const int pc = (cj + H) * PI + (ci + HX);  // own column inside a staged variable tile
-  const int h = tid - kSwMain;              // halo-thread index
+  const int h = tid - kSwMain;               // halo-thread index
+  const int ii = active ? i : g.is, jj = active ? j : g.js;
+  const double *x3f = g.t.x3f + (size_t)b * (g.nk + 1);
 
 #ifdef AB200_FAST_MATH
   // Cartesian: A_d / V = 1 / dx_d; one reciprocal per thread (x1, x2) and per plane (x3)
   double rx = 0.0, ry = 0.0;
   if (is_main) {
     const double *x1f = g.t.x1f + (size_t)b * (g.ni + 1), *x2f = g.t.x2f + (size_t)b * (g.nj + 1);
-    const int ii = active ? i : g.is, jj = active ? j : g.js;
     rx = ddiv(bdt, x1f[ii + 1] - x1f[ii]);
     ry = ddiv(bdt, x2f[jj + 1] - x2f[jj]);
   }
 #endif
 
-  // carried across planes (x3 march): interface value I(k|k+1), upper-edge state of cell k,
-  // face quantities at the lower face of cell k (momentum fluxes in pack order)
-  double Ilo[NV], Qup[NV], Fz[NF];
+  // carried across planes (x3 march): interface value I(k|k+1) in registers; the upper-edge
+  // state of cell k (qus) and the face quantities at the lower face of cell k (fzs, momentum
+  // fluxes in pack order) in private shared-memory slots
+  double Ilo[NV];
 #pragma unroll
-  for (int v = 0; v < NV; ++v) Ilo[v] = Qup[v] = 0.0;
-#pragma unroll
-  for (int m = 0; m < NF; ++m) Fz[m] = 0.0;
+  for (int v = 0; v < NV; ++v) Ilo[v] = 0.0;
   double tmin = 1.79769313486231570815e+308;
 
-  for (int st = 0; st < nsteps; ++st) {
+  // One plane step.  INP: the plane k = ks-3+st is an interior plane (in-plane x1/x2 work and
+  // the zone update happen); ZR: the x3 Riemann problem at face k+1 is solved (st >= 2).
+  // The first three steps (planes ks-3 .. ks-1) only warm up the x3 march and are instantiated
+  // without any in-plane code, so the steady-state loop body carries no `inplane` branches.
+  auto step = [&](auto inp_tag, auto zr_tag, const int st) {
+    constexpr bool INP = decltype(inp_tag)::value;
+    constexpr bool ZR = decltype(zr_tag)::value;
     const int k = g.ks - H + st;
-    const bool inplane = (st >= H);
-    // ---- wait for the planes this step reads for the first time -------------------------------
-    // (plane k+3, needed by the x3 interface value only, is waited for at the top of P2 so
-    // that its TMA latency hides behind P3/P4 of the previous step and P1 of this one)
-    if (st == 0) {
-      for (int p = 0; p < kSwRing - 1; ++p) mbar_wait(bar + p, 0);
-    }
     const double *R0 = sm + SM::ring + ((st + 0) & 3) * NV * kSwTile;  // plane k
     const double *R1 = sm + SM::ring + ((st + 1) & 3) * NV * kSwTile;
     const double *R2 = sm + SM::ring + ((st + 2) & 3) * NV * kSwTile;
     const double *R3 = sm + SM::ring + ((st + 3) & 3) * NV * kSwTile;
+    const int off = (k * g.nj + jj) * g.ni + ii;
 
-    double W0[NV], W1[NV], Inew[NV], Ixl[NV], Iyl[NV];
+    double W0[NV], Ixl[NV], Iyl[NV];
     // =========================== P1: interface values ==========================================
     if (is_main) {
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        W0[v] = R0[v * kSwTile + pc];
-        Inew[v] = Ixl[v] = Iyl[v] = 0.0;
-      }
-      if (inplane) {
+      for (int v = 0; v < NV; ++v) W0[v] = R0[v * kSwTile + pc];
+      if (INP) {
         if (active) {  // own zone's u0 / u1 -> private shared-memory slots, asynchronously
-          const int off = (k * g.nj + j) * g.ni + i;
 #pragma unroll
           for (int m = 0; m < NV; ++m) {
             if (need_u0) cp_async8(sm + SM::ust + m * kSwMain + tid, s_ptr[m] + off);
@@ -248,7 +256,7 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
           }
         }
       }
-    } else if (inplane && PPM) {
+    } else if (INP && PPM) {
       // halo: lower interface value of cells -1, TI, TI+1 of every row (x1) and of rows
       // -1, TJ, TJ+1 of every column (x2)
       for (int t = h; t < 3 * TJ + 3 * TI; t += kSwHalo) {
@@ -269,22 +277,49 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
         }
       }
     }
-    if (inplane && PPM) __syncthreads();
+    // (also orders P4 of the previous step, which reads the face slots, before P2 refills them)
+    if (INP) __syncthreads();
 
     // =========================== P2: limit the cells ===========================================
-    double QupN[NV], qrz[NV], qrx[NV], qry[NV];
+    // plane k+3 (needed by the x3 interface value only) is waited for here so that its TMA
+    // latency hides behind P3/P4 of the previous step and P1 of this one
+    double Inew[NV], QupN[NV], qrx[NV], qry[NV], FzN[NF];
     mbar_wait(bar + ((st + 3) & (kSwRing - 1)), (uint32_t)(((st + 3) >> 2) & 1));
     if (is_main) {
 #pragma unroll
+      double qrz[NV];
+#pragma unroll
       for (int v = 0; v < NV; ++v) {  // x3: interface value I(k+1|k+2), then cell k+1
-        qrx[v] = qry[v] = 0.0;
-        W1[v] = R1[v * kSwTile + pc];
-        if (PPM) Inew[v] = ppm_iface(W0[v], W1[v], R2[v * kSwTile + pc], R3[v * kSwTile + pc]);
-        if (PPM) ppm_mono(Ilo[v], W1[v], Inew[v], QupN[v], qrz[v]);
-        else if (RC == AB200_PLM) plm(W0[v], W1[v], R2[v * kSwTile + pc], QupN[v], qrz[v]);
-        else { QupN[v] = W1[v]; qrz[v] = W1[v]; }
+        const double W1 = R1[v * kSwTile + pc];
+        if (PPM) {
+          Inew[v] = ppm_iface(W0[v], W1, R2[v * kSwTile + pc], R3[v * kSwTile + pc]);
+          ppm_mono(Ilo[v], W1, Inew[v], QupN[v], qrz[v]);
+        } else if (RC == AB200_PLM) {
+          plm(W0[v], W1, R2[v * kSwTile + pc], QupN[v], qrz[v]);
+        } else {
+          QupN[v] = W1;
+          qrz[v] = W1;
+        }
       }
-      if (inplane) {
+      // the x3 Riemann problem is solved here, before the in-plane limiting, so that Qup / qrz
+      // are dead when the x1 / x2 states become live (register pressure of P3)
+      if (ZR) {  // x3, face k+1: recon order (rho, v3, v1, v2, P, sie)
+        double wl[NV], wr[NV], out[8];
+        const double *Qup = sm + SM::qus + tid;
+        wl[0] = Qup[0]; wl[1] = Qup[3 * kSwMain]; wl[2] = Qup[1 * kSwMain];
+        wl[3] = Qup[2 * kSwMain];
+        wr[0] = qrz[0]; wr[1] = qrz[3]; wr[2] = qrz[1]; wr[3] = qrz[2];
+        if (gas) {
+          wl[4] = Qup[4 * kSwMain]; wl[5] = Qup[5 * kSwMain];
+          wr[4] = qrz[4]; wr[5] = qrz[5];
+        }
+        Riemann<RS, FLUID>::solve(eos, wl, wr, out);
+        FzN[0] = out[0]; FzN[3] = out[1]; FzN[1] = out[2]; FzN[2] = out[3];
+        if (gas) { FzN[4] = out[4]; FzN[5] = out[5]; FzN[6] = out[6]; FzN[7] = out[7]; }
+      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) sm[SM::qus + v * kSwMain + tid] = QupN[v];
+      if (INP) {
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           const double *q = R0 + v * kSwTile + pc;
@@ -297,7 +332,7 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
           sm[SM::qly + v * SM::qly_vs + (cj + 1) * TI + ci] = ql;
         }
       }
-    } else if (inplane) {
+    } else if (INP) {
       // halo: cells -1 (upper edge -> left state of face 0) and TI / TJ (lower edge -> right
       // state of the last face)
       for (int t = h; t < 2 * TJ + 2 * TI; t += kSwHalo) {
@@ -333,20 +368,15 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
     if (tid == 0 && st + kSwRing < nplanes) issue(st + kSwRing);
 
     // =========================== P3: Riemann solves ============================================
-    double FzN[NF];
-#pragma unroll
-    for (int m = 0; m < NF; ++m) FzN[m] = 0.0;
+#ifdef AB200_FAST_MATH
+    double z0 = 0.0, z1 = 1.0;
+    if (INP && is_main) {  // issued here so the table latency hides behind the Riemann solves
+      z0 = x3f[k];
+      z1 = x3f[k + 1];
+    }
+#endif
     if (is_main) {
-      if (st >= 2) {  // x3, face k+1: recon order (rho, v3, v1, v2, P, sie)
-        double wl[NV], wr[NV], out[8];
-        wl[0] = Qup[0]; wl[1] = Qup[3]; wl[2] = Qup[1]; wl[3] = Qup[2];
-        wr[0] = qrz[0]; wr[1] = qrz[3]; wr[2] = qrz[1]; wr[3] = qrz[2];
-        if (gas) { wl[4] = Qup[4]; wl[5] = Qup[5]; wr[4] = qrz[4]; wr[5] = qrz[5]; }
-        Riemann<RS, FLUID>::solve(eos, wl, wr, out);
-        FzN[0] = out[0]; FzN[3] = out[1]; FzN[1] = out[2]; FzN[2] = out[3];
-        if (gas) { FzN[4] = out[4]; FzN[5] = out[5]; FzN[6] = out[6]; FzN[7] = out[7]; }
-      }
-      if (inplane) {
+      if (INP) {
         {  // x1, face ci: recon order == pack order
           double wl[NV], out[8];
 #pragma unroll
@@ -376,7 +406,7 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
           }
         }
       }
-    } else if (inplane) {
+    } else if (INP) {
       // halo: the last face of every row (x1, face TI) and of every column (x2, face TJ)
       for (int t = h; t < TJ + TI; t += kSwHalo) {
         const bool isx = t < TJ;
@@ -413,19 +443,19 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
         }
       }
     }
-    if (inplane) __syncthreads();
+    if (INP) __syncthreads();
 
     // =========================== P4: update the zone ===========================================
-    if (is_main && inplane) {
+    if (INP && is_main) {
       cp_async_wait_all();
-      const int off = (k * g.nj + j) * g.ni + i;
       const int ox = cj * (TI + 1) + ci, oy = cj * TI + ci;
-      double u[6] = {0, 0, 0, 0, 0, 0};
+      double u[6], Fz[NF];
+#pragma unroll
+      for (int m = 0; m < NF; ++m) Fz[m] = sm[SM::fzs + m * kSwMain + tid];
 #ifdef AB200_FAST_MATH
-      const double *x3f = g.t.x3f + (size_t)b * (g.nk + 1);
-      const double rz = ddiv(bdt, x3f[k + 1] - x3f[k]);
+      const double rz = ddiv(bdt, z1 - z0);
 #else
-      Coords<AB200_CARTESIAN> cc(g, b, k, active ? j : g.js, active ? i : g.is);
+      Coords<AB200_CARTESIAN> cc(g, b, k, jj, ii);
       const double ax1[2] = {cc.area1(cc.x1[0]), cc.area1(cc.x1[1])};
       const double ax2[2] = {cc.area2(0), cc.area2(1)};
       const double ax3[2] = {cc.area3(), cc.area3()};
@@ -435,14 +465,15 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
       for (int m = 0; m < NV; ++m) {
         const double xl = sm[SM::fx + m * SM::fx_vs + ox], xh = sm[SM::fx + m * SM::fx_vs + ox + 1];
         const double yl = sm[SM::fy + m * SM::fy_vs + oy], yh = sm[SM::fy + m * SM::fy_vs + oy + TI];
-        const double v0 = need_u0 ? sm[SM::ust + m * kSwMain + tid] : 0.0;
-        const double v1 = need_u1 ? sm[SM::ust + (NV + m) * kSwMain + tid] : 0.0;
         double base;
-        if (a.copy_u1) {
-          base = v0;
-          if (active) __stcg(s_ptr[NV + m] + off, v0);  // u1 <- u0
+        if (MODE == 0) {
+          base = sm[SM::ust + m * kSwMain + tid];
+          if (active) __stcg(s_ptr[NV + m] + off, base);  // u1 <- u0
+        } else if (MODE == 1) {
+          base = a.gam1 * sm[SM::ust + (NV + m) * kSwMain + tid];
         } else {
-          base = (a.gam0 == 0.0) ? a.gam1 * v1 : a.gam0 * v0 + a.gam1 * v1;
+          base = a.gam0 * sm[SM::ust + m * kSwMain + tid] +
+                 a.gam1 * sm[SM::ust + (NV + m) * kSwMain + tid];
         }
         // ApplyUpdate (artemis_integrator.hpp:95-106)
 #ifdef AB200_FAST_MATH
@@ -525,11 +556,27 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
       }
     }
     // ---- rotate the x3 march state ---------------------------------------------------------------
+    if (is_main) {
+      if (PPM) {
 #pragma unroll
-    for (int v = 0; v < NV; ++v) { Ilo[v] = Inew[v]; Qup[v] = QupN[v]; }
+        for (int v = 0; v < NV; ++v) Ilo[v] = Inew[v];
+      }
+      if (ZR) {
 #pragma unroll
-    for (int m = 0; m < NF; ++m) Fz[m] = FzN[m];
-  }
+        for (int m = 0; m < NF; ++m) sm[SM::fzs + m * kSwMain + tid] = FzN[m];
+      }
+    }
+  };
+
+  // planes ks-3 .. ks-1 arrive before the first step; plane ks is waited for inside it
+  for (int p = 0; p < kSwRing - 1; ++p) mbar_wait(bar + p, 0);
+  using T_ = std::true_type;
+  using F_ = std::false_type;
+  step(F_{}, F_{}, 0);
+  step(F_{}, F_{}, 1);
+  step(F_{}, T_{}, 2);
+  for (int st = H; st < nsteps; ++st) step(T_{}, T_{}, st);
+
   if (a.dt_min) {  // warp-shuffle min, one atomic per warp
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tmin = dmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
