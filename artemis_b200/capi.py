@@ -43,7 +43,7 @@ class AB200Error(RuntimeError):
 SYMBOLS = [
     "ab200_abi_version", "ab200_last_error", "ab200_device_count", "ab200_create",
     "ab200_destroy", "ab200_synchronize", "ab200_set_grid", "ab200_bind_pack", "ab200_unbind",
-    "ab200_set_rotating_frame", "ab200_calculate_fluxes", "ab200_apply_update",
+    "ab200_set_rotating_frame", "ab200_set_stage_path", "ab200_get_stage_path", "ab200_calculate_fluxes", "ab200_apply_update",
     "ab200_flux_source", "ab200_set_auxillary_fields", "ab200_cons_to_prim",
     "ab200_prim_to_cons", "ab200_deep_copy_conserved", "ab200_estimate_timestep",
     "ab200_fused_stage", "ab200_sync_prim", "ab200_prim_to_cons_ghosts", "ab200_estimate_timestep_device",
@@ -84,6 +84,7 @@ def load(variant: str | None = None) -> C.CDLL:
         "ab200_set_grid": [vp, C.POINTER(GridDesc)],
         "ab200_bind_pack": [vp, C.POINTER(FluidDesc), C.POINTER(PackDesc)],
         "ab200_unbind": [vp, i], "ab200_set_rotating_frame": [vp, d],
+        "ab200_set_stage_path": [vp, i], "ab200_get_stage_path": [vp, i, C.POINTER(C.c_int)],
         "ab200_calculate_fluxes": [vp, i, i], "ab200_apply_update": [vp, d, d, d],
         "ab200_flux_source": [vp, i, d], "ab200_set_auxillary_fields": [vp],
         "ab200_cons_to_prim": [vp], "ab200_prim_to_cons": [vp],

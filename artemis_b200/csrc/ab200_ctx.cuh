@@ -74,6 +74,7 @@ struct ab200_ctx {
   ab200::FluidHost fl[2];
   ab200::Topology topo;
   double omf = 0.0;
+  int stage_path = 0;  // AB200_PATH_*
   double *d_time = nullptr;     // device double[4]: dt, new_dt, time, ncycle
   double *d_red = nullptr;      // reduction scratch
   double *h_pinned = nullptr;   // pinned host scratch (8 doubles)

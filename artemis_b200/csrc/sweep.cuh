@@ -111,6 +111,12 @@ AB_D void cp_async8(void *smem_dst, const void *gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc)
                : "memory");
 }
+// L2 prefetch of a tensor-map box (no shared-memory destination, no completion to wait for)
+AB_D void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 AB_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 AB_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -186,8 +192,17 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
     for (int v = 0; v < NV; ++v)
       tma_load_3d(dst + v * kSwTile, mp + pvx(v), bar + slot, i0 - HX, j0 - H, g.ks - H + p);
   };
+  // planes further ahead than the ring can hold are pulled into L2 so that the TMA load that
+  // eventually fills a freed slot does not pay the DRAM latency
+  constexpr int kAhead = 3;
+  auto prefetch = [&](int p) {
+    const CUtensorMap *mp = a.maps + (size_t)b * nvar;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) tma_prefetch_3d(mp + pvx(v), i0 - HX, j0 - H, g.ks - H + p);
+  };
   if (tid == 0) {
     for (int p = 0; p < kSwRing && p < nplanes; ++p) issue(p);
+    for (int p = kSwRing; p < kSwRing + kAhead && p < nplanes; ++p) prefetch(p);
   }
 
   const double dt = a.dt_dev ? *a.dt_dev : a.dt;
@@ -198,14 +213,18 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
   const int h = tid - kSwMain;               // halo-thread index
   const int ii = active ? i : g.is, jj = active ? j : g.js;
   const double *x3f = g.t.x3f + (size_t)b * (g.nk + 1);
+  const int plane = g.nj * g.ni;
+  int offk = ((g.ks - H) * g.nj + jj) * g.ni + ii;  // own zone in the current plane (carried)
 
 #ifdef AB200_FAST_MATH
-  // Cartesian: A_d / V = 1 / dx_d; one reciprocal per thread (x1, x2) and per plane (x3)
+  // Cartesian: A_d / V = 1 / dx_d; one reciprocal per thread (x1, x2) and per plane (x3).
+  // The flux divergence and the FluxSource terms of a component are summed first and applied
+  // with one fma(beta*dt, sum, base).
   double rx = 0.0, ry = 0.0;
   if (is_main) {
     const double *x1f = g.t.x1f + (size_t)b * (g.ni + 1), *x2f = g.t.x2f + (size_t)b * (g.nj + 1);
-    rx = ddiv(bdt, x1f[ii + 1] - x1f[ii]);
-    ry = ddiv(bdt, x2f[jj + 1] - x2f[jj]);
+    rx = drcp(x1f[ii + 1] - x1f[ii]);
+    ry = drcp(x2f[jj + 1] - x2f[jj]);
   }
 #endif
 
@@ -216,6 +235,7 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
 #pragma unroll
   for (int v = 0; v < NV; ++v) Ilo[v] = 0.0;
   double tmin = 1.79769313486231570815e+308;
+  double tden = 0.0;  // fast build: max over zones of sum_d (|v_d| + c_s) / dx_d
 
   // One plane step.  INP: the plane k = ks-3+st is an interior plane (in-plane x1/x2 work and
   // the zone update happen); ZR: the x3 Riemann problem at face k+1 is solved (st >= 2).
@@ -229,7 +249,7 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
     const double *R1 = sm + SM::ring + ((st + 1) & 3) * NV * kSwTile;
     const double *R2 = sm + SM::ring + ((st + 2) & 3) * NV * kSwTile;
     const double *R3 = sm + SM::ring + ((st + 3) & 3) * NV * kSwTile;
-    const int off = (k * g.nj + jj) * g.ni + ii;
+    const int off = offk;
 
     double W0[NV], Ixl[NV], Iyl[NV];
     // =========================== P1: interface values ==========================================
@@ -365,7 +385,10 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
     }
     __syncthreads();
     // plane k is dead: refill its slot with plane k+4
-    if (tid == 0 && st + kSwRing < nplanes) issue(st + kSwRing);
+    if (tid == 0) {
+      if (st + kSwRing < nplanes) issue(st + kSwRing);
+      if (st + kSwRing + kAhead < nplanes) prefetch(st + kSwRing + kAhead);
+    }
 
     // =========================== P3: Riemann solves ============================================
 #ifdef AB200_FAST_MATH
@@ -450,10 +473,13 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
       cp_async_wait_all();
       const int ox = cj * (TI + 1) + ci, oy = cj * TI + ci;
       double u[6], Fz[NF];
+#ifdef AB200_FAST_MATH
+      double ub[6];
+#endif
 #pragma unroll
       for (int m = 0; m < NF; ++m) Fz[m] = sm[SM::fzs + m * kSwMain + tid];
 #ifdef AB200_FAST_MATH
-      const double rz = ddiv(bdt, z1 - z0);
+      const double rz = drcp(z1 - z0);
 #else
       Coords<AB200_CARTESIAN> cc(g, b, k, jj, ii);
       const double ax1[2] = {cc.area1(cc.x1[0]), cc.area1(cc.x1[1])};
@@ -477,7 +503,8 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
         }
         // ApplyUpdate (artemis_integrator.hpp:95-106)
 #ifdef AB200_FAST_MATH
-        u[m] = base + ((xl - xh) * rx + (yl - yh) * ry + (Fz[m] - FzN[m]) * rz);
+        u[m] = (xl - xh) * rx + (yl - yh) * ry + (Fz[m] - FzN[m]) * rz;
+        ub[m] = base;
 #else
         double divf = (ax1[0] * xl - ax1[1] * xh);
         divf += (ax2[0] * yl - ax2[1] * yh);
@@ -497,6 +524,8 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
         u[5] -= ry * 0.5 * (pyl + pyh) * (vyh - vyl);
         u[3] += rz * (Fz[6] - FzN[6]);
         u[5] -= rz * 0.5 * (Fz[6] + FzN[6]) * (FzN[7] - Fz[7]);
+#pragma unroll
+        for (int m = 0; m < NV; ++m) u[m] = fma(bdt, u[m], ub[m]);
 #else
         const double dx1 = cc.x1[1] - cc.x1[0], dx2 = cc.x2[1] - cc.x2[0],
                      dx3 = cc.x3[1] - cc.x3[0];
@@ -508,6 +537,12 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
         u[5] -= bdt / vol * 0.5 * (Fz[6] + FzN[6]) * (ax3[1] * FzN[7] - ax3[0] * Fz[7]);
 #endif
       }
+#ifdef AB200_FAST_MATH
+      if (!gas) {
+#pragma unroll
+        for (int m = 0; m < NV; ++m) u[m] = fma(bdt, u[m], ub[m]);
+      }
+#endif
       if (active) {
         const double hx[3] = {1.0, 1.0, 1.0};
         if (gas)  // SetAuxillaryFields (fill_derived.cpp:55-72)
@@ -549,9 +584,15 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
           __stcg(pu[4] + off, u_u + ke);
         }
         if (a.dt_min) {  // EstimateTimestepMesh folded in (src/gas/gas.cpp:411-433)
+#ifdef AB200_FAST_MATH
+          double cs = 0.0;
+          if (gas) cs = dsqrt(ddiv(dmax(0.0, (f.gm1 + 1) * f.gm1 * w_d * w_s), w_d));
+          tden = dmax(tden, (fabs(v1) + cs) * rx + (fabs(v2) + cs) * ry + (fabs(v3) + cs) * rz);
+#else
           Coords<AB200_CARTESIAN> cd(g, b, k, j, i);
           const double vel[3] = {v1, v2, v3};
           tmin = dmin(tmin, cell_dt<AB200_CARTESIAN, FLUID>(g, f, cd, w_d, vel, w_s));
+#endif
         }
       }
     }
@@ -566,6 +607,7 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
         for (int m = 0; m < NF; ++m) sm[SM::fzs + m * kSwMain + tid] = FzN[m];
       }
     }
+    offk += plane;
   };
 
   // planes ks-3 .. ks-1 arrive before the first step; plane ks is waited for inside it
@@ -578,6 +620,9 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
   for (int st = H; st < nsteps; ++st) step(T_{}, T_{}, st);
 
   if (a.dt_min) {  // warp-shuffle min, one atomic per warp
+#ifdef AB200_FAST_MATH
+    if (tden > 0.0) tmin = drcp(tden);
+#endif
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tmin = dmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
     if ((tid & 31) == 0 && is_main)

@@ -90,12 +90,24 @@ static int ensure_sweep(ab200_ctx *c, int fluid) {
   return AB200_OK;
 }
 
+// AB200_PATH_AUTO policy, from the B200 measurements in profiles/r01d_stage_matrix.json (256^3
+// zones, 64^3 blocks).  The single-pass kernel moves 2.2x less HBM traffic but runs one CTA of
+// 10 warps per SM with three barriers per plane; it is bound by instruction issue and smem /
+// dependency latency, not by HBM.  It beats the barrier-free directional passes only where the
+// arithmetic per zone is light: LLF fluxes with PCM / PLM reconstruction (gas 1.53 vs 1.80 ms,
+// dust 1.04 vs 1.17 ms per stage); for everything else (PPM, HLLC, HLLE) the passes win.
+static bool sweep_preferred(const FluidDev &f) {
+  return f.riemann == AB200_LLF && f.recon != AB200_PPM;
+}
+
 bool sweep_eligible(ab200_ctx *c, int fluid) {
-  static int off = -1;
-  if (off < 0) off = getenv("AB200_NO_SWEEP") ? 1 : 0;
-  if (off) return false;
+  static int env = -2;  // -1: forced off, 1: forced on, 0: no override
+  if (env == -2) env = getenv("AB200_NO_SWEEP") ? -1 : (getenv("AB200_SWEEP") ? 1 : 0);
+  if (env < 0 || c->stage_path == AB200_PATH_THREE_PASS) return false;
   const GridDev &g = c->g;
   if (g.ndim != 3 || g.geom != AB200_CARTESIAN) return false;
+  if (c->stage_path == AB200_PATH_AUTO && env == 0 && !sweep_preferred(c->fl[fluid].d))
+    return false;
   if (ensure_sweep(c, fluid) != AB200_OK) return false;
   return c->fl[fluid].sw_ready;
 }

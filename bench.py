@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--cpu-cycles", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--path", default="auto", choices=["auto", "three_pass", "single_pass"],
+                    help="ab200_set_stage_path: which stage kernels run (auto = library policy)")
     return ap.parse_args()
 
 
@@ -228,6 +230,8 @@ def main():
             if rl[d] < lay[d] - 1:
                 bcs[2 * d + 1] = 3
     md = MeshData(mesh, gas=gp, device=local, materialize_fluxes=False, bcs=bcs)
+    md.set_stage_path(args.path)
+    path = md.stage_path()
     if world > 1:
         comm = HaloComm(md, lay, rl, rank, world)
     prim = pgen.blast(mesh, gp.gamma, d0=1.0, p0=1e-5, internal_energy=1.0, radius=0.1, samples=0)
@@ -306,8 +310,12 @@ def main():
             traffic = json.load(fh).get("fused_stage_dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "kernel": "k_sweep_stage (one launch = one full stage: x1+x2+x3 reconstruct/Riemann/"
-                          "update + C2P, primitives and conserved state cross HBM once)",
+                "kernel": ("k_sweep_stage (one launch = one full stage: x1+x2+x3 reconstruct/Riemann/"
+                           "update + C2P, primitives and conserved state cross HBM once)"
+                           if path == "single_pass" else
+                           "k_xchunk_pass + k_march_pass<2> + k_march_pass<3> (one fused stage = the "
+                           "three directional passes; 'achieved' = algorithmic bytes of the stage / "
+                           "their summed duration)"),
                 "stage_ms": kms, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_ZONE_STAGE * zones_local,
                 "whole_cycle_frac": value / world * 2 * ALG_BYTES_PER_ZONE_STAGE / (peak * 1e9)}
@@ -353,10 +361,11 @@ def main():
                                        f"MeshBlocks, nghost=4, outflow",
                            "zones_total": zones, "ranks": list(lay),
                            "l2": "state 3.4 GB/GPU >> 126 MB L2, no flush needed",
-                           "path": "single-pass stage kernel + fused ghost fill + "
-                                   "device-resident dt"
-                                   if world == 1 else "single-pass stage kernel + NCCL halo "
-                                   "sweeps + device-resident dt all-reduce"},
+                           "path": ("single-pass stage kernel" if path == "single_pass" else
+                                    "three directional fused passes") +
+                                   (" + fused ghost fill + device-resident dt" if world == 1 else
+                                    " + NCCL halo sweeps + device-resident dt all-reduce"),
+                           "stage_path": path},
                 "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks}
         if ts is not None:

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AB200_ABI_VERSION 3
+#define AB200_ABI_VERSION 4
 
 /* src/artemis.hpp:78-105 */
 enum { AB200_CARTESIAN = 0, AB200_CYLINDRICAL = 1, AB200_SPHERICAL1D = 2,
@@ -165,6 +165,23 @@ int ab200_estimate_timestep(ab200_ctx *ctx, int fluid, double *dt_host);
 #define AB200_STAGE_PINGPONG 4
 int ab200_fused_stage(ab200_ctx *ctx, double gam0, double gam1, double beta, double dt,
                       int pcm, int stage1_copy, int flags);
+/* Which kernels ab200_fused_stage runs on meshes where both exist (3-D Cartesian, TMA-able
+ * arrays); every other mesh always takes the directional passes.
+ *   AB200_PATH_AUTO         the faster of the two as measured on B200 for the bound fluid's
+ *                           reconstruction / Riemann solver
+ *   AB200_PATH_THREE_PASS   one kernel per direction (x1, x2, x3)
+ *   AB200_PATH_SINGLE_PASS  the single-pass stage kernel (requires the alternate primitive set)
+ * The two paths agree to the parity bar (1e-12 per zone and cycle); in the strict build the
+ * single-pass kernel is bit-identical to the reference (it sums the flux divergence over the
+ * three directions before the update, artemis_integrator.hpp:95-106), the directional passes
+ * round once per direction. */
+#define AB200_PATH_AUTO 0
+#define AB200_PATH_THREE_PASS 1
+#define AB200_PATH_SINGLE_PASS 2
+int ab200_set_stage_path(ab200_ctx *ctx, int path);
+/* *path_out = AB200_PATH_THREE_PASS or AB200_PATH_SINGLE_PASS: what ab200_fused_stage runs for
+ * `fluid` on the bound mesh under the current setting (resolves AUTO and eligibility). */
+int ab200_get_stage_path(ab200_ctx *ctx, int fluid, int *path_out);
 /* Copies the current primitives (interior and ghosts) into the caller's arrays if a
  * AB200_STAGE_PINGPONG stage left them in the alternate set; no-op otherwise.  Entry points
  * that hand the caller's primitive arrays to task-level kernels call it implicitly. */

@@ -1,5 +1,6 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
-python scripts/diag_reflect.py reflect dust 2>&1 | tail -40
-python scripts/diag_reflect.py reflect nodust 2>&1 | tail -20
-AB200_NO_SWEEP=1 python scripts/diag_reflect.py reflect dust 2>&1 | tail -20
+for path in three_pass single_pass; do
+python scripts/diag_reflect.py reflect nodust strict $path rk3 2>&1 | tail -12
+done
+python scripts/diag_reflect.py outflow nodust strict three_pass rk3 2>&1 | tail -6

@@ -169,10 +169,13 @@ def test_hundred_cycles_blast_within_1e9(mode):
     (Coordinates.spherical3D, "mixed", False, "rk2"),
     (Coordinates.axisymmetric, "reflect", False, "rk2"),
 ])
-def test_device_resident_driver_matches_host_driven(coords, bc, with_dust, integ):
+@pytest.mark.parametrize("variant", ["strict", "fast"])
+def test_device_resident_driver_matches_host_driven(coords, bc, with_dust, integ, variant):
     """ab200_run_cycles (fused ghost fill, dt reduction folded into the last pass, dt on the
     device, no host round trip) == the host-driven fused loop built from the per-task entry
-    points, bit for bit."""
+    points: bit for bit in the strict build; in the fast build the single-pass stage kernel
+    estimates dt from hoisted reciprocal cell widths, so dt agrees to rounding and the state
+    to the 1e-12 parity bar."""
     B = BoundaryFlag
     bcs = {"outflow": (B.outflow,) * 6, "periodic": (B.periodic,) * 6, "reflect": (B.reflect,) * 6,
            "mixed": (B.reflect, B.outflow, B.periodic, B.periodic, B.outflow, B.reflect)}[bc]
@@ -182,14 +185,14 @@ def test_device_resident_driver_matches_host_driven(coords, bc, with_dust, integ
     prim = random_prim(mesh, gp, seed=11, shocks=False)
     dprim = random_prim(mesh, dp, seed=12, shocks=False) if with_dust else None
     ncyc = 4
-    md1 = MeshData(mesh, gas=gp, dust=dp, materialize_fluxes=False)
+    md1 = MeshData(mesh, gas=gp, dust=dp, variant=variant, materialize_fluxes=False)
     md1.gas.prim.set(prim)
     if with_dust:
         md1.dust.prim.set(dprim)
     d1 = ArtemisDriver(md1, integ, mode="fused", nlim=ncyc)
     d1.Initialize()
     d1.Execute()
-    md2 = MeshData(mesh, gas=gp, dust=dp, materialize_fluxes=False)
+    md2 = MeshData(mesh, gas=gp, dust=dp, variant=variant, materialize_fluxes=False)
     md2.gas.prim.set(prim)
     if with_dust:
         md2.dust.prim.set(dprim)
@@ -199,11 +202,18 @@ def test_device_resident_driver_matches_host_driven(coords, bc, with_dust, integ
     code = {"rk1": 0, "rk2": 1, "vl2": 2, "rk3": 3}[integ]
     md2.call("ab200_run_cycles", code, ncyc, float(np.finfo(np.float64).max))
     ts = md2.time_state()
-    assert ts[3] == ncyc and abs(ts[2] - d1.time) <= 1e-15 * d1.time
-    assert ts[0] == d1.dt
-    for f1, f2 in zip(md1.fluids, md2.fluids):
-        assert np.array_equal(f1.u0.get(), f2.u0.get())
-        assert np.array_equal(f1.prim.get(), f2.prim.get())
+    if variant == "strict":
+        assert ts[3] == ncyc and abs(ts[2] - d1.time) <= 1e-15 * d1.time
+        assert ts[0] == d1.dt
+        for f1, f2 in zip(md1.fluids, md2.fluids):
+            assert np.array_equal(f1.u0.get(), f2.u0.get())
+            assert np.array_equal(f1.prim.get(), f2.prim.get())
+    else:
+        assert ts[3] == ncyc and abs(ts[2] - d1.time) <= 1e-13 * d1.time
+        assert abs(ts[0] - d1.dt) <= 1e-13 * d1.dt
+        for f1, f2 in zip(md1.fluids, md2.fluids):
+            assert rel_err(f1.u0.get(), f2.u0.get()) <= 1e-12
+            assert rel_err(f1.prim.get(), f2.prim.get()) <= 1e-12
     md1.close()
     md2.close()
 

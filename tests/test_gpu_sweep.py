@@ -25,6 +25,7 @@ def _mesh(nx, bnx, bcs=None, ng=4):
 def _twin(mesh, gp, dp, variant, integ, ncyc, device_resident=False, seed=5, shocks=True):
     osim = OracleSim(mesh, gas=gp, dust=dp, integrator=integ)
     md = MeshData(mesh, gas=gp, dust=dp, variant=variant, materialize_fluxes=False)
+    md.set_stage_path("single_pass")
     for which, fp in ((Fluid.gas, gp), (Fluid.dust, dp)):
         if fp is None:
             continue
@@ -107,6 +108,7 @@ def test_sweep_blast_hundred_cycles_and_single_launch_per_stage():
     osim.initialize()
     osim.run()
     md = MeshData(mesh, gas=gp, materialize_fluxes=False)
+    md.set_stage_path("single_pass")
     md.gas.prim.set(prim)
     drv = ArtemisDriver(md, "rk2", mode="fused")
     drv.Initialize()
@@ -120,3 +122,49 @@ def test_sweep_blast_hundred_cycles_and_single_launch_per_stage():
     assert ts[3] == 100 and abs(ts[2] - osim.time) <= 1e-12 * osim.time
     assert per_cycle <= 8, per_cycle
     md.close()
+
+
+@pytest.mark.parametrize("bc", ["reflect", "outflow"])
+def test_paths_agree_and_can_be_switched_mid_run(bc):
+    """ab200_set_stage_path: the single-pass kernel and the three directional passes agree to
+    the parity bar (the directional passes round the flux divergence once per direction, the
+    single-pass kernel sums it first like the reference, so only the latter is bit-identical
+    to the oracle), also when the path is switched while the primitives sit in the alternate
+    set.  Gas PPM+HLLC and 2 dust species, reflecting walls included."""
+    B = BoundaryFlag
+    bcs = (B.reflect,) * 6 if bc == "reflect" else (B.outflow,) * 6
+    mesh = _mesh((32, 32, 32), (16, 16, 16), bcs)
+    gp = gas_params(C, "ppm", "hllc")
+    dp = dust_params(C, "plm", "hlle", S=2)
+    out = {}
+    for path in ("three_pass", "single_pass", "switch"):
+        md = MeshData(mesh, gas=gp, dust=dp, variant="strict", materialize_fluxes=False)
+        md.set_stage_path("single_pass" if path == "switch" else path)
+        assert md.stage_path() == ("three_pass" if path == "three_pass" else "single_pass")
+        md.gas.prim.set(random_prim(mesh, gp, seed=3))
+        md.dust.prim.set(random_prim(mesh, dp, seed=4))
+        drv = ArtemisDriver(md, "rk3", mode="fused")
+        drv.Initialize()
+        md.set_time_state(drv.dt)
+        big = float(np.finfo(np.float64).max)
+        if path == "switch":
+            md.call("ab200_fused_stage", 0.0, 1.0, 1.0, 0.0, 0, 1, 1 | 4)  # prim left in the alternate set
+            md.call("ab200_fill_ghosts")
+            md.set_stage_path("three_pass")
+            md.call("ab200_fused_stage", 0.25, 0.75, 0.25, 0.0, 0, 0, 1 | 4)
+            md.call("ab200_fill_ghosts")
+            md.set_stage_path("single_pass")
+            md.call("ab200_fused_stage", 2.0 / 3.0, 1.0 / 3.0, 2.0 / 3.0, 0.0, 0, 0, 1 | 2 | 4)
+            md.call("ab200_fill_ghosts")
+            md.call("ab200_set_global_timestep_device", big, 1)
+            md.call("ab200_sync_prim")
+        else:
+            md.call("ab200_run_cycles", 3, 1, big)
+        out[path] = [(f.u0.get(), f.prim.get()) for f in md.fluids] + [md.time_state()]
+        md.close()
+    for path in ("single_pass", "switch"):
+        for (u_a, p_a), (u_b, p_b) in zip(out["three_pass"][:2], out[path][:2]):
+            assert rel_err(u_a, u_b) <= 1e-12, path
+            assert rel_err(p_a, p_b) <= 1e-12, path
+        ta, tb = out["three_pass"][2], out[path][2]
+        assert ta[3] == tb[3] == 1 and abs(ta[0] - tb[0]) <= 1e-13 * ta[0], path
