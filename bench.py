@@ -219,6 +219,9 @@ def main():
     torch.cuda.set_device(local)
     comm = None
     if world > 1:
+        # NCCL_DEBUG=VERSION prints its banner on stdout, which must carry the JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     mesh, gp, lay, rl = make_problem(args, rank, world)
     bcs = list(mesh.bcs)
@@ -307,7 +310,8 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         with open(tp) as fh:
-            traffic = json.load(fh).get("fused_stage_dram_bytes_per_launch")
+            traffic = json.load(fh).get("single_pass_dram_bytes_per_launch" if path == "single_pass"
+                                        else "fused_stage_dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "kernel": ("k_sweep_stage (one launch = one full stage: x1+x2+x3 reconstruct/Riemann/"
@@ -343,9 +347,46 @@ def main():
                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 2 * nbytes,
                "ms_per_step": te * 1e3,
                "api": "ab200_cycles_host (pinned host prim in; prim + cons out)"}
-    elif world > 1:
-        e2e = {"value": None, "unit": "zone-cycles/s", "h2d_bytes_per_step": 0,
-               "d2h_bytes_per_step": 0, "note": "host-buffer entry point is measured at N=1"}
+    elif not args.no_e2e:
+        # N > 1: the same end-to-end step through the public entry points every rank calls --
+        # pinned host primitives in, ab200_prim_to_cons, one device-resident cycle with the NCCL
+        # halo sweeps and the dt all-reduce, primitives + conserved state back to pinned host
+        # memory; wall clock between barriers, max over ranks
+        nv = gp.nvar
+        shape = mesh.shape(nv)
+        nbytes = int(np.prod(shape)) * 8
+        hp = torch.empty(shape, dtype=torch.float64).pin_memory()
+        hc = torch.empty(shape, dtype=torch.float64).pin_memory()
+        hp.numpy()[:] = md.gas.prim.get()
+
+        def e2e_step():
+            capi_check(md.L.ab200_memcpy_h2d(md.ctx, md.gas.prim.ptr, hp.data_ptr(), nbytes))
+            md.call("ab200_prim_to_cons")
+            drv.StepDevice()
+            capi_check(md.L.ab200_memcpy_d2h(md.ctx, hp.data_ptr(), md.gas.prim.ptr, nbytes))
+            capi_check(md.L.ab200_memcpy_d2h(md.ctx, hc.data_ptr(), md.gas.u0.ptr, nbytes))
+
+        def capi_check(rc):
+            if rc != 0:
+                raise SystemExit(f"bench.py: host<->device copy failed ({rc})")
+
+        e2e_step()  # warm-up
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        sync_all()
+        te = (time.perf_counter() - t0) / args.e2e_steps
+        tt = torch.tensor([te], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        te = float(tt.item())
+        e2e = {"value": zones / te, "unit": "zone-cycles/s", "h2d_bytes_per_step": nbytes * world,
+               "d2h_bytes_per_step": 2 * nbytes * world, "ms_per_step": te * 1e3,
+               "api": "per rank: ab200_memcpy_h2d (pinned prim) -> ab200_prim_to_cons -> "
+                      "device-resident cycle (NCCL halo sweeps, dt all-reduce) -> "
+                      "ab200_memcpy_d2h (prim + cons)"}
+    else:
+        e2e = None
 
     base = None
     if rank == 0 and world == 1 and not args.no_cpu:
