@@ -69,6 +69,8 @@ struct ab200_ctx {
   cudaStream_t stream = nullptr;
   bool grid_set = false;
   ab200::GridDev g{};
+  ab200::GridDev gc{};          // coarse buffers of the multilevel operators (refine.cu)
+  bool coarse_ready = false;
   std::vector<void *> grid_allocs;
   std::vector<double> h_xmin, h_dx;
   ab200::FluidHost fl[2];
@@ -122,4 +124,6 @@ bool topology_is_local(const ab200_ctx *c);
 int launch_halo(ab200_ctx *c, const ab200_bnd_desc *bnd, int n, int unpack);
 int launch_set_global_dt(ab200_ctx *c, double tlim, int advance_time);
 int ensure_scratch(ab200_ctx *c, int fluid, bool need_flux, bool need_u1);
+int build_geom_tables_for(ab200_ctx *c, GeomTab &t, int geom, int nb, int ni, int nj, int nk,
+                          const double *xmin_all, const double *dx_all);
 }  // namespace ab200

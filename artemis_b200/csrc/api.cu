@@ -60,28 +60,30 @@ static double h_x2v(int geom, double a, double b) {
   return 0.5 * (a + b);
 }
 
-static int build_geom_tables(ab200_ctx *c, const ab200_grid_desc *gd) {
-  const int nb = gd->nblocks, ni = gd->ni, nj = gd->nj, nk = gd->nk;
+// Metric tables of nb blocks of ni x nj x nk cells (xmin / dx: [nb][3]); used for the bound
+// (fine) grid and, by refine.cu, for the coarse buffers of the multilevel operators.
+int build_geom_tables_for(ab200_ctx *c, GeomTab &t, int geom, int nb, int ni, int nj, int nk,
+                          const double *xmin_all, const double *dx_all) {
   std::vector<double> x1f((size_t)nb * (ni + 1)), x2f((size_t)nb * (nj + 1)),
       x3f((size_t)nb * (nk + 1)), x1v((size_t)nb * ni), x2v((size_t)nb * nj),
       x3v((size_t)nb * nk), cosf((size_t)nb * (nj + 1)), sinf((size_t)nb * (nj + 1)),
       sinv((size_t)nb * nj), sinc((size_t)nb * nj);
   for (int b = 0; b < nb; ++b) {
-    const double *xm = gd->xmin + 3 * b, *dx = gd->dx + 3 * b;
+    const double *xm = xmin_all + 3 * b, *dx = dx_all + 3 * b;
     // P:coordinates/uniform_cartesian.hpp:153-157  Xf(idx) = xmin + idx*dx
     for (int i = 0; i <= ni; ++i) x1f[(size_t)b * (ni + 1) + i] = xm[0] + i * dx[0];
     for (int j = 0; j <= nj; ++j) x2f[(size_t)b * (nj + 1) + j] = xm[1] + j * dx[1];
     for (int k = 0; k <= nk; ++k) x3f[(size_t)b * (nk + 1) + k] = xm[2] + k * dx[2];
     for (int i = 0; i < ni; ++i)
       x1v[(size_t)b * ni + i] =
-          h_x1v(gd->geom, x1f[(size_t)b * (ni + 1) + i], x1f[(size_t)b * (ni + 1) + i + 1]);
+          h_x1v(geom, x1f[(size_t)b * (ni + 1) + i], x1f[(size_t)b * (ni + 1) + i + 1]);
     for (int j = 0; j <= nj; ++j) {
       cosf[(size_t)b * (nj + 1) + j] = std::cos(x2f[(size_t)b * (nj + 1) + j]);
       sinf[(size_t)b * (nj + 1) + j] = std::sin(x2f[(size_t)b * (nj + 1) + j]);
     }
     for (int j = 0; j < nj; ++j) {
       const double a = x2f[(size_t)b * (nj + 1) + j], bb = x2f[(size_t)b * (nj + 1) + j + 1];
-      const double v = h_x2v(gd->geom, a, bb);
+      const double v = h_x2v(geom, a, bb);
       x2v[(size_t)b * nj + j] = v;
       sinv[(size_t)b * nj + j] = std::sin(v);
       sinc[(size_t)b * nj + j] = std::sin(0.5 * (a + bb));
@@ -90,7 +92,6 @@ static int build_geom_tables(ab200_ctx *c, const ab200_grid_desc *gd) {
       x3v[(size_t)b * nk + k] =
           0.5 * (x3f[(size_t)b * (nk + 1) + k] + x3f[(size_t)b * (nk + 1) + k + 1]);
   }
-  GeomTab &t = c->g.t;
   double *p;
 #define UP(field, vec)                                                                   \
   AB_TRY(upload<double>(c, &p, vec.data(), vec.size(), &c->grid_allocs));                \
@@ -99,6 +100,11 @@ static int build_geom_tables(ab200_ctx *c, const ab200_grid_desc *gd) {
   UP(cosf, cosf) UP(sinf, sinf) UP(sinv, sinv) UP(sinc, sinc)
 #undef UP
   return AB200_OK;
+}
+
+static int build_geom_tables(ab200_ctx *c, const ab200_grid_desc *gd) {
+  return build_geom_tables_for(c, c->g.t, gd->geom, gd->nblocks, gd->ni, gd->nj, gd->nk, gd->xmin,
+                               gd->dx);
 }
 
 int ensure_scratch(ab200_ctx *c, int fluid, bool need_flux, bool need_u1) {
@@ -224,6 +230,7 @@ int ab200_set_grid(ab200_ctx *c, const ab200_grid_desc *gd) {
   c->h_xmin.assign(gd->xmin, gd->xmin + 3 * gd->nblocks);
   c->h_dx.assign(gd->dx, gd->dx + 3 * gd->nblocks);
   AB_TRY(build_geom_tables(c, gd));
+  c->coarse_ready = false;
   c->grid_set = true;
   c->topo.set = false;
   c->host_path_ready = false;

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AB200_ABI_VERSION 4
+#define AB200_ABI_VERSION 5
 
 /* src/artemis.hpp:78-105 */
 enum { AB200_CARTESIAN = 0, AB200_CYLINDRICAL = 1, AB200_SPHERICAL1D = 2,
@@ -188,6 +188,28 @@ int ab200_get_stage_path(ab200_ctx *ctx, int fluid, int *path_out);
 int ab200_sync_prim(ab200_ctx *ctx);
 /* PrimToCons restricted to ghost zones (completes :261 after the exchange). */
 int ab200_prim_to_cons_ghosts(ab200_ctx *ctx);
+
+/* ---- multilevel ghost exchange operators (config 5: static / adaptive refinement) ---------
+ * Replace the stencils Parthenon's refinement::Restrict / Prolongate apply over the index
+ * ranges of BndInfo (P:prolong_restrict/prolong_restrict.hpp):
+ *   ab200_restrict    ArtemisUtils::RestrictAverage<GEOM>        src/utils/refinement/restriction.hpp:41-114
+ *   ab200_prolongate  ArtemisUtils::ProlongateSharedMinMod<GEOM> src/utils/refinement/prolongation.hpp:82-184
+ * A descriptor names pack entries var0 .. var0+nvar-1 of one MeshBlock's primitive (FillGhost)
+ * or conserved arrays, the block's coarse buffer for those entries (device memory,
+ * [nvar][cnk][cnj][cni], Parthenon's `coarse_s`), and the inclusive COARSE index box to loop
+ * over.  The coarse buffer shape is Parthenon's c_cellbounds: nx/2 interior cells plus nghost
+ * ghosts in every active direction (P:mesh/meshblock.cpp:205-228); ab200_coarse_shape returns
+ * {cni, cnj, cnk, cis, cjs, cks}.  A whole descriptor list is ONE kernel launch. */
+#define AB200_REFINE_PRIM 0
+#define AB200_REFINE_CONS 1
+typedef struct ab200_refine_desc {
+  int fluid, block, var0, nvar, kind;
+  int cis, cie, cjs, cje, cks, cke;
+  double *coarse;
+} ab200_refine_desc;
+int ab200_coarse_shape(ab200_ctx *ctx, int *dims6);
+int ab200_restrict(ab200_ctx *ctx, const ab200_refine_desc *descs, int n);
+int ab200_prolongate(ab200_ctx *ctx, const ab200_refine_desc *descs, int n);
 
 /* ---- timestep on the device (replaces the per-cycle host round trip of
  *      P:driver/driver.cpp:210-269 + MPI_Allreduce :237) ------------------------------------ */

@@ -1074,3 +1074,146 @@ void ao_exchange_ghosts(const ao_grid *g, int nbx, int nby, int nbz, const int *
                         int nvar, double *a, int nv, const int *vars, const int *vec_dir) {
   ao_exchange_ghosts_phase(g, nbx, nby, nbz, bc, nvar, a, nv, vars, vec_dir, 3);
 }
+
+/* ===================================================================================== */
+/* Multilevel operators.                                               */
+/* ===================================================================================== */
+/* P:coordinates/uniform_cartesian.hpp:41-55 UniformCartesian(src, coarsen = 2): the coarse
+ * buffer keeps ng ghost cells of twice the width in every active direction. */
+static void coarse_coords(const ao_refine_geom *r, double cxmin[3], double cdx[3]) {
+  const int act[3] = {1, r->ndim > 1, r->ndim > 2};
+  for (int d = 0; d < 3; ++d) {
+    const int istart = act[d] ? r->ng : 0;
+    const int coarsen = 2;
+    cdx[d] = r->dx[d];
+    cxmin[d] = r->xmin[d];
+    cxmin[d] += istart * cdx[d] * (1 - coarsen);
+    cdx[d] *= (d == 0 ? coarsen : (istart > 0 ? coarsen : 1));
+  }
+}
+#define RIDX(nk_, nj_, ni_, n, k, j, i) ((((size_t)(n) * (nk_) + (k)) * (nj_) + (j)) * (ni_) + (i))
+
+/* restriction.hpp:41-114 (el = CC): coarse = sum(vol * fine) / sum(vol) over the 2^ndim fine
+ * cells, both sums in the reference's pairing ((000+010)+(001+011))+((100+110)+(101+111)). */
+void ao_restrict_average(const ao_refine_geom *r, int nvar, const double *fine, double *coarse,
+                         const int *box) {
+  const int inc1 = r->ndim > 0, inc2 = r->ndim > 1, inc3 = r->ndim > 2;
+  for (int n = 0; n < nvar; ++n)
+    for (int ck = box[4]; ck <= box[5]; ++ck)
+      for (int cj = box[2]; cj <= box[3]; ++cj)
+        for (int ci = box[0]; ci <= box[1]; ++ci) {
+          const int i = inc1 ? (ci - r->cib_s) * 2 + r->ib_s : r->ib_s;
+          const int j = inc2 ? (cj - r->cjb_s) * 2 + r->jb_s : r->jb_s;
+          const int k = inc3 ? (ck - r->ckb_s) * 2 + r->kb_s : r->kb_s;
+          double vol[2][2][2], terms[2][2][2];
+          for (int ok = 0; ok < 2; ++ok)
+            for (int oj = 0; oj < 2; ++oj)
+              for (int oi = 0; oi < 2; ++oi) vol[ok][oj][oi] = terms[ok][oj][oi] = 0;
+          for (int ok = 0; ok < 1 + inc3; ++ok)
+            for (int oj = 0; oj < 1 + inc2; ++oj)
+              for (int oi = 0; oi < 1 + inc1; ++oi) {
+                const bbox_t b = make_bbox(r->xmin, r->dx, k + ok, j + oj, i + oi);
+                vol[ok][oj][oi] = g_volume(r->geom, &b);
+                terms[ok][oj][oi] =
+                    vol[ok][oj][oi] * fine[RIDX(r->nk, r->nj, r->ni, n, k + ok, j + oj, i + oi)];
+              }
+          const double tvol = ((vol[0][0][0] + vol[0][1][0]) + (vol[0][0][1] + vol[0][1][1])) +
+                              ((vol[1][0][0] + vol[1][1][0]) + (vol[1][0][1] + vol[1][1][1]));
+          coarse[RIDX(r->cnk, r->cnj, r->cni, n, ck, cj, ci)] =
+              (((terms[0][0][0] + terms[0][1][0]) + (terms[0][0][1] + terms[0][1][1])) +
+               ((terms[1][0][0] + terms[1][1][0]) + (terms[1][0][1] + terms[1][1][1]))) /
+              tvol;
+        }
+}
+
+/* prolongation.hpp:72-79 GradMinMod, SIGN from P:config.hpp.in:86 */
+static inline double grad_minmod(double fc, double fm, double fp, double dxm, double dxp) {
+  const double gxm = (fc - fm) / dxm;
+  const double gxp = (fp - fc) / dxp;
+  const double sm = (gxm < 0.0) ? -1.0 : 1.0, sp = (gxp < 0.0) ? -1.0 : 1.0;
+  return 0.5 * (sm + sp) * dmin(fabs(gxm), fabs(gxp));
+}
+/* prolongation.hpp:39-67 GetGridSpacings<C, DIM>: centroid distances on both levels */
+static inline void grid_spacings(int geom, int dim, const double *xmin, const double *dx,
+                                 const double *cxmin, const double *cdx, int k, int j, int i,
+                                 int fk, int fj, int fi, double *dxm, double *dxp, double *dxfm,
+                                 double *dxfp) {
+  const int o3 = dim == 3, o2 = dim == 2, o1 = dim == 1;
+  const bbox_t cc = make_bbox(cxmin, cdx, k, j, i);
+  const bbox_t cm = make_bbox(cxmin, cdx, k - o3, j - o2, i - o1);
+  const bbox_t cp = make_bbox(cxmin, cdx, k + o3, j + o2, i + o1);
+  const bbox_t fm = make_bbox(xmin, dx, fk, fj, fi);
+  const bbox_t fp = make_bbox(xmin, dx, fk + o3, fj + o2, fi + o1);
+  double xm, xc, xp, fxm, fxp;
+  if (dim == 1) {
+    xm = g_x1v(geom, &cm); xc = g_x1v(geom, &cc); xp = g_x1v(geom, &cp);
+    fxm = g_x1v(geom, &fm); fxp = g_x1v(geom, &fp);
+  } else if (dim == 2) {
+    xm = g_x2v(geom, &cm); xc = g_x2v(geom, &cc); xp = g_x2v(geom, &cp);
+    fxm = g_x2v(geom, &fm); fxp = g_x2v(geom, &fp);
+  } else {
+    xm = g_x3v(geom, &cm); xc = g_x3v(geom, &cc); xp = g_x3v(geom, &cp);
+    fxm = g_x3v(geom, &fm); fxp = g_x3v(geom, &fp);
+  }
+  *dxm = xc - xm;
+  *dxp = xp - xc;
+  *dxfm = xc - fxm;
+  *dxfp = fxp - xc;
+}
+
+/* prolongation.hpp:82-184 ProlongateSharedMinMod<GEOM>::Do<DIM, CC> */
+void ao_prolongate_minmod(const ao_refine_geom *r, int nvar, const double *coarse, double *fine,
+                          const int *box) {
+  const int inc1 = r->ndim > 0, inc2 = r->ndim > 1, inc3 = r->ndim > 2;
+  double cxmin[3], cdx[3];
+  coarse_coords(r, cxmin, cdx);
+#define CO(n, k, j, i) coarse[RIDX(r->cnk, r->cnj, r->cni, n, k, j, i)]
+#define FI(n, k, j, i) fine[RIDX(r->nk, r->nj, r->ni, n, k, j, i)]
+  for (int n = 0; n < nvar; ++n)
+    for (int k = box[4]; k <= box[5]; ++k)
+      for (int j = box[2]; j <= box[3]; ++j)
+        for (int i = box[0]; i <= box[1]; ++i) {
+          const int fi = inc1 ? (i - r->cib_s) * 2 + r->ib_s : r->ib_s;
+          const int fj = inc2 ? (j - r->cjb_s) * 2 + r->jb_s : r->jb_s;
+          const int fk = inc3 ? (k - r->ckb_s) * 2 + r->kb_s : r->kb_s;
+          const double fc = CO(n, k, j, i);
+          double dx1fm = 0, dx1fp = 0, gx1m = 0, gx1p = 0;
+          if (inc1) {
+            double dx1m, dx1p;
+            grid_spacings(r->geom, 1, r->xmin, r->dx, cxmin, cdx, k, j, i, fk, fj, fi, &dx1m,
+                          &dx1p, &dx1fm, &dx1fp);
+            const double g = grad_minmod(fc, CO(n, k, j, i - 1), CO(n, k, j, i + 1), dx1m, dx1p);
+            gx1m = g; gx1p = g;
+          }
+          double dx2fm = 0, dx2fp = 0, gx2m = 0, gx2p = 0;
+          if (inc2) {
+            double dx2m, dx2p;
+            grid_spacings(r->geom, 2, r->xmin, r->dx, cxmin, cdx, k, j, i, fk, fj, fi, &dx2m,
+                          &dx2p, &dx2fm, &dx2fp);
+            const double g = grad_minmod(fc, CO(n, k, j - 1, i), CO(n, k, j + 1, i), dx2m, dx2p);
+            gx2m = g; gx2p = g;
+          }
+          double dx3fm = 0, dx3fp = 0, gx3m = 0, gx3p = 0;
+          if (inc3) {
+            double dx3m, dx3p;
+            grid_spacings(r->geom, 3, r->xmin, r->dx, cxmin, cdx, k, j, i, fk, fj, fi, &dx3m,
+                          &dx3p, &dx3fm, &dx3fp);
+            const double g = grad_minmod(fc, CO(n, k - 1, j, i), CO(n, k + 1, j, i), dx3m, dx3p);
+            gx3m = g; gx3p = g;
+          }
+          FI(n, fk, fj, fi) = fc - (gx1m * dx1fm + gx2m * dx2fm + gx3m * dx3fm);
+          if (inc1) FI(n, fk, fj, fi + 1) = fc + (gx1p * dx1fp - gx2m * dx2fm - gx3m * dx3fm);
+          if (inc2) FI(n, fk, fj + 1, fi) = fc - (gx1m * dx1fm - gx2p * dx2fp + gx3m * dx3fm);
+          if (inc2 && inc1)
+            FI(n, fk, fj + 1, fi + 1) = fc + (gx1p * dx1fp + gx2p * dx2fp - gx3m * dx3fm);
+          if (inc3) FI(n, fk + 1, fj, fi) = fc - (gx1m * dx1fm + gx2m * dx2fm - gx3p * dx3fp);
+          if (inc3 && inc1)
+            FI(n, fk + 1, fj, fi + 1) = fc + (gx1p * dx1fp - gx2m * dx2fm + gx3p * dx3fp);
+          if (inc3 && inc2)
+            FI(n, fk + 1, fj + 1, fi) = fc - (gx1m * dx1fm - gx2p * dx2fp - gx3p * dx3fp);
+          if (inc3 && inc2 && inc1)
+            FI(n, fk + 1, fj + 1, fi + 1) = fc + (gx1p * dx1fp + gx2p * dx2fp + gx3p * dx3fp);
+        }
+#undef CO
+#undef FI
+}

@@ -105,6 +105,26 @@ void ao_riemann(int solver, int fluid, double gm1, const double *wl, const doubl
 
 int ao_num_threads(void);
 
+/* ---- multilevel operators ------------------------------------------ */
+/* One MeshBlock: fine array [nvar][nk][nj][ni] and its coarse buffer [nvar][cnk][cnj][cni]
+ * (Parthenon's c_cellbounds: nx/2 interior cells + ng ghosts in every active direction,
+ * P:mesh/meshblock.cpp:205-228).  box = {cis, cie, cjs, cje, cks, cke}: inclusive COARSE index
+ * range the operator loops over.  xmin/dx: the block's fine UniformCartesian. */
+typedef struct {
+  int geom, ndim, ng;
+  int ni, nj, nk;
+  int cni, cnj, cnk;
+  int ib_s, jb_s, kb_s;     /* fine interior start   */
+  int cib_s, cjb_s, ckb_s;  /* coarse interior start */
+  double xmin[3], dx[3];
+} ao_refine_geom;
+/* restriction.hpp:41-114: volume-weighted average of the 2^ndim fine cells */
+void ao_restrict_average(const ao_refine_geom *r, int nvar, const double *fine, double *coarse,
+                         const int *box);
+/* prolongation.hpp:82-184: minmod-limited linear interpolation onto the 2^ndim fine cells */
+void ao_prolongate_minmod(const ao_refine_geom *r, int nvar, const double *coarse, double *fine,
+                          const int *box);
+
 #ifdef __cplusplus
 }
 #endif

@@ -223,3 +223,41 @@ class OracleSim:
 if __name__ == "__main__":
     build(force=True)
     print(_LIB, "threads:", lib().ao_num_threads(), file=sys.stderr)
+
+
+# ---- multilevel operators ----------------------------------------------
+class RefineGeom(C.Structure):
+    """ao_refine_geom: one MeshBlock's fine array and coarse buffer (artemis_oracle.h)."""
+    _fields_ = [(n, C.c_int) for n in
+                ("geom", "ndim", "ng", "ni", "nj", "nk", "cni", "cnj", "cnk", "ib_s", "jb_s",
+                 "kb_s", "cib_s", "cjb_s", "ckb_s")] + [("xmin", C.c_double * 3),
+                                                        ("dx", C.c_double * 3)]
+
+
+def refine_geom(mesh, b=0):
+    """Coarse-buffer geometry of block b: nx/2 interior cells + ng ghosts in every active
+    direction (P:mesh/meshblock.cpp:205-228)."""
+    ng, nd = mesh.nghost, mesh.ndim
+    cn = [mesh.block_nx[d] // 2 + 2 * ng if d < nd else 1 for d in range(3)]
+    cs = [ng if d < nd else 0 for d in range(3)]
+    r = RefineGeom(int(mesh.coords), nd, ng, mesh.ni, mesh.nj, mesh.nk, cn[0], cn[1], cn[2],
+                   mesh.is_, mesh.js, mesh.ks, cs[0], cs[1], cs[2])
+    for d in range(3):
+        r.xmin[d] = float(mesh.blk_xmin[b, d])
+        r.dx[d] = float(mesh.blk_dx[b, d])
+    return r
+
+
+def _box(box):
+    return (C.c_int * 6)(*[int(v) for v in box])
+
+
+def restrict_average(L, r, fine, coarse, box, prefix="ao"):
+    """coarse[box] <- volume-weighted average of fine; fine [nvar][nk][nj][ni]."""
+    getattr(L, prefix + "_restrict_average")(C.byref(r), fine.shape[0], _p(fine), _p(coarse),
+                                             _box(box))
+
+
+def prolongate_minmod(L, r, coarse, fine, box, prefix="ao"):
+    getattr(L, prefix + "_prolongate_minmod")(C.byref(r), coarse.shape[0], _p(coarse), _p(fine),
+                                              _box(box))

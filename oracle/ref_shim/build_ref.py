@@ -17,15 +17,20 @@ def build(force=False):
     lib = os.path.join(OUT, "libartemis_ref.so")
     if not os.path.isdir(os.path.join(REF, "src")):
         return lib if os.path.exists(lib) else None
-    srcs = [os.path.join(HERE, "ref_api.cpp")] + [
+    srcs = [os.path.join(HERE, "ref_api.cpp"), os.path.join(HERE, "ref_refine.cpp")] + [
         os.path.join(dp, f) for dp, _, fs in os.walk(os.path.join(HERE, "include")) for f in fs]
     if (not force and os.path.exists(lib)
             and all(os.path.getmtime(lib) >= os.path.getmtime(s) for s in srcs)):
         return lib
     os.makedirs(OUT, exist_ok=True)
+    refine = os.path.join(REF, "src", "utils", "refinement")
     cmd = ["g++", "-O3", "-DNDEBUG", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-fPIC",
            "-shared", "-w", "-I", os.path.join(HERE, "include"), "-I", os.path.join(REF, "src"),
-           os.path.join(HERE, "ref_api.cpp"), "-o", lib]
+           # the two multilevel operator headers, named explicitly (the include path resolves
+           # "utils/refinement/*.hpp" to the mocks of the uniform-mesh translation unit)
+           '-DAR_PROLONGATION_HPP="%s"' % os.path.join(refine, "prolongation.hpp"),
+           '-DAR_RESTRICTION_HPP="%s"' % os.path.join(refine, "restriction.hpp"),
+           os.path.join(HERE, "ref_api.cpp"), os.path.join(HERE, "ref_refine.cpp"), "-o", lib]
     subprocess.check_call(cmd)
     return lib
 

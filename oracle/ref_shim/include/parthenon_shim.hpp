@@ -83,6 +83,22 @@ struct UniformCartesian {
 };
 using Coordinates_t = UniformCartesian;
 
+// ---- multilevel operators (src/utils/refinement/*.hpp) ------------------------------------
+// SIGN: P:config.hpp.in:86.  ParArrayND<Real, VariableState>: the 7-index accessor the
+// prolongation / restriction stencils use, over ONE borrowed [nvar][nk][nj][ni] array
+// (cell-centred fields only: element index, l and m are always 0).
+#define SIGN(x) (((x) < 0.0) ? -1.0 : 1.0)
+using TE = TopologicalElement;
+struct VariableState {};
+template <class T, class State = void>
+struct ParArrayND {
+  T *data = nullptr;
+  int nvar = 0, nk = 0, nj = 0, ni = 0;
+  T &operator()(int /*el*/, int /*l*/, int /*m*/, int n, int k, int j, int i) const {
+    return data[(((size_t)n * nk + k) * nj + j) * ni + i];
+  }
+};
+
 // ---- metadata flags / pack options ---------------------------------------------------------
 enum class MetadataFlag { Conserved, WithFluxes, FillGhost };
 struct Metadata {
