@@ -125,6 +125,111 @@ def plan_sweeps(mesh, fluids, lay, rl, periodic=(False, False, False)):
     return plans
 
 
+class PeerPlan:
+    """One aggregated message per peer rank (direct scheme): every (block, neighbour offset)
+    sub-box this rank owes that peer, and where the peer's matching message is unpacked."""
+
+    def __init__(self, peer):
+        self.peer = peer
+        self.send = []     # (fluid, block, var0, ncomp, si, ei, sj, ej, sk, ek, offset)
+        self.recv = []
+        self.nsend = 0     # doubles
+        self.nrecv = 0
+
+
+def plan_direct(mesh, fluids, lay, rl, periodic=(False, False, False)):
+    """Single-round exchange: for every neighbour offset o in {-1,0,1}^3 whose non-zero
+    directions ALL cross onto another rank, the blocks on that rank face / edge / corner send
+    their ng innermost layers along the non-zero directions and their INTERIOR range along the
+    others, straight to the rank that owns the ghost zones (<= 26 peers, 7 in a 2x2x2 lattice).
+    Ghost cells that combine a remote direction with a same-rank neighbour or a physical
+    boundary are not sent at all: ab200_finish_remote_ghosts resolves them on the receiver from
+    the delivered cells.  Returns [PeerPlan] sorted by peer.
+
+    Matching: both ends walk the offsets in the same canonical order (the sender in o, the
+    receiver in -o) and the blocks of a face / edge in lexicographic order of the tangential
+    lattice coordinates, so the aggregated buffers line up without tags."""
+    nbd = tuple(mesh.lattice_n)
+    ng = mesh.ngd
+    s = (mesh.is_, mesh.js, mesh.ks)
+    e = (mesh.ie, mesh.je, mesh.ke)
+    nt = (mesh.ni, mesh.nj, mesh.nk)
+    offsets = [(ox, oy, oz) for oz in (-1, 0, 1) for oy in (-1, 0, 1) for ox in (-1, 0, 1)
+               if (ox, oy, oz) != (0, 0, 0)]
+
+    def peer_of(o):
+        """rank owning the neighbour tile at offset o, or None if some non-zero direction does
+        not cross onto another rank"""
+        prc = list(rl)
+        for d in range(3):
+            if o[d] == 0:
+                continue
+            if nt[d] == 1 or lay[d] == 1:
+                return None
+            prc[d] += o[d]
+            if prc[d] < 0 or prc[d] >= lay[d]:
+                if not periodic[d]:
+                    return None
+                prc[d] %= lay[d]
+        return rank_of(prc, lay)
+
+    def boxes(o, sending):
+        """(block, lo[3], hi[3]) of every block on the face / edge / corner of offset o"""
+        rng = []
+        for d in range(3):
+            if o[d] == 0:
+                rng.append(range(nbd[d]))
+            else:
+                rng.append([nbd[d] - 1] if o[d] > 0 else [0])
+        out = []
+        for lz in rng[2]:
+            for ly in rng[1]:
+                for lx in rng[0]:
+                    l = (lx, ly, lz)
+                    b = lx + nbd[0] * (ly + nbd[1] * lz)
+                    lo, hi = [0, 0, 0], [0, 0, 0]
+                    for d in range(3):
+                        if o[d] == 0:
+                            lo[d], hi[d] = s[d], e[d]
+                        elif sending:
+                            lo[d], hi[d] = ((e[d] - ng[d] + 1, e[d]) if o[d] > 0
+                                            else (s[d], s[d] + ng[d] - 1))
+                        else:
+                            lo[d], hi[d] = ((e[d] + 1, e[d] + ng[d]) if o[d] > 0
+                                            else (s[d] - ng[d], s[d] - 1))
+                    out.append((b, lo, hi))
+        return out
+
+    plans = {}
+
+    def add(o, sending):
+        # the receiver walks the offsets in the sender's order: its offset is -o of the sender
+        peer = peer_of(o)
+        if peer is None:
+            return
+        p = plans.setdefault(peer, PeerPlan(peer))
+        for b, lo, hi in boxes(o, sending):
+            ncell = 1
+            for d in range(3):
+                ncell *= hi[d] - lo[d] + 1
+            for fl, S in fluids:
+                for var0, ncomp in ghost_var_runs(fl, S):
+                    if sending:
+                        p.send.append((int(fl), b, var0, ncomp, lo[0], hi[0], lo[1], hi[1], lo[2],
+                                       hi[2], p.nsend))
+                        p.nsend += ncomp * ncell
+                    else:
+                        p.recv.append((int(fl), b, var0, ncomp, lo[0], hi[0], lo[1], hi[1], lo[2],
+                                       hi[2], p.nrecv))
+                        p.nrecv += ncomp * ncell
+
+    for o in offsets:
+        add(o, True)
+    for o in offsets:
+        add(tuple(-v for v in o), False)
+    return [plans[k] for k in sorted(plans)]
+
+
 class DeviceBackend:
     """Pack/unpack through the C ABI into torch CUDA tensors."""
 
@@ -202,6 +307,21 @@ class HaloComm:
                            (self.backend.alloc(p.nelem), self.backend.alloc(p.nelem)))
             self.bufs.append(row)
         self.bytes_per_exchange = 8 * sum(p.nelem for pair in self.plans for p in pair if p)
+        # direct (single-round) scheme: ONE send slab and ONE receive slab, a slice per peer,
+        # so all packing is one kernel launch, all unpacking another
+        self.direct = plan_direct(md.mesh, fluids, self.lay, self.rl, periodic)
+        ns = sum(p.nsend for p in self.direct)
+        nr = sum(p.nrecv for p in self.direct)
+        self.dsend, self.drecv = self.backend.alloc(ns), self.backend.alloc(nr)
+        self._dsend_items, self._drecv_items, self._dslices = [], [], []
+        so = ro = 0
+        for p in self.direct:
+            self._dsend_items += [it[:10] + (it[10] + so,) for it in p.send]
+            self._drecv_items += [it[:10] + (it[10] + ro,) for it in p.recv]
+            self._dslices.append((p.peer, self.dsend[so:so + p.nsend], self.drecv[ro:ro + p.nrecv]))
+            so += p.nsend
+            ro += p.nrecv
+        self.bytes_per_direct_exchange = 8 * ns
 
     def pack_sweep(self, d):
         """ab200_halo_pack of both sides of direction d into the send buffers."""
@@ -238,6 +358,24 @@ class HaloComm:
             self.pack_sweep(d)
             self.transfer_sweep(d)
             self.unpack_sweep(d)
+
+    def transfer_direct(self):
+        """One grouped send + recv per peer, all peers in one NCCL group."""
+        dist = self.dist
+        ops = [dist.P2POp(dist.isend, sb, peer) for peer, sb, _ in self._dslices]
+        ops += [dist.P2POp(dist.irecv, rb, peer) for peer, _, rb in self._dslices]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def exchange_direct(self, md=None):
+        """Single-round remote exchange (one pack launch, one NCCL group, one unpack launch).
+        Delivers only the ghost cells whose non-interior directions are all remote; call
+        ab200_finish_remote_ghosts afterwards (the device-resident cycle does)."""
+        if not self._dslices:
+            return
+        self.backend.pack(self._dsend_items, self.dsend)
+        self.transfer_direct()
+        self.backend.unpack(self._drecv_items, self.drecv)
 
     def allreduce_min(self, value: float) -> float:
         """MPI_Allreduce(&dt, 1, MPI_DOUBLE, MPI_MIN) of P:driver/driver.cpp:237."""

@@ -236,7 +236,7 @@ class ArtemisDriver:
                 md.call("ab200_fill_ghosts")
             else:
                 md.call("ab200_fill_ghosts_local")
-                self.comm.exchange(md)
+                self.comm.exchange_direct(md)     # single round: faces, edges, corners at once
                 md.call("ab200_finish_remote_ghosts")
         if self.comm is not None:
             self.comm.allreduce_min_device()

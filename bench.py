@@ -284,6 +284,23 @@ def main():
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt.item())
     value = zones * args.steps / (t_ms * 1e-3)
+    # N > 1: device time of the remote halo exchange alone (single round: one pack launch, one
+    # NCCL group of sends/receives to all peers, one unpack launch), back to back with no compute in between -- explains the scaling loss
+    comm_ms = None
+    if world > 1:
+        sync_all()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            comm.exchange_direct(md)
+        sync_all()
+        ev0.record()
+        for _ in range(20):
+            comm.exchange_direct(md)
+        ev1.record()
+        torch.cuda.synchronize()
+        ct = torch.tensor([ev0.elapsed_time(ev1) / 20.0], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(ct, op=dist.ReduceOp.MAX)
+        comm_ms = float(ct.item())
     ts = md.time_state() if world == 1 else None
 
     # ---- per-kernel timing of the dominant kernels (fused directional passes) -------------
@@ -405,8 +422,9 @@ def main():
                            "path": ("single-pass stage kernel" if path == "single_pass" else
                                     "three directional fused passes") +
                                    (" + fused ghost fill + device-resident dt" if world == 1 else
-                                    " + NCCL halo sweeps + device-resident dt all-reduce"),
-                           "stage_path": path},
+                                    " + single-round NCCL halo exchange + device-resident dt all-reduce"),
+                           "stage_path": path, "halo_exchange_ms": comm_ms,
+                           "halo_bytes_per_exchange": (comm.bytes_per_direct_exchange if comm else 0)},
                 "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks}
         if ts is not None:

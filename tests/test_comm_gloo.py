@@ -14,7 +14,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from artemis_b200.comm import HaloComm, plan_sweeps, rank_coords
+from artemis_b200.comm import HaloComm, plan_direct, plan_sweeps, rank_coords
 from artemis_b200.enums import BoundaryFlag, Coordinates, Fluid, ReconstructionMethod, RSolver
 from artemis_b200.mesh import UniformMesh
 from artemis_b200.params import FluidParams
@@ -99,7 +99,33 @@ def _oracle_exchange(mesh, fp, prim, bc, phases):
                                gv.ctypes.data_as(IP), vd.ctypes.data_as(IP), phases)
 
 
-def _worker(rank, world, lay, bc_name, port, q):
+def _pure_remote_mask(tm, tbc):
+    """[nb] boolean masks [nk][nj][ni] of the ghost cells the direct scheme delivers: ghost
+    index only along directions whose face belongs to another rank, interior along the rest."""
+    s = (tm.is_, tm.js, tm.ks)
+    e = (tm.ie, tm.je, tm.ke)
+    nt = (tm.ni, tm.nj, tm.nk)
+    nbd = tuple(tm.lattice_n)
+    masks = []
+    for b in range(tm.nb):
+        l = (b % nbd[0], (b // nbd[0]) % nbd[1], b // (nbd[0] * nbd[1]))
+        ok = np.ones((nt[2], nt[1], nt[0]), dtype=bool)
+        ghost_any = np.zeros_like(ok)
+        for d in range(3):
+            idx = np.arange(nt[d])
+            shape = [1, 1, 1]
+            shape[2 - d] = nt[d]
+            lo_g = (idx < s[d]).reshape(shape)
+            hi_g = (idx > e[d]).reshape(shape)
+            lo_remote = l[d] == 0 and tbc[2 * d] == 3
+            hi_remote = l[d] == nbd[d] - 1 and tbc[2 * d + 1] == 3
+            ok &= ~(lo_g & (not lo_remote)) & ~(hi_g & (not hi_remote))
+            ghost_any |= lo_g | hi_g
+        masks.append(ok & ghost_any)
+    return masks
+
+
+def _worker(rank, world, lay, bc_name, port, q, scheme="sweeps"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -143,16 +169,29 @@ def _worker(rank, world, lay, bc_name, port, q):
                         periodic=periodic, dist=dist)
         for fp in fps:   # same-rank neighbours
             _oracle_exchange(tm, fp, tprims[int(fp.fluid_type)], tbc, 1)
-        comm.exchange()
-        for fp in fps:   # physical boundaries
-            _oracle_exchange(tm, fp, tprims[int(fp.fluid_type)], tbc, 2)
         ok = True
-        for fp, w in zip(fps, want):
-            got = tprims[int(fp.fluid_type)]
-            gv, _ = _ghost_lists(fp)
-            ok = ok and np.array_equal(got[:, gv], w[gid][:, gv])
+        if scheme == "direct":
+            # single round; delivers exactly the pure-remote ghost cells (the rest is resolved
+            # on the device by ab200_finish_remote_ghosts, covered by tests/test_gpu_multirank.py)
+            comm.exchange_direct()
+            masks = _pure_remote_mask(tm, tbc)
+            for fp, w in zip(fps, want):
+                got = tprims[int(fp.fluid_type)]
+                gv, _ = _ghost_lists(fp)
+                for b in range(tm.nb):
+                    ok = ok and masks[b].any()
+                    ok = ok and np.array_equal(got[b][gv][:, masks[b]], w[gid[b]][gv][:, masks[b]])
+        else:
+            comm.exchange()
+            for fp in fps:   # physical boundaries
+                _oracle_exchange(tm, fp, tprims[int(fp.fluid_type)], tbc, 2)
+            for fp, w in zip(fps, want):
+                got = tprims[int(fp.fluid_type)]
+                gv, _ = _ghost_lists(fp)
+                ok = ok and np.array_equal(got[:, gv], w[gid][:, gv])
         dtmin = comm.allreduce_min(1.0 + rank)
-        q.put((rank, bool(ok), dtmin, comm.bytes_per_exchange))
+        q.put((rank, bool(ok), dtmin, comm.bytes_per_exchange if scheme == "sweeps"
+               else comm.bytes_per_direct_exchange))
     finally:
         dist.destroy_process_group()
 
@@ -206,3 +245,55 @@ def test_plan_is_symmetric_between_peers():
                     assert [a[5] - a[4], a[7] - a[6], a[9] - a[8]] == \
                            [b[5] - b[4], b[7] - b[6], b[9] - b[8]]
     assert npeers == 8 * 3   # 2x2x2, non-periodic: every rank has exactly 3 face peers
+
+
+@pytest.mark.parametrize("lay,bc_name", [((2, 1, 1), "periodic"), ((2, 2, 1), "outflow"),
+                                         ((1, 2, 2), "periodic")])
+def test_direct_exchange_delivers_every_pure_remote_ghost_cell(lay, bc_name, oracle_lib):
+    """Single-round scheme over gloo with 2 and 4 ranks: faces, rank edges (two remote
+    directions) and the periodic wrap onto one peer from both sides."""
+    world = lay[0] * lay[1] * lay[2]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + 11 * sum(lay) + len(bc_name)
+    procs = [ctx.Process(target=_worker, args=(r, world, lay, bc_name, port, q, "direct"))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, dtmin, nbytes in res:
+        assert ok, f"rank {rank}: delivered ghost zones differ from the single-process exchange"
+        assert dtmin == 1.0 and nbytes > 0
+
+
+def test_direct_plan_is_symmetric_between_peers():
+    """2x2x2 lattice: 7 peers per rank (3 faces, 3 edges, 1 corner); what A packs for B is
+    exactly what B expects from A, box by box."""
+    lay = (2, 2, 2)
+    fps = _fps()
+    fl = [(fp.fluid_type, fp.nspecies) for fp in fps]
+    plans = {}
+    for r in range(8):
+        rl = rank_coords(r, lay)
+        gm = _global_mesh((BoundaryFlag.outflow,) * 6, lay)
+        nbt = tuple(gm.nrb[d] // lay[d] for d in range(3))
+        tm = UniformMesh(nx=gm.nx, xmin=gm.xmin, xmax=gm.xmax, block_nx=gm.block_nx, nghost=2,
+                         bcs=gm.bcs, lattice_lo=tuple(rl[d] * nbt[d] for d in range(3)),
+                         lattice_n=nbt)
+        plans[r] = {p.peer: p for p in plan_direct(tm, fl, lay, rl)}
+    for r in range(8):
+        assert len(plans[r]) == 7
+        for peer, p in plans[r].items():
+            q = plans[peer][r]
+            assert p.nsend == q.nrecv and p.nrecv == q.nsend and len(p.send) == len(q.recv)
+            for a, b in zip(p.send, q.recv):
+                assert a[0] == b[0] and a[2:4] == b[2:4] and a[10] == b[10]
+                assert [a[5] - a[4], a[7] - a[6], a[9] - a[8]] == \
+                       [b[5] - b[4], b[7] - b[6], b[9] - b[8]]
+    # the single round moves less than the three forwarding sweeps (no tangential ghosts)
+    rl = rank_coords(0, lay)
+    sweep_elems = sum(p.nelem for pair in plan_sweeps(tm, fl, lay, rank_coords(7, lay)) for p in pair if p)
+    assert sum(p.nsend for p in plans[7].values()) < sweep_elems

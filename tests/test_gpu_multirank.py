@@ -41,7 +41,8 @@ def _tile_bcs(bcs, lay, rl, periodic):
     ((1, 2, 2), "reflect", True, "rk3"),
     ((2, 2, 1), "mixed", False, "rk2"),
 ])
-def test_multirank_cycles_bit_identical_to_single_context(lay, bc, with_dust, integ):
+@pytest.mark.parametrize("scheme", ["direct", "sweeps"])
+def test_multirank_cycles_bit_identical_to_single_context(lay, bc, with_dust, integ, scheme):
     bcs = {"outflow": (B.outflow,) * 6, "periodic": (B.periodic,) * 6, "reflect": (B.reflect,) * 6,
            "mixed": (B.reflect, B.outflow, B.periodic, B.periodic, B.outflow, B.reflect)}[bc]
     periodic = tuple(bcs[2 * d] == B.periodic for d in range(3))
@@ -104,6 +105,28 @@ def test_multirank_cycles_bit_identical_to_single_context(lay, bc, with_dust, in
             torch.cuda.synchronize()
             for _, c, _ in ranks:
                 c.unpack_sweep(d)
+
+    def direct():
+        """single-round scheme: every rank packs once, the loopback copies each peer slice into
+        the peer's receive slice for this rank, every rank unpacks once"""
+        import torch
+        for _, c, _ in ranks:
+            if c._dslices:
+                c.backend.pack(c._dsend_items, c.dsend)
+        for tmd, c, _ in ranks:
+            tmd.synchronize()
+        for r, (_, c, _) in enumerate(ranks):
+            for peer, sb, _ in c._dslices:
+                back = [rb for pr, _, rb in ranks[peer][1]._dslices if pr == r]
+                assert len(back) == 1 and back[0].numel() == sb.numel()
+                back[0].copy_(sb)
+        torch.cuda.synchronize()
+        for _, c, _ in ranks:
+            if c._dslices:
+                c.backend.unpack(c._drecv_items, c.drecv)
+
+    if scheme == "direct":
+        sweeps = direct  # noqa: F811
 
     # Mesh::Initialize: PrimToCons, exchange, PrimToCons (driver.py Initialize, split by phase)
     for tmd, _, _ in ranks:
