@@ -13,4 +13,4 @@ PY
 run base A=1
 run ch16 NCCL_MIN_P2P_NCHANNELS=16 NCCL_MAX_P2P_NCHANNELS=32
 run ch32 NCCL_MIN_P2P_NCHANNELS=32 NCCL_MAX_P2P_NCHANNELS=32
-run ce NCCL_P2P_USE_CUDA_MEMCPY=1
+# (NCCL_P2P_USE_CUDA_MEMCPY=1 hangs the 4-rank job on this box: do not retry)

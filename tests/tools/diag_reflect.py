@@ -1,7 +1,7 @@
 """Where does the sweep path differ from the oracle under reflecting boundaries?"""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from artemis_b200.driver import ArtemisDriver
 from artemis_b200.enums import BoundaryFlag, Coordinates, Fluid
 from artemis_b200.mesh import UniformMesh
