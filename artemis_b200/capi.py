@@ -53,7 +53,7 @@ SYMBOLS = [
     "ab200_prim_to_cons", "ab200_deep_copy_conserved", "ab200_estimate_timestep",
     "ab200_fused_stage", "ab200_sync_prim", "ab200_prim_to_cons_ghosts", "ab200_estimate_timestep_device",
     "ab200_set_global_timestep_device", "ab200_dt_device", "ab200_read_time_state",
-    "ab200_write_time_state", "ab200_halo_pack", "ab200_halo_unpack", "ab200_coarse_shape", "ab200_restrict", "ab200_prolongate",
+    "ab200_write_time_state", "ab200_halo_pack", "ab200_halo_unpack", "ab200_set_halo_stream", "ab200_coarse_shape", "ab200_restrict", "ab200_prolongate",
     "ab200_set_topology",
     "ab200_exchange_ghosts", "ab200_apply_physical_bcs", "ab200_fill_ghosts",
     "ab200_fill_ghosts_local", "ab200_finish_remote_ghosts", "ab200_cycles_host",
@@ -101,6 +101,7 @@ def load(variant: str | None = None) -> C.CDLL:
         "ab200_read_time_state": [vp, _DP], "ab200_write_time_state": [vp, _DP],
         "ab200_halo_pack": [vp, C.POINTER(BndDesc), i],
         "ab200_halo_unpack": [vp, C.POINTER(BndDesc), i],
+        "ab200_set_halo_stream": [vp, vp],
         "ab200_coarse_shape": [vp, C.POINTER(C.c_int)],
         "ab200_restrict": [vp, C.POINTER(RefineDesc), i],
         "ab200_prolongate": [vp, C.POINTER(RefineDesc), i],

@@ -377,6 +377,45 @@ class HaloComm:
         self.transfer_direct()
         self.backend.unpack(self._drecv_items, self.drecv)
 
+    # ---- overlapped form: the remote round runs on its own stream next to the local fill ----
+    def _async_setup(self):
+        import os
+        t = getattr(self.backend, "torch", None)
+        if (t is None or not t.cuda.is_available() or not isinstance(self.backend, DeviceBackend)
+                or os.environ.get("AB200_NO_OVERLAP")):
+            self._async = False
+            return
+        self._async = True
+        self._t = t
+        self.stream = t.cuda.Stream(device=self.backend.device)
+        self._ev_stage = t.cuda.Event()
+        self._ev_comm = t.cuda.Event()
+
+    def begin_direct(self, md=None):
+        """Start the single-round remote exchange of the stage that was just launched on the
+        current stream.  On a GPU it runs on a second stream (pack, NCCL group, unpack), so
+        ab200_fill_ghosts_local -- which reads interior zones only and writes none of the
+        ghost cells the unpack writes -- can run concurrently; end_direct() joins."""
+        if not hasattr(self, "_async"):
+            self._async_setup()
+        if not self._async or not self._dslices:
+            self.exchange_direct(md)
+            return
+        t = self._t
+        self._ev_stage.record(t.cuda.current_stream())
+        self.md.call("ab200_set_halo_stream", C.c_void_p(self.stream.cuda_stream))
+        try:
+            with t.cuda.stream(self.stream):
+                self.stream.wait_event(self._ev_stage)
+                self.exchange_direct(md)
+                self._ev_comm.record(self.stream)
+        finally:
+            self.md.call("ab200_set_halo_stream", None)
+
+    def end_direct(self, md=None):
+        if getattr(self, "_async", False) and self._dslices:
+            self._t.cuda.current_stream().wait_event(self._ev_comm)
+
     def allreduce_min(self, value: float) -> float:
         """MPI_Allreduce(&dt, 1, MPI_DOUBLE, MPI_MIN) of P:driver/driver.cpp:237."""
         return self.backend.allreduce_min(self.dist, value)

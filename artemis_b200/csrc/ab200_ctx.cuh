@@ -67,6 +67,8 @@ struct Topology {
 struct ab200_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t halo_stream = nullptr;  // ab200_set_halo_stream (pack / unpack kernels)
+  bool halo_stream_set = false;
   bool grid_set = false;
   ab200::GridDev g{};
   ab200::GridDev gc{};          // coarse buffers of the multilevel operators (refine.cu)

@@ -333,6 +333,13 @@ int ab200_set_stage_path(ab200_ctx *c, int path) {
   return AB200_OK;
 }
 
+int ab200_set_halo_stream(ab200_ctx *c, void *cuda_stream) {
+  AB_REQUIRE(c, AB200_EINVAL, "null context");
+  c->halo_stream = (cudaStream_t)cuda_stream;
+  c->halo_stream_set = cuda_stream != nullptr;
+  return AB200_OK;
+}
+
 int ab200_get_stage_path(ab200_ctx *c, int fluid, int *path_out) {
   AB_REQUIRE(c && path_out, AB200_EINVAL, "ab200_get_stage_path: null argument");
   AB_REQUIRE(c->grid_set, AB200_ESTATE, "no grid bound: call ab200_set_grid");

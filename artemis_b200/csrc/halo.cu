@@ -369,8 +369,9 @@ int launch_halo(ab200_ctx *c, const ab200_bnd_desc *bnd, int n, int unpack) {
   if (gx > 64) gx = 64;
   dim3 grid(gx, (unsigned)n);
   const FluidDev &f0 = c->fl[0].d, &f1 = c->fl[1].d;
-  if (unpack) k_halo<true><<<grid, kThreads, 0, c->stream>>>(g, f0, f1, d);
-  else k_halo<false><<<grid, kThreads, 0, c->stream>>>(g, f0, f1, d);
+  cudaStream_t hs = c->halo_stream_set ? c->halo_stream : c->stream;
+  if (unpack) k_halo<true><<<grid, kThreads, 0, hs>>>(g, f0, f1, d);
+  else k_halo<false><<<grid, kThreads, 0, hs>>>(g, f0, f1, d);
   c->launches++;
   AB_CUDA(cudaGetLastError());
   return AB200_OK;

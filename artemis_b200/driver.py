@@ -224,7 +224,8 @@ class ArtemisDriver:
         """One cycle with no host round trip: per stage ab200_fused_stage (dt read from the
         device scalar, CFL reduction folded into the last stage) -> ghost fill; then the dt
         all-reduce on the device scalar and ab200_set_global_timestep_device.  Multi-rank:
-        local ghost fill -> three remote face sweeps (pack / NCCL / unpack) -> finish."""
+        single-round remote exchange (pack / NCCL / unpack on a second stream) concurrent with
+        the local ghost fill -> finish."""
         md, integ = self.md, self.integrator
         for stage in range(1, integ.nstages + 1):
             do_pcm = (stage == 1) and (integ.GetName() == "vl2")
@@ -235,8 +236,11 @@ class ArtemisDriver:
             if self.comm is None:
                 md.call("ab200_fill_ghosts")
             else:
+                # single remote round (faces, rank edges, corners at once) on its own stream,
+                # concurrent with the same-GPU ghost fill; both join before the finish pass
+                self.comm.begin_direct(md)
                 md.call("ab200_fill_ghosts_local")
-                self.comm.exchange_direct(md)     # single round: faces, edges, corners at once
+                self.comm.end_direct(md)
                 md.call("ab200_finish_remote_ghosts")
         if self.comm is not None:
             self.comm.allreduce_min_device()

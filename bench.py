@@ -268,8 +268,10 @@ def main():
     l0 = md.launch_count()
     sync_all()
     md.call("ab200_timer_begin")
+    t_cpu0 = time.perf_counter()
     for _ in range(args.steps):
         one_step()
+    cpu_issue_ms = 1e3 * (time.perf_counter() - t_cpu0) / args.steps   # host time to ISSUE a step
     ms = __import__("ctypes").c_float()
     md.call("ab200_timer_end", __import__("ctypes").byref(ms))
     sync_all()
@@ -423,7 +425,7 @@ def main():
                                     "three directional fused passes") +
                                    (" + fused ghost fill + device-resident dt" if world == 1 else
                                     " + single-round NCCL halo exchange + device-resident dt all-reduce"),
-                           "stage_path": path, "halo_exchange_ms": comm_ms,
+                           "stage_path": path, "halo_exchange_ms": comm_ms, "host_issue_ms_per_step": cpu_issue_ms,
                            "halo_bytes_per_exchange": (comm.bytes_per_direct_exchange if comm else 0)},
                 "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks}

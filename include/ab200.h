@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AB200_ABI_VERSION 5
+#define AB200_ABI_VERSION 6
 
 /* src/artemis.hpp:78-105 */
 enum { AB200_CARTESIAN = 0, AB200_CYLINDRICAL = 1, AB200_SPHERICAL1D = 2,
@@ -227,6 +227,12 @@ int ab200_write_time_state(ab200_ctx *ctx, const double *host4);
  * (P:bvals/comms/boundary_communication.cpp:95-140, 273-334) driven by the caller's BndInfo. */
 int ab200_halo_pack(ab200_ctx *ctx, const ab200_bnd_desc *bnd, int n);
 int ab200_halo_unpack(ab200_ctx *ctx, const ab200_bnd_desc *bnd, int n);
+/* Stream the two halo kernels above are launched on (NULL: the context stream).  Lets the
+ * caller run pack -> transfer -> unpack of the remote neighbours concurrently with
+ * ab200_fill_ghosts_local on the context stream; the caller orders the two streams with events
+ * (the stage must have finished before the pack, both must have finished before
+ * ab200_finish_remote_ghosts).  The two touch disjoint ghost cells. */
+int ab200_set_halo_stream(ab200_ctx *ctx, void *cuda_stream);
 /* Library-managed same-level exchange for a uniform nbx*nby*nbz lattice of the bound blocks
  * (block id = lx + nbx*(ly + nby*lz)).
  *  ab200_exchange_ghosts: same-GPU neighbours are filled ghost<-interior in ONE kernel (no

@@ -1,0 +1,92 @@
+"""N-rank check of the device-resident cycle on REAL GPUs (one process per GPU, NCCL): after a
+few cycles every rank's tile must be bit-identical to the undivided mesh advanced by one
+context with ab200_run_cycles.  Complements tests/test_gpu_multirank.py (loopback transport on
+one GPU), which cannot see stream-ordering mistakes of the overlapped exchange.
+
+  python -m torch.distributed.run --nproc-per-node N tests/tools/check_multigpu.py [--cycles 3]
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from artemis_b200.comm import HaloComm, rank_coords  # noqa: E402
+from artemis_b200.driver import ArtemisDriver  # noqa: E402
+from artemis_b200.enums import BoundaryFlag, Coordinates  # noqa: E402
+from artemis_b200.mesh import UniformMesh  # noqa: E402
+from artemis_b200.meshdata import MeshData  # noqa: E402
+from tests.helpers import dust_params, gas_params, random_prim  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--cycles", type=int, default=3)
+ap.add_argument("--bnx", type=int, default=16)
+args = ap.parse_args()
+world, rank, local = (int(os.environ[k]) for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+lay = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
+B = BoundaryFlag
+bcs = (B.reflect, B.outflow, B.outflow, B.reflect, B.outflow, B.outflow)
+nblk = tuple(2 * lay[d] for d in range(3))
+bnx = (args.bnx,) * 3
+gm = UniformMesh(nx=tuple(nblk[d] * bnx[d] for d in range(3)), xmin=(0, 0, 0), xmax=(1.0, 0.8, 0.6),
+                 block_nx=bnx, nghost=4, bcs=bcs)
+C = Coordinates.cartesian
+gp, dp = gas_params(C, "ppm", "hllc"), dust_params(C, "plm", "hlle", S=1)
+prim, dprim = random_prim(gm, gp, seed=21, shocks=True), random_prim(gm, dp, seed=22, shocks=False)
+BIG = float(np.finfo(np.float64).max)
+
+# the undivided mesh on this rank's own GPU (every rank computes it: no gather needed)
+md = MeshData(gm, gas=gp, dust=dp, device=local, materialize_fluxes=False)
+md.gas.prim.set(prim)
+md.dust.prim.set(dprim)
+drv = ArtemisDriver(md, "rk2", mode="fused")
+drv.Initialize()
+dt0 = drv.dt
+md.set_time_state(dt0)
+md.call("ab200_run_cycles", 1, args.cycles, BIG)
+want = [(f.prim.get(), f.u0.get()) for f in md.fluids]
+want_ts = md.time_state()
+md.close()
+
+rl = rank_coords(rank, lay)
+nbt = tuple(gm.nrb[d] // lay[d] for d in range(3))
+tm = UniformMesh(nx=gm.nx, xmin=gm.xmin, xmax=gm.xmax, block_nx=gm.block_nx, nghost=4, bcs=bcs,
+                 lattice_lo=tuple(rl[d] * nbt[d] for d in range(3)), lattice_n=nbt)
+gid = [int(l[0] + gm.nrb[0] * (l[1] + gm.nrb[1] * l[2])) for l in tm.blk_loc]
+tbc = [int(v) for v in bcs]
+for d in range(3):
+    if lay[d] > 1 and rl[d] > 0:
+        tbc[2 * d] = 3
+    if lay[d] > 1 and rl[d] < lay[d] - 1:
+        tbc[2 * d + 1] = 3
+tmd = MeshData(tm, gas=gp, dust=dp, device=local, materialize_fluxes=False, bcs=tbc)
+comm = HaloComm(tmd, lay, rl, rank, world)
+tmd.gas.prim.set(np.ascontiguousarray(prim[gid]))
+tmd.dust.prim.set(np.ascontiguousarray(dprim[gid]))
+tdrv = ArtemisDriver(tmd, "rk2", mode="fused", comm=comm)
+tdrv.Initialize()
+assert tdrv.dt == dt0, (tdrv.dt, dt0)
+tmd.set_time_state(tdrv.dt)
+for _ in range(args.cycles):
+    tdrv.StepDevice()
+tmd.synchronize()
+torch.cuda.synchronize()
+ts = tmd.time_state()
+ok = bool(ts[3] == args.cycles and ts[0] == want_ts[0] and ts[2] == want_ts[2])
+for f, (wp, wu) in zip(tmd.fluids, want):
+    ok = ok and np.array_equal(f.prim.get(), wp[gid]) and np.array_equal(f.u0.get(), wu[gid])
+flag = torch.tensor([1.0 if ok else 0.0], device=f"cuda:{local}")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("check_multigpu: world %d lattice %s cycles %d -> %s (overlapped exchange: %s)" % (
+        world, lay, args.cycles, "BIT-IDENTICAL" if flag.item() == 1.0 else "MISMATCH",
+        getattr(comm, "_async", None)))
+tmd.close()
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1.0 else 1)
