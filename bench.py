@@ -195,11 +195,32 @@ def run_reference(args):
             "e2e": {"value": base["value"], "unit": "zone-cycles/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line, but NCCL (its version banner at any NCCL_DEBUG
+    level >= VERSION), torch and the CUDA runtime write to file descriptor 1 behind Python's
+    back.  Point fd 1 at stderr for the whole run and keep a private duplicate of the real
+    stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -219,9 +240,6 @@ def main():
     torch.cuda.set_device(local)
     comm = None
     if world > 1:
-        # NCCL_DEBUG=VERSION prints its banner on stdout, which must carry the JSON line only
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     mesh, gp, lay, rl = make_problem(args, rank, world)
     bcs = list(mesh.bcs)
@@ -431,7 +449,7 @@ def main():
                 "gpu_launches": launches, "clocks": clocks}
         if ts is not None:
             line["config"]["sim_time"] = float(ts[2])
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
     md.close()
