@@ -248,7 +248,8 @@ def test_plan_is_symmetric_between_peers():
 
 
 @pytest.mark.parametrize("lay,bc_name", [((2, 1, 1), "periodic"), ((2, 2, 1), "outflow"),
-                                         ((1, 2, 2), "periodic"), ((2, 2, 2), "reflect")])
+                                         ((1, 2, 2), "periodic"), ((2, 2, 1), "periodic"),
+                                         ((2, 2, 2), "reflect")])
 def test_direct_exchange_delivers_every_pure_remote_ghost_cell(lay, bc_name, oracle_lib):
     """Single-round scheme over gloo with 2, 4 and 8 ranks: faces, rank edges (two remote
     directions), the rank corner (three) and the periodic wrap onto one peer from both sides."""

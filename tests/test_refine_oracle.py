@@ -119,3 +119,25 @@ def test_prolongation_is_exact_on_constants_and_inverted_by_restriction(coords):
     tol = 1e-14 if coords == Coordinates.cartesian else 0.2
     err = np.abs(back[(slice(None),) + csl] - coarse[(slice(None),) + csl]).max()
     assert err <= tol * np.abs(coarse).max()
+
+
+@needs_ref
+@pytest.mark.parametrize("ndim", [1, 2])
+def test_lower_dimensional_cartesian_meshes_match_reference_code(ndim):
+    """DIM = 1 and 2 instantiations of both stencils (unused directions contribute exact zeros)."""
+    mesh = make_mesh(Coordinates.cartesian, ndim, nblk=(2, 1, 1), bnx=(8, 6, 4),
+                     bcs=(BoundaryFlag.outflow,) * 6)
+    r = oracle_py.refine_geom(mesh, b=0)
+    rng = np.random.default_rng(9)
+    fine = 1.0 + rng.random((2, mesh.nk, mesh.nj, mesh.ni))
+    coarse = rng.normal(size=(2, r.cnk, r.cnj, r.cni))
+    box = _interior_box(r, mesh)
+    a, b = coarse.copy(), coarse.copy()
+    oracle_py.restrict_average(oracle_py.lib(), r, fine, a, box)
+    oracle_py.restrict_average(ref_py.lib(), r, fine, b, box, prefix="ar")
+    assert np.array_equal(a, b) and not np.array_equal(a, coarse)
+    box = _interior_box(r, mesh, grow=1)
+    a, b = fine.copy(), fine.copy()
+    oracle_py.prolongate_minmod(oracle_py.lib(), r, coarse, a, box)
+    oracle_py.prolongate_minmod(ref_py.lib(), r, coarse, b, box, prefix="ar")
+    assert np.array_equal(a, b) and not np.array_equal(a, fine)
