@@ -167,3 +167,37 @@ def test_refine_rejects_bad_descriptors():
         md.call("ab200_restrict", dust, 1)
     cb.free()
     md.close()
+
+
+@pytest.mark.parametrize("ndim", [1, 2])
+def test_lower_dimensional_cartesian_meshes(ndim):
+    """DIM = 1 and 2: the unused directions contribute exact zeros, like in the reference."""
+    coords = Coordinates.cartesian
+    mesh = make_mesh(coords, ndim, nblk=(2, 1, 1), bnx=(8, 6, 4), bcs=(BoundaryFlag.outflow,) * 6)
+    gp = gas_params(coords, "plm", "hlle")
+    md = MeshData(mesh, gas=gp, variant="strict", materialize_fluxes=False)
+    rng = np.random.default_rng(3)
+    fine = 1.0 + rng.random(mesh.shape(gp.nvar))
+    md.gas.prim.set(fine)
+    r0 = oracle_py.refine_geom(mesh, 0)
+    L = oracle_py.lib()
+    box = _box(mesh, r0, 0)
+    cb = _Coarse(md, md.gas, Fluid.gas, 0, box)
+    c0 = rng.normal(size=cb.shape)
+    cb.set(c0)
+    md.call("ab200_restrict", cb.descs, mesh.nb)
+    want = c0.copy()
+    for b in range(mesh.nb):
+        oracle_py.restrict_average(L, oracle_py.refine_geom(mesh, b), fine[b], want[b], box)
+    assert np.array_equal(cb.get(), want)
+    cb.free()
+    box = _box(mesh, r0, 1)
+    cb = _Coarse(md, md.gas, Fluid.gas, 0, box)
+    cb.set(c0)
+    md.call("ab200_prolongate", cb.descs, mesh.nb)
+    want = fine.copy()
+    for b in range(mesh.nb):
+        oracle_py.prolongate_minmod(L, oracle_py.refine_geom(mesh, b), c0[b], want[b], box)
+    assert np.array_equal(md.gas.prim.get(), want)
+    cb.free()
+    md.close()
