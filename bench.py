@@ -345,10 +345,18 @@ def main():
     achieved = ALG_BYTES_PER_ZONE_STAGE * zones_local / (stage_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
+    counters = None
     if os.path.exists(tp):
         with open(tp) as fh:
-            traffic = json.load(fh).get("single_pass_dram_bytes_per_launch" if path == "single_pass"
-                                        else "fused_stage_dram_bytes_per_launch")
+            tj = json.load(fh)
+        traffic = tj.get("single_pass_dram_bytes_per_launch" if path == "single_pass"
+                         else "fused_stage_dram_bytes_per_launch")
+        # ncu counters of the same kernels (committed evidence, not re-measured here): the fp64
+        # pipe and issue-slot utilisation that explain why the HBM fraction is what it is
+        cj = tj.get("counters") or {}
+        counters = cj.get("single_pass" if path == "single_pass" else "three_pass")
+        if counters is not None:
+            counters = dict(counters, source=cj.get("source"), secondary_bound=cj.get("secondary_bound"))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "kernel": ("k_sweep_stage (one launch = one full stage: x1+x2+x3 reconstruct/Riemann/"
@@ -357,7 +365,7 @@ def main():
                            "k_xchunk_pass + k_march_pass<2> + k_march_pass<3> (one fused stage = the "
                            "three directional passes; 'achieved' = algorithmic bytes of the stage / "
                            "their summed duration)"),
-                "stage_ms": kms, "peak_source": peak_src,
+                "stage_ms": kms, "peak_source": peak_src, "ncu_counters": counters,
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_ZONE_STAGE * zones_local,
                 "whole_cycle_frac": value / world * 2 * ALG_BYTES_PER_ZONE_STAGE / (peak * 1e9)}
 
