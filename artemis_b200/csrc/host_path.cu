@@ -20,7 +20,16 @@ extern "C" int ab200_run_cycles(ab200_ctx *c, int integrator, int ncycles, doubl
   AB_REQUIRE(c && c->grid_set, AB200_ESTATE, "ab200_run_cycles: no grid bound");
   AB_REQUIRE(c->topo.set, AB200_ESTATE, "ab200_run_cycles: call ab200_set_topology first");
   AB_REQUIRE(integrator >= 0 && integrator <= 3, AB200_EINVAL, "unknown integrator");
+  // single-rank entry point: faces owned by another rank (AB200_BC_NONE) need the remote
+  // exchange between the stages, which only the caller's transport can do
+  AB_REQUIRE(topology_is_local(c), AB200_ESTATE,
+             "ab200_run_cycles: topology has AB200_BC_NONE (remote) faces; drive the stages "
+             "with ab200_fused_stage + the remote ghost exchange instead");
   AB_CUDA(cudaSetDevice(c->device));
+  // a finite tlim is honoured like EvolutionDriver::Execute does (P:driver/driver.cpp:99):
+  // the loop stops once time >= tlim, which costs one 32-byte read-back per cycle; with
+  // tlim = DBL_MAX the cycles are queued without any host round trip
+  const bool finite_tlim = tlim < 1.0e300;
   const Stage *st = integrator == 0 ? kRK1 : integrator == 1 ? kRK2 : integrator == 2 ? kVL2 : kRK3;
   const int nst = integrator == 0 ? 1 : integrator == 3 ? 3 : 2;
   for (int cyc = 0; cyc < ncycles; ++cyc) {
@@ -29,15 +38,14 @@ extern "C" int ab200_run_cycles(ab200_ctx *c, int integrator, int ncycles, doubl
       const int flags = AB200_STAGE_DEVICE_DT | AB200_STAGE_PINGPONG |
                         (s == nst - 1 ? AB200_STAGE_REDUCE_DT : 0);
       AB_TRY(ab200_fused_stage(c, st[s].g0, st[s].g1, st[s].b, 0.0, pcm, s == 0, flags));
-      if (topology_is_local(c)) {
-        AB_TRY(ab200_fill_ghosts(c));
-      } else {
-        AB_TRY(ab200_exchange_ghosts(c));
-        AB_TRY(ab200_apply_physical_bcs(c));
-        AB_TRY(ab200_prim_to_cons_ghosts(c));
-      }
+      AB_TRY(ab200_fill_ghosts(c));
     }
     AB_TRY(ab200_set_global_timestep_device(c, tlim, 1));
+    if (finite_tlim) {
+      double ts[4];
+      AB_TRY(ab200_read_time_state(c, ts));
+      if (ts[2] >= tlim) break;
+    }
   }
   // odd number of single-pass stages in total (rk1 / rk3): primitives back to the caller
   AB_TRY(ab200_sync_prim(c));

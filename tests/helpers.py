@@ -79,12 +79,69 @@ def random_prim(mesh, fp, seed=0, smooth=True, shocks=True):
 
 
 def rel_err(a, b, floor=None):
+    """Element-wise relative difference with an absolute floor.  Used only where no per-zone
+    physical scale exists (flux arrays, refinement buffers, strided golden samples); state
+    comparisons use `zone_rel_err`."""
     a = np.asarray(a)
     b = np.asarray(b)
     scale = np.maximum(np.abs(a), np.abs(b))
     if floor is None:
         floor = max(np.max(scale) * 1e-3, 1e-300)
     return float(np.max(np.abs(a - b) / np.maximum(scale, floor)))
+
+
+def zone_rel_err(got, want, fp, kind, vref=None, per_var=False):
+    """north_star's parity metric: the PER-ZONE relative difference of a state array
+    [nb][nvar][nk][nj][ni] (pack order IDN=n, IVX=S+3n+d, IPR|IEN=4S+n, ISE|IU=5S+n) against
+    the reference values `want`.  No global-maximum floor:
+
+      * positive scalars (density; pressure / total energy; sie / internal energy): the
+        difference divided by the zone's own reference value (floors: dfloor, siefloor*dfloor);
+      * vector components (velocity; momentum): the difference divided by the zone's own
+        vector magnitude, floored by the zone's own sound speed (gas: c_s = sqrt(gamma gm1 sie)
+        of that zone, times the zone's density for momenta).  A component that vanishes by
+        symmetry has no relative error of its own; the zone's characteristic speed is the
+        per-zone scale of its velocity vector.  Pressureless dust has no sound speed: its floor
+        is `vref` (per-zone array or scalar, e.g. the co-located gas sound speed) or, failing
+        that, 1e-6 of the largest dust speed on the mesh.
+    kind = "cons" | "prim".  Curvilinear momenta carry the scale factor h_d (O(1) on the test
+    domains); it is ignored in the floor only."""
+    from artemis_b200.enums import Fluid
+    got = np.asarray(got)
+    want = np.asarray(want)
+    assert got.shape == want.shape and kind in ("cons", "prim")
+    S = fp.nspecies
+    gas = fp.fluid_type == Fluid.gas
+    worst = []
+    tiny = 1e-300
+    for n in range(S):
+        rho = np.maximum(np.abs(want[:, n]), fp.dfloor)
+        vec = want[:, S + 3 * n:S + 3 * n + 3]
+        mag = np.sqrt(np.sum(vec * vec, axis=1))
+        if gas:
+            ie = np.abs(want[:, 5 * S + n])                       # sie (prim) or u (cons)
+            sie = ie / rho if kind == "cons" else ie
+            cs = np.sqrt((fp.gm1 + 1.0) * fp.gm1 * np.maximum(sie, fp.siefloor))
+            vfloor = cs * rho if kind == "cons" else cs
+        else:
+            if vref is None:
+                vf = 1e-6 * float(np.max(mag / rho if kind == "cons" else mag))
+            else:
+                vf = vref
+            vfloor = vf * rho if kind == "cons" else vf * np.ones_like(rho)
+        vscale = np.maximum(np.maximum(mag, vfloor), tiny)
+        e = [np.max(np.abs(got[:, n] - want[:, n]) / rho)]
+        for d in range(3):
+            e.append(np.max(np.abs(got[:, S + 3 * n + d] - vec[:, d]) / vscale))
+        if gas:
+            efl = fp.siefloor * fp.dfloor if kind == "cons" else fp.siefloor
+            for v in (4 * S + n, 5 * S + n):
+                sc = np.maximum(np.abs(want[:, v]), max(efl, tiny))
+                e.append(np.max(np.abs(got[:, v] - want[:, v]) / sc))
+        worst.append([float(x) for x in e])
+    if per_var:
+        return worst
+    return max(max(w) for w in worst)
 
 
 def interior(mesh, a):

@@ -13,7 +13,7 @@ from artemis_b200.mesh import UniformMesh
 from artemis_b200.meshdata import MeshData
 from artemis_b200.params import FluidParams
 from oracle.oracle_py import OracleSim
-from tests.helpers import dust_params, gas_params, make_mesh, random_prim, rel_err
+from tests.helpers import dust_params, gas_params, make_mesh, random_prim, zone_rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -104,7 +104,7 @@ def _twin_run(mesh, gp, dp, mode, variant, ncycles, integrator="rk2", seed=3, pr
         if fp is None:
             continue
         p = prim if (prim is not None and which == Fluid.gas) else random_prim(
-            mesh, fp, seed=seed + int(which), shocks=False)
+            mesh, fp, seed=seed + int(which))
         (osim.gas if which == Fluid.gas else osim.dust).prim[:] = p
         md.fluid(which).prim.set(p)
     osim.nlim = ncycles
@@ -116,7 +116,8 @@ def _twin_run(mesh, gp, dp, mode, variant, ncycles, integrator="rk2", seed=3, pr
     drv.Execute()
     out = []
     for of, df in zip(osim.fluids, md.fluids):
-        out.append((rel_err(df.u0.get(), of.u0), rel_err(df.prim.get(), of.prim)))
+        out.append((zone_rel_err(df.u0.get(), of.u0, of.fp, "cons"),
+                    zone_rel_err(df.prim.get(), of.prim, of.fp, "prim")))
     md.close()
     return out, drv, osim
 
@@ -182,8 +183,8 @@ def test_device_resident_driver_matches_host_driven(coords, bc, with_dust, integ
     mesh = make_mesh(coords, 3, bcs=bcs)
     gp = gas_params(coords, "ppm", "hllc")
     dp = dust_params(coords, "plm", "hlle", S=2) if with_dust else None
-    prim = random_prim(mesh, gp, seed=11, shocks=False)
-    dprim = random_prim(mesh, dp, seed=12, shocks=False) if with_dust else None
+    prim = random_prim(mesh, gp, seed=11)
+    dprim = random_prim(mesh, dp, seed=12) if with_dust else None
     ncyc = 4
     md1 = MeshData(mesh, gas=gp, dust=dp, variant=variant, materialize_fluxes=False)
     md1.gas.prim.set(prim)
@@ -212,8 +213,8 @@ def test_device_resident_driver_matches_host_driven(coords, bc, with_dust, integ
         assert ts[3] == ncyc and abs(ts[2] - d1.time) <= 1e-13 * d1.time
         assert abs(ts[0] - d1.dt) <= 1e-13 * d1.dt
         for f1, f2 in zip(md1.fluids, md2.fluids):
-            assert rel_err(f1.u0.get(), f2.u0.get()) <= 1e-12
-            assert rel_err(f1.prim.get(), f2.prim.get()) <= 1e-12
+            assert zone_rel_err(f1.u0.get(), f2.u0.get(), f1.fp, "cons") <= 1e-12
+            assert zone_rel_err(f1.prim.get(), f2.prim.get(), f1.fp, "prim") <= 1e-12
     md1.close()
     md2.close()
 

@@ -52,8 +52,8 @@ def test_multirank_cycles_bit_identical_to_single_context(lay, bc, with_dust, in
                      xmax=(1.0, 0.8, 0.6), block_nx=bnx, nghost=4, bcs=bcs)
     gp = gas_params(Coordinates.cartesian, "ppm", "hllc")
     dp = dust_params(Coordinates.cartesian, "plm", "hlle", S=2) if with_dust else None
-    prim = random_prim(gm, gp, seed=21, shocks=False)
-    dprim = random_prim(gm, dp, seed=22, shocks=False) if with_dust else None
+    prim = random_prim(gm, gp, seed=21)
+    dprim = random_prim(gm, dp, seed=22) if with_dust else None
     ncyc = 3
     code = {"rk1": 0, "rk2": 1, "vl2": 2, "rk3": 3}[integ]
 

@@ -11,7 +11,7 @@ from artemis_b200.mesh import UniformMesh
 from artemis_b200.meshdata import MeshData
 from artemis_b200.params import FluidParams
 from oracle.oracle_py import OracleSim
-from tests.helpers import dust_params, gas_params, random_prim, rel_err
+from tests.helpers import dust_params, gas_params, random_prim, zone_rel_err
 
 pytestmark = pytest.mark.gpu
 C = Coordinates.cartesian
@@ -43,7 +43,8 @@ def _twin(mesh, gp, dp, variant, integ, ncyc, device_resident=False, seed=5, sho
         md.call("ab200_run_cycles", code, ncyc, float(np.finfo(np.float64).max))
     else:
         drv.Execute()
-    res = [(df.u0.get(), df.prim.get(), of.u0, of.prim) for of, df in zip(osim.fluids, md.fluids)]
+    res = [(df.u0.get(), df.prim.get(), of.u0, of.prim, of.fp)
+           for of, df in zip(osim.fluids, md.fluids)]
     launches = md.launch_count()
     md.close()
     return res, launches
@@ -60,7 +61,7 @@ def test_sweep_strict_is_bit_identical_to_oracle(recon, integ, rs):
     gp = gas_params(C, recon, rs, S=2)
     dp = dust_params(C, recon, "llf" if rs == "llf" else "hlle", S=2)
     res, _ = _twin(mesh, gp, dp, "strict", integ, 2)
-    for u0, prim, ou0, oprim in res:
+    for u0, prim, ou0, oprim, _ in res:
         assert np.array_equal(u0, ou0)
         assert np.array_equal(prim, oprim)
 
@@ -75,10 +76,10 @@ def test_sweep_fast_within_1e12_one_cycle(bnx, bc):
     mesh = _mesh(tuple(2 * b for b in bnx), bnx, bcs)
     gp = gas_params(C, "ppm", "hllc")
     dp = dust_params(C, "plm", "hlle", S=2)
-    res, _ = _twin(mesh, gp, dp, "fast", "rk2", 1, shocks=False)
-    for u0, prim, ou0, oprim in res:
-        assert rel_err(u0, ou0) <= 1e-12
-        assert rel_err(prim, oprim) <= 1e-12
+    res, _ = _twin(mesh, gp, dp, "fast", "rk2", 1)
+    for u0, prim, ou0, oprim, fp in res:
+        assert zone_rel_err(u0, ou0, fp, "cons") <= 1e-12
+        assert zone_rel_err(prim, oprim, fp, "prim") <= 1e-12
 
 
 @pytest.mark.parametrize("integ", ["rk1", "rk2", "vl2", "rk3"])
@@ -88,7 +89,7 @@ def test_sweep_device_resident_pingpong_matches_oracle(integ):
     mesh = _mesh((32, 32, 32), (16, 16, 16), (BoundaryFlag.outflow,) * 6)
     gp = gas_params(C, "ppm", "hllc")
     res, launches = _twin(mesh, gp, None, "strict", integ, 3, device_resident=True)
-    for u0, prim, ou0, oprim in res:
+    for u0, prim, ou0, oprim, _ in res:
         assert np.array_equal(u0, ou0)
         assert np.array_equal(prim, oprim)
     assert launches > 0
@@ -116,8 +117,8 @@ def test_sweep_blast_hundred_cycles_and_single_launch_per_stage():
     n0 = md.launch_count()
     md.call("ab200_run_cycles", 1, 100, float(np.finfo(np.float64).max))
     per_cycle = (md.launch_count() - n0) / 100.0
-    assert rel_err(md.gas.u0.get(), osim.gas.u0) <= 1e-9
-    assert rel_err(md.gas.prim.get(), osim.gas.prim) <= 1e-9
+    assert zone_rel_err(md.gas.u0.get(), osim.gas.u0, gp, "cons") <= 1e-9
+    assert zone_rel_err(md.gas.prim.get(), osim.gas.prim, gp, "prim") <= 1e-9
     ts = md.time_state()
     assert ts[3] == 100 and abs(ts[2] - osim.time) <= 1e-12 * osim.time
     assert per_cycle <= 8, per_cycle
@@ -160,11 +161,11 @@ def test_paths_agree_and_can_be_switched_mid_run(bc):
             md.call("ab200_sync_prim")
         else:
             md.call("ab200_run_cycles", 3, 1, big)
-        out[path] = [(f.u0.get(), f.prim.get()) for f in md.fluids] + [md.time_state()]
+        out[path] = [(f.u0.get(), f.prim.get(), f.fp) for f in md.fluids] + [md.time_state()]
         md.close()
     for path in ("single_pass", "switch"):
-        for (u_a, p_a), (u_b, p_b) in zip(out["three_pass"][:2], out[path][:2]):
-            assert rel_err(u_a, u_b) <= 1e-12, path
-            assert rel_err(p_a, p_b) <= 1e-12, path
+        for (u_a, p_a, fp), (u_b, p_b, _) in zip(out["three_pass"][:2], out[path][:2]):
+            assert zone_rel_err(u_b, u_a, fp, "cons") <= 1e-12, path
+            assert zone_rel_err(p_b, p_a, fp, "prim") <= 1e-12, path
         ta, tb = out["three_pass"][2], out[path][2]
         assert ta[3] == tb[3] == 1 and abs(ta[0] - tb[0]) <= 1e-13 * ta[0], path
