@@ -27,6 +27,7 @@ UNITS = [("api.cu", [], ""), ("tasks.cu", [], ""), ("halo.cu", [], ""),
          ("fused_dispatch.cu", [], ""), ("host_path.cu", [], ""), ("tma_maps.cu", [], "")]
 UNITS += [("sweep_host.cu", [], ""), ("refine.cu", [], "")]
 UNITS += [("sweep.cu", [f"-DAB_RS={r}"], f"_r{r}") for r in range(3)]
+UNITS += [("trio.cu", [f"-DAB_RS={r}"], f"_r{r}") for r in range(3)]
 UNITS += [("fused.cu", [f"-DAB_GEOM={g}"], f"_g{g}") for g in range(6)]
 UNITS += [("tasks_flux.cu", [f"-DAB_GEOM={g}"], f"_g{g}") for g in range(6)]
 

@@ -113,6 +113,7 @@ int launch_fused_stage(ab200_ctx *c, int fluid, double gam0, double gam1, double
 bool fused_folds_dt(const ab200_ctx *c);
 // single-pass stage (sweep.cuh / sweep_host.cu)
 bool sweep_eligible(ab200_ctx *c, int fluid);
+bool sweep_uses_role_split(const ab200_ctx *c, int fluid);
 int launch_sweep_stage(ab200_ctx *c, int fluid, double gam0, double gam1, double beta, double dt,
                        int pcm, int stage1_copy, int use_device_dt, unsigned long long *dt_min);
 // bring the current primitives back into the caller's arrays (no-op when already there)

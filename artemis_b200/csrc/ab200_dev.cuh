@@ -55,32 +55,37 @@ AB_D double sqr(double x) { return x * x; }
 // which is every face of a quiescent region), and 0/0 or x/0 still produce NaN/Inf-class
 // values that the callers' selects discard exactly like the reference does.
 #ifdef AB200_FAST_MATH
+// rcp.approx.ftz.f64 / rsqrt.approx.ftz.f64 (MUFU.RCP64H / MUFU.RSQ64H) are good to ~2^-22;
+// ONE cubically convergent correction (error e -> e^3 ~ 2^-66) replaces the two Newton steps
+// of round 1: 3 dependent DFMAs per reciprocal instead of 4, 5 per inverse root instead of 7.
 AB_D double drcp(double b) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-  double e = fma(-b, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-b, r, 1.0);
-  r = fma(r, e, r);
-  return r;
+  const double e = fma(-b, r, 1.0);
+  return fma(r, fma(e, e, e), r);  // r (1 + e + e^2)
 }
 AB_D double ddiv(double a, double b) {
   const double r = drcp(b);
   const double q = a * r;
   return fma(fma(-b, q, a), r, q);
 }
-// Square root of a non-negative normal number without nvcc's slow-path CALL: MUFU.RSQ64H
-// seed (2^-22) + two Goldschmidt steps (<= 1 ulp); x == 0 returns 0 like sqrt().
-AB_D double dsqrt(double x) {
+// 1/sqrt(x) for x > 0 (x == 0 gives NaN/Inf: callers guard)
+AB_D double drsqrt(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double gq = x * y, h = 0.5 * y;
-  double r = fma(-gq, h, 0.5);
-  gq = fma(gq, r, gq);
-  h = fma(h, r, h);
-  r = fma(-gq, h, 0.5);
-  gq = fma(gq, r, gq);
-  return x > 0.0 ? gq : 0.0;
+  const double e = fma(-(x * y), y, 1.0);             // 1 - x y^2
+  return fma(y, e * fma(0.375, e, 0.5), y);           // y (1 + e/2 + 3 e^2 / 8)
+}
+// Square root of a non-negative number without nvcc's slow-path CALL (<= 1.5 ulp); x == 0
+// returns 0 like sqrt().
+AB_D double dsqrt(double x) {
+  const double s = x * drsqrt(x);
+  return x > 0.0 ? s : 0.0;
+}
+// sqrt(a / b) for a >= 0, b > 0 as a * rsqrt(a b): one MUFU, no reciprocal
+AB_D double dsqrt_ratio(double a, double b) {
+  const double s = a * drsqrt(a * b);
+  return a > 0.0 ? s : 0.0;
 }
 #else
 AB_D double drcp(double b) { return 1.0 / b; }
@@ -348,15 +353,17 @@ struct Riemann<AB200_HLLC, AB200_GAS> {  // hllc.hpp:76-180
     const double dl = wl[0], vxl = wl[1], pl = wl[4];
     const double dr = wr[0], vxr = wr[1], pr = wr[4];
     const double gamma = eos.gamma, alpha = eos.alpha, igm1 = eos.igm1;
-    const double idl = drcp(dl), idr = drcp(dr);
-    const double al = dsqrt(gamma * pl * idl);
-    const double ar = dsqrt(gamma * pr * idr);
+    const double gpl = gamma * pl, gpr = gamma * pr;
+    const double al = dsqrt_ratio(gpl, dl);
+    const double ar = dsqrt_ratio(gpr, dr);
     const double el = pl * igm1 + 0.5 * dl * (sqr(vxl) + sqr(wl[2]) + sqr(wl[3]));
     const double er = pr * igm1 + 0.5 * dr * (sqr(vxr) + sqr(wr[2]) + sqr(wr[3]));
     const double rhoa = 0.25 * (dl + dr) * (al + ar);
     const double pm = 0.5 * (pl + pr + (vxl - vxr) * rhoa);
-    const double cl = (pm <= pl) ? al : dsqrt(gamma * fma(alpha, pm - pl, pl) * idl);
-    const double cr = (pm <= pr) ? ar : dsqrt(gamma * fma(alpha, pm - pr, pr) * idr);
+    // shock branches of the PVRS estimate: taken only where p* exceeds the side's pressure
+    double cl = al, cr = ar;
+    if (pm > pl) cl = dsqrt_ratio(gamma * fma(alpha, pm - pl, pl), dl);
+    if (pm > pr) cr = dsqrt_ratio(gamma * fma(alpha, pm - pr, pr), dr);
     const double sl = vxl - cl;
     const double sr = vxr + cr;
     const double bp = sr > 0.0 ? sr : 1.0e-20;
@@ -387,7 +394,7 @@ struct Riemann<AB200_HLLC, AB200_GAS> {  // hllc.hpp:76-180
     out[4] = fma(ws, fma(e, tt, p * vx), wc * am);
     const bool fpos = (frho >= 0.0);
     out[5] = frho * (fpos ? wl[5] : wr[5]);
-    out[7] = frho * (fpos ? idl : idr);
+    out[7] = frho * drcp(fpos ? dl : dr);
   }
 };
 #else
@@ -419,14 +426,8 @@ struct Riemann<AB200_HLLC, AB200_GAS> {  // hllc.hpp:76-180
     qd = wr_ipr + qf * wr_idn * wr_ivx;
     const double ml = wl_idn * qe;
     const double mr = -(wr_idn * qf);
-#ifdef AB200_FAST_MATH
-    const double rm = drcp(ml + mr);
-    const double am = (qc - qd) * rm;
-    double cp = (ml * qd + mr * qc) * rm;
-#else
     const double am = (qc - qd) / (ml + mr);
     double cp = (ml * qd + mr * qc) / (ml + mr);
-#endif
     cp = cp > 0.0 ? cp : 0.0;
     qe = wl_idn * (wl_ivx - qb);
     qf = wr_idn * (wr_ivx - qa);
@@ -436,15 +437,6 @@ struct Riemann<AB200_HLLC, AB200_GAS> {  // hllc.hpp:76-180
     const double flmz = qe * wl_ivz, frmz = qf * wr_ivz;
     const double fle = el * (wl_ivx - qb) + wl_ipr * wl_ivx;
     const double fre = er * (wr_ivx - qa) + wr_ipr * wr_ivx;
-#ifdef AB200_FAST_MATH
-    {
-      const bool pos = (am >= 0.0);
-      const double rw = drcp(pos ? (am - qb) : (qa - am));
-      qc = pos ? am * rw : 0.0;
-      qd = pos ? 0.0 : -am * rw;
-      qe = pos ? -qb * rw : qa * rw;
-    }
-#else
     if (am >= 0.0) {
       qc = am / (am - qb);
       qd = 0.0;
@@ -454,7 +446,6 @@ struct Riemann<AB200_HLLC, AB200_GAS> {  // hllc.hpp:76-180
       qd = -am / (qa - am);
       qe = qa / (qa - am);
     }
-#endif
     out[6] = qc * wl_ipr + qd * wr_ipr + qe * cp;
     const double frho = qc * fld + qd * frd;
     out[0] = frho;

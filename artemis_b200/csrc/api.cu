@@ -321,7 +321,7 @@ int ab200_bind_pack(ab200_ctx *c, const ab200_fluid_desc *fd, const ab200_pack_d
 
 int ab200_set_stage_path(ab200_ctx *c, int path) {
   AB_REQUIRE(c, AB200_EINVAL, "null context");
-  AB_REQUIRE(path >= AB200_PATH_AUTO && path <= AB200_PATH_SINGLE_PASS, AB200_EINVAL,
+  AB_REQUIRE(path >= AB200_PATH_AUTO && path <= AB200_PATH_ROLE_SPLIT, AB200_EINVAL,
              "ab200_set_stage_path: unknown path");
   // the primitives may sit in the alternate set of the single-pass kernel: bring them home
   // before the other path takes over
@@ -346,7 +346,8 @@ int ab200_get_stage_path(ab200_ctx *c, int fluid, int *path_out) {
   AB_REQUIRE(fluid == 0 || fluid == 1, AB200_EINVAL, "Fluid type not recognized!");
   AB_REQUIRE(c->fl[fluid].bound, AB200_ESTATE, "fluid pack not bound: call ab200_bind_pack");
   AB_CUDA(cudaSetDevice(c->device));
-  *path_out = sweep_eligible(c, fluid) ? AB200_PATH_SINGLE_PASS : AB200_PATH_THREE_PASS;
+  *path_out = !sweep_eligible(c, fluid) ? AB200_PATH_THREE_PASS
+              : sweep_uses_role_split(c, fluid) ? AB200_PATH_ROLE_SPLIT : AB200_PATH_SINGLE_PASS;
   return AB200_OK;
 }
 

@@ -5,9 +5,15 @@
 
 #include <cstdlib>
 
-#include "sweep.cuh"
+#include "trio.cuh"
 
 namespace ab200 {
+
+template <int RS>
+int launch_trio_rs(ab200_ctx *c, int fluid, int recon, const SweepArgs &a);
+template <> int launch_trio_rs<0>(ab200_ctx *, int, int, const SweepArgs &);
+template <> int launch_trio_rs<1>(ab200_ctx *, int, int, const SweepArgs &);
+template <> int launch_trio_rs<2>(ab200_ctx *, int, int, const SweepArgs &);
 
 template <int RS>
 int launch_sweep_rs(ab200_ctx *c, int fluid, int recon, const SweepArgs &a);
@@ -100,6 +106,14 @@ static bool sweep_preferred(const FluidDev &f) {
   return f.riemann == AB200_LLF && f.recon != AB200_PPM;
 }
 
+// Which of the two single-pass kernels runs: the warp-specialised one (trio.cuh) when asked for
+// explicitly or chosen by AUTO, the one-role plane sweep (sweep.cuh) for AB200_PATH_SINGLE_PASS.
+bool sweep_uses_role_split(const ab200_ctx *c, int fluid) {
+  (void)fluid;
+  if (c->stage_path == AB200_PATH_SINGLE_PASS) return false;
+  return true;  // AB200_PATH_ROLE_SPLIT, or AUTO once the single-pass family is chosen
+}
+
 bool sweep_eligible(ab200_ctx *c, int fluid) {
   static int env = -2;  // -1: forced off, 1: forced on, 0: no override
   if (env == -2) env = getenv("AB200_NO_SWEEP") ? -1 : (getenv("AB200_SWEEP") ? 1 : 0);
@@ -129,11 +143,20 @@ int launch_sweep_stage(ab200_ctx *c, int fluid, double gam0, double gam1, double
   a.dt_min = dt_min;
   const int recon = pcm ? AB200_PCM : fh.d.recon;
   int rc = AB200_EINVAL;
-  switch (fh.d.riemann) {
-  case AB200_HLLC: rc = launch_sweep_rs<0>(c, fluid, recon, a); break;
-  case AB200_HLLE: rc = launch_sweep_rs<1>(c, fluid, recon, a); break;
-  case AB200_LLF: rc = launch_sweep_rs<2>(c, fluid, recon, a); break;
-  default: set_error("Riemann solver not recognized!");
+  if (sweep_uses_role_split(c, fluid)) {  // warp-specialised kernel (trio.cuh)
+    switch (fh.d.riemann) {
+    case AB200_HLLC: rc = launch_trio_rs<0>(c, fluid, recon, a); break;
+    case AB200_HLLE: rc = launch_trio_rs<1>(c, fluid, recon, a); break;
+    case AB200_LLF: rc = launch_trio_rs<2>(c, fluid, recon, a); break;
+    default: set_error("Riemann solver not recognized!");
+    }
+  } else {
+    switch (fh.d.riemann) {
+    case AB200_HLLC: rc = launch_sweep_rs<0>(c, fluid, recon, a); break;
+    case AB200_HLLE: rc = launch_sweep_rs<1>(c, fluid, recon, a); break;
+    case AB200_LLF: rc = launch_sweep_rs<2>(c, fluid, recon, a); break;
+    default: set_error("Riemann solver not recognized!");
+    }
   }
   AB_TRY(rc);
   fh.prim_cur = out;  // the new primitives live in the other set now

@@ -159,15 +159,16 @@ class MeshData:
         capi.check(self.L, getattr(self.L, name)(self.ctx, *args), name)
 
     def set_stage_path(self, path: int | str):
-        """ab200_set_stage_path: 'auto' (0), 'three_pass' (1) or 'single_pass' (2)."""
-        code = {"auto": 0, "three_pass": 1, "single_pass": 2}.get(path, path)
+        """ab200_set_stage_path: 'auto' (0), 'three_pass' (1), 'single_pass' (2) or
+        'role_split' (3)."""
+        code = {"auto": 0, "three_pass": 1, "single_pass": 2, "role_split": 3}.get(path, path)
         self.call("ab200_set_stage_path", int(code))
 
     def stage_path(self, which=Fluid.gas) -> str:
-        """What ab200_fused_stage runs for a fluid: 'three_pass' or 'single_pass'."""
+        """What ab200_fused_stage runs for a fluid: 'three_pass', 'single_pass', 'role_split'."""
         out = C.c_int(0)
         self.call("ab200_get_stage_path", int(which), C.byref(out))
-        return {1: "three_pass", 2: "single_pass"}[out.value]
+        return {1: "three_pass", 2: "single_pass", 3: "role_split"}[out.value]
 
     def synchronize(self):
         self.call("ab200_synchronize")

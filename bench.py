@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--cpu-cycles", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--path", default="auto", choices=["auto", "three_pass", "single_pass"],
+    ap.add_argument("--path", default="auto", choices=["auto", "three_pass", "single_pass", "role_split"],
                     help="ab200_set_stage_path: which stage kernels run (auto = library policy)")
     return ap.parse_args()
 

@@ -170,16 +170,21 @@ int ab200_fused_stage(ab200_ctx *ctx, double gam0, double gam1, double beta, dou
  *   AB200_PATH_AUTO         the faster of the two as measured on B200 for the bound fluid's
  *                           reconstruction / Riemann solver
  *   AB200_PATH_THREE_PASS   one kernel per direction (x1, x2, x3)
- *   AB200_PATH_SINGLE_PASS  the single-pass stage kernel (requires the alternate primitive set)
- * The two paths agree to the parity bar (1e-12 per zone and cycle); in the strict build the
+ *   AB200_PATH_SINGLE_PASS  the single-pass stage kernel, one role per CTA (sweep.cuh; requires
+ *                           the alternate primitive set)
+ *   AB200_PATH_ROLE_SPLIT   the single-pass stage kernel, warp-specialised: x1 / x2 / x3+update
+ *                           warp groups pipelined over named barriers (trio.cuh; same
+ *                           requirements, same results bit for bit as SINGLE_PASS)
+ * The paths agree to the parity bar (1e-12 per zone and cycle); in the strict build the
  * single-pass kernel is bit-identical to the reference (it sums the flux divergence over the
  * three directions before the update, artemis_integrator.hpp:95-106), the directional passes
  * round once per direction. */
 #define AB200_PATH_AUTO 0
 #define AB200_PATH_THREE_PASS 1
 #define AB200_PATH_SINGLE_PASS 2
+#define AB200_PATH_ROLE_SPLIT 3
 int ab200_set_stage_path(ab200_ctx *ctx, int path);
-/* *path_out = AB200_PATH_THREE_PASS or AB200_PATH_SINGLE_PASS: what ab200_fused_stage runs for
+/* *path_out = AB200_PATH_THREE_PASS, AB200_PATH_SINGLE_PASS or AB200_PATH_ROLE_SPLIT: what ab200_fused_stage runs for
  * `fluid` on the bound mesh under the current setting (resolves AUTO and eligibility). */
 int ab200_get_stage_path(ab200_ctx *ctx, int fluid, int *path_out);
 /* Copies the current primitives (interior and ghosts) into the caller's arrays if a

@@ -32,7 +32,7 @@ pytestmark = pytest.mark.gpu
 TOL_1 = 1e-12
 TOL_100 = 1e-9
 BIG = float(np.finfo(np.float64).max)
-PATHS = ["three_pass", "single_pass"]
+PATHS = ["three_pass", "single_pass", "role_split"]
 
 with open(os.path.join(os.path.dirname(__file__), "golden", "reference_linwave.json")) as fh:
     GOLDEN = json.load(fh)
@@ -110,9 +110,10 @@ def test_config2_blast_64cubed_blocks_hundred_cycles(blast_oracle, path):
     assert eu <= TOL_100 and ep <= TOL_100, (path, eu, ep)
 
 
-def test_config2_blast_64cubed_blocks_single_pass_strict_bit_identical(blast_oracle):
+@pytest.mark.parametrize("path", ["single_pass", "role_split"])
+def test_config2_blast_64cubed_blocks_single_pass_strict_bit_identical(blast_oracle, path):
     mesh, gp, prim, snaps = blast_oracle
-    u0, w, _ = _blast_gpu(mesh, gp, prim, "single_pass", "strict", 2, device_resident=True)
+    u0, w, _ = _blast_gpu(mesh, gp, prim, path, "strict", 2, device_resident=True)
     assert np.array_equal(u0, snaps[2][0])
     assert np.array_equal(w, snaps[2][1])
 

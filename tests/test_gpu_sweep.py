@@ -22,10 +22,15 @@ def _mesh(nx, bnx, bcs=None, ng=4):
                        nghost=ng, bcs=tuple(bcs or (BoundaryFlag.periodic,) * 6), coords=C)
 
 
-def _twin(mesh, gp, dp, variant, integ, ncyc, device_resident=False, seed=5, shocks=True):
+SINGLE_PASS_KERNELS = ["single_pass", "role_split"]   # sweep.cuh | trio.cuh
+
+
+def _twin(mesh, gp, dp, variant, integ, ncyc, device_resident=False, seed=5, shocks=True,
+          path="single_pass"):
     osim = OracleSim(mesh, gas=gp, dust=dp, integrator=integ)
     md = MeshData(mesh, gas=gp, dust=dp, variant=variant, materialize_fluxes=False)
-    md.set_stage_path("single_pass")
+    md.set_stage_path(path)
+    assert md.stage_path() == path
     for which, fp in ((Fluid.gas, gp), (Fluid.dust, dp)):
         if fp is None:
             continue
@@ -50,25 +55,27 @@ def _twin(mesh, gp, dp, variant, integ, ncyc, device_resident=False, seed=5, sho
     return res, launches
 
 
+@pytest.mark.parametrize("path", SINGLE_PASS_KERNELS)
 @pytest.mark.parametrize("rs", ["hllc", "hlle", "llf"])
 @pytest.mark.parametrize("recon,integ", [("ppm", "rk2"), ("plm", "vl2"), ("ppm", "rk3"),
                                          ("plm", "rk1")])
-def test_sweep_strict_is_bit_identical_to_oracle(recon, integ, rs):
+def test_sweep_strict_is_bit_identical_to_oracle(recon, integ, rs, path):
     """The single-pass kernel sums the three flux differences and applies the sources in the
     reference's own order, so the strict build reproduces the oracle bit for bit.  32^3 blocks
     hold 2x2 tiles each (tile-to-tile halos inside a block); 2 gas + 2 dust species."""
     mesh = _mesh((64, 32, 32), (32, 32, 32))
     gp = gas_params(C, recon, rs, S=2)
     dp = dust_params(C, recon, "llf" if rs == "llf" else "hlle", S=2)
-    res, _ = _twin(mesh, gp, dp, "strict", integ, 2)
+    res, _ = _twin(mesh, gp, dp, "strict", integ, 2, path=path)
     for u0, prim, ou0, oprim, _ in res:
         assert np.array_equal(u0, ou0)
         assert np.array_equal(prim, oprim)
 
 
+@pytest.mark.parametrize("path", SINGLE_PASS_KERNELS)
 @pytest.mark.parametrize("bnx", [(16, 16, 16), (8, 6, 4), (32, 16, 8), (24, 20, 12)])
 @pytest.mark.parametrize("bc", ["periodic", "outflow", "reflect"])
-def test_sweep_fast_within_1e12_one_cycle(bnx, bc):
+def test_sweep_fast_within_1e12_one_cycle(bnx, bc, path):
     """Default (FMA, fast division) build, full and ragged tiles, every boundary kind."""
     B = BoundaryFlag
     bcs = {"periodic": (B.periodic,) * 6, "outflow": (B.outflow,) * 6,
@@ -76,19 +83,20 @@ def test_sweep_fast_within_1e12_one_cycle(bnx, bc):
     mesh = _mesh(tuple(2 * b for b in bnx), bnx, bcs)
     gp = gas_params(C, "ppm", "hllc")
     dp = dust_params(C, "plm", "hlle", S=2)
-    res, _ = _twin(mesh, gp, dp, "fast", "rk2", 1)
+    res, _ = _twin(mesh, gp, dp, "fast", "rk2", 1, path=path)
     for u0, prim, ou0, oprim, fp in res:
         assert zone_rel_err(u0, ou0, fp, "cons") <= 1e-12
         assert zone_rel_err(prim, oprim, fp, "prim") <= 1e-12
 
 
+@pytest.mark.parametrize("path", SINGLE_PASS_KERNELS)
 @pytest.mark.parametrize("integ", ["rk1", "rk2", "vl2", "rk3"])
-def test_sweep_device_resident_pingpong_matches_oracle(integ):
+def test_sweep_device_resident_pingpong_matches_oracle(integ, path):
     """ab200_run_cycles leaves the primitives in the alternate set between stages (no copy
     back); after 3 cycles (odd and even stage counts) the caller's arrays hold the result."""
     mesh = _mesh((32, 32, 32), (16, 16, 16), (BoundaryFlag.outflow,) * 6)
     gp = gas_params(C, "ppm", "hllc")
-    res, launches = _twin(mesh, gp, None, "strict", integ, 3, device_resident=True)
+    res, launches = _twin(mesh, gp, None, "strict", integ, 3, device_resident=True, path=path)
     for u0, prim, ou0, oprim, _ in res:
         assert np.array_equal(u0, ou0)
         assert np.array_equal(prim, oprim)
