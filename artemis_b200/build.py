@@ -25,7 +25,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 # (source, extra defines, object suffix)
 UNITS = [("api.cu", [], ""), ("tasks.cu", [], ""), ("halo.cu", [], ""),
          ("fused_dispatch.cu", [], ""), ("host_path.cu", [], ""), ("tma_maps.cu", [], "")]
-UNITS += [("sweep_host.cu", [], ""), ("refine.cu", [], "")]
+UNITS += [("sweep_host.cu", [], ""), ("refine.cu", [], ""), ("comm.cu", [], "")]
 UNITS += [("sweep.cu", [f"-DAB_RS={r}"], f"_r{r}") for r in range(3)]
 UNITS += [("trio.cu", [f"-DAB_RS={r}"], f"_r{r}") for r in range(3)]
 UNITS += [("fused.cu", [f"-DAB_GEOM={g}"], f"_g{g}") for g in range(6)]
@@ -96,7 +96,7 @@ def build_variant(variant: str, flags, verbose=False, jobs=None):
             if err.strip():
                 print(err, file=sys.stderr)
     objs = [o for o, _ in res]
-    cmd = [NVCC, *ARCH, "-shared", "-o", out, *objs, "-lcudart"]
+    cmd = [NVCC, *ARCH, "-shared", "-o", out, *objs, "-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -51,7 +51,8 @@ SYMBOLS = [
     "ab200_set_rotating_frame", "ab200_set_stage_path", "ab200_get_stage_path", "ab200_calculate_fluxes", "ab200_apply_update",
     "ab200_flux_source", "ab200_set_auxillary_fields", "ab200_cons_to_prim",
     "ab200_prim_to_cons", "ab200_deep_copy_conserved", "ab200_estimate_timestep",
-    "ab200_fused_stage", "ab200_sync_prim", "ab200_prim_to_cons_ghosts", "ab200_estimate_timestep_device",
+    "ab200_fused_stage", "ab200_sync_prim", "ab200_prim_to_cons_ghosts", "ab200_set_ghost_cons_lazy",
+    "ab200_sync_ghost_cons", "ab200_estimate_timestep_device",
     "ab200_set_global_timestep_device", "ab200_dt_device", "ab200_read_time_state",
     "ab200_write_time_state", "ab200_halo_pack", "ab200_halo_unpack", "ab200_set_halo_stream", "ab200_coarse_shape", "ab200_restrict", "ab200_prolongate",
     "ab200_set_topology",
@@ -59,6 +60,9 @@ SYMBOLS = [
     "ab200_fill_ghosts_local", "ab200_finish_remote_ghosts", "ab200_cycles_host",
     "ab200_run_cycles", "ab200_malloc", "ab200_free", "ab200_memcpy_h2d", "ab200_memcpy_d2h",
     "ab200_launch_count", "ab200_timer_begin", "ab200_timer_end",
+    "ab200_comm_unique_id", "ab200_comm_init", "ab200_comm_destroy", "ab200_comm_set_layout",
+    "ab200_comm_bytes_per_exchange", "ab200_comm_exchange_begin", "ab200_comm_exchange_end",
+    "ab200_allreduce_min", "ab200_run_cycles_mr", "ab200_comm_plan_direct", "ab200_comm_plan_free",
 ]
 
 _libs: dict[str, C.CDLL] = {}
@@ -84,6 +88,10 @@ def load(variant: str | None = None) -> C.CDLL:
     L.ab200_dt_device.argtypes = [C.c_void_p]
     L.ab200_launch_count.restype = C.c_longlong
     L.ab200_launch_count.argtypes = [C.c_void_p]
+    L.ab200_comm_bytes_per_exchange.restype = C.c_longlong
+    L.ab200_comm_bytes_per_exchange.argtypes = [C.c_void_p]
+    L.ab200_comm_plan_free.restype = None
+    L.ab200_comm_plan_free.argtypes = [C.POINTER(C.c_longlong)]
     vp, i, d = C.c_void_p, C.c_int, C.c_double
     sig = {
         "ab200_create": [C.POINTER(vp), i, vp], "ab200_destroy": [vp], "ab200_synchronize": [vp],
@@ -96,6 +104,7 @@ def load(variant: str | None = None) -> C.CDLL:
         "ab200_cons_to_prim": [vp], "ab200_prim_to_cons": [vp],
         "ab200_deep_copy_conserved": [vp], "ab200_estimate_timestep": [vp, i, _DP],
         "ab200_fused_stage": [vp, d, d, d, d, i, i, i], "ab200_prim_to_cons_ghosts": [vp], "ab200_sync_prim": [vp],
+        "ab200_set_ghost_cons_lazy": [vp, i], "ab200_sync_ghost_cons": [vp],
         "ab200_estimate_timestep_device": [vp],
         "ab200_set_global_timestep_device": [vp, d, i],
         "ab200_read_time_state": [vp, _DP], "ab200_write_time_state": [vp, _DP],
@@ -114,6 +123,12 @@ def load(variant: str | None = None) -> C.CDLL:
         "ab200_malloc": [vp, C.POINTER(vp), C.c_size_t], "ab200_free": [vp, vp],
         "ab200_memcpy_h2d": [vp, vp, vp, C.c_size_t], "ab200_memcpy_d2h": [vp, vp, vp, C.c_size_t],
         "ab200_timer_begin": [vp], "ab200_timer_end": [vp, C.POINTER(C.c_float)],
+        "ab200_comm_unique_id": [C.c_char_p], "ab200_comm_init": [vp, i, i, C.c_char_p],
+        "ab200_comm_destroy": [vp], "ab200_comm_set_layout": [vp, i, i, i, C.POINTER(C.c_int)],
+        "ab200_comm_exchange_begin": [vp], "ab200_comm_exchange_end": [vp],
+        "ab200_allreduce_min": [vp, vp], "ab200_run_cycles_mr": [vp, i, i, d],
+        "ab200_comm_plan_direct": [C.POINTER(C.c_int)] * 5 + [i] + [C.POINTER(C.c_int)] * 5 +
+                                  [C.POINTER(C.POINTER(C.c_longlong)), C.POINTER(C.c_int)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

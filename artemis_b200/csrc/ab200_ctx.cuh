@@ -50,6 +50,8 @@ struct FluidHost {
   double *const *prim_tab[2] = {nullptr, nullptr};
   void *sw_maps[2] = {nullptr, nullptr};  // CUtensorMap[nb*nvar] per set, box {PI, PJ, 1}
   int prim_cur = 0;
+  // lazy ghost cons (ab200_set_ghost_cons_lazy): the ghost fills wrote primitives only
+  bool ghost_cons_stale = false;
 };
 int ensure_tma(ab200_ctx *c, int fluid, int max_threads);
 void release_tma(FluidHost &fh);
@@ -79,6 +81,7 @@ struct ab200_ctx {
   ab200::Topology topo;
   double omf = 0.0;
   int stage_path = 0;  // AB200_PATH_*
+  bool ghost_cons_lazy = false;  // ghost fills skip PrimToCons until ab200_sync_ghost_cons
   double *d_time = nullptr;     // device double[4]: dt, new_dt, time, ncycle
   double *d_red = nullptr;      // reduction scratch
   double *h_pinned = nullptr;   // pinned host scratch (8 doubles)
@@ -95,6 +98,8 @@ struct ab200_ctx {
     void *dev = nullptr;
   };
   std::vector<HaloCacheEntry> halo_cache;
+  // multi-rank transport (comm.cu): NCCL communicator, comm stream, planned exchange
+  void *comm_state = nullptr;
 };
 
 namespace ab200 {

@@ -186,6 +186,7 @@ int ab200_destroy(ab200_ctx *c) {
   if (!c) return AB200_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  ab200_comm_destroy(c);
   for (int f = 0; f < 2; ++f) ab200_unbind(c, f);
   free_all(c->grid_allocs);
   free_all(c->host_path_allocs);
@@ -429,7 +430,26 @@ int ab200_prim_to_cons(ab200_ctx *c) {
 int ab200_prim_to_cons_ghosts(ab200_ctx *c) {
   AB_ENTER(c)
   for (int f = 0; f < 2; ++f)
-    if (c->fl[f].bound) AB_TRY(launch_prim_to_cons(c, f, 1));
+    if (c->fl[f].bound) {
+      AB_TRY(launch_prim_to_cons(c, f, 1));
+      c->fl[f].ghost_cons_stale = false;
+    }
+  return AB200_OK;
+}
+
+int ab200_set_ghost_cons_lazy(ab200_ctx *c, int lazy) {
+  AB_REQUIRE(c, AB200_EINVAL, "null context");
+  c->ghost_cons_lazy = lazy != 0;
+  return AB200_OK;
+}
+
+int ab200_sync_ghost_cons(ab200_ctx *c) {
+  AB_ENTER(c)
+  for (int f = 0; f < 2; ++f)
+    if (c->fl[f].bound && c->fl[f].ghost_cons_stale) {
+      AB_TRY(launch_prim_to_cons(c, f, 1));
+      c->fl[f].ghost_cons_stale = false;
+    }
   return AB200_OK;
 }
 

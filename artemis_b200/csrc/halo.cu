@@ -76,7 +76,10 @@ int launch_exchange(ab200_ctx *c, int fluid) {
 // normal velocity under each reflection).  Sources are interior cells only, which this kernel
 // never writes, so there is no ordering hazard.
 // ----------------------------------------------------------------------------------------
-template <int GEOM, int FLUID>
+// CONS = false ("lazy ghost cons", ab200_set_ghost_cons_lazy): only the primitives are written.
+// The fused stage kernels never read conserved ghost zones, so the device-resident cycle
+// converts them once, when the caller next needs them, instead of after every stage.
+template <int GEOM, int FLUID, bool CONS>
 __global__ void __launch_bounds__(kThreads)
 k_fill_ghosts(GridDev g, FluidDev f, int nbx, int nby, int nbz, int bc0, int bc1, int bc2,
               int bc3, int bc4, int bc5, int remote_pass) {
@@ -165,21 +168,23 @@ k_fill_ghosts(GridDev g, FluidDev f, int nbx, int nby, int nbz, int bc0, int bc1
     // ... then PrimToCons on the ghost cell (fill_derived.cpp:217-274)
     w_d = (w_d > f.dfloor) ? w_d : f.dfloor;
     f.prim[ed + n][doff] = w_d;
-    f.u0[ed + n][doff] = w_d;
+    if (CONS) f.u0[ed + n][doff] = w_d;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       f.prim[ed + S + 3 * n + d][doff] = vel[d];
-      f.u0[ed + S + 3 * n + d][doff] = w_d * vel[d] * hx[d];
+      if (CONS) f.u0[ed + S + 3 * n + d][doff] = w_d * vel[d] * hx[d];
     }
     if (gas) {
       double w_s = f.prim[es + 5 * S + n][soff];
       w_s = (w_s > f.siefloor) ? w_s : f.siefloor;
       f.prim[ed + 5 * S + n][doff] = w_s;
-      const double u_u = w_s * w_d;
-      f.u0[ed + 5 * S + n][doff] = u_u;
       f.prim[ed + 4 * S + n][doff] = dmax(0.0, f.gm1 * w_d * w_s);
-      const double ke = 0.5 * w_d * (sqr(vel[0]) + sqr(vel[1]) + sqr(vel[2]));
-      f.u0[ed + 4 * S + n][doff] = u_u + ke;
+      if (CONS) {
+        const double u_u = w_s * w_d;
+        f.u0[ed + 5 * S + n][doff] = u_u;
+        const double ke = 0.5 * w_d * (sqr(vel[0]) + sqr(vel[1]) + sqr(vel[2]));
+        f.u0[ed + 4 * S + n][doff] = u_u + ke;
+      }
     }
   }
 }
@@ -206,22 +211,28 @@ bool topology_is_local(const ab200_ctx *c) {
 
 int launch_fill_ghosts(ab200_ctx *c, int fluid, int remote_pass) {
   const GridDev &g = c->g;
-  const FluidHost &fh = c->fl[fluid];
+  FluidHost &fh = c->fl[fluid];
   const Topology &tp = c->topo;
   const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
   const long long nghost = (long long)g.ni * g.nj * g.nk - (long long)nir * njr * nkr;
   if (nghost <= 0) return AB200_OK;
   dim3 grid((unsigned)((nghost + kThreads - 1) / kThreads), (unsigned)g.nb);
+  const bool lazy = c->ghost_cons_lazy;
   int rc = dispatch_geom_h(g.geom, [&](auto G) {
     constexpr int GG = decltype(G)::value;
-    if (fluid == AB200_GAS)
-      k_fill_ghosts<GG, AB200_GAS><<<grid, kThreads, 0, c->stream>>>(
-          g, fh.d, tp.nbx, tp.nby, tp.nbz, tp.bc[0], tp.bc[1], tp.bc[2], tp.bc[3], tp.bc[4], tp.bc[5], remote_pass);
-    else
-      k_fill_ghosts<GG, AB200_DUST><<<grid, kThreads, 0, c->stream>>>(
-          g, fh.d, tp.nbx, tp.nby, tp.nbz, tp.bc[0], tp.bc[1], tp.bc[2], tp.bc[3], tp.bc[4], tp.bc[5], remote_pass);
+#define AB_FILL(FL, CONS)                                                                      \
+  k_fill_ghosts<GG, FL, CONS><<<grid, kThreads, 0, c->stream>>>(                               \
+      g, fh.d, tp.nbx, tp.nby, tp.nbz, tp.bc[0], tp.bc[1], tp.bc[2], tp.bc[3], tp.bc[4],      \
+      tp.bc[5], remote_pass)
+    if (fluid == AB200_GAS) {
+      if (lazy) AB_FILL(AB200_GAS, false); else AB_FILL(AB200_GAS, true);
+    } else {
+      if (lazy) AB_FILL(AB200_DUST, false); else AB_FILL(AB200_DUST, true);
+    }
+#undef AB_FILL
     return AB200_OK;
   });
+  if (lazy) fh.ghost_cons_stale = true;
   c->launches++;
   AB_CUDA(cudaGetLastError());
   return rc;

@@ -30,6 +30,15 @@ extern "C" int ab200_run_cycles(ab200_ctx *c, int integrator, int ncycles, doubl
   // the loop stops once time >= tlim, which costs one 32-byte read-back per cycle; with
   // tlim = DBL_MAX the cycles are queued without any host round trip
   const bool finite_tlim = tlim < 1.0e300;
+  // the fused stages never read conserved ghost zones: inside the loop the ghost fills write
+  // primitives only; PrimToCons on the ghosts (ghost part of fill_derived.cpp:217-274) runs once
+  // after the last cycle so the caller's arrays are complete again
+  const bool lazy_before = c->ghost_cons_lazy;
+  c->ghost_cons_lazy = true;
+  struct Restore {
+    ab200_ctx *c; bool v;
+    ~Restore() { c->ghost_cons_lazy = v; }
+  } restore{c, lazy_before};
   const Stage *st = integrator == 0 ? kRK1 : integrator == 1 ? kRK2 : integrator == 2 ? kVL2 : kRK3;
   const int nst = integrator == 0 ? 1 : integrator == 3 ? 3 : 2;
   for (int cyc = 0; cyc < ncycles; ++cyc) {
@@ -49,6 +58,7 @@ extern "C" int ab200_run_cycles(ab200_ctx *c, int integrator, int ncycles, doubl
   }
   // odd number of single-pass stages in total (rk1 / rk3): primitives back to the caller
   AB_TRY(ab200_sync_prim(c));
+  if (!lazy_before) AB_TRY(ab200_sync_ghost_cons(c));
   return AB200_OK;
 }
 

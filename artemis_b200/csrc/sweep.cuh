@@ -400,33 +400,31 @@ k_sweep_stage(GridDev g, FluidDev f, SweepArgs a) {
 #endif
     if (is_main) {
       if (INP) {
-        {  // x1, face ci: recon order == pack order
-          double wl[NV], out[8];
+        // x1 (face ci, recon order == pack order) and x2 (face cj, recon order rho, v2, v3, v1,
+        // P, sie): both left states are loaded first and both results stored last, so the two
+        // independent solves form one straight-line block the scheduler can interleave
+        double wlx[NV], wly[NV], wry[NV], ox_[8], oy_[8];
+        const int o = cj * TI + ci;
 #pragma unroll
-          for (int v = 0; v < NV; ++v) wl[v] = sm[SM::qlx + v * SM::qlx_vs + cj * (TI + 1) + ci];
-          Riemann<RS, FLUID>::solve(eos, wl, qrx, out);
-#pragma unroll
-          for (int m = 0; m < NF; ++m) sm[SM::fx + m * SM::fx_vs + cj * (TI + 1) + ci] = out[m];
+        for (int v = 0; v < NV; ++v) wlx[v] = sm[SM::qlx + v * SM::qlx_vs + cj * (TI + 1) + ci];
+        wly[0] = sm[SM::qly + 0 * SM::qly_vs + o]; wly[1] = sm[SM::qly + 2 * SM::qly_vs + o];
+        wly[2] = sm[SM::qly + 3 * SM::qly_vs + o]; wly[3] = sm[SM::qly + 1 * SM::qly_vs + o];
+        wry[0] = qry[0]; wry[1] = qry[2]; wry[2] = qry[3]; wry[3] = qry[1];
+        if (gas) {
+          wly[4] = sm[SM::qly + 4 * SM::qly_vs + o]; wly[5] = sm[SM::qly + 5 * SM::qly_vs + o];
+          wry[4] = qry[4]; wry[5] = qry[5];
         }
-        {  // x2, face cj: recon order (rho, v2, v3, v1, P, sie)
-          double wl[NV], wr[NV], out[8];
-          const int o = cj * TI + ci;
-          wl[0] = sm[SM::qly + 0 * SM::qly_vs + o]; wl[1] = sm[SM::qly + 2 * SM::qly_vs + o];
-          wl[2] = sm[SM::qly + 3 * SM::qly_vs + o]; wl[3] = sm[SM::qly + 1 * SM::qly_vs + o];
-          wr[0] = qry[0]; wr[1] = qry[2]; wr[2] = qry[3]; wr[3] = qry[1];
-          if (gas) {
-            wl[4] = sm[SM::qly + 4 * SM::qly_vs + o]; wl[5] = sm[SM::qly + 5 * SM::qly_vs + o];
-            wr[4] = qry[4]; wr[5] = qry[5];
-          }
-          Riemann<RS, FLUID>::solve(eos, wl, wr, out);
-          sm[SM::fy + 0 * SM::fy_vs + o] = out[0];
-          sm[SM::fy + 2 * SM::fy_vs + o] = out[1];
-          sm[SM::fy + 3 * SM::fy_vs + o] = out[2];
-          sm[SM::fy + 1 * SM::fy_vs + o] = out[3];
-          if (gas) {
+        Riemann<RS, FLUID>::solve(eos, wlx, qrx, ox_);
+        Riemann<RS, FLUID>::solve(eos, wly, wry, oy_);
 #pragma unroll
-            for (int m = 4; m < 8; ++m) sm[SM::fy + m * SM::fy_vs + o] = out[m];
-          }
+        for (int m = 0; m < NF; ++m) sm[SM::fx + m * SM::fx_vs + cj * (TI + 1) + ci] = ox_[m];
+        sm[SM::fy + 0 * SM::fy_vs + o] = oy_[0];
+        sm[SM::fy + 2 * SM::fy_vs + o] = oy_[1];
+        sm[SM::fy + 3 * SM::fy_vs + o] = oy_[2];
+        sm[SM::fy + 1 * SM::fy_vs + o] = oy_[3];
+        if (gas) {
+#pragma unroll
+          for (int m = 4; m < 8; ++m) sm[SM::fy + m * SM::fy_vs + o] = oy_[m];
         }
       }
     } else if (INP) {

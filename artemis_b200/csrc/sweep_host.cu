@@ -110,8 +110,10 @@ static bool sweep_preferred(const FluidDev &f) {
 // explicitly or chosen by AUTO, the one-role plane sweep (sweep.cuh) for AB200_PATH_SINGLE_PASS.
 bool sweep_uses_role_split(const ab200_ctx *c, int fluid) {
   (void)fluid;
-  if (c->stage_path == AB200_PATH_SINGLE_PASS) return false;
-  return true;  // AB200_PATH_ROLE_SPLIT, or AUTO once the single-pass family is chosen
+  // AUTO keeps the one-role kernel where it picks the single-pass family (LLF with PCM / PLM):
+  // measured on B200 (r02) the warp-specialised kernel's x3+update group is the critical path
+  // and the other two groups idle ~60 % of the time at the hand-over barriers
+  return c->stage_path == AB200_PATH_ROLE_SPLIT;
 }
 
 bool sweep_eligible(ab200_ctx *c, int fluid) {

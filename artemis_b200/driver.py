@@ -219,6 +219,8 @@ class ArtemisDriver:
     # ---- device-resident cycle (fused path; dt, time and ncycle live on the device) ----------
     def BeginDeviceResident(self):
         self.md.set_time_state(self.dt, 0.0, self.time, self.ncycle)
+        # conserved ghost zones are dead between fused stages: convert them once at the end
+        self.md.call("ab200_set_ghost_cons_lazy", 1)
 
     def StepDevice(self, tlim: float = _BIG):
         """One cycle with no host round trip: per stage ab200_fused_stage (dt read from the
@@ -248,6 +250,8 @@ class ArtemisDriver:
         md.call("ab200_sync_prim")  # no-op after an even number of single-pass stages
 
     def EndDeviceResident(self):
+        self.md.call("ab200_set_ghost_cons_lazy", 0)
+        self.md.call("ab200_sync_ghost_cons")
         ts = self.md.time_state()
         self.dt, self.time, self.ncycle = float(ts[0]), float(ts[2]), int(ts[3])
 

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AB200_ABI_VERSION 6
+#define AB200_ABI_VERSION 7
 
 /* src/artemis.hpp:78-105 */
 enum { AB200_CARTESIAN = 0, AB200_CYLINDRICAL = 1, AB200_SPHERICAL1D = 2,
@@ -193,6 +193,14 @@ int ab200_get_stage_path(ab200_ctx *ctx, int fluid, int *path_out);
 int ab200_sync_prim(ab200_ctx *ctx);
 /* PrimToCons restricted to ghost zones (completes :261 after the exchange). */
 int ab200_prim_to_cons_ghosts(ab200_ctx *ctx);
+/* Lazy conserved ghost zones.  The fused stage kernels read conserved variables of interior
+ * zones only, so between stages the ghost part of PrimToCons (fill_derived.cpp:217-274 over
+ * the ENTIRE domain) is dead work.  With lazy != 0, ab200_fill_ghosts / _local /
+ * ab200_finish_remote_ghosts write the ghost primitives only and mark the conserved ghost zones
+ * stale; ab200_sync_ghost_cons converts them once (no-op when nothing is stale).
+ * ab200_run_cycles and ab200_cycles_host do this internally and return complete arrays. */
+int ab200_set_ghost_cons_lazy(ab200_ctx *ctx, int lazy);
+int ab200_sync_ghost_cons(ab200_ctx *ctx);
 
 /* ---- multilevel ghost exchange operators (config 5: static / adaptive refinement) ---------
  * Replace the stencils Parthenon's refinement::Restrict / Prolongate apply over the index
@@ -282,6 +290,48 @@ int ab200_cycles_host(ab200_ctx *ctx, int integrator, int ncycles, double *dt_io
  * ArtemisDriver::Step (src/artemis_driver.cpp:101-121) for a single-rank uniform mesh with
  * no host round trip.  State must already be bound; dt/time live in ab200_dt_device(). */
 int ab200_run_cycles(ab200_ctx *ctx, int integrator, int ncycles, double tlim);
+
+/* ---- multi-rank transport (one process per GPU; NCCL over NVLink / NVSwitch) ----------------
+ * Replaces, for blocks whose neighbour lives on another rank, the MPI path of
+ * parthenon::SendBoundBufs / ReceiveBoundBufs / SetBounds
+ * (P:bvals/comms/boundary_communication.cpp:48-334, CommBuffer::Send / TryReceive
+ * P:utils/communication_buffer.hpp:209-420: one MPI_Isend per (block, neighbour, variable), polled
+ * with MPI_Iprobe / MPI_Test) and the MPI_Allreduce(MIN) of EvolutionDriver::SetGlobalTimeStep
+ * (P:driver/driver.cpp:237).  NCCL is bound at run time (dlopen): single-rank hosts never load it.
+ *
+ *   rank 0: ab200_comm_unique_id(id)  -> host broadcasts the 128 bytes (MPI_Bcast in Parthenon)
+ *   every rank: ab200_comm_init(ctx, nranks, rank, id)            ncclCommInitRank on ctx's device
+ *               ab200_comm_set_layout(ctx, lx, ly, lz, periodic)  rank lattice of the block-spatial
+ *                   partition (rank = x + lx*(y + ly*z)); plans the SINGLE-ROUND exchange -- one
+ *                   aggregated message per peer rank (faces, rank edges and corner at once) --
+ *                   for the bound fluids.  Faces towards other ranks carry AB200_BC_NONE in
+ *                   ab200_set_topology.
+ *   per stage:  ab200_fused_stage -> ab200_comm_exchange_begin (pack / grouped ncclSend+ncclRecv /
+ *               unpack on a library-owned stream, ordered after the stage by an event)
+ *               -> ab200_fill_ghosts_local (concurrently) -> ab200_comm_exchange_end
+ *               -> ab200_finish_remote_ghosts
+ *   per cycle:  ab200_allreduce_min(ctx, ab200_dt_device(ctx) + 1) -> ab200_set_global_timestep_device
+ * ab200_run_cycles_mr is that loop (the multi-rank twin of ab200_run_cycles). */
+int ab200_comm_unique_id(char *id128);
+int ab200_comm_init(ab200_ctx *ctx, int nranks, int rank, const char *id128);
+int ab200_comm_destroy(ab200_ctx *ctx);
+int ab200_comm_set_layout(ab200_ctx *ctx, int layx, int layy, int layz, const int *periodic3);
+long long ab200_comm_bytes_per_exchange(ab200_ctx *ctx);
+int ab200_comm_exchange_begin(ab200_ctx *ctx);
+int ab200_comm_exchange_end(ab200_ctx *ctx);
+/* in-place MIN all-reduce of one DEVICE double on the context's stream; identity without a
+ * communicator */
+int ab200_allreduce_min(ab200_ctx *ctx, double *dev_scalar);
+int ab200_run_cycles_mr(ab200_ctx *ctx, int integrator, int ncycles, double tlim);
+/* The exchange planner on its own (no context, no GPU): rows of 13 values (peer, is_recv, fluid,
+ * block, var0, ncomp, si, ei, sj, ej, sk, ek, offset-in-message) for the rank at lattice position
+ * rl3 of lay3; index ranges are the same-level branch of CalcIndices
+ * (P:bvals/comms/bnd_info.cpp:152-213).  *rows_out is malloc'd: free with ab200_comm_plan_free. */
+int ab200_comm_plan_direct(const int *nblk3, const int *nt3, const int *s3, const int *e3,
+                           const int *ng3, int nfluids, const int *fluid_type,
+                           const int *nspecies, const int *lay3, const int *rl3,
+                           const int *periodic3, long long **rows_out, int *nrows_out);
+void ab200_comm_plan_free(long long *rows);
 
 /* ---- utilities ---------------------------------------------------------------------------- */
 int ab200_malloc(ab200_ctx *ctx, void **dptr, size_t bytes);

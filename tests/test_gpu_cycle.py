@@ -227,3 +227,38 @@ def test_fill_ghosts_refuses_remote_faces():
     with pytest.raises(capi.AB200Error, match="AB200_BC_NONE"):
         md.call("ab200_fill_ghosts")
     md.close()
+
+
+@pytest.mark.parametrize("variant", ["strict", "fast"])
+def test_lazy_ghost_cons_equals_eager(variant):
+    """ab200_set_ghost_cons_lazy: the ghost fills write primitives only; after
+    ab200_sync_ghost_cons the arrays are bit for bit those of the eager path (the reference's
+    PrimToCons over the entire domain after every exchange, fill_derived.cpp:217-274)."""
+    B = BoundaryFlag
+    bcs = (B.reflect, B.outflow, B.periodic, B.periodic, B.outflow, B.reflect)
+    mesh = make_mesh(Coordinates.cartesian, 3, bcs=bcs)
+    gp = gas_params(Coordinates.cartesian, "ppm", "hllc")
+    dp = dust_params(Coordinates.cartesian, "plm", "hlle", S=2)
+    out = []
+    for lazy in (0, 1):
+        md = MeshData(mesh, gas=gp, dust=dp, variant=variant, materialize_fluxes=False)
+        md.gas.prim.set(random_prim(mesh, gp, seed=31))
+        md.dust.prim.set(random_prim(mesh, dp, seed=32))
+        drv = ArtemisDriver(md, "rk2", mode="fused")
+        drv.Initialize()
+        md.set_time_state(drv.dt)
+        md.call("ab200_set_ghost_cons_lazy", lazy)
+        for stage, (g0, g1, b) in enumerate(((0.0, 1.0, 1.0), (0.5, 0.5, 0.5))):
+            md.call("ab200_fused_stage", g0, g1, b, 0.0, 0, int(stage == 0), 1 | 4)
+            md.call("ab200_fill_ghosts")
+        md.call("ab200_sync_prim")
+        if lazy:
+            stale = md.gas.u0.get()
+            md.call("ab200_sync_ghost_cons")
+            assert not np.array_equal(stale, md.gas.u0.get())   # ghosts really were skipped
+            md.call("ab200_sync_ghost_cons")                     # idempotent no-op
+        out.append([(f.u0.get(), f.prim.get()) for f in md.fluids])
+        md.close()
+    for (u_e, p_e), (u_l, p_l) in zip(*out):
+        assert np.array_equal(u_e, u_l)
+        assert np.array_equal(p_e, p_l)
