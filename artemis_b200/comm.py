@@ -422,3 +422,75 @@ class HaloComm:
 
     def allreduce_min_device(self):
         self.backend.allreduce_min_device(self.dist)
+
+
+# ---------------------------------------------------------------------------------------------
+# C-ABI transport (csrc/comm.cu): the planner, the NCCL communicator, the comm stream and the
+# dt all-reduce live in libartemis_b200; Python only bootstraps the communicator (the 128-byte
+# NCCL unique id travels over whatever the host already has -- torch.distributed here,
+# MPI_Bcast in Parthenon).
+# ---------------------------------------------------------------------------------------------
+def c_plan_direct(L, mesh, fluids, lay, rl, periodic=(False, False, False)):
+    """ab200_comm_plan_direct as [PeerPlan] (same structure as plan_direct, for the tests)."""
+    I3 = C.c_int * 3
+    nfl = len(fluids)
+    rows = C.POINTER(C.c_longlong)()
+    n = C.c_int(0)
+    capi.check(L, L.ab200_comm_plan_direct(
+        I3(*mesh.lattice_n), I3(mesh.ni, mesh.nj, mesh.nk), I3(mesh.is_, mesh.js, mesh.ks),
+        I3(mesh.ie, mesh.je, mesh.ke), I3(*mesh.ngd), nfl,
+        (C.c_int * max(nfl, 1))(*[int(f) for f, _ in fluids]),
+        (C.c_int * max(nfl, 1))(*[int(s) for _, s in fluids]), I3(*lay), I3(*rl),
+        I3(*[int(bool(p)) for p in periodic]), C.byref(rows), C.byref(n)), "ab200_comm_plan_direct")
+    plans = {}
+    try:
+        for q in range(n.value):
+            r = [int(rows[13 * q + c]) for c in range(13)]
+            p = plans.setdefault(r[0], PeerPlan(r[0]))
+            item = tuple(r[2:12]) + (r[12],)
+            ncell = (r[7] - r[6] + 1) * (r[9] - r[8] + 1) * (r[11] - r[10] + 1)
+            if r[1]:
+                p.recv.append(item)
+                p.nrecv = r[12] + r[5] * ncell
+            else:
+                p.send.append(item)
+                p.nsend = r[12] + r[5] * ncell
+    finally:
+        L.ab200_comm_plan_free(rows)
+    return [plans[k] for k in sorted(plans)]
+
+
+class NativeComm:
+    """One rank's handle on the library-owned transport.  Usage (see bench.py):
+
+        comm = NativeComm(md, lay, rank, world, periodic)   # after bind + set_topology
+        md.call("ab200_run_cycles_mr", integ, ncycles, tlim)
+    """
+
+    def __init__(self, md, lay, rank, world, periodic=(False, False, False), dist=None):
+        import torch
+        if dist is None:
+            import torch.distributed as dist
+        self.md = md
+        idbuf = C.create_string_buffer(128)
+        if rank == 0:
+            capi.check(md.L, md.L.ab200_comm_unique_id(idbuf), "ab200_comm_unique_id")
+        t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).clone()
+        dev = torch.device(f"cuda:{md.device}") if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = t.to(dev)
+        dist.broadcast(t, src=0)
+        idbytes = bytes(t.cpu().numpy().tobytes())
+        md.call("ab200_comm_init", int(world), int(rank), C.c_char_p(idbytes))
+        per = (C.c_int * 3)(*[int(bool(p)) for p in periodic])
+        md.call("ab200_comm_set_layout", int(lay[0]), int(lay[1]), int(lay[2]), per)
+        self.bytes_per_exchange = int(md.L.ab200_comm_bytes_per_exchange(md.ctx))
+
+    def begin(self):
+        self.md.call("ab200_comm_exchange_begin")
+
+    def end(self):
+        self.md.call("ab200_comm_exchange_end")
+
+    def allreduce_min_device(self):
+        ptr = int(self.md.L.ab200_dt_device(self.md.ctx))
+        self.md.call("ab200_allreduce_min", C.c_void_p(ptr + 8))

@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--cpu-cycles", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--transport", default="native", choices=["native", "torch"],
+                    help="N > 1: 'native' = the C ABI's own NCCL transport (ab200_run_cycles_mr), "
+                         "'torch' = torch.distributed driven from Python (round-1 path)")
     ap.add_argument("--path", default="auto", choices=["auto", "three_pass", "single_pass", "role_split"],
                     help="ab200_set_stage_path: which stage kernels run (auto = library policy)")
     return ap.parse_args()
@@ -253,8 +256,12 @@ def main():
     md = MeshData(mesh, gas=gp, device=local, materialize_fluxes=False, bcs=bcs)
     md.set_stage_path(args.path)
     path = md.stage_path()
+    native = None
     if world > 1:
-        comm = HaloComm(md, lay, rl, rank, world)
+        comm = HaloComm(md, lay, rl, rank, world)   # Initialize() + the exchange-only probe
+        if args.transport == "native":
+            from artemis_b200.comm import NativeComm
+            native = NativeComm(md, lay, rank, world)
     prim = pgen.blast(mesh, gp.gamma, d0=1.0, p0=1e-5, internal_energy=1.0, radius=0.1, samples=0)
     md.gas.prim.set(prim)
     drv = ArtemisDriver(md, "rk2", mode="fused", comm=comm)
@@ -272,6 +279,8 @@ def main():
     def one_step():
         if world == 1:
             md.call("ab200_run_cycles", integ, 1, float(np.finfo(np.float64).max))
+        elif native is not None:   # the whole multi-rank cycle behind the C ABI
+            md.call("ab200_run_cycles_mr", integ, 1, float(np.finfo(np.float64).max))
         else:
             drv.StepDevice()
 

@@ -15,7 +15,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from artemis_b200.comm import HaloComm, rank_coords  # noqa: E402
+from artemis_b200.comm import HaloComm, NativeComm, rank_coords  # noqa: E402
 from artemis_b200.driver import ArtemisDriver  # noqa: E402
 from artemis_b200.enums import BoundaryFlag, Coordinates  # noqa: E402
 from artemis_b200.mesh import UniformMesh  # noqa: E402
@@ -25,6 +25,9 @@ from tests.helpers import dust_params, gas_params, random_prim  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--cycles", type=int, default=3)
 ap.add_argument("--bnx", type=int, default=16)
+ap.add_argument("--transport", default="native", choices=["native", "torch"],
+                help="native: ab200_run_cycles_mr over the C ABI's own NCCL transport (comm.cu); "
+                     "torch: StepDevice driven from Python over torch.distributed")
 args = ap.parse_args()
 world, rank, local = (int(os.environ[k]) for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"))
 torch.cuda.set_device(local)
@@ -73,8 +76,14 @@ tdrv = ArtemisDriver(tmd, "rk2", mode="fused", comm=comm)
 tdrv.Initialize()
 assert tdrv.dt == dt0, (tdrv.dt, dt0)
 tmd.set_time_state(tdrv.dt)
-for _ in range(args.cycles):
-    tdrv.StepDevice()
+if args.transport == "native":
+    ncomm = NativeComm(tmd, lay, rank, world)
+    tmd.call("ab200_run_cycles_mr", 1, args.cycles, BIG)
+else:
+    tdrv.BeginDeviceResident()
+    for _ in range(args.cycles):
+        tdrv.StepDevice()
+    tdrv.EndDeviceResident()
 tmd.synchronize()
 torch.cuda.synchronize()
 ts = tmd.time_state()
@@ -84,9 +93,9 @@ for f, (wp, wu) in zip(tmd.fluids, want):
 flag = torch.tensor([1.0 if ok else 0.0], device=f"cuda:{local}")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("check_multigpu: world %d lattice %s cycles %d -> %s (overlapped exchange: %s)" % (
-        world, lay, args.cycles, "BIT-IDENTICAL" if flag.item() == 1.0 else "MISMATCH",
-        getattr(comm, "_async", None)))
+    print("check_multigpu: world %d lattice %s cycles %d transport %s -> %s" % (
+        world, lay, args.cycles, args.transport,
+        "BIT-IDENTICAL" if flag.item() == 1.0 else "MISMATCH"))
 tmd.close()
 dist.destroy_process_group()
 sys.exit(0 if flag.item() == 1.0 else 1)
