@@ -42,6 +42,12 @@ def parse():
     ap.add_argument("--cpu-cycles", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
+                    help="BASELINE.json config: 2 = the headline (3-D blast, PPM+HLLC, 256^3 per "
+                         "GPU, weak scaling); 3 = gas + 4 dust species, PLM+HLLE, periodic, "
+                         "--mesh^3 zones IN TOTAL split over the GPUs (strong scaling)")
+    ap.add_argument("--mesh", type=int, default=512, help="config 3: total zones per direction")
+    ap.add_argument("--dust-species", type=int, default=4)
     ap.add_argument("--transport", default="native", choices=["native", "torch"],
                     help="N > 1: 'native' = the C ABI's own NCCL transport (ab200_run_cycles_mr), "
                          "'torch' = torch.distributed driven from Python (round-1 path)")
@@ -221,11 +227,133 @@ def _emit(line: dict):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
+def main_config3(args):
+    """BASELINE.json config 3: gas + dust multifluid (inputs/drag/simple_drag.in state extended to
+    3-D: gas rho 10, v (1,0,0); dust rho 0.01 at rest; seeded sin-mode perturbation),
+    PLM+HLLE both fluids, periodic, rk2, 64^3 MeshBlocks, STRONG scaling: --mesh^3 zones in total
+    split block-spatially over the GPUs.  Drag itself stays on the reference path."""
+    import torch
+    import torch.distributed as dist
+
+    from artemis_b200 import pgen
+    from artemis_b200.driver import ArtemisDriver
+    from artemis_b200.enums import BoundaryFlag, Coordinates, Fluid, ReconstructionMethod, RSolver
+    from artemis_b200.mesh import UniformMesh
+    from artemis_b200.meshdata import MeshData
+    from artemis_b200.params import FluidParams
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    lay = rank_layout(world)
+    M, B, S = args.mesh, args.block, args.dust_species
+    nbt = tuple(M // B // lay[d] for d in range(3))
+    rl = (rank % lay[0], (rank // lay[0]) % lay[1], rank // (lay[0] * lay[1]))
+    mesh = UniformMesh(nx=(M, M, M), xmin=(0, 0, 0), xmax=(1, 1, 1), block_nx=(B, B, B), nghost=4,
+                       bcs=(BoundaryFlag.periodic,) * 6,
+                       lattice_lo=tuple(rl[d] * nbt[d] for d in range(3)), lattice_n=nbt)
+    Cc = Coordinates.cartesian
+    gp = FluidParams(Fluid.gas, Cc, ReconstructionMethod.plm, RSolver.hlle, cfl=0.3, nspecies=1,
+                     dfloor=1e-10, gamma=1.4, siefloor=1e-10)
+    dp = FluidParams(Fluid.dust, Cc, ReconstructionMethod.plm, RSolver.hlle, cfl=0.3, nspecies=S,
+                     dfloor=1e-10)
+    bcs = [int(v) for v in mesh.bcs]
+    for d in range(3):
+        if lay[d] > 1:          # periodic + several ranks: both faces belong to other ranks
+            bcs[2 * d] = bcs[2 * d + 1] = 3
+    md = MeshData(mesh, gas=gp, dust=dp, device=local, materialize_fluxes=False, bcs=bcs)
+    md.set_stage_path(args.path)
+    prim, dprim = pgen.perturbed_constant(mesh, 6, S, amp=1e-3, seed=1234)
+    prim[:, 4] = gp.gm1 * prim[:, 0] * prim[:, 5]
+    md.gas.prim.set(prim)
+    md.dust.prim.set(dprim)
+    del prim, dprim
+    comm = native = None
+    if world > 1:
+        from artemis_b200.comm import HaloComm, NativeComm
+        comm = HaloComm(md, lay, rl, rank, world, periodic=(True, True, True))
+        native = NativeComm(md, lay, rank, world, periodic=(True, True, True))
+    drv = ArtemisDriver(md, "rk2", mode="fused", comm=comm)
+    drv.Initialize()
+    md.set_time_state(drv.dt)
+    md.call("ab200_set_ghost_cons_lazy", 1)
+    big = float(np.finfo(np.float64).max)
+
+    def one_step():
+        md.call("ab200_run_cycles_mr" if world > 1 else "ab200_run_cycles", 1, 1, big)
+
+    def sync_all():
+        md.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step()
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = md.launch_count()
+    sync_all()
+    md.call("ab200_timer_begin")
+    for _ in range(args.steps):
+        one_step()
+    ms = __import__("ctypes").c_float()
+    md.call("ab200_timer_end", __import__("ctypes").byref(ms))
+    sync_all()
+    launches = md.launch_count() - l0
+    clocks = sampler.finish() if sampler else None
+    t_ms = float(ms.value)
+    if world > 1:
+        tt = torch.tensor([t_ms, float(launches)], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(tt[0:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt[1:2], op=dist.ReduceOp.SUM)
+        t_ms, launches = float(tt[0].item()), int(tt[1].item())
+    zones = M ** 3
+    ms_step = t_ms / args.steps
+    value = zones * args.steps / (t_ms * 1e-3)
+    peak, peak_src = measured_peaks()
+    alg = (240.0 + 160.0 * S) * 2          # B per zone-cycle, rk2 (SURVEY 8d)
+    if rank == 0:
+        _emit({"metric": METRIC, "value": value, "unit": "zone-cycles/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": f"config 3: gas + {S} dust species (inputs/drag state + seeded "
+                                      f"perturbation), PLM+HLLE, rk2, periodic, {M}^3 zones in TOTAL in "
+                                      f"{B}^3 MeshBlocks split over {world} GPU(s) (strong scaling); "
+                                      "drag on the reference path",
+                          "zones_total": zones, "ranks": list(lay), "stage_path": md.stage_path(),
+                          "l2": "state >> 126 MB L2, no flush needed"},
+               "roofline": {"bound": "hbm", "achieved": value * alg / world / 1e9, "peak": peak,
+                            "unit": "GB/s", "frac": value * alg / world / 1e9 / peak, "traffic": None,
+                            "peak_source": peak_src,
+                            "algorithmic_bytes_per_zone_cycle": alg,
+                            "note": "whole cycle per GPU (stages + ghost fills + exchange)"},
+               "cpu_baseline": None, "e2e": None, "gpu_launches": launches, "clocks": clocks})
+    md.call("ab200_set_ghost_cons_lazy", 0)
+    md.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.config == 3:
+        main_config3(args)
         return
     import torch
     import torch.distributed as dist
