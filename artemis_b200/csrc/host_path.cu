@@ -67,24 +67,32 @@ extern "C" int ab200_cycles_host(ab200_ctx *c, int integrator, int ncycles, doub
                                  double *dust_prim_host, double *dust_cons_host) {
   AB_REQUIRE(c && c->grid_set, AB200_ESTATE, "ab200_cycles_host: no grid bound");
   AB_REQUIRE(c->topo.set, AB200_ESTATE, "ab200_cycles_host: call ab200_set_topology first");
+  AB_REQUIRE(topology_is_local(c), AB200_ESTATE,
+             "ab200_cycles_host: single-rank entry point (topology has AB200_BC_NONE faces)");
   AB_REQUIRE(dt_io, AB200_EINVAL, "ab200_cycles_host: null dt");
   AB_CUDA(cudaSetDevice(c->device));
   const GridDev &g = c->g;
   const size_t cells = (size_t)g.ni * g.nj * g.nk;
   double *hp[2] = {gas_prim_host, dust_prim_host};
   double *hc[2] = {gas_cons_host, dust_cons_host};
-  // upload primitives: the caller's arrays are [nblocks][nvar][nk][nj][ni]
+  // Upload the primitives, [nblocks][nvar][nk][nj][ni].  The gas pressure entries are NOT
+  // uploaded: PrimToCons recomputes P = EOS(rho, sie) over the entire domain
+  // (fill_derived.cpp:247) before anything reads it, so those bytes never need to cross PCIe.
   for (int fl = 0; fl < 2; ++fl) {
     if (!c->fl[fl].bound) continue;
-    AB_REQUIRE(hp[fl] && hc[fl], AB200_EINVAL, "ab200_cycles_host: null host array for a bound fluid");
+    AB_REQUIRE(hp[fl], AB200_EINVAL, "ab200_cycles_host: null host array for a bound fluid");
     const FluidDev &f = c->fl[fl].d;
+    AB_TRY(sync_prim_home(c, fl, 0));
     std::vector<double *> tab((size_t)g.nb * f.nvar);
     AB_CUDA(cudaMemcpyAsync(tab.data(), f.prim, tab.size() * sizeof(double *),
                             cudaMemcpyDeviceToHost, c->stream));
     AB_CUDA(cudaStreamSynchronize(c->stream));
-    for (size_t e = 0; e < tab.size(); ++e)
+    for (size_t e = 0; e < tab.size(); ++e) {
+      const int n = (int)(e % f.nvar);
+      if (fl == AB200_GAS && n >= 4 * f.S && n < 5 * f.S) continue;  // pressure: derived
       AB_CUDA(cudaMemcpyAsync(tab[e], hp[fl] + e * cells, cells * sizeof(double),
                               cudaMemcpyHostToDevice, c->stream));
+    }
   }
   AB_TRY(ab200_prim_to_cons(c));  // cons == PrimToCons(prim) at every cycle boundary
   double ts[4] = {0, 0, 0, 0};
@@ -97,7 +105,15 @@ extern "C" int ab200_cycles_host(ab200_ctx *c, int integrator, int ncycles, doub
     AB_TRY(ab200_estimate_timestep_device(c));
     AB_TRY(ab200_set_global_timestep_device(c, 1.79769313486231570815e+308, 0));
   }
-  AB_TRY(ab200_run_cycles(c, integrator, ncycles, 1.79769313486231570815e+308));
+  // Conserved arrays are optional on the way back (cons is a pure function of prim: the host
+  // can ask for primitives only and halve the download); when they are not wanted the ghost
+  // PrimToCons is skipped as well.
+  const bool want_cons = (hc[0] != nullptr) || (hc[1] != nullptr);
+  const bool lazy_before = c->ghost_cons_lazy;
+  if (!want_cons) c->ghost_cons_lazy = true;
+  const int rc_run = ab200_run_cycles(c, integrator, ncycles, 1.79769313486231570815e+308);
+  c->ghost_cons_lazy = lazy_before;
+  AB_TRY(rc_run);
   for (int fl = 0; fl < 2; ++fl) {
     if (!c->fl[fl].bound) continue;
     const FluidDev &f = c->fl[fl].d;
@@ -110,8 +126,9 @@ extern "C" int ab200_cycles_host(ab200_ctx *c, int integrator, int ncycles, doub
     for (size_t e = 0; e < tp.size(); ++e) {
       AB_CUDA(cudaMemcpyAsync(hp[fl] + e * cells, tp[e], cells * sizeof(double),
                               cudaMemcpyDeviceToHost, c->stream));
-      AB_CUDA(cudaMemcpyAsync(hc[fl] + e * cells, tc[e], cells * sizeof(double),
-                              cudaMemcpyDeviceToHost, c->stream));
+      if (hc[fl])
+        AB_CUDA(cudaMemcpyAsync(hc[fl] + e * cells, tc[e], cells * sizeof(double),
+                                cudaMemcpyDeviceToHost, c->stream));
     }
   }
   AB_TRY(ab200_read_time_state(c, ts));

@@ -279,7 +279,11 @@ int ab200_finish_remote_ghosts(ab200_ctx *ctx);
  * Runs `ncycles` full rk/vl cycles on state held in HOST memory: uploads the gas (and dust)
  * primitives [nblocks][nvar][nk][nj][ni], rebuilds conserved state with PrimToCons, advances
  * (fused path + library exchange + device dt), downloads primitives and conserved u0.
- * integrator: 0 rk1, 1 rk2, 2 vl2, 3 rk3.  dt_io: in = current dt (<=0: estimate), out = next. */
+ * integrator: 0 rk1, 1 rk2, 2 vl2, 3 rk3.  dt_io: in = current dt (<=0: estimate), out = next.
+ * Bytes that need not cross PCIe do not: the gas PRESSURE entries of the input are ignored
+ * (PrimToCons recomputes P = EOS(rho, sie) over the entire domain, fill_derived.cpp:247) and
+ * are not uploaded; *_cons_host may be NULL (cons is a pure function of prim), which halves
+ * the download and skips the ghost PrimToCons. */
 int ab200_cycles_host(ab200_ctx *ctx, int integrator, int ncycles, double *dt_io,
                       double *gas_prim_host, double *gas_cons_host, double *dust_prim_host,
                       double *dust_cons_host);

@@ -262,3 +262,46 @@ def test_lazy_ghost_cons_equals_eager(variant):
     for (u_e, p_e), (u_l, p_l) in zip(*out):
         assert np.array_equal(u_e, u_l)
         assert np.array_equal(p_e, p_l)
+
+
+@pytest.mark.parametrize("want_cons", [True, False])
+def test_cycles_host_equals_device_resident_cycles(want_cons):
+    """ab200_cycles_host (host arrays in / out, the e2e leg of bench.py): bit for bit the state
+    ab200_run_cycles leaves on the device; the input's pressure entries are ignored (recomputed
+    by PrimToCons) and the conserved arrays are optional."""
+    import ctypes as C
+    mesh = make_mesh(Coordinates.cartesian, 3, bcs=(BoundaryFlag.outflow,) * 6)
+    gp = gas_params(Coordinates.cartesian, "ppm", "hllc")
+    dp = dust_params(Coordinates.cartesian, "plm", "hlle", S=2)
+    prim, dprim = random_prim(mesh, gp, seed=51), random_prim(mesh, dp, seed=52)
+    big = float(np.finfo(np.float64).max)
+    md = MeshData(mesh, gas=gp, dust=dp, variant="strict", materialize_fluxes=False)
+    md.gas.prim.set(prim)
+    md.dust.prim.set(dprim)
+    drv = ArtemisDriver(md, "rk2", mode="fused")
+    drv.Initialize()
+    # the host's arrays carry valid ghost zones (Parthenon's do after Mesh::Initialize)
+    prim, dprim = md.gas.prim.get(), md.dust.prim.get()
+    md.set_time_state(drv.dt)
+    md.call("ab200_run_cycles", 1, 2, big)
+    want = [(f.prim.get(), f.u0.get()) for f in md.fluids]
+    want_dt = md.time_state()[0]
+    md.close()
+
+    md = MeshData(mesh, gas=gp, dust=dp, variant="strict", materialize_fluxes=False)
+    DP = C.POINTER(C.c_double)
+    hp, hd = np.ascontiguousarray(prim), np.ascontiguousarray(dprim)
+    hp[:, 4] = -7.0   # pressure entries of the input must not matter
+    hc, hdc = np.full_like(hp, np.nan), np.full_like(hd, np.nan)
+    dt_io = C.c_double(drv.dt)
+    md.call("ab200_cycles_host", 1, 2, C.byref(dt_io), hp.ctypes.data_as(DP),
+            hc.ctypes.data_as(DP) if want_cons else None, hd.ctypes.data_as(DP),
+            hdc.ctypes.data_as(DP) if want_cons else None)
+    md.synchronize()
+    assert dt_io.value == want_dt
+    assert np.array_equal(hp, want[0][0]) and np.array_equal(hd, want[1][0])
+    if want_cons:
+        assert np.array_equal(hc, want[0][1]) and np.array_equal(hdc, want[1][1])
+    else:
+        assert np.all(np.isnan(hc))
+    md.close()
