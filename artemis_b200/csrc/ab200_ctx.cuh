@@ -114,7 +114,7 @@ int launch_deep_copy(ab200_ctx *c, int fluid);
 int launch_estimate_dt(ab200_ctx *c, int fluid, double *d_out, int combine);
 int launch_fused_stage(ab200_ctx *c, int fluid, double gam0, double gam1, double beta,
                        double dt, int pcm, int stage1_copy, int use_device_dt,
-                       unsigned long long *dt_min);
+                       unsigned long long *dt_min, int defer_c2p = 0);
 bool fused_folds_dt(const ab200_ctx *c);
 // single-pass stage (sweep.cuh / sweep_host.cu)
 bool sweep_eligible(ab200_ctx *c, int fluid);

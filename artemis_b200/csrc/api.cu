@@ -518,10 +518,13 @@ int ab200_fused_stage(ab200_ctx *c, double gam0, double gam1, double beta, doubl
   AB_ENTER(c)
   AB_REQUIRE(!stage1_copy || (gam0 == 0.0 && gam1 == 1.0), AB200_EINVAL,
              "ab200_fused_stage: stage1_copy requires gam0 == 0 and gam1 == 1");
-  AB_REQUIRE((flags & ~(AB200_STAGE_DEVICE_DT | AB200_STAGE_REDUCE_DT | AB200_STAGE_PINGPONG)) == 0,
+  AB_REQUIRE((flags & ~(AB200_STAGE_DEVICE_DT | AB200_STAGE_REDUCE_DT | AB200_STAGE_PINGPONG |
+                        AB200_STAGE_DEFER_C2P)) == 0,
              AB200_EINVAL, "ab200_fused_stage: unknown flag");
   const int use_device_dt = (flags & AB200_STAGE_DEVICE_DT) != 0;
-  const int reduce_dt = (flags & AB200_STAGE_REDUCE_DT) != 0;
+  const int defer = (flags & AB200_STAGE_DEFER_C2P) != 0;
+  // deferred C2P: the timestep is estimated by ab200_finish_stage, from the final primitives
+  const int reduce_dt = (flags & AB200_STAGE_REDUCE_DT) != 0 && !defer;
   const int pingpong = (flags & AB200_STAGE_PINGPONG) != 0;
   // per-fluid raw minimum (bit pattern of a positive double), reset to a huge finite value
   unsigned long long *slots = reinterpret_cast<unsigned long long *>(c->d_red + 3072);
@@ -531,7 +534,7 @@ int ab200_fused_stage(ab200_ctx *c, double gam0, double gam1, double beta, doubl
     if (!c->fl[f].bound) continue;
     AB_TRY(ensure_scratch(c, f, false, true));
     bool fold;
-    if (sweep_eligible(c, f)) {
+    if (!defer && sweep_eligible(c, f)) {
       // single-pass stage (sweep.cuh): reads the current primitive set, writes the other one
       fold = reduce_dt;
       AB_TRY(launch_sweep_stage(c, f, gam0, gam1, beta, dt, pcm, stage1_copy, use_device_dt,
@@ -541,7 +544,7 @@ int ab200_fused_stage(ab200_ctx *c, double gam0, double gam1, double beta, doubl
       AB_TRY(sync_prim_home(c, f, 0));
       fold = reduce_dt && fused_folds_dt(c);
       AB_TRY(launch_fused_stage(c, f, gam0, gam1, beta, dt, pcm, stage1_copy, use_device_dt,
-                                fold ? slots + f : nullptr));
+                                fold ? slots + f : nullptr, defer));
     }
     if (reduce_dt) {  // new_dt = min over fluids of cfl * min dt  (EstimateTimestepMesh)
       if (fold)
@@ -553,6 +556,27 @@ int ab200_fused_stage(ab200_ctx *c, double gam0, double gam1, double beta, doubl
     any = 1;
   }
   AB_REQUIRE(any, AB200_ESTATE, "ab200_fused_stage: no fluid bound");
+  return AB200_OK;
+}
+
+// Second half of a stage whose C2P was deferred (AB200_STAGE_DEFER_C2P) so that out-of-scope or
+// library source terms could act on the conserved state in between: SetAuxillaryFields ->
+// ConsToPrim -> PrimToCons (src/artemis_driver.cpp:251-261 without the exchange), and with
+// AB200_STAGE_REDUCE_DT the CFL timestep of the new primitives into ab200_dt_device()[1].
+int ab200_finish_stage(ab200_ctx *c, int flags) {
+  AB_ENTER(c)
+  AB_REQUIRE((flags & ~AB200_STAGE_REDUCE_DT) == 0, AB200_EINVAL, "ab200_finish_stage: unknown flag");
+  int any = 0;
+  for (int f = 0; f < 2; ++f) {
+    if (!c->fl[f].bound) continue;
+    AB_TRY(sync_prim_home(c, f, 0));
+    if (f == AB200_GAS) AB_TRY(launch_set_aux(c));
+    AB_TRY(launch_cons_to_prim(c, f));
+    AB_TRY(launch_prim_to_cons(c, f, 0));
+    if (flags & AB200_STAGE_REDUCE_DT) AB_TRY(launch_estimate_dt(c, f, c->d_time + 1, any));
+    any = 1;
+  }
+  AB_REQUIRE(any, AB200_ESTATE, "ab200_finish_stage: no fluid bound");
   return AB200_OK;
 }
 

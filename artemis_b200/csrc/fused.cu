@@ -124,18 +124,19 @@ static int launch_dirs(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
   const int copy = a.copy_u1;
   unsigned long long *dt_min = a.dt_min;
   a.dt_min = nullptr;  // only the marching kernel of the last direction folds the dt reduction
-  a.first = 1; a.last = (ndim == 1); a.copy_u1 = copy;
+  const int fin = a.defer_c2p ? 0 : 1;  // deferred: SetAux / C2P run in ab200_finish_stage
+  a.first = 1; a.last = fin * (ndim == 1); a.copy_u1 = copy;
   if (ndim >= 2 && use_xchunk()) AB_TRY((launch_xchunk<GEOM, FLUID, RS, RC>(c, f, a)));
   else AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 1>(c, f, a)));
   if (ndim >= 2) {
-    a.first = 0; a.last = (ndim == 2); a.copy_u1 = 0;
-    a.dt_min = (ndim == 2) ? dt_min : nullptr;
+    a.first = 0; a.last = fin * (ndim == 2); a.copy_u1 = 0;
+    a.dt_min = (ndim == 2 && fin) ? dt_min : nullptr;
     if (use_march()) AB_TRY((launch_march<GEOM, FLUID, RS, RC, 2>(c, f, a)));
     else AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 2>(c, f, a)));
   }
   if (ndim >= 3) {
-    a.first = 0; a.last = 1; a.copy_u1 = 0;
-    a.dt_min = dt_min;
+    a.first = 0; a.last = fin; a.copy_u1 = 0;
+    a.dt_min = fin ? dt_min : nullptr;
     if (use_march()) AB_TRY((launch_march<GEOM, FLUID, RS, RC, 3>(c, f, a)));
     else AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 3>(c, f, a)));
   }

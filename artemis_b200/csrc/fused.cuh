@@ -37,6 +37,7 @@ struct FusedArgs {
   double gam0, gam1, beta, dt, omf;
   const double *dt_dev;  // if non-null: dt = *dt_dev
   int first, last, copy_u1;
+  int defer_c2p;  // AB200_STAGE_DEFER_C2P: no pass is the LAST one (source terms follow)
   int np;        // pencils per CTA
   int npencils;  // pencils per MeshBlock
   int tiles_per_row;    // TMA: tiles along the transverse index that is tiled

@@ -19,9 +19,11 @@ bool fused_folds_dt(const ab200_ctx *c) {
 }
 
 int launch_fused_stage(ab200_ctx *c, int fluid, double gam0, double gam1, double beta, double dt,
-                       int pcm, int stage1_copy, int use_device_dt, unsigned long long *dt_min) {
+                       int pcm, int stage1_copy, int use_device_dt, unsigned long long *dt_min,
+                       int defer_c2p) {
   FusedArgs a{};
   a.dt_min = dt_min;
+  a.defer_c2p = defer_c2p;
   a.gam0 = gam0; a.gam1 = gam1; a.beta = beta; a.dt = dt; a.omf = c->omf;
   a.dt_dev = use_device_dt ? c->d_time : nullptr;
   a.copy_u1 = stage1_copy;

@@ -1,0 +1,255 @@
+// sources.cu -- pointwise source terms that sit between FluxSource and SetAuxillaryFields in
+// the stage task list (src/artemis_driver.cpp:217-248): they read the
+// STAGE-START primitives (ConsToPrim has not run yet) and add to the conserved state of the
+// interior zones.  One kernel per source over every bound fluid and species, one thread per
+// zone, coalesced along i; HBM-bound streaming by construction (read rho, v: 4 doubles per
+// species; read-modify-write m, E: 4).  With a source enabled the stage is driven as
+//   ab200_fused_stage(.. | AB200_STAGE_DEFER_C2P) -> ab200_<source> ... -> ab200_finish_stage
+// because the conserved state must exist in memory between the update and C2P.
+//
+//   ab200_uniform_gravity  Gravity::UniformGravity<GEOM>     src/gravity/uniform.cpp:28-90
+//   ab200_shearing_box     RotatingFrame::ShearingBoxImpl    src/rotating_frame/rotating_frame_impl.hpp:28-94
+//   ab200_drag_simple      Drag::SimpleDragSourceImpl (constant stopping times, no damping
+//                          zones, no viscous target velocity) src/drag/drag.hpp:296-482
+#include <type_traits>
+
+#include "tasks.cuh"
+
+namespace ab200 {
+
+template <typename F>
+static int dispatch_geom_s(int geom, F &&fn) {
+  switch (geom) {
+  case 0: return fn(std::integral_constant<int, 0>{});
+  case 1: return fn(std::integral_constant<int, 1>{});
+  case 2: return fn(std::integral_constant<int, 2>{});
+  case 3: return fn(std::integral_constant<int, 3>{});
+  case 4: return fn(std::integral_constant<int, 4>{});
+  case 5: return fn(std::integral_constant<int, 5>{});
+  }
+  set_error("Coordinate type not recognized!");
+  return AB200_EINVAL;
+}
+
+struct TwoFluids {
+  FluidDev f[2];
+  int on[2];
+};
+
+template <int GEOM>
+__global__ void __launch_bounds__(kThreads)
+k_uniform_gravity(GridDev g, TwoFluids tf, double dt, double gx1, double gx2, double gx3) {
+  const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)g.nb * nkr * njr * nir) return;
+  const CellIdx c = decode(t, nir, njr, nkr, g.is, g.js, g.ks);
+  Coords<GEOM> cc(g, c.b, c.k, c.j, c.i);
+  const double hx[3] = {cc.hx1v(), cc.hx2v(), cc.hx3v()};
+  const double gv[3] = {gx1, gx2, gx3};
+  const size_t off = ((size_t)c.k * g.nj + c.j) * g.ni + c.i;
+#pragma unroll
+  for (int fl = 0; fl < 2; ++fl) {
+    if (!tf.on[fl]) continue;
+    const FluidDev &f = tf.f[fl];
+    const int S = f.S;
+    const size_t e = (size_t)c.b * f.nvar;
+    for (int n = 0; n < S; ++n) {
+      const double rdt = dt * f.prim[e + n][off];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) f.u0[e + S + 3 * n + d][off] += rdt * hx[d] * gv[d];
+      if (fl == AB200_GAS)
+        f.u0[e + 4 * S + n][off] += rdt * (f.prim[e + S + 3 * n + 0][off] * gx1 +
+                                           f.prim[e + S + 3 * n + 1][off] * gx2 +
+                                           f.prim[e + S + 3 * n + 2][off] * gx3);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_shearing_box(GridDev g, TwoFluids tf, double dt, double om0, double qshear) {
+  const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)g.nb * nkr * njr * nir) return;
+  const CellIdx c = decode(t, nir, njr, nkr, g.is, g.js, g.ks);
+  Coords<AB200_CARTESIAN> cc(g, c.b, c.k, c.j, c.i);
+  const double three_d = (g.ndim == 3) ? 1.0 : 0.0;
+  const double omsq = om0 * om0;
+  const double dx = cc.x1[1] - cc.x1[0];
+  const double dz = cc.x3[1] - cc.x3[0];
+  const double phi_xm1 = -qshear * omsq * cc.x1[0] * cc.x1[0];
+  const double phi_xp1 = -qshear * omsq * cc.x1[1] * cc.x1[1];
+  const double phi_zm1 = 0.5 * omsq * cc.x3[0] * cc.x3[0];
+  const double phi_zp1 = 0.5 * omsq * cc.x3[1] * cc.x3[1];
+  const double dpx = (phi_xp1 - phi_xm1) / dx;
+  const double dpz = three_d * ((phi_zp1 - phi_zm1) / dz);
+  const size_t off = ((size_t)c.k * g.nj + c.j) * g.ni + c.i;
+#pragma unroll
+  for (int fl = 0; fl < 2; ++fl) {
+    if (!tf.on[fl]) continue;
+    const FluidDev &f = tf.f[fl];
+    const int S = f.S;
+    const size_t e = (size_t)c.b * f.nvar;
+    for (int n = 0; n < S; ++n) {
+      const double dens = f.prim[e + n][off];
+      const double v1 = f.prim[e + S + 3 * n + 0][off], v2 = f.prim[e + S + 3 * n + 1][off],
+                   v3 = f.prim[e + S + 3 * n + 2][off];
+      const double rdt = dens * dt;
+      f.u0[e + S + 3 * n + 0][off] -= rdt * (dpx - 2.0 * om0 * v2);
+      f.u0[e + S + 3 * n + 1][off] -= rdt * 2.0 * om0 * v1;
+      f.u0[e + S + 3 * n + 2][off] -= rdt * dpz;
+      if (fl == AB200_GAS) f.u0[e + 4 * S + n][off] -= rdt * (v1 * dpx + v3 * dpz);
+    }
+  }
+}
+
+constexpr int kMaxDustSpecies = 16;
+struct DragTau {
+  double tau[kMaxDustSpecies];
+};
+
+// The implicit two-pass update of drag.hpp:403-478 with bg = bd = 0, vt = vdt = 0 kept as
+// explicit zeros so the operation order (and the strict build's bits) are the reference's.
+template <int GEOM>
+__global__ void __launch_bounds__(kThreads)
+k_drag_simple(GridDev g, FluidDev fg, FluidDev fd_, double dt, DragTau tp) {
+  const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)g.nb * nkr * njr * nir) return;
+  const CellIdx c = decode(t, nir, njr, nkr, g.is, g.js, g.ks);
+  Coords<GEOM> cc(g, c.b, c.k, c.j, c.i);
+  const double hx[3] = {cc.hx1v(), cc.hx2v(), cc.hx3v()};
+  const size_t off = ((size_t)c.k * g.nj + c.j) * g.ni + c.i;
+  const int Sg = fg.S, Sd = fd_.S;
+  const size_t eg = (size_t)c.b * fg.nvar, ed = (size_t)c.b * fd_.nvar;
+  const double big = 1.79769313486231570815e+308;
+  const double bg = 0.0, bd = 0.0, vt = 0.0, vdt = 0.0;
+  const double dg = fg.u0[eg][off];
+  double vg[3], fd[3] = {0.0, 0.0, 0.0}, fvd[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) vg[d] = fg.u0[eg + Sg + d][off] / (hx[d] * dg);
+  for (int n = 0; n < Sd; ++n) {
+    const double dens = fd_.u0[ed + n][off];
+    const double tc = tp.tau[n];
+    const double alpha = dt * ((tc <= 0.0) ? big : 1.0 / tc);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double vd = fd_.u0[ed + Sd + 3 * n + d][off] / (hx[d] * dens);
+      const double rhop = dens * alpha / (1.0 + alpha + bd);
+      fd[d] += rhop * (1.0 + bd);
+      fvd[d] += rhop * (vd + bd * vdt);
+    }
+  }
+  double vgp[3], delta_g[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    vgp[d] = (dg * (vg[d] + bg * vt) + fvd[d]) / (dg * (1.0 + bg) + fd[d]);
+    fvd[d] = 0.;
+  }
+  for (int n = 0; n < Sd; ++n) {
+    const double dens = fd_.u0[ed + n][off];
+    const double tc = tp.tau[n];
+    const double alpha = dt * ((tc <= 0.0) ? big : 1.0 / tc);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      double *pm = fd_.u0[ed + Sd + 3 * n + d] + off;
+      const double vd = *pm / (hx[d] * dens);
+      double delta_d = 0.;
+      const double rhop = dens * alpha / (1.0 + alpha + bd);
+      const double delta = rhop * ((vgp[d] - vd + bd * (vgp[d] - vdt)));
+      delta_d += delta;
+      delta_g[d] -= delta;
+      delta_d -= bd * dens / (1. + alpha + bd) * (vd - vdt + alpha * (vgp[d] - vdt));
+      fvd[d] += rhop * (vd - vt + bd * (vdt - vt));
+      *pm += hx[d] * delta_d;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double prefac = dg * bg / (1.0 + bg + fd[d]);
+    delta_g[d] -= prefac * (dg * (vg[d] - vt) + fvd[d]);
+    fg.u0[eg + Sg + d][off] += hx[d] * delta_g[d];
+    fg.u0[eg + 4 * Sg][off] += 0.5 * (vg[d] + vgp[d]) * delta_g[d];
+  }
+}
+
+static unsigned grid_s(const GridDev &g) {
+  const long long n = (long long)g.nb * (g.ke - g.ks + 1) * (g.je - g.js + 1) * (g.ie - g.is + 1);
+  return (unsigned)((n + kThreads - 1) / kThreads);
+}
+
+static int two_fluids(ab200_ctx *c, TwoFluids &tf) {
+  int any = 0;
+  for (int f = 0; f < 2; ++f) {
+    tf.on[f] = c->fl[f].bound ? 1 : 0;
+    if (tf.on[f]) {
+      AB_TRY(sync_prim_home(c, f, 0));  // the sources read the caller-visible primitives
+      tf.f[f] = c->fl[f].d;
+      any = 1;
+    }
+  }
+  AB_REQUIRE(any, AB200_ESTATE, "source term: no fluid bound");
+  return AB200_OK;
+}
+
+}  // namespace ab200
+
+using namespace ab200;
+
+#define AB_ENTER_S(c)                                                                    \
+  AB_REQUIRE((c) != nullptr, AB200_EINVAL, "null context");                              \
+  AB_REQUIRE((c)->grid_set, AB200_ESTATE, "no grid bound: call ab200_set_grid");         \
+  AB_CUDA(cudaSetDevice((c)->device));
+
+extern "C" {
+
+int ab200_uniform_gravity(ab200_ctx *c, double dt, double gx1, double gx2, double gx3) {
+  AB_ENTER_S(c)
+  TwoFluids tf{};
+  AB_TRY(two_fluids(c, tf));
+  const GridDev &g = c->g;
+  int rc = dispatch_geom_s(g.geom, [&](auto G) {
+    k_uniform_gravity<decltype(G)::value><<<grid_s(g), kThreads, 0, c->stream>>>(g, tf, dt, gx1, gx2, gx3);
+    return AB200_OK;
+  });
+  c->launches++;
+  AB_CUDA(cudaGetLastError());
+  return rc;
+}
+
+int ab200_shearing_box(ab200_ctx *c, double dt, double omega, double qshear) {
+  AB_ENTER_S(c)
+  // src/rotating_frame/rotating_frame.cpp:31-37
+  AB_REQUIRE(omega != 0.0, AB200_EINVAL, "rotating_frame/omega cannot be zero!");
+  AB_REQUIRE(c->g.geom == AB200_CARTESIAN, AB200_EINVAL,
+             "ab200_shearing_box: the shearing box is Cartesian (curvilinear frames use "
+             "RotatingFrameImpl, which stays on the reference path)");
+  TwoFluids tf{};
+  AB_TRY(two_fluids(c, tf));
+  k_shearing_box<<<grid_s(c->g), kThreads, 0, c->stream>>>(c->g, tf, dt, omega, qshear);
+  c->launches++;
+  AB_CUDA(cudaGetLastError());
+  return AB200_OK;
+}
+
+int ab200_drag_simple(ab200_ctx *c, double dt, int ntau, const double *tau) {
+  AB_ENTER_S(c)
+  AB_REQUIRE(c->fl[0].bound && c->fl[1].bound, AB200_ESTATE,
+             "ab200_drag_simple: gas and dust must both be bound");
+  AB_REQUIRE(tau && ntau == c->fl[1].d.S, AB200_EINVAL,
+             "ab200_drag_simple: one stopping time per dust species");
+  AB_REQUIRE(ntau <= kMaxDustSpecies, AB200_EINVAL, "ab200_drag_simple: too many dust species");
+  AB_REQUIRE(c->fl[0].d.S == 1, AB200_EINVAL,
+             "ab200_drag_simple: the reference couples gas species 0 only (drag.hpp:387)");
+  DragTau tp{};
+  for (int n = 0; n < ntau; ++n) tp.tau[n] = tau[n];
+  const GridDev &g = c->g;
+  int rc = dispatch_geom_s(g.geom, [&](auto G) {
+    k_drag_simple<decltype(G)::value><<<grid_s(g), kThreads, 0, c->stream>>>(g, c->fl[0].d, c->fl[1].d, dt, tp);
+    return AB200_OK;
+  });
+  c->launches++;
+  AB_CUDA(cudaGetLastError());
+  return rc;
+}
+
+}  // extern "C"

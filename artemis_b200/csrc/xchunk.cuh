@@ -28,6 +28,8 @@ namespace ab200 {
 
 constexpr int kXcWarps = 4;  // warps per CTA (independent of each other)
 
+// (r02: forcing 4 CTAs per SM -- 128 registers, 16 warps -- was measured 10 % SLOWER per cycle
+// than the 160 registers / 12 warps the compiler picks: the pass lives on per-thread ILP)
 template <int GEOM, int FLUID, int RS, int RC>
 __global__ void __launch_bounds__(kXcWarps * 32)
 k_xchunk_pass(GridDev g, FluidDev f, FusedArgs a) {

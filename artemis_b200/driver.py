@@ -132,8 +132,12 @@ class ArtemisDriver:
     """
 
     def __init__(self, md: MeshData, integrator: str = "rk2", mode: str = "tasks",
-                 tlim: float = np.inf, nlim: int = -1, comm=None):
+                 tlim: float = np.inf, nlim: int = -1, comm=None, sources=()):
         self.md = md
+        # pointwise source terms between FluxSource and SetAuxillaryFields
+        # (src/artemis_driver.cpp:217-248): ("gravity", gx1, gx2, gx3) |
+        # ("shearing_box", omega, qshear) | ("drag", [tau per dust species])
+        self.sources = list(sources)
         self.integrator = LowStorageIntegrator(integrator)
         self.mode = mode
         self.comm = comm
@@ -179,6 +183,25 @@ class ArtemisDriver:
         if self.time < self.tlim and (self.tlim - self.time) < self.dt:
             self.dt = self.tlim - self.time
 
+    def ApplySources(self, bdt: float):
+        """ExternalGravity -> RotatingFrameForce -> DragSource, the reference's task order
+        (src/artemis_driver.cpp:222-243)."""
+        md, req = self.md, self._require
+        order = {"gravity": 0, "shearing_box": 1, "drag": 2}
+        for src in sorted(self.sources, key=lambda t: order[t[0]]):
+            if src[0] == "gravity":
+                req(_task(md, "ab200_uniform_gravity", float(bdt), *[float(v) for v in src[1:4]]),
+                    md, "Gravity::UniformGravity")
+            elif src[0] == "shearing_box":
+                req(_task(md, "ab200_shearing_box", float(bdt), float(src[1]), float(src[2])),
+                    md, "RotatingFrame::ShearingBoxImpl")
+            elif src[0] == "drag":
+                tau = np.ascontiguousarray(src[1], dtype=np.float64)
+                req(_task(md, "ab200_drag_simple", float(bdt), len(tau), tau.ctypes.data_as(_DP)),
+                    md, "Drag::DragSource")
+            else:
+                raise ValueError(f"unknown source term {src[0]!r}")
+
     def StepTasks(self):
         md, integ = self.md, self.integrator
         req = self._require
@@ -197,14 +220,21 @@ class ArtemisDriver:
                     req(Gas.FluxSource(md, bdt), md, "Gas::FluxSource")
                 if self.do_dust:
                     req(Dust.FluxSource(md, bdt), md, "Dust::FluxSource")
+                self.ApplySources(bdt)
                 req(ArtemisDerived.SetAuxillaryFields(md), md, "SetAuxillaryFields")
                 req(ArtemisDerived.ConsToPrim(md), md, "ConsToPrim")
                 req(AddBoundaryExchangeTasks(md, self.comm), md, "AddBoundaryExchangeTasks")
                 req(ArtemisDerived.PrimToCons(md), md, "PrimToCons")
             else:
+                # with source terms the conserved state must exist between the update and C2P:
+                # the fused passes stop after FluxSource (AB200_STAGE_DEFER_C2P = 8)
+                defer = 8 if self.sources else 0
                 req(_task(md, "ab200_fused_stage", integ.gam0[stage - 1], integ.gam1[stage - 1],
-                          integ.beta[stage - 1], integ.dt, int(do_pcm), int(stage == 1), 0),
+                          integ.beta[stage - 1], integ.dt, int(do_pcm), int(stage == 1), defer),
                     md, "ab200_fused_stage")
+                if defer:
+                    self.ApplySources(bdt)
+                    req(_task(md, "ab200_finish_stage", 0), md, "ab200_finish_stage")
                 req(AddBoundaryExchangeTasks(md, self.comm), md, "AddBoundaryExchangeTasks")
                 req(_task(md, "ab200_prim_to_cons_ghosts"), md, "PrimToCons(ghosts)")
 

@@ -163,8 +163,35 @@ int ab200_estimate_timestep(ab200_ctx *ctx, int fluid, double *dt_host);
 #define AB200_STAGE_DEVICE_DT 1
 #define AB200_STAGE_REDUCE_DT 2
 #define AB200_STAGE_PINGPONG 4
+/*        AB200_STAGE_DEFER_C2P  the passes only update the conserved state (ApplyUpdate +
+ *                               FluxSource); SetAuxillaryFields / ConsToPrim / PrimToCons and the
+ *                               timestep wait for ab200_finish_stage, so that source terms
+ *                               (src/artemis_driver.cpp:217-248: the library's ab200_uniform_gravity /
+ *                               ab200_shearing_box / ab200_drag_simple, or the host's own Kokkos
+ *                               kernels) can act on the conserved state in between.  Takes the
+ *                               directional passes (the single-pass kernels always finish). */
+#define AB200_STAGE_DEFER_C2P 8
 int ab200_fused_stage(ab200_ctx *ctx, double gam0, double gam1, double beta, double dt,
                       int pcm, int stage1_copy, int flags);
+/* SetAuxillaryFields -> ConsToPrim -> PrimToCons after a AB200_STAGE_DEFER_C2P stage and its
+ * source terms; flags: AB200_STAGE_REDUCE_DT (last stage of a cycle: Gas/Dust::
+ * EstimateTimestepMesh of the new primitives into ab200_dt_device()[1]). */
+int ab200_finish_stage(ab200_ctx *ctx, int flags);
+
+/* ---- pointwise source terms between FluxSource and SetAuxillaryFields --------
+ * They read the stage-start primitives and add to the conserved state of interior zones of every
+ * bound fluid; dt = beta * dt of the stage (src/artemis_driver.cpp:217-248).
+ *   ab200_uniform_gravity  Gravity::UniformGravity<GEOM>   src/gravity/uniform.cpp:28-90
+ *   ab200_shearing_box     RotatingFrame::ShearingBoxImpl  src/rotating_frame/rotating_frame_impl.hpp:28-94
+ *                          (Cartesian; the curvilinear RotatingFrameImpl :96-199 reads the density
+ *                          fluxes and stays on the reference path)
+ *   ab200_drag_simple      Drag::SimpleDragSourceImpl      src/drag/drag.hpp:296-482 with constant
+ *                          stopping times tau[n] per dust species (<drag/dust> type = constant),
+ *                          no damping zones and no viscous target velocity (inputs/drag/simple_drag.in) */
+int ab200_uniform_gravity(ab200_ctx *ctx, double dt, double gx1, double gx2, double gx3);
+int ab200_shearing_box(ab200_ctx *ctx, double dt, double omega, double qshear);
+int ab200_drag_simple(ab200_ctx *ctx, double dt, int ntau, const double *tau);
+
 /* Which kernels ab200_fused_stage runs on meshes where both exist (3-D Cartesian, TMA-able
  * arrays); every other mesh always takes the directional passes.
  *   AB200_PATH_AUTO         the faster of the two as measured on B200 for the bound fluid's

@@ -1217,3 +1217,168 @@ void ao_prolongate_minmod(const ao_refine_geom *r, int nvar, const double *coars
 #undef CO
 #undef FI
 }
+
+/* ==========================================================================================
+ * Pointwise source terms between FluxSource and SetAuxillaryFields (SURVEY 8f rank 1,
+ * src/artemis_driver.cpp:217-248).  They read the STAGE-START primitives (C2P has not run yet)
+ * and add to the conserved state of interior zones.
+ * ========================================================================================== */
+
+/* Gravity::UniformGravity<GEOM>, src/gravity/uniform.cpp:28-90 */
+void ao_uniform_gravity(const ao_grid *g, const ao_fluid *gas, const double *gprim, double *gcons,
+                        const ao_fluid *dust, const double *dprim, double *dcons, double dt,
+                        double gx1, double gx2, double gx3) {
+  const size_t cells = (size_t)g->ni * g->nj * g->nk;
+#pragma omp parallel for collapse(3) schedule(static)
+  for (int b = 0; b < g->nb; ++b)
+    for (int k = g->ks; k <= g->ke; ++k)
+      for (int j = g->js; j <= g->je; ++j)
+        for (int i = g->is; i <= g->ie; ++i) {
+          const bbox_t bb = make_bbox(g->xmin + 3 * b, g->dx + 3 * b, k, j, i);
+          const double hx[3] = {g_hx1v(g->geom, &bb), g_hx2v(g->geom, &bb), g_hx3v(g->geom, &bb)};
+          const size_t o = ((size_t)k * g->nj + j) * g->ni + i;
+          if (gas) {
+            const int S = gas->nspecies;
+            const double *w = gprim + (size_t)b * 6 * S * cells;
+            double *u = gcons + (size_t)b * 6 * S * cells;
+            for (int n = 0; n < S; ++n) {
+              const double rdt = dt * w[(size_t)n * cells + o];
+              u[(size_t)(S + 3 * n + 0) * cells + o] += rdt * hx[0] * gx1;
+              u[(size_t)(S + 3 * n + 1) * cells + o] += rdt * hx[1] * gx2;
+              u[(size_t)(S + 3 * n + 2) * cells + o] += rdt * hx[2] * gx3;
+              u[(size_t)(4 * S + n) * cells + o] +=
+                  rdt * (w[(size_t)(S + 3 * n + 0) * cells + o] * gx1 +
+                         w[(size_t)(S + 3 * n + 1) * cells + o] * gx2 +
+                         w[(size_t)(S + 3 * n + 2) * cells + o] * gx3);
+            }
+          }
+          if (dust) {
+            const int S = dust->nspecies;
+            const double *w = dprim + (size_t)b * 4 * S * cells;
+            double *u = dcons + (size_t)b * 4 * S * cells;
+            for (int n = 0; n < S; ++n) {
+              const double rdt = dt * w[(size_t)n * cells + o];
+              u[(size_t)(S + 3 * n + 0) * cells + o] += rdt * hx[0] * gx1;
+              u[(size_t)(S + 3 * n + 1) * cells + o] += rdt * hx[1] * gx2;
+              u[(size_t)(S + 3 * n + 2) * cells + o] += rdt * hx[2] * gx3;
+            }
+          }
+        }
+}
+
+/* RotatingFrame::ShearingBoxImpl, src/rotating_frame/rotating_frame_impl.hpp:28-94
+ * (Cartesian only: Coriolis + tidal potential differenced across the cell) */
+void ao_shearing_box(const ao_grid *g, const ao_fluid *gas, const double *gprim, double *gcons,
+                     const ao_fluid *dust, const double *dprim, double *dcons, double dt,
+                     double om0, double qshear) {
+  const size_t cells = (size_t)g->ni * g->nj * g->nk;
+  const int three_d = (g->ndim == 3);
+  const double omsq = om0 * om0;
+#pragma omp parallel for collapse(3) schedule(static)
+  for (int b = 0; b < g->nb; ++b)
+    for (int k = g->ks; k <= g->ke; ++k)
+      for (int j = g->js; j <= g->je; ++j)
+        for (int i = g->is; i <= g->ie; ++i) {
+          const bbox_t bb = make_bbox(g->xmin + 3 * b, g->dx + 3 * b, k, j, i);
+          const double dx = bb.x1[1] - bb.x1[0];
+          const double dz = bb.x3[1] - bb.x3[0];
+          const double phi_xm1 = -qshear * omsq * bb.x1[0] * bb.x1[0];
+          const double phi_xp1 = -qshear * omsq * bb.x1[1] * bb.x1[1];
+          const double phi_zm1 = 0.5 * omsq * bb.x3[0] * bb.x3[0];
+          const double phi_zp1 = 0.5 * omsq * bb.x3[1] * bb.x3[1];
+          const double dpx = (phi_xp1 - phi_xm1) / dx;
+          const double dpz = three_d * ((phi_zp1 - phi_zm1) / dz);
+          const size_t o = ((size_t)k * g->nj + j) * g->ni + i;
+          for (int fl = 0; fl < 2; ++fl) {
+            const ao_fluid *f = fl ? dust : gas;
+            if (!f) continue;
+            const int S = f->nspecies, nv = (fl ? 4 : 6) * S;
+            const double *w = (fl ? dprim : gprim) + (size_t)b * nv * cells;
+            double *u = (fl ? dcons : gcons) + (size_t)b * nv * cells;
+            for (int n = 0; n < S; ++n) {
+              const double dens = w[(size_t)n * cells + o];
+              const double v1 = w[(size_t)(S + 3 * n + 0) * cells + o];
+              const double v2 = w[(size_t)(S + 3 * n + 1) * cells + o];
+              const double v3 = w[(size_t)(S + 3 * n + 2) * cells + o];
+              const double rdt = dens * dt;
+              u[(size_t)(S + 3 * n + 0) * cells + o] -= rdt * (dpx - 2.0 * om0 * v2);
+              u[(size_t)(S + 3 * n + 1) * cells + o] -= rdt * 2.0 * om0 * v1;
+              u[(size_t)(S + 3 * n + 2) * cells + o] -= rdt * dpz;
+              if (!fl) u[(size_t)(4 * S + n) * cells + o] -= rdt * (v1 * dpx + v3 * dpz);
+            }
+          }
+        }
+}
+
+/* Drag::SimpleDragSourceImpl<DiffType::null, DragModel::constant, GEOM>,
+ * src/drag/drag.hpp:296-482, with no damping zones (irate = orate = 0 => bg = bd = 0) and no
+ * viscous target velocity (mu = 0 => vt = 0): the implicit gas <-> dust momentum exchange with
+ * constant stopping times tau[n] (tp.tau, drag.hpp:112-129).  gas species 0 couples to every
+ * dust species; total momentum is conserved to rounding (tst/scripts/drag/drag.py:135-137). */
+void ao_drag_simple(const ao_grid *g, const ao_fluid *gas, double *gcons, const ao_fluid *dust,
+                    double *dcons, double dt, const double *tau) {
+  const size_t cells = (size_t)g->ni * g->nj * g->nk;
+  const int Sg = gas->nspecies, Sd = dust->nspecies;
+  const double big = 1.79769313486231570815e+308; /* Big<Real>() */
+#pragma omp parallel for collapse(3) schedule(static)
+  for (int b = 0; b < g->nb; ++b)
+    for (int k = g->ks; k <= g->ke; ++k)
+      for (int j = g->js; j <= g->je; ++j)
+        for (int i = g->is; i <= g->ie; ++i) {
+          const bbox_t bb = make_bbox(g->xmin + 3 * b, g->dx + 3 * b, k, j, i);
+          const double hx[3] = {g_hx1v(g->geom, &bb), g_hx2v(g->geom, &bb), g_hx3v(g->geom, &bb)};
+          const size_t o = ((size_t)k * g->nj + j) * g->ni + i;
+          double *ug = gcons + (size_t)b * 6 * Sg * cells;
+          double *ud = dcons + (size_t)b * 4 * Sd * cells;
+          const double bg[3] = {0.0, 0.0, 0.0}, bd[3] = {0.0, 0.0, 0.0};
+          const double vt[3] = {0.0, 0.0, 0.0}, vdt[3] = {0.0, 0.0, 0.0};
+          const double dg = ug[o];
+          const double vg[3] = {ug[(size_t)(Sg + 0) * cells + o] / (hx[0] * dg),
+                                ug[(size_t)(Sg + 1) * cells + o] / (hx[1] * dg),
+                                ug[(size_t)(Sg + 2) * cells + o] / (hx[2] * dg)};
+          double fd[3] = {0.0, 0.0, 0.0}, fvd[3] = {0.0, 0.0, 0.0};
+          for (int n = 0; n < Sd; ++n) {
+            const double dens = ud[(size_t)n * cells + o];
+            const double vd[3] = {ud[(size_t)(Sd + 3 * n + 0) * cells + o] / (hx[0] * dens),
+                                  ud[(size_t)(Sd + 3 * n + 1) * cells + o] / (hx[1] * dens),
+                                  ud[(size_t)(Sd + 3 * n + 2) * cells + o] / (hx[2] * dens)};
+            const double tc = tau[n];
+            const double alpha = dt * ((tc <= 0.0) ? big : 1.0 / tc);
+            for (int d = 0; d < 3; d++) {
+              const double rhop = dens * alpha / (1.0 + alpha + bd[d]);
+              fd[d] += rhop * (1.0 + bd[d]);
+              fvd[d] += rhop * (vd[d] + bd[d] * vdt[d]);
+            }
+          }
+          double vgp[3];
+          for (int d = 0; d < 3; d++)
+            vgp[d] = (dg * (vg[d] + bg[d] * vt[d]) + fvd[d]) / (dg * (1.0 + bg[d]) + fd[d]);
+          double delta_g[3] = {0.0, 0.0, 0.0};
+          for (int d = 0; d < 3; d++) fvd[d] = 0.;
+          for (int n = 0; n < Sd; ++n) {
+            const double dens = ud[(size_t)n * cells + o];
+            const double vd[3] = {ud[(size_t)(Sd + 3 * n + 0) * cells + o] / (hx[0] * dens),
+                                  ud[(size_t)(Sd + 3 * n + 1) * cells + o] / (hx[1] * dens),
+                                  ud[(size_t)(Sd + 3 * n + 2) * cells + o] / (hx[2] * dens)};
+            const double tc = tau[n];
+            const double alpha = dt * ((tc <= 0.0) ? big : 1.0 / tc);
+            for (int d = 0; d < 3; d++) {
+              double delta_d = 0.;
+              const double rhop = dens * alpha / (1.0 + alpha + bd[d]);
+              const double delta = rhop * ((vgp[d] - vd[d] + bd[d] * (vgp[d] - vdt[d])));
+              delta_d += delta;
+              delta_g[d] -= delta;
+              delta_d -= bd[d] * dens / (1. + alpha + bd[d]) *
+                         (vd[d] - vdt[d] + alpha * (vgp[d] - vdt[d]));
+              fvd[d] += rhop * (vd[d] - vt[d] + bd[d] * (vdt[d] - vt[d]));
+              ud[(size_t)(Sd + 3 * n + d) * cells + o] += hx[d] * delta_d;
+            }
+          }
+          for (int d = 0; d < 3; d++) {
+            const double prefac = dg * bg[d] / (1.0 + bg[d] + fd[d]);
+            delta_g[d] -= prefac * (dg * (vg[d] - vt[d]) + fvd[d]);
+            ug[(size_t)(Sg + d) * cells + o] += hx[d] * delta_g[d];
+            ug[(size_t)(4 * Sg) * cells + o] += 0.5 * (vg[d] + vgp[d]) * delta_g[d];
+          }
+        }
+}

@@ -125,6 +125,22 @@ void ao_restrict_average(const ao_refine_geom *r, int nvar, const double *fine, 
 void ao_prolongate_minmod(const ao_refine_geom *r, int nvar, const double *coarse, double *fine,
                           const int *box);
 
+/* ---- pointwise source terms between FluxSource and SetAuxillaryFields ----
+ * gas / dust may be NULL (fluid absent).  They read the stage-start primitives and update the
+ * conserved state of interior zones in place. */
+/* Gravity::UniformGravity<GEOM>, src/gravity/uniform.cpp:28-90 */
+void ao_uniform_gravity(const ao_grid *g, const ao_fluid *gas, const double *gprim, double *gcons,
+                        const ao_fluid *dust, const double *dprim, double *dcons, double dt,
+                        double gx1, double gx2, double gx3);
+/* RotatingFrame::ShearingBoxImpl, src/rotating_frame/rotating_frame_impl.hpp:28-94 */
+void ao_shearing_box(const ao_grid *g, const ao_fluid *gas, const double *gprim, double *gcons,
+                     const ao_fluid *dust, const double *dprim, double *dcons, double dt,
+                     double om0, double qshear);
+/* Drag::SimpleDragSourceImpl (constant stopping times, no damping zones, no viscous target
+ * velocity), src/drag/drag.hpp:296-482 */
+void ao_drag_simple(const ao_grid *g, const ao_fluid *gas, double *gcons, const ao_fluid *dust,
+                    double *dcons, double dt, const double *tau);
+
 #ifdef __cplusplus
 }
 #endif

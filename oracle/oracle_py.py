@@ -120,6 +120,43 @@ class OracleSim:
         self.dt = np.finfo(np.float64).max
         self.tlim = np.inf
         self.nlim = -1
+        # pointwise source terms between FluxSource and SetAuxillaryFields
+        # (src/artemis_driver.cpp:217-248): list of ("gravity", gx1, gx2, gx3) |
+        # ("shearing_box", om0, qshear) | ("drag", [tau per dust species])
+        self.sources = []
+
+    def _both(self):
+        fg = make_fluid(self.gas.fp) if self.gas is not None else None
+        fd = make_fluid(self.dust.fp) if self.dust is not None else None
+        null = C.POINTER(C.c_double)()
+        return (fg, fd,
+                (C.byref(fg) if fg is not None else None, _p(self.gas.prim) if fg is not None else null,
+                 _p(self.gas.u0) if fg is not None else null,
+                 C.byref(fd) if fd is not None else None, _p(self.dust.prim) if fd is not None else null,
+                 _p(self.dust.u0) if fd is not None else null))
+
+    def _src_lib(self):
+        return self.L, "ao"
+
+    def ApplySources(self, dt):
+        """ExternalGravity / RotatingFrameForce / DragSource in the reference's task order
+        (src/artemis_driver.cpp:222-243: gravity, rotating frame, drag)."""
+        if not self.sources:
+            return
+        L, pre = self._src_lib()
+        fg, fd, args = self._both()
+        order = {"gravity": 0, "shearing_box": 1, "drag": 2}
+        for src in sorted(self.sources, key=lambda t: order[t[0]]):
+            if src[0] == "gravity":
+                getattr(L, pre + "_uniform_gravity")(C.byref(self.g), *args, C.c_double(dt),
+                                                    *[C.c_double(v) for v in src[1:4]])
+            elif src[0] == "shearing_box":
+                getattr(L, pre + "_shearing_box")(C.byref(self.g), *args, C.c_double(dt),
+                                                 C.c_double(src[1]), C.c_double(src[2]))
+            elif src[0] == "drag":
+                tau = np.ascontiguousarray(src[1], dtype=np.float64)
+                self.L.ao_drag_simple(C.byref(self.g), args[0], args[2], args[3], args[5],
+                                      C.c_double(dt), _p(tau))
 
     # ---- task functions (names follow the reference) ---------------------------------
     def CalculateFluxes(self, fs, pcm):
@@ -196,6 +233,7 @@ class OracleSim:
             self.ApplyUpdate(fs, gam0, gam1, bdt)
         for fs in self.fluids:
             self.FluxSource(fs, bdt)
+        self.ApplySources(bdt)
         for fs in self.fluids:
             self.SetAuxillaryFields(fs)
             self.ConsToPrim(fs)

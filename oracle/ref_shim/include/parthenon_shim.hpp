@@ -261,6 +261,10 @@ class SparsePackShim {
     return (*this)(b, type_off[shim_type_id<V>()] + v.idx, k, j, i);
   }
   template <class V, class = decltype(V::name())>
+  Real &flux(int b, int dir, const V &v, int k, int j, int i) const {
+    return flux(b, dir, type_off[shim_type_id<V>()] + v.idx, k, j, i);
+  }
+  template <class V, class = decltype(V::name())>
   int GetSize(int, const V &) const {
     return type_size[shim_type_id<V>()];
   }

@@ -16,6 +16,9 @@
 #include "derived/fill_derived.cpp"
 #include "utils/fluxes/fluid_fluxes.hpp"
 #include "utils/integrators/artemis_integrator.hpp"
+// source terms between FluxSource and SetAuxillaryFields
+#include "rotating_frame/rotating_frame_impl.hpp"
+#include "gravity/uniform.cpp"
 
 #include "../artemis_oracle.h"
 
@@ -351,5 +354,44 @@ int ar_num_threads(void) {
 #else
   return 1;
 #endif
+}
+
+// ---- pointwise source terms: the reference's own kernels over BOTH fluids of one MeshData ---
+static void SetBoth(Ctx &c, const ao_grid *g, const ao_fluid *gas, double *gprim, double *gcons,
+                    const ao_fluid *dust, double *dprim, double *dcons) {
+  SetGrid(c, g);
+  if (gas) {
+    SetFluidPkg(c, g, gas);
+    AddSlab(c, g, gas, true, gprim, nullptr, nullptr, nullptr);
+    AddSlab(c, g, gas, false, gcons, nullptr, nullptr, nullptr);
+  }
+  if (dust) {
+    SetFluidPkg(c, g, dust);
+    AddSlab(c, g, dust, true, dprim, nullptr, nullptr, nullptr);
+    AddSlab(c, g, dust, false, dcons, nullptr, nullptr, nullptr);
+  }
+}
+
+void ar_shearing_box(const ao_grid *g, const ao_fluid *gas, double *gprim, double *gcons,
+                     const ao_fluid *dust, double *dprim, double *dcons, double dt, double om0,
+                     double qshear) {
+  Ctx c;
+  SetBoth(c, g, gas, gprim, gcons, dust, dprim, dcons);
+  RotatingFrame::ShearingBoxImpl(&c.md, om0, qshear, gas != nullptr, dust != nullptr, dt);
+}
+
+void ar_uniform_gravity(const ao_grid *g, const ao_fluid *gas, double *gprim, double *gcons,
+                        const ao_fluid *dust, double *dprim, double *dcons, double dt, double gx1,
+                        double gx2, double gx3) {
+  Ctx c;
+  SetBoth(c, g, gas, gprim, gcons, dust, dprim, dcons);
+  auto grav = std::make_shared<StateDescriptor>();
+  grav->AddParam<Real>("gx1", gx1);
+  grav->AddParam<Real>("gx2", gx2);
+  grav->AddParam<Real>("gx3", gx3);
+  c.mesh.packages.pkgs["gravity"] = grav;
+  GeomDispatch(g->geom, [&](auto G) {
+    Gravity::UniformGravity<decltype(G)::value>(&c.md, 0.0, dt);
+  });
 }
 }  // extern "C"

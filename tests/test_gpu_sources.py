@@ -1,0 +1,90 @@
+"""GPU parity of the pointwise source terms and of the split stage that hosts
+them: ab200_fused_stage(AB200_STAGE_DEFER_C2P) -> ab200_uniform_gravity / ab200_shearing_box /
+ab200_drag_simple -> ab200_finish_stage, against the oracle (gravity and shearing box pinned bit
+for bit to the reference's own code, tests/test_sources_oracle.py)."""
+import numpy as np
+import pytest
+
+from artemis_b200.driver import ArtemisDriver
+from artemis_b200.enums import BoundaryFlag, Coordinates
+from artemis_b200.meshdata import MeshData
+from oracle.oracle_py import OracleSim
+from tests.helpers import dust_params, gas_params, make_mesh, random_prim, zone_rel_err
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    (Coordinates.cartesian, [("gravity", 0.3, -0.2, 0.1)], "rk2"),
+    (Coordinates.cartesian, [("shearing_box", 1.0, 1.5), ("gravity", 0.0, 0.0, -0.4)], "vl2"),
+    (Coordinates.cartesian, [("drag", [1e-3, 0.5])], "rk2"),
+    (Coordinates.cylindrical, [("gravity", -0.5, 0.0, 0.2), ("drag", [0.05, 2.0])], "rk3"),
+    (Coordinates.spherical3D, [("gravity", -0.7, 0.0, 0.0)], "rk2"),
+]
+
+
+def _run(coords, sources, integ, mode, variant, ncyc=2):
+    bcs = (BoundaryFlag.outflow,) * 6 if coords != Coordinates.cartesian else None
+    mesh = make_mesh(coords, 3, bcs=bcs)
+    gp, dp = gas_params(coords, "ppm", "hllc"), dust_params(coords, "plm", "hlle", S=2)
+    prim, dprim = random_prim(mesh, gp, seed=71), random_prim(mesh, dp, seed=72)
+    osim = OracleSim(mesh, gas=gp, dust=dp, integrator=integ)
+    osim.gas.prim[:] = prim
+    osim.dust.prim[:] = dprim
+    osim.sources = list(sources)
+    osim.nlim = ncyc
+    osim.initialize()
+    osim.run()
+    md = MeshData(mesh, gas=gp, dust=dp, variant=variant, materialize_fluxes=(mode == "tasks"))
+    md.gas.prim.set(prim)
+    md.dust.prim.set(dprim)
+    drv = ArtemisDriver(md, integ, mode=mode, nlim=ncyc, sources=sources)
+    drv.Initialize()
+    drv.Execute()
+    out = [(f.u0.get(), f.prim.get(), of.u0, of.prim, of.fp) for f, of in zip(md.fluids, osim.fluids)]
+    assert md.launch_count() > 0 and drv.ncycle == osim.ncycle == ncyc
+    md.close()
+    return out, drv, osim
+
+
+@pytest.mark.parametrize("coords,sources,integ", CASES)
+def test_tasks_with_sources_strict_bit_identical(coords, sources, integ):
+    out, drv, osim = _run(coords, sources, integ, "tasks", "strict")
+    assert drv.dt == osim.dt
+    for u0, w, ou0, ow, _ in out:
+        assert np.array_equal(u0, ou0) and np.array_equal(w, ow)
+
+
+@pytest.mark.parametrize("coords,sources,integ", CASES)
+def test_split_fused_stage_with_sources_within_1e12(coords, sources, integ):
+    """fast build, fused passes + deferred C2P, two cycles"""
+    out, drv, osim = _run(coords, sources, integ, "fused", "fast", ncyc=1)
+    for u0, w, ou0, ow, fp in out:
+        assert zone_rel_err(u0, ou0, fp, "cons") <= 1e-12
+        assert zone_rel_err(w, ow, fp, "prim") <= 1e-12
+
+
+def test_drag_on_the_gpu_conserves_total_momentum():
+    """tst/scripts/drag/drag.py:135-137: total (gas + dust) momentum conserved to 1e-13."""
+    mesh = make_mesh(Coordinates.cartesian, 3)
+    gp = gas_params(Coordinates.cartesian, "plm", "hlle")
+    dp = dust_params(Coordinates.cartesian, "plm", "hlle", S=4)
+    prim = np.zeros(mesh.shape(6))
+    prim[:, 0], prim[:, 1], prim[:, 5] = 10.0, 1.0, 1.0
+    prim[:, 4] = gp.gm1 * 10.0
+    dprim = np.zeros(mesh.shape(16))
+    dprim[:, :4] = 0.01
+    md = MeshData(mesh, gas=gp, dust=dp, materialize_fluxes=False)
+    md.gas.prim.set(prim)
+    md.dust.prim.set(dprim)
+    drv = ArtemisDriver(md, "rk2", mode="fused", nlim=40, sources=[("drag", [1e-3, 1e-2, 1e-1, 1.0])])
+    drv.Initialize()
+    sl = (slice(None),) + mesh.interior()
+    gu, du = md.gas.u0.get(), md.dust.u0.get()
+    p0 = gu[:, 1][sl] + sum(du[:, 4 + 3 * n][sl] for n in range(4))
+    drv.Execute()
+    gu, du = md.gas.u0.get(), md.dust.u0.get()
+    p1 = gu[:, 1][sl] + sum(du[:, 4 + 3 * n][sl] for n in range(4))
+    assert np.max(np.abs(p1 - p0) / np.abs(p0)) <= 1e-13
+    vd = md.dust.prim.get()
+    assert 0.0 < np.mean(vd[:, 4 + 9][sl]) < np.mean(vd[:, 4][sl])   # tau = 1 lags tau = 1e-3
+    md.close()

@@ -1,0 +1,83 @@
+"""Pointwise source terms between FluxSource and SetAuxillaryFields:
+the oracle's restatement of Gravity::UniformGravity (src/gravity/uniform.cpp:28-90) and
+RotatingFrame::ShearingBoxImpl (src/rotating_frame/rotating_frame_impl.hpp:28-94) against the
+reference's OWN code compiled in oracle/_ref -- bit for bit, all geometries, gas + dust, over a
+whole rk2 cycle; and the reference's own checks on the drag restatement (no reference build of
+drag.hpp here): total momentum conserved to 1e-13 and relaxation to the common velocity
+(tst/scripts/drag/drag.py:57-137)."""
+import numpy as np
+import pytest
+
+from artemis_b200.enums import BoundaryFlag, Coordinates
+from oracle import ref_py
+from oracle.oracle_py import OracleSim
+from tests.helpers import dust_params, gas_params, make_mesh, random_prim
+
+needs_ref = pytest.mark.skipif(not ref_py.available(), reason="oracle/_ref not built")
+
+
+def _pair(coords, sources, integ="rk2", ncyc=1):
+    bcs = (BoundaryFlag.outflow,) * 6 if coords != Coordinates.cartesian else None
+    mesh = make_mesh(coords, 3, bcs=bcs)
+    gp, dp = gas_params(coords, "plm", "hlle"), dust_params(coords, "plm", "hlle", S=2)
+    sims = []
+    for cls in (OracleSim, ref_py.RefSim):
+        sim = cls(mesh, gas=gp, dust=dp, integrator=integ)
+        sim.gas.prim[:] = random_prim(mesh, gp, seed=61)
+        sim.dust.prim[:] = random_prim(mesh, dp, seed=62)
+        sim.sources = list(sources)
+        sim.nlim = ncyc
+        sim.initialize()
+        sim.run()
+        sims.append(sim)
+    return sims
+
+
+@needs_ref
+@pytest.mark.parametrize("coords", [Coordinates.cartesian, Coordinates.cylindrical,
+                                    Coordinates.spherical3D, Coordinates.axisymmetric])
+def test_uniform_gravity_restatement_is_bit_identical_to_reference_code(coords):
+    o, r = _pair(coords, [("gravity", 0.3, -0.2, 0.1)])
+    for fo, fr in zip(o.fluids, r.fluids):
+        assert np.array_equal(fo.u0, fr.u0) and np.array_equal(fo.prim, fr.prim)
+    # and the source really acted
+    base, _ = _pair(coords, [])
+    assert not np.array_equal(base.gas.u0, o.gas.u0)
+
+
+@needs_ref
+def test_shearing_box_restatement_is_bit_identical_to_reference_code():
+    o, r = _pair(Coordinates.cartesian, [("shearing_box", 1.0, 1.5), ("gravity", 0.0, 0.0, -0.4)],
+                 integ="vl2", ncyc=2)
+    for fo, fr in zip(o.fluids, r.fluids):
+        assert np.array_equal(fo.u0, fr.u0) and np.array_equal(fo.prim, fr.prim)
+
+
+def test_drag_conserves_total_momentum_and_relaxes_to_the_common_velocity():
+    """inputs/drag/simple_drag.in physics: constant stopping times, gas rho 10 v (1,0,0), four
+    dust species rho 0.01 at rest, uniform state => no fluxes, only the implicit drag update."""
+    mesh = make_mesh(Coordinates.cartesian, 3)
+    gp = gas_params(Coordinates.cartesian, "plm", "hlle")
+    dp = dust_params(Coordinates.cartesian, "plm", "hlle", S=4)
+    sim = OracleSim(mesh, gas=gp, dust=dp)
+    sim.gas.prim[:] = 0.0
+    sim.gas.prim[:, 0] = 10.0
+    sim.gas.prim[:, 1] = 1.0
+    sim.gas.prim[:, 5] = 1.0
+    sim.gas.prim[:, 4] = gp.gm1 * 10.0
+    sim.dust.prim[:] = 0.0
+    sim.dust.prim[:, :4] = 0.01
+    tau = [1e-3, 1e-2, 1e-1, 1.0]
+    sim.sources = [("drag", tau)]
+    sim.initialize()
+    sl = (slice(None),) + mesh.interior()
+    p0 = sim.gas.u0[:, 1][sl] + sum(sim.dust.u0[:, 4 + 3 * n][sl] for n in range(4))
+    sim.nlim = 40
+    sim.run()
+    p1 = sim.gas.u0[:, 1][sl] + sum(sim.dust.u0[:, 4 + 3 * n][sl] for n in range(4))
+    assert np.max(np.abs(p1 - p0) / np.abs(p0)) <= 1e-13        # drag.py:135-137
+    vd = [float(np.mean(sim.dust.prim[:, 4 + 3 * n][sl])) for n in range(4)]
+    vg = float(np.mean(sim.gas.prim[:, 1][sl]))
+    assert 0.0 < vd[3] < min(vd[:3])                             # the longest tau lags behind
+    vcom = 10.0 / (10.0 + 0.04)
+    assert abs(vd[0] - vg) < 1e-4 and abs(vg - vcom) < 1e-2
