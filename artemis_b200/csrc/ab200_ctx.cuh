@@ -98,6 +98,9 @@ struct ab200_ctx {
     void *dev = nullptr;
   };
   std::vector<HaloCacheEntry> halo_cache;
+  // source terms applied by the device-resident drivers (ab200_configure_sources)
+  ab200_sources_desc sources{};
+  bool has_sources = false;
   // multi-rank transport (comm.cu): NCCL communicator, comm stream, planned exchange
   void *comm_state = nullptr;
 };
@@ -129,6 +132,8 @@ int launch_exchange(ab200_ctx *c, int fluid);
 int launch_physical_bcs(ab200_ctx *c, int fluid);
 int launch_fill_ghosts(ab200_ctx *c, int fluid, int remote_pass);
 bool topology_is_local(const ab200_ctx *c);
+// one stage of the device-resident drivers: fused stage (+ sources + finish when configured)
+int run_stage(ab200_ctx *c, double g0, double g1, double beta, int pcm, int first, int last);
 int launch_halo(ab200_ctx *c, const ab200_bnd_desc *bnd, int n, int unpack);
 int launch_set_global_dt(ab200_ctx *c, double tlim, int advance_time);
 int ensure_scratch(ab200_ctx *c, int fluid, bool need_flux, bool need_u1);

@@ -427,9 +427,7 @@ int ab200_run_cycles_mr(ab200_ctx *c, int integrator, int ncycles, double tlim) 
   for (int cyc = 0; cyc < ncycles; ++cyc) {
     for (int s = 0; s < nst; ++s) {
       const int pcm = (s == 0 && integrator == 2);
-      const int flags = AB200_STAGE_DEVICE_DT | AB200_STAGE_PINGPONG |
-                        (s == nst - 1 ? AB200_STAGE_REDUCE_DT : 0);
-      AB_TRY(ab200_fused_stage(c, st[s].g0, st[s].g1, st[s].b, 0.0, pcm, s == 0, flags));
+      AB_TRY(run_stage(c, st[s].g0, st[s].g1, st[s].b, pcm, s == 0, s == nst - 1));
       if (remote) AB_TRY(ab200_comm_exchange_begin(c));
       AB_TRY(ab200_fill_ghosts_local(c));
       if (remote) {

@@ -44,9 +44,7 @@ extern "C" int ab200_run_cycles(ab200_ctx *c, int integrator, int ncycles, doubl
   for (int cyc = 0; cyc < ncycles; ++cyc) {
     for (int s = 0; s < nst; ++s) {
       const int pcm = (s == 0 && integrator == 2);  // vl2 stage 1: artemis_driver.cpp:182
-      const int flags = AB200_STAGE_DEVICE_DT | AB200_STAGE_PINGPONG |
-                        (s == nst - 1 ? AB200_STAGE_REDUCE_DT : 0);
-      AB_TRY(ab200_fused_stage(c, st[s].g0, st[s].g1, st[s].b, 0.0, pcm, s == 0, flags));
+      AB_TRY(run_stage(c, st[s].g0, st[s].g1, st[s].b, pcm, s == 0, s == nst - 1));
       AB_TRY(ab200_fill_ghosts(c));
     }
     AB_TRY(ab200_set_global_timestep_device(c, tlim, 1));

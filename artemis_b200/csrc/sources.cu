@@ -38,7 +38,9 @@ struct TwoFluids {
 
 template <int GEOM>
 __global__ void __launch_bounds__(kThreads)
-k_uniform_gravity(GridDev g, TwoFluids tf, double dt, double gx1, double gx2, double gx3) {
+k_uniform_gravity(GridDev g, TwoFluids tf, double dt_host, const double *dt_dev, double beta,
+                  double gx1, double gx2, double gx3) {
+  const double dt = dt_dev ? beta * *dt_dev : dt_host;
   const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)g.nb * nkr * njr * nir) return;
@@ -66,7 +68,9 @@ k_uniform_gravity(GridDev g, TwoFluids tf, double dt, double gx1, double gx2, do
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_shearing_box(GridDev g, TwoFluids tf, double dt, double om0, double qshear) {
+k_shearing_box(GridDev g, TwoFluids tf, double dt_host, const double *dt_dev, double beta,
+               double om0, double qshear) {
+  const double dt = dt_dev ? beta * *dt_dev : dt_host;
   const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)g.nb * nkr * njr * nir) return;
@@ -111,7 +115,9 @@ struct DragTau {
 // explicit zeros so the operation order (and the strict build's bits) are the reference's.
 template <int GEOM>
 __global__ void __launch_bounds__(kThreads)
-k_drag_simple(GridDev g, FluidDev fg, FluidDev fd_, double dt, DragTau tp) {
+k_drag_simple(GridDev g, FluidDev fg, FluidDev fd_, double dt_host, const double *dt_dev,
+              double beta, DragTau tp) {
+  const double dt = dt_dev ? beta * *dt_dev : dt_host;
   const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)g.nb * nkr * njr * nir) return;
@@ -202,21 +208,26 @@ using namespace ab200;
 
 extern "C" {
 
-int ab200_uniform_gravity(ab200_ctx *c, double dt, double gx1, double gx2, double gx3) {
+static int gravity_impl(ab200_ctx *c, double dt, const double *dt_dev, double beta, double gx1,
+                        double gx2, double gx3) {
   AB_ENTER_S(c)
   TwoFluids tf{};
   AB_TRY(two_fluids(c, tf));
   const GridDev &g = c->g;
   int rc = dispatch_geom_s(g.geom, [&](auto G) {
-    k_uniform_gravity<decltype(G)::value><<<grid_s(g), kThreads, 0, c->stream>>>(g, tf, dt, gx1, gx2, gx3);
+    k_uniform_gravity<decltype(G)::value><<<grid_s(g), kThreads, 0, c->stream>>>(g, tf, dt, dt_dev, beta, gx1, gx2, gx3);
     return AB200_OK;
   });
   c->launches++;
   AB_CUDA(cudaGetLastError());
   return rc;
 }
+int ab200_uniform_gravity(ab200_ctx *c, double dt, double gx1, double gx2, double gx3) {
+  return gravity_impl(c, dt, nullptr, 0.0, gx1, gx2, gx3);
+}
 
-int ab200_shearing_box(ab200_ctx *c, double dt, double omega, double qshear) {
+static int shearing_impl(ab200_ctx *c, double dt, const double *dt_dev, double beta, double omega,
+                         double qshear) {
   AB_ENTER_S(c)
   // src/rotating_frame/rotating_frame.cpp:31-37
   AB_REQUIRE(omega != 0.0, AB200_EINVAL, "rotating_frame/omega cannot be zero!");
@@ -225,13 +236,17 @@ int ab200_shearing_box(ab200_ctx *c, double dt, double omega, double qshear) {
              "RotatingFrameImpl, which stays on the reference path)");
   TwoFluids tf{};
   AB_TRY(two_fluids(c, tf));
-  k_shearing_box<<<grid_s(c->g), kThreads, 0, c->stream>>>(c->g, tf, dt, omega, qshear);
+  k_shearing_box<<<grid_s(c->g), kThreads, 0, c->stream>>>(c->g, tf, dt, dt_dev, beta, omega, qshear);
   c->launches++;
   AB_CUDA(cudaGetLastError());
   return AB200_OK;
 }
+int ab200_shearing_box(ab200_ctx *c, double dt, double omega, double qshear) {
+  return shearing_impl(c, dt, nullptr, 0.0, omega, qshear);
+}
 
-int ab200_drag_simple(ab200_ctx *c, double dt, int ntau, const double *tau) {
+static int drag_impl(ab200_ctx *c, double dt, const double *dt_dev, double beta, int ntau,
+                     const double *tau) {
   AB_ENTER_S(c)
   AB_REQUIRE(c->fl[0].bound && c->fl[1].bound, AB200_ESTATE,
              "ab200_drag_simple: gas and dust must both be bound");
@@ -244,12 +259,47 @@ int ab200_drag_simple(ab200_ctx *c, double dt, int ntau, const double *tau) {
   for (int n = 0; n < ntau; ++n) tp.tau[n] = tau[n];
   const GridDev &g = c->g;
   int rc = dispatch_geom_s(g.geom, [&](auto G) {
-    k_drag_simple<decltype(G)::value><<<grid_s(g), kThreads, 0, c->stream>>>(g, c->fl[0].d, c->fl[1].d, dt, tp);
+    k_drag_simple<decltype(G)::value><<<grid_s(g), kThreads, 0, c->stream>>>(g, c->fl[0].d, c->fl[1].d, dt, dt_dev, beta, tp);
     return AB200_OK;
   });
   c->launches++;
   AB_CUDA(cudaGetLastError());
   return rc;
 }
+int ab200_drag_simple(ab200_ctx *c, double dt, int ntau, const double *tau) {
+  return drag_impl(c, dt, nullptr, 0.0, ntau, tau);
+}
+
+
+int ab200_configure_sources(ab200_ctx *c, const ab200_sources_desc *src) {
+  AB_REQUIRE(c, AB200_EINVAL, "null context");
+  if (!src) {
+    c->sources = ab200_sources_desc{};
+    c->has_sources = false;
+    return AB200_OK;
+  }
+  AB_REQUIRE(!src->drag || (src->ntau >= 1 && src->ntau <= 16), AB200_EINVAL,
+             "ab200_configure_sources: 1..16 stopping times");
+  c->sources = *src;
+  c->has_sources = src->gravity || src->shearing_box || src->drag;
+  return AB200_OK;
+}
 
 }  // extern "C"
+
+namespace ab200 {
+// ArtemisDriver::StepTasks for one stage on the device-resident path
+// (src/artemis_driver.cpp:184-255): dt comes from the device scalar.
+int run_stage(ab200_ctx *c, double g0, double g1, double beta, int pcm, int first, int last) {
+  const int base = AB200_STAGE_DEVICE_DT | AB200_STAGE_PINGPONG;
+  if (!c->has_sources)
+    return ab200_fused_stage(c, g0, g1, beta, 0.0, pcm, first, base | (last ? AB200_STAGE_REDUCE_DT : 0));
+  AB_TRY(ab200_fused_stage(c, g0, g1, beta, 0.0, pcm, first, base | AB200_STAGE_DEFER_C2P));
+  // beta * dt is formed on the device from the dt scalar: no host round trip
+  const ab200_sources_desc &s = c->sources;
+  if (s.gravity) AB_TRY(gravity_impl(c, 0.0, c->d_time, beta, s.g[0], s.g[1], s.g[2]));
+  if (s.shearing_box) AB_TRY(shearing_impl(c, 0.0, c->d_time, beta, s.omega, s.qshear));
+  if (s.drag) AB_TRY(drag_impl(c, 0.0, c->d_time, beta, s.ntau, s.tau));
+  return ab200_finish_stage(c, last ? AB200_STAGE_REDUCE_DT : 0);
+}
+}  // namespace ab200

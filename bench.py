@@ -48,6 +48,8 @@ def parse():
                          "--mesh^3 zones IN TOTAL split over the GPUs (strong scaling)")
     ap.add_argument("--mesh", type=int, default=512, help="config 3: total zones per direction")
     ap.add_argument("--dust-species", type=int, default=4)
+    ap.add_argument("--no-drag", action="store_true",
+                    help="config 3: leave Drag::DragSource out (it then stays on the reference path)")
     ap.add_argument("--transport", default="native", choices=["native", "torch"],
                     help="N > 1: 'native' = the C ABI's own NCCL transport (ab200_run_cycles_mr), "
                          "'torch' = torch.distributed driven from Python (round-1 path)")
@@ -284,6 +286,14 @@ def main_config3(args):
     md.set_time_state(drv.dt)
     md.call("ab200_set_ghost_cons_lazy", 1)
     big = float(np.finfo(np.float64).max)
+    if not args.no_drag:   # <drag/dust> type = constant, one stopping time per species
+        import ctypes as C
+        from artemis_b200 import capi
+        sd = capi.SourcesDesc()
+        sd.drag, sd.ntau = 1, S
+        for n in range(S):
+            sd.tau[n] = 10.0 ** (n - 3)
+        md.call("ab200_configure_sources", C.byref(sd))
 
     def one_step():
         md.call("ab200_run_cycles_mr" if world > 1 else "ab200_run_cycles", 1, 1, big)
@@ -331,7 +341,9 @@ def main_config3(args):
                "config": {"workload": f"config 3: gas + {S} dust species (inputs/drag state + seeded "
                                       f"perturbation), PLM+HLLE, rk2, periodic, {M}^3 zones in TOTAL in "
                                       f"{B}^3 MeshBlocks split over {world} GPU(s) (strong scaling); "
-                                      "drag on the reference path",
+                                      + ("Drag::DragSource stays on the reference path" if args.no_drag
+                                         else "implicit gas-dust drag (constant stopping times) every stage, "
+                                              "split stage: passes -> drag -> SetAux/C2P/P2C"),
                           "zones_total": zones, "ranks": list(lay), "stage_path": md.stage_path(),
                           "l2": "state >> 126 MB L2, no flush needed"},
                "roofline": {"bound": "hbm", "achieved": value * alg / world / 1e9, "peak": peak,

@@ -191,6 +191,15 @@ int ab200_finish_stage(ab200_ctx *ctx, int flags);
 int ab200_uniform_gravity(ab200_ctx *ctx, double dt, double gx1, double gx2, double gx3);
 int ab200_shearing_box(ab200_ctx *ctx, double dt, double omega, double qshear);
 int ab200_drag_simple(ab200_ctx *ctx, double dt, int ntau, const double *tau);
+/* Source terms the device-resident drivers (ab200_run_cycles, ab200_run_cycles_mr,
+ * ab200_cycles_host) apply every stage, in the reference's task order gravity -> rotating frame
+ * -> drag; NULL or all-zero switches them off (the stage then runs un-split). */
+typedef struct ab200_sources_desc {
+  int gravity;       double g[3];            /* Gravity::UniformGravity          */
+  int shearing_box;  double omega, qshear;   /* RotatingFrame::ShearingBoxImpl   */
+  int drag;          int ntau; double tau[16]; /* Drag::SimpleDragSourceImpl      */
+} ab200_sources_desc;
+int ab200_configure_sources(ab200_ctx *ctx, const ab200_sources_desc *src);
 
 /* Which kernels ab200_fused_stage runs on meshes where both exist (3-D Cartesian, TMA-able
  * arrays); every other mesh always takes the directional passes.

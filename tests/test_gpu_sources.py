@@ -88,3 +88,47 @@ def test_drag_on_the_gpu_conserves_total_momentum():
     vd = md.dust.prim.get()
     assert 0.0 < np.mean(vd[:, 4 + 9][sl]) < np.mean(vd[:, 4][sl])   # tau = 1 lags tau = 1e-3
     md.close()
+
+
+@pytest.mark.parametrize("variant", ["strict", "fast"])
+def test_device_resident_cycles_with_configured_sources(variant):
+    """ab200_configure_sources + ab200_run_cycles (split stages, beta*dt formed on the device)
+    == the host-driven fused loop with the same sources; strict: bit for bit."""
+    import ctypes as C
+    from artemis_b200 import capi
+    coords = Coordinates.cartesian
+    mesh = make_mesh(coords, 3)
+    gp, dp = gas_params(coords, "ppm", "hllc"), dust_params(coords, "plm", "hlle", S=2)
+    prim, dprim = random_prim(mesh, gp, seed=81), random_prim(mesh, dp, seed=82)
+    sources = [("gravity", 0.1, 0.0, -0.3), ("shearing_box", 0.8, 1.5), ("drag", [0.02, 0.7])]
+    ncyc = 3
+    md1 = MeshData(mesh, gas=gp, dust=dp, variant=variant, materialize_fluxes=False)
+    md1.gas.prim.set(prim)
+    md1.dust.prim.set(dprim)
+    d1 = ArtemisDriver(md1, "rk2", mode="fused", nlim=ncyc, sources=sources)
+    d1.Initialize()
+    d1.Execute()
+    md2 = MeshData(mesh, gas=gp, dust=dp, variant=variant, materialize_fluxes=False)
+    md2.gas.prim.set(prim)
+    md2.dust.prim.set(dprim)
+    d2 = ArtemisDriver(md2, "rk2", mode="fused")
+    d2.Initialize()
+    sd = capi.SourcesDesc()
+    sd.gravity, sd.g[0], sd.g[1], sd.g[2] = 1, 0.1, 0.0, -0.3
+    sd.shearing_box, sd.omega, sd.qshear = 1, 0.8, 1.5
+    sd.drag, sd.ntau, sd.tau[0], sd.tau[1] = 1, 2, 0.02, 0.7
+    md2.call("ab200_configure_sources", C.byref(sd))
+    md2.set_time_state(d2.dt)
+    md2.call("ab200_run_cycles", 1, ncyc, float(np.finfo(np.float64).max))
+    ts = md2.time_state()
+    assert int(ts[3]) == ncyc
+    for f1, f2 in zip(md1.fluids, md2.fluids):
+        if variant == "strict":
+            assert np.array_equal(f1.u0.get(), f2.u0.get())
+            assert np.array_equal(f1.prim.get(), f2.prim.get())
+        else:
+            assert zone_rel_err(f2.u0.get(), f1.u0.get(), f1.fp, "cons") <= 1e-12
+    if variant == "strict":
+        assert ts[0] == d1.dt and ts[2] == d1.time
+    md1.close()
+    md2.close()
