@@ -98,6 +98,10 @@ struct ab200_ctx {
     void *dev = nullptr;
   };
   std::vector<HaloCacheEntry> halo_cache;
+  // block subsets for compute / communication overlap: [0] surface blocks (touch a face owned
+  // by another rank, AB200_BC_NONE), [1] all other blocks; built by ab200_set_topology
+  int *d_blist[2] = {nullptr, nullptr};
+  int n_blist[2] = {0, 0};
   // source terms applied by the device-resident drivers (ab200_configure_sources)
   ab200_sources_desc sources{};
   bool has_sources = false;
@@ -117,7 +121,8 @@ int launch_deep_copy(ab200_ctx *c, int fluid);
 int launch_estimate_dt(ab200_ctx *c, int fluid, double *d_out, int combine);
 int launch_fused_stage(ab200_ctx *c, int fluid, double gam0, double gam1, double beta,
                        double dt, int pcm, int stage1_copy, int use_device_dt,
-                       unsigned long long *dt_min, int defer_c2p = 0);
+                       unsigned long long *dt_min, int defer_c2p = 0, int subset = 0);
+bool fused_supports_subsets(const ab200_ctx *c);
 bool fused_folds_dt(const ab200_ctx *c);
 // single-pass stage (sweep.cuh / sweep_host.cu)
 bool sweep_eligible(ab200_ctx *c, int fluid);

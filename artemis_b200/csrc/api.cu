@@ -192,6 +192,8 @@ int ab200_destroy(ab200_ctx *c) {
   free_all(c->host_path_allocs);
   for (auto &e : c->halo_cache) cudaFree(e.dev);
   c->halo_cache.clear();
+  for (int q = 0; q < 2; ++q)
+    if (c->d_blist[q]) cudaFree(c->d_blist[q]);
   cudaFree(c->d_time);
   cudaFree(c->d_red);
   cudaFreeHost(c->h_pinned);
@@ -519,8 +521,15 @@ int ab200_fused_stage(ab200_ctx *c, double gam0, double gam1, double beta, doubl
   AB_REQUIRE(!stage1_copy || (gam0 == 0.0 && gam1 == 1.0), AB200_EINVAL,
              "ab200_fused_stage: stage1_copy requires gam0 == 0 and gam1 == 1");
   AB_REQUIRE((flags & ~(AB200_STAGE_DEVICE_DT | AB200_STAGE_REDUCE_DT | AB200_STAGE_PINGPONG |
-                        AB200_STAGE_DEFER_C2P)) == 0,
+                        AB200_STAGE_DEFER_C2P | AB200_STAGE_SURFACE | AB200_STAGE_INTERIOR)) == 0,
              AB200_EINVAL, "ab200_fused_stage: unknown flag");
+  const int subset = (flags & AB200_STAGE_SURFACE) ? 1 : ((flags & AB200_STAGE_INTERIOR) ? 2 : 0);
+  AB_REQUIRE(!((flags & AB200_STAGE_SURFACE) && (flags & AB200_STAGE_INTERIOR)), AB200_EINVAL,
+             "ab200_fused_stage: SURFACE and INTERIOR are two separate calls");
+  AB_REQUIRE(!subset || (c->topo.set && fused_supports_subsets(c)), AB200_ESTATE,
+             "ab200_fused_stage: block subsets need ab200_set_topology and a >= 2-D mesh");
+  AB_REQUIRE(!subset || (c->n_blist[0] > 0 && c->n_blist[1] > 0), AB200_ESTATE,
+             "ab200_fused_stage: SURFACE / INTERIOR need both block subsets to be non-empty");
   const int use_device_dt = (flags & AB200_STAGE_DEVICE_DT) != 0;
   const int defer = (flags & AB200_STAGE_DEFER_C2P) != 0;
   // deferred C2P: the timestep is estimated by ab200_finish_stage, from the final primitives
@@ -528,13 +537,15 @@ int ab200_fused_stage(ab200_ctx *c, double gam0, double gam1, double beta, doubl
   const int pingpong = (flags & AB200_STAGE_PINGPONG) != 0;
   // per-fluid raw minimum (bit pattern of a positive double), reset to a huge finite value
   unsigned long long *slots = reinterpret_cast<unsigned long long *>(c->d_red + 3072);
-  if (reduce_dt) AB_CUDA(cudaMemsetAsync(slots, 0x7f, 2 * sizeof(unsigned long long), c->stream));
+  // (a SURFACE call opens the reduction, the INTERIOR call that follows closes it)
+  if (reduce_dt && subset != 2)
+    AB_CUDA(cudaMemsetAsync(slots, 0x7f, 2 * sizeof(unsigned long long), c->stream));
   int any = 0;
   for (int f = 0; f < 2; ++f) {
     if (!c->fl[f].bound) continue;
     AB_TRY(ensure_scratch(c, f, false, true));
     bool fold;
-    if (!defer && sweep_eligible(c, f)) {
+    if (!defer && !subset && sweep_eligible(c, f)) {
       // single-pass stage (sweep.cuh): reads the current primitive set, writes the other one
       fold = reduce_dt;
       AB_TRY(launch_sweep_stage(c, f, gam0, gam1, beta, dt, pcm, stage1_copy, use_device_dt,
@@ -544,9 +555,9 @@ int ab200_fused_stage(ab200_ctx *c, double gam0, double gam1, double beta, doubl
       AB_TRY(sync_prim_home(c, f, 0));
       fold = reduce_dt && fused_folds_dt(c);
       AB_TRY(launch_fused_stage(c, f, gam0, gam1, beta, dt, pcm, stage1_copy, use_device_dt,
-                                fold ? slots + f : nullptr, defer));
+                                fold ? slots + f : nullptr, defer, subset));
     }
-    if (reduce_dt) {  // new_dt = min over fluids of cfl * min dt  (EstimateTimestepMesh)
+    if (reduce_dt && subset != 1) {  // new_dt = min over fluids of cfl * min dt  (EstimateTimestepMesh)
       if (fold)
         AB_TRY(launch_finish_dt(c, reinterpret_cast<const double *>(slots + f), 1, c->fl[f].d.cfl,
                                 c->d_time + 1, any));
@@ -603,6 +614,28 @@ int ab200_set_topology(ab200_ctx *c, int nbx, int nby, int nbz, const int bc[6])
   c->topo.set = true;
   c->topo.nbx = nbx; c->topo.nby = nby; c->topo.nbz = nbz;
   for (int i = 0; i < 6; ++i) c->topo.bc[i] = bc[i];
+  // surface / interior block lists (the surface is staged first so that the remote exchange
+  // overlaps the interior blocks' stage, ab200_run_cycles_mr)
+  std::vector<int> lists[2];
+  const int nbd[3] = {nbx, nby, nbz};
+  for (int b = 0; b < c->g.nb; ++b) {
+    const int l[3] = {b % nbx, (b / nbx) % nby, b / (nbx * nby)};
+    bool surf = false;
+    for (int d = 0; d < 3; ++d) {
+      if (l[d] == 0 && bc[2 * d] == AB200_BC_NONE) surf = true;
+      if (l[d] == nbd[d] - 1 && bc[2 * d + 1] == AB200_BC_NONE) surf = true;
+    }
+    lists[surf ? 0 : 1].push_back(b);
+  }
+  for (int q = 0; q < 2; ++q) {
+    if (c->d_blist[q]) cudaFree(c->d_blist[q]);
+    c->d_blist[q] = nullptr;
+    c->n_blist[q] = (int)lists[q].size();
+    if (lists[q].empty()) continue;
+    AB_CUDA(cudaMalloc((void **)&c->d_blist[q], lists[q].size() * sizeof(int)));
+    AB_CUDA(cudaMemcpy(c->d_blist[q], lists[q].data(), lists[q].size() * sizeof(int),
+                       cudaMemcpyHostToDevice));
+  }
   return AB200_OK;
 }
 

@@ -17,6 +17,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -424,11 +425,28 @@ int ab200_run_cycles_mr(ab200_ctx *c, int integrator, int ncycles, double tlim) 
     ~Restore() { c->ghost_cons_lazy = v; }
   } restore{c, lazy_before};
   const bool remote = cs && cs->planned && !cs->peers.empty();
+  // Overlap: stage the blocks that touch another rank first, start the remote round as soon as
+  // they are done and run the interior blocks' stage underneath it.  Needs the directional
+  // passes (block subsets) for every bound fluid and no split-stage source terms.
+  bool split = remote && !c->has_sources && fused_supports_subsets(c) && c->n_blist[0] > 0 &&
+               c->n_blist[1] > 0 && !getenv("AB200_NO_OVERLAP");
+  for (int f = 0; f < 2 && split; ++f)
+    if (c->fl[f].bound && sweep_eligible(c, f)) split = false;
   for (int cyc = 0; cyc < ncycles; ++cyc) {
     for (int s = 0; s < nst; ++s) {
       const int pcm = (s == 0 && integrator == 2);
-      AB_TRY(run_stage(c, st[s].g0, st[s].g1, st[s].b, pcm, s == 0, s == nst - 1));
-      if (remote) AB_TRY(ab200_comm_exchange_begin(c));
+      if (split) {
+        const int flags = AB200_STAGE_DEVICE_DT | AB200_STAGE_PINGPONG |
+                          (s == nst - 1 ? AB200_STAGE_REDUCE_DT : 0);
+        AB_TRY(ab200_fused_stage(c, st[s].g0, st[s].g1, st[s].b, 0.0, pcm, s == 0,
+                                 flags | AB200_STAGE_SURFACE));
+        AB_TRY(ab200_comm_exchange_begin(c));
+        AB_TRY(ab200_fused_stage(c, st[s].g0, st[s].g1, st[s].b, 0.0, pcm, s == 0,
+                                 flags | AB200_STAGE_INTERIOR));
+      } else {
+        AB_TRY(run_stage(c, st[s].g0, st[s].g1, st[s].b, pcm, s == 0, s == nst - 1));
+        if (remote) AB_TRY(ab200_comm_exchange_begin(c));
+      }
       AB_TRY(ab200_fill_ghosts_local(c));
       if (remote) {
         AB_TRY(ab200_comm_exchange_end(c));

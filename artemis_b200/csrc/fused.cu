@@ -78,8 +78,8 @@ static int launch_march(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
   const GridDev &g = c->g;
   const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
   const int ncols = nir * (DIR == 2 ? nkr : njr);
-  dim3 grid((unsigned)((ncols + kMarchThreads - 1) / kMarchThreads), (unsigned)g.nb,
-            (unsigned)f.S);
+  dim3 grid((unsigned)((ncols + kMarchThreads - 1) / kMarchThreads),
+            (unsigned)(a.blist ? a.nbl : g.nb), (unsigned)f.S);
   if (a.last) k_march_pass<GEOM, FLUID, RS, RC, DIR, true><<<grid, kMarchThreads, 0, c->stream>>>(g, f, a);
   else k_march_pass<GEOM, FLUID, RS, RC, DIR, false><<<grid, kMarchThreads, 0, c->stream>>>(g, f, a);
   c->launches++;
@@ -97,7 +97,7 @@ static int launch_xchunk(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
   if (nseg > njr) nseg = njr;
   a.np = nseg;
   constexpr int NV = FLUID == AB200_GAS ? 6 : 4, NF = FLUID == AB200_GAS ? 8 : 4;
-  const long long nwarps = (long long)g.nb * f.S * nkr * nseg;
+  const long long nwarps = (long long)(a.blist ? a.nbl : g.nb) * f.S * nkr * nseg;
   const size_t shmem = sizeof(double) * kXcWarps * (2 * NV + NF) * 64;
   const unsigned grid = (unsigned)((nwarps + kXcWarps - 1) / kXcWarps);
   k_xchunk_pass<GEOM, FLUID, RS, RC><<<grid, kXcWarps * 32, shmem, c->stream>>>(g, f, a);
@@ -121,22 +121,39 @@ static bool use_march() {
 template <int GEOM, int FLUID, int RS, int RC>
 static int launch_dirs(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
   const int ndim = c->g.ndim;
+  AB_REQUIRE(!a.blist || (ndim >= 2 && use_xchunk() && use_march()), AB200_ESTATE,
+             "block subsets need the streaming / marching passes");
+  // Block subsets (AB200_STAGE_SURFACE / _INTERIOR) split only the LAST directional pass: the
+  // SURFACE call runs the earlier passes over every block and the last pass over the surface
+  // blocks, the INTERIOR call runs the last pass over the remaining blocks.  Passes of one
+  // block never read another block, so the order is free; the remote exchange then overlaps
+  // the interior share of the last pass (enough to hide it) at the price of ONE extra launch.
+  const int *blist = a.blist;
+  const int nbl = a.nbl;
+  const bool interior_call = blist && a.subset == 2;
+  a.blist = nullptr;
   const int copy = a.copy_u1;
   unsigned long long *dt_min = a.dt_min;
   a.dt_min = nullptr;  // only the marching kernel of the last direction folds the dt reduction
   const int fin = a.defer_c2p ? 0 : 1;  // deferred: SetAux / C2P run in ab200_finish_stage
   a.first = 1; a.last = fin * (ndim == 1); a.copy_u1 = copy;
-  if (ndim >= 2 && use_xchunk()) AB_TRY((launch_xchunk<GEOM, FLUID, RS, RC>(c, f, a)));
-  else AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 1>(c, f, a)));
+  if (!interior_call) {
+    if (ndim >= 2 && use_xchunk()) AB_TRY((launch_xchunk<GEOM, FLUID, RS, RC>(c, f, a)));
+    else AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 1>(c, f, a)));
+  }
   if (ndim >= 2) {
     a.first = 0; a.last = fin * (ndim == 2); a.copy_u1 = 0;
     a.dt_min = (ndim == 2 && fin) ? dt_min : nullptr;
-    if (use_march()) AB_TRY((launch_march<GEOM, FLUID, RS, RC, 2>(c, f, a)));
-    else AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 2>(c, f, a)));
+    if (ndim == 2) { a.blist = blist; a.nbl = nbl; }
+    if (ndim == 2 || !interior_call) {
+      if (use_march()) AB_TRY((launch_march<GEOM, FLUID, RS, RC, 2>(c, f, a)));
+      else AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 2>(c, f, a)));
+    }
   }
   if (ndim >= 3) {
     a.first = 0; a.last = fin; a.copy_u1 = 0;
     a.dt_min = fin ? dt_min : nullptr;
+    a.blist = blist; a.nbl = nbl;
     if (use_march()) AB_TRY((launch_march<GEOM, FLUID, RS, RC, 3>(c, f, a)));
     else AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 3>(c, f, a)));
   }

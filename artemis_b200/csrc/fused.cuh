@@ -38,6 +38,11 @@ struct FusedArgs {
   const double *dt_dev;  // if non-null: dt = *dt_dev
   int first, last, copy_u1;
   int defer_c2p;  // AB200_STAGE_DEFER_C2P: no pass is the LAST one (source terms follow)
+  // block subset of this launch (AB200_STAGE_SURFACE / _INTERIOR): the launch covers blocks
+  // blist[0 .. nbl-1]; nullptr = all g.nb blocks
+  const int *blist;
+  int nbl;
+  int subset;  // 0 all, 1 surface call, 2 interior call (host-side bookkeeping)
   int np;        // pencils per CTA
   int npencils;  // pencils per MeshBlock
   int tiles_per_row;    // TMA: tiles along the transverse index that is tiled

@@ -77,7 +77,7 @@ k_march_pass(GridDev g, FluidDev f, FusedArgs a) {
   const int ntr = DIR == 2 ? nkr : njr;  // transverse (non-i) extent
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= nir * ntr) return;
-  const int b = blockIdx.y, n = blockIdx.z;
+  const int b = a.blist ? a.blist[blockIdx.y] : blockIdx.y, n = blockIdx.z;
   const int i = g.is + col % nir;
   const int tr = col / nir;
   const int S = f.S, nvar = f.nvar;

@@ -55,11 +55,11 @@ k_xchunk_pass(GridDev g, FluidDev f, FusedArgs a) {
   // work item of this warp: (block, species, plane, segment of the plane's rows)
   const int nseg = a.np;  // segments per plane
   int w = blockIdx.x * kXcWarps + wid;
-  if (w >= g.nb * S * nkr * nseg) return;
+  if (w >= (a.blist ? a.nbl : g.nb) * S * nkr * nseg) return;
   const int seg = w % nseg; w /= nseg;
   const int k = g.ks + w % nkr; w /= nkr;
   const int n = w % S;
-  const int b = w / S;
+  const int b = a.blist ? a.blist[w / S] : w / S;
   const int rows_per_seg = (njr + nseg - 1) / nseg;
   const int j0 = g.js + seg * rows_per_seg;
   const int j1 = min(j0 + rows_per_seg, g.je + 1);  // exclusive

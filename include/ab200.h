@@ -171,6 +171,14 @@ int ab200_estimate_timestep(ab200_ctx *ctx, int fluid, double *dt_host);
  *                               kernels) can act on the conserved state in between.  Takes the
  *                               directional passes (the single-pass kernels always finish). */
 #define AB200_STAGE_DEFER_C2P 8
+/*        AB200_STAGE_SURFACE / AB200_STAGE_INTERIOR  the call covers only the MeshBlocks that
+ *                               touch a face owned by another rank (AB200_BC_NONE in
+ *                               ab200_set_topology) / only the others.  A stage is then TWO calls,
+ *                               surface first: the remote ghost exchange (ab200_comm_exchange_begin)
+ *                               starts as soon as the surface blocks are done and overlaps the
+ *                               interior blocks' stage.  Directional passes only. */
+#define AB200_STAGE_SURFACE 16
+#define AB200_STAGE_INTERIOR 32
 int ab200_fused_stage(ab200_ctx *ctx, double gam0, double gam1, double beta, double dt,
                       int pcm, int stage1_copy, int flags);
 /* SetAuxillaryFields -> ConsToPrim -> PrimToCons after a AB200_STAGE_DEFER_C2P stage and its
