@@ -7,7 +7,19 @@
 
 #include "ab200_dev.cuh"
 
+// NVTX ranges carrying the reference's own kernel / task labels (Parthenon wraps every par_for in
+// a Kokkos profiling region named by its label, P:utils/instrument.hpp:22-49), so a timeline of
+// this library lines up with one of the reference.  Header-only NVTX3: a no-op unless a profiler
+// injects itself.
+#include <nvtx3/nvToolsExt.h>
+
 namespace ab200 {
+
+struct NvtxRange {
+  explicit NvtxRange(const char *label) { nvtxRangePushA(label); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+};
 
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);

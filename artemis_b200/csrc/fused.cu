@@ -5,6 +5,7 @@
 #include "fused.cuh"
 #include "march.cuh"
 #include "xchunk.cuh"
+#include "xtile.cuh"
 
 #ifndef AB_GEOM
 #error "compile with -DAB_GEOM=<0..5>"
@@ -75,6 +76,7 @@ static int launch_pass(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
 // x2 / x3 passes as marching kernels (march.cuh): one thread per pencil, register window.
 template <int GEOM, int FLUID, int RS, int RC, int DIR>
 static int launch_march(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
+  NvtxRange nvtx_(DIR == 2 ? "CalculateFluxes::X2-Flux + ApplyUpdate + GeometricSourceTerms [fused]" : (a.last ? "Hydro::X3-Flux + ApplyUpdate + GeometricSourceTerms + SetAuxillaryFields + ConsToPrim + PrimToCons [fused]" : "Hydro::X3-Flux + ApplyUpdate + GeometricSourceTerms [fused]"));
   const GridDev &g = c->g;
   const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
   const int ncols = nir * (DIR == 2 ? nkr : njr);
@@ -90,6 +92,7 @@ static int launch_march(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
 // x1 pass as the warp-autonomous streaming kernel (xchunk.cuh); first pass of a >= 2-D stage.
 template <int GEOM, int FLUID, int RS, int RC>
 static int launch_xchunk(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
+  NvtxRange nvtx_("CalculateFluxes::X1-Flux + ApplyUpdate + GeometricSourceTerms [fused]");
   const GridDev &g = c->g;
   const int njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
   int nseg = njr >= 32 ? 2 : 1;
@@ -104,6 +107,41 @@ static int launch_xchunk(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
   c->launches++;
   AB_CUDA(cudaGetLastError());
   return AB200_OK;
+}
+
+// x1 pass as the thread-per-cell tile kernel (xtile.cuh)
+template <int GEOM, int FLUID, int RS, int RC>
+static int launch_xtile(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
+  NvtxRange nvtx_("CalculateFluxes::X1-Flux + ApplyUpdate + GeometricSourceTerms [fused]");
+  const GridDev &g = c->g;
+  const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
+  int R = kXtThreads / (nir + 2);
+  if (R > njr) R = njr;
+  a.np = R;
+  constexpr int NV = FLUID == AB200_GAS ? 6 : 4, NF = FLUID == AB200_GAS ? 8 : 4;
+  const size_t shmem = sizeof(double) * (size_t)(NV + NF) * R * (nir + 1);
+  const long long ncta = (long long)(a.blist ? a.nbl : g.nb) * f.S * nkr * ((njr + R - 1) / R);
+  auto kern = k_xtile_pass<GEOM, FLUID, RS, RC>;
+  if (shmem > 48 * 1024)
+    AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+  kern<<<(unsigned)ncta, kXtThreads, shmem, c->stream>>>(g, f, a);
+  c->launches++;
+  AB_CUDA(cudaGetLastError());
+  return AB200_OK;
+}
+
+// which x1 kernel: AB200_X1=tile | chunk.  Default: chunk -- measured on B200 (r02, 256^3 blast)
+// the thread-per-cell tile kernel (72 registers, 27 warps per SM) takes 1.2 ms per pass against
+// 0.8 ms for the lane-pipelined streaming kernel (160 registers, 12 warps): on this path the
+// fp64 dependency chains are hidden by per-thread ILP, not by occupancy.
+static bool use_xtile(const ab200_ctx *c) {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("AB200_X1");
+    v = (e && e[0] == 't') ? 1 : 0;
+  }
+  const int nir = c->g.ie - c->g.is + 1;
+  return v == 1 && nir + 2 <= kXtThreads && nir >= 8;
 }
 
 static bool use_xchunk() {
@@ -138,7 +176,8 @@ static int launch_dirs(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
   const int fin = a.defer_c2p ? 0 : 1;  // deferred: SetAux / C2P run in ab200_finish_stage
   a.first = 1; a.last = fin * (ndim == 1); a.copy_u1 = copy;
   if (!interior_call) {
-    if (ndim >= 2 && use_xchunk()) AB_TRY((launch_xchunk<GEOM, FLUID, RS, RC>(c, f, a)));
+    if (ndim >= 2 && use_xchunk() && use_xtile(c)) AB_TRY((launch_xtile<GEOM, FLUID, RS, RC>(c, f, a)));
+    else if (ndim >= 2 && use_xchunk()) AB_TRY((launch_xchunk<GEOM, FLUID, RS, RC>(c, f, a)));
     else AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 1>(c, f, a)));
   }
   if (ndim >= 2) {

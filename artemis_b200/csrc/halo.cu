@@ -52,6 +52,7 @@ k_exchange(GridDev g, FluidDev f, int nbx, int nby, int nbz, int bc0, int bc1, i
 }
 
 int launch_exchange(ab200_ctx *c, int fluid) {
+  NvtxRange nvtx_("SendBoundBufs + SetBounds (same GPU)");
   const GridDev &g = c->g;
   const FluidHost &fh = c->fl[fluid];
   const Topology &tp = c->topo;
@@ -210,6 +211,7 @@ bool topology_is_local(const ab200_ctx *c) {
 }
 
 int launch_fill_ghosts(ab200_ctx *c, int fluid, int remote_pass) {
+  NvtxRange nvtx_("SendBoundBufs + SetBounds + GenericBC + PrimToCons(ghosts) [fused]");
   const GridDev &g = c->g;
   FluidHost &fh = c->fl[fluid];
   const Topology &tp = c->topo;
@@ -287,6 +289,7 @@ k_physical_bc(GridDev g, FluidDev f, int nbx, int nby, int nbz, int face, int ty
 }
 
 int launch_physical_bcs(ab200_ctx *c, int fluid) {
+  NvtxRange nvtx_("GenericBC");
   const GridDev &g = c->g;
   const FluidHost &fh = c->fl[fluid];
   const Topology &tp = c->topo;
@@ -342,6 +345,7 @@ k_halo(GridDev g, FluidDev f0, FluidDev f1, const BndDev *__restrict__ bnd) {
 }
 
 int launch_halo(ab200_ctx *c, const ab200_bnd_desc *bnd, int n, int unpack) {
+  NvtxRange nvtx_(unpack ? "SetBounds" : "SendBoundBufs");
   const GridDev &g = c->g;
   std::vector<BndDev> h(n);
   long long maxel = 0;

@@ -130,6 +130,7 @@ bool sweep_eligible(ab200_ctx *c, int fluid) {
 
 int launch_sweep_stage(ab200_ctx *c, int fluid, double gam0, double gam1, double beta, double dt,
                        int pcm, int stage1_copy, int use_device_dt, unsigned long long *dt_min) {
+  NvtxRange nvtx_("CalculateFluxes + ApplyUpdate + GeometricSourceTerms + SetAuxillaryFields + ConsToPrim + PrimToCons [single pass]");
   FluidHost &fh = c->fl[fluid];
   AB_REQUIRE(fh.sw_ready, AB200_ESTATE, "launch_sweep_stage: sweep path not available");
   const GridDev &g = c->g;

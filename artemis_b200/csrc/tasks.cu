@@ -35,12 +35,14 @@ static long long interior_cells(const GridDev &g) {
 }
 
 int launch_calculate_fluxes(ab200_ctx *c, int fluid, int pcm) {
+  NvtxRange nvtx_("CalculateFluxes::X1-Flux / X2-Flux / Hydro::X3-Flux");
   return dispatch_geom(c->g.geom, [&](auto G) {
     return launch_flux_geom<decltype(G)::value>(c, fluid, pcm);
   });
 }
 
 int launch_apply_update(ab200_ctx *c, int fluid, double gam0, double gam1, double beta_dt) {
+  NvtxRange nvtx_("ApplyUpdate");
   const GridDev &g = c->g;
   const FluidDev &f = c->fl[fluid].d;
   const unsigned grid = grid_for(interior_cells(g));
@@ -54,6 +56,7 @@ int launch_apply_update(ab200_ctx *c, int fluid, double gam0, double gam1, doubl
 }
 
 int launch_flux_source(ab200_ctx *c, int fluid, double dt) {
+  NvtxRange nvtx_("GeometricSourceTerms");
   const GridDev &g = c->g;
   const FluidDev &f = c->fl[fluid].d;
   const bool x1dep = g.geom != AB200_CARTESIAN;
@@ -76,6 +79,7 @@ int launch_flux_source(ab200_ctx *c, int fluid, double dt) {
 }
 
 int launch_set_aux(ab200_ctx *c) {
+  NvtxRange nvtx_("SetAuxillaryFields");
   const GridDev &g = c->g;
   const FluidDev &f = c->fl[AB200_GAS].d;
   const unsigned grid = grid_for(interior_cells(g));
@@ -89,6 +93,7 @@ int launch_set_aux(ab200_ctx *c) {
 }
 
 int launch_cons_to_prim(ab200_ctx *c, int fluid) {
+  NvtxRange nvtx_("ConsToPrim");
   const GridDev &g = c->g;
   const FluidDev &f = c->fl[fluid].d;
   const unsigned grid = grid_for(interior_cells(g));
@@ -106,6 +111,7 @@ int launch_cons_to_prim(ab200_ctx *c, int fluid) {
 }
 
 int launch_prim_to_cons(ab200_ctx *c, int fluid, int ghosts_only) {
+  NvtxRange nvtx_("PrimToCons");
   const GridDev &g = c->g;
   const FluidDev &f = c->fl[fluid].d;
   const unsigned grid = grid_for((long long)g.nb * g.nk * g.nj * g.ni);
@@ -133,6 +139,7 @@ __global__ void __launch_bounds__(kThreads) k_deep_copy(GridDev g, FluidDev f) {
 }
 
 int launch_deep_copy(ab200_ctx *c, int fluid) {
+  NvtxRange nvtx_("DeepCopyConservedData");
   const GridDev &g = c->g;
   const FluidDev &f = c->fl[fluid].d;
   k_deep_copy<<<c->sm_count * 8, kThreads, 0, c->stream>>>(g, f);
@@ -170,6 +177,7 @@ int launch_finish_dt(ab200_ctx *c, const double *partial, int n, double cfl, dou
 }
 
 int launch_estimate_dt(ab200_ctx *c, int fluid, double *d_out, int combine) {
+  NvtxRange nvtx_(fluid == AB200_GAS ? "Gas::EstimateTimestepMesh" : "Dust::EstimateTimestepMesh");
   const GridDev &g = c->g;
   const FluidDev &f = c->fl[fluid].d;
   long long total = interior_cells(g);

@@ -50,6 +50,11 @@ def parse():
     ap.add_argument("--dust-species", type=int, default=4)
     ap.add_argument("--no-drag", action="store_true",
                     help="config 3: leave Drag::DragSource out (it then stays on the reference path)")
+    ap.add_argument("--state", default="blast", choices=["blast", "shocked"],
+                    help="config 2 initial state: 'blast' = the configured deck (ambient gas is "
+                         "quiescent, limiter / wave-speed branches are warp-uniform); 'shocked' = a "
+                         "seeded multi-mode field with jumps and noise in every MeshBlock, so the "
+                         "branches diverge inside warps (a second number beside the headline)")
     ap.add_argument("--transport", default="native", choices=["native", "torch"],
                     help="N > 1: 'native' = the C ABI's own NCCL transport (ab200_run_cycles_mr), "
                          "'torch' = torch.distributed driven from Python (round-1 path)")
@@ -402,7 +407,11 @@ def main():
         if args.transport == "native":
             from artemis_b200.comm import NativeComm
             native = NativeComm(md, lay, rank, world)
-    prim = pgen.blast(mesh, gp.gamma, d0=1.0, p0=1e-5, internal_energy=1.0, radius=0.1, samples=0)
+    if args.state == "blast":
+        prim = pgen.blast(mesh, gp.gamma, d0=1.0, p0=1e-5, internal_energy=1.0, radius=0.1, samples=0)
+    else:
+        from tests.helpers import random_prim
+        prim = random_prim(mesh, gp, seed=1234)
     md.gas.prim.set(prim)
     drv = ArtemisDriver(md, "rk2", mode="fused", comm=comm)
     drv.Initialize()
@@ -503,19 +512,21 @@ def main():
     if os.path.exists(tp):
         with open(tp) as fh:
             tj = json.load(fh)
-        traffic = tj.get("single_pass_dram_bytes_per_launch" if path == "single_pass"
-                         else "fused_stage_dram_bytes_per_launch")
+        traffic = tj.get({"single_pass": "single_pass_dram_bytes_per_launch",
+                          "role_split": "role_split_dram_bytes_per_launch"}.get(
+                              path, "fused_stage_dram_bytes_per_launch"))
         # ncu counters of the same kernels (committed evidence, not re-measured here): the fp64
         # pipe and issue-slot utilisation that explain why the HBM fraction is what it is
         cj = tj.get("counters") or {}
-        counters = cj.get("single_pass" if path == "single_pass" else "three_pass")
+        counters = cj.get(path if path in ("single_pass", "role_split") else "three_pass")
         if counters is not None:
             counters = dict(counters, source=cj.get("source"), secondary_bound=cj.get("secondary_bound"))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "kernel": ("k_sweep_stage (one launch = one full stage: x1+x2+x3 reconstruct/Riemann/"
+                "kernel": (("k_trio_stage" if path == "role_split" else "k_sweep_stage") +
+                           " (one launch = one full stage: x1+x2+x3 reconstruct/Riemann/"
                            "update + C2P, primitives and conserved state cross HBM once)"
-                           if path == "single_pass" else
+                           if path in ("single_pass", "role_split") else
                            "k_xchunk_pass + k_march_pass<2> + k_march_pass<3> (one fused stage = the "
                            "three directional passes; 'achieved' = algorithmic bytes of the stage / "
                            "their summed duration)"),
@@ -609,10 +620,11 @@ def main():
                                        f"MeshBlocks, nghost=4, outflow",
                            "zones_total": zones, "ranks": list(lay),
                            "l2": "state 3.4 GB/GPU >> 126 MB L2, no flush needed",
-                           "path": ("single-pass stage kernel" if path == "single_pass" else
+                           "path": ("single-pass stage kernel" if path in ("single_pass", "role_split") else
                                     "three directional fused passes") +
                                    (" + fused ghost fill + device-resident dt" if world == 1 else
                                     " + single-round NCCL halo exchange + device-resident dt all-reduce"),
+                           "state": args.state, "transport": args.transport if world > 1 else None,
                            "stage_path": path, "halo_exchange_ms": comm_ms, "host_issue_ms_per_step": cpu_issue_ms,
                            "halo_bytes_per_exchange": (comm.bytes_per_direct_exchange if comm else 0)},
                 "roofline": roofline, "cpu_baseline": base, "e2e": e2e,

@@ -39,6 +39,17 @@ def test_c_program_compiles_links_and_fails_loudly_without_a_gpu(tmp_path):
         assert "no CUDA device" in r.stdout and "no CPU fallback" in r.stdout
 
 
+def test_glue_tu_compiles():
+    """tests/c/ab200_glue.cpp -- the file INTEGRATION.md tells a maintainer to add to Artemis --
+    compiles against include/ab200.h and a mock that declares exactly the public Parthenon
+    accessors it uses (tests/c/parthenon_glue_mock.hpp, each cited to its reference file:line)."""
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Werror",
+           "-DAB200_GLUE_SYNTAX_CHECK", "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(ROOT, "tests", "c"), os.path.join(ROOT, "tests", "c", "ab200_glue.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def _ctypes_twin(path):
     """Same mesh, state and call sequence as tests/c/abi_roundtrip.c, through ctypes."""
     from artemis_b200.enums import Coordinates, Fluid, ReconstructionMethod, RSolver
