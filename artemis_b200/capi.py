@@ -67,7 +67,7 @@ SYMBOLS = [
     "ab200_fill_ghosts_local", "ab200_finish_remote_ghosts", "ab200_cycles_host",
     "ab200_run_cycles", "ab200_malloc", "ab200_free", "ab200_memcpy_h2d", "ab200_memcpy_d2h",
     "ab200_launch_count", "ab200_timer_begin", "ab200_timer_end",
-    "ab200_configure_sources", "ab200_finish_stage", "ab200_uniform_gravity", "ab200_shearing_box", "ab200_drag_simple",
+    "ab200_history_volume_integrals", "ab200_configure_sources", "ab200_finish_stage", "ab200_uniform_gravity", "ab200_shearing_box", "ab200_drag_simple",
     "ab200_comm_unique_id", "ab200_comm_init", "ab200_comm_destroy", "ab200_comm_set_layout",
     "ab200_comm_bytes_per_exchange", "ab200_comm_exchange_begin", "ab200_comm_exchange_end",
     "ab200_allreduce_min", "ab200_run_cycles_mr", "ab200_comm_plan_direct", "ab200_comm_plan_free",
@@ -131,7 +131,7 @@ def load(variant: str | None = None) -> C.CDLL:
         "ab200_malloc": [vp, C.POINTER(vp), C.c_size_t], "ab200_free": [vp, vp],
         "ab200_memcpy_h2d": [vp, vp, vp, C.c_size_t], "ab200_memcpy_d2h": [vp, vp, vp, C.c_size_t],
         "ab200_timer_begin": [vp], "ab200_timer_end": [vp, C.POINTER(C.c_float)],
-        "ab200_configure_sources": [vp, vp], "ab200_finish_stage": [vp, i], "ab200_uniform_gravity": [vp, d, d, d, d],
+        "ab200_history_volume_integrals": [vp, i, _DP, i], "ab200_configure_sources": [vp, vp], "ab200_finish_stage": [vp, i], "ab200_uniform_gravity": [vp, d, d, d, d],
         "ab200_shearing_box": [vp, d, d, d], "ab200_drag_simple": [vp, d, i, _DP],
         "ab200_comm_unique_id": [C.c_char_p], "ab200_comm_init": [vp, i, i, C.c_char_p],
         "ab200_comm_destroy": [vp], "ab200_comm_set_layout": [vp, i, i, i, C.POINTER(C.c_int)],

@@ -402,6 +402,15 @@ class HaloComm:
             self.exchange_direct(md)
             return
         t = self._t
+        # the events below order the side stream against torch's CURRENT stream; the stage
+        # kernels run on the stream given to ab200_create.  The two must be the same stream
+        # (the C transport, NativeComm / ab200_comm_exchange_begin, orders against the context's
+        # own stream and has no such requirement).
+        cur = t.cuda.current_stream().cuda_stream
+        if cur != getattr(self.md, "stream", 0):
+            raise RuntimeError("HaloComm.begin_direct: torch's current stream is not the stream "
+                               "the ab200 context was created on; use NativeComm or run under "
+                               "torch.cuda.stream(ExternalStream(ctx_stream))")
         self._ev_stage.record(t.cuda.current_stream())
         self.md.call("ab200_set_halo_stream", C.c_void_p(self.stream.cuda_stream))
         try:

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -122,6 +123,42 @@ struct ab200_ctx {
 };
 
 namespace ab200 {
+// Device copy of a host descriptor list, cached by content.  `host` must have been zero-filled
+// before its members were assigned (struct padding takes part in the memcmp key).  The cache is
+// bounded: past kDescCacheMax entries the oldest is released (remeshes change every list), and
+// ab200_set_grid / ab200_unbind clear it.  grid.y of the descriptor kernels is the list length:
+// lists longer than 65535 are rejected here instead of failing at launch.
+constexpr size_t kDescCacheMax = 64;
+inline int cached_descriptors(ab200_ctx *c, const void *host, size_t bytes, int n, void **dev_out) {
+  AB_REQUIRE(n > 0 && n <= 65535, AB200_EINVAL,
+             "descriptor list: 1..65535 entries per call (split longer lists)");
+  for (auto &e : c->halo_cache)
+    if (e.bytes == bytes && memcmp(e.host.data(), host, bytes) == 0) {
+      *dev_out = e.dev;
+      return AB200_OK;
+    }
+  if (c->halo_cache.size() >= kDescCacheMax) {
+    AB_CUDA(cudaStreamSynchronize(c->stream));  // a kernel may still read the oldest copy
+    if (c->halo_stream_set) AB_CUDA(cudaStreamSynchronize(c->halo_stream));
+    cudaFree(c->halo_cache.front().dev);
+    c->halo_cache.erase(c->halo_cache.begin());
+  }
+  void *d = nullptr;
+  AB_CUDA(cudaMalloc(&d, bytes));
+  AB_CUDA(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, c->stream));
+  AB_CUDA(cudaStreamSynchronize(c->stream));  // the host list goes out of scope
+  ab200_ctx::HaloCacheEntry e;
+  e.bytes = bytes;
+  e.host.assign((const unsigned char *)host, (const unsigned char *)host + bytes);
+  e.dev = d;
+  c->halo_cache.push_back(std::move(e));
+  *dev_out = d;
+  return AB200_OK;
+}
+inline void clear_descriptor_cache(ab200_ctx *c) {
+  for (auto &e : c->halo_cache) cudaFree(e.dev);
+  c->halo_cache.clear();
+}
 // kernel launch entry points implemented in tasks_*.cu / fused.cu / halo.cu
 int launch_calculate_fluxes(ab200_ctx *c, int fluid, int pcm);
 int launch_apply_update(ab200_ctx *c, int fluid, double gam0, double gam1, double beta_dt);

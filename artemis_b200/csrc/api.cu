@@ -169,15 +169,28 @@ int ab200_create(ab200_ctx **out, int device, void *cuda_stream) {
   ab200_ctx *c = new ab200_ctx();
   c->device = device;
   c->stream = (cudaStream_t)cuda_stream;
-  AB_CUDA(cudaMalloc((void **)&c->d_time, 8 * sizeof(double)));
-  AB_CUDA(cudaMemset(c->d_time, 0, 8 * sizeof(double)));
-  AB_CUDA(cudaMalloc((void **)&c->d_red, 4096 * sizeof(double)));
-  AB_CUDA(cudaMallocHost((void **)&c->h_pinned, 16 * sizeof(double)));
-  AB_CUDA(cudaEventCreate(&c->ev0));
-  AB_CUDA(cudaEventCreate(&c->ev1));
-  cudaDeviceProp prop;
-  AB_CUDA(cudaGetDeviceProperties(&prop, device));
-  c->sm_count = prop.multiProcessorCount;
+  // any failure below releases what was allocated so far (ab200_destroy tolerates nulls)
+  auto init = [&]() -> int {
+    AB_CUDA(cudaMalloc((void **)&c->d_time, 8 * sizeof(double)));
+    AB_CUDA(cudaMemset(c->d_time, 0, 8 * sizeof(double)));
+    AB_CUDA(cudaMalloc((void **)&c->d_red, 4096 * sizeof(double)));
+    AB_CUDA(cudaMallocHost((void **)&c->h_pinned, 16 * sizeof(double)));
+    // d_red[3080..3081]: bit pattern of Big<Real>() = DBL_MAX, the seed of the folded CFL
+    // reduction (the same start value as k_estimate_dt and the reference's Kokkos::Min)
+    const double big[2] = {1.79769313486231570815e+308, 1.79769313486231570815e+308};
+    AB_CUDA(cudaMemcpy(c->d_red + 3080, big, sizeof big, cudaMemcpyHostToDevice));
+    AB_CUDA(cudaEventCreate(&c->ev0));
+    AB_CUDA(cudaEventCreate(&c->ev1));
+    cudaDeviceProp prop;
+    AB_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    return AB200_OK;
+  };
+  const int rc = init();
+  if (rc != AB200_OK) {
+    ab200_destroy(c);
+    return rc;
+  }
   *out = c;
   return AB200_OK;
 }
@@ -190,14 +203,13 @@ int ab200_destroy(ab200_ctx *c) {
   for (int f = 0; f < 2; ++f) ab200_unbind(c, f);
   free_all(c->grid_allocs);
   free_all(c->host_path_allocs);
-  for (auto &e : c->halo_cache) cudaFree(e.dev);
-  c->halo_cache.clear();
+  clear_descriptor_cache(c);
   for (int q = 0; q < 2; ++q)
     if (c->d_blist[q]) cudaFree(c->d_blist[q]);
-  cudaFree(c->d_time);
-  cudaFree(c->d_red);
-  cudaFreeHost(c->h_pinned);
-  cudaEventDestroy(c->ev0);
+  if (c->d_time) cudaFree(c->d_time);
+  if (c->d_red) cudaFree(c->d_red);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->ev0) cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   delete c;
   return AB200_OK;
@@ -225,6 +237,10 @@ int ab200_set_grid(ab200_ctx *c, const ab200_grid_desc *gd) {
   AB_CUDA(cudaStreamSynchronize(c->stream));
   for (int f = 0; f < 2; ++f) ab200_unbind(c, f);
   free_all(c->grid_allocs);
+  clear_descriptor_cache(c);  // halo / refinement descriptor lists describe the old mesh
+  // the (block, variable) index sits in grid.y / grid.z of several launches
+  AB_REQUIRE(gd->nblocks <= 65535, AB200_EINVAL,
+             "ab200_set_grid: at most 65535 MeshBlocks per MeshData partition");
   GridDev &g = c->g;
   g.geom = gd->geom; g.ndim = gd->ndim; g.ng = gd->nghost; g.nb = gd->nblocks;
   g.ni = gd->ni; g.nj = gd->nj; g.nk = gd->nk;
@@ -539,7 +555,8 @@ int ab200_fused_stage(ab200_ctx *c, double gam0, double gam1, double beta, doubl
   unsigned long long *slots = reinterpret_cast<unsigned long long *>(c->d_red + 3072);
   // (a SURFACE call opens the reduction, the INTERIOR call that follows closes it)
   if (reduce_dt && subset != 2)
-    AB_CUDA(cudaMemsetAsync(slots, 0x7f, 2 * sizeof(unsigned long long), c->stream));
+    AB_CUDA(cudaMemcpyAsync(slots, c->d_red + 3080, 2 * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToDevice, c->stream));
   int any = 0;
   for (int f = 0; f < 2; ++f) {
     if (!c->fl[f].bound) continue;

@@ -216,6 +216,7 @@ static int launch_refine(ab200_ctx *c, const ab200_refine_desc *descs, int n, bo
   const int act[3] = {1, g.ndim > 1, g.ndim > 2};
   const int grow = prolong ? 1 : 0;  // the minmod stencil reads one coarse neighbour per side
   std::vector<RefineDev> h(n);
+  memset(h.data(), 0, sizeof(RefineDev) * (size_t)n);
   long long maxel = 0;
   for (int q = 0; q < n; ++q) {
     const ab200_refine_desc &d = descs[q];
@@ -242,27 +243,18 @@ static int launch_refine(ab200_ctx *c, const ab200_refine_desc *descs, int n, bo
       AB_REQUIRE((lo[a] - cs[a]) * 2 + fs[a] >= 0 && (hi[a] - cs[a]) * 2 + fs[a] + 1 < fn[a],
                  AB200_EINVAL, "refine: fine cells of the coarse box fall outside the block");
     }
-    h[q] = {d.fluid, d.block, d.var0, d.nvar, d.kind, d.cis, d.cie, d.cjs, d.cje, d.cks, d.cke,
-            d.coarse};
+    // member-wise into zero-filled storage: the padding bytes are part of the cache key
+    RefineDev &o = h[q];
+    o.fluid = d.fluid; o.block = d.block; o.var0 = d.var0; o.nvar = d.nvar; o.kind = d.kind;
+    o.cis = d.cis; o.cie = d.cie; o.cjs = d.cjs; o.cje = d.cje; o.cks = d.cks; o.cke = d.cke;
+    o.coarse = d.coarse;
     const long long el = (long long)d.nvar * (d.cie - d.cis + 1) * (d.cje - d.cjs + 1) *
                          (d.cke - d.cks + 1);
     if (el > maxel) maxel = el;
   }
   // descriptor lists are static between remeshes: cached on the device, keyed by content
   RefineDev *dd = nullptr;
-  const size_t bytes = sizeof(RefineDev) * (size_t)n;
-  for (auto &e : c->halo_cache)
-    if (e.bytes == bytes && memcmp(e.host.data(), h.data(), bytes) == 0) { dd = (RefineDev *)e.dev; break; }
-  if (!dd) {
-    AB_CUDA(cudaMalloc((void **)&dd, bytes));
-    AB_CUDA(cudaMemcpyAsync(dd, h.data(), bytes, cudaMemcpyHostToDevice, c->stream));
-    AB_CUDA(cudaStreamSynchronize(c->stream));
-    ab200_ctx::HaloCacheEntry e;
-    e.bytes = bytes;
-    e.host.assign((const unsigned char *)h.data(), (const unsigned char *)h.data() + bytes);
-    e.dev = dd;
-    c->halo_cache.push_back(std::move(e));
-  }
+  AB_TRY(cached_descriptors(c, h.data(), sizeof(RefineDev) * (size_t)n, n, (void **)&dd));
   unsigned gx = (unsigned)((maxel + kThreads - 1) / kThreads);
   if (gx > 1024) gx = 1024;
   dim3 grid(gx, (unsigned)n);

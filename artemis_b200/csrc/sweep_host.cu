@@ -191,9 +191,15 @@ int sync_prim_home(ab200_ctx *c, int fluid, int interior_only) {
   const long long cells = (long long)g.ni * g.nj * g.nk;
   int gx = (int)((cells + 256 * 8 - 1) / (256 * 8));
   if (gx < 1) gx = 1;
-  dim3 grid((unsigned)gx, (unsigned)(g.nb * fh.d.nvar));
-  k_copy_prim<<<grid, 256, 0, c->stream>>>(g, fh.prim_tab[0], fh.prim_tab[1], interior_only);
-  c->launches++;
+  // (block, variable) arrays in chunks of 65535: grid.y is a 16-bit dimension
+  const long long nent = (long long)g.nb * fh.d.nvar;
+  for (long long e0 = 0; e0 < nent; e0 += 65535) {
+    const unsigned ny = (unsigned)((nent - e0) < 65535 ? (nent - e0) : 65535);
+    dim3 grid((unsigned)gx, ny);
+    k_copy_prim<<<grid, 256, 0, c->stream>>>(g, fh.prim_tab[0] + e0, fh.prim_tab[1] + e0,
+                                             interior_only);
+    c->launches++;
+  }
   AB_CUDA(cudaGetLastError());
   fh.prim_cur = 0;
   fh.d.prim = fh.prim_tab[0];

@@ -103,6 +103,7 @@ class MeshData:
         self.ctx = C.c_void_p()
         capi.check(self.L, self.L.ab200_create(C.byref(self.ctx), device, stream), "ab200_create")
         self.device = device
+        self.stream = int(stream) if stream else 0   # 0 = the legacy default stream
         self._torch = None
         if use_torch:
             import torch

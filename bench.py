@@ -42,10 +42,12 @@ def parse():
     ap.add_argument("--cpu-cycles", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
                     help="BASELINE.json config: 2 = the headline (3-D blast, PPM+HLLC, 256^3 per "
                          "GPU, weak scaling); 3 = gas + 4 dust species, PLM+HLLE, periodic, "
-                         "--mesh^3 zones IN TOTAL split over the GPUs (strong scaling)")
+                         "--mesh^3 zones IN TOTAL split over the GPUs (strong scaling); 4 = spherical "
+                         "3-D disk-like gas + dust, PPM+HLLE (WENO5 does not exist in the reference), "
+                         "32^3 MeshBlocks, outflow, curvilinear geometry + geometric source terms")
     ap.add_argument("--mesh", type=int, default=512, help="config 3: total zones per direction")
     ap.add_argument("--dust-species", type=int, default=4)
     ap.add_argument("--no-drag", action="store_true",
@@ -259,24 +261,58 @@ def main_config3(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     lay = rank_layout(world)
-    M, B, S = args.mesh, args.block, args.dust_species
+    cfg4 = args.config == 4
+    M, B, S = args.mesh, (32 if cfg4 else args.block), (1 if cfg4 else args.dust_species)
+    if cfg4 and args.mesh == 512:
+        M = 256
     nbt = tuple(M // B // lay[d] for d in range(3))
     rl = (rank % lay[0], (rank // lay[0]) % lay[1], rank // (lay[0] * lay[1]))
-    mesh = UniformMesh(nx=(M, M, M), xmin=(0, 0, 0), xmax=(1, 1, 1), block_nx=(B, B, B), nghost=4,
-                       bcs=(BoundaryFlag.periodic,) * 6,
-                       lattice_lo=tuple(rl[d] * nbt[d] for d in range(3)), lattice_n=nbt)
-    Cc = Coordinates.cartesian
-    gp = FluidParams(Fluid.gas, Cc, ReconstructionMethod.plm, RSolver.hlle, cfl=0.3, nspecies=1,
+    if cfg4:   # inputs/disk/disk_sph.in geometry: r in [0.4, 2.5], theta around the midplane
+        Cc = Coordinates.spherical3D
+        mesh = UniformMesh(nx=(M, M, M), xmin=(0.4, 1.0707963267948966, 0.0),
+                           xmax=(2.5, 2.0707963267948966, 6.283185307179586), block_nx=(B, B, B),
+                           nghost=4, bcs=(BoundaryFlag.outflow,) * 4 + (BoundaryFlag.periodic,) * 2,
+                           coords=Cc, lattice_lo=tuple(rl[d] * nbt[d] for d in range(3)), lattice_n=nbt)
+        recon, per = ReconstructionMethod.ppm, (False, False, True)
+    else:
+        Cc = Coordinates.cartesian
+        mesh = UniformMesh(nx=(M, M, M), xmin=(0, 0, 0), xmax=(1, 1, 1), block_nx=(B, B, B), nghost=4,
+                           bcs=(BoundaryFlag.periodic,) * 6,
+                           lattice_lo=tuple(rl[d] * nbt[d] for d in range(3)), lattice_n=nbt)
+        recon, per = ReconstructionMethod.plm, (True, True, True)
+    gp = FluidParams(Fluid.gas, Cc, recon, RSolver.hlle, cfl=0.3, nspecies=1,
                      dfloor=1e-10, gamma=1.4, siefloor=1e-10)
-    dp = FluidParams(Fluid.dust, Cc, ReconstructionMethod.plm, RSolver.hlle, cfl=0.3, nspecies=S,
-                     dfloor=1e-10)
+    dp = FluidParams(Fluid.dust, Cc, recon, RSolver.hlle, cfl=0.3, nspecies=S, dfloor=1e-10)
     bcs = [int(v) for v in mesh.bcs]
     for d in range(3):
-        if lay[d] > 1:          # periodic + several ranks: both faces belong to other ranks
-            bcs[2 * d] = bcs[2 * d + 1] = 3
+        if lay[d] > 1:
+            if per[d]:          # periodic + several ranks: both faces belong to other ranks
+                bcs[2 * d] = bcs[2 * d + 1] = 3
+            else:
+                if rl[d] > 0:
+                    bcs[2 * d] = 3
+                if rl[d] < lay[d] - 1:
+                    bcs[2 * d + 1] = 3
     md = MeshData(mesh, gas=gp, dust=dp, device=local, materialize_fluxes=False, bcs=bcs)
     md.set_stage_path(args.path)
-    prim, dprim = pgen.perturbed_constant(mesh, 6, S, amp=1e-3, seed=1234)
+    if cfg4:   # Keplerian power-law disk (disk.hpp profile shape) with a seeded azimuthal mode
+        prim = np.zeros(mesh.shape(6))
+        dprim = np.zeros(mesh.shape(4))
+        for b in range(mesh.nb):
+            x1v, x2v, x3v = pgen.cell_centers(mesh, b)
+            r = x1v[None, None, :] + 0 * x2v[None, :, None] + 0 * x3v[:, None, None]
+            th = x2v[None, :, None] + 0 * r
+            ph = x3v[:, None, None] + 0 * r
+            R = r * np.sin(th)
+            rho = R ** -1.5 * np.exp(-((th - np.pi / 2) / 0.2) ** 2) * (1 + 1e-2 * np.sin(3 * ph))
+            prim[b, 0] = np.maximum(rho, 1e-6)
+            prim[b, 3] = R ** -0.5
+            prim[b, 1] = 1e-3 * np.cos(2 * ph)
+            prim[b, 5] = 0.05 ** 2 / gp.gm1 / R
+            dprim[b, 0] = 0.01 * prim[b, 0]
+            dprim[b, 3] = R ** -0.5
+    else:
+        prim, dprim = pgen.perturbed_constant(mesh, 6, S, amp=1e-3, seed=1234)
     prim[:, 4] = gp.gm1 * prim[:, 0] * prim[:, 5]
     md.gas.prim.set(prim)
     md.dust.prim.set(dprim)
@@ -284,14 +320,14 @@ def main_config3(args):
     comm = native = None
     if world > 1:
         from artemis_b200.comm import HaloComm, NativeComm
-        comm = HaloComm(md, lay, rl, rank, world, periodic=(True, True, True))
-        native = NativeComm(md, lay, rank, world, periodic=(True, True, True))
+        comm = HaloComm(md, lay, rl, rank, world, periodic=per)
+        native = NativeComm(md, lay, rank, world, periodic=per)
     drv = ArtemisDriver(md, "rk2", mode="fused", comm=comm)
     drv.Initialize()
     md.set_time_state(drv.dt)
     md.call("ab200_set_ghost_cons_lazy", 1)
     big = float(np.finfo(np.float64).max)
-    if not args.no_drag:   # <drag/dust> type = constant, one stopping time per species
+    if not args.no_drag and not cfg4:   # <drag/dust> type = constant, one stopping time per species
         import ctypes as C
         from artemis_b200 import capi
         sd = capi.SourcesDesc()
@@ -343,12 +379,17 @@ def main_config3(args):
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
-               "config": {"workload": f"config 3: gas + {S} dust species (inputs/drag state + seeded "
-                                      f"perturbation), PLM+HLLE, rk2, periodic, {M}^3 zones in TOTAL in "
-                                      f"{B}^3 MeshBlocks split over {world} GPU(s) (strong scaling); "
-                                      + ("Drag::DragSource stays on the reference path" if args.no_drag
-                                         else "implicit gas-dust drag (constant stopping times) every stage, "
-                                              "split stage: passes -> drag -> SetAux/C2P/P2C"),
+               "config": {"workload": (f"config 4: spherical 3-D Keplerian disk, gas + 1 dust species, "
+                                       f"PPM+HLLE (WENO5 absent upstream), rk2, outflow r/theta + periodic "
+                                       f"phi, {M}^3 zones in TOTAL in {B}^3 MeshBlocks over {world} GPU(s); "
+                                       "curvilinear fluxes, PLM_G-free PPM, geometric source terms; gravity / "
+                                       "rotating frame / viscosity on the reference path" if cfg4 else
+                                       f"config 3: gas + {S} dust species (inputs/drag state + seeded "
+                                       f"perturbation), PLM+HLLE, rk2, periodic, {M}^3 zones in TOTAL in "
+                                       f"{B}^3 MeshBlocks split over {world} GPU(s) (strong scaling); "
+                                       + ("Drag::DragSource stays on the reference path" if args.no_drag
+                                          else "implicit gas-dust drag (constant stopping times) every stage, "
+                                               "split stage: passes -> drag -> SetAux/C2P/P2C")),
                           "zones_total": zones, "ranks": list(lay), "stage_path": md.stage_path(),
                           "l2": "state >> 126 MB L2, no flush needed"},
                "roofline": {"bound": "hbm", "achieved": value * alg / world / 1e9, "peak": peak,
@@ -369,7 +410,7 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
-    if args.config == 3:
+    if args.config in (3, 4):
         main_config3(args)
         return
     import torch

@@ -209,6 +209,15 @@ typedef struct ab200_sources_desc {
 } ab200_sources_desc;
 int ab200_configure_sources(ab200_ctx *ctx, const ab200_sources_desc *src);
 
+/* ---- history reductions -------------------------------------------------
+ * out_host[v] = sum over the interior zones of the partition of cons0[v] * Volume, for every
+ * conserved pack entry v of `fluid` (nout = its pack size): the integrals behind gas_mass,
+ * gas_momentum_x{1,2,3}, gas_energy, gas_internal_energy and the dust ones --
+ * ArtemisUtils::ReduceSpeciesVolumeIntegral / ReduceSpeciesVectorVolumeIntegral
+ * (src/utils/history.hpp:24-95, registered in src/gas/gas.cpp:650-675).  One launch for all
+ * entries + one ordered finishing kernel (deterministic); synchronises the stream. */
+int ab200_history_volume_integrals(ab200_ctx *ctx, int fluid, double *out_host, int nout);
+
 /* Which kernels ab200_fused_stage runs on meshes where both exist (3-D Cartesian, TMA-able
  * arrays); every other mesh always takes the directional passes.
  *   AB200_PATH_AUTO         the faster of the two as measured on B200 for the bound fluid's

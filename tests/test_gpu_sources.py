@@ -132,3 +132,40 @@ def test_device_resident_cycles_with_configured_sources(variant):
         assert ts[0] == d1.dt and ts[2] == d1.time
     md1.close()
     md2.close()
+
+
+@pytest.mark.parametrize("coords", [Coordinates.cartesian, Coordinates.spherical3D,
+                                    Coordinates.cylindrical])
+def test_history_volume_integrals(coords):
+    """ab200_history_volume_integrals == sum(u * Volume) over interior zones (history.hpp:24-95)
+    with the oracle's cell volumes, for every conserved pack entry of gas and dust."""
+    import ctypes as C
+    from oracle import oracle_py
+    bcs = (BoundaryFlag.outflow,) * 6 if coords != Coordinates.cartesian else None
+    mesh = make_mesh(coords, 3, bcs=bcs)
+    gp, dp = gas_params(coords, "ppm", "hllc", S=2), dust_params(coords, "plm", "hlle", S=2)
+    md = MeshData(mesh, gas=gp, dust=dp, materialize_fluxes=False)
+    md.gas.prim.set(random_prim(mesh, gp, seed=91))
+    md.dust.prim.set(random_prim(mesh, dp, seed=92))
+    md.call("ab200_prim_to_cons")
+    L = oracle_py.lib()
+    vol = np.zeros((mesh.nb, mesh.nk, mesh.nj, mesh.ni))
+    out = np.zeros(32)
+    DP = C.POINTER(C.c_double)
+    for b in range(mesh.nb):
+        xm, dx = np.ascontiguousarray(mesh.blk_xmin[b]), np.ascontiguousarray(mesh.blk_dx[b])
+        for k in range(mesh.ks, mesh.ke + 1):
+            for j in range(mesh.js, mesh.je + 1):
+                for i in range(mesh.is_, mesh.ie + 1):
+                    L.ao_geom_cell(int(coords), xm.ctypes.data_as(DP), dx.ctypes.data_as(DP), k, j, i,
+                                   out.ctypes.data_as(DP))
+                    vol[b, k, j, i] = out[6]
+    for ff in md.fluids:
+        nv = ff.fp.nvar
+        got = np.zeros(nv)
+        md.call("ab200_history_volume_integrals", int(ff.fp.fluid_type), got.ctypes.data_as(DP), nv)
+        u0 = ff.u0.get()
+        want = np.array([np.sum(u0[:, v] * vol) for v in range(nv)])
+        scale = np.array([np.sum(np.abs(u0[:, v]) * vol) for v in range(nv)])
+        assert np.max(np.abs(got - want) / scale) <= 1e-13
+    md.close()
