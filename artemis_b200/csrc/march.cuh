@@ -142,6 +142,15 @@ k_march_pass(GridDev g, FluidDev f, FusedArgs a) {
   for (int m = 0; m < 8; ++m) AA[m] = AB[m] = 0.0;
   const int cend = s0 + L;
   double tmin = 1.79769313486231570815e+308;
+  double tden = 0.0;                   // Cartesian fast build: max of sum_d (|v_d| + c_s) / dx_d
+  double rdx[3] = {0.0, 0.0, 0.0};     // 1 / dx_d of this pencil's block (0 beyond ndim)
+  if (HOIST && LAST) {
+    const double *x1f = g.t.x1f + (size_t)b * (g.ni + 1), *x2f = g.t.x2f + (size_t)b * (g.nj + 1);
+    const double *x3f = g.t.x3f + (size_t)b * (g.nk + 1);
+    rdx[0] = drcp(x1f[g.is + 1] - x1f[g.is]);
+    if (g.ndim >= 2) rdx[1] = drcp(x2f[g.js + 1] - x2f[g.js]);
+    if (g.ndim >= 3) rdx[2] = drcp(x3f[g.ks + 1] - x3f[g.ks]);
+  }
 
   // one marching step for cell c; Wa..Wd = q(c-1), q(c), q(c+1), q(c+2)
   auto step = [&](const int c, double(&Wa)[NV], double(&Wb)[NV], double(&Wc)[NV],
@@ -251,6 +260,39 @@ k_march_pass(GridDev g, FluidDev f, FusedArgs a) {
       if (!LAST) {
 #pragma unroll
         for (int m = 0; m < NV; ++m) __stcg(pu[m] + off, u[m]);
+      } else if (HOIST) {
+        // Cartesian fast build: SetAuxillaryFields + ConsToPrim + PrimToCons + the CFL estimate
+        // (fill_derived.cpp:55-72, 129-164, 217-274; gas.cpp:411-433) with ONE reciprocal of the
+        // floored density and one inverse root (h == 1; the generic branch below spends twelve
+        // Newton sequences on the same zone, three of them dividing by the constant 1).  The
+        // timestep is reduced as max over zones of sum_d (|v_d| + c_s) / dx_d and inverted once.
+        const double w_d = (u[0] > f.dfloor) ? u[0] : f.dfloor;
+        const double rwd = drcp(w_d);
+        const double v1 = u[1] * rwd, v2 = u[2] * rwd, v3 = u[3] * rwd;
+        const double ke = 0.5 * w_d * (sqr(v1) + sqr(v2) + sqr(v3));
+        __stcg(pq[wslot[0]] + off, w_d);
+        __stcg(pq[wslot[1]] + off, v1);
+        __stcg(pq[wslot[2]] + off, v2);
+        __stcg(pq[wslot[3]] + off, v3);
+        __stcg(pu[0] + off, w_d);
+        __stcg(pu[1] + off, w_d * v1);
+        __stcg(pu[2] + off, w_d * v2);
+        __stcg(pu[3] + off, w_d * v3);
+        double cs = 0.0;
+        if (gas) {
+          const double ue = u[4] - ke;
+          double w_s = ((ue > f.de_switch * u[4]) ? ue : u[5]) * rwd;
+          w_s = dmax(w_s, f.siefloor);
+          const double u_u = w_s * w_d;
+          __stcg(pq[wslot[5]] + off, w_s);
+          __stcg(pq[wslot[4]] + off, dmax(0.0, f.gm1 * w_d * w_s));
+          __stcg(pu[5] + off, u_u);
+          __stcg(pu[4] + off, u_u + ke);
+          if (a.dt_min) cs = dsqrt(dmax(0.0, (f.gm1 + 1) * f.gm1 * w_d * w_s) * rwd);
+        }
+        if (a.dt_min)
+          tden = dmax(tden, (fabs(v1) + cs) * rdx[0] + (fabs(v2) + cs) * rdx[1] +
+                                (fabs(v3) + cs) * rdx[2]);
       } else {
         const double hx[3] = {cc.hx1v(), cc.hx2v(), cc.hx3v()};
         if (gas)  // SetAuxillaryFields (fill_derived.cpp:55-72)
@@ -318,6 +360,7 @@ k_march_pass(GridDev g, FluidDev f, FusedArgs a) {
     step(c + 3, W3, W0, W1, W2, IB, IA, QB, QA, UB, UA, AB, AA);
   }
   if (a.dt_min) {  // warp-shuffle min, one atomic per warp
+    if (HOIST && LAST && tden > 0.0) tmin = drcp(tden);
     if (__activemask() == 0xffffffffu) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) tmin = dmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
