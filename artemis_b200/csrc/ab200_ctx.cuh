@@ -186,6 +186,7 @@ int launch_exchange(ab200_ctx *c, int fluid);
 int launch_physical_bcs(ab200_ctx *c, int fluid);
 int launch_fill_ghosts(ab200_ctx *c, int fluid, int remote_pass);
 bool topology_is_local(const ab200_ctx *c);
+int launch_finish_stage(ab200_ctx *c, int fluid, unsigned long long *dt_min);
 // one stage of the device-resident drivers: fused stage (+ sources + finish when configured)
 int run_stage(ab200_ctx *c, double g0, double g1, double beta, int pcm, int first, int last);
 int launch_halo(ab200_ctx *c, const ab200_bnd_desc *bnd, int n, int unpack);

@@ -594,14 +594,20 @@ int ab200_fused_stage(ab200_ctx *c, double gam0, double gam1, double beta, doubl
 int ab200_finish_stage(ab200_ctx *c, int flags) {
   AB_ENTER(c)
   AB_REQUIRE((flags & ~AB200_STAGE_REDUCE_DT) == 0, AB200_EINVAL, "ab200_finish_stage: unknown flag");
+  const int reduce_dt = (flags & AB200_STAGE_REDUCE_DT) != 0;
+  unsigned long long *slots = reinterpret_cast<unsigned long long *>(c->d_red + 3072);
+  if (reduce_dt)
+    AB_CUDA(cudaMemcpyAsync(slots, c->d_red + 3080, 2 * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToDevice, c->stream));
   int any = 0;
   for (int f = 0; f < 2; ++f) {
     if (!c->fl[f].bound) continue;
     AB_TRY(sync_prim_home(c, f, 0));
-    if (f == AB200_GAS) AB_TRY(launch_set_aux(c));
-    AB_TRY(launch_cons_to_prim(c, f));
-    AB_TRY(launch_prim_to_cons(c, f, 0));
-    if (flags & AB200_STAGE_REDUCE_DT) AB_TRY(launch_estimate_dt(c, f, c->d_time + 1, any));
+    // one pointwise kernel per fluid: SetAux + C2P + interior P2C (+ CFL minimum)
+    AB_TRY(launch_finish_stage(c, f, reduce_dt ? slots + f : nullptr));
+    if (reduce_dt)
+      AB_TRY(launch_finish_dt(c, reinterpret_cast<const double *>(slots + f), 1, c->fl[f].d.cfl,
+                              c->d_time + 1, any));
     any = 1;
   }
   AB_REQUIRE(any, AB200_ESTATE, "ab200_finish_stage: no fluid bound");

@@ -178,6 +178,86 @@ k_drag_simple(GridDev g, FluidDev fg, FluidDev fd_, double dt_host, const double
   }
 }
 
+// SetAuxillaryFields + ConsToPrim + interior PrimToCons (+ the CFL estimate) of ONE fluid in one
+// pointwise kernel: the second half of a split stage (fill_derived.cpp:55-72, 129-164, 217-274;
+// gas.cpp:411-433 / dust.cpp:256-272).  Same device functions, same operation order as the LAST
+// marching pass (march.cuh), so the strict build stays bit-identical to the task kernels.
+template <int GEOM, int FLUID>
+__global__ void __launch_bounds__(kThreads)
+k_finish_stage(GridDev g, FluidDev f, unsigned long long *dt_min) {
+  constexpr bool gas = (FLUID == AB200_GAS);
+  const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  double tmin = 1.79769313486231570815e+308;
+  if (t < (long long)g.nb * nkr * njr * nir) {
+    const CellIdx c = decode(t, nir, njr, nkr, g.is, g.js, g.ks);
+    Coords<GEOM> cc(g, c.b, c.k, c.j, c.i);
+    const double hx[3] = {cc.hx1v(), cc.hx2v(), cc.hx3v()};
+    const size_t off = ((size_t)c.k * g.nj + c.j) * g.ni + c.i;
+    const int S = f.S;
+    const size_t e = (size_t)c.b * f.nvar;
+    for (int n = 0; n < S; ++n) {
+      double u[6];
+      u[0] = f.u0[e + n][off];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) u[1 + d] = f.u0[e + S + 3 * n + d][off];
+      if (gas) {
+        u[4] = f.u0[e + 4 * S + n][off];
+        u[5] = f.u0[e + 5 * S + n][off];
+        u[5] = set_aux_cell(u[0], u[1], u[2], u[3], u[4], u[5], hx, f.dfloor, f.siefloor, f.de_switch);
+      }
+      double w_d = (u[0] > f.dfloor) ? u[0] : f.dfloor;
+      const double v1 = ddiv(u[1], w_d * hx[0]), v2 = ddiv(u[2], w_d * hx[1]),
+                   v3 = ddiv(u[3], w_d * hx[2]);
+      w_d = (w_d > f.dfloor) ? w_d : f.dfloor;
+      f.prim[e + n][off] = w_d;
+      f.prim[e + S + 3 * n + 0][off] = v1;
+      f.prim[e + S + 3 * n + 1][off] = v2;
+      f.prim[e + S + 3 * n + 2][off] = v3;
+      f.u0[e + n][off] = w_d;
+      f.u0[e + S + 3 * n + 0][off] = w_d * v1 * hx[0];
+      f.u0[e + S + 3 * n + 1][off] = w_d * v2 * hx[1];
+      f.u0[e + S + 3 * n + 2][off] = w_d * v3 * hx[2];
+      const double vel[3] = {v1, v2, v3};
+      if (gas) {
+        double w_s = ddiv(u[5], (u[0] > f.dfloor) ? u[0] : f.dfloor);
+        w_s = (w_s > f.siefloor) ? w_s : f.siefloor;
+        const double u_u = w_s * w_d;
+        f.prim[e + 5 * S + n][off] = w_s;
+        f.prim[e + 4 * S + n][off] = dmax(0.0, f.gm1 * w_d * w_s);
+        f.u0[e + 5 * S + n][off] = u_u;
+        const double ke = 0.5 * w_d * (sqr(v1) + sqr(v2) + sqr(v3));
+        f.u0[e + 4 * S + n][off] = u_u + ke;
+        if (dt_min) tmin = dmin(tmin, cell_dt<GEOM, FLUID>(g, f, cc, w_d, vel, w_s));
+      } else if (dt_min) {
+        tmin = dmin(tmin, cell_dt<GEOM, FLUID>(g, f, cc, w_d, vel, 0.0));
+      }
+    }
+  }
+  if (dt_min) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmin = dmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(dt_min, (unsigned long long)__double_as_longlong(tmin));
+  }
+}
+
+int launch_finish_stage(ab200_ctx *c, int fluid, unsigned long long *dt_min) {
+  const GridDev &g = c->g;
+  const FluidDev &f = c->fl[fluid].d;
+  const long long n = (long long)g.nb * (g.ke - g.ks + 1) * (g.je - g.js + 1) * (g.ie - g.is + 1);
+  const unsigned grid = (unsigned)((n + kThreads - 1) / kThreads);
+  NvtxRange nvtx_("SetAuxillaryFields + ConsToPrim + PrimToCons [fused]");
+  int rc = dispatch_geom_s(g.geom, [&](auto G) {
+    constexpr int GG = decltype(G)::value;
+    if (fluid == AB200_GAS) k_finish_stage<GG, AB200_GAS><<<grid, kThreads, 0, c->stream>>>(g, f, dt_min);
+    else k_finish_stage<GG, AB200_DUST><<<grid, kThreads, 0, c->stream>>>(g, f, dt_min);
+    return AB200_OK;
+  });
+  c->launches++;
+  AB_CUDA(cudaGetLastError());
+  return rc;
+}
+
 static unsigned grid_s(const GridDev &g) {
   const long long n = (long long)g.nb * (g.ke - g.ks + 1) * (g.je - g.js + 1) * (g.ie - g.is + 1);
   return (unsigned)((n + kThreads - 1) / kThreads);
