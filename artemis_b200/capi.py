@@ -69,7 +69,7 @@ SYMBOLS = [
     "ab200_launch_count", "ab200_timer_begin", "ab200_timer_end",
     "ab200_history_volume_integrals", "ab200_configure_sources", "ab200_finish_stage", "ab200_uniform_gravity", "ab200_shearing_box", "ab200_drag_simple",
     "ab200_comm_unique_id", "ab200_comm_init", "ab200_comm_destroy", "ab200_comm_set_layout",
-    "ab200_comm_bytes_per_exchange", "ab200_comm_exchange_begin", "ab200_comm_exchange_end",
+    "ab200_comm_bytes_per_exchange", "ab200_comm_is_direct", "ab200_comm_exchange_begin", "ab200_comm_exchange_end",
     "ab200_allreduce_min", "ab200_run_cycles_mr", "ab200_comm_plan_direct", "ab200_comm_plan_free",
 ]
 
@@ -135,7 +135,7 @@ def load(variant: str | None = None) -> C.CDLL:
         "ab200_shearing_box": [vp, d, d, d], "ab200_drag_simple": [vp, d, i, _DP],
         "ab200_comm_unique_id": [C.c_char_p], "ab200_comm_init": [vp, i, i, C.c_char_p],
         "ab200_comm_destroy": [vp], "ab200_comm_set_layout": [vp, i, i, i, C.POINTER(C.c_int)],
-        "ab200_comm_exchange_begin": [vp], "ab200_comm_exchange_end": [vp],
+        "ab200_comm_is_direct": [vp], "ab200_comm_exchange_begin": [vp], "ab200_comm_exchange_end": [vp],
         "ab200_allreduce_min": [vp, vp], "ab200_run_cycles_mr": [vp, i, i, d],
         "ab200_comm_plan_direct": [C.POINTER(C.c_int)] * 5 + [i] + [C.POINTER(C.c_int)] * 5 +
                                   [C.POINTER(C.POINTER(C.c_longlong)), C.POINTER(C.c_int)],

@@ -36,6 +36,7 @@ struct NcclApi {
   int (*CommInitRank)(NcclComm *, int, NcclUniqueId, int) = nullptr;
   int (*CommDestroy)(NcclComm) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t) = nullptr;
   int (*Send)(const void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*Recv)(void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
@@ -65,6 +66,7 @@ static NcclApi *nccl_api() {
   AB_SYM(CommInitRank, "ncclCommInitRank")
   AB_SYM(CommDestroy, "ncclCommDestroy")
   AB_SYM(AllReduce, "ncclAllReduce")
+  AB_SYM(AllGather, "ncclAllGather")
   AB_SYM(Send, "ncclSend")
   AB_SYM(Recv, "ncclRecv")
   AB_SYM(GroupStart, "ncclGroupStart")
@@ -177,7 +179,48 @@ struct CommState {
   double *dsend = nullptr, *drecv = nullptr;
   std::vector<ab200_bnd_desc> send_desc, recv_desc;
   long long bytes_per_exchange = 0;
+  // ---- direct transport: the pack kernel stores straight into the PEER's receive slab over
+  // NVLink (CUDA IPC mappings exchanged once), a flag per peer replaces the NCCL round
+  bool direct = false;
+  double *rslab[2] = {nullptr, nullptr};          // local receive slabs, alternating by step
+  unsigned long long *flags = nullptr;            // local [nranks]: last step each peer delivered
+  int *d_err = nullptr;                           // set by a wait that timed out
+  std::vector<double *> peer_rslab[2];            // [peer index] mapped receive slabs of the peers
+  std::vector<unsigned long long *> peer_flags;   // [peer index] mapped flag arrays of the peers
+  std::vector<void *> ipc_opened;
+  std::vector<ab200_bnd_desc> dsend_desc[2], drecv_desc[2];
+  int *d_peer_rank = nullptr;                     // device copy of the peer ranks
+  unsigned long long **d_peer_flags = nullptr;    // device copy of peer_flags
+  unsigned long long step = 0;
 };
+
+// signal: my step counter into every peer's flag array (after the pack kernel of this stream
+// has completed, i.e. its remote stores are performed); wait: until every peer delivered `step`
+__global__ void k_comm_signal(unsigned long long *const *peer_flags, int npeers, int my_rank,
+                              unsigned long long step) {
+  const int t = threadIdx.x;
+  if (t < npeers) {
+    __threadfence_system();
+    *((volatile unsigned long long *)(peer_flags[t] + my_rank)) = step;
+    __threadfence_system();
+  }
+}
+__global__ void k_comm_wait(const unsigned long long *flags, const int *peer_rank, int npeers,
+                            unsigned long long step, int *err) {
+  const int t = threadIdx.x;
+  if (t < npeers) {
+    const volatile unsigned long long *f = flags + peer_rank[t];
+    long long spins = 0;
+    while (*f < step) {
+      __nanosleep(200);
+      if (++spins > 20000000LL) {  // ~ 4 s: a peer died; do not hang the GPU
+        *err = 1;
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+}
 
 static CommState *cs_of(ab200_ctx *c) { return static_cast<CommState *>(c->comm_state); }
 
@@ -215,7 +258,12 @@ int ab200_comm_init(ab200_ctx *c, int nranks, int rank, const char *id128) {
     delete cs;
     return AB200_ECUDA;
   }
-  cudaStreamCreateWithFlags(&cs->stream, cudaStreamNonBlocking);
+  // default priority; AB200_COMM_HIGH_PRIO=1 raises it (measured: it makes the overlapped cycle
+  // slower, see ab200_run_cycles_mr)
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  cudaStreamCreateWithPriority(&cs->stream, cudaStreamNonBlocking,
+                               getenv("AB200_COMM_HIGH_PRIO") ? prio_hi : prio_lo);
   cudaEventCreateWithFlags(&cs->ev_stage, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&cs->ev_done, cudaEventDisableTiming);
   c->comm_state = cs;
@@ -231,6 +279,13 @@ int ab200_comm_destroy(ab200_ctx *c) {
   if (cs->comm) nccl_api()->CommDestroy(cs->comm);
   if (cs->dsend) cudaFree(cs->dsend);
   if (cs->drecv) cudaFree(cs->drecv);
+  for (void *p : cs->ipc_opened) cudaIpcCloseMemHandle(p);
+  for (int q = 0; q < 2; ++q)
+    if (cs->rslab[q]) cudaFree(cs->rslab[q]);
+  if (cs->flags) cudaFree(cs->flags);
+  if (cs->d_err) cudaFree(cs->d_err);
+  if (cs->d_peer_rank) cudaFree(cs->d_peer_rank);
+  if (cs->d_peer_flags) cudaFree(cs->d_peer_flags);
   cudaEventDestroy(cs->ev_stage);
   cudaEventDestroy(cs->ev_done);
   cudaStreamDestroy(cs->stream);
@@ -323,7 +378,115 @@ int ab200_comm_set_layout(ab200_ctx *c, int layx, int layy, int layz, const int 
   }
   cs->bytes_per_exchange = 8 * so;
   cs->planned = true;
+  cs->direct = false;
+  if (!cs->peers.empty() && !getenv("AB200_NO_DIRECT")) {
+    // ---- direct transport over CUDA IPC peer mappings -----------------------------------------
+    // Every rank owns two receive slabs (alternating by step: a sender may write step s+1 while
+    // the receiver still unpacks step s; it cannot run two steps ahead because it waits for the
+    // receiver's own step-s+1 flag first) and one flag array.  The handles are all-gathered once.
+    NcclApi *n = nccl_api();
+    const int R = cs->nranks;
+    for (int q = 0; q < 2; ++q) {
+      if (cs->rslab[q]) cudaFree(cs->rslab[q]);
+      AB_CUDA(cudaMalloc((void **)&cs->rslab[q], sizeof(double) * std::max<long long>(ro, 1)));
+    }
+    if (!cs->flags) AB_CUDA(cudaMalloc((void **)&cs->flags, sizeof(unsigned long long) * R));
+    if (!cs->d_err) AB_CUDA(cudaMalloc((void **)&cs->d_err, sizeof(int)));
+    AB_CUDA(cudaMemset(cs->flags, 0, sizeof(unsigned long long) * R));
+    AB_CUDA(cudaMemset(cs->d_err, 0, sizeof(int)));
+    cs->step = 0;
+    struct Handles { cudaIpcMemHandle_t slab[2], flags; };
+    std::vector<Handles> all(R);
+    bool ok = cudaIpcGetMemHandle(&all[cs->rank].slab[0], cs->rslab[0]) == cudaSuccess &&
+              cudaIpcGetMemHandle(&all[cs->rank].slab[1], cs->rslab[1]) == cudaSuccess &&
+              cudaIpcGetMemHandle(&all[cs->rank].flags, cs->flags) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    Handles *d_all = nullptr;
+    AB_CUDA(cudaMalloc((void **)&d_all, sizeof(Handles) * R));
+    AB_CUDA(cudaMemcpy(d_all + cs->rank, &all[cs->rank], sizeof(Handles), cudaMemcpyHostToDevice));
+    AB_NCCL(n->AllGather(d_all + cs->rank, d_all, sizeof(Handles), /*ncclChar*/ 0, cs->comm, c->stream));
+    AB_CUDA(cudaStreamSynchronize(c->stream));
+    AB_CUDA(cudaMemcpy(all.data(), d_all, sizeof(Handles) * R, cudaMemcpyDeviceToHost));
+    AB_CUDA(cudaFree(d_all));
+    // every rank must take the same decision: all-reduce the "ok" bit through the dt reducer
+    double *d_ok = nullptr;
+    AB_CUDA(cudaMalloc((void **)&d_ok, sizeof(double)));
+    for (void *p : cs->ipc_opened) cudaIpcCloseMemHandle(p);
+    cs->ipc_opened.clear();
+    for (int q = 0; q < 2; ++q) cs->peer_rslab[q].assign(cs->peers.size(), nullptr);
+    cs->peer_flags.assign(cs->peers.size(), nullptr);
+    for (size_t pi = 0; pi < cs->peers.size() && ok; ++pi) {
+      const Handles &h = all[cs->peers[pi].rank];
+      void *p0 = nullptr, *p1 = nullptr, *pf = nullptr;
+      ok = cudaIpcOpenMemHandle(&p0, h.slab[0], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+           cudaIpcOpenMemHandle(&p1, h.slab[1], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+           cudaIpcOpenMemHandle(&pf, h.flags, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      if (!ok) { cudaGetLastError(); break; }
+      cs->ipc_opened.push_back(p0); cs->ipc_opened.push_back(p1); cs->ipc_opened.push_back(pf);
+      cs->peer_rslab[0][pi] = (double *)p0;
+      cs->peer_rslab[1][pi] = (double *)p1;
+      cs->peer_flags[pi] = (unsigned long long *)pf;
+    }
+    const double okv = ok ? 1.0 : 0.0;
+    AB_CUDA(cudaMemcpy(d_ok, &okv, sizeof(double), cudaMemcpyHostToDevice));
+    AB_NCCL(n->AllReduce(d_ok, d_ok, 1, kNcclFloat64, kNcclMin, cs->comm, c->stream));
+    double all_ok = 0.0;
+    AB_CUDA(cudaMemcpyAsync(&all_ok, d_ok, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    AB_CUDA(cudaStreamSynchronize(c->stream));
+    AB_CUDA(cudaFree(d_ok));
+    if (all_ok == 1.0) {
+      // where MY message starts inside each peer's receive slab: the peer's own plan (a pure
+      // function of its lattice position; all ranks own tiles of the same shape)
+      std::vector<long long> my_off_in_peer(cs->peers.size(), 0);
+      for (size_t pi = 0; pi < cs->peers.size(); ++pi) {
+        const int pr = cs->peers[pi].rank;
+        const int prl[3] = {pr % layx, (pr / layx) % layy, pr / (layx * layy)};
+        std::vector<PlanRow> prow;
+        std::map<int, std::pair<long long, long long>> psz;
+        plan_direct(nbd, nt, s, e, ng, nfl, ftype, fS, lay, prl, per, prow, psz);
+        long long off = 0;
+        for (auto &kv : psz) {
+          if (kv.first == cs->rank) break;
+          off += kv.second.second;
+        }
+        my_off_in_peer[pi] = off;
+      }
+      for (int q = 0; q < 2; ++q) {
+        cs->dsend_desc[q].clear();
+        cs->drecv_desc[q].clear();
+      }
+      for (const PlanRow &r : rows) {
+        const size_t pi = index[r.peer];
+        const CommState::Peer &p = cs->peers[pi];
+        for (int q = 0; q < 2; ++q) {
+          ab200_bnd_desc d{r.fluid, r.block, r.var0, r.ncomp, r.si, r.ei, r.sj, r.ej, r.sk, r.ek, nullptr};
+          if (r.recv) {
+            d.buf = cs->rslab[q] + p.roff + r.offset;
+            cs->drecv_desc[q].push_back(d);
+          } else {
+            d.buf = cs->peer_rslab[q][pi] + my_off_in_peer[pi] + r.offset;
+            cs->dsend_desc[q].push_back(d);
+          }
+        }
+      }
+      std::vector<int> pr(cs->peers.size());
+      for (size_t pi = 0; pi < cs->peers.size(); ++pi) pr[pi] = cs->peers[pi].rank;
+      if (cs->d_peer_rank) cudaFree(cs->d_peer_rank);
+      if (cs->d_peer_flags) cudaFree(cs->d_peer_flags);
+      AB_CUDA(cudaMalloc((void **)&cs->d_peer_rank, sizeof(int) * pr.size()));
+      AB_CUDA(cudaMalloc((void **)&cs->d_peer_flags, sizeof(void *) * pr.size()));
+      AB_CUDA(cudaMemcpy(cs->d_peer_rank, pr.data(), sizeof(int) * pr.size(), cudaMemcpyHostToDevice));
+      AB_CUDA(cudaMemcpy(cs->d_peer_flags, cs->peer_flags.data(), sizeof(void *) * pr.size(),
+                         cudaMemcpyHostToDevice));
+      cs->direct = true;
+    }
+  }
   return AB200_OK;
+}
+
+int ab200_comm_is_direct(ab200_ctx *c) {
+  CommState *cs = c ? cs_of(c) : nullptr;
+  return cs && cs->direct ? 1 : 0;
 }
 
 long long ab200_comm_bytes_per_exchange(ab200_ctx *c) {
@@ -350,6 +513,28 @@ int ab200_comm_exchange_begin(ab200_ctx *c) {
   const bool saved_set = c->halo_stream_set;
   c->halo_stream = cs->stream;
   c->halo_stream_set = true;
+  if (cs->direct) {
+    // pack = remote stores into the peers' receive slabs; signal; wait for every peer's signal;
+    // unpack from the own slab.  No NCCL on the data path.
+    const int q = (int)(cs->step & 1);
+    const unsigned long long stepno = cs->step + 1;
+    const int np = (int)cs->peers.size();
+    int rc = launch_halo(c, cs->dsend_desc[q].data(), (int)cs->dsend_desc[q].size(), 0);
+    if (rc == AB200_OK) {
+      k_comm_signal<<<1, 32 * ((np + 31) / 32), 0, cs->stream>>>(cs->d_peer_flags, np, cs->rank, stepno);
+      k_comm_wait<<<1, 32 * ((np + 31) / 32), 0, cs->stream>>>(cs->flags, cs->d_peer_rank, np, stepno, cs->d_err);
+      c->launches += 2;
+      rc = launch_halo(c, cs->drecv_desc[q].data(), (int)cs->drecv_desc[q].size(), 1);
+    }
+    c->halo_stream = saved;
+    c->halo_stream_set = saved_set;
+    AB_TRY(rc);
+    AB_CUDA(cudaGetLastError());
+    AB_CUDA(cudaEventRecord(cs->ev_done, cs->stream));
+    cs->step++;
+    cs->in_flight = true;
+    return AB200_OK;
+  }
   int rc = launch_halo(c, cs->send_desc.data(), (int)cs->send_desc.size(), 0);
   if (rc == AB200_OK) {
     int e = n->GroupStart();
@@ -425,11 +610,15 @@ int ab200_run_cycles_mr(ab200_ctx *c, int integrator, int ncycles, double tlim) 
     ~Restore() { c->ghost_cons_lazy = v; }
   } restore{c, lazy_before};
   const bool remote = cs && cs->planned && !cs->peers.empty();
-  // Overlap: stage the blocks that touch another rank first, start the remote round as soon as
-  // they are done and run the interior blocks' stage underneath it.  Needs the directional
-  // passes (block subsets) for every bound fluid and no split-stage source terms.
-  bool split = remote && !c->has_sources && fused_supports_subsets(c) && c->n_blist[0] > 0 &&
-               c->n_blist[1] > 0 && !getenv("AB200_NO_OVERLAP");
+  // Overlap (opt-in, AB200_OVERLAP=1): stage the blocks that touch another rank first, start the
+  // remote round as soon as they are done and run the interior blocks' share of the last pass
+  // underneath it.  Measured on B200 (r02, A/B inside one box, 256^3 per GPU): N = 4: 4.467 ms
+  // per cycle without overlap, 4.570 with it, 4.679 with a high-priority comm stream -- the stage
+  // kernels are latency-bound at low occupancy, so sharing SMs with the transport kernels and
+  // paying one extra launch costs more than the 0.13 ms round it hides; N = 2: 4.556 vs 4.597
+  // (marginal gain).  Hence off by default.
+  bool split = remote && getenv("AB200_OVERLAP") && !c->has_sources && fused_supports_subsets(c) &&
+               c->n_blist[0] > 0 && c->n_blist[1] > 0;
   for (int f = 0; f < 2 && split; ++f)
     if (c->fl[f].bound && sweep_eligible(c, f)) split = false;
   for (int cyc = 0; cyc < ncycles; ++cyc) {

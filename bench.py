@@ -666,6 +666,8 @@ def main():
                                    (" + fused ghost fill + device-resident dt" if world == 1 else
                                     " + single-round NCCL halo exchange + device-resident dt all-reduce"),
                            "state": args.state, "transport": args.transport if world > 1 else None,
+                           "peer_write_ipc": (bool(md.L.ab200_comm_is_direct(md.ctx)) if native is not None else None),
+                           "overlap": bool(os.environ.get("AB200_OVERLAP")) if world > 1 else None,
                            "stage_path": path, "halo_exchange_ms": comm_ms, "host_issue_ms_per_step": cpu_issue_ms,
                            "halo_bytes_per_exchange": (comm.bytes_per_direct_exchange if comm else 0)},
                 "roofline": roofline, "cpu_baseline": base, "e2e": e2e,

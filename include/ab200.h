@@ -374,6 +374,11 @@ int ab200_comm_init(ab200_ctx *ctx, int nranks, int rank, const char *id128);
 int ab200_comm_destroy(ab200_ctx *ctx);
 int ab200_comm_set_layout(ab200_ctx *ctx, int layx, int layy, int layz, const int *periodic3);
 long long ab200_comm_bytes_per_exchange(ab200_ctx *ctx);
+/* 1 if the exchange runs over CUDA IPC peer mappings (the pack kernel stores straight into the
+ * peers' receive slabs over NVLink, one flag per peer; NCCL only bootstraps the handles and does
+ * the dt all-reduce), 0 if it goes through grouped ncclSend / ncclRecv (AB200_NO_DIRECT=1 or IPC
+ * unavailable on some rank). */
+int ab200_comm_is_direct(ab200_ctx *ctx);
 int ab200_comm_exchange_begin(ab200_ctx *ctx);
 int ab200_comm_exchange_end(ab200_ctx *ctx);
 /* in-place MIN all-reduce of one DEVICE double on the context's stream; identity without a

@@ -93,9 +93,11 @@ for f, (wp, wu) in zip(tmd.fluids, want):
 flag = torch.tensor([1.0 if ok else 0.0], device=f"cuda:{local}")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("check_multigpu: world %d lattice %s cycles %d transport %s -> %s" % (
-        world, lay, args.cycles, args.transport,
-        "BIT-IDENTICAL" if flag.item() == 1.0 else "MISMATCH"))
+    direct = int(tmd.L.ab200_comm_is_direct(tmd.ctx)) if args.transport == "native" else 0
+    print("check_multigpu: world %d lattice %s cycles %d transport %s (peer-write over CUDA IPC: %s, "
+          "overlap: %s) -> %s" % (world, lay, args.cycles, args.transport, bool(direct),
+                                  bool(os.environ.get("AB200_OVERLAP")),
+                                  "BIT-IDENTICAL" if flag.item() == 1.0 else "MISMATCH"))
 tmd.close()
 dist.destroy_process_group()
 sys.exit(0 if flag.item() == 1.0 else 1)
