@@ -38,8 +38,11 @@ def parse():
     ap.add_argument("--tile", type=int, default=256, help="zones per GPU per direction")
     ap.add_argument("--block", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample", type=int, default=128, help="CPU baseline mesh size")
-    ap.add_argument("--cpu-cycles", type=int, default=4)
+    ap.add_argument("--cpu-sample", type=int, default=256,
+                    help="CPU baseline mesh size per direction (default: the GPU arm's own 256^3 "
+                         "single-GPU mesh, so both arms run the SAME config; the sample is bounded "
+                         "in cycles, not in mesh size)")
+    ap.add_argument("--cpu-cycles", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
@@ -148,8 +151,8 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_baseline(args, steps=None):
-    """The oracle (CPU restatement of the reference path) timed on the host cores: a bounded
-    sample of the same workload (same numerics, smaller mesh)."""
+    """The reference's CPU implementation of the path timed on the host cores: a bounded number
+    of cycles of the same workload (by default the same 256^3 mesh as the GPU arm at N = 1)."""
     from artemis_b200 import pgen
     from artemis_b200.enums import BoundaryFlag, Coordinates, Fluid, ReconstructionMethod, RSolver
     from artemis_b200.mesh import UniformMesh
@@ -201,9 +204,10 @@ def run_reference(args):
             "unit": "zone-cycles/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3D Sedov blast PPM+HLLC rk2 fp64, bounded sample "
-                                   f"{args.cpu_sample}^3 per step on host cores (GPU arm: "
-                                   f"{args.tile}^3 per GPU, 64^3 MeshBlocks)",
+            "config": {"workload": f"3D Sedov blast PPM+HLLC rk2 fp64, {args.cpu_sample}^3 zones in 64^3 "
+                                   f"MeshBlocks, one rk2 cycle per step on the host cores (GPU arm: "
+                                   f"{args.tile}^3 per GPU, 64^3 MeshBlocks"
+                                   + (" -- the same mesh)" if args.cpu_sample == args.tile else ")"),
                        "note": "the full Kokkos/Parthenon build needs cmake and is not "
                                "buildable under this round's rules; this times the reference's "
                                "own hot-path sources compiled against a mock Parthenon "
