@@ -40,11 +40,17 @@ class RefineDesc(C.Structure):
                                        "cjs", "cje", "cks", "cke")] + [("coarse", C.c_void_p)]
 
 
+class PointMassDesc(C.Structure):
+    """ab200_point_mass_desc"""
+    _fields_ = [(n, C.c_double) for n in ("gm", "x", "y", "z", "soft", "sink_rate", "sink")]
+
+
 class SourcesDesc(C.Structure):
     """ab200_sources_desc"""
     _fields_ = [("gravity", C.c_int), ("g", C.c_double * 3), ("shearing_box", C.c_int),
                 ("omega", C.c_double), ("qshear", C.c_double), ("drag", C.c_int),
-                ("ntau", C.c_int), ("tau", C.c_double * 16)]
+                ("ntau", C.c_int), ("tau", C.c_double * 16), ("point_mass", C.c_int),
+                ("pm", PointMassDesc), ("rotating_frame", C.c_int), ("rf_omega", C.c_double)]
 
 
 class AB200Error(RuntimeError):
@@ -68,6 +74,7 @@ SYMBOLS = [
     "ab200_run_cycles", "ab200_malloc", "ab200_free", "ab200_memcpy_h2d", "ab200_memcpy_d2h",
     "ab200_launch_count", "ab200_timer_begin", "ab200_timer_end",
     "ab200_history_volume_integrals", "ab200_configure_sources", "ab200_finish_stage", "ab200_uniform_gravity", "ab200_shearing_box", "ab200_drag_simple",
+    "ab200_point_mass_gravity", "ab200_rotating_frame",
     "ab200_comm_unique_id", "ab200_comm_init", "ab200_comm_destroy", "ab200_comm_set_layout",
     "ab200_comm_bytes_per_exchange", "ab200_comm_is_direct", "ab200_comm_exchange_begin", "ab200_comm_exchange_end",
     "ab200_allreduce_min", "ab200_run_cycles_mr", "ab200_comm_plan_direct", "ab200_comm_plan_free",
@@ -133,6 +140,8 @@ def load(variant: str | None = None) -> C.CDLL:
         "ab200_timer_begin": [vp], "ab200_timer_end": [vp, C.POINTER(C.c_float)],
         "ab200_history_volume_integrals": [vp, i, _DP, i], "ab200_configure_sources": [vp, vp], "ab200_finish_stage": [vp, i], "ab200_uniform_gravity": [vp, d, d, d, d],
         "ab200_shearing_box": [vp, d, d, d], "ab200_drag_simple": [vp, d, i, _DP],
+        "ab200_point_mass_gravity": [vp, d, C.POINTER(PointMassDesc)],
+        "ab200_rotating_frame": [vp, d, d],
         "ab200_comm_unique_id": [C.c_char_p], "ab200_comm_init": [vp, i, i, C.c_char_p],
         "ab200_comm_destroy": [vp], "ab200_comm_set_layout": [vp, i, i, i, C.POINTER(C.c_int)],
         "ab200_comm_is_direct": [vp], "ab200_comm_exchange_begin": [vp], "ab200_comm_exchange_end": [vp],

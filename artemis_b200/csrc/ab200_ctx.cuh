@@ -65,6 +65,10 @@ struct FluidHost {
   int prim_cur = 0;
   // lazy ghost cons (ab200_set_ghost_cons_lazy): the ghost fills wrote primitives only
   bool ghost_cons_stale = false;
+  // where the mass fluxes of the latest stage live (ab200_rotating_frame reads them):
+  // 0 nowhere, 1 the tap tables d.dflux (fused stage with AB200_STAGE_TAP_DFLUX), 2 the full
+  // flux arrays d.flux (ab200_calculate_fluxes)
+  int dflux_src = 0;
 };
 int ensure_tma(ab200_ctx *c, int fluid, int max_threads);
 void release_tma(FluidHost &fh);
@@ -170,7 +174,8 @@ int launch_deep_copy(ab200_ctx *c, int fluid);
 int launch_estimate_dt(ab200_ctx *c, int fluid, double *d_out, int combine);
 int launch_fused_stage(ab200_ctx *c, int fluid, double gam0, double gam1, double beta,
                        double dt, int pcm, int stage1_copy, int use_device_dt,
-                       unsigned long long *dt_min, int defer_c2p = 0, int subset = 0);
+                       unsigned long long *dt_min, int defer_c2p = 0, int subset = 0,
+                       int tap = 0);
 bool fused_supports_subsets(const ab200_ctx *c);
 bool fused_folds_dt(const ab200_ctx *c);
 // single-pass stage (sweep.cuh / sweep_host.cu)
@@ -192,6 +197,8 @@ int run_stage(ab200_ctx *c, double g0, double g1, double beta, int pcm, int firs
 int launch_halo(ab200_ctx *c, const ab200_bnd_desc *bnd, int n, int unpack);
 int launch_set_global_dt(ab200_ctx *c, double tlim, int advance_time);
 int ensure_scratch(ab200_ctx *c, int fluid, bool need_flux, bool need_u1);
+// density-flux tap tables of the fused passes (FluidDev::dflux), allocated on first use
+int ensure_dflux(ab200_ctx *c, int fluid);
 int build_geom_tables_for(ab200_ctx *c, GeomTab &t, int geom, int nb, int ni, int nj, int nk,
                           const double *xmin_all, const double *dx_all);
 }  // namespace ab200

@@ -24,6 +24,8 @@ struct GeomTab {
   const double *x1v, *x2v, *x3v;          // [nb][n]   volume centroids (geometry specific)
   const double *cosf, *sinf;              // [nb][nj+1] cos/sin(x2f)   (spherical)
   const double *sinv, *sinc;              // [nb][nj]   sin(x2v), sin(0.5*(x2f[j]+x2f[j+1]))
+  const double *cosv;                     // [nb][nj]   cos(x2v)
+  const double *sin3v, *cos3v;            // [nb][nk]   sin/cos(x3v)  (coordinate conversions)
 };
 
 struct GridDev {
@@ -44,6 +46,10 @@ struct FluidDev {
   double *const *flux[3];
   double *const *pflux[3];
   double *const *vface[3];
+  // density-flux tap of the fused passes: [nb][S] arrays per direction holding ONLY the mass
+  // flux of each species (RotatingFrameImpl reads it; nothing else of the 21 flux arrays of
+  // the reference is ever materialised on the fused path)
+  double *const *dflux[3];
 };
 
 AB_D double sqr(double x) { return x * x; }
@@ -132,6 +138,9 @@ struct Coords {
   AB_D double sinf(int f) const { return t.sinf[o2 + f]; }
   AB_D double sinv() const { return t.sinv[o2 - b_]; }  // [nb][nj] -> offset b*nj + j
   AB_D double sinc() const { return t.sinc[o2 - b_]; }
+  AB_D double cosv() const { return t.cosv[o2 - b_]; }
+  AB_D double sin3v() const { return t.sin3v[o3 - b_]; }
+  AB_D double cos3v() const { return t.cos3v[o3 - b_]; }
 
   // <r> on a theta/phi/z face: cylindrical.hpp:52-56
   AB_D double rface() const {
@@ -250,6 +259,84 @@ struct Coords {
     w[0] = 1.0 * (x1[1] - x1[0]);
     w[1] = h2 * (x2[1] - x2[0]);
     w[2] = h3 * (x3[1] - x3[0]);
+  }
+  // ConvertToCartWithVec at the cell centroid (geometry.hpp:246-260, cylindrical.hpp:95-109,
+  // spherical.hpp:171-189 / 375-393 / 527-545, axisymmetric.hpp:98-113); trig of the centroid
+  // coordinates comes from the host tables, so the strict build matches libm bit for bit.
+  // e[r][c]: component c of the row ex{r+1}.
+  AB_D void to_cart(double xo[3], double e[3][3]) const {
+    const double a = x1v();
+    if (GEOM == AB200_CYLINDRICAL) {
+      const double cp = cosv(), sp = sinv();
+      e[0][0] = cp;  e[0][1] = sp;  e[0][2] = 0.0;
+      e[1][0] = -sp; e[1][1] = cp;  e[1][2] = 0.0;
+      e[2][0] = 0.0; e[2][1] = 0.0; e[2][2] = 1.0;
+      xo[0] = a * cp; xo[1] = a * sp; xo[2] = x3v();
+    } else if (GEOM == AB200_AXISYMMETRIC) {
+      const double cp = cos3v(), sp = sin3v();
+      e[0][0] = cp;  e[0][1] = 0.0; e[0][2] = sp;
+      e[1][0] = -sp; e[1][1] = 0.0; e[1][2] = cp;
+      e[2][0] = 0.0; e[2][1] = 1.0; e[2][2] = 0.0;
+      xo[0] = a * cp; xo[1] = a * sp; xo[2] = x2v();
+    } else if (sph) {
+      const double cp = (GEOM == AB200_SPHERICAL3D) ? cos3v() : 1.0;
+      const double sp = (GEOM == AB200_SPHERICAL3D) ? sin3v() : 0.0;
+      const double ct = (GEOM == AB200_SPHERICAL1D) ? 0.0 : cosv();
+      const double st = (GEOM == AB200_SPHERICAL1D) ? 1.0 : sinv();
+      e[0][0] = st * cp; e[0][1] = st * sp; e[0][2] = ct;
+      e[1][0] = ct * cp; e[1][1] = ct * sp; e[1][2] = -st;
+      e[2][0] = -sp;     e[2][1] = cp;      e[2][2] = 0.0;
+      xo[0] = a * st * cp; xo[1] = a * st * sp; xo[2] = a * ct;
+    } else {
+      e[0][0] = 1.0; e[0][1] = 0.0; e[0][2] = 0.0;
+      e[1][0] = 0.0; e[1][1] = 1.0; e[1][2] = 0.0;
+      e[2][0] = 0.0; e[2][1] = 0.0; e[2][2] = 1.0;
+      xo[0] = a; xo[1] = x2v(); xo[2] = x3v();
+    }
+  }
+  // ConvertToCylWithVec at the cell centroid for the curvilinear systems: cylindrical radius
+  // xcyl0 and the rows ex1..ex3 (cylindrical.hpp:127-137, spherical.hpp:201-222 / 405-426 /
+  // 557-578, axisymmetric.hpp:134-146)
+  AB_D void to_cyl(double &xcyl0, double e[3][3]) const {
+    const double a = x1v();
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { e[r][0] = 0.0; e[r][1] = 0.0; e[r][2] = 0.0; }
+    if (sph) {
+      const double ct = (GEOM == AB200_SPHERICAL1D) ? 0.0 : cosv();
+      const double st = (GEOM == AB200_SPHERICAL1D) ? 1.0 : sinv();
+      e[0][0] = st; e[0][2] = ct;
+      e[1][0] = ct; e[1][2] = -st;
+      e[2][1] = 1.0;
+      xcyl0 = a * st;
+    } else if (GEOM == AB200_AXISYMMETRIC) {
+      e[0][0] = 1.0; e[1][2] = 1.0; e[2][1] = 1.0;
+      xcyl0 = a;
+    } else {
+      e[0][0] = 1.0; e[1][1] = 1.0; e[2][2] = 1.0;
+      xcyl0 = a;
+    }
+  }
+  // RFWeights: +-(<R^2>_face - <R^2>) of the cylindrical radius (cylindrical.hpp:88-93,
+  // axisymmetric.hpp:91-96, spherical.hpp:148-169 / 352-373 / 514-525)
+  AB_D void rf_weights(double bx[3][2]) const {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { bx[d][0] = 0.0; bx[d][1] = 0.0; }
+    if (GEOM == AB200_CYLINDRICAL || GEOM == AB200_AXISYMMETRIC) {
+      const double ans = 0.5 * (x1[0] + x1[1]) * (x1[1] - x1[0]);
+      bx[0][0] = ans; bx[0][1] = ans;
+    } else if (sph23) {
+      const double rv = x1v(), stv = sinv(), rf = rface();
+      const double r2cyl = sqr(rv * stv);
+      bx[0][0] = r2cyl - sqr(x1[0] * stv);
+      bx[0][1] = sqr(x1[1] * stv) - r2cyl;
+      bx[1][0] = r2cyl - sqr(rf * sinf(0));
+      bx[1][1] = sqr(rf * sinf(1)) - r2cyl;
+    } else if (GEOM == AB200_SPHERICAL1D) {
+      const double rv = x1v();
+      const double r2cyl = sqr(rv);
+      bx[0][0] = r2cyl - sqr(x1[0]);
+      bx[0][1] = sqr(x1[1]) - r2cyl;
+    }
   }
   // RotatingFrame::RotationVelocity: src/rotating_frame/rotating_frame.hpp:32-49
   AB_D void rotation_velocity(double omf, double vf[3]) const {

@@ -67,7 +67,8 @@ int build_geom_tables_for(ab200_ctx *c, GeomTab &t, int geom, int nb, int ni, in
   std::vector<double> x1f((size_t)nb * (ni + 1)), x2f((size_t)nb * (nj + 1)),
       x3f((size_t)nb * (nk + 1)), x1v((size_t)nb * ni), x2v((size_t)nb * nj),
       x3v((size_t)nb * nk), cosf((size_t)nb * (nj + 1)), sinf((size_t)nb * (nj + 1)),
-      sinv((size_t)nb * nj), sinc((size_t)nb * nj);
+      sinv((size_t)nb * nj), sinc((size_t)nb * nj), cosv((size_t)nb * nj),
+      sin3v((size_t)nb * nk), cos3v((size_t)nb * nk);
   for (int b = 0; b < nb; ++b) {
     const double *xm = xmin_all + 3 * b, *dx = dx_all + 3 * b;
     // P:coordinates/uniform_cartesian.hpp:153-157  Xf(idx) = xmin + idx*dx
@@ -86,18 +87,23 @@ int build_geom_tables_for(ab200_ctx *c, GeomTab &t, int geom, int nb, int ni, in
       const double v = h_x2v(geom, a, bb);
       x2v[(size_t)b * nj + j] = v;
       sinv[(size_t)b * nj + j] = std::sin(v);
+      cosv[(size_t)b * nj + j] = std::cos(v);
       sinc[(size_t)b * nj + j] = std::sin(0.5 * (a + bb));
     }
-    for (int k = 0; k < nk; ++k)
-      x3v[(size_t)b * nk + k] =
-          0.5 * (x3f[(size_t)b * (nk + 1) + k] + x3f[(size_t)b * (nk + 1) + k + 1]);
+    for (int k = 0; k < nk; ++k) {
+      const double v = 0.5 * (x3f[(size_t)b * (nk + 1) + k] + x3f[(size_t)b * (nk + 1) + k + 1]);
+      x3v[(size_t)b * nk + k] = v;
+      sin3v[(size_t)b * nk + k] = std::sin(v);
+      cos3v[(size_t)b * nk + k] = std::cos(v);
+    }
   }
   double *p;
 #define UP(field, vec)                                                                   \
   AB_TRY(upload<double>(c, &p, vec.data(), vec.size(), &c->grid_allocs));                \
   t.field = p;
   UP(x1f, x1f) UP(x2f, x2f) UP(x3f, x3f) UP(x1v, x1v) UP(x2v, x2v) UP(x3v, x3v)
-  UP(cosf, cosf) UP(sinf, sinf) UP(sinv, sinv) UP(sinc, sinc)
+  UP(cosf, cosf) UP(sinf, sinf) UP(sinv, sinv) UP(sinc, sinc) UP(cosv, cosv)
+  UP(sin3v, sin3v) UP(cos3v, cos3v)
 #undef UP
   return AB200_OK;
 }
@@ -133,6 +139,24 @@ int ensure_scratch(ab200_ctx *c, int fluid, bool need_flux, bool need_u1) {
         AB_TRY(make_table(&f.d.vface[d], f.d.S, fcells));
       }
     }
+  }
+  return AB200_OK;
+}
+
+int ensure_dflux(ab200_ctx *c, int fluid) {
+  FluidHost &f = c->fl[fluid];
+  const GridDev &g = c->g;
+  const size_t cells = (size_t)g.ni * g.nj * g.nk;
+  for (int d = 0; d < g.ndim; ++d) {
+    if (f.d.dflux[d]) continue;
+    double *slab;
+    AB_TRY(dev_alloc(c, (void **)&slab, sizeof(double) * cells * f.d.S * g.nb, &f.owned_scratch));
+    AB_CUDA(cudaMemsetAsync(slab, 0, sizeof(double) * cells * f.d.S * g.nb, c->stream));
+    std::vector<double *> tab((size_t)f.d.S * g.nb);
+    for (size_t e = 0; e < tab.size(); ++e) tab[e] = slab + e * cells;
+    double **dt;
+    AB_TRY(upload<double *>(c, &dt, tab.data(), tab.size(), &f.owned_tables));
+    f.d.dflux[d] = dt;
   }
   return AB200_OK;
 }
@@ -399,6 +423,7 @@ int ab200_calculate_fluxes(ab200_ctx *c, int fluid, int pcm) {
   AB_ENTER(c) AB_FLUID(c, fluid)
   AB_PRIM_HOME(c)
   AB_TRY(ensure_scratch(c, fluid, true, false));
+  c->fl[fluid].dflux_src = 2;  // the mass fluxes of this stage live in the full flux arrays
   return launch_calculate_fluxes(c, fluid, pcm);
 }
 
@@ -537,7 +562,8 @@ int ab200_fused_stage(ab200_ctx *c, double gam0, double gam1, double beta, doubl
   AB_REQUIRE(!stage1_copy || (gam0 == 0.0 && gam1 == 1.0), AB200_EINVAL,
              "ab200_fused_stage: stage1_copy requires gam0 == 0 and gam1 == 1");
   AB_REQUIRE((flags & ~(AB200_STAGE_DEVICE_DT | AB200_STAGE_REDUCE_DT | AB200_STAGE_PINGPONG |
-                        AB200_STAGE_DEFER_C2P | AB200_STAGE_SURFACE | AB200_STAGE_INTERIOR)) == 0,
+                        AB200_STAGE_DEFER_C2P | AB200_STAGE_SURFACE | AB200_STAGE_INTERIOR |
+                        AB200_STAGE_TAP_DFLUX)) == 0,
              AB200_EINVAL, "ab200_fused_stage: unknown flag");
   const int subset = (flags & AB200_STAGE_SURFACE) ? 1 : ((flags & AB200_STAGE_INTERIOR) ? 2 : 0);
   AB_REQUIRE(!((flags & AB200_STAGE_SURFACE) && (flags & AB200_STAGE_INTERIOR)), AB200_EINVAL,
@@ -551,6 +577,10 @@ int ab200_fused_stage(ab200_ctx *c, double gam0, double gam1, double beta, doubl
   // deferred C2P: the timestep is estimated by ab200_finish_stage, from the final primitives
   const int reduce_dt = (flags & AB200_STAGE_REDUCE_DT) != 0 && !defer;
   const int pingpong = (flags & AB200_STAGE_PINGPONG) != 0;
+  const int tap = (flags & AB200_STAGE_TAP_DFLUX) != 0;
+  AB_REQUIRE(!tap || c->g.geom != AB200_CARTESIAN, AB200_EINVAL,
+             "ab200_fused_stage: the mass-flux tap exists for the curvilinear systems only "
+             "(its reader, RotatingFrameImpl, is never Cartesian: rotating_frame.cpp:67-82)");
   // per-fluid raw minimum (bit pattern of a positive double), reset to a huge finite value
   unsigned long long *slots = reinterpret_cast<unsigned long long *>(c->d_red + 3072);
   // (a SURFACE call opens the reduction, the INTERIOR call that follows closes it)
@@ -561,8 +591,10 @@ int ab200_fused_stage(ab200_ctx *c, double gam0, double gam1, double beta, doubl
   for (int f = 0; f < 2; ++f) {
     if (!c->fl[f].bound) continue;
     AB_TRY(ensure_scratch(c, f, false, true));
+    if (tap) AB_TRY(ensure_dflux(c, f));
+    c->fl[f].dflux_src = tap ? 1 : 0;
     bool fold;
-    if (!defer && !subset && sweep_eligible(c, f)) {
+    if (!defer && !subset && !tap && sweep_eligible(c, f)) {
       // single-pass stage (sweep.cuh): reads the current primitive set, writes the other one
       fold = reduce_dt;
       AB_TRY(launch_sweep_stage(c, f, gam0, gam1, beta, dt, pcm, stage1_copy, use_device_dt,
@@ -572,7 +604,7 @@ int ab200_fused_stage(ab200_ctx *c, double gam0, double gam1, double beta, doubl
       AB_TRY(sync_prim_home(c, f, 0));
       fold = reduce_dt && fused_folds_dt(c);
       AB_TRY(launch_fused_stage(c, f, gam0, gam1, beta, dt, pcm, stage1_copy, use_device_dt,
-                                fold ? slots + f : nullptr, defer, subset));
+                                fold ? slots + f : nullptr, defer, subset, tap));
     }
     if (reduce_dt && subset != 1) {  // new_dt = min over fluids of cfl * min dt  (EstimateTimestepMesh)
       if (fold)

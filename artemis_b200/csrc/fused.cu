@@ -176,7 +176,7 @@ static int launch_dirs(ab200_ctx *c, const FluidDev &f, FusedArgs a) {
   const int fin = a.defer_c2p ? 0 : 1;  // deferred: SetAux / C2P run in ab200_finish_stage
   a.first = 1; a.last = fin * (ndim == 1); a.copy_u1 = copy;
   if (!interior_call) {
-    if (ndim >= 2 && use_xchunk() && use_xtile(c)) AB_TRY((launch_xtile<GEOM, FLUID, RS, RC>(c, f, a)));
+    if (ndim >= 2 && use_xchunk() && use_xtile(c) && !a.tap) AB_TRY((launch_xtile<GEOM, FLUID, RS, RC>(c, f, a)));
     else if (ndim >= 2 && use_xchunk()) AB_TRY((launch_xchunk<GEOM, FLUID, RS, RC>(c, f, a)));
     else AB_TRY((launch_pass<GEOM, FLUID, RS, RC, 1>(c, f, a)));
   }

@@ -38,6 +38,7 @@ struct FusedArgs {
   const double *dt_dev;  // if non-null: dt = *dt_dev
   int first, last, copy_u1;
   int defer_c2p;  // AB200_STAGE_DEFER_C2P: no pass is the LAST one (source terms follow)
+  int tap;        // AB200_STAGE_TAP_DFLUX: every pass also stores its MASS flux into f.dflux
   // block subset of this launch (AB200_STAGE_SURFACE / _INTERIOR): the launch covers blocks
   // blist[0 .. nbl-1]; nullptr = all g.nb blocks
   const int *blist;
@@ -283,6 +284,7 @@ k_fused_pass(GridDev g, FluidDev f, FusedArgs a) {
       }
 #pragma unroll
       for (int m = 0; m < NF; ++m) s_fx[m * nslots + slot(c)] = lo[m];
+      if (!CART && a.tap) f.dflux[DIR - 1][(size_t)b * S + n][off] = lo[0];
     }
     __syncthreads();
 

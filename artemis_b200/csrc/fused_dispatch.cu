@@ -25,10 +25,11 @@ bool fused_supports_subsets(const ab200_ctx *c) {
 
 int launch_fused_stage(ab200_ctx *c, int fluid, double gam0, double gam1, double beta, double dt,
                        int pcm, int stage1_copy, int use_device_dt, unsigned long long *dt_min,
-                       int defer_c2p, int subset) {
+                       int defer_c2p, int subset, int tap) {
   FusedArgs a{};
   a.dt_min = dt_min;
   a.defer_c2p = defer_c2p;
+  a.tap = tap;
   if (subset) {  // 1 = surface blocks (touch a face owned by another rank), 2 = the rest
     a.blist = c->d_blist[subset - 1];
     a.nbl = c->n_blist[subset - 1];

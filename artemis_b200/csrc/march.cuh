@@ -210,6 +210,9 @@ k_march_pass(GridDev g, FluidDev f, FusedArgs a) {
 #pragma unroll
       for (int m = 1; m <= 3; ++m) lo[m] *= hs[(DIR - 1 + (m - 1)) % 3];
     }
+    // mass-flux tap (curvilinear meshes only -- RotatingFrameImpl is their only reader -- so the
+    // Cartesian kernels carry no trace of it: a run-time test alone cost 5 % per cycle there)
+    if (!CART && a.tap) __stcg(f.dflux[DIR - 1][(size_t)b * S + n] + base + c * st, lo[0]);
     // ---- finish cell c-1: ApplyUpdate + FluxSource of direction DIR --------------------------
     // (artemis_integrator.hpp:95-106, fluid_fluxes.hpp:365-392)
     if (c >= s0 + 1) {

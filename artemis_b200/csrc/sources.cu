@@ -11,6 +11,12 @@
 //   ab200_shearing_box     RotatingFrame::ShearingBoxImpl    src/rotating_frame/rotating_frame_impl.hpp:28-94
 //   ab200_drag_simple      Drag::SimpleDragSourceImpl (constant stopping times, no damping
 //                          zones, no viscous target velocity) src/drag/drag.hpp:296-482
+//   ab200_point_mass_gravity  Gravity::PointMassGravity<GEOM> (softened, off-centre, mass sink)
+//                          src/gravity/point_mass.cpp:26-196
+//   ab200_rotating_frame   RotatingFrame::RotatingFrameImpl<GEOM> (every curvilinear system)
+//                          src/rotating_frame/rotating_frame_impl.hpp:96-199 -- reads the MASS
+//                          fluxes of the stage: the fused passes tap them into FluidDev::dflux
+//                          (AB200_STAGE_TAP_DFLUX), the task path leaves them in the flux arrays
 #include <type_traits>
 
 #include "tasks.cuh"
@@ -102,6 +108,159 @@ k_shearing_box(GridDev g, TwoFluids tf, double dt_host, const double *dt_dev, do
       f.u0[e + S + 3 * n + 1][off] -= rdt * 2.0 * om0 * v1;
       f.u0[e + S + 3 * n + 2][off] -= rdt * dpz;
       if (fl == AB200_GAS) f.u0[e + 4 * S + n][off] -= rdt * (v1 * dpx + v3 * dpz);
+    }
+  }
+}
+
+struct PointMass {
+  double gm, pos[3], rsft2, sink_rate, sink_rad;  // sink_rate: per unit time (x dt in the kernel)
+};
+
+// Gravity::PointMassGravity<GEOM>, src/gravity/point_mass.cpp:62-193.  The acceleration is a
+// function of position only; the conversions to / from Cartesian use the host-built trig tables
+// of the cell centroids, so the strict build reproduces the reference bit for bit.
+template <int GEOM>
+__global__ void __launch_bounds__(kThreads)
+k_point_mass(GridDev g, TwoFluids tf, double dt_host, const double *dt_dev, double beta,
+             PointMass pm) {
+  const double dt = dt_dev ? beta * *dt_dev : dt_host;
+  const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)g.nb * nkr * njr * nir) return;
+  const CellIdx c = decode(t, nir, njr, nkr, g.is, g.js, g.ks);
+  Coords<GEOM> cc(g, c.b, c.k, c.j, c.i);
+  const double hx[3] = {cc.hx1v(), cc.hx2v(), cc.hx3v()};
+  const double gm = pm.gm;
+  double gx1 = 0.0, gx2 = 0.0, gx3 = 0.0, dr;
+  if (GEOM == AB200_SPHERICAL1D || GEOM == AB200_SPHERICAL2D) {  // :76-80
+    const double rad2 = sqr(cc.x1v()) + pm.rsft2;
+    gx1 = -gm / rad2;
+    dr = sqrt(rad2);
+  } else if (GEOM == AB200_AXISYMMETRIC) {  // :81-88 with axisymmetric.hpp:115-133
+    const double x0 = cc.x1v(), x1 = cc.x2v();
+    const double rs = sqrt(x0 * x0 + x1 * x1);
+    const double ct = x1 / (rs + 1e-99);
+    const double st = x0 / (rs + 1e-99);
+    dr = rs;
+    const double rad2 = sqr(dr) + pm.rsft2;
+    const double gg = -gm / rad2;
+    gx1 = gg * st;
+    gx2 = gg * ct;
+  } else {  // :89-114
+    double dxc[3], e[3][3];
+    cc.to_cart(dxc, e);
+#pragma unroll
+    for (int n = 0; n < 3; n++) dxc[n] -= pm.pos[n];
+    const double R = sqrt(dxc[0] * dxc[0] + dxc[1] * dxc[1]);  // geometry.hpp:262-269
+    dr = sqrt(R * R + dxc[2] * dxc[2]);
+    const double rad2 = sqr(dr) + pm.rsft2;
+    const double idr3 = 1.0 / (sqrt(rad2) * rad2);
+    const double multi_d = (g.ndim >= 2) ? 1.0 : 0.0, three_d = (g.ndim == 3) ? 1.0 : 0.0;
+    const double gv[3] = {-gm * dxc[0] * idr3, multi_d * (-gm * dxc[1] * idr3),
+                          three_d * (-gm * dxc[2] * idr3)};
+    gx1 = gv[0] * e[0][0] + gv[1] * e[0][1] + gv[2] * e[0][2];
+    gx2 = gv[0] * e[1][0] + gv[1] * e[1][1] + gv[2] * e[1][2];
+    gx3 = gv[0] * e[2][0] + gv[1] * e[2][1] + gv[2] * e[2][2];
+  }
+  // mass accretion :146-148 (quad_ramp(x) = x^2, gravity.hpp:116); sink_rate * dt
+  const double srate = dt * pm.sink_rate;
+  const double sramp = srate * sqr((dr - pm.sink_rad) / pm.sink_rad);
+  double fd = dmin(0.5, sramp / (1.0 + sramp));
+  fd *= ((srate > 0.0) && (dr <= pm.sink_rad)) ? 1.0 : 0.0;
+  const size_t off = ((size_t)c.k * g.nj + c.j) * g.ni + c.i;
+#pragma unroll
+  for (int fl = 0; fl < 2; ++fl) {
+    if (!tf.on[fl]) continue;
+    const FluidDev &f = tf.f[fl];
+    const int S = f.S;
+    const size_t e = (size_t)c.b * f.nvar;
+    for (int n = 0; n < S; ++n) {
+      const double rho = f.prim[e + n][off];
+      const double v1 = f.prim[e + S + 3 * n + 0][off], v2 = f.prim[e + S + 3 * n + 1][off],
+                   v3 = f.prim[e + S + 3 * n + 2][off];
+      double m1 = f.u0[e + S + 3 * n + 0][off], m2 = f.u0[e + S + 3 * n + 1][off],
+             m3 = f.u0[e + S + 3 * n + 2][off];
+      m1 += dt * rho * hx[0] * gx1;
+      m2 += dt * rho * hx[1] * gx2;
+      m3 += dt * rho * hx[2] * gx3;
+      if (fl == AB200_GAS) {
+        const double sie = f.prim[e + 5 * S + n][off];
+        const double tote = rho * (sie + 0.5 * (sqr(v1) + sqr(v2) + sqr(v3)));
+        double en = f.u0[e + 4 * S + n][off];
+        en += dt * rho * (v1 * gx1 + v2 * gx2 + v3 * gx3);
+        en -= fd * tote;
+        f.u0[e + 4 * S + n][off] = en;
+      }
+      f.u0[e + n][off] -= fd * rho;
+      m1 -= fd * hx[0] * rho * v1;
+      m2 -= fd * hx[1] * rho * v2;
+      m3 -= fd * hx[2] * rho * v3;
+      f.u0[e + S + 3 * n + 0][off] = m1;
+      f.u0[e + S + 3 * n + 1][off] = m2;
+      f.u0[e + S + 3 * n + 2][off] = m3;
+    }
+  }
+}
+
+// where the mass fluxes of one fluid live: table [nb][stride] per direction, entry n < S
+struct MassFlux {
+  double *const *tab[3];
+  int stride;
+};
+struct TwoMassFlux {
+  MassFlux m[2];
+};
+
+// RotatingFrame::RotatingFrameImpl<GEOM>, rotating_frame_impl.hpp:96-199: angular-momentum
+// conserving form -- the mass fluxes through the six faces weighted by +-(<R^2>_face - <R^2>).
+template <int GEOM>
+__global__ void __launch_bounds__(kThreads)
+k_rotating_frame(GridDev g, TwoFluids tf, TwoMassFlux mf, double dt_host, const double *dt_dev,
+                 double beta, double om0) {
+  const double dt = dt_dev ? beta * *dt_dev : dt_host;
+  const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)g.nb * nkr * njr * nir) return;
+  const CellIdx c = decode(t, nir, njr, nkr, g.is, g.js, g.ks);
+  Coords<GEOM> cc(g, c.b, c.k, c.j, c.i);
+  const double multi_d = (g.ndim >= 2) ? 1.0 : 0.0, three_d = (g.ndim == 3) ? 1.0 : 0.0;
+  const double omdt = om0 * dt;
+  const double om2dt = omdt * om0;
+  double xcyl0, e[3][3], bx[3][2];
+  cc.to_cyl(xcyl0, e);
+  cc.rf_weights(bx);
+  const double ax1[2] = {cc.area1(cc.x1[0]), cc.area1(cc.x1[1])};
+  const double ax2[2] = {g.ndim >= 2 ? cc.area2(0) : 0.0, g.ndim >= 2 ? cc.area2(1) : 0.0};
+  const double ax3[2] = {g.ndim == 3 ? cc.area3() : 0.0, g.ndim == 3 ? cc.area3() : 0.0};
+  const double vol = cc.volume();
+  const size_t off = ((size_t)c.k * g.nj + c.j) * g.ni + c.i;
+  const size_t sj = (size_t)g.ni, sk = (size_t)g.ni * g.nj;
+#pragma unroll
+  for (int fl = 0; fl < 2; ++fl) {
+    if (!tf.on[fl]) continue;
+    const FluidDev &f = tf.f[fl];
+    const MassFlux &m = mf.m[fl];
+    const int S = f.S;
+    const size_t eb = (size_t)c.b * f.nvar;
+    for (int n = 0; n < S; ++n) {
+      const size_t fe = (size_t)c.b * m.stride + n;
+      const double *f1 = m.tab[0][fe];
+      const double f1m = f1[off], f1p = f1[off + 1];
+      double f2m = 0.0, f2p = 0.0, f3m = 0.0, f3p = 0.0;
+      if (g.ndim >= 2) { const double *f2 = m.tab[1][fe]; f2m = f2[off]; f2p = f2[off + sj]; }
+      if (g.ndim == 3) { const double *f3 = m.tab[2][fe]; f3m = f3[off]; f3p = f3[off + sk]; }
+      const double divf = (f1m * ax1[0] * bx[0][0] + f1p * ax1[1] * bx[0][1]) +
+                          multi_d * (f2m * ax2[0] * bx[1][0] + f2p * ax2[1] * bx[1][1]) +
+                          three_d * (f3m * ax3[0] * bx[2][0] + f3p * ax3[1] * bx[2][1]);
+      f.u0[eb + S + 3 * n + 0][off] -= omdt * (divf / vol) * e[0][1];
+      f.u0[eb + S + 3 * n + 1][off] -= omdt * (divf / vol) * e[1][1];
+      f.u0[eb + S + 3 * n + 2][off] -= omdt * (divf / vol) * e[2][1];
+      if (fl == AB200_GAS) {
+        const double fx[3] = {0.5 * (f1m + f1p), multi_d * 0.5 * (f2m + f2p),
+                              three_d * 0.5 * (f3m + f3p)};
+        f.u0[eb + 4 * S + n][off] +=
+            om2dt * xcyl0 * (fx[0] * e[0][0] + fx[1] * e[1][0] + fx[2] * e[2][0]);
+      }
     }
   }
 }
@@ -351,6 +510,65 @@ int ab200_drag_simple(ab200_ctx *c, double dt, int ntau, const double *tau) {
 }
 
 
+static int point_mass_impl(ab200_ctx *c, double dt, const double *dt_dev, double beta,
+                           const ab200_point_mass_desc *d) {
+  AB_ENTER_S(c)
+  AB_REQUIRE(d != nullptr, AB200_EINVAL, "ab200_point_mass_gravity: null descriptor");
+  TwoFluids tf{};
+  AB_TRY(two_fluids(c, tf));
+  PointMass pm{d->gm, {d->x, d->y, d->z}, d->soft * d->soft, d->sink_rate, d->sink};
+  const GridDev &g = c->g;
+  int rc = dispatch_geom_s(g.geom, [&](auto G) {
+    k_point_mass<decltype(G)::value><<<grid_s(g), kThreads, 0, c->stream>>>(g, tf, dt, dt_dev, beta, pm);
+    return AB200_OK;
+  });
+  c->launches++;
+  AB_CUDA(cudaGetLastError());
+  return rc;
+}
+int ab200_point_mass_gravity(ab200_ctx *c, double dt, const ab200_point_mass_desc *d) {
+  return point_mass_impl(c, dt, nullptr, 0.0, d);
+}
+
+static int rotating_frame_impl(ab200_ctx *c, double dt, const double *dt_dev, double beta,
+                               double omega) {
+  AB_ENTER_S(c)
+  AB_REQUIRE(omega != 0.0, AB200_EINVAL, "rotating_frame/omega cannot be zero!");
+  AB_REQUIRE(c->g.geom != AB200_CARTESIAN, AB200_EINVAL,
+             "ab200_rotating_frame: the Cartesian rotating frame is ab200_shearing_box "
+             "(rotating_frame.cpp:67-68)");
+  TwoFluids tf{};
+  TwoMassFlux mf{};
+  // only the conserved state is touched; the primitives are not read
+  int any = 0;
+  for (int f = 0; f < 2; ++f) {
+    tf.on[f] = c->fl[f].bound ? 1 : 0;
+    if (!tf.on[f]) continue;
+    const FluidHost &fh = c->fl[f];
+    AB_REQUIRE(fh.dflux_src != 0, AB200_ESTATE,
+               "ab200_rotating_frame: no mass fluxes of this stage (run ab200_fused_stage with "
+               "AB200_STAGE_TAP_DFLUX or ab200_calculate_fluxes first)");
+    tf.f[f] = fh.d;
+    for (int d = 0; d < 3; ++d) mf.m[f].tab[d] = fh.dflux_src == 1 ? fh.d.dflux[d] : fh.d.flux[d];
+    mf.m[f].stride = fh.dflux_src == 1 ? fh.d.S : fh.d.nvar;
+    any = 1;
+  }
+  AB_REQUIRE(any, AB200_ESTATE, "source term: no fluid bound");
+  const GridDev &g = c->g;
+  int rc = dispatch_geom_s(g.geom, [&](auto G) {
+    constexpr int GG = decltype(G)::value;
+    if constexpr (GG != AB200_CARTESIAN)
+      k_rotating_frame<GG><<<grid_s(g), kThreads, 0, c->stream>>>(g, tf, mf, dt, dt_dev, beta, omega);
+    return AB200_OK;
+  });
+  c->launches++;
+  AB_CUDA(cudaGetLastError());
+  return rc;
+}
+int ab200_rotating_frame(ab200_ctx *c, double dt, double omega) {
+  return rotating_frame_impl(c, dt, nullptr, 0.0, omega);
+}
+
 int ab200_configure_sources(ab200_ctx *c, const ab200_sources_desc *src) {
   AB_REQUIRE(c, AB200_EINVAL, "null context");
   if (!src) {
@@ -361,7 +579,12 @@ int ab200_configure_sources(ab200_ctx *c, const ab200_sources_desc *src) {
   AB_REQUIRE(!src->drag || (src->ntau >= 1 && src->ntau <= 16), AB200_EINVAL,
              "ab200_configure_sources: 1..16 stopping times");
   c->sources = *src;
-  c->has_sources = src->gravity || src->shearing_box || src->drag;
+  AB_REQUIRE(!(src->gravity && src->point_mass), AB200_EINVAL,
+             "ab200_configure_sources: one gravity type (gravity.cpp:68-88)");
+  AB_REQUIRE(!(src->shearing_box && src->rotating_frame), AB200_EINVAL,
+             "ab200_configure_sources: shearing box (Cartesian) or rotating frame (curvilinear)");
+  c->has_sources = src->gravity || src->shearing_box || src->drag || src->point_mass ||
+                   src->rotating_frame;
   return AB200_OK;
 }
 
@@ -374,11 +597,15 @@ int run_stage(ab200_ctx *c, double g0, double g1, double beta, int pcm, int firs
   const int base = AB200_STAGE_DEVICE_DT | AB200_STAGE_PINGPONG;
   if (!c->has_sources)
     return ab200_fused_stage(c, g0, g1, beta, 0.0, pcm, first, base | (last ? AB200_STAGE_REDUCE_DT : 0));
-  AB_TRY(ab200_fused_stage(c, g0, g1, beta, 0.0, pcm, first, base | AB200_STAGE_DEFER_C2P));
-  // beta * dt is formed on the device from the dt scalar: no host round trip
   const ab200_sources_desc &s = c->sources;
+  AB_TRY(ab200_fused_stage(c, g0, g1, beta, 0.0, pcm, first,
+                           base | AB200_STAGE_DEFER_C2P |
+                               (s.rotating_frame ? AB200_STAGE_TAP_DFLUX : 0)));
+  // beta * dt is formed on the device from the dt scalar: no host round trip
   if (s.gravity) AB_TRY(gravity_impl(c, 0.0, c->d_time, beta, s.g[0], s.g[1], s.g[2]));
+  if (s.point_mass) AB_TRY(point_mass_impl(c, 0.0, c->d_time, beta, &s.pm));
   if (s.shearing_box) AB_TRY(shearing_impl(c, 0.0, c->d_time, beta, s.omega, s.qshear));
+  if (s.rotating_frame) AB_TRY(rotating_frame_impl(c, 0.0, c->d_time, beta, s.rf_omega));
   if (s.drag) AB_TRY(drag_impl(c, 0.0, c->d_time, beta, s.ntau, s.tau));
   return ab200_finish_stage(c, last ? AB200_STAGE_REDUCE_DT : 0);
 }

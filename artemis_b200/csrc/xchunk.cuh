@@ -186,6 +186,11 @@ k_xchunk_pass(GridDev g, FluidDev f, FusedArgs a) {
 #pragma unroll
       for (int m = 0; m < NF; ++m) fl[m] = sF[m * 64 + pm1];
       const double *hi = lo;
+      if (!CART && a.tap) {  // density-flux tap: lower face of every interior cell + the face at ie+1
+        double *pf = f.dflux[0][(size_t)b * S + n];
+        __stcg(pf + gu, fl[0]);
+        if (ic == g.ie) __stcg(pf + gu + 1, hi[0]);
+      }
       double u[6];
 #pragma unroll
       for (int m = 0; m < NV; ++m) {

@@ -187,9 +187,16 @@ class ArtemisDriver:
         """ExternalGravity -> RotatingFrameForce -> DragSource, the reference's task order
         (src/artemis_driver.cpp:222-243)."""
         md, req = self.md, self._require
-        order = {"gravity": 0, "shearing_box": 1, "drag": 2}
+        order = {"gravity": 0, "point_mass": 0, "shearing_box": 1, "rotating_frame": 1, "drag": 2}
         for src in sorted(self.sources, key=lambda t: order[t[0]]):
-            if src[0] == "gravity":
+            if src[0] == "point_mass":
+                pm = capi.PointMassDesc(*[float(v) for v in src[1:8]])
+                req(_task(md, "ab200_point_mass_gravity", float(bdt), C.byref(pm)),
+                    md, "Gravity::PointMassGravity")
+            elif src[0] == "rotating_frame":
+                req(_task(md, "ab200_rotating_frame", float(bdt), float(src[1])),
+                    md, "RotatingFrame::RotatingFrameImpl")
+            elif src[0] == "gravity":
                 req(_task(md, "ab200_uniform_gravity", float(bdt), *[float(v) for v in src[1:4]]),
                     md, "Gravity::UniformGravity")
             elif src[0] == "shearing_box":
@@ -229,6 +236,8 @@ class ArtemisDriver:
                 # with source terms the conserved state must exist between the update and C2P:
                 # the fused passes stop after FluxSource (AB200_STAGE_DEFER_C2P = 8)
                 defer = 8 if self.sources else 0
+                if any(src[0] == "rotating_frame" for src in self.sources):
+                    defer |= 64   # AB200_STAGE_TAP_DFLUX: the passes keep their mass fluxes
                 req(_task(md, "ab200_fused_stage", integ.gam0[stage - 1], integ.gam1[stage - 1],
                           integ.beta[stage - 1], integ.dt, int(do_pcm), int(stage == 1), defer),
                     md, "ab200_fused_stage")

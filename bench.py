@@ -53,6 +53,8 @@ def parse():
                          "32^3 MeshBlocks, outflow, curvilinear geometry + geometric source terms")
     ap.add_argument("--mesh", type=int, default=512, help="config 3: total zones per direction")
     ap.add_argument("--dust-species", type=int, default=4)
+    ap.add_argument("--no-sources", action="store_true",
+                    help="config 4: without the deck's point-mass gravity and rotating frame")
     ap.add_argument("--no-drag", action="store_true",
                     help="config 3: leave Drag::DragSource out (it then stays on the reference path)")
     ap.add_argument("--state", default="blast", choices=["blast", "shocked"],
@@ -310,11 +312,12 @@ def main_config3(args):
             R = r * np.sin(th)
             rho = R ** -1.5 * np.exp(-((th - np.pi / 2) / 0.2) ** 2) * (1 + 1e-2 * np.sin(3 * ph))
             prim[b, 0] = np.maximum(rho, 1e-6)
-            prim[b, 3] = R ** -0.5
+            om = 0.0 if args.no_sources else 1.0     # <rotating_frame> omega = 1 (disk_sph.in)
+            prim[b, 3] = R ** -0.5 - om * R
             prim[b, 1] = 1e-3 * np.cos(2 * ph)
             prim[b, 5] = 0.05 ** 2 / gp.gm1 / R
             dprim[b, 0] = 0.01 * prim[b, 0]
-            dprim[b, 3] = R ** -0.5
+            dprim[b, 3] = R ** -0.5 - om * R
     else:
         prim, dprim = pgen.perturbed_constant(mesh, 6, S, amp=1e-3, seed=1234)
     prim[:, 4] = gp.gm1 * prim[:, 0] * prim[:, 5]
@@ -331,6 +334,17 @@ def main_config3(args):
     md.set_time_state(drv.dt)
     md.call("ab200_set_ghost_cons_lazy", 1)
     big = float(np.finfo(np.float64).max)
+    if cfg4 and not args.no_sources:
+        # inputs/disk/disk_sph.in: <gravity/point> mass = 1, <rotating_frame> omega = 1 -- every
+        # stage is split (passes + mass-flux tap -> PointMassGravity -> RotatingFrameImpl ->
+        # SetAux/C2P/P2C); the frame velocity also enters FluxSource (fluid_fluxes.hpp:433-437)
+        import ctypes as C
+        from artemis_b200 import capi
+        md.call("ab200_set_rotating_frame", 1.0)
+        sd = capi.SourcesDesc()
+        sd.point_mass, sd.pm = 1, capi.PointMassDesc(1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
+        sd.rotating_frame, sd.rf_omega = 1, 1.0
+        md.call("ab200_configure_sources", C.byref(sd))
     if not args.no_drag and not cfg4:   # <drag/dust> type = constant, one stopping time per species
         import ctypes as C
         from artemis_b200 import capi
@@ -386,8 +400,12 @@ def main_config3(args):
                "config": {"workload": (f"config 4: spherical 3-D Keplerian disk, gas + 1 dust species, "
                                        f"PPM+HLLE (WENO5 absent upstream), rk2, outflow r/theta + periodic "
                                        f"phi, {M}^3 zones in TOTAL in {B}^3 MeshBlocks over {world} GPU(s); "
-                                       "curvilinear fluxes, PLM_G-free PPM, geometric source terms; gravity / "
-                                       "rotating frame / viscosity on the reference path" if cfg4 else
+                                       "curvilinear fluxes, PLM_G-free PPM, geometric source terms; "
+                                       + ("no source terms" if args.no_sources else
+                                          "point-mass gravity (gm 1) + rotating frame (omega 1, mass-flux "
+                                          "tap) every stage as in disk_sph.in, split stage")
+                                       + "; alpha viscosity and the disk user BCs stay on the reference "
+                                         "path" if cfg4 else
                                        f"config 3: gas + {S} dust species (inputs/drag state + seeded "
                                        f"perturbation), PLM+HLLE, rk2, periodic, {M}^3 zones in TOTAL in "
                                        f"{B}^3 MeshBlocks split over {world} GPU(s) (strong scaling); "

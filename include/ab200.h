@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AB200_ABI_VERSION 7
+#define AB200_ABI_VERSION 8
 
 /* src/artemis.hpp:78-105 */
 enum { AB200_CARTESIAN = 0, AB200_CYLINDRICAL = 1, AB200_SPHERICAL1D = 2,
@@ -179,6 +179,13 @@ int ab200_estimate_timestep(ab200_ctx *ctx, int fluid, double *dt_host);
  *                               interior blocks' stage.  Directional passes only. */
 #define AB200_STAGE_SURFACE 16
 #define AB200_STAGE_INTERIOR 32
+/*   AB200_STAGE_TAP_DFLUX      every directional pass also stores its MASS flux (one array per
+ *                               species and direction, library-owned) for ab200_rotating_frame:
+ *                               the only part of the reference's 21 flux arrays per zone that a
+ *                               source term reads (rotating_frame_impl.hpp:135-163).  Curvilinear
+ *                               systems only (AB200_EINVAL on a Cartesian mesh, whose rotating
+ *                               frame is the shearing box and reads no flux). */
+#define AB200_STAGE_TAP_DFLUX 64
 int ab200_fused_stage(ab200_ctx *ctx, double gam0, double gam1, double beta, double dt,
                       int pcm, int stage1_copy, int flags);
 /* SetAuxillaryFields -> ConsToPrim -> PrimToCons after a AB200_STAGE_DEFER_C2P stage and its
@@ -191,14 +198,30 @@ int ab200_finish_stage(ab200_ctx *ctx, int flags);
  * bound fluid; dt = beta * dt of the stage (src/artemis_driver.cpp:217-248).
  *   ab200_uniform_gravity  Gravity::UniformGravity<GEOM>   src/gravity/uniform.cpp:28-90
  *   ab200_shearing_box     RotatingFrame::ShearingBoxImpl  src/rotating_frame/rotating_frame_impl.hpp:28-94
- *                          (Cartesian; the curvilinear RotatingFrameImpl :96-199 reads the density
- *                          fluxes and stays on the reference path)
+ *                          (Cartesian)
+ *   ab200_rotating_frame   RotatingFrame::RotatingFrameImpl<GEOM> :96-199, every curvilinear
+ *                          system (rotating_frame.cpp:69-82).  Reads the mass fluxes of the stage:
+ *                          call after ab200_fused_stage(.. | AB200_STAGE_DEFER_C2P |
+ *                          AB200_STAGE_TAP_DFLUX) or after ab200_calculate_fluxes; AB200_ESTATE
+ *                          otherwise.  Updates momentum and total energy only.
+ *   ab200_point_mass_gravity  Gravity::PointMassGravity<GEOM>  src/gravity/point_mass.cpp:26-196:
+ *                          softened point mass at a Cartesian position + the mass sink inside
+ *                          `sink` (rate `sink_rate`; 0 disables it)
  *   ab200_drag_simple      Drag::SimpleDragSourceImpl      src/drag/drag.hpp:296-482 with constant
  *                          stopping times tau[n] per dust species (<drag/dust> type = constant),
  *                          no damping zones and no viscous target velocity (inputs/drag/simple_drag.in) */
 int ab200_uniform_gravity(ab200_ctx *ctx, double dt, double gx1, double gx2, double gx3);
 int ab200_shearing_box(ab200_ctx *ctx, double dt, double omega, double qshear);
 int ab200_drag_simple(ab200_ctx *ctx, double dt, int ntau, const double *tau);
+typedef struct ab200_point_mass_desc {
+  double gm;          /* <gravity/point> gm                                  */
+  double x, y, z;     /* Cartesian position of the mass                      */
+  double soft;        /* softening length                                    */
+  double sink_rate;   /* mass removal rate inside the sink radius (per time) */
+  double sink;        /* sink radius                                         */
+} ab200_point_mass_desc;
+int ab200_point_mass_gravity(ab200_ctx *ctx, double dt, const ab200_point_mass_desc *pm);
+int ab200_rotating_frame(ab200_ctx *ctx, double dt, double omega);
 /* Source terms the device-resident drivers (ab200_run_cycles, ab200_run_cycles_mr,
  * ab200_cycles_host) apply every stage, in the reference's task order gravity -> rotating frame
  * -> drag; NULL or all-zero switches them off (the stage then runs un-split). */
@@ -206,6 +229,8 @@ typedef struct ab200_sources_desc {
   int gravity;       double g[3];            /* Gravity::UniformGravity          */
   int shearing_box;  double omega, qshear;   /* RotatingFrame::ShearingBoxImpl   */
   int drag;          int ntau; double tau[16]; /* Drag::SimpleDragSourceImpl      */
+  int point_mass;    ab200_point_mass_desc pm; /* Gravity::PointMassGravity (instead of `gravity`) */
+  int rotating_frame; double rf_omega;       /* RotatingFrame::RotatingFrameImpl (curvilinear) */
 } ab200_sources_desc;
 int ab200_configure_sources(ab200_ctx *ctx, const ab200_sources_desc *src);
 

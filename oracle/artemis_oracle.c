@@ -1266,6 +1266,277 @@ void ao_uniform_gravity(const ao_grid *g, const ao_fluid *gas, const double *gpr
         }
 }
 
+/* ---- coordinate-system conversions used by the point-mass and rotating-frame sources ------
+ * ConvertTo{Cart,Cyl,Sph}WithVec(x) = { Convert*Coords*(x), rows ex1, ex2, ex3 of Convert*Vec*(x) }
+ * (geometry.hpp:438-484).  e[r][c]: component c of row ex{r+1}. */
+#define AO_FUZZ 1e-99 /* Fuzz<Real>(), src/artemis.hpp:112-118 */
+static inline void e_set(double e[3][3], double a0, double a1, double a2, double b0, double b1,
+                         double b2, double c0, double c1, double c2) {
+  e[0][0] = a0; e[0][1] = a1; e[0][2] = a2;
+  e[1][0] = b0; e[1][1] = b1; e[1][2] = b2;
+  e[2][0] = c0; e[2][1] = c1; e[2][2] = c2;
+}
+/* geometry.hpp:246-260, cylindrical.hpp:95-109, spherical.hpp:171-189 / 375-393 / 527-545,
+ * axisymmetric.hpp:98-113 */
+static void g_to_cart(int geom, const double xi[3], double xo[3], double e[3][3]) {
+  switch (geom) {
+  case AO_CYLINDRICAL: {
+    const double cp = cos(xi[1]), sp = sin(xi[1]);
+    e_set(e, cp, sp, 0.0, -sp, cp, 0.0, 0.0, 0.0, 1.0);
+    xo[0] = xi[0] * cp; xo[1] = xi[0] * sp; xo[2] = xi[2];
+    break;
+  }
+  case AO_AXISYMMETRIC: {
+    const double cp = cos(xi[2]), sp = sin(xi[2]);
+    e_set(e, cp, 0.0, sp, -sp, 0.0, cp, 0.0, 1.0, 0.0);
+    xo[0] = xi[0] * cp; xo[1] = xi[0] * sp; xo[2] = xi[1];
+    break;
+  }
+  case AO_SPHERICAL3D:
+  case AO_SPHERICAL2D:
+  case AO_SPHERICAL1D: {
+    const double cp = (geom == AO_SPHERICAL3D) ? cos(xi[2]) : 1.0;
+    const double sp = (geom == AO_SPHERICAL3D) ? sin(xi[2]) : 0.0;
+    const double ct = (geom == AO_SPHERICAL1D) ? 0.0 : cos(xi[1]);
+    const double st = (geom == AO_SPHERICAL1D) ? 1.0 : sin(xi[1]);
+    e_set(e, st * cp, st * sp, ct, ct * cp, ct * sp, -st, -sp, cp, 0.0);
+    xo[0] = xi[0] * st * cp; xo[1] = xi[0] * st * sp; xo[2] = xi[0] * ct;
+    break;
+  }
+  default:
+    e_set(e, 1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0);
+    xo[0] = xi[0]; xo[1] = xi[1]; xo[2] = xi[2];
+  }
+}
+/* geometry.hpp:284-302, cylindrical.hpp:127-137, spherical.hpp:201-222 / 405-426 / 557-578,
+ * axisymmetric.hpp:134-146 */
+static void g_to_cyl(int geom, const double xi[3], double xo[3], double e[3][3]) {
+  switch (geom) {
+  case AO_CYLINDRICAL:
+    e_set(e, 1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0);
+    xo[0] = xi[0]; xo[1] = xi[1]; xo[2] = xi[2];
+    break;
+  case AO_AXISYMMETRIC:
+    e_set(e, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 1.0, 0.0);
+    xo[0] = xi[0]; xo[1] = xi[2]; xo[2] = xi[1];
+    break;
+  case AO_SPHERICAL3D:
+  case AO_SPHERICAL2D:
+  case AO_SPHERICAL1D: {
+    const double ct = (geom == AO_SPHERICAL1D) ? 0.0 : cos(xi[1]);
+    const double st = (geom == AO_SPHERICAL1D) ? 1.0 : sin(xi[1]);
+    e_set(e, st, 0.0, ct, ct, 0.0, -st, 0.0, 1.0, 0.0);
+    xo[0] = xi[0] * st; xo[1] = (geom == AO_SPHERICAL3D) ? xi[2] : 0.0; xo[2] = xi[0] * ct;
+    break;
+  }
+  default: { /* Cartesian */
+    const double R = sqrt(xi[0] * xi[0] + xi[1] * xi[1]);
+    const double cp = xi[0] / (R + AO_FUZZ), sp = xi[1] / (R + AO_FUZZ);
+    e_set(e, cp, -sp, 0.0, sp, cp, 0.0, 0.0, 0.0, 1.0);
+    xo[0] = R; xo[1] = atan2(sp, cp); xo[2] = xi[2];
+  }
+  }
+}
+/* RFWeights: +-(<R^2>_face - <R^2>) of the cylindrical radius; geometry.hpp:228-232,
+ * cylindrical.hpp:88-93, axisymmetric.hpp:91-96, spherical.hpp:148-169 / 352-373 / 514-525 */
+static void g_rf_weights(int geom, const bbox_t *b, double bx[3][2]) {
+  for (int d = 0; d < 3; ++d) bx[d][0] = bx[d][1] = 0.0;
+  if (geom == AO_CYLINDRICAL || geom == AO_AXISYMMETRIC) {
+    const double ans = 0.5 * (b->x1[0] + b->x1[1]) * (b->x1[1] - b->x1[0]);
+    bx[0][0] = bx[0][1] = ans;
+  } else if (geom == AO_SPHERICAL3D || geom == AO_SPHERICAL2D) {
+    const double rv = g_x1v(geom, b);
+    const double stv = sin(g_x2v(geom, b));
+    const double rf = rface_avg(b);
+    const double r2cyl = (rv * stv) * (rv * stv);
+    bx[0][0] = r2cyl - (b->x1[0] * stv) * (b->x1[0] * stv);
+    bx[0][1] = (b->x1[1] * stv) * (b->x1[1] * stv) - r2cyl;
+    bx[1][0] = r2cyl - (rf * sin(b->x2[0])) * (rf * sin(b->x2[0]));
+    bx[1][1] = (rf * sin(b->x2[1])) * (rf * sin(b->x2[1])) - r2cyl;
+  } else if (geom == AO_SPHERICAL1D) {
+    const double rv = g_x1v(geom, b);
+    const double r2cyl = rv * rv;
+    bx[0][0] = r2cyl - b->x1[0] * b->x1[0];
+    bx[0][1] = b->x1[1] * b->x1[1] - r2cyl;
+  }
+}
+
+/* Gravity::PointMassGravity<GEOM>, src/gravity/point_mass.cpp:26-196.
+ * pm = {gm, x, y, z, soft, sink_rate, sink}: the gravity-package parameters it reads. */
+void ao_point_mass_gravity(const ao_grid *g, const ao_fluid *gas, const double *gprim,
+                           double *gcons, const ao_fluid *dust, const double *dprim,
+                           double *dcons, double dt, const double *pm) {
+  const size_t cells = (size_t)g->ni * g->nj * g->nk;
+  const int geom = g->geom;
+  const double gm = pm[0];
+  const double pos[3] = {pm[1], pm[2], pm[3]};
+  const double rsft2 = pm[4] * pm[4];
+  const double sink_rate = dt * pm[5];
+  const double sink_rad = pm[6];
+  const int multi_d = (g->ndim >= 2), three_d = (g->ndim == 3);
+#pragma omp parallel for collapse(3) schedule(static)
+  for (int b = 0; b < g->nb; ++b)
+    for (int k = g->ks; k <= g->ke; ++k)
+      for (int j = g->js; j <= g->je; ++j)
+        for (int i = g->is; i <= g->ie; ++i) {
+          const bbox_t bb = make_bbox(g->xmin + 3 * b, g->dx + 3 * b, k, j, i);
+          const double dx[3] = {g_x1v(geom, &bb), g_x2v(geom, &bb), g_x3v(geom, &bb)};
+          const double hx[3] = {g_hx1v(geom, &bb), g_hx2v(geom, &bb), g_hx3v(geom, &bb)};
+          double gx1 = 0.0, gx2 = 0.0, gx3 = 0.0, dr;
+          if (geom == AO_SPHERICAL1D || geom == AO_SPHERICAL2D) { /* :76-80 */
+            const double rad2 = dx[0] * dx[0] + rsft2;
+            gx1 = -gm / rad2;
+            dr = sqrt(rad2);
+          } else if (geom == AO_AXISYMMETRIC) { /* :81-88 with axisymmetric.hpp:115-133 */
+            const double rs = sqrt(dx[0] * dx[0] + dx[1] * dx[1]);
+            const double ct = dx[1] / (rs + AO_FUZZ);
+            const double st = dx[0] / (rs + AO_FUZZ);
+            dr = rs;
+            const double rad2 = dr * dr + rsft2;
+            const double gg = -gm / rad2;
+            gx1 = gg * st; /* ex1[0] */
+            gx2 = gg * ct; /* ex3[0] */
+          } else { /* :89-114 */
+            double dxc[3], e[3][3];
+            g_to_cart(geom, dx, dxc, e);
+            for (int n = 0; n < 3; n++) dxc[n] -= pos[n];
+            /* Coords<cartesian>::ConvertToSph: only the radius is used (geometry.hpp:262-269) */
+            const double R = sqrt(dxc[0] * dxc[0] + dxc[1] * dxc[1]);
+            dr = sqrt(R * R + dxc[2] * dxc[2]);
+            const double rad2 = dr * dr + rsft2;
+            const double idr3 = 1.0 / (sqrt(rad2) * rad2);
+            const double gv[3] = {-gm * dxc[0] * idr3, (multi_d) * (-gm * dxc[1] * idr3),
+                                  (three_d) * (-gm * dxc[2] * idr3)};
+            gx1 = gv[0] * e[0][0] + gv[1] * e[0][1] + gv[2] * e[0][2];
+            gx2 = gv[0] * e[1][0] + gv[1] * e[1][1] + gv[2] * e[1][2];
+            gx3 = gv[0] * e[2][0] + gv[1] * e[2][1] + gv[2] * e[2][2];
+          }
+          /* mass accretion :146-148 (quad_ramp(x) = x^2, gravity.hpp:116) */
+          const double xr = (dr - sink_rad) / sink_rad;
+          const double sramp = sink_rate * (xr * xr);
+          double fd = dmin(0.5, sramp / (1.0 + sramp));
+          fd *= ((sink_rate > 0.0) && (dr <= sink_rad));
+          const size_t o = ((size_t)k * g->nj + j) * g->ni + i;
+          if (gas) {
+            const int S = gas->nspecies;
+            const double *w = gprim + (size_t)b * 6 * S * cells;
+            double *u = gcons + (size_t)b * 6 * S * cells;
+            for (int n = 0; n < S; ++n) {
+              const double rho = w[(size_t)n * cells + o];
+              const double v1 = w[(size_t)(S + 3 * n + 0) * cells + o];
+              const double v2 = w[(size_t)(S + 3 * n + 1) * cells + o];
+              const double v3 = w[(size_t)(S + 3 * n + 2) * cells + o];
+              const double sie = w[(size_t)(5 * S + n) * cells + o];
+              const double tote = rho * (sie + 0.5 * (v1 * v1 + v2 * v2 + v3 * v3));
+              double *m1 = u + (size_t)(S + 3 * n + 0) * cells + o;
+              double *m2 = u + (size_t)(S + 3 * n + 1) * cells + o;
+              double *m3 = u + (size_t)(S + 3 * n + 2) * cells + o;
+              double *en = u + (size_t)(4 * S + n) * cells + o;
+              *m1 += dt * rho * hx[0] * gx1;
+              *m2 += dt * rho * hx[1] * gx2;
+              *m3 += dt * rho * hx[2] * gx3;
+              *en += dt * rho * (v1 * gx1 + v2 * gx2 + v3 * gx3);
+              u[(size_t)n * cells + o] -= fd * rho;
+              *m1 -= fd * hx[0] * rho * v1;
+              *m2 -= fd * hx[1] * rho * v2;
+              *m3 -= fd * hx[2] * rho * v3;
+              *en -= fd * tote;
+            }
+          }
+          if (dust) {
+            const int S = dust->nspecies;
+            const double *w = dprim + (size_t)b * 4 * S * cells;
+            double *u = dcons + (size_t)b * 4 * S * cells;
+            for (int n = 0; n < S; ++n) {
+              const double rho = w[(size_t)n * cells + o];
+              const double v1 = w[(size_t)(S + 3 * n + 0) * cells + o];
+              const double v2 = w[(size_t)(S + 3 * n + 1) * cells + o];
+              const double v3 = w[(size_t)(S + 3 * n + 2) * cells + o];
+              double *m1 = u + (size_t)(S + 3 * n + 0) * cells + o;
+              double *m2 = u + (size_t)(S + 3 * n + 1) * cells + o;
+              double *m3 = u + (size_t)(S + 3 * n + 2) * cells + o;
+              *m1 += dt * rho * hx[0] * gx1;
+              *m2 += dt * rho * hx[1] * gx2;
+              *m3 += dt * rho * hx[2] * gx3;
+              u[(size_t)n * cells + o] -= fd * rho;
+              *m1 -= fd * hx[0] * rho * v1;
+              *m2 -= fd * hx[1] * rho * v2;
+              *m3 -= fd * hx[2] * rho * v3;
+            }
+          }
+        }
+}
+
+/* RotatingFrame::RotatingFrameImpl<GEOM>, src/rotating_frame/rotating_frame_impl.hpp:96-199
+ * (every non-Cartesian geometry, rotating_frame.cpp:69-82).  Reads the DENSITY fluxes of the
+ * stage: gflux[d] / dflux[d] are the [nb][nvar][cells] flux slabs of ao_calculate_fluxes. */
+static void rotating_frame_fluid(const ao_grid *g, int gasf, int S, int nvar, double *cons,
+                                 const double *const fl[3], int b, int k, int j, int i,
+                                 const double ax[3][2], const double bx[3][2], double vol,
+                                 double omdt, double om2dt, double xcyl0, double e[3][3]) {
+  const size_t cells = (size_t)g->ni * g->nj * g->nk;
+  const int multi_d = (g->ndim >= 2), three_d = (g->ndim == 3);
+  const size_t sj = (size_t)g->ni, sk = (size_t)g->ni * g->nj;
+  const size_t o = ((size_t)k * g->nj + j) * g->ni + i;
+  double *u = cons + (size_t)b * nvar * cells;
+  for (int n = 0; n < S; ++n) {
+    const double *f1 = fl[0] + ((size_t)b * nvar + n) * cells;
+    const double *f2 = fl[1] ? fl[1] + ((size_t)b * nvar + n) * cells : f1;
+    const double *f3 = fl[2] ? fl[2] + ((size_t)b * nvar + n) * cells : f1;
+    const double f1m = f1[o], f1p = f1[o + 1];
+    const double f2m = multi_d ? f2[o] : 0.0, f2p = multi_d ? f2[o + sj] : 0.0;
+    const double f3m = three_d ? f3[o] : 0.0, f3p = three_d ? f3[o + sk] : 0.0;
+    const double divf = (f1m * ax[0][0] * bx[0][0] + f1p * ax[0][1] * bx[0][1]) +
+                        multi_d * (f2m * ax[1][0] * bx[1][0] + f2p * ax[1][1] * bx[1][1]) +
+                        three_d * (f3m * ax[2][0] * bx[2][0] + f3p * ax[2][1] * bx[2][1]);
+    u[(size_t)(S + 3 * n + 0) * cells + o] -= omdt * (divf / vol) * e[0][1];
+    u[(size_t)(S + 3 * n + 1) * cells + o] -= omdt * (divf / vol) * e[1][1];
+    u[(size_t)(S + 3 * n + 2) * cells + o] -= omdt * (divf / vol) * e[2][1];
+    if (gasf) {
+      const double fx[3] = {0.5 * (f1m + f1p), multi_d * 0.5 * (f2m + f2p),
+                            three_d * 0.5 * (f3m + f3p)};
+      u[(size_t)(4 * S + n) * cells + o] +=
+          om2dt * xcyl0 * (fx[0] * e[0][0] + fx[1] * e[1][0] + fx[2] * e[2][0]);
+    }
+  }
+}
+void ao_rotating_frame(const ao_grid *g, const ao_fluid *gas, double *gcons,
+                       const double *gflux1, const double *gflux2, const double *gflux3,
+                       const ao_fluid *dust, double *dcons, const double *dflux1,
+                       const double *dflux2, const double *dflux3, double dt, double om0) {
+  const int geom = g->geom;
+  if (geom == AO_CARTESIAN) return; /* the Cartesian frame is the shearing box */
+  const int multi_d = (g->ndim >= 2), three_d = (g->ndim == 3);
+  const double omdt = om0 * dt;
+  const double om2dt = omdt * om0;
+  const double *const gf[3] = {gflux1, gflux2, gflux3};
+  const double *const df[3] = {dflux1, dflux2, dflux3};
+#pragma omp parallel for collapse(3) schedule(static)
+  for (int b = 0; b < g->nb; ++b)
+    for (int k = g->ks; k <= g->ke; ++k)
+      for (int j = g->js; j <= g->je; ++j)
+        for (int i = g->is; i <= g->ie; ++i) {
+          const bbox_t bb = make_bbox(g->xmin + 3 * b, g->dx + 3 * b, k, j, i);
+          const double xv[3] = {g_x1v(geom, &bb), g_x2v(geom, &bb), g_x3v(geom, &bb)};
+          double xcyl[3], e[3][3], bx[3][2], ax[3][2];
+          g_to_cyl(geom, xv, xcyl, e);
+          g_rf_weights(geom, &bb, bx);
+          ax[0][0] = g_area1(geom, &bb, bb.x1[0]);
+          ax[0][1] = g_area1(geom, &bb, bb.x1[1]);
+          ax[1][0] = multi_d ? g_area2(geom, &bb, bb.x2[0]) : 0.0;
+          ax[1][1] = multi_d ? g_area2(geom, &bb, bb.x2[1]) : 0.0;
+          ax[2][0] = three_d ? g_area3(geom, &bb, bb.x3[0]) : 0.0;
+          ax[2][1] = three_d ? g_area3(geom, &bb, bb.x3[1]) : 0.0;
+          const double vol = g_volume(geom, &bb);
+          if (gas)
+            rotating_frame_fluid(g, 1, gas->nspecies, 6 * gas->nspecies, gcons, gf, b, k, j, i,
+                                 ax, bx, vol, omdt, om2dt, xcyl[0], e);
+          if (dust)
+            rotating_frame_fluid(g, 0, dust->nspecies, 4 * dust->nspecies, dcons, df, b, k, j, i,
+                                 ax, bx, vol, omdt, om2dt, xcyl[0], e);
+        }
+}
+
 /* RotatingFrame::ShearingBoxImpl, src/rotating_frame/rotating_frame_impl.hpp:28-94
  * (Cartesian only: Coriolis + tidal potential differenced across the cell) */
 void ao_shearing_box(const ao_grid *g, const ao_fluid *gas, const double *gprim, double *gcons,

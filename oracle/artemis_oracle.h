@@ -136,6 +136,17 @@ void ao_uniform_gravity(const ao_grid *g, const ao_fluid *gas, const double *gpr
 void ao_shearing_box(const ao_grid *g, const ao_fluid *gas, const double *gprim, double *gcons,
                      const ao_fluid *dust, const double *dprim, double *dcons, double dt,
                      double om0, double qshear);
+/* Gravity::PointMassGravity<GEOM>, src/gravity/point_mass.cpp:26-196;
+ * pm = {gm, x, y, z, soft, sink_rate, sink} */
+void ao_point_mass_gravity(const ao_grid *g, const ao_fluid *gas, const double *gprim,
+                           double *gcons, const ao_fluid *dust, const double *dprim,
+                           double *dcons, double dt, const double *pm);
+/* RotatingFrame::RotatingFrameImpl<GEOM> (non-Cartesian), rotating_frame_impl.hpp:96-199;
+ * g/dflux{1,2,3}: the [nb][nvar][cells] flux slabs of the stage (unused directions may be NULL) */
+void ao_rotating_frame(const ao_grid *g, const ao_fluid *gas, double *gcons,
+                       const double *gflux1, const double *gflux2, const double *gflux3,
+                       const ao_fluid *dust, double *dcons, const double *dflux1,
+                       const double *dflux2, const double *dflux3, double dt, double om0);
 /* Drag::SimpleDragSourceImpl (constant stopping times, no damping zones, no viscous target
  * velocity), src/drag/drag.hpp:296-482 */
 void ao_drag_simple(const ao_grid *g, const ao_fluid *gas, double *gcons, const ao_fluid *dust,

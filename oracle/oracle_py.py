@@ -122,7 +122,8 @@ class OracleSim:
         self.nlim = -1
         # pointwise source terms between FluxSource and SetAuxillaryFields
         # (src/artemis_driver.cpp:217-248): list of ("gravity", gx1, gx2, gx3) |
-        # ("shearing_box", om0, qshear) | ("drag", [tau per dust species])
+        # ("shearing_box", om0, qshear) | ("drag", [tau per dust species]) |
+        # ("point_mass", gm, x, y, z, soft, sink_rate, sink) | ("rotating_frame", om0)
         self.sources = []
 
     def _both(self):
@@ -145,8 +146,22 @@ class OracleSim:
             return
         L, pre = self._src_lib()
         fg, fd, args = self._both()
-        order = {"gravity": 0, "shearing_box": 1, "drag": 2}
+        order = {"gravity": 0, "point_mass": 0, "shearing_box": 1, "rotating_frame": 1, "drag": 2}
         for src in sorted(self.sources, key=lambda t: order[t[0]]):
+            if src[0] == "point_mass":
+                pm = np.ascontiguousarray(src[1:8], dtype=np.float64)
+                getattr(L, pre + "_point_mass_gravity")(C.byref(self.g), *args, C.c_double(dt),
+                                                        _p(pm))
+                continue
+            if src[0] == "rotating_frame":
+                null = C.POINTER(C.c_double)()
+                fa = []
+                for fs in (self.gas, self.dust):
+                    fa += ([args[0 if fs is self.gas else 3], _p(fs.u0)] + [_p(a) for a in fs.flux]
+                           if fs is not None else [None, null, null, null, null])
+                getattr(L, pre + "_rotating_frame")(C.byref(self.g), *fa, C.c_double(dt),
+                                                    C.c_double(src[1]))
+                continue
             if src[0] == "gravity":
                 getattr(L, pre + "_uniform_gravity")(C.byref(self.g), *args, C.c_double(dt),
                                                     *[C.c_double(v) for v in src[1:4]])

@@ -19,6 +19,7 @@
 // source terms between FluxSource and SetAuxillaryFields
 #include "rotating_frame/rotating_frame_impl.hpp"
 #include "gravity/uniform.cpp"
+#include "gravity/point_mass.cpp"
 
 #include "../artemis_oracle.h"
 
@@ -392,6 +393,51 @@ void ar_uniform_gravity(const ao_grid *g, const ao_fluid *gas, double *gprim, do
   c.mesh.packages.pkgs["gravity"] = grav;
   GeomDispatch(g->geom, [&](auto G) {
     Gravity::UniformGravity<decltype(G)::value>(&c.md, 0.0, dt);
+  });
+}
+
+// Gravity::PointMassGravity<GEOM> (src/gravity/point_mass.cpp:26-196); pm = {gm, x, y, z, soft,
+// sink_rate, sink}: the "gravity" package parameters it reads.
+void ar_point_mass_gravity(const ao_grid *g, const ao_fluid *gas, double *gprim, double *gcons,
+                           const ao_fluid *dust, double *dprim, double *dcons, double dt,
+                           const double *pm) {
+  Ctx c;
+  SetBoth(c, g, gas, gprim, gcons, dust, dprim, dcons);
+  auto grav = std::make_shared<StateDescriptor>();
+  grav->AddParam<Real>("gm", pm[0]);
+  grav->AddParam<Real>("x", pm[1]);
+  grav->AddParam<Real>("y", pm[2]);
+  grav->AddParam<Real>("z", pm[3]);
+  grav->AddParam<Real>("soft", pm[4]);
+  grav->AddParam<Real>("sink_rate", pm[5]);
+  grav->AddParam<Real>("sink", pm[6]);
+  c.mesh.packages.pkgs["gravity"] = grav;
+  GeomDispatch(g->geom, [&](auto G) {
+    Gravity::PointMassGravity<decltype(G)::value>(&c.md, 0.0, dt);
+  });
+}
+
+// RotatingFrame::RotatingFrameImpl<GEOM> (rotating_frame_impl.hpp:96-199), the curvilinear
+// branch of RotatingFrameForce (rotating_frame.cpp:54-86): reads the DENSITY fluxes of the
+// stage.  gflux / dflux: [3] slabs [nb][nvar][cells] as written by ar_calculate_fluxes.
+void ar_rotating_frame(const ao_grid *g, const ao_fluid *gas, double *gcons, double *gflux1,
+                       double *gflux2, double *gflux3, const ao_fluid *dust, double *dcons,
+                       double *dflux1, double *dflux2, double *dflux3, double dt, double om0) {
+  Ctx c;
+  SetGrid(c, g);
+  double *gf[3] = {gflux1, gflux2, gflux3}, *df[3] = {dflux1, dflux2, dflux3};
+  if (gas) {
+    SetFluidPkg(c, g, gas);
+    AddSlab(c, g, gas, false, gcons, gf, nullptr, nullptr);
+  }
+  if (dust) {
+    SetFluidPkg(c, g, dust);
+    AddSlab(c, g, dust, false, dcons, df, nullptr, nullptr);
+  }
+  GeomDispatch(g->geom, [&](auto G) {
+    constexpr Coordinates GG = decltype(G)::value;
+    if constexpr (GG != Coordinates::cartesian)
+      RotatingFrame::RotatingFrameImpl<GG>(&c.md, om0, gas != nullptr, dust != nullptr, dt);
   });
 }
 }  // extern "C"

@@ -1,7 +1,8 @@
 """GPU parity of the pointwise source terms and of the split stage that hosts
 them: ab200_fused_stage(AB200_STAGE_DEFER_C2P) -> ab200_uniform_gravity / ab200_shearing_box /
-ab200_drag_simple -> ab200_finish_stage, against the oracle (gravity and shearing box pinned bit
-for bit to the reference's own code, tests/test_sources_oracle.py)."""
+ab200_drag_simple / ab200_point_mass_gravity / ab200_rotating_frame -> ab200_finish_stage,
+against the oracle (gravity, point mass, shearing box and rotating frame pinned bit for bit to the
+reference's own code, tests/test_sources_oracle.py)."""
 import numpy as np
 import pytest
 
@@ -19,12 +20,26 @@ CASES = [
     (Coordinates.cartesian, [("drag", [1e-3, 0.5])], "rk2"),
     (Coordinates.cylindrical, [("gravity", -0.5, 0.0, 0.2), ("drag", [0.05, 2.0])], "rk3"),
     (Coordinates.spherical3D, [("gravity", -0.7, 0.0, 0.0)], "rk2"),
+    # Gravity::PointMassGravity (off-centre, softened, with and without the mass sink) and the
+    # curvilinear RotatingFrameImpl on the mass fluxes of the stage -- the disk decks' sources
+    (Coordinates.cartesian, [("point_mass", 0.7, 0.11, -0.07, 0.05, 0.03, 40.0, 2.5)], "rk2"),
+    (Coordinates.cylindrical, [("point_mass", 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0),
+                               ("rotating_frame", 0.8)], "vl2"),
+    (Coordinates.spherical3D, [("point_mass", 0.7, 0.11, -0.07, 0.05, 0.03, 40.0, 2.5),
+                               ("rotating_frame", 0.6), ("drag", [0.05, 2.0])], "rk2"),
+    (Coordinates.spherical2D, [("point_mass", 1.0, 0.0, 0.0, 0.0, 0.02, 0.0, 0.0),
+                               ("rotating_frame", -0.7)], "rk2"),
+    (Coordinates.spherical1D, [("point_mass", 1.0, 0.0, 0.0, 0.0, 0.0, 30.0, 1.2),
+                               ("rotating_frame", 0.5)], "rk2"),
+    (Coordinates.axisymmetric, [("point_mass", 0.9, 0.0, 0.0, 0.0, 0.03, 25.0, 1.0),
+                                ("rotating_frame", 0.9)], "rk3"),
 ]
+NDIM = {Coordinates.axisymmetric: 2}
 
 
 def _run(coords, sources, integ, mode, variant, ncyc=2):
     bcs = (BoundaryFlag.outflow,) * 6 if coords != Coordinates.cartesian else None
-    mesh = make_mesh(coords, 3, bcs=bcs)
+    mesh = make_mesh(coords, NDIM.get(coords, 3), bcs=bcs)
     gp, dp = gas_params(coords, "ppm", "hllc"), dust_params(coords, "plm", "hlle", S=2)
     prim, dprim = random_prim(mesh, gp, seed=71), random_prim(mesh, dp, seed=72)
     osim = OracleSim(mesh, gas=gp, dust=dp, integrator=integ)
@@ -132,6 +147,63 @@ def test_device_resident_cycles_with_configured_sources(variant):
         assert ts[0] == d1.dt and ts[2] == d1.time
     md1.close()
     md2.close()
+
+
+@pytest.mark.parametrize("variant", ["strict", "fast"])
+def test_device_resident_cycles_with_point_mass_and_rotating_frame(variant):
+    """The disk decks' sources through ab200_configure_sources + ab200_run_cycles on a spherical
+    mesh: every stage taps the mass fluxes of its three passes (AB200_STAGE_TAP_DFLUX) for
+    RotatingFrameImpl.  == the host-driven fused loop; strict: bit for bit."""
+    import ctypes as C
+    from artemis_b200 import capi
+    coords = Coordinates.spherical3D
+    mesh = make_mesh(coords, 3, bcs=(BoundaryFlag.outflow,) * 6)
+    gp, dp = gas_params(coords, "ppm", "hlle"), dust_params(coords, "plm", "hlle", S=2)
+    prim, dprim = random_prim(mesh, gp, seed=83), random_prim(mesh, dp, seed=84)
+    pm = (0.7, 0.11, -0.07, 0.05, 0.03, 40.0, 2.5)
+    sources = [("point_mass",) + pm, ("rotating_frame", 0.6)]
+    ncyc = 3
+    md1 = MeshData(mesh, gas=gp, dust=dp, variant=variant, materialize_fluxes=False)
+    md1.gas.prim.set(prim)
+    md1.dust.prim.set(dprim)
+    d1 = ArtemisDriver(md1, "rk2", mode="fused", nlim=ncyc, sources=sources)
+    d1.Initialize()
+    d1.Execute()
+    md2 = MeshData(mesh, gas=gp, dust=dp, variant=variant, materialize_fluxes=False)
+    md2.gas.prim.set(prim)
+    md2.dust.prim.set(dprim)
+    d2 = ArtemisDriver(md2, "rk2", mode="fused")
+    d2.Initialize()
+    sd = capi.SourcesDesc()
+    sd.point_mass, sd.pm = 1, capi.PointMassDesc(*pm)
+    sd.rotating_frame, sd.rf_omega = 1, 0.6
+    md2.call("ab200_configure_sources", C.byref(sd))
+    md2.set_time_state(d2.dt)
+    md2.call("ab200_run_cycles", 1, ncyc, float(np.finfo(np.float64).max))
+    ts = md2.time_state()
+    assert int(ts[3]) == ncyc
+    for f1, f2 in zip(md1.fluids, md2.fluids):
+        if variant == "strict":
+            assert np.array_equal(f1.u0.get(), f2.u0.get())
+            assert np.array_equal(f1.prim.get(), f2.prim.get())
+        else:
+            assert zone_rel_err(f2.u0.get(), f1.u0.get(), f1.fp, "cons") <= 1e-12
+    md1.close()
+    md2.close()
+
+
+def test_rotating_frame_without_mass_fluxes_is_an_error():
+    """ab200_rotating_frame after a stage that did not keep its mass fluxes -> AB200_ESTATE."""
+    from artemis_b200 import capi
+    coords = Coordinates.cylindrical
+    mesh = make_mesh(coords, 3, bcs=(BoundaryFlag.outflow,) * 6)
+    gp = gas_params(coords, "plm", "hlle")
+    md = MeshData(mesh, gas=gp, materialize_fluxes=False)
+    md.gas.prim.set(random_prim(mesh, gp, seed=85))
+    md.call("ab200_prim_to_cons")
+    with pytest.raises(capi.AB200Error, match="no mass fluxes"):
+        md.call("ab200_rotating_frame", 1e-3, 0.5)
+    md.close()
 
 
 @pytest.mark.parametrize("coords", [Coordinates.cartesian, Coordinates.spherical3D,

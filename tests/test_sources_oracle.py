@@ -16,9 +16,9 @@ from tests.helpers import dust_params, gas_params, make_mesh, random_prim
 needs_ref = pytest.mark.skipif(not ref_py.available(), reason="oracle/_ref not built")
 
 
-def _pair(coords, sources, integ="rk2", ncyc=1):
+def _pair(coords, sources, integ="rk2", ncyc=1, ndim=3):
     bcs = (BoundaryFlag.outflow,) * 6 if coords != Coordinates.cartesian else None
-    mesh = make_mesh(coords, 3, bcs=bcs)
+    mesh = make_mesh(coords, ndim, bcs=bcs)
     gp, dp = gas_params(coords, "plm", "hlle"), dust_params(coords, "plm", "hlle", S=2)
     sims = []
     for cls in (OracleSim, ref_py.RefSim):
@@ -51,6 +51,41 @@ def test_shearing_box_restatement_is_bit_identical_to_reference_code():
                  integ="vl2", ncyc=2)
     for fo, fr in zip(o.fluids, r.fluids):
         assert np.array_equal(fo.u0, fr.u0) and np.array_equal(fo.prim, fr.prim)
+
+
+ALL_GEOMS = [(Coordinates.cartesian, 3), (Coordinates.cartesian, 2), (Coordinates.cylindrical, 3),
+             (Coordinates.spherical1D, 1), (Coordinates.spherical2D, 2),
+             (Coordinates.spherical3D, 3), (Coordinates.axisymmetric, 2)]
+
+
+@needs_ref
+@pytest.mark.parametrize("coords,ndim", ALL_GEOMS)
+@pytest.mark.parametrize("sink", [False, True])
+def test_point_mass_gravity_restatement_is_bit_identical_to_reference_code(coords, ndim, sink):
+    """Gravity::PointMassGravity<GEOM> (src/gravity/point_mass.cpp:26-196): off-centre mass with
+    softening; with `sink` the accretion radius covers part of the mesh."""
+    pm = ("point_mass", 0.7, 0.11, -0.07, 0.05, 0.03) + ((40.0, 2.5) if sink else (0.0, 0.0))
+    o, r = _pair(coords, [pm], ndim=ndim)
+    for fo, fr in zip(o.fluids, r.fluids):
+        assert np.array_equal(fo.u0, fr.u0) and np.array_equal(fo.prim, fr.prim)
+    base, _ = _pair(coords, [], ndim=ndim)
+    assert not np.array_equal(base.gas.u0, o.gas.u0)
+    if sink:   # the sink removed mass somewhere
+        nos, _ = _pair(coords, [pm[:6] + (0.0, 0.0)], ndim=ndim)
+        assert np.any(o.gas.u0[:, 0] < nos.gas.u0[:, 0])
+
+
+@needs_ref
+@pytest.mark.parametrize("coords,ndim", [g for g in ALL_GEOMS if g[0] != Coordinates.cartesian])
+def test_rotating_frame_restatement_is_bit_identical_to_reference_code(coords, ndim):
+    """RotatingFrame::RotatingFrameImpl<GEOM> (rotating_frame_impl.hpp:96-199) on the density
+    fluxes of the stage, together with the point mass (the disk decks' pair of sources)."""
+    src = [("rotating_frame", 0.8), ("point_mass", 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0)]
+    o, r = _pair(coords, src, integ="vl2", ncyc=2, ndim=ndim)
+    for fo, fr in zip(o.fluids, r.fluids):
+        assert np.array_equal(fo.u0, fr.u0) and np.array_equal(fo.prim, fr.prim)
+    base, _ = _pair(coords, src[1:], integ="vl2", ncyc=2, ndim=ndim)
+    assert not np.array_equal(base.gas.u0, o.gas.u0)
 
 
 def test_drag_conserves_total_momentum_and_relaxes_to_the_common_velocity():
