@@ -1537,6 +1537,329 @@ void ao_rotating_frame(const ao_grid *g, const ao_fluid *gas, double *gcons,
         }
 }
 
+/* ==========================================================================================
+ * Diffusion operators: viscous stress and heat conduction of the gas.
+ * Reference: src/utils/diffusion/{momentum_diffusion,thermal_diffusion,diffusion_coeff,
+ * diffusion}.hpp driven by Gas::{ZeroDiffusionFlux,ViscousFlux,ThermalFlux,DiffusionUpdate}
+ * (src/gas/gas.cpp:524-642).  The reference marches pencils with scratch rows; face by face the
+ * arithmetic is the one restated here (same operands, same operation order).
+ * ========================================================================================== */
+typedef struct {
+  double xv[3], hx[3];
+  bbox_t bb;
+} dcell_t;
+static inline dcell_t dcell(const ao_grid *g, int b, int k, int j, int i) {
+  dcell_t c;
+  c.bb = make_bbox(g->xmin + 3 * b, g->dx + 3 * b, k, j, i);
+  c.xv[0] = g_x1v(g->geom, &c.bb); c.xv[1] = g_x2v(g->geom, &c.bb); c.xv[2] = g_x3v(g->geom, &c.bb);
+  c.hx[0] = g_hx1v(g->geom, &c.bb); c.hx[1] = g_hx2v(g->geom, &c.bb); c.hx[2] = g_hx3v(g->geom, &c.bb);
+  return c;
+}
+/* CoordsBase::Distance, geometry.hpp:398-403 */
+static inline double g_distance(int geom, const double x1[3], const double x2[3]) {
+  double a[3], b[3], e[3][3];
+  g_to_cart(geom, x1, a, e);
+  g_to_cart(geom, x2, b, e);
+  return sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) +
+              (a[2] - b[2]) * (a[2] - b[2]));
+}
+/* radius of ConvertToSph(xv): geometry.hpp:262-269, cylindrical.hpp:110-115,
+ * axisymmetric.hpp:115-120, spherical.hpp (identity) */
+static inline double g_sph_radius(int geom, const double xi[3]) {
+  if (geom == AO_CARTESIAN) {
+    const double R = sqrt(xi[0] * xi[0] + xi[1] * xi[1]);
+    return sqrt(R * R + xi[2] * xi[2]);
+  }
+  if (geom == AO_CYLINDRICAL) return sqrt(xi[0] * xi[0] + xi[2] * xi[2]);
+  if (geom == AO_AXISYMMETRIC) return sqrt(xi[0] * xi[0] + xi[1] * xi[1]);
+  return xi[0];
+}
+/* dh_D/dx_k: geometry.hpp:234-244 (all zero by default) + the overrides in g_conn1 / g_conn2 */
+static inline void g_dh(int geom, const bbox_t *b, double dh[3][3]) {
+  double c1[3], c2[3];
+  g_conn1(geom, b, c1);
+  g_conn2(geom, b, c2);
+  for (int D = 0; D < 3; ++D) { dh[D][0] = c1[D]; dh[D][1] = c2[D]; dh[D][2] = 0.0; }
+}
+#define PR(v, kk, jj, ii) prim[IDX(g, nvar, b, (v), (kk), (jj), (ii))]
+/* DiffusionCoeff<viscosity_plaw / viscosity_alpha>, diffusion_coeff.hpp:178-268 */
+static double visc_mu(const ao_grid *g, const ao_fluid *f, const ao_diffusion *dd, const double *prim,
+                      int b, int n, int k, int j, int i) {
+  const int S = f->nspecies, nvar = 6 * S;
+  const dcell_t c = dcell(g, b, k, j, i);
+  const double dens = PR(n, k, j, i);
+  if (dd->visc_type == AO_VISC_PLAW) {
+    double xs[3], e[3][3];
+    g_to_cyl(g->geom, c.xv, xs, e);
+    return dd->nu * dens * pow(xs[0] / dd->r0, dd->r_exp);
+  }
+  const double rs = g_sph_radius(g->geom, c.xv);
+  const double Omk = dd->omega0 * pow(rs / dd->r0, -1.5);
+  const double sie = PR(5 * S + n, k, j, i);
+  const double blk = dmax(0.0, (f->gm1 + 1) * f->gm1 * dens * sie);
+  return dd->alpha * blk / Omk;
+}
+/* DiffusionCoeff<conductivity_plaw / thermaldiff_plaw>, diffusion_coeff.hpp:270-384 */
+static double cond_kappa(const ao_grid *g, const ao_fluid *f, const ao_diffusion *dd,
+                         const double *prim, int b, int n, int k, int j, int i) {
+  const int S = f->nspecies, nvar = 6 * S;
+  const double dens = PR(n, k, j, i), sie = PR(5 * S + n, k, j, i);
+  const double T = dmax(0.0, sie / dd->cv);
+  if (dd->cond_type == AO_COND_CONDUCTIVITY)
+    return dd->cond * pow(T / dd->t_ref, dd->temp_exp) * pow(dens / dd->rho_ref, dd->rho_exp);
+  return dd->kappa * pow(T / dd->t_ref, dd->temp_exp) * pow(dens / dd->rho_ref, dd->rho_exp) *
+         dens * dd->cv;
+}
+/* FaceAverage selection of StressTensorFaceX* / ThermalFluxImpl: avg * arithmetic + havg * harmonic
+ * (both evaluated), diffusion_coeff.hpp:148-160 */
+static inline double face_avg(int avg_type, double m1, double m2) {
+  const double avg = (avg_type == AO_AVG_ARITHMETIC), havg = (avg_type == AO_AVG_HARMONIC);
+  return avg * (0.5 * (m1 + m2)) + havg * (2.0 * m1 * m2 / (m1 + m2));
+}
+/* VelocityDivergence, momentum_diffusion.hpp:553-590 */
+static double vel_div(const ao_grid *g, const double *prim, int nvar, int S, int b, int n, int k,
+                      int j, int i) {
+  const int multid = (g->ndim >= 2), threed = (g->ndim == 3);
+  const bbox_t bb = make_bbox(g->xmin + 3 * b, g->dx + 3 * b, k, j, i);
+  const double vol = g_volume(g->geom, &bb);
+  const double a1[2] = {g_area1(g->geom, &bb, bb.x1[0]), g_area1(g->geom, &bb, bb.x1[1])};
+  const double a2[2] = {multid ? g_area2(g->geom, &bb, bb.x2[0]) : 0.0,
+                        multid ? g_area2(g->geom, &bb, bb.x2[1]) : 0.0};
+  const double a3[2] = {threed ? g_area3(g->geom, &bb, bb.x3[0]) : 0.0,
+                        threed ? g_area3(g->geom, &bb, bb.x3[1]) : 0.0};
+  const int v1 = S + 3 * n, v2 = S + 3 * n + 1, v3 = S + 3 * n + 2;
+  const double divv =
+      a1[1] * (PR(v1, k, j, i) + PR(v1, k, j, i + 1)) -
+      a1[0] * (PR(v1, k, j, i) + PR(v1, k, j, i - 1)) +
+      multid * a2[1] * (PR(v2, k, j, i) + PR(v2, k, j + multid, i)) -
+      multid * a2[0] * (PR(v2, k, j, i) + PR(v2, k, j - multid, i)) +
+      threed * a3[1] * (PR(v3, k, j, i) + PR(v3, k + threed, j, i)) -
+      threed * a3[0] * (PR(v3, k, j, i) + PR(v3, k - threed, j, i));
+  return divv / (2.0 * vol);
+}
+/* Viscous flux through the LOWER face of cell (k,j,i) in direction D (0,1,2):
+ * StrainTensorFace<XDIR> + StressTensorFaceX{1,2,3}, momentum_diffusion.hpp:27-551.
+ * out = {F(m1), F(m2), F(m3), F(E)}. */
+static void visc_face(const ao_grid *g, const ao_fluid *f, const ao_diffusion *dd,
+                      const double *prim, int D, int b, int n, int k, int j, int i, double out[4]) {
+  const int S = f->nspecies, nvar = 6 * S, geom = g->geom;
+  const int multid = (g->ndim >= 2), threed = (g->ndim == 3);
+  const int off[3] = {1, multid, threed};   /* neighbour offset along each direction */
+  const int vi[3] = {S + 3 * n, S + 3 * n + 1, S + 3 * n + 2};
+  int dk[3] = {0, 0, 0}, dj[3] = {0, 0, 0}, di[3] = {0, 0, 0};
+  di[0] = 1; dj[1] = 1; dk[2] = 1;          /* unit step of direction c */
+  const dcell_t c0 = dcell(g, b, k, j, i);
+  const int km = k - dk[D], jm = j - dj[D], im = i - di[D];  /* the cell across the face */
+  const dcell_t cm = dcell(g, b, km, jm, im);
+  double v[3], vm[3];
+  for (int c = 0; c < 3; ++c) {
+    v[c] = PR(vi[c], k, j, i) / c0.hx[c];
+    vm[c] = PR(vi[c], km, jm, im) / cm.hx[c];
+  }
+  double xf[3];
+  if (D == 0) g_facecen1(geom, &c0.bb, 0, xf);
+  else if (D == 1) g_facecen2(geom, &c0.bb, 0, xf);
+  else g_facecen3(geom, &c0.bb, 0, xf);
+  const double hxf[3] = {g_hx1(geom, xf[0], xf[1], xf[2]), g_hx2(geom, xf[0], xf[1], xf[2]),
+                         g_hx3(geom, xf[0], xf[1], xf[2])};
+  const double dxD = g_distance(geom, c0.xv, cm.xv);
+  double dh0[3][3], dhm[3][3];
+  g_dh(geom, &c0.bb, dh0);
+  g_dh(geom, &cm.bb, dhm);
+  double flx[3];
+  for (int c = 0; c < 3; ++c) {
+    if (c == D) {
+      /* T_D^D = 2 dv^D/dxD + v^k dhD/dxk / hD  (averaged over the two cells) */
+      const double dv = v[D] - vm[D];
+      const double src = v[0] * dh0[D][0] + v[1] * dh0[D][1] + v[2] * dh0[D][2];
+      const double srm = vm[0] * dhm[D][0] + vm[1] * dhm[D][1] + vm[2] * dhm[D][2];
+      flx[c] = 2 * dv / dxD + 0.5 * (src + srm);
+    } else {
+      /* T_c^D = dv^D/dxc (transverse, averaged over the two cells) + hc^2/hD^2 dv^c/dxD */
+      const int o = off[c];
+      const int kp = k + o * dk[c], jp = j + o * dj[c], ip = i + o * di[c];
+      const int kq = k - o * dk[c], jq = j - o * dj[c], iq = i - o * di[c];
+      const int kmp = km + o * dk[c], jmp = jm + o * dj[c], imp = im + o * di[c];
+      const int kmq = km - o * dk[c], jmq = jm - o * dj[c], imq = im - o * di[c];
+      const dcell_t cp = dcell(g, b, kp, jp, ip), cq = dcell(g, b, kq, jq, iq);
+      const dcell_t cmp = dcell(g, b, kmp, jmp, imp), cmq = dcell(g, b, kmq, jmq, imq);
+      const double dxc = o ? g_distance(geom, cq.xv, cp.xv) : AO_FUZZ;
+      const double dxc_m = o ? g_distance(geom, cmq.xv, cmp.xv) : AO_FUZZ;
+      const double dvt = PR(vi[D], kp, jp, ip) / cp.hx[D] - PR(vi[D], kq, jq, iq) / cq.hx[D];
+      const double dvt_m = PR(vi[D], kmp, jmp, imp) / cmp.hx[D] - PR(vi[D], kmq, jmq, imq) / cmq.hx[D];
+      const double dv = v[c] - vm[c];
+      const double r = hxf[c] / hxf[D];
+      flx[c] = o * 0.5 * (dvt / dxc + dvt_m / dxc_m) + (r * r) * dv / dxD;
+    }
+  }
+  const double mus = face_avg(dd->visc_avg, visc_mu(g, f, dd, prim, b, n, k, j, i),
+                              visc_mu(g, f, dd, prim, b, n, km, jm, im));
+  const double divs = (D == 0) ? vel_div(g, prim, nvar, S, b, n, k, j, i) +
+                                     vel_div(g, prim, nvar, S, b, n, km, jm, im)
+                               : vel_div(g, prim, nvar, S, b, n, km, jm, im) +
+                                     vel_div(g, prim, nvar, S, b, n, k, j, i);
+  const double hDf = hxf[D];
+  double fc[3];
+  for (int c = 0; c < 3; ++c)
+    fc[c] = (c == D) ? hDf * mus * (flx[c] - 1. / 3 * (1. - dd->eta) * divs) : hDf * mus * flx[c];
+  out[0] = fc[0]; out[1] = fc[1]; out[2] = fc[2];
+  out[3] = 0.5 * (PR(vi[0], k, j, i) / c0.hx[0] + PR(vi[0], km, jm, im) / cm.hx[0]) * fc[0] +
+           0.5 * (PR(vi[1], k, j, i) / c0.hx[1] + PR(vi[1], km, jm, im) / cm.hx[1]) * fc[1] +
+           0.5 * (PR(vi[2], k, j, i) / c0.hx[2] + PR(vi[2], km, jm, im) / cm.hx[2]) * fc[2];
+}
+/* Heat flux through the lower face of cell (k,j,i) in direction D, thermal_diffusion.hpp:62-218 */
+static double cond_face(const ao_grid *g, const ao_fluid *f, const ao_diffusion *dd,
+                        const double *prim, int D, int b, int n, int k, int j, int i) {
+  const int S = f->nspecies, nvar = 6 * S;
+  const int km = k - (D == 2), jm = j - (D == 1), im = i - (D == 0);
+  const dcell_t c0 = dcell(g, b, k, j, i), cm = dcell(g, b, km, jm, im);
+  const double dxD = g_distance(g->geom, c0.xv, cm.xv);
+  const double T = dmax(0.0, PR(5 * S + n, k, j, i) / dd->cv);
+  const double Tm = dmax(0.0, PR(5 * S + n, km, jm, im) / dd->cv);
+  const double kc = face_avg(dd->cond_avg, cond_kappa(g, f, dd, prim, b, n, k, j, i),
+                             cond_kappa(g, f, dd, prim, b, n, km, jm, im));
+  return kc * (T - Tm) / dxD;
+}
+#undef PR
+
+/* Gas::ZeroDiffusionFlux + Gas::ViscousFlux + Gas::ThermalFlux (src/gas/gas.cpp:524-603): every
+ * face of every interior cell: x1 faces is..ie+1, x2 faces js..je+1, x3 faces ks..ke+1 */
+void ao_diffusion_flux(const ao_grid *g, const ao_fluid *gas, const double *gprim,
+                       const ao_diffusion *dd, double *dflx1, double *dflx2, double *dflx3) {
+  const int S = gas->nspecies, nv = 4 * S;
+  const int multid = (g->ndim >= 2), threed = (g->ndim == 3);
+  double *dflx[3] = {dflx1, dflx2, dflx3};
+#pragma omp parallel for collapse(3) schedule(static)
+  for (int b = 0; b < g->nb; ++b)
+    for (int k = g->ks; k <= g->ke + threed; ++k)
+      for (int j = g->js; j <= g->je + multid; ++j)
+        for (int i = g->is; i <= g->ie + 1; ++i)
+          for (int D = 0; D < g->ndim; ++D) {
+            /* the face must bound an interior cell in the two transverse directions */
+            if (D != 0 && i > g->ie) continue;
+            if (D != 1 && j > g->je) continue;
+            if (D != 2 && k > g->ke) continue;
+            for (int n = 0; n < S; ++n) {
+              double o[4] = {0.0, 0.0, 0.0, 0.0}, acc[4] = {0.0, 0.0, 0.0, 0.0};
+              if (dd->visc_type != AO_DIFF_NONE) {
+                visc_face(g, gas, dd, gprim, D, b, n, k, j, i, o);
+                for (int m = 0; m < 4; ++m) acc[m] += o[m];
+              }
+              if (dd->cond_type != AO_COND_NONE)
+                acc[3] += cond_face(g, gas, dd, gprim, D, b, n, k, j, i);
+              dflx[D][FIDX(g, nv, b, 3 * n + 0, k, j, i)] = acc[0];
+              dflx[D][FIDX(g, nv, b, 3 * n + 1, k, j, i)] = acc[1];
+              dflx[D][FIDX(g, nv, b, 3 * n + 2, k, j, i)] = acc[2];
+              dflx[D][FIDX(g, nv, b, 3 * S + n, k, j, i)] = acc[3];
+            }
+          }
+}
+
+/* Diffusion::DiffusionUpdateImpl, diffusion.hpp:113-242 */
+void ao_diffusion_update(const ao_grid *g, const ao_fluid *gas, const double *gprim, double *gcons,
+                         const ao_diffusion *dd, const double *dflx1, const double *dflx2,
+                         const double *dflx3, double dt) {
+  const int S = gas->nspecies, nv = 4 * S, nvar = 6 * S, geom = g->geom;
+  const int multi_d = (g->ndim > 1), three_d = (g->ndim > 2);
+  const int do_viscosity = dd->visc_type != AO_DIFF_NONE;
+  const int x1dep = g_x1dep(geom), x2dep = g_x2dep(geom) && multi_d, x3dep = 0;
+  const double *F1 = dflx1, *F2 = multi_d ? dflx2 : dflx1, *F3 = three_d ? dflx3 : dflx1;
+#pragma omp parallel for collapse(3) schedule(static)
+  for (int b = 0; b < g->nb; ++b)
+    for (int k = g->ks; k <= g->ke; ++k)
+      for (int j = g->js; j <= g->je; ++j)
+        for (int i = g->is; i <= g->ie; ++i) {
+          const bbox_t bb = make_bbox(g->xmin + 3 * b, g->dx + 3 * b, k, j, i);
+          const double ax1[2] = {g_area1(geom, &bb, bb.x1[0]), g_area1(geom, &bb, bb.x1[1])};
+          const double ax2[2] = {multi_d ? g_area2(geom, &bb, bb.x2[0]) : 0.0,
+                                 multi_d ? g_area2(geom, &bb, bb.x2[1]) : 0.0};
+          const double ax3[2] = {three_d ? g_area3(geom, &bb, bb.x3[0]) : 0.0,
+                                 three_d ? g_area3(geom, &bb, bb.x3[1]) : 0.0};
+          double dhdx1[3] = {0, 0, 0}, dhdx2[3] = {0, 0, 0}, dhdx3[3] = {0, 0, 0};
+          if (x1dep) g_conn1(geom, &bb, dhdx1);
+          if (x2dep) g_conn2(geom, &bb, dhdx2);
+          const double hx[3] = {g_hx1v(geom, &bb), g_hx2v(geom, &bb), g_hx3v(geom, &bb)};
+          const double vol = g_volume(geom, &bb);
+#define F(A, v, kk, jj, ii) A[FIDX(g, nv, b, (v), (kk), (jj), (ii))]
+          for (int n = 0; n < S; ++n) {
+            const int m1 = 3 * n, m2 = 3 * n + 1, m3 = 3 * n + 2, ien = 3 * S + n;
+            double divfxm = 0., divfym = 0., divfzm = 0.;
+            if (do_viscosity) {
+              const double s1 = 0.5 * (F(F1, m1, k, j, i) + F(F1, m1, k, j, i + 1));
+              const double s2 = 0.5 * (F(F2, m2, k, j, i) + F(F2, m2, k, j + multi_d, i));
+              const double s3 = 0.5 * (F(F3, m3, k, j, i) + F(F3, m3, k + three_d, j, i));
+              divfxm = (ax1[0] * F(F1, m1, k, j, i) - ax1[1] * F(F1, m1, k, j, i + 1)) +
+                       multi_d * (ax2[0] * F(F2, m1, k, j, i) - ax2[1] * F(F2, m1, k, j + multi_d, i)) +
+                       three_d * (ax3[0] * F(F3, m1, k, j, i) - ax3[1] * F(F3, m1, k + three_d, j, i));
+              divfxm /= vol;
+              double src = dhdx1[0] * s1 + multi_d * dhdx1[1] * s2 + three_d * dhdx1[2] * s3;
+              divfxm += x1dep * src;
+              divfym = (ax1[0] * F(F1, m2, k, j, i) - ax1[1] * F(F1, m2, k, j, i + 1)) +
+                       multi_d * (ax2[0] * F(F2, m2, k, j, i) - ax2[1] * F(F2, m2, k, j + multi_d, i)) +
+                       three_d * (ax3[0] * F(F3, m2, k, j, i) - ax3[1] * F(F3, m2, k + three_d, j, i));
+              divfym /= vol;
+              src = dhdx2[0] * s1 + multi_d * dhdx2[1] * s2 + three_d * dhdx2[2] * s3;
+              divfym += x2dep * src;
+              divfzm = (ax1[0] * F(F1, m3, k, j, i) - ax1[1] * F(F1, m3, k, j, i + 1)) +
+                       multi_d * (ax2[0] * F(F2, m3, k, j, i) - ax2[1] * F(F2, m3, k, j + multi_d, i)) +
+                       three_d * (ax3[0] * F(F3, m3, k, j, i) - ax3[1] * F(F3, m3, k + three_d, j, i));
+              divfzm /= vol;
+              src = dhdx3[0] * s1 + multi_d * dhdx3[1] * s2 + three_d * dhdx3[2] * s3;
+              divfzm += x3dep * src;
+            }
+            double divfe = (ax1[0] * F(F1, ien, k, j, i) - ax1[1] * F(F1, ien, k, j, i + 1)) +
+                           multi_d * (ax2[0] * F(F2, ien, k, j, i) - ax2[1] * F(F2, ien, k, j + multi_d, i)) +
+                           three_d * (ax3[0] * F(F3, ien, k, j, i) - ax3[1] * F(F3, ien, k + three_d, j, i));
+            divfe /= vol;
+            gcons[IDX(g, nvar, b, S + 3 * n + 0, k, j, i)] -= dt * divfxm;
+            gcons[IDX(g, nvar, b, S + 3 * n + 1, k, j, i)] -= dt * divfym;
+            gcons[IDX(g, nvar, b, S + 3 * n + 2, k, j, i)] -= dt * divfzm;
+            gcons[IDX(g, nvar, b, 4 * S + n, k, j, i)] -= dt * divfe;
+            gcons[IDX(g, nvar, b, 5 * S + n, k, j, i)] -=
+                dt * divfe - dt * (divfxm * gprim[IDX(g, nvar, b, S + 3 * n + 0, k, j, i)] / hx[0] +
+                                   divfym * gprim[IDX(g, nvar, b, S + 3 * n + 1, k, j, i)] / hx[1] +
+                                   divfzm * gprim[IDX(g, nvar, b, S + 3 * n + 2, k, j, i)] / hx[2]);
+          }
+#undef F
+        }
+}
+
+/* Diffusion::EstimateTimestep for the configured viscosity / conduction, min of the two
+ * (diffusion.hpp:64-111, src/gas/gas.cpp:437-464) */
+double ao_diffusion_dt(const ao_grid *g, const ao_fluid *gas, const double *gprim,
+                       const ao_diffusion *dd) {
+  const int S = gas->nspecies, nvar = 6 * S;
+  const double big = 1.79769313486231570815e+308;
+  double dtv = big, dtc = big;
+#pragma omp parallel for collapse(2) schedule(static) reduction(min : dtv) reduction(min : dtc)
+  for (int b = 0; b < g->nb; ++b)
+    for (int k = g->ks; k <= g->ke; ++k)
+      for (int j = g->js; j <= g->je; ++j)
+        for (int i = g->is; i <= g->ie; ++i) {
+          const bbox_t bb = make_bbox(g->xmin + 3 * b, g->dx + 3 * b, k, j, i);
+          double dx[3];
+          g_cell_widths(g->geom, &bb, dx);
+          double min_dx = big;
+          for (int d = 0; d < g->ndim; d++) min_dx = dmin(min_dx, dx[d]);
+          for (int n = 0; n < S; ++n) {
+            const double dens = gprim[IDX(g, nvar, b, n, k, j, i)];
+            if (dd->visc_type != AO_DIFF_NONE) {
+              double mu = visc_mu(g, gas, dd, gprim, b, n, k, j, i);
+              mu *= (1.0 + (dd->eta > 1.0) * (dd->eta - 1.0)) / dens;
+              dtv = dmin(dtv, min_dx * min_dx / (mu + AO_FUZZ));
+            }
+            if (dd->cond_type != AO_COND_NONE) {
+              double mu = cond_kappa(g, gas, dd, gprim, b, n, k, j, i);
+              if (dd->cond_type == AO_COND_CONDUCTIVITY) mu /= (dens * dd->cv);
+              dtc = dmin(dtc, min_dx * min_dx / (mu + AO_FUZZ));
+            }
+          }
+        }
+  if (dd->visc_type != AO_DIFF_NONE) dtv = dtv / (2.0 * g->ndim);
+  if (dd->cond_type != AO_COND_NONE) dtc = dtc / (2.0 * g->ndim);
+  return dmin(dtv, dtc);
+}
+
 /* RotatingFrame::ShearingBoxImpl, src/rotating_frame/rotating_frame_impl.hpp:28-94
  * (Cartesian only: Coriolis + tidal potential differenced across the cell) */
 void ao_shearing_box(const ao_grid *g, const ao_fluid *gas, const double *gprim, double *gcons,

@@ -152,6 +152,32 @@ void ao_rotating_frame(const ao_grid *g, const ao_fluid *gas, double *gcons,
 void ao_drag_simple(const ao_grid *g, const ao_fluid *gas, double *gcons, const ao_fluid *dust,
                     double *dcons, double dt, const double *tau);
 
+/* ---- diffusion operators: src/utils/diffusion/{diffusion,diffusion_coeff,
+ * momentum_diffusion,thermal_diffusion}.hpp driven by Gas::{ZeroDiffusionFlux,ViscousFlux,
+ * ThermalFlux,DiffusionUpdate} (src/gas/gas.cpp:524-642) and the diffusive timestep limits of
+ * Gas::EstimateTimestepMesh (src/gas/gas.cpp:437-467). */
+enum { AO_DIFF_NONE = 0, AO_VISC_PLAW = 1, AO_VISC_ALPHA = 2 };
+enum { AO_COND_NONE = 0, AO_COND_CONDUCTIVITY = 1, AO_COND_DIFFUSIVITY = 2 };
+enum { AO_AVG_ARITHMETIC = 0, AO_AVG_HARMONIC = 1 };
+typedef struct {
+  int visc_type, visc_avg;           /* DiffCoeffParams of <gas/viscosity>            */
+  double nu, eta, r0, r_exp;         /*   plaw: nu_s, eta_bulk, problem/r0, r_exp      */
+  double alpha, omega0;              /*   alpha: alpha, Omega0 = sqrt(gm / r0^3)       */
+  int cond_type, cond_avg;           /* DiffCoeffParams of <gas/conductivity>         */
+  double cond, kappa, temp_exp, rho_exp, rho_ref, t_ref;
+  double cv;                         /* specific heat of the ideal-gas EOS            */
+} ao_diffusion;
+/* diffusion flux slabs: dflx{1,2,3} = [nb][4S][fnk][fnj][fni] face arrays (gas.diff.momentum 3S
+ * entries then gas.diff.energy S entries, Metadata::Face: src/gas/gas.cpp:277-285) */
+void ao_diffusion_flux(const ao_grid *g, const ao_fluid *gas, const double *gprim,
+                       const ao_diffusion *dd, double *dflx1, double *dflx2, double *dflx3);
+void ao_diffusion_update(const ao_grid *g, const ao_fluid *gas, const double *gprim, double *gcons,
+                         const ao_diffusion *dd, const double *dflx1, const double *dflx2,
+                         const double *dflx3, double dt);
+/* min(visc_dt, cond_dt) BEFORE the cfl factor (src/gas/gas.cpp:437-464) */
+double ao_diffusion_dt(const ao_grid *g, const ao_fluid *gas, const double *gprim,
+                       const ao_diffusion *dd);
+
 #ifdef __cplusplus
 }
 #endif

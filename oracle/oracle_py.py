@@ -100,6 +100,48 @@ class FluidState:
         self.vec_dir = [((v - S) % 3 + 1) if S <= v < 4 * S else 0 for v in self.ghost_vars]
 
 
+class Diffusion(C.Structure):
+    """ao_diffusion (artemis_oracle.h): viscosity / conduction parameters of the gas."""
+    _fields_ = [("visc_type", C.c_int), ("visc_avg", C.c_int), ("nu", C.c_double),
+                ("eta", C.c_double), ("r0", C.c_double), ("r_exp", C.c_double),
+                ("alpha", C.c_double), ("omega0", C.c_double), ("cond_type", C.c_int),
+                ("cond_avg", C.c_int), ("cond", C.c_double), ("kappa", C.c_double),
+                ("temp_exp", C.c_double), ("rho_exp", C.c_double), ("rho_ref", C.c_double),
+                ("t_ref", C.c_double), ("cv", C.c_double)]
+
+
+def make_diffusion(visc=None, cond=None, cv=1.0, r0=1.0, gm=1.0):
+    """visc: ("constant"|"powerlaw", nu[, r_exp[, eta_bulk]]) | ("alpha", alpha[, eta_bulk]);
+    cond: ("conductivity", cond[, temp_exp[, rho_exp]]) | ("diffusivity", kappa[, temp_exp[,
+    rho_exp]]); optional trailing "harmonic" selects the face average (diffusion_coeff.hpp:84-140)."""
+    d = Diffusion()
+    d.cv, d.r0, d.rho_ref, d.t_ref = cv, r0, 1.0, 1.0
+    if visc is not None:
+        v = list(visc)
+        if v[-1] in ("harmonic", "arithmetic"):
+            d.visc_avg = int(v.pop() == "harmonic")
+        if v[0] == "alpha":
+            d.visc_type, d.alpha = 2, float(v[1])
+            d.eta = float(v[2]) if len(v) > 2 else 0.0
+            d.omega0 = float(np.sqrt(gm / (r0 * r0 * r0)))
+        else:
+            d.visc_type, d.nu = 1, float(v[1])
+            d.r_exp = float(v[2]) if len(v) > 2 else 0.0
+            d.eta = float(v[3]) if len(v) > 3 else 0.0
+    if cond is not None:
+        c = list(cond)
+        if c[-1] in ("harmonic", "arithmetic"):
+            d.cond_avg = int(c.pop() == "harmonic")
+        d.cond_type = 1 if c[0] == "conductivity" else 2
+        if d.cond_type == 1:
+            d.cond = float(c[1])
+        else:
+            d.kappa = float(c[1])
+        d.temp_exp = float(c[2]) if len(c) > 2 else 0.0
+        d.rho_exp = float(c[3]) if len(c) > 3 else 0.0
+    return d
+
+
 class OracleSim:
     """Mini driver: same task order as the reference, one numpy-backed MeshData."""
 
@@ -125,6 +167,41 @@ class OracleSim:
         # ("shearing_box", om0, qshear) | ("drag", [tau per dust species]) |
         # ("point_mass", gm, x, y, z, soft, sink_rate, sink) | ("rotating_frame", om0)
         self.sources = []
+        # gas diffusion (ao_diffusion, make_diffusion()); None = physics/viscosity and
+        # physics/conduction off
+        self.diffusion = None
+        self.dflx = None
+
+    def _diff_lib(self):
+        return self.L, "ao"
+
+    def DiffusionFlux(self):
+        """Gas::ZeroDiffusionFlux -> ViscousFlux -> ThermalFlux (artemis_driver.cpp:188-196)."""
+        fs = self.gas
+        if self.dflx is None:
+            m = self.mesh
+            self.dflx = [np.zeros((m.nb, 4 * fs.fp.nspecies, m.fnk, m.fnj, m.fni)) for _ in range(3)]
+        L, pre = self._diff_lib()
+        f = make_fluid(fs.fp)
+        getattr(L, pre + "_diffusion_flux")(C.byref(self.g), C.byref(f), _p(fs.prim),
+                                            C.byref(self.diffusion), *[_p(a) for a in self.dflx])
+
+    def DiffusionUpdate(self, dt):
+        """Gas::DiffusionUpdate (artemis_driver.cpp:217-221)."""
+        fs = self.gas
+        L, pre = self._diff_lib()
+        f = make_fluid(fs.fp)
+        getattr(L, pre + "_diffusion_update")(C.byref(self.g), C.byref(f), _p(fs.prim), _p(fs.u0),
+                                              C.byref(self.diffusion), *[_p(a) for a in self.dflx],
+                                              C.c_double(dt))
+
+    def DiffusionTimestep(self):
+        fs = self.gas
+        L, pre = self._diff_lib()
+        f = make_fluid(fs.fp)
+        fn = getattr(L, pre + "_diffusion_dt")
+        fn.restype = C.c_double
+        return fs.fp.cfl * fn(C.byref(self.g), C.byref(f), _p(fs.prim), C.byref(self.diffusion))
 
     def _both(self):
         fg = make_fluid(self.gas.fp) if self.gas is not None else None
@@ -217,6 +294,8 @@ class OracleSim:
         for fs in self.fluids:
             f = make_fluid(fs.fp)
             dts.append(self.L.ao_estimate_dt(C.byref(self.g), C.byref(f), _p(fs.prim)))
+        if self.diffusion is not None:   # cfl * min(hydro, viscous, conductive), gas.cpp:437-467
+            dts.append(self.DiffusionTimestep())
         return min(dts)
 
     # ---- Mesh::Initialize sequence after the pgen (P:mesh/mesh.cpp:783-814) -----------
@@ -244,10 +323,14 @@ class OracleSim:
         pcm = (s == 0 and self.integrator == "vl2")
         for fs in self.fluids:
             self.CalculateFluxes(fs, pcm)
+        if self.diffusion is not None:
+            self.DiffusionFlux()
         for fs in self.fluids:
             self.ApplyUpdate(fs, gam0, gam1, bdt)
         for fs in self.fluids:
             self.FluxSource(fs, bdt)
+        if self.diffusion is not None:
+            self.DiffusionUpdate(bdt)
         self.ApplySources(bdt)
         for fs in self.fluids:
             self.SetAuxillaryFields(fs)

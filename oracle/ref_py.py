@@ -49,6 +49,9 @@ class RefSim(OracleSim):
     def _src_lib(self):   # gravity + shearing box run the reference's own kernels
         return self.R, "ar"
 
+    def _diff_lib(self):  # the reference's own diffusion operators
+        return self.R, "ar"
+
     def CalculateFluxes(self, fs, pcm):
         f = make_fluid(fs.fp)
         self.R.ar_calculate_fluxes(C.byref(self.g), C.byref(f), int(pcm), _p(fs.prim),

@@ -22,6 +22,7 @@ namespace cons { SHIM_VARIABLE(gas.cons, density); SHIM_VARIABLE(gas.cons, total
 namespace prim { SHIM_VARIABLE(gas.prim, density); SHIM_VARIABLE(gas.prim, pressure);
                  SHIM_VARIABLE(gas.prim, velocity); SHIM_VARIABLE(gas.prim, sie); }
 namespace face { SHIM_VARIABLE(gas.face, velocity); }
+namespace diff { SHIM_VARIABLE(gas.diff, momentum); SHIM_VARIABLE(gas.diff, energy); }
 }  // namespace gas
 namespace dust {
 namespace cons { SHIM_VARIABLE(dust.cons, density); SHIM_VARIABLE(dust.cons, momentum); }

@@ -23,6 +23,7 @@
 #include <map>
 #include <memory>
 #include <set>
+#include <sstream>
 #include <string>
 #include <tuple>
 #include <typeindex>
@@ -44,11 +45,17 @@ using Real = double;
   std::fprintf(stderr, "### ref_shim FAIL: %s (%s:%d)\n", msg, file, line);
   std::abort();
 }
+inline void shim_fail(const std::stringstream &msg, const char *file, int line) {
+  shim_fail(msg.str().c_str(), file, line);
+}
 #define PARTHENON_FAIL(msg) shim_fail(msg, __FILE__, __LINE__)
 #define PARTHENON_REQUIRE(cond, msg)                                                       \
   do {                                                                                     \
     if (!(cond)) shim_fail(msg, __FILE__, __LINE__);                                       \
   } while (0)
+
+#define PARTHENON_DEBUG_REQUIRE(cond, msg) ((void)0)  // Release build: compiled out
+#define PARTHENON_AUTO_LABEL "shim"
 
 // loop-pattern tags (only passed through)
 struct shim_loop_tag {};
@@ -56,6 +63,11 @@ static constexpr shim_loop_tag DEFAULT_LOOP_PATTERN{}, DEFAULT_OUTER_LOOP_PATTER
     DEFAULT_INNER_LOOP_PATTERN{};
 
 namespace Kokkos {
+template <class T>
+struct Min {  // reducer handle of par_reduce
+  T &ref;
+  explicit Min(T &r) : ref(r) {}
+};
 struct MemoryUnmanaged {};
 template <class...>
 struct View {
@@ -174,6 +186,11 @@ struct Packages_t {
     if (it == pkgs.end()) shim_fail(("missing package " + n).c_str(), __FILE__, __LINE__);
     return it->second;
   }
+  const std::shared_ptr<StateDescriptor> &Get(const std::string &n) const {
+    auto it = pkgs.find(n);
+    if (it == pkgs.end()) shim_fail(("missing package " + n).c_str(), __FILE__, __LINE__);
+    return it->second;
+  }
 };
 
 class Mesh {
@@ -183,7 +200,13 @@ class Mesh {
   std::shared_ptr<StateDescriptor> resolved_packages = std::make_shared<StateDescriptor>();
 };
 
-class ParameterInput {};
+class ParameterInput {  // never consulted: the shim fills parameter structs field by field
+ public:
+  std::string GetString(const std::string &, const std::string &) { return ""; }
+  std::string GetOrAddString(const std::string &, const std::string &, const std::string &d) { return d; }
+  Real GetReal(const std::string &, const std::string &) { return 0.0; }
+  Real GetOrAddReal(const std::string &, const std::string &, Real d) { return d; }
+};
 
 template <class T>
 class MeshData {
@@ -259,6 +282,10 @@ class SparsePackShim {
   template <class V, class = decltype(V::name())>
   Real &operator()(int b, const V &v, int k, int j, int i) const {
     return (*this)(b, type_off[shim_type_id<V>()] + v.idx, k, j, i);
+  }
+  template <class V, class = decltype(V::name())>
+  Real &operator()(int b, TopologicalElement el, const V &v, int k, int j, int i) const {
+    return (*this)(b, el, type_off[shim_type_id<V>()] + v.idx, k, j, i);
   }
   template <class V, class = decltype(V::name())>
   Real &flux(int b, int dir, const V &v, int k, int j, int i) const {
@@ -350,7 +377,16 @@ class ScratchPad2D {
   int m_ = 0;
 };
 template <class T>
-class ScratchPad1D {};
+class ScratchPad1D {
+ public:
+  ScratchPad1D() = default;
+  ScratchPad1D(ScratchArena &a, int n) : p_(a.base + a.used) { a.used += (size_t)n; }
+  T &operator()(int i) const { return p_[i]; }
+  static int shmem_size(int n) { return (int)sizeof(T) * n; }
+
+ private:
+  T *p_ = nullptr;
+};
 
 template <class F>
 inline void par_for_inner(shim_loop_tag, const team_mbr_t &, int il, int iu, const F &f) {
@@ -399,6 +435,23 @@ inline void par_for(shim_loop_tag, const char *, DevExecSpace, int b0, int b1, i
     for (int k = k0; k <= k1; ++k)
       for (int j = j0; j <= j1; ++j)
         for (int i = i0; i <= i1; ++i) f(b, k, j, i);
+}
+
+// par_reduce with a Min reducer over (b, k, j, i): min is order-independent, so the OpenMP
+// reduction returns the same bits as any other traversal
+struct loop_pattern_mdrange_tag_t {};
+static constexpr loop_pattern_mdrange_tag_t loop_pattern_mdrange_tag{};
+template <class F>
+inline void par_reduce(loop_pattern_mdrange_tag_t, const char *, DevExecSpace, int b0, int b1,
+                       int k0, int k1, int j0, int j1, int i0, int i1, const F &f,
+                       Kokkos::Min<Real> red) {
+  Real m = std::numeric_limits<Real>::max();
+#pragma omp parallel for collapse(3) schedule(static) reduction(min : m)
+  for (int b = b0; b <= b1; ++b)
+    for (int k = k0; k <= k1; ++k)
+      for (int j = j0; j <= j1; ++j)
+        for (int i = i0; i <= i1; ++i) f(b, k, j, i, m);
+  red.ref = m;
 }
 
 class LowStorageIntegrator {

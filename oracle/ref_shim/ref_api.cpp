@@ -20,6 +20,10 @@
 #include "rotating_frame/rotating_frame_impl.hpp"
 #include "gravity/uniform.cpp"
 #include "gravity/point_mass.cpp"
+// diffusion operators
+#include "utils/diffusion/diffusion.hpp"
+#include "utils/diffusion/momentum_diffusion.hpp"
+#include "utils/diffusion/thermal_diffusion.hpp"
 
 #include "../artemis_oracle.h"
 
@@ -30,6 +34,7 @@ struct Ctx {
   Mesh mesh;
   MeshData<Real> md;
 };
+double g_cv = 1.0;  // specific heat handed to the EOS (only the diffusion operators read it)
 
 void SetGrid(Ctx &c, const ao_grid *g) {
   c.mesh.ndim = g->ndim;
@@ -65,7 +70,7 @@ void SetFluidPkg(Ctx &c, const ao_grid *g, const ao_fluid *f, double omf = 0.0) 
   if (f->fluid == AO_GAS) {
     pkg->AddParam<Real>("siefloor", f->siefloor);
     pkg->AddParam<Real>("de_switch", f->de_switch);
-    pkg->AddParam<EOS>("eos_d", EOS(f->gm1, 1.0));  // src/gas/gas.cpp:104-117 (cv irrelevant)
+    pkg->AddParam<EOS>("eos_d", EOS(f->gm1, g_cv));  // src/gas/gas.cpp:104-117
   }
   const bool gas = f->fluid == AO_GAS;
   c.mesh.packages.pkgs[gas ? "gas" : "dust"] = pkg;
@@ -439,5 +444,148 @@ void ar_rotating_frame(const ao_grid *g, const ao_fluid *gas, double *gcons, dou
     if constexpr (GG != Coordinates::cartesian)
       RotatingFrame::RotatingFrameImpl<GG>(&c.md, om0, gas != nullptr, dust != nullptr, dt);
   });
+}
+// ---- diffusion: the reference's own MomentumFluxImpl / ThermalFluxImpl / DiffusionUpdateImpl /
+// EstimateTimestep / ZeroDiffusionImpl; the type dispatch of Gas::ViscousFlux / ThermalFlux /
+// ZeroDiffusionFlux / DiffusionUpdate (src/gas/gas.cpp:524-642, that .cpp pulls in all of
+// Artemis) and of the timestep (src/gas/gas.cpp:437-464) is restated here.
+static void SetDiffusion(Ctx &c, const ao_grid *g, const ao_fluid *gas, double *gprim,
+                         double *gcons, const ao_diffusion *dd, double *dflx[3],
+                         Diffusion::DiffCoeffParams &vp, Diffusion::DiffCoeffParams &cp) {
+  g_cv = dd->cv;
+  SetGrid(c, g);
+  SetFluidPkg(c, g, gas);
+  g_cv = 1.0;
+  AddSlab(c, g, gas, true, gprim, nullptr, nullptr, nullptr);
+  if (gcons) AddSlab(c, g, gas, false, gcons, nullptr, nullptr, nullptr);
+  const int S = gas->nspecies;
+  const size_t fcells = (size_t)g->fni * g->fnj * g->fnk;
+  if (dflx) {
+    Field fm, fe;
+    fm.name = "gas.diff.momentum"; fm.ncomp = 3 * S;
+    fe.name = "gas.diff.energy";   fe.ncomp = S;
+    for (int d = 0; d < 3; ++d) {
+      fm.face[d] = dflx[d];
+      fe.face[d] = dflx[d] ? dflx[d] + (size_t)3 * S * fcells : nullptr;
+    }
+    fm.face_bstride = fe.face_bstride = (size_t)4 * S * fcells;
+    c.md.fields.push_back(fm);
+    c.md.fields.push_back(fe);
+  }
+  using Diffusion::DiffType;
+  using Diffusion::DiffAvg;
+  vp = Diffusion::DiffCoeffParams();
+  cp = Diffusion::DiffCoeffParams();
+  vp.type = dd->visc_type == AO_VISC_PLAW ? DiffType::viscosity_plaw
+            : dd->visc_type == AO_VISC_ALPHA ? DiffType::viscosity_alpha : DiffType::null;
+  vp.avg = dd->visc_avg == AO_AVG_HARMONIC ? DiffAvg::harmonic : DiffAvg::arithmetic;
+  vp.nu_s = dd->nu; vp.eta = dd->eta; vp.R0 = dd->r0; vp.r_exp = dd->r_exp;
+  vp.alpha = dd->alpha; vp.Omega0 = dd->omega0;
+  cp.type = dd->cond_type == AO_COND_CONDUCTIVITY ? DiffType::conductivity_plaw
+            : dd->cond_type == AO_COND_DIFFUSIVITY ? DiffType::thermaldiff_plaw : DiffType::null;
+  cp.avg = dd->cond_avg == AO_AVG_HARMONIC ? DiffAvg::harmonic : DiffAvg::arithmetic;
+  cp.hcond_0 = dd->cond; cp.kappa_0 = dd->kappa; cp.temp_exp = dd->temp_exp;
+  cp.rho_exp = dd->rho_exp; cp.d0 = dd->rho_ref; cp.T0 = dd->t_ref;
+}
+
+void ar_diffusion_flux(const ao_grid *g, const ao_fluid *gas, double *gprim,
+                       const ao_diffusion *dd, double *dflx1, double *dflx2, double *dflx3) {
+  Ctx c;
+  double *dflx[3] = {dflx1, dflx2, dflx3};
+  Diffusion::DiffCoeffParams vp, cp;
+  SetDiffusion(c, g, gas, gprim, nullptr, dd, dflx, vp, cp);
+  MeshData<Real> *md = &c.md;
+  auto pm = md->GetParentPointer();
+  auto &pkg = pm->packages.Get("gas");
+  auto &resolved_pkgs = pm->resolved_packages;
+  using Diffusion::DiffType;
+  GeomDispatch(g->geom, [&](auto G) {
+    constexpr Coordinates GG = decltype(G)::value;
+    {  // Gas::ZeroDiffusionFlux, src/gas/gas.cpp:592-603
+      auto desc_flux = parthenon::MakePackDescriptor<gas::diff::momentum, gas::diff::energy>(
+          resolved_pkgs.get(), {}, {parthenon::PDOpt::WithFluxes});
+      auto vf = desc_flux.GetPack(md);
+      Diffusion::ZeroDiffusionImpl(md, vf);
+    }
+    if (vp.type != DiffType::null) {  // Gas::ViscousFlux, src/gas/gas.cpp:524-556
+      auto desc_prim = parthenon::MakePackDescriptor<gas::prim::density, gas::prim::velocity,
+                                                     gas::prim::sie>(resolved_pkgs.get());
+      auto desc_flux = parthenon::MakePackDescriptor<gas::diff::momentum, gas::diff::energy>(
+          resolved_pkgs.get(), {}, {parthenon::PDOpt::WithFluxes});
+      auto vprim = desc_prim.GetPack(md);
+      auto vf = desc_flux.GetPack(md);
+      if (vp.type == DiffType::viscosity_plaw)
+        Diffusion::MomentumFluxImpl<GG, Fluid::gas, DiffType::viscosity_plaw>(md, vp, pkg, vprim, vf);
+      else
+        Diffusion::MomentumFluxImpl<GG, Fluid::gas, DiffType::viscosity_alpha>(md, vp, pkg, vprim, vf);
+    }
+    if (cp.type != DiffType::null) {  // Gas::ThermalFlux, src/gas/gas.cpp:561-587
+      auto desc_prim = parthenon::MakePackDescriptor<gas::prim::density, gas::prim::sie>(
+          resolved_pkgs.get());
+      auto desc_flux = parthenon::MakePackDescriptor<gas::diff::energy>(
+          resolved_pkgs.get(), {}, {parthenon::PDOpt::WithFluxes});
+      auto vprim = desc_prim.GetPack(md);
+      auto vf = desc_flux.GetPack(md);
+      if (cp.type == DiffType::conductivity_plaw)
+        Diffusion::ThermalFluxImpl<GG, Fluid::gas, DiffType::conductivity_plaw>(md, cp, pkg, vprim, vf);
+      else
+        Diffusion::ThermalFluxImpl<GG, Fluid::gas, DiffType::thermaldiff_plaw>(md, cp, pkg, vprim, vf);
+    }
+  });
+}
+
+void ar_diffusion_update(const ao_grid *g, const ao_fluid *gas, double *gprim, double *gcons,
+                         const ao_diffusion *dd, double *dflx1, double *dflx2, double *dflx3,
+                         double dt) {  // Gas::DiffusionUpdate, src/gas/gas.cpp:608-642
+  Ctx c;
+  double *dflx[3] = {dflx1, dflx2, dflx3};
+  Diffusion::DiffCoeffParams vp, cp;
+  SetDiffusion(c, g, gas, gprim, gcons, dd, dflx, vp, cp);
+  MeshData<Real> *md = &c.md;
+  auto pm = md->GetParentPointer();
+  auto &pkg = pm->packages.Get("gas");
+  auto &resolved_pkgs = pm->resolved_packages;
+  const bool do_viscosity = vp.type != Diffusion::DiffType::null;
+  GeomDispatch(g->geom, [&](auto G) {
+    constexpr Coordinates GG = decltype(G)::value;
+    auto desc_cons = parthenon::MakePackDescriptor<gas::cons::momentum, gas::cons::total_energy,
+                                                   gas::cons::internal_energy>(resolved_pkgs.get());
+    auto desc_prim = parthenon::MakePackDescriptor<gas::prim::velocity>(resolved_pkgs.get());
+    auto desc_flux = parthenon::MakePackDescriptor<gas::diff::momentum, gas::diff::energy>(
+        resolved_pkgs.get(), {}, {parthenon::PDOpt::WithFluxes});
+    auto vcons = desc_cons.GetPack(md);
+    auto vprim = desc_prim.GetPack(md);
+    auto vf = desc_flux.GetPack(md);
+    Diffusion::DiffusionUpdateImpl<GG, Fluid::gas>(md, pkg, vcons, vprim, vf, do_viscosity, dt);
+  });
+}
+
+double ar_diffusion_dt(const ao_grid *g, const ao_fluid *gas, double *gprim,
+                       const ao_diffusion *dd) {  // src/gas/gas.cpp:437-464
+  Ctx c;
+  Diffusion::DiffCoeffParams vp, cp;
+  SetDiffusion(c, g, gas, gprim, nullptr, dd, nullptr, vp, cp);
+  MeshData<Real> *md = &c.md;
+  auto pm = md->GetParentPointer();
+  auto &gas_pkg = pm->packages.Get("gas");
+  auto &resolved_pkgs = pm->resolved_packages;
+  auto eos_d = gas_pkg->Param<EOS>("eos_d");
+  using Diffusion::DiffType;
+  Real visc_dt = Big<Real>(), cond_dt = Big<Real>();
+  GeomDispatch(g->geom, [&](auto G) {
+    constexpr Coordinates GG = decltype(G)::value;
+    auto desc = parthenon::MakePackDescriptor<gas::prim::density, gas::prim::velocity,
+                                              gas::prim::sie>(resolved_pkgs.get());
+    auto vmesh = desc.GetPack(md);
+    if (vp.type == DiffType::viscosity_plaw)
+      visc_dt = Diffusion::EstimateTimestep<GG, Fluid::gas, DiffType::viscosity_plaw>(md, vp, gas_pkg, eos_d, vmesh);
+    else if (vp.type == DiffType::viscosity_alpha)
+      visc_dt = Diffusion::EstimateTimestep<GG, Fluid::gas, DiffType::viscosity_alpha>(md, vp, gas_pkg, eos_d, vmesh);
+    if (cp.type == DiffType::conductivity_plaw)
+      cond_dt = Diffusion::EstimateTimestep<GG, Fluid::gas, DiffType::conductivity_plaw>(md, cp, gas_pkg, eos_d, vmesh);
+    else if (cp.type == DiffType::thermaldiff_plaw)
+      cond_dt = Diffusion::EstimateTimestep<GG, Fluid::gas, DiffType::thermaldiff_plaw>(md, cp, gas_pkg, eos_d, vmesh);
+  });
+  return std::min(visc_dt, cond_dt);
 }
 }  // extern "C"
