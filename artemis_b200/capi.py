@@ -45,6 +45,16 @@ class PointMassDesc(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("gm", "x", "y", "z", "soft", "sink_rate", "sink")]
 
 
+class DiffusionDesc(C.Structure):
+    """ab200_diffusion_desc"""
+    _fields_ = [("visc_type", C.c_int), ("visc_avg", C.c_int), ("nu", C.c_double),
+                ("eta_bulk", C.c_double), ("r0", C.c_double), ("r_exp", C.c_double),
+                ("alpha", C.c_double), ("omega0", C.c_double), ("cond_type", C.c_int),
+                ("cond_avg", C.c_int), ("cond", C.c_double), ("kappa", C.c_double),
+                ("temp_exp", C.c_double), ("rho_exp", C.c_double), ("rho_ref", C.c_double),
+                ("t_ref", C.c_double), ("cv", C.c_double)]
+
+
 class SourcesDesc(C.Structure):
     """ab200_sources_desc"""
     _fields_ = [("gravity", C.c_int), ("g", C.c_double * 3), ("shearing_box", C.c_int),
@@ -75,6 +85,8 @@ SYMBOLS = [
     "ab200_launch_count", "ab200_timer_begin", "ab200_timer_end",
     "ab200_history_volume_integrals", "ab200_configure_sources", "ab200_finish_stage", "ab200_uniform_gravity", "ab200_shearing_box", "ab200_drag_simple",
     "ab200_point_mass_gravity", "ab200_rotating_frame",
+    "ab200_configure_diffusion", "ab200_diffusion_flux", "ab200_diffusion_update",
+    "ab200_diffusion_timestep", "ab200_diffusion_flux_array",
     "ab200_comm_unique_id", "ab200_comm_init", "ab200_comm_destroy", "ab200_comm_set_layout",
     "ab200_comm_bytes_per_exchange", "ab200_comm_is_direct", "ab200_comm_exchange_begin", "ab200_comm_exchange_end",
     "ab200_allreduce_min", "ab200_run_cycles_mr", "ab200_comm_plan_direct", "ab200_comm_plan_free",
@@ -142,6 +154,9 @@ def load(variant: str | None = None) -> C.CDLL:
         "ab200_shearing_box": [vp, d, d, d], "ab200_drag_simple": [vp, d, i, _DP],
         "ab200_point_mass_gravity": [vp, d, C.POINTER(PointMassDesc)],
         "ab200_rotating_frame": [vp, d, d],
+        "ab200_configure_diffusion": [vp, C.POINTER(DiffusionDesc)], "ab200_diffusion_flux": [vp],
+        "ab200_diffusion_update": [vp, d], "ab200_diffusion_timestep": [vp, _DP],
+        "ab200_diffusion_flux_array": [vp, i, C.POINTER(_DP), C.POINTER(C.c_size_t)],
         "ab200_comm_unique_id": [C.c_char_p], "ab200_comm_init": [vp, i, i, C.c_char_p],
         "ab200_comm_destroy": [vp], "ab200_comm_set_layout": [vp, i, i, i, C.POINTER(C.c_int)],
         "ab200_comm_is_direct": [vp], "ab200_comm_exchange_begin": [vp], "ab200_comm_exchange_end": [vp],

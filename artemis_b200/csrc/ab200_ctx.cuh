@@ -122,6 +122,11 @@ struct ab200_ctx {
   // source terms applied by the device-resident drivers (ab200_configure_sources)
   ab200_sources_desc sources{};
   bool has_sources = false;
+  // gas diffusion (ab200_configure_diffusion): parameters + library-owned face flux arrays
+  ab200_diffusion_desc diffusion{};
+  bool has_diffusion = false;
+  double *d_dflx[3] = {nullptr, nullptr, nullptr};
+  size_t dflx_elems = 0;
   // multi-rank transport (comm.cu): NCCL communicator, comm stream, planned exchange
   void *comm_state = nullptr;
 };
@@ -197,6 +202,10 @@ int run_stage(ab200_ctx *c, double g0, double g1, double beta, int pcm, int firs
 int launch_halo(ab200_ctx *c, const ab200_bnd_desc *bnd, int n, int unpack);
 int launch_set_global_dt(ab200_ctx *c, double tlim, int advance_time);
 int ensure_scratch(ab200_ctx *c, int fluid, bool need_flux, bool need_u1);
+// diffusion.cu
+int launch_diffusion_flux(ab200_ctx *c);
+int launch_diffusion_update(ab200_ctx *c, double dt, const double *dt_dev, double beta);
+int launch_diffusion_dt(ab200_ctx *c, double *d_out, int combine);
 // density-flux tap tables of the fused passes (FluidDev::dflux), allocated on first use
 int ensure_dflux(ab200_ctx *c, int fluid);
 int build_geom_tables_for(ab200_ctx *c, GeomTab &t, int geom, int nb, int ni, int nj, int nk,

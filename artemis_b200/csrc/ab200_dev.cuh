@@ -316,6 +316,27 @@ struct Coords {
       xcyl0 = a;
     }
   }
+  // cylindrical radius of the centroid = ConvertToCyl(xv)[0] (geometry.hpp:284-291 for Cartesian)
+  AB_D double cyl_radius() const {
+    const double a = x1v();
+    if (GEOM == AB200_CARTESIAN) { const double y = x2v(); return sqrt(a * a + y * y); }
+    if (sph23) return a * sinv();
+    if (GEOM == AB200_SPHERICAL1D) return a * 1.0;
+    return a;
+  }
+  // spherical radius of the centroid = ConvertToSph(xv)[0] (geometry.hpp:262-269,
+  // cylindrical.hpp:110-115, axisymmetric.hpp:115-120)
+  AB_D double sph_radius() const {
+    const double a = x1v();
+    if (GEOM == AB200_CARTESIAN) {
+      const double y = x2v(), z = x3v();
+      const double R = sqrt(a * a + y * y);
+      return sqrt(R * R + z * z);
+    }
+    if (GEOM == AB200_CYLINDRICAL) { const double z = x3v(); return sqrt(a * a + z * z); }
+    if (GEOM == AB200_AXISYMMETRIC) { const double z = x2v(); return sqrt(a * a + z * z); }
+    return a;
+  }
   // RFWeights: +-(<R^2>_face - <R^2>) of the cylindrical radius (cylindrical.hpp:88-93,
   // axisymmetric.hpp:91-96, spherical.hpp:148-169 / 352-373 / 514-525)
   AB_D void rf_weights(double bx[3][2]) const {

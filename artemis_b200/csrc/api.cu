@@ -230,6 +230,8 @@ int ab200_destroy(ab200_ctx *c) {
   clear_descriptor_cache(c);
   for (int q = 0; q < 2; ++q)
     if (c->d_blist[q]) cudaFree(c->d_blist[q]);
+  for (int q = 0; q < 3; ++q)
+    if (c->d_dflx[q]) cudaFree(c->d_dflx[q]);
   if (c->d_time) cudaFree(c->d_time);
   if (c->d_red) cudaFree(c->d_red);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -607,11 +609,14 @@ int ab200_fused_stage(ab200_ctx *c, double gam0, double gam1, double beta, doubl
                                 fold ? slots + f : nullptr, defer, subset, tap));
     }
     if (reduce_dt && subset != 1) {  // new_dt = min over fluids of cfl * min dt  (EstimateTimestepMesh)
-      if (fold)
+      if (fold) {
         AB_TRY(launch_finish_dt(c, reinterpret_cast<const double *>(slots + f), 1, c->fl[f].d.cfl,
                                 c->d_time + 1, any));
-      else
+        // Gas::EstimateTimestepMesh also applies the diffusive limits (gas.cpp:437-467)
+        if (f == AB200_GAS && c->has_diffusion) AB_TRY(launch_diffusion_dt(c, c->d_time + 1, 1));
+      } else {
         AB_TRY(launch_estimate_dt(c, f, c->d_time + 1, any));
+      }
     }
     any = 1;
   }
@@ -637,9 +642,11 @@ int ab200_finish_stage(ab200_ctx *c, int flags) {
     AB_TRY(sync_prim_home(c, f, 0));
     // one pointwise kernel per fluid: SetAux + C2P + interior P2C (+ CFL minimum)
     AB_TRY(launch_finish_stage(c, f, reduce_dt ? slots + f : nullptr));
-    if (reduce_dt)
+    if (reduce_dt) {
       AB_TRY(launch_finish_dt(c, reinterpret_cast<const double *>(slots + f), 1, c->fl[f].d.cfl,
                               c->d_time + 1, any));
+      if (f == AB200_GAS && c->has_diffusion) AB_TRY(launch_diffusion_dt(c, c->d_time + 1, 1));
+    }
     any = 1;
   }
   AB_REQUIRE(any, AB200_ESTATE, "ab200_finish_stage: no fluid bound");

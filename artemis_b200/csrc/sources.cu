@@ -595,13 +595,16 @@ namespace ab200 {
 // (src/artemis_driver.cpp:184-255): dt comes from the device scalar.
 int run_stage(ab200_ctx *c, double g0, double g1, double beta, int pcm, int first, int last) {
   const int base = AB200_STAGE_DEVICE_DT | AB200_STAGE_PINGPONG;
-  if (!c->has_sources)
+  if (!c->has_sources && !c->has_diffusion)
     return ab200_fused_stage(c, g0, g1, beta, 0.0, pcm, first, base | (last ? AB200_STAGE_REDUCE_DT : 0));
   const ab200_sources_desc &s = c->sources;
+  // diffusion fluxes come from the stage-start primitives, which the deferred stage leaves alone
+  if (c->has_diffusion) AB_TRY(launch_diffusion_flux(c));
   AB_TRY(ab200_fused_stage(c, g0, g1, beta, 0.0, pcm, first,
                            base | AB200_STAGE_DEFER_C2P |
                                (s.rotating_frame ? AB200_STAGE_TAP_DFLUX : 0)));
   // beta * dt is formed on the device from the dt scalar: no host round trip
+  if (c->has_diffusion) AB_TRY(launch_diffusion_update(c, 0.0, c->d_time, beta));
   if (s.gravity) AB_TRY(gravity_impl(c, 0.0, c->d_time, beta, s.g[0], s.g[1], s.g[2]));
   if (s.point_mass) AB_TRY(point_mass_impl(c, 0.0, c->d_time, beta, &s.pm));
   if (s.shearing_box) AB_TRY(shearing_impl(c, 0.0, c->d_time, beta, s.omega, s.qshear));

@@ -196,6 +196,9 @@ int launch_estimate_dt(ab200_ctx *c, int fluid, double *d_out, int combine) {
   k_finish_dt<<<1, 256, 0, c->stream>>>(partial, grid, f.cfl, d_out, combine);
   c->launches += 2;
   AB_CUDA(cudaGetLastError());
+  // Gas::EstimateTimestepMesh: cfl * min(hydro, viscous, conductive) (gas.cpp:437-467)
+  if (rc == AB200_OK && fluid == AB200_GAS && c->has_diffusion)
+    rc = launch_diffusion_dt(c, d_out, 1);
   return rc;
 }
 

@@ -132,8 +132,13 @@ class ArtemisDriver:
     """
 
     def __init__(self, md: MeshData, integrator: str = "rk2", mode: str = "tasks",
-                 tlim: float = np.inf, nlim: int = -1, comm=None, sources=()):
+                 tlim: float = np.inf, nlim: int = -1, comm=None, sources=(), diffusion=None):
         self.md = md
+        # gas diffusion (physics/viscosity, physics/conduction): a capi.DiffusionDesc; the
+        # operators run every stage as in src/artemis_driver.cpp:188-196, 217-221
+        self.diffusion = diffusion
+        if diffusion is not None:
+            md.call("ab200_configure_diffusion", C.byref(diffusion))
         # pointwise source terms between FluxSource and SetAuxillaryFields
         # (src/artemis_driver.cpp:217-248): ("gravity", gx1, gx2, gx3) |
         # ("shearing_box", omega, qshear) | ("drag", [tau per dust species])
@@ -222,11 +227,15 @@ class ArtemisDriver:
                     req(Gas.CalculateFluxes(md, do_pcm), md, "Gas::CalculateFluxes")
                 if self.do_dust:
                     req(Dust.CalculateFluxes(md, do_pcm), md, "Dust::CalculateFluxes")
+                if self.diffusion is not None:
+                    req(_task(md, "ab200_diffusion_flux"), md, "Gas::ViscousFlux/ThermalFlux")
                 req(ArtemisUtils.ApplyUpdate(md, stage, integ), md, "ApplyUpdate")
                 if self.do_gas:
                     req(Gas.FluxSource(md, bdt), md, "Gas::FluxSource")
                 if self.do_dust:
                     req(Dust.FluxSource(md, bdt), md, "Dust::FluxSource")
+                if self.diffusion is not None:
+                    req(_task(md, "ab200_diffusion_update", float(bdt)), md, "Gas::DiffusionUpdate")
                 self.ApplySources(bdt)
                 req(ArtemisDerived.SetAuxillaryFields(md), md, "SetAuxillaryFields")
                 req(ArtemisDerived.ConsToPrim(md), md, "ConsToPrim")
@@ -235,13 +244,17 @@ class ArtemisDriver:
             else:
                 # with source terms the conserved state must exist between the update and C2P:
                 # the fused passes stop after FluxSource (AB200_STAGE_DEFER_C2P = 8)
-                defer = 8 if self.sources else 0
+                defer = 8 if (self.sources or self.diffusion is not None) else 0
                 if any(src[0] == "rotating_frame" for src in self.sources):
                     defer |= 64   # AB200_STAGE_TAP_DFLUX: the passes keep their mass fluxes
                 req(_task(md, "ab200_fused_stage", integ.gam0[stage - 1], integ.gam1[stage - 1],
                           integ.beta[stage - 1], integ.dt, int(do_pcm), int(stage == 1), defer),
                     md, "ab200_fused_stage")
                 if defer:
+                    if self.diffusion is not None:   # stage-start primitives are still in place
+                        req(_task(md, "ab200_diffusion_flux"), md, "Gas::ViscousFlux/ThermalFlux")
+                        req(_task(md, "ab200_diffusion_update", float(bdt)), md,
+                            "Gas::DiffusionUpdate")
                     self.ApplySources(bdt)
                     req(_task(md, "ab200_finish_stage", 0), md, "ab200_finish_stage")
                 req(AddBoundaryExchangeTasks(md, self.comm), md, "AddBoundaryExchangeTasks")

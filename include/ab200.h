@@ -234,6 +234,50 @@ typedef struct ab200_sources_desc {
 } ab200_sources_desc;
 int ab200_configure_sources(ab200_ctx *ctx, const ab200_sources_desc *src);
 
+/* ---- diffusion operators of the gas -------------------------------------------
+ * Viscous stress (constant / power-law / alpha viscosity, bulk viscosity) and heat conduction
+ * (power-law conductivity or thermal diffusivity) of src/utils/diffusion/{diffusion_coeff,
+ * momentum_diffusion,thermal_diffusion,diffusion}.hpp, as the reference's driver applies them
+ * every stage (src/artemis_driver.cpp:188-196, 217-221):
+ *   ab200_diffusion_flux      Gas::ZeroDiffusionFlux + Gas::ViscousFlux + Gas::ThermalFlux
+ *                             (src/gas/gas.cpp:524-603) in ONE kernel: the fluxes of
+ *                             gas.diff.momentum / gas.diff.energy through every face of the
+ *                             interior zones from the current primitives (ghost zones valid to
+ *                             depth 2), into library-owned face arrays
+ *   ab200_diffusion_update    Gas::DiffusionUpdate (src/gas/gas.cpp:608-642): momentum, total and
+ *                             internal energy of the interior zones -= dt * div(flux) (+ the
+ *                             curvilinear stress source terms)
+ *   ab200_diffusion_timestep  cfl * min(viscous, conductive limit), the diffusive part of
+ *                             Gas::EstimateTimestepMesh (src/gas/gas.cpp:437-467)
+ * Once configured, ab200_estimate_timestep[_device](AB200_GAS) includes the diffusive limits and
+ * the device-resident drivers (ab200_run_cycles, ab200_run_cycles_mr, ab200_cycles_host) apply
+ * flux + update every stage, after FluxSource and before the gravity / rotating-frame / drag
+ * sources.  Parameters mirror Diffusion::DiffCoeffParams (diffusion_coeff.hpp:59-146). */
+#define AB200_VISC_NONE 0
+#define AB200_VISC_PLAW 1         /* <gas/viscosity> type = constant | powerlaw */
+#define AB200_VISC_ALPHA 2        /* type = alpha: nu = alpha c_s^2 / Omega_K   */
+#define AB200_COND_NONE 0
+#define AB200_COND_CONDUCTIVITY 1 /* <gas/conductivity> type = conductivity     */
+#define AB200_COND_DIFFUSIVITY 2  /* type = diffusivity                         */
+#define AB200_AVG_ARITHMETIC 0
+#define AB200_AVG_HARMONIC 1
+typedef struct ab200_diffusion_desc {
+  int visc_type, visc_avg;
+  double nu, eta_bulk, r0, r_exp;  /* plaw: nu (r/r0)^r_exp; eta_bulk = bulk / shear          */
+  double alpha, omega0;            /* alpha; omega0 = sqrt(gm / r0^3) (diffusion_coeff.hpp:113) */
+  int cond_type, cond_avg;
+  double cond, kappa, temp_exp, rho_exp, rho_ref, t_ref;
+  double cv;                       /* specific heat of the ideal-gas EOS (T = sie / cv)       */
+} ab200_diffusion_desc;
+int ab200_configure_diffusion(ab200_ctx *ctx, const ab200_diffusion_desc *dd); /* NULL: off */
+int ab200_diffusion_flux(ab200_ctx *ctx);
+int ab200_diffusion_update(ab200_ctx *ctx, double dt);
+int ab200_diffusion_timestep(ab200_ctx *ctx, double *dt_host);
+/* device pointer and element count of the library-owned flux array of direction dir (1..3):
+ * [nblocks][4 nspecies][fnk][fnj][fni], entries 3n..3n+2 = gas.diff.momentum of species n,
+ * 3 nspecies + n = gas.diff.energy (Metadata::Face arrays, src/gas/gas.cpp:277-285) */
+int ab200_diffusion_flux_array(ab200_ctx *ctx, int dir, double **dev_ptr, size_t *count);
+
 /* ---- history reductions -------------------------------------------------
  * out_host[v] = sum over the interior zones of the partition of cons0[v] * Volume, for every
  * conserved pack entry v of `fluid` (nout = its pack size): the integrals behind gas_mass,
