@@ -345,6 +345,14 @@ def main_config3(args):
         sd.point_mass, sd.pm = 1, capi.PointMassDesc(1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
         sd.rotating_frame, sd.rf_omega = 1, 1.0
         md.call("ab200_configure_sources", C.byref(sd))
+        # <gas/viscosity> type = alpha, alpha = 1e-3 (nu = alpha c_s^2 / Omega_K, r0 = 1, gm = 1)
+        dd = capi.DiffusionDesc()
+        dd.visc_type, dd.alpha, dd.r0, dd.omega0 = 2, 1e-3, 1.0, 1.0
+        md.call("ab200_configure_diffusion", C.byref(dd))
+        drv.block_dt = drv.EstimateTimestep()    # the viscous limit enters the first dt
+        drv.dt = float(np.finfo(np.float64).max)
+        drv.SetGlobalTimeStep()
+        md.set_time_state(drv.dt)
     if not args.no_drag and not cfg4:   # <drag/dust> type = constant, one stopping time per species
         import ctypes as C
         from artemis_b200 import capi
@@ -403,9 +411,9 @@ def main_config3(args):
                                        "curvilinear fluxes, PLM_G-free PPM, geometric source terms; "
                                        + ("no source terms" if args.no_sources else
                                           "point-mass gravity (gm 1) + rotating frame (omega 1, mass-flux "
-                                          "tap) every stage as in disk_sph.in, split stage")
-                                       + "; alpha viscosity and the disk user BCs stay on the reference "
-                                         "path" if cfg4 else
+                                          "tap) + alpha viscosity (1e-3) every stage as in disk_sph.in, "
+                                          "split stage")
+                                       + "; the disk user BCs stay on the reference path" if cfg4 else
                                        f"config 3: gas + {S} dust species (inputs/drag state + seeded "
                                        f"perturbation), PLM+HLLE, rk2, periodic, {M}^3 zones in TOTAL in "
                                        f"{B}^3 MeshBlocks split over {world} GPU(s) (strong scaling); "

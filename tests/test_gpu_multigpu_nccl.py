@@ -39,3 +39,22 @@ def test_ranks_on_real_gpus_are_bit_identical_to_the_undivided_mesh(nranks, tran
             fh.write(r.stdout[-4000:] + "\n--- stderr ---\n" + r.stderr[-4000:])
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
     assert "BIT-IDENTICAL" in r.stdout
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_ranks_with_sources_and_diffusion_are_bit_identical_to_the_undivided_mesh(nranks):
+    """same check with uniform gravity + gas-dust drag + viscosity + conduction configured: every
+    stage is split and the diffusion operators read ghost zones the exchange filled."""
+    if _ngpus() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29650 + nranks),
+           os.path.join(ROOT, "tests", "tools", "check_multigpu.py"), "--cycles", "3",
+           "--transport", "native", "--physics"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, f"check_multigpu_n{nranks}_native_physics.log"), "w") as fh:
+            fh.write(r.stdout[-4000:] + "\n--- stderr ---\n" + r.stderr[-4000:])
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    assert "BIT-IDENTICAL" in r.stdout

@@ -28,6 +28,9 @@ ap.add_argument("--bnx", type=int, default=16)
 ap.add_argument("--transport", default="native", choices=["native", "torch"],
                 help="native: ab200_run_cycles_mr over the C ABI's own NCCL transport (comm.cu); "
                      "torch: StepDevice driven from Python over torch.distributed")
+ap.add_argument("--physics", action="store_true",
+                help="also configure uniform gravity, gas-dust drag, viscosity and conduction "
+                     "(split stages + diffusion operators on every rank)")
 args = ap.parse_args()
 world, rank, local = (int(os.environ[k]) for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"))
 torch.cuda.set_device(local)
@@ -44,10 +47,29 @@ gp, dp = gas_params(C, "ppm", "hllc"), dust_params(C, "plm", "hlle", S=1)
 prim, dprim = random_prim(gm, gp, seed=21, shocks=True), random_prim(gm, dp, seed=22, shocks=False)
 BIG = float(np.finfo(np.float64).max)
 
+
+
+def configure_physics(m):
+    """the same source terms and diffusion operators on the undivided mesh and on every tile"""
+    if not args.physics:
+        return
+    import ctypes as C
+    from artemis_b200 import capi
+    sd = capi.SourcesDesc()
+    sd.gravity, sd.g[0], sd.g[1], sd.g[2] = 1, 0.1, -0.2, 0.3
+    sd.drag, sd.ntau, sd.tau[0] = 1, 1, 0.05
+    m.call("ab200_configure_sources", C.byref(sd))
+    dd = capi.DiffusionDesc()
+    dd.visc_type, dd.nu, dd.r0, dd.eta_bulk = 1, 3e-3, 1.0, 0.4
+    dd.cond_type, dd.kappa, dd.rho_ref, dd.t_ref, dd.cv = 2, 5e-3, 1.0, 1.0, 1.1
+    m.call("ab200_configure_diffusion", C.byref(dd))
+
+
 # the undivided mesh on this rank's own GPU (every rank computes it: no gather needed)
 md = MeshData(gm, gas=gp, dust=dp, device=local, materialize_fluxes=False)
 md.gas.prim.set(prim)
 md.dust.prim.set(dprim)
+configure_physics(md)
 drv = ArtemisDriver(md, "rk2", mode="fused")
 drv.Initialize()
 dt0 = drv.dt
@@ -72,6 +94,7 @@ tmd = MeshData(tm, gas=gp, dust=dp, device=local, materialize_fluxes=False, bcs=
 comm = HaloComm(tmd, lay, rl, rank, world)
 tmd.gas.prim.set(np.ascontiguousarray(prim[gid]))
 tmd.dust.prim.set(np.ascontiguousarray(dprim[gid]))
+configure_physics(tmd)
 tdrv = ArtemisDriver(tmd, "rk2", mode="fused", comm=comm)
 tdrv.Initialize()
 assert tdrv.dt == dt0, (tdrv.dt, dt0)
@@ -94,9 +117,10 @@ flag = torch.tensor([1.0 if ok else 0.0], device=f"cuda:{local}")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     direct = int(tmd.L.ab200_comm_is_direct(tmd.ctx)) if args.transport == "native" else 0
-    print("check_multigpu: world %d lattice %s cycles %d transport %s (peer-write over CUDA IPC: %s, "
-          "overlap: %s) -> %s" % (world, lay, args.cycles, args.transport, bool(direct),
-                                  bool(os.environ.get("AB200_OVERLAP")),
+    print("check_multigpu: world %d lattice %s cycles %d transport %s physics %s (peer-write over "
+          "CUDA IPC: %s, overlap: %s) -> %s" % (world, lay, args.cycles, args.transport,
+                                  "gravity+drag+viscosity+conduction" if args.physics else "hydro",
+                                  bool(direct), bool(os.environ.get("AB200_OVERLAP")),
                                   "BIT-IDENTICAL" if flag.item() == 1.0 else "MISMATCH"))
 tmd.close()
 dist.destroy_process_group()
