@@ -127,6 +127,8 @@ struct ab200_ctx {
   bool has_diffusion = false;
   double *d_dflx[3] = {nullptr, nullptr, nullptr};
   size_t dflx_elems = 0;
+  double *d_dcoef = nullptr;  // [3][nb][S][cells]: viscosity, conductivity, div(u) per zone
+  size_t dcoef_elems = 0;
   // multi-rank transport (comm.cu): NCCL communicator, comm stream, planned exchange
   void *comm_state = nullptr;
 };

@@ -232,6 +232,7 @@ int ab200_destroy(ab200_ctx *c) {
     if (c->d_blist[q]) cudaFree(c->d_blist[q]);
   for (int q = 0; q < 3; ++q)
     if (c->d_dflx[q]) cudaFree(c->d_dflx[q]);
+  if (c->d_dcoef) cudaFree(c->d_dcoef);
   if (c->d_time) cudaFree(c->d_time);
   if (c->d_red) cudaFree(c->d_red);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);

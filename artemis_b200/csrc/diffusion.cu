@@ -7,12 +7,13 @@
 // for viscosity and conduction, each re-evaluating div(u) and the coefficient of every row) and
 // one for the update.  Here:
 //
-//   k_diffusion_flux    ONE kernel, one thread per zone of the interior extended by one face layer:
-//                       the thread evaluates the transport coefficients and div(u) of ITS zone
-//                       once and the fluxes through its (up to three) lower faces, i.e. every
-//                       face of the interior is computed exactly once; writes 4 face values per
-//                       species and direction (gas.diff.momentum, gas.diff.energy), coalesced
-//                       along i.  Zeroing is the store itself.
+//   k_diffusion_coeff   pre-pass: dynamic viscosity, conductivity (the pow() calls) and div(u) of
+//                       every zone ONCE (3 doubles per zone and species)
+//   k_diffusion_flux    one thread per zone of the interior extended by one face layer: the
+//                       fluxes through its (up to three) lower faces, i.e. every face of the
+//                       interior is computed exactly once; writes 4 face values per species and
+//                       direction (gas.diff.momentum, gas.diff.energy), coalesced along i.
+//                       Zeroing is the store itself.
 //   k_diffusion_update  Gas::DiffusionUpdate, one thread per interior zone.
 //   k_diffusion_dt      the two diffusive timestep limits in one pass over the primitives.
 //
@@ -47,29 +48,99 @@ struct DiffDev {  // Diffusion::DiffCoeffParams of <gas/viscosity> and <gas/cond
   double *flx[3];  // [nb][4S][fnk][fnj][fni] per direction
 };
 
-// volume centroid, volume-averaged scale factors and Cartesian image of one cell
-template <int GEOM>
-struct DCell {
-  double xv[3], hx[3], xc[3];
-  AB_D DCell(const GridDev &g, int b, int k, int j, int i) {
+// Per-thread geometry of the 3 x 3 x 3 neighbourhood of one zone.  Everything the strain tensor
+// needs is position-only and separable: centroids x1v(i), x2v(j), x3v(k) (host tables: the same
+// expressions evaluated once per index instead of once per use -- each costs a division), the
+// centroid trig, hx3v(i, j).  A face kernel then assembles the volume-averaged scale factors and
+// the Cartesian image of any neighbour from cached pieces with compile-time offsets (NDIM is a
+// template parameter, so inactive directions fold away).  Same operands, same operation order
+// as Coords<GEOM>::{x?v, hx?v, to_cart}: the strict build stays bit-identical.
+template <int GEOM, int NDIM>
+struct GeoCache {
+  static constexpr bool multid = NDIM >= 2, threed = NDIM == 3;
+  static constexpr bool sph = Coords<GEOM>::sph, sph23 = Coords<GEOM>::sph23;
+  double x1[3], x2[3], x3[3];      // centroids at index - 1, index, index + 1
+  double s2[3], c2[3], s3[3], c3[3];  // sin / cos of x2v, x3v
+  double h3[3][3];                 // hx3v at [dj + 1][di + 1] (spherical 2-D / 3-D)
+  double c1_0[3], c2_0[3];         // GetConnX1 / GetConnX2 of the zone itself
+  AB_D GeoCache(const GridDev &g, int b, int k, int j, int i) {
+    const GeomTab &t = g.t;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int ii = i + q - 1, jj = multid ? j + q - 1 : j, kk = threed ? k + q - 1 : k;
+      x1[q] = t.x1v[(size_t)b * g.ni + ii];
+      x2[q] = t.x2v[(size_t)b * g.nj + jj];
+      x3[q] = t.x3v[(size_t)b * g.nk + kk];
+      s2[q] = t.sinv[(size_t)b * g.nj + jj];
+      c2[q] = t.cosv[(size_t)b * g.nj + jj];
+      s3[q] = t.sin3v[(size_t)b * g.nk + kk];
+      c3[q] = t.cos3v[(size_t)b * g.nk + kk];
+    }
+    if (sph23) {
+#pragma unroll
+      for (int qj = 0; qj < 3; ++qj)
+#pragma unroll
+        for (int qi = 0; qi < 3; ++qi) {
+          if (!multid && qj != 1) { h3[qj][qi] = 0.0; continue; }
+          const Coords<GEOM> c(g, b, k, multid ? j + qj - 1 : j, i + qi - 1);
+          h3[qj][qi] = c.hx3v();
+        }
+    }
     const Coords<GEOM> c(g, b, k, j, i);
-    xv[0] = c.x1v(); xv[1] = c.x2v(); xv[2] = c.x3v();
-    hx[0] = c.hx1v(); hx[1] = c.hx2v(); hx[2] = c.hx3v();
-    double e[3][3];
-    c.to_cart(xc, e);
+    c.conn1(c1_0);
+    c.conn2(c2_0);
+  }
+  // volume-averaged scale factor h_c of the neighbour at offset (oj, oi) (no k dependence)
+  AB_D double hx(int c, int oj, int oi) const {
+    if (c == 1) return (GEOM == AB200_CYLINDRICAL || sph23) ? x1[oi + 1] : 1.0;
+    if (c == 2) {
+      if (GEOM == AB200_AXISYMMETRIC) return x1[oi + 1];
+      if (sph23) return h3[oj + 1][oi + 1];
+    }
+    return 1.0;
+  }
+  // is h_c identically 1 in this geometry?  (x / 1.0 == x: the division is skipped)
+  static AB_D constexpr bool unit_h(int c) {
+    return c == 0 || (c == 1 && !(GEOM == AB200_CYLINDRICAL || sph23)) ||
+           (c == 2 && !(GEOM == AB200_AXISYMMETRIC || sph23));
+  }
+  // ConvertCoordsToCart of the neighbour's centroid (see Coords<GEOM>::to_cart)
+  AB_D void cart(int ok, int oj, int oi, double xo[3]) const {
+    const double a = x1[oi + 1];
+    if (GEOM == AB200_CYLINDRICAL) {
+      xo[0] = a * c2[oj + 1]; xo[1] = a * s2[oj + 1]; xo[2] = x3[ok + 1];
+    } else if (GEOM == AB200_AXISYMMETRIC) {
+      xo[0] = a * c3[ok + 1]; xo[1] = a * s3[ok + 1]; xo[2] = x2[oj + 1];
+    } else if (sph) {
+      const double cp = (GEOM == AB200_SPHERICAL3D) ? c3[ok + 1] : 1.0;
+      const double sp = (GEOM == AB200_SPHERICAL3D) ? s3[ok + 1] : 0.0;
+      const double ct = (GEOM == AB200_SPHERICAL1D) ? 0.0 : c2[oj + 1];
+      const double st = (GEOM == AB200_SPHERICAL1D) ? 1.0 : s2[oj + 1];
+      xo[0] = a * st * cp; xo[1] = a * st * sp; xo[2] = a * ct;
+    } else {
+      xo[0] = a; xo[1] = x2[oj + 1]; xo[2] = x3[ok + 1];
+    }
+  }
+  // CoordsBase::Distance between the centroids of two neighbours (geometry.hpp:398-403)
+  AB_D double dist(int ak, int aj, int ai, int bk, int bj, int bi) const {
+    double p[3], q[3];
+    cart(ak, aj, ai, p);
+    cart(bk, bj, bi, q);
+    return dsqrt(sqr(p[0] - q[0]) + sqr(p[1] - q[1]) + sqr(p[2] - q[2]));
   }
 };
-// CoordsBase::Distance between two cell centroids (geometry.hpp:398-403)
-template <int GEOM>
-AB_D double ddist(const DCell<GEOM> &a, const DCell<GEOM> &b) {
-  return sqrt(sqr(a.xc[0] - b.xc[0]) + sqr(a.xc[1] - b.xc[1]) + sqr(a.xc[2] - b.xc[2]));
+// x / h_c with the unit scale factors folded away
+template <int GEOM, int NDIM>
+AB_D double hdiv(const GeoCache<GEOM, NDIM> &gc, double x, int c, int oj, int oi) {
+  return GeoCache<GEOM, NDIM>::unit_h(c) ? x : ddiv(x, gc.hx(c, oj, oi));
 }
+
 // FaceAverage selection of StressTensorFaceX* / ThermalFluxImpl: both means are evaluated
 // (diffusion_coeff.hpp:148-160, momentum_diffusion.hpp:398-399)
 AB_D double face_avg(int avg_type, double m1, double m2) {
   const double avg = (avg_type == AB200_AVG_ARITHMETIC) ? 1.0 : 0.0;
   const double havg = (avg_type == AB200_AVG_HARMONIC) ? 1.0 : 0.0;
-  return avg * (0.5 * (m1 + m2)) + havg * (2.0 * m1 * m2 / (m1 + m2));
+  return avg * (0.5 * (m1 + m2)) + havg * ddiv(2.0 * m1 * m2, m1 + m2);
 }
 
 #define PRD(v, kk, jj, ii) f.prim[eb + (v)][((size_t)(kk) * g.nj + (jj)) * g.ni + (ii)]
@@ -116,75 +187,65 @@ AB_D double vel_div(const GridDev &g, const FluidDev &f, int b, int n, int k, in
                       md * a2[0] * (PRD(v2, k, j, i) + PRD(v2, k, j - multid, i)) +
                       td * a3[1] * (PRD(v3, k, j, i) + PRD(v3, k + threed, j, i)) -
                       td * a3[0] * (PRD(v3, k, j, i) + PRD(v3, k - threed, j, i));
-  return divv / (2.0 * vol);
+  return ddiv(divv, 2.0 * vol);
 }
-// dh_D/dx_k of one cell: geometry.hpp:234-244 + the overrides (conn1 / conn2); dh_D/dx3 == 0
-template <int GEOM>
-AB_D void dh_matrix(const GridDev &g, int b, int k, int j, int i, double dh[3][3]) {
-  const Coords<GEOM> c(g, b, k, j, i);
-  double c1[3], c2[3];
-  c.conn1(c1);
-  c.conn2(c2);
-#pragma unroll
-  for (int D = 0; D < 3; ++D) { dh[D][0] = c1[D]; dh[D][1] = c2[D]; dh[D][2] = 0.0; }
-}
-
 // Viscous flux through the LOWER face of zone (k,j,i) in direction D+1:
 // StrainTensorFace<XDIR> + StressTensorFaceX{1,2,3}, momentum_diffusion.hpp:27-551.
-// mu0 / div0: coefficient and div(u) of the zone itself (shared by its three faces).
-template <int GEOM, int D>
-AB_D void visc_face(const GridDev &g, const FluidDev &f, const DiffDev &dd, int b, int n, int k,
-                    int j, int i, double mu0, double div0, double out[4]) {
+// mu0 / div0, mum / divm: coefficient and div(u) of the zone itself and of the zone across the
+// face, from the pre-pass (k_diffusion_coeff).
+template <int GEOM, int NDIM, int D>
+AB_D void visc_face(const GridDev &g, const FluidDev &f, const DiffDev &dd,
+                    const GeoCache<GEOM, NDIM> &gc, int b, int n, int k, int j, int i, double mu0,
+                    double div0, double mum, double divm, double out[4]) {
   const size_t eb = (size_t)b * f.nvar;
-  const int multid = (g.ndim >= 2), threed = (g.ndim == 3);
-  const int offs[3] = {1, multid, threed};
+  constexpr int offs[3] = {1, NDIM >= 2, NDIM == 3};
   const int vi[3] = {f.S + 3 * n, f.S + 3 * n + 1, f.S + 3 * n + 2};
   constexpr int dk[3] = {0, 0, 1}, dj[3] = {0, 1, 0}, di[3] = {1, 0, 0};
-  const int km = k - dk[D], jm = j - dj[D], im = i - di[D];
-  const DCell<GEOM> c0(g, b, k, j, i), cm(g, b, km, jm, im);
+  constexpr int mk = -dk[D], mj = -dj[D], mi = -di[D];  // the zone across the face
   double v[3], vm[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    v[c] = PRD(vi[c], k, j, i) / c0.hx[c];
-    vm[c] = PRD(vi[c], km, jm, im) / cm.hx[c];
+    v[c] = hdiv(gc, PRD(vi[c], k, j, i), c, 0, 0);
+    vm[c] = hdiv(gc, PRD(vi[c], k + mk, j + mj, i + mi), c, mj, mi);
   }
   double hxf[3];
   {
     const Coords<GEOM> cc(g, b, k, j, i);
     cc.template face_scale<D + 1>(hxf);
   }
-  const double dxD = ddist(c0, cm);
-  double dh0[3][3], dhm[3][3];
-  dh_matrix<GEOM>(g, b, k, j, i, dh0);
-  dh_matrix<GEOM>(g, b, km, jm, im, dhm);
+  const double dxD = gc.dist(0, 0, 0, mk, mj, mi);
+  // dh_D/dx_k = {GetConnX1()[D], GetConnX2()[D], 0}; across the face only the factor that
+  // depends on the marching index changes (conn1: x1 faces, conn2: theta faces)
+  double c1m[3] = {gc.c1_0[0], gc.c1_0[1], gc.c1_0[2]}, c2m[3] = {gc.c2_0[0], gc.c2_0[1], gc.c2_0[2]};
+  if (D == 0 || D == 1) {
+    const Coords<GEOM> cmc(g, b, k + mk, j + mj, i + mi);
+    if (D == 0) cmc.conn1(c1m);
+    if (D == 1) cmc.conn2(c2m);
+  }
   double flx[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     if (c == D) {
       const double dv = v[D] - vm[D];
-      const double src = v[0] * dh0[D][0] + v[1] * dh0[D][1] + v[2] * dh0[D][2];
-      const double srm = vm[0] * dhm[D][0] + vm[1] * dhm[D][1] + vm[2] * dhm[D][2];
-      flx[c] = 2 * dv / dxD + 0.5 * (src + srm);
+      const double src = v[0] * gc.c1_0[D] + v[1] * gc.c2_0[D] + v[2] * 0.0;
+      const double srm = vm[0] * c1m[D] + vm[1] * c2m[D] + vm[2] * 0.0;
+      flx[c] = ddiv(2 * dv, dxD) + 0.5 * (src + srm);
     } else {
       const int o = offs[c];
-      const int kp = k + o * dk[c], jp = j + o * dj[c], ip = i + o * di[c];
-      const int kq = k - o * dk[c], jq = j - o * dj[c], iq = i - o * di[c];
-      const int kmp = km + o * dk[c], jmp = jm + o * dj[c], imp = im + o * di[c];
-      const int kmq = km - o * dk[c], jmq = jm - o * dj[c], imq = im - o * di[c];
-      const DCell<GEOM> cp(g, b, kp, jp, ip), cq(g, b, kq, jq, iq);
-      const DCell<GEOM> cmp(g, b, kmp, jmp, imp), cmq(g, b, kmq, jmq, imq);
-      const double dxc = o ? ddist(cq, cp) : 1e-99;
-      const double dxc_m = o ? ddist(cmq, cmp) : 1e-99;
-      const double dvt = PRD(vi[D], kp, jp, ip) / cp.hx[D] - PRD(vi[D], kq, jq, iq) / cq.hx[D];
+      const int ok = o * dk[c], oj = o * dj[c], oi = o * di[c];
+      const double dxc = o ? gc.dist(-ok, -oj, -oi, ok, oj, oi) : 1e-99;
+      const double dxc_m = o ? gc.dist(mk - ok, mj - oj, mi - oi, mk + ok, mj + oj, mi + oi) : 1e-99;
+      const double dvt = hdiv(gc, PRD(vi[D], k + ok, j + oj, i + oi), D, oj, oi) -
+                         hdiv(gc, PRD(vi[D], k - ok, j - oj, i - oi), D, -oj, -oi);
       const double dvt_m =
-          PRD(vi[D], kmp, jmp, imp) / cmp.hx[D] - PRD(vi[D], kmq, jmq, imq) / cmq.hx[D];
+          hdiv(gc, PRD(vi[D], k + mk + ok, j + mj + oj, i + mi + oi), D, mj + oj, mi + oi) -
+          hdiv(gc, PRD(vi[D], k + mk - ok, j + mj - oj, i + mi - oi), D, mj - oj, mi - oi);
       const double dv = v[c] - vm[c];
-      const double r = hxf[c] / hxf[D];
-      flx[c] = (double)o * 0.5 * (dvt / dxc + dvt_m / dxc_m) + (r * r) * dv / dxD;
+      const double r = ddiv(hxf[c], hxf[D]);
+      flx[c] = (double)o * 0.5 * (ddiv(dvt, dxc) + ddiv(dvt_m, dxc_m)) + ddiv((r * r) * dv, dxD);
     }
   }
-  const double mus = face_avg(dd.visc_avg, mu0, visc_mu<GEOM>(g, f, dd, b, n, km, jm, im));
-  const double divm = vel_div<GEOM>(g, f, b, n, km, jm, im);
+  const double mus = face_avg(dd.visc_avg, mu0, mum);
   const double divs = (D == 0) ? div0 + divm : divm + div0;
   const double hDf = hxf[D];
   double fc[3];
@@ -192,34 +253,48 @@ AB_D void visc_face(const GridDev &g, const FluidDev &f, const DiffDev &dd, int 
   for (int c = 0; c < 3; ++c)
     fc[c] = (c == D) ? hDf * mus * (flx[c] - 1. / 3 * (1. - dd.eta) * divs) : hDf * mus * flx[c];
   out[0] = fc[0]; out[1] = fc[1]; out[2] = fc[2];
-  out[3] = 0.5 * (PRD(vi[0], k, j, i) / c0.hx[0] + PRD(vi[0], km, jm, im) / cm.hx[0]) * fc[0] +
-           0.5 * (PRD(vi[1], k, j, i) / c0.hx[1] + PRD(vi[1], km, jm, im) / cm.hx[1]) * fc[1] +
-           0.5 * (PRD(vi[2], k, j, i) / c0.hx[2] + PRD(vi[2], km, jm, im) / cm.hx[2]) * fc[2];
+  // (the same quotients as v[] / vm[] above: the reference re-divides, the bits are equal)
+  out[3] = 0.5 * (v[0] + vm[0]) * fc[0] + 0.5 * (v[1] + vm[1]) * fc[1] +
+           0.5 * (v[2] + vm[2]) * fc[2];
 }
 // Heat flux through the lower face of zone (k,j,i) in direction D+1, thermal_diffusion.hpp:62-218
-template <int GEOM, int D>
-AB_D double cond_face(const GridDev &g, const FluidDev &f, const DiffDev &dd, int b, int n, int k,
-                      int j, int i, double kap0) {
+template <int GEOM, int NDIM, int D>
+AB_D double cond_face(const GridDev &g, const FluidDev &f, const DiffDev &dd,
+                      const GeoCache<GEOM, NDIM> &gc, int b, int n, int k, int j, int i,
+                      double kap0, double kapm) {
   const size_t eb = (size_t)b * f.nvar;
-  const int km = k - (D == 2), jm = j - (D == 1), im = i - (D == 0);
-  const DCell<GEOM> c0(g, b, k, j, i), cm(g, b, km, jm, im);
-  const double dxD = ddist(c0, cm);
-  const double T = dmax(0.0, PRD(5 * f.S + n, k, j, i) / dd.cv);
-  const double Tm = dmax(0.0, PRD(5 * f.S + n, km, jm, im) / dd.cv);
-  const double kc = face_avg(dd.cond_avg, kap0, cond_kappa(g, f, dd, b, n, km, jm, im));
-  return kc * (T - Tm) / dxD;
+  constexpr int mk = -(D == 2), mj = -(D == 1), mi = -(D == 0);
+  const double dxD = gc.dist(0, 0, 0, mk, mj, mi);
+  const double T = dmax(0.0, ddiv(PRD(5 * f.S + n, k, j, i), dd.cv));
+  const double Tm = dmax(0.0, ddiv(PRD(5 * f.S + n, k + mk, j + mj, i + mi), dd.cv));
+  const double kc = face_avg(dd.cond_avg, kap0, kapm);
+  return ddiv(kc * (T - Tm), dxD);
 }
 
-template <int GEOM, int D>
-AB_D void face_fluxes(const GridDev &g, const FluidDev &f, const DiffDev &dd, int b, int n, int k,
-                      int j, int i, double mu0, double div0, double kap0) {
+// per-zone inputs of the face kernels, computed ONCE per zone by k_diffusion_coeff (the reference
+// re-evaluates them for every pencil row of every direction): [3][nb][S][cells] = dynamic
+// viscosity, conductivity, div(u)
+struct CoefDev {
+  double *mu, *kap, *div;
+};
+
+template <int GEOM, int NDIM, int D>
+AB_D void face_fluxes(const GridDev &g, const FluidDev &f, const DiffDev &dd, const CoefDev &cf,
+                      const GeoCache<GEOM, NDIM> &gc, int b, int n, int k, int j, int i) {
+  constexpr int dk = (D == 2), dj = (D == 1), di = (D == 0);
+  const size_t cells = (size_t)g.ni * g.nj * g.nk;
+  const size_t co = ((size_t)b * f.S + n) * cells;
+  const size_t o0 = co + ((size_t)k * g.nj + j) * g.ni + i;
+  const size_t om = co + ((size_t)(k - dk) * g.nj + (j - dj)) * g.ni + (i - di);
   double o[4] = {0.0, 0.0, 0.0, 0.0}, acc[4] = {0.0, 0.0, 0.0, 0.0};
   if (dd.visc_type != AB200_VISC_NONE) {
-    visc_face<GEOM, D>(g, f, dd, b, n, k, j, i, mu0, div0, o);
+    visc_face<GEOM, NDIM, D>(g, f, dd, gc, b, n, k, j, i, cf.mu[o0], cf.div[o0], cf.mu[om],
+                             cf.div[om], o);
 #pragma unroll
     for (int m = 0; m < 4; ++m) acc[m] += o[m];
   }
-  if (dd.cond_type != AB200_COND_NONE) acc[3] += cond_face<GEOM, D>(g, f, dd, b, n, k, j, i, kap0);
+  if (dd.cond_type != AB200_COND_NONE)
+    acc[3] += cond_face<GEOM, NDIM, D>(g, f, dd, gc, b, n, k, j, i, cf.kap[o0], cf.kap[om]);
   const int S = f.S;
   const size_t fcells = (size_t)g.fni * g.fnj * g.fnk;
   const size_t fo = ((size_t)k * g.fnj + j) * g.fni + i;
@@ -230,12 +305,35 @@ AB_D void face_fluxes(const GridDev &g, const FluidDev &f, const DiffDev &dd, in
   base[(size_t)(3 * S + n) * fcells] = acc[3];
 }
 
-// Gas::ZeroDiffusionFlux + ViscousFlux + ThermalFlux: x1 faces is..ie+1, x2 faces js..je+1,
-// x3 faces ks..ke+1 of the interior zones
+// pre-pass: transport coefficients and div(u) of every zone a face kernel touches = the interior
+// extended by one zone on every side of the active directions
 template <int GEOM>
 __global__ void __launch_bounds__(kThreads)
-k_diffusion_flux(GridDev g, FluidDev f, DiffDev dd) {
+k_diffusion_coeff(GridDev g, FluidDev f, DiffDev dd, CoefDev cf) {
   const int multid = (g.ndim >= 2), threed = (g.ndim == 3);
+  const int nir = g.ie - g.is + 3, njr = g.je - g.js + 1 + 2 * multid,
+            nkr = g.ke - g.ks + 1 + 2 * threed;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)g.nb * nkr * njr * nir) return;
+  const CellIdx c = decode(t, nir, njr, nkr, g.is - 1, g.js - multid, g.ks - threed);
+  const size_t cells = (size_t)g.ni * g.nj * g.nk;
+  for (int n = 0; n < f.S; ++n) {
+    const size_t o = ((size_t)c.b * f.S + n) * cells + ((size_t)c.k * g.nj + c.j) * g.ni + c.i;
+    if (dd.visc_type != AB200_VISC_NONE) {
+      cf.mu[o] = visc_mu<GEOM>(g, f, dd, c.b, n, c.k, c.j, c.i);
+      cf.div[o] = vel_div<GEOM>(g, f, c.b, n, c.k, c.j, c.i);
+    }
+    if (dd.cond_type != AB200_COND_NONE) cf.kap[o] = cond_kappa(g, f, dd, c.b, n, c.k, c.j, c.i);
+  }
+}
+
+// Gas::ZeroDiffusionFlux + ViscousFlux + ThermalFlux: x1 faces is..ie+1, x2 faces js..je+1,
+// x3 faces ks..ke+1 of the interior zones
+constexpr int kFluxThreads = 128;  // 120-170 registers: three CTAs of four warps per SM
+template <int GEOM, int NDIM>
+__global__ void __launch_bounds__(kFluxThreads)
+k_diffusion_flux(GridDev g, FluidDev f, DiffDev dd, CoefDev cf) {
+  constexpr int multid = (NDIM >= 2), threed = (NDIM == 3);
   const int nir = g.ie - g.is + 2, njr = g.je - g.js + 1 + multid, nkr = g.ke - g.ks + 1 + threed;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)g.nb * nkr * njr * nir) return;
@@ -243,22 +341,17 @@ k_diffusion_flux(GridDev g, FluidDev f, DiffDev dd) {
   const bool in_i = c.i <= g.ie, in_j = c.j <= g.je, in_k = c.k <= g.ke;
   // a corner / edge zone of the extended box bounds no interior face
   if ((int)!in_i + (int)!in_j + (int)!in_k > 1) return;
+  const GeoCache<GEOM, NDIM> gc(g, c.b, c.k, c.j, c.i);
   for (int n = 0; n < f.S; ++n) {
-    double mu0 = 0.0, div0 = 0.0, kap0 = 0.0;
-    if (dd.visc_type != AB200_VISC_NONE) {
-      mu0 = visc_mu<GEOM>(g, f, dd, c.b, n, c.k, c.j, c.i);
-      div0 = vel_div<GEOM>(g, f, c.b, n, c.k, c.j, c.i);
-    }
-    if (dd.cond_type != AB200_COND_NONE) kap0 = cond_kappa(g, f, dd, c.b, n, c.k, c.j, c.i);
-    if (in_j && in_k) face_fluxes<GEOM, 0>(g, f, dd, c.b, n, c.k, c.j, c.i, mu0, div0, kap0);
-    if (multid && in_i && in_k) face_fluxes<GEOM, 1>(g, f, dd, c.b, n, c.k, c.j, c.i, mu0, div0, kap0);
-    if (threed && in_i && in_j) face_fluxes<GEOM, 2>(g, f, dd, c.b, n, c.k, c.j, c.i, mu0, div0, kap0);
+    if (in_j && in_k) face_fluxes<GEOM, NDIM, 0>(g, f, dd, cf, gc, c.b, n, c.k, c.j, c.i);
+    if (multid && in_i && in_k) face_fluxes<GEOM, NDIM, 1>(g, f, dd, cf, gc, c.b, n, c.k, c.j, c.i);
+    if (threed && in_i && in_j) face_fluxes<GEOM, NDIM, 2>(g, f, dd, cf, gc, c.b, n, c.k, c.j, c.i);
   }
 }
 
 // Diffusion::DiffusionUpdateImpl, diffusion.hpp:113-242
 template <int GEOM>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 k_diffusion_update(GridDev g, FluidDev f, DiffDev dd, double dt_host, const double *dt_dev,
                    double beta) {
   const double dt = dt_dev ? beta * *dt_dev : dt_host;
@@ -428,7 +521,20 @@ static size_t dflx_count(const ab200_ctx *c) {
   return (size_t)g.nb * 4 * c->fl[AB200_GAS].d.S * g.fni * g.fnj * g.fnk;
 }
 
+static size_t dcoef_count(const ab200_ctx *c) {
+  const GridDev &g = c->g;
+  return (size_t)g.nb * c->fl[AB200_GAS].d.S * g.ni * g.nj * g.nk;
+}
+
 static int ensure_dflx(ab200_ctx *c) {
+  const size_t nc = dcoef_count(c);
+  if (!c->d_dcoef || c->dcoef_elems != nc) {
+    if (c->d_dcoef) cudaFree(c->d_dcoef);
+    c->d_dcoef = nullptr;
+    AB_CUDA(cudaMalloc((void **)&c->d_dcoef, 3 * nc * sizeof(double)));
+    AB_CUDA(cudaMemsetAsync(c->d_dcoef, 0, 3 * nc * sizeof(double), c->stream));
+    c->dcoef_elems = nc;
+  }
   const size_t n = dflx_count(c);
   for (int d = 0; d < c->g.ndim; ++d) {
     if (c->d_dflx[d] && c->dflx_elems == n) continue;
@@ -459,13 +565,32 @@ int launch_diffusion_flux(ab200_ctx *c) {
   const int multid = g.ndim >= 2, threed = g.ndim == 3;
   const long long n = (long long)g.nb * (g.ke - g.ks + 1 + threed) * (g.je - g.js + 1 + multid) *
                       (g.ie - g.is + 2);
-  const unsigned grid = (unsigned)((n + kThreads - 1) / kThreads);
+  const unsigned grid = (unsigned)((n + kFluxThreads - 1) / kFluxThreads);
   const DiffDev dd = diff_dev(c);
+  const CoefDev cf{c->d_dcoef, c->d_dcoef + c->dcoef_elems, c->d_dcoef + 2 * c->dcoef_elems};
+  const long long nco = (long long)g.nb * (g.ke - g.ks + 1 + 2 * threed) *
+                        (g.je - g.js + 1 + 2 * multid) * (g.ie - g.is + 3);
+  const unsigned gridc = (unsigned)((nco + kThreads - 1) / kThreads);
   int rc = dispatch_geom_d(g.geom, [&](auto G) {
-    k_diffusion_flux<decltype(G)::value><<<grid, kThreads, 0, c->stream>>>(g, c->fl[AB200_GAS].d, dd);
+    constexpr int GG = decltype(G)::value;
+    k_diffusion_coeff<GG><<<gridc, kThreads, 0, c->stream>>>(g, c->fl[AB200_GAS].d, dd, cf);
+    const FluidDev &fd = c->fl[AB200_GAS].d;
+    // the dimensionalities each coordinate system admits (spherical1D / 2D / 3D fix theirs)
+    constexpr bool only1 = GG == AB200_SPHERICAL1D, only2 = GG == AB200_SPHERICAL2D,
+                   only3 = GG == AB200_SPHERICAL3D;
+    if (g.ndim == 1) {
+      if constexpr (!only2 && !only3) k_diffusion_flux<GG, 1><<<grid, kFluxThreads, 0, c->stream>>>(g, fd, dd, cf);
+      else { set_error("diffusion: coordinate system and ndim do not match"); return AB200_EINVAL; }
+    } else if (g.ndim == 2) {
+      if constexpr (!only1 && !only3) k_diffusion_flux<GG, 2><<<grid, kFluxThreads, 0, c->stream>>>(g, fd, dd, cf);
+      else { set_error("diffusion: coordinate system and ndim do not match"); return AB200_EINVAL; }
+    } else {
+      if constexpr (!only1 && !only2) k_diffusion_flux<GG, 3><<<grid, kFluxThreads, 0, c->stream>>>(g, fd, dd, cf);
+      else { set_error("diffusion: coordinate system and ndim do not match"); return AB200_EINVAL; }
+    }
     return AB200_OK;
   });
-  c->launches++;
+  c->launches += 2;
   AB_CUDA(cudaGetLastError());
   return rc;
 }

@@ -214,7 +214,7 @@ struct TwoMassFlux {
 // RotatingFrame::RotatingFrameImpl<GEOM>, rotating_frame_impl.hpp:96-199: angular-momentum
 // conserving form -- the mass fluxes through the six faces weighted by +-(<R^2>_face - <R^2>).
 template <int GEOM>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 k_rotating_frame(GridDev g, TwoFluids tf, TwoMassFlux mf, double dt_host, const double *dt_dev,
                  double beta, double om0) {
   const double dt = dt_dev ? beta * *dt_dev : dt_host;
