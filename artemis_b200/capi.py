@@ -55,12 +55,23 @@ class DiffusionDesc(C.Structure):
                 ("t_ref", C.c_double), ("cv", C.c_double)]
 
 
+class DragDesc(C.Structure):
+    """ab200_drag_desc"""
+    _fields_ = [("coupling", C.c_int), ("model", C.c_int), ("tau", C.c_double * 16),
+                ("scale", C.c_double), ("grain_density", C.c_double), ("sizes", C.c_double * 16),
+                ("g_ix", C.c_double * 3), ("g_ox", C.c_double * 3), ("g_irate", C.c_double * 3),
+                ("g_orate", C.c_double * 3), ("g_damp_to_visc", C.c_int),
+                ("d_ix", C.c_double * 3), ("d_ox", C.c_double * 3), ("d_irate", C.c_double * 3),
+                ("d_orate", C.c_double * 3), ("xmin", C.c_double * 3), ("xmax", C.c_double * 3)]
+
+
 class SourcesDesc(C.Structure):
     """ab200_sources_desc"""
     _fields_ = [("gravity", C.c_int), ("g", C.c_double * 3), ("shearing_box", C.c_int),
                 ("omega", C.c_double), ("qshear", C.c_double), ("drag", C.c_int),
                 ("ntau", C.c_int), ("tau", C.c_double * 16), ("point_mass", C.c_int),
-                ("pm", PointMassDesc), ("rotating_frame", C.c_int), ("rf_omega", C.c_double)]
+                ("pm", PointMassDesc), ("rotating_frame", C.c_int), ("rf_omega", C.c_double),
+                ("drag_model", C.c_int), ("drag_desc", DragDesc)]
 
 
 class AB200Error(RuntimeError):
@@ -84,7 +95,7 @@ SYMBOLS = [
     "ab200_run_cycles", "ab200_malloc", "ab200_free", "ab200_memcpy_h2d", "ab200_memcpy_d2h",
     "ab200_launch_count", "ab200_timer_begin", "ab200_timer_end",
     "ab200_history_volume_integrals", "ab200_configure_sources", "ab200_finish_stage", "ab200_uniform_gravity", "ab200_shearing_box", "ab200_drag_simple",
-    "ab200_point_mass_gravity", "ab200_rotating_frame",
+    "ab200_point_mass_gravity", "ab200_rotating_frame", "ab200_drag_source",
     "ab200_configure_diffusion", "ab200_diffusion_flux", "ab200_diffusion_update",
     "ab200_diffusion_timestep", "ab200_diffusion_flux_array",
     "ab200_comm_unique_id", "ab200_comm_init", "ab200_comm_destroy", "ab200_comm_set_layout",
@@ -153,7 +164,7 @@ def load(variant: str | None = None) -> C.CDLL:
         "ab200_history_volume_integrals": [vp, i, _DP, i], "ab200_configure_sources": [vp, vp], "ab200_finish_stage": [vp, i], "ab200_uniform_gravity": [vp, d, d, d, d],
         "ab200_shearing_box": [vp, d, d, d], "ab200_drag_simple": [vp, d, i, _DP],
         "ab200_point_mass_gravity": [vp, d, C.POINTER(PointMassDesc)],
-        "ab200_rotating_frame": [vp, d, d],
+        "ab200_rotating_frame": [vp, d, d], "ab200_drag_source": [vp, d, C.POINTER(DragDesc)],
         "ab200_configure_diffusion": [vp, C.POINTER(DiffusionDesc)], "ab200_diffusion_flux": [vp],
         "ab200_diffusion_update": [vp, d], "ab200_diffusion_timestep": [vp, _DP],
         "ab200_diffusion_flux_array": [vp, i, C.POINTER(_DP), C.POINTER(C.c_size_t)],

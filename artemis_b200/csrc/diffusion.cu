@@ -23,7 +23,7 @@
 // non-trivial exponent (CUDA's pow and glibc's differ by <= 2 ulp there).
 #include <type_traits>
 
-#include "tasks.cuh"
+#include "diffcoef.cuh"
 
 namespace ab200 {
 
@@ -40,13 +40,6 @@ static int dispatch_geom_d(int geom, F &&fn) {
   set_error("Coordinate type not recognized!");
   return AB200_EINVAL;
 }
-
-struct DiffDev {  // Diffusion::DiffCoeffParams of <gas/viscosity> and <gas/conductivity>
-  int visc_type, visc_avg, cond_type, cond_avg;
-  double nu, eta, r0, r_exp, alpha, omega0;
-  double cond, kappa, temp_exp, rho_exp, rho_ref, t_ref, cv;
-  double *flx[3];  // [nb][4S][fnk][fnj][fni] per direction
-};
 
 // Per-thread geometry of the 3 x 3 x 3 neighbourhood of one zone.  Everything the strain tensor
 // needs is position-only and separable: centroids x1v(i), x2v(j), x3v(k) (host tables: the same
@@ -145,18 +138,13 @@ AB_D double face_avg(int avg_type, double m1, double m2) {
 
 #define PRD(v, kk, jj, ii) f.prim[eb + (v)][((size_t)(kk) * g.nj + (jj)) * g.ni + (ii)]
 
-// DiffusionCoeff<viscosity_plaw / viscosity_alpha>::Get, diffusion_coeff.hpp:178-268
+// DiffusionCoeff<viscosity_plaw / viscosity_alpha>::Get from the primitives of one zone
 template <int GEOM>
 AB_D double visc_mu(const GridDev &g, const FluidDev &f, const DiffDev &dd, int b, int n, int k,
                     int j, int i) {
   const size_t eb = (size_t)b * f.nvar;
   const Coords<GEOM> c(g, b, k, j, i);
-  const double dens = PRD(n, k, j, i);
-  if (dd.visc_type == AB200_VISC_PLAW) return dd.nu * dens * pow(c.cyl_radius() / dd.r0, dd.r_exp);
-  const double Omk = dd.omega0 * pow(c.sph_radius() / dd.r0, -1.5);
-  const double sie = PRD(5 * f.S + n, k, j, i);
-  const double blk = dmax(0.0, (f.gm1 + 1) * f.gm1 * dens * sie);
-  return dd.alpha * blk / Omk;
+  return visc_mu_val<GEOM>(c, dd, f.gm1, PRD(n, k, j, i), PRD(5 * f.S + n, k, j, i));
 }
 // DiffusionCoeff<conductivity_plaw / thermaldiff_plaw>::Get, diffusion_coeff.hpp:270-384
 AB_D double cond_kappa(const GridDev &g, const FluidDev &f, const DiffDev &dd, int b, int n,
@@ -501,19 +489,6 @@ __global__ void k_finish_diffusion_dt(const double *partial, int n, int ndim, in
     const double v = cfl * dmin(a, c2);
     *out = combine ? dmin(*out, v) : v;
   }
-}
-
-static DiffDev diff_dev(const ab200_ctx *c) {
-  const ab200_diffusion_desc &s = c->diffusion;
-  DiffDev d{};
-  d.visc_type = s.visc_type; d.visc_avg = s.visc_avg;
-  d.cond_type = s.cond_type; d.cond_avg = s.cond_avg;
-  d.nu = s.nu; d.eta = s.eta_bulk; d.r0 = s.r0; d.r_exp = s.r_exp;
-  d.alpha = s.alpha; d.omega0 = s.omega0;
-  d.cond = s.cond; d.kappa = s.kappa; d.temp_exp = s.temp_exp; d.rho_exp = s.rho_exp;
-  d.rho_ref = s.rho_ref; d.t_ref = s.t_ref; d.cv = s.cv;
-  for (int k = 0; k < 3; ++k) d.flx[k] = c->d_dflx[k];
-  return d;
 }
 
 static size_t dflx_count(const ab200_ctx *c) {

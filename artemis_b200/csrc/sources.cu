@@ -9,8 +9,11 @@
 //
 //   ab200_uniform_gravity  Gravity::UniformGravity<GEOM>     src/gravity/uniform.cpp:28-90
 //   ab200_shearing_box     RotatingFrame::ShearingBoxImpl    src/rotating_frame/rotating_frame_impl.hpp:28-94
-//   ab200_drag_simple      Drag::SimpleDragSourceImpl (constant stopping times, no damping
-//                          zones, no viscous target velocity) src/drag/drag.hpp:296-482
+//   ab200_drag_source      Drag::DragSource<GEOM> in full: simple_dust coupling (implicit gas-
+//                          dust drag, constant or Stokes stopping times) or self coupling, damping
+//                          zones of gas and dust, damping towards the viscous inflow velocity
+//                          src/drag/drag.cpp:88-165, drag.hpp:144-482
+//   ab200_drag_simple      the constant-stopping-time, no-damping special case of the above
 //   ab200_point_mass_gravity  Gravity::PointMassGravity<GEOM> (softened, off-centre, mass sink)
 //                          src/gravity/point_mass.cpp:26-196
 //   ab200_rotating_frame   RotatingFrame::RotatingFrameImpl<GEOM> (every curvilinear system)
@@ -19,7 +22,7 @@
 //                          (AB200_STAGE_TAP_DFLUX), the task path leaves them in the flux arrays
 #include <type_traits>
 
-#include "tasks.cuh"
+#include "diffcoef.cuh"
 
 namespace ab200 {
 
@@ -266,72 +269,164 @@ k_rotating_frame(GridDev g, TwoFluids tf, TwoMassFlux mf, double dt_host, const 
 }
 
 constexpr int kMaxDustSpecies = 16;
-struct DragTau {
-  double tau[kMaxDustSpecies];
+struct DragDev {  // ab200_drag_desc as the kernel reads it
+  int coupling, model, damp_to_visc;
+  double tau[kMaxDustSpecies], scale, grain_density, sizes[kMaxDustSpecies];
+  double g_ix[3], g_ox[3], g_irate[3], g_orate[3];
+  double d_ix[3], d_ox[3], d_irate[3], d_orate[3];
+  double xmin[3], xmax[3];
 };
 
-// The implicit two-pass update of drag.hpp:403-478 with bg = bd = 0, vt = vdt = 0 kept as
-// explicit zeros so the operation order (and the strict build's bits) are the reference's.
+// quadratic damping ramp of one direction (drag.hpp:195-199)
+AB_D double damp_ramp(double dt, double x, double ix, double ox, double irate, double orate,
+                      double xmin, double xmax) {
+  const double ri = (x - ix) / (ix - xmin), ro = (x - ox) / (ox - xmax);
+  return dt * (irate * ((x < ix ? 1.0 : 0.0) * (ri * ri)) + orate * ((x > ox ? 1.0 : 0.0) * (ro * ro)));
+}
+
+// Drag::SelfDragSourceImpl / SimpleDragSourceImpl (drag.hpp:144-482): the implicit two-pass
+// update with the damping ramps bg / bd and the gas target velocity vt; with no damping zone and
+// no viscous target they are zeros and the operation order (hence the strict build's bits) is the
+// reference's either way.
 template <int GEOM>
 __global__ void __launch_bounds__(kThreads)
-k_drag_simple(GridDev g, FluidDev fg, FluidDev fd_, double dt_host, const double *dt_dev,
-              double beta, DragTau tp) {
+k_drag(GridDev g, TwoFluids tf, double dt_host, const double *dt_dev, double beta, DragDev dp,
+       DiffDev dd) {
   const double dt = dt_dev ? beta * *dt_dev : dt_host;
   const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)g.nb * nkr * njr * nir) return;
   const CellIdx c = decode(t, nir, njr, nkr, g.is, g.js, g.ks);
   Coords<GEOM> cc(g, c.b, c.k, c.j, c.i);
+  const double xv[3] = {cc.x1v(), cc.x2v(), cc.x3v()};
   const double hx[3] = {cc.hx1v(), cc.hx2v(), cc.hx3v()};
+  double xcyl0, e[3][3];
+  if (GEOM == AB200_CARTESIAN) {  // geometry.hpp:284-302
+    const double R = sqrt(xv[0] * xv[0] + xv[1] * xv[1]);
+    const double cp = xv[0] / (R + 1e-99), sp = xv[1] / (R + 1e-99);
+    e[0][0] = cp;  e[0][1] = -sp; e[0][2] = 0.0;
+    e[1][0] = sp;  e[1][1] = cp;  e[1][2] = 0.0;
+    e[2][0] = 0.0; e[2][1] = 0.0; e[2][2] = 1.0;
+    xcyl0 = R;
+  } else {
+    cc.to_cyl(xcyl0, e);
+  }
   const size_t off = ((size_t)c.k * g.nj + c.j) * g.ni + c.i;
-  const int Sg = fg.S, Sd = fd_.S;
+  const FluidDev &fg = tf.f[AB200_GAS], &fd_ = tf.f[AB200_DUST];
+  const int Sg = tf.on[AB200_GAS] ? fg.S : 0, Sd = tf.on[AB200_DUST] ? fd_.S : 0;
   const size_t eg = (size_t)c.b * fg.nvar, ed = (size_t)c.b * fd_.nvar;
   const double big = 1.79769313486231570815e+308;
-  const double bg = 0.0, bd = 0.0, vt = 0.0, vdt = 0.0;
+  const double dsc[3] = {1.0, g.ndim >= 2 ? 1.0 : 0.0, g.ndim == 3 ? 1.0 : 0.0};
+  double bg[3], bd[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double rg = damp_ramp(dt, xv[d], dp.g_ix[d], dp.g_ox[d], dp.g_irate[d], dp.g_orate[d],
+                                dp.xmin[d], dp.xmax[d]);
+    const double rd = damp_ramp(dt, xv[d], dp.d_ix[d], dp.d_ox[d], dp.d_irate[d], dp.d_orate[d],
+                                dp.xmin[d], dp.xmax[d]);
+    bg[d] = (d == 0) ? rg : dsc[d] * rg;
+    bd[d] = (d == 0) ? rd : dsc[d] * rd;
+  }
+  const bool use_visc = dp.damp_to_visc && dd.visc_type != AB200_VISC_NONE;
+  // ArtemisUtils::GetSpecificInternalEnergy of gas species n (artemis_utils.hpp:42-62)
+  auto cons_sie = [&](int n) {
+    const double u_d = dmax(fg.u0[eg + n][off], fg.dfloor);
+    const double rv1 = fg.u0[eg + Sg + 3 * n + 0][off] / hx[0];
+    const double rv2 = fg.u0[eg + Sg + 3 * n + 1][off] / hx[1];
+    const double rv3 = fg.u0[eg + Sg + 3 * n + 2][off] / hx[2];
+    const double ke = 0.5 * (sqr(rv1) + sqr(rv2) + sqr(rv3)) / u_d;
+    const double e_cons = fg.u0[eg + 4 * Sg + n][off];
+    const double ue_cons = e_cons - ke;
+    const double sie = (ue_cons > fg.de_switch * e_cons) ? ue_cons / u_d
+                                                         : fg.u0[eg + 5 * Sg + n][off] / u_d;
+    return dmax(sie, fg.siefloor);
+  };
+  if (dp.coupling == AB200_DRAG_SELF) {  // SelfDragSourceImpl, drag.hpp:150-291
+    for (int n = 0; n < Sg; ++n) {
+      const double dens = fg.u0[eg + n][off];
+      double vg[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) vg[d] = fg.u0[eg + Sg + 3 * n + d][off] / (hx[d] * dens);
+      const double sieg = cons_sie(n);
+      const double mu = use_visc ? visc_mu_val<GEOM>(cc, dd, fg.gm1, dens, sieg) : 0.0;
+      const double vR = -1.5 * mu / (xcyl0 * dens);
+      const double vd[3] = {e[0][0] * vR, e[1][0] * vR, e[2][0] * vR};
+      const double dm1 = -bg[0] * dens * (vg[0] - vd[0]) / (1.0 + bg[0]);
+      const double dm2 = -bg[1] * dens * (vg[1] - vd[1]) / (1.0 + bg[1]);
+      const double dm3 = -bg[2] * dens * (vg[2] - vd[2]) / (1.0 + bg[2]);
+      fg.u0[eg + Sg + 3 * n + 0][off] += hx[0] * dm1;
+      fg.u0[eg + Sg + 3 * n + 1][off] += hx[1] * dm2;
+      fg.u0[eg + Sg + 3 * n + 2][off] += hx[2] * dm3;
+      fg.u0[eg + 4 * Sg + n][off] += dm1 * (vg[0] + 0.5 * dm1 / dens) +
+                                     dm2 * (vg[1] + 0.5 * dm2 / dens) +
+                                     dm3 * (vg[2] + 0.5 * dm3 / dens);
+    }
+    for (int n = 0; n < Sd; ++n) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        double *pm = fd_.u0[ed + Sd + 3 * n + d] + off;
+        const double mom = *pm;
+        *pm = mom - bd[d] * mom / (1.0 + bd[d]);
+      }
+    }
+    return;
+  }
+  // SimpleDragSourceImpl, drag.hpp:296-482 (gas species 0 couples to every dust species)
   const double dg = fg.u0[eg][off];
   double vg[3], fd[3] = {0.0, 0.0, 0.0}, fvd[3] = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int d = 0; d < 3; ++d) vg[d] = fg.u0[eg + Sg + d][off] / (hx[d] * dg);
+  const double sieg = cons_sie(0);
+  const double mu = use_visc ? visc_mu_val<GEOM>(cc, dd, fg.gm1, dg, sieg) : 0.0;
+  const double vR = -1.5 * mu / (xcyl0 * dg);
+  const double vt[3] = {e[0][0] * vR, e[1][0] * vR, e[2][0] * vR};
+  const double vdt[3] = {0.0, 0.0, 0.0};
+  double vth = 0.0;
+  if (dp.model == AB200_DRAG_STOKES) vth = sqrt(8.0 / 3.14159265358979323846 * fg.gm1 * sieg);
+  auto stopping_time = [&](int n) {
+    if (dp.model == AB200_DRAG_STOKES) return dp.scale * dp.grain_density / dg * dp.sizes[n] / vth;
+    return dp.scale * dp.tau[n];
+  };
   for (int n = 0; n < Sd; ++n) {
     const double dens = fd_.u0[ed + n][off];
-    const double tc = tp.tau[n];
+    const double tc = stopping_time(n);
     const double alpha = dt * ((tc <= 0.0) ? big : 1.0 / tc);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       const double vd = fd_.u0[ed + Sd + 3 * n + d][off] / (hx[d] * dens);
-      const double rhop = dens * alpha / (1.0 + alpha + bd);
-      fd[d] += rhop * (1.0 + bd);
-      fvd[d] += rhop * (vd + bd * vdt);
+      const double rhop = dens * alpha / (1.0 + alpha + bd[d]);
+      fd[d] += rhop * (1.0 + bd[d]);
+      fvd[d] += rhop * (vd + bd[d] * vdt[d]);
     }
   }
   double vgp[3], delta_g[3] = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    vgp[d] = (dg * (vg[d] + bg * vt) + fvd[d]) / (dg * (1.0 + bg) + fd[d]);
+    vgp[d] = (dg * (vg[d] + bg[d] * vt[d]) + fvd[d]) / (dg * (1.0 + bg[d]) + fd[d]);
     fvd[d] = 0.;
   }
   for (int n = 0; n < Sd; ++n) {
     const double dens = fd_.u0[ed + n][off];
-    const double tc = tp.tau[n];
+    const double tc = stopping_time(n);
     const double alpha = dt * ((tc <= 0.0) ? big : 1.0 / tc);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       double *pm = fd_.u0[ed + Sd + 3 * n + d] + off;
       const double vd = *pm / (hx[d] * dens);
       double delta_d = 0.;
-      const double rhop = dens * alpha / (1.0 + alpha + bd);
-      const double delta = rhop * ((vgp[d] - vd + bd * (vgp[d] - vdt)));
+      const double rhop = dens * alpha / (1.0 + alpha + bd[d]);
+      const double delta = rhop * ((vgp[d] - vd + bd[d] * (vgp[d] - vdt[d])));
       delta_d += delta;
       delta_g[d] -= delta;
-      delta_d -= bd * dens / (1. + alpha + bd) * (vd - vdt + alpha * (vgp[d] - vdt));
-      fvd[d] += rhop * (vd - vt + bd * (vdt - vt));
+      delta_d -= bd[d] * dens / (1. + alpha + bd[d]) * (vd - vdt[d] + alpha * (vgp[d] - vdt[d]));
+      fvd[d] += rhop * (vd - vt[d] + bd[d] * (vdt[d] - vt[d]));
       *pm += hx[d] * delta_d;
     }
   }
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    const double prefac = dg * bg / (1.0 + bg + fd[d]);
-    delta_g[d] -= prefac * (dg * (vg[d] - vt) + fvd[d]);
+    const double prefac = dg * bg[d] / (1.0 + bg[d] + fd[d]);
+    delta_g[d] -= prefac * (dg * (vg[d] - vt[d]) + fvd[d]);
     fg.u0[eg + Sg + d][off] += hx[d] * delta_g[d];
     fg.u0[eg + 4 * Sg][off] += 0.5 * (vg[d] + vgp[d]) * delta_g[d];
   }
@@ -484,29 +579,76 @@ int ab200_shearing_box(ab200_ctx *c, double dt, double omega, double qshear) {
   return shearing_impl(c, dt, nullptr, 0.0, omega, qshear);
 }
 
-static int drag_impl(ab200_ctx *c, double dt, const double *dt_dev, double beta, int ntau,
-                     const double *tau) {
+static int drag_impl(ab200_ctx *c, double dt, const double *dt_dev, double beta,
+                     const ab200_drag_desc *d) {
   AB_ENTER_S(c)
-  AB_REQUIRE(c->fl[0].bound && c->fl[1].bound, AB200_ESTATE,
-             "ab200_drag_simple: gas and dust must both be bound");
-  AB_REQUIRE(tau && ntau == c->fl[1].d.S, AB200_EINVAL,
-             "ab200_drag_simple: one stopping time per dust species");
-  AB_REQUIRE(ntau <= kMaxDustSpecies, AB200_EINVAL, "ab200_drag_simple: too many dust species");
-  AB_REQUIRE(c->fl[0].d.S == 1, AB200_EINVAL,
-             "ab200_drag_simple: the reference couples gas species 0 only (drag.hpp:387)");
-  DragTau tp{};
-  for (int n = 0; n < ntau; ++n) tp.tau[n] = tau[n];
+  AB_REQUIRE(d != nullptr, AB200_EINVAL, "ab200_drag_source: null descriptor");
+  AB_REQUIRE(d->coupling == AB200_DRAG_SIMPLE_DUST || d->coupling == AB200_DRAG_SELF, AB200_EINVAL,
+             "Invalid drag model!");
+  AB_REQUIRE(d->model == AB200_DRAG_CONSTANT || d->model == AB200_DRAG_STOKES, AB200_EINVAL,
+             "bad type for stopping time model");
+  const bool gas = c->fl[0].bound, dust = c->fl[1].bound;
+  if (d->coupling == AB200_DRAG_SIMPLE_DUST) {
+    // src/drag/drag.cpp:76-80, drag.hpp:387
+    AB_REQUIRE(gas && dust, AB200_ESTATE, "drag type simple_dust requires do_gas = do_dust = true");
+    AB_REQUIRE(c->fl[0].d.S == 1, AB200_EINVAL,
+               "ab200_drag_source: simple_dust couples gas species 0 only (drag.hpp:387)");
+    AB_REQUIRE(c->fl[1].d.S <= kMaxDustSpecies, AB200_EINVAL, "ab200_drag_source: too many dust species");
+  }
+  AB_REQUIRE(gas || dust, AB200_ESTATE, "source term: no fluid bound");
+  for (int k = 0; k < 3; ++k) {  // drag.hpp:101-106
+    AB_REQUIRE(d->g_irate[k] >= 0.0 && d->d_irate[k] >= 0.0, AB200_EINVAL,
+               "The damping rate in the x1 direction must be >= 0");
+    AB_REQUIRE(d->g_ix[k] <= d->g_ox[k] && d->d_ix[k] <= d->d_ox[k], AB200_EINVAL,
+               "The damping bounds must have inner_x1 <= outer_x1");
+  }
+  AB_REQUIRE(!d->g_damp_to_visc || (c->has_diffusion && c->diffusion.visc_type != AB200_VISC_NONE),
+             AB200_ESTATE, "The chosen viscosity model does not work with damping");
+  TwoFluids tf{};
+  for (int f = 0; f < 2; ++f) {
+    tf.on[f] = c->fl[f].bound ? 1 : 0;
+    if (tf.on[f]) tf.f[f] = c->fl[f].d;  // the conserved state only: primitives are not read
+  }
+  DragDev dp{};
+  dp.coupling = d->coupling; dp.model = d->model; dp.damp_to_visc = d->g_damp_to_visc;
+  dp.scale = d->scale; dp.grain_density = d->grain_density;
+  for (int n = 0; n < kMaxDustSpecies; ++n) { dp.tau[n] = d->tau[n]; dp.sizes[n] = d->sizes[n]; }
+  for (int k = 0; k < 3; ++k) {
+    dp.g_ix[k] = d->g_ix[k]; dp.g_ox[k] = d->g_ox[k];
+    dp.g_irate[k] = d->g_irate[k]; dp.g_orate[k] = d->g_orate[k];
+    dp.d_ix[k] = d->d_ix[k]; dp.d_ox[k] = d->d_ox[k];
+    dp.d_irate[k] = d->d_irate[k]; dp.d_orate[k] = d->d_orate[k];
+    dp.xmin[k] = d->xmin[k]; dp.xmax[k] = d->xmax[k];
+  }
+  const DiffDev dd = c->has_diffusion ? diff_dev(c) : DiffDev{};
   const GridDev &g = c->g;
   int rc = dispatch_geom_s(g.geom, [&](auto G) {
-    k_drag_simple<decltype(G)::value><<<grid_s(g), kThreads, 0, c->stream>>>(g, c->fl[0].d, c->fl[1].d, dt, dt_dev, beta, tp);
+    k_drag<decltype(G)::value><<<grid_s(g), kThreads, 0, c->stream>>>(g, tf, dt, dt_dev, beta, dp, dd);
     return AB200_OK;
   });
   c->launches++;
   AB_CUDA(cudaGetLastError());
   return rc;
 }
+int ab200_drag_source(ab200_ctx *c, double dt, const ab200_drag_desc *d) {
+  return drag_impl(c, dt, nullptr, 0.0, d);
+}
+// <dust/stopping_time> type = constant, no damping zones (inputs/drag/simple_drag.in)
+static ab200_drag_desc constant_drag(int ntau, const double *tau) {
+  ab200_drag_desc d{};
+  d.coupling = AB200_DRAG_SIMPLE_DUST; d.model = AB200_DRAG_CONSTANT; d.scale = 1.0;
+  for (int n = 0; n < ntau && n < kMaxDustSpecies; ++n) d.tau[n] = tau[n];
+  const double big = 1.79769313486231570815e+308;
+  for (int k = 0; k < 3; ++k) { d.g_ix[k] = d.d_ix[k] = -big; d.g_ox[k] = d.d_ox[k] = big; }
+  return d;
+}
 int ab200_drag_simple(ab200_ctx *c, double dt, int ntau, const double *tau) {
-  return drag_impl(c, dt, nullptr, 0.0, ntau, tau);
+  AB_REQUIRE(c, AB200_EINVAL, "null context");
+  AB_REQUIRE(tau && c->fl[1].bound && ntau == c->fl[1].d.S, AB200_EINVAL,
+             "ab200_drag_simple: one stopping time per dust species");
+  AB_REQUIRE(ntau <= kMaxDustSpecies, AB200_EINVAL, "ab200_drag_simple: too many dust species");
+  const ab200_drag_desc d = constant_drag(ntau, tau);
+  return drag_impl(c, dt, nullptr, 0.0, &d);
 }
 
 
@@ -583,8 +725,10 @@ int ab200_configure_sources(ab200_ctx *c, const ab200_sources_desc *src) {
              "ab200_configure_sources: one gravity type (gravity.cpp:68-88)");
   AB_REQUIRE(!(src->shearing_box && src->rotating_frame), AB200_EINVAL,
              "ab200_configure_sources: shearing box (Cartesian) or rotating frame (curvilinear)");
+  AB_REQUIRE(!(src->drag && src->drag_model), AB200_EINVAL,
+             "ab200_configure_sources: drag (constant tau) or drag_model (full descriptor)");
   c->has_sources = src->gravity || src->shearing_box || src->drag || src->point_mass ||
-                   src->rotating_frame;
+                   src->rotating_frame || src->drag_model;
   return AB200_OK;
 }
 
@@ -609,7 +753,12 @@ int run_stage(ab200_ctx *c, double g0, double g1, double beta, int pcm, int firs
   if (s.point_mass) AB_TRY(point_mass_impl(c, 0.0, c->d_time, beta, &s.pm));
   if (s.shearing_box) AB_TRY(shearing_impl(c, 0.0, c->d_time, beta, s.omega, s.qshear));
   if (s.rotating_frame) AB_TRY(rotating_frame_impl(c, 0.0, c->d_time, beta, s.rf_omega));
-  if (s.drag) AB_TRY(drag_impl(c, 0.0, c->d_time, beta, s.ntau, s.tau));
+  if (s.drag_model) {
+    AB_TRY(drag_impl(c, 0.0, c->d_time, beta, &s.drag_desc));
+  } else if (s.drag) {
+    const ab200_drag_desc d = constant_drag(s.ntau, s.tau);
+    AB_TRY(drag_impl(c, 0.0, c->d_time, beta, &d));
+  }
   return ab200_finish_stage(c, last ? AB200_STAGE_REDUCE_DT : 0);
 }
 }  // namespace ab200

@@ -192,7 +192,8 @@ class ArtemisDriver:
         """ExternalGravity -> RotatingFrameForce -> DragSource, the reference's task order
         (src/artemis_driver.cpp:222-243)."""
         md, req = self.md, self._require
-        order = {"gravity": 0, "point_mass": 0, "shearing_box": 1, "rotating_frame": 1, "drag": 2}
+        order = {"gravity": 0, "point_mass": 0, "shearing_box": 1, "rotating_frame": 1, "drag": 2,
+                 "drag_model": 2}
         for src in sorted(self.sources, key=lambda t: order[t[0]]):
             if src[0] == "point_mass":
                 pm = capi.PointMassDesc(*[float(v) for v in src[1:8]])
@@ -207,6 +208,9 @@ class ArtemisDriver:
             elif src[0] == "shearing_box":
                 req(_task(md, "ab200_shearing_box", float(bdt), float(src[1]), float(src[2])),
                     md, "RotatingFrame::ShearingBoxImpl")
+            elif src[0] == "drag_model":    # ("drag_model", capi.DragDesc)
+                req(_task(md, "ab200_drag_source", float(bdt), C.byref(src[1])), md,
+                    "Drag::DragSource")
             elif src[0] == "drag":
                 tau = np.ascontiguousarray(src[1], dtype=np.float64)
                 req(_task(md, "ab200_drag_simple", float(bdt), len(tau), tau.ctypes.data_as(_DP)),

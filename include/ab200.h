@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AB200_ABI_VERSION 8
+#define AB200_ABI_VERSION 9
 
 /* src/artemis.hpp:78-105 */
 enum { AB200_CARTESIAN = 0, AB200_CYLINDRICAL = 1, AB200_SPHERICAL1D = 2,
@@ -209,10 +209,31 @@ int ab200_finish_stage(ab200_ctx *ctx, int flags);
  *                          `sink` (rate `sink_rate`; 0 disables it)
  *   ab200_drag_simple      Drag::SimpleDragSourceImpl      src/drag/drag.hpp:296-482 with constant
  *                          stopping times tau[n] per dust species (<drag/dust> type = constant),
- *                          no damping zones and no viscous target velocity (inputs/drag/simple_drag.in) */
+ *                          no damping zones and no viscous target velocity (inputs/drag/simple_drag.in)
+ *   ab200_drag_source      Drag::DragSource<GEOM> in full (see ab200_drag_desc below) */
 int ab200_uniform_gravity(ab200_ctx *ctx, double dt, double gx1, double gx2, double gx3);
 int ab200_shearing_box(ab200_ctx *ctx, double dt, double omega, double qshear);
 int ab200_drag_simple(ab200_ctx *ctx, double dt, int ntau, const double *tau);
+/* Drag::DragSource<GEOM> in full (src/drag/drag.cpp:88-165, src/drag/drag.hpp:144-482): the
+ * parameters of <drag>, <dust/stopping_time>, <dust> sizes / grain_density, <gas/damping>,
+ * <dust/damping> and the mesh bounds the damping ramps are normalised with.  Unused damping
+ * directions: inner = -DBL_MAX, outer = +DBL_MAX, rates 0 (the deck defaults).  With
+ * g_damp_to_visc the gas is damped towards the viscous inflow velocity -1.5 nu / R of the
+ * viscosity configured through ab200_configure_diffusion (AB200_ESTATE without one). */
+#define AB200_DRAG_SIMPLE_DUST 0  /* <drag> type = simple_dust: implicit gas-dust coupling */
+#define AB200_DRAG_SELF 1         /* type = self: damping zones only                      */
+#define AB200_DRAG_CONSTANT 0     /* <dust/stopping_time> type = constant                  */
+#define AB200_DRAG_STOKES 1       /* type = stokes: tau = scale rho_s s / (rho_g v_th)     */
+typedef struct ab200_drag_desc {
+  int coupling, model;
+  double tau[16], scale;
+  double grain_density, sizes[16];
+  double g_ix[3], g_ox[3], g_irate[3], g_orate[3];
+  int g_damp_to_visc;
+  double d_ix[3], d_ox[3], d_irate[3], d_orate[3];
+  double xmin[3], xmax[3];
+} ab200_drag_desc;
+int ab200_drag_source(ab200_ctx *ctx, double dt, const ab200_drag_desc *drag);
 typedef struct ab200_point_mass_desc {
   double gm;          /* <gravity/point> gm                                  */
   double x, y, z;     /* Cartesian position of the mass                      */
@@ -231,6 +252,7 @@ typedef struct ab200_sources_desc {
   int drag;          int ntau; double tau[16]; /* Drag::SimpleDragSourceImpl      */
   int point_mass;    ab200_point_mass_desc pm; /* Gravity::PointMassGravity (instead of `gravity`) */
   int rotating_frame; double rf_omega;       /* RotatingFrame::RotatingFrameImpl (curvilinear) */
+  int drag_model;    ab200_drag_desc drag_desc; /* Drag::DragSource in full (instead of `drag`) */
 } ab200_sources_desc;
 int ab200_configure_sources(ab200_ctx *ctx, const ab200_sources_desc *src);
 

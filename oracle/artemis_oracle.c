@@ -1583,11 +1583,9 @@ static inline void g_dh(int geom, const bbox_t *b, double dh[3][3]) {
 }
 #define PR(v, kk, jj, ii) prim[IDX(g, nvar, b, (v), (kk), (jj), (ii))]
 /* DiffusionCoeff<viscosity_plaw / viscosity_alpha>, diffusion_coeff.hpp:178-268 */
-static double visc_mu(const ao_grid *g, const ao_fluid *f, const ao_diffusion *dd, const double *prim,
-                      int b, int n, int k, int j, int i) {
-  const int S = f->nspecies, nvar = 6 * S;
+static double visc_mu_val(const ao_grid *g, const ao_fluid *f, const ao_diffusion *dd, int b, int k,
+                          int j, int i, double dens, double sie) {
   const dcell_t c = dcell(g, b, k, j, i);
-  const double dens = PR(n, k, j, i);
   if (dd->visc_type == AO_VISC_PLAW) {
     double xs[3], e[3][3];
     g_to_cyl(g->geom, c.xv, xs, e);
@@ -1595,9 +1593,13 @@ static double visc_mu(const ao_grid *g, const ao_fluid *f, const ao_diffusion *d
   }
   const double rs = g_sph_radius(g->geom, c.xv);
   const double Omk = dd->omega0 * pow(rs / dd->r0, -1.5);
-  const double sie = PR(5 * S + n, k, j, i);
   const double blk = dmax(0.0, (f->gm1 + 1) * f->gm1 * dens * sie);
   return dd->alpha * blk / Omk;
+}
+static double visc_mu(const ao_grid *g, const ao_fluid *f, const ao_diffusion *dd, const double *prim,
+                      int b, int n, int k, int j, int i) {
+  const int S = f->nspecies, nvar = 6 * S;
+  return visc_mu_val(g, f, dd, b, k, j, i, PR(n, k, j, i), PR(5 * S + n, k, j, i));
 }
 /* DiffusionCoeff<conductivity_plaw / thermaldiff_plaw>, diffusion_coeff.hpp:270-384 */
 static double cond_kappa(const ao_grid *g, const ao_fluid *f, const ao_diffusion *dd,
@@ -1858,6 +1860,153 @@ double ao_diffusion_dt(const ao_grid *g, const ao_fluid *gas, const double *gpri
   if (dd->visc_type != AO_DIFF_NONE) dtv = dtv / (2.0 * g->ndim);
   if (dd->cond_type != AO_COND_NONE) dtc = dtc / (2.0 * g->ndim);
   return dmin(dtv, dtc);
+}
+
+/* quadratic damping ramp of one direction (drag.hpp:195-199): dt * (irate * [x < ix] *
+ * ((x - ix) / (ix - xmin))^2 + orate * [x > ox] * ((x - ox) / (ox - xmax))^2) */
+static inline double damp_ramp(double dt, double x, double ix, double ox, double irate,
+                               double orate, double xmin, double xmax) {
+  const double ri = (x - ix) / (ix - xmin), ro = (x - ox) / (ox - xmax);
+  return dt * (irate * ((x < ix) * (ri * ri)) + orate * ((x > ox) * (ro * ro)));
+}
+/* ArtemisUtils::GetSpecificInternalEnergy, src/utils/artemis_utils.hpp:42-62 */
+static inline double cons_sie(const double *ug, size_t cells, size_t o, int S, int n,
+                              const double hx[3], double de_switch, double dflr, double sieflr) {
+  const double u_d = dmax(ug[(size_t)n * cells + o], dflr);
+  const double rv1 = ug[(size_t)(S + 3 * n + 0) * cells + o] / hx[0];
+  const double rv2 = ug[(size_t)(S + 3 * n + 1) * cells + o] / hx[1];
+  const double rv3 = ug[(size_t)(S + 3 * n + 2) * cells + o] / hx[2];
+  const double ke = 0.5 * (rv1 * rv1 + rv2 * rv2 + rv3 * rv3) / u_d;
+  const double e_cons = ug[(size_t)(4 * S + n) * cells + o];
+  const double ue_cons = e_cons - ke;
+  const double sie = (ue_cons > de_switch * e_cons) ? ue_cons / u_d
+                                                    : ug[(size_t)(5 * S + n) * cells + o] / u_d;
+  return dmax(sie, sieflr);
+}
+
+void ao_drag_source(const ao_grid *g, const ao_fluid *gas, double *gcons, const ao_fluid *dust,
+                    double *dcons, const ao_drag *dp, const ao_diffusion *dd, double dt) {
+  const size_t cells = (size_t)g->ni * g->nj * g->nk;
+  const int geom = g->geom;
+  const int Sg = gas ? gas->nspecies : 0, Sd = dust ? dust->nspecies : 0;
+  const double big = 1.79769313486231570815e+308; /* Big<Real>() */
+  const int multi_d = (g->ndim >= 2), three_d = (g->ndim == 3);
+  const int use_visc = dp->g_damp_to_visc && dd && dd->visc_type != AO_DIFF_NONE;
+#pragma omp parallel for collapse(3) schedule(static)
+  for (int b = 0; b < g->nb; ++b)
+    for (int k = g->ks; k <= g->ke; ++k)
+      for (int j = g->js; j <= g->je; ++j)
+        for (int i = g->is; i <= g->ie; ++i) {
+          const bbox_t bb = make_bbox(g->xmin + 3 * b, g->dx + 3 * b, k, j, i);
+          const double xv[3] = {g_x1v(geom, &bb), g_x2v(geom, &bb), g_x3v(geom, &bb)};
+          const double hx[3] = {g_hx1v(geom, &bb), g_hx2v(geom, &bb), g_hx3v(geom, &bb)};
+          double xcyl[3], e[3][3];
+          g_to_cyl(geom, xv, xcyl, e);
+          const size_t o = ((size_t)k * g->nj + j) * g->ni + i;
+          double *ug = gas ? gcons + (size_t)b * 6 * Sg * cells : NULL;
+          double *ud = dust ? dcons + (size_t)b * 4 * Sd * cells : NULL;
+          const double dsc[3] = {1.0, multi_d, three_d};
+          double bg[3], bd[3];
+          for (int d = 0; d < 3; ++d) {
+            const double rg = damp_ramp(dt, xv[d], dp->g_ix[d], dp->g_ox[d], dp->g_irate[d],
+                                        dp->g_orate[d], dp->xmin[d], dp->xmax[d]);
+            const double rd = damp_ramp(dt, xv[d], dp->d_ix[d], dp->d_ox[d], dp->d_irate[d],
+                                        dp->d_orate[d], dp->xmin[d], dp->xmax[d]);
+            /* fx1 = dt * (..); fx2 = multi_d * dt * (..); fx3 = three_d * dt * (..) */
+            bg[d] = (d == 0) ? rg : dsc[d] * rg;
+            bd[d] = (d == 0) ? rd : dsc[d] * rd;
+          }
+          if (dp->coupling == AO_DRAG_SELF) { /* SelfDragSourceImpl, drag.hpp:150-291 */
+            for (int n = 0; n < Sg; ++n) {
+              const double dens = ug[(size_t)n * cells + o];
+              const double vg[3] = {ug[(size_t)(Sg + 3 * n + 0) * cells + o] / (hx[0] * dens),
+                                    ug[(size_t)(Sg + 3 * n + 1) * cells + o] / (hx[1] * dens),
+                                    ug[(size_t)(Sg + 3 * n + 2) * cells + o] / (hx[2] * dens)};
+              const double sieg = cons_sie(ug, cells, o, Sg, n, hx, gas->de_switch, gas->dfloor,
+                                           gas->siefloor);
+              const double mu = use_visc ? visc_mu_val(g, gas, dd, b, k, j, i, dens, sieg) : 0.0;
+              const double vR = -1.5 * mu / (xcyl[0] * dens);
+              const double vd[3] = {e[0][0] * vR, e[1][0] * vR, e[2][0] * vR};
+              const double dm1 = -bg[0] * dens * (vg[0] - vd[0]) / (1.0 + bg[0]);
+              const double dm2 = -bg[1] * dens * (vg[1] - vd[1]) / (1.0 + bg[1]);
+              const double dm3 = -bg[2] * dens * (vg[2] - vd[2]) / (1.0 + bg[2]);
+              ug[(size_t)(Sg + 3 * n + 0) * cells + o] += hx[0] * dm1;
+              ug[(size_t)(Sg + 3 * n + 1) * cells + o] += hx[1] * dm2;
+              ug[(size_t)(Sg + 3 * n + 2) * cells + o] += hx[2] * dm3;
+              ug[(size_t)(4 * Sg + n) * cells + o] += dm1 * (vg[0] + 0.5 * dm1 / dens) +
+                                                      dm2 * (vg[1] + 0.5 * dm2 / dens) +
+                                                      dm3 * (vg[2] + 0.5 * dm3 / dens);
+            }
+            for (int n = 0; n < Sd; ++n)
+              for (int d = 0; d < 3; ++d) {
+                double *m = ud + (size_t)(Sd + 3 * n + d) * cells + o;
+                const double mom = *m;
+                *m -= bd[d] * mom / (1.0 + bd[d]);
+              }
+            continue;
+          }
+          /* SimpleDragSourceImpl, drag.hpp:296-482 */
+          const double dg = ug[o];
+          const double vg[3] = {ug[(size_t)(Sg + 0) * cells + o] / (hx[0] * dg),
+                                ug[(size_t)(Sg + 1) * cells + o] / (hx[1] * dg),
+                                ug[(size_t)(Sg + 2) * cells + o] / (hx[2] * dg)};
+          const double sieg = cons_sie(ug, cells, o, Sg, 0, hx, gas->de_switch, gas->dfloor,
+                                       gas->siefloor);
+          const double mu = use_visc ? visc_mu_val(g, gas, dd, b, k, j, i, dg, sieg) : 0.0;
+          const double vR = -1.5 * mu / (xcyl[0] * dg);
+          const double vt[3] = {e[0][0] * vR, e[1][0] * vR, e[2][0] * vR};
+          const double vdt[3] = {0.0, 0.0, 0.0};
+          double vth = 0.0;
+          if (dp->model == AO_DRAG_STOKES) vth = sqrt(8.0 / M_PI * gas->gm1 * sieg);
+          double fd[3] = {0.0, 0.0, 0.0}, fvd[3] = {0.0, 0.0, 0.0};
+          for (int n = 0; n < Sd; ++n) {
+            const double dens = ud[(size_t)n * cells + o];
+            const double vd[3] = {ud[(size_t)(Sd + 3 * n + 0) * cells + o] / (hx[0] * dens),
+                                  ud[(size_t)(Sd + 3 * n + 1) * cells + o] / (hx[1] * dens),
+                                  ud[(size_t)(Sd + 3 * n + 2) * cells + o] / (hx[2] * dens)};
+            double tc = (dp->model == AO_DRAG_STOKES) ? dp->scale : dp->scale * dp->tau[n];
+            if (dp->model == AO_DRAG_STOKES)
+              tc = dp->scale * dp->grain_density / dg * dp->sizes[n] / vth;
+            const double alpha = dt * ((tc <= 0.0) ? big : 1.0 / tc);
+            for (int d = 0; d < 3; d++) {
+              const double rhop = dens * alpha / (1.0 + alpha + bd[d]);
+              fd[d] += rhop * (1.0 + bd[d]);
+              fvd[d] += rhop * (vd[d] + bd[d] * vdt[d]);
+            }
+          }
+          double vgp[3];
+          for (int d = 0; d < 3; d++)
+            vgp[d] = (dg * (vg[d] + bg[d] * vt[d]) + fvd[d]) / (dg * (1.0 + bg[d]) + fd[d]);
+          double delta_g[3] = {0.0, 0.0, 0.0};
+          for (int d = 0; d < 3; d++) fvd[d] = 0.;
+          for (int n = 0; n < Sd; ++n) {
+            const double dens = ud[(size_t)n * cells + o];
+            const double vd[3] = {ud[(size_t)(Sd + 3 * n + 0) * cells + o] / (hx[0] * dens),
+                                  ud[(size_t)(Sd + 3 * n + 1) * cells + o] / (hx[1] * dens),
+                                  ud[(size_t)(Sd + 3 * n + 2) * cells + o] / (hx[2] * dens)};
+            double tc = (dp->model == AO_DRAG_STOKES) ? dp->scale : dp->scale * dp->tau[n];
+            if (dp->model == AO_DRAG_STOKES)
+              tc = dp->scale * dp->grain_density / dg * dp->sizes[n] / vth;
+            const double alpha = dt * ((tc <= 0.0) ? big : 1.0 / tc);
+            for (int d = 0; d < 3; d++) {
+              double delta_d = 0.;
+              const double rhop = dens * alpha / (1.0 + alpha + bd[d]);
+              const double delta = rhop * ((vgp[d] - vd[d] + bd[d] * (vgp[d] - vdt[d])));
+              delta_d += delta;
+              delta_g[d] -= delta;
+              delta_d -= bd[d] * dens / (1. + alpha + bd[d]) *
+                         (vd[d] - vdt[d] + alpha * (vgp[d] - vdt[d]));
+              fvd[d] += rhop * (vd[d] - vt[d] + bd[d] * (vdt[d] - vt[d]));
+              ud[(size_t)(Sd + 3 * n + d) * cells + o] += hx[d] * delta_d;
+            }
+          }
+          for (int d = 0; d < 3; d++) {
+            const double prefac = dg * bg[d] / (1.0 + bg[d] + fd[d]);
+            delta_g[d] -= prefac * (dg * (vg[d] - vt[d]) + fvd[d]);
+            ug[(size_t)(Sg + d) * cells + o] += hx[d] * delta_g[d];
+            ug[(size_t)(4 * Sg) * cells + o] += 0.5 * (vg[d] + vgp[d]) * delta_g[d];
+          }
+        }
 }
 
 /* RotatingFrame::ShearingBoxImpl, src/rotating_frame/rotating_frame_impl.hpp:28-94

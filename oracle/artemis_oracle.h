@@ -125,6 +125,8 @@ void ao_restrict_average(const ao_refine_geom *r, int nvar, const double *fine, 
 void ao_prolongate_minmod(const ao_refine_geom *r, int nvar, const double *coarse, double *fine,
                           const int *box);
 
+struct ao_diffusion_s;
+typedef struct ao_diffusion_s ao_diffusion_fwd;
 /* ---- pointwise source terms between FluxSource and SetAuxillaryFields ----
  * gas / dust may be NULL (fluid absent).  They read the stage-start primitives and update the
  * conserved state of interior zones in place. */
@@ -152,6 +154,25 @@ void ao_rotating_frame(const ao_grid *g, const ao_fluid *gas, double *gcons,
 void ao_drag_simple(const ao_grid *g, const ao_fluid *gas, double *gcons, const ao_fluid *dust,
                     double *dcons, double dt, const double *tau);
 
+/* Drag::DragSource<GEOM> in full (src/drag/drag.cpp:88-165 dispatch, src/drag/drag.hpp:144-482):
+ * coupling simple_dust (implicit gas-dust drag, constant or Stokes stopping times) or self
+ * (damping zones only); quadratic damping ramps of gas and dust towards rest or, for the gas with
+ * damp_to_visc, towards the viscous inflow velocity -1.5 nu / R. */
+enum { AO_DRAG_SIMPLE_DUST = 0, AO_DRAG_SELF = 1 };
+enum { AO_DRAG_CONSTANT = 0, AO_DRAG_STOKES = 1 };
+typedef struct {
+  int coupling, model;
+  double tau[16], scale;             /* <dust/stopping_time> tau (constant), scale          */
+  double grain_density, sizes[16];   /* <dust> grain_density, sizes (Stokes)                */
+  double g_ix[3], g_ox[3], g_irate[3], g_orate[3]; /* <gas/damping> inner_x*, outer_x*, rates */
+  int g_damp_to_visc;
+  double d_ix[3], d_ox[3], d_irate[3], d_orate[3]; /* <dust/damping>                        */
+  double xmin[3], xmax[3];           /* <parthenon/mesh> x*min, x*max                       */
+} ao_drag;
+/* dd: the viscosity parameters (read only with g_damp_to_visc; may be NULL otherwise) */
+void ao_drag_source(const ao_grid *g, const ao_fluid *gas, double *gcons, const ao_fluid *dust,
+                    double *dcons, const ao_drag *dp, const ao_diffusion_fwd *dd, double dt);
+
 /* ---- diffusion operators: src/utils/diffusion/{diffusion,diffusion_coeff,
  * momentum_diffusion,thermal_diffusion}.hpp driven by Gas::{ZeroDiffusionFlux,ViscousFlux,
  * ThermalFlux,DiffusionUpdate} (src/gas/gas.cpp:524-642) and the diffusive timestep limits of
@@ -159,7 +180,7 @@ void ao_drag_simple(const ao_grid *g, const ao_fluid *gas, double *gcons, const 
 enum { AO_DIFF_NONE = 0, AO_VISC_PLAW = 1, AO_VISC_ALPHA = 2 };
 enum { AO_COND_NONE = 0, AO_COND_CONDUCTIVITY = 1, AO_COND_DIFFUSIVITY = 2 };
 enum { AO_AVG_ARITHMETIC = 0, AO_AVG_HARMONIC = 1 };
-typedef struct {
+typedef struct ao_diffusion_s {
   int visc_type, visc_avg;           /* DiffCoeffParams of <gas/viscosity>            */
   double nu, eta, r0, r_exp;         /*   plaw: nu_s, eta_bulk, problem/r0, r_exp      */
   double alpha, omega0;              /*   alpha: alpha, Omega0 = sqrt(gm / r0^3)       */

@@ -100,6 +100,43 @@ class FluidState:
         self.vec_dir = [((v - S) % 3 + 1) if S <= v < 4 * S else 0 for v in self.ghost_vars]
 
 
+class Drag(C.Structure):
+    """ao_drag (artemis_oracle.h): <drag>, <dust/stopping_time>, <gas|dust/damping> parameters."""
+    _fields_ = [("coupling", C.c_int), ("model", C.c_int), ("tau", C.c_double * 16),
+                ("scale", C.c_double), ("grain_density", C.c_double), ("sizes", C.c_double * 16),
+                ("g_ix", C.c_double * 3), ("g_ox", C.c_double * 3), ("g_irate", C.c_double * 3),
+                ("g_orate", C.c_double * 3), ("g_damp_to_visc", C.c_int),
+                ("d_ix", C.c_double * 3), ("d_ox", C.c_double * 3), ("d_irate", C.c_double * 3),
+                ("d_orate", C.c_double * 3), ("xmin", C.c_double * 3), ("xmax", C.c_double * 3)]
+
+
+def make_drag(mesh, coupling="simple_dust", model="constant", tau=(), scale=1.0,
+              grain_density=1.0, sizes=(), gas_damping=None, dust_damping=None,
+              damp_to_visc=False):
+    """gas_damping / dust_damping: dict(inner=(x1,x2,x3), outer=(...), inner_rate=(...),
+    outer_rate=(...)) with None entries = the deck defaults (-Big / +Big bounds, rate 0)."""
+    big = float(np.finfo(np.float64).max)
+    d = Drag()
+    d.coupling = {"simple_dust": 0, "self": 1}[coupling]
+    d.model = {"constant": 0, "stokes": 1}[model]
+    d.scale, d.grain_density = scale, grain_density
+    for n, v in enumerate(tau):
+        d.tau[n] = float(v)
+    for n, v in enumerate(sizes):
+        d.sizes[n] = float(v)
+    for pre, dm in (("g", gas_damping), ("d", dust_damping)):
+        dm = dm or {}
+        for k in range(3):
+            getattr(d, pre + "_ix")[k] = float((dm.get("inner") or (-big,) * 3)[k])
+            getattr(d, pre + "_ox")[k] = float((dm.get("outer") or (big,) * 3)[k])
+            getattr(d, pre + "_irate")[k] = float((dm.get("inner_rate") or (0.0,) * 3)[k])
+            getattr(d, pre + "_orate")[k] = float((dm.get("outer_rate") or (0.0,) * 3)[k])
+    d.g_damp_to_visc = int(damp_to_visc)
+    for k in range(3):
+        d.xmin[k], d.xmax[k] = float(mesh.xmin[k]), float(mesh.xmax[k])
+    return d
+
+
 class Diffusion(C.Structure):
     """ao_diffusion (artemis_oracle.h): viscosity / conduction parameters of the gas."""
     _fields_ = [("visc_type", C.c_int), ("visc_avg", C.c_int), ("nu", C.c_double),
@@ -223,7 +260,8 @@ class OracleSim:
             return
         L, pre = self._src_lib()
         fg, fd, args = self._both()
-        order = {"gravity": 0, "point_mass": 0, "shearing_box": 1, "rotating_frame": 1, "drag": 2}
+        order = {"gravity": 0, "point_mass": 0, "shearing_box": 1, "rotating_frame": 1, "drag": 2,
+                 "drag_model": 2}
         for src in sorted(self.sources, key=lambda t: order[t[0]]):
             if src[0] == "point_mass":
                 pm = np.ascontiguousarray(src[1:8], dtype=np.float64)
@@ -245,10 +283,12 @@ class OracleSim:
             elif src[0] == "shearing_box":
                 getattr(L, pre + "_shearing_box")(C.byref(self.g), *args, C.c_double(dt),
                                                  C.c_double(src[1]), C.c_double(src[2]))
-            elif src[0] == "drag":
-                tau = np.ascontiguousarray(src[1], dtype=np.float64)
-                self.L.ao_drag_simple(C.byref(self.g), args[0], args[2], args[3], args[5],
-                                      C.c_double(dt), _p(tau))
+            elif src[0] in ("drag", "drag_model"):
+                # ("drag", [tau]) = constant stopping times, no damping; ("drag_model", Drag)
+                dp = make_drag(self.mesh, tau=src[1]) if src[0] == "drag" else src[1]
+                dd = C.byref(self.diffusion) if self.diffusion is not None else None
+                getattr(L, pre + "_drag_source")(C.byref(self.g), args[0], args[2], args[3],
+                                                 args[5], C.byref(dp), dd, C.c_double(dt))
 
     # ---- task functions (names follow the reference) ---------------------------------
     def CalculateFluxes(self, fs, pcm):

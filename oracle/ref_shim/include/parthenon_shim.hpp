@@ -164,19 +164,54 @@ inline int shim_type_id() {
 }
 constexpr int kShimMaxTypes = 64;
 
-class StateDescriptor {
+// Params: the type-erased key/value store of a package (P:interface/params.hpp)
+class Params {
  public:
   template <class T>
-  const T &Param(const std::string &key) const {
+  void Add(const std::string &key, T v) { params_[key] = std::move(v); }
+  template <class T>
+  const T &Get(const std::string &key) const {
     auto it = params_.find(key);
     if (it == params_.end()) shim_fail(("missing param " + key).c_str(), __FILE__, __LINE__);
-    return *std::any_cast<T>(&it->second);
+    const T *p = std::any_cast<T>(&it->second);
+    if (!p) shim_fail(("param type mismatch " + key).c_str(), __FILE__, __LINE__);
+    return *p;
   }
-  template <class T>
-  void AddParam(const std::string &key, T v) { params_[key] = std::move(v); }
 
  private:
   std::map<std::string, std::any> params_;
+};
+
+class StateDescriptor {
+ public:
+  StateDescriptor() = default;
+  explicit StateDescriptor(const std::string &) {}
+  template <class T>
+  const T &Param(const std::string &key) const { return params_.Get<T>(key); }
+  template <class T>
+  void AddParam(const std::string &key, T v) { params_.Add(key, std::move(v)); }
+  Params &AllParams() { return params_; }
+
+ private:
+  Params params_;
+};
+
+// 1-D device array with a host mirror (here both are host memory)
+template <class T>
+class ParArray1D {
+ public:
+  ParArray1D() = default;
+  ParArray1D(const std::string &, int n) : d_(std::make_shared<std::vector<T>>(n)) {}
+  ParArray1D GetHostMirror() const {
+    ParArray1D m;
+    m.d_ = std::make_shared<std::vector<T>>(d_->size());
+    return m;
+  }
+  void DeepCopy(const ParArray1D &src) { *d_ = *src.d_; }
+  T &operator()(int i) const { return (*d_)[i]; }
+
+ private:
+  std::shared_ptr<std::vector<T>> d_;
 };
 
 struct Packages_t {
@@ -200,12 +235,52 @@ class Mesh {
   std::shared_ptr<StateDescriptor> resolved_packages = std::make_shared<StateDescriptor>();
 };
 
-class ParameterInput {  // never consulted: the shim fills parameter structs field by field
+// ParameterInput: "block/name" -> text, filled by the harness (the reference's Initialize
+// functions read it exactly as they read a parsed input deck)
+class ParameterInput {
  public:
-  std::string GetString(const std::string &, const std::string &) { return ""; }
-  std::string GetOrAddString(const std::string &, const std::string &, const std::string &d) { return d; }
-  Real GetReal(const std::string &, const std::string &) { return 0.0; }
-  Real GetOrAddReal(const std::string &, const std::string &, Real d) { return d; }
+  std::map<std::string, std::string> kv;
+  void Set(const std::string &block, const std::string &name, const std::string &v) {
+    kv[block + "/" + name] = v;
+  }
+  void Set(const std::string &block, const std::string &name, Real v) {
+    std::ostringstream o;
+    o.precision(17);
+    o << v;
+    kv[block + "/" + name] = o.str();
+  }
+  bool DoesBlockExist(const std::string &block) const {
+    const std::string pre = block + "/";
+    auto it = kv.lower_bound(pre);
+    return it != kv.end() && it->first.compare(0, pre.size(), pre) == 0;
+  }
+  bool Has(const std::string &b, const std::string &n) const { return kv.count(b + "/" + n) != 0; }
+  std::string GetString(const std::string &b, const std::string &n) {
+    auto it = kv.find(b + "/" + n);
+    if (it == kv.end()) shim_fail(("missing input " + b + "/" + n).c_str(), __FILE__, __LINE__);
+    return it->second;
+  }
+  std::string GetOrAddString(const std::string &b, const std::string &n, const std::string &d) {
+    return Has(b, n) ? kv[b + "/" + n] : d;
+  }
+  Real GetReal(const std::string &b, const std::string &n) { return std::stod(GetString(b, n)); }
+  Real GetOrAddReal(const std::string &b, const std::string &n, Real d) {
+    return Has(b, n) ? std::stod(kv[b + "/" + n]) : d;
+  }
+  int GetOrAddInteger(const std::string &b, const std::string &n, int d) {
+    return Has(b, n) ? std::stoi(kv[b + "/" + n]) : d;
+  }
+  bool GetOrAddBoolean(const std::string &b, const std::string &n, bool d) {
+    return Has(b, n) ? (kv[b + "/" + n] == "true" || kv[b + "/" + n] == "1") : d;
+  }
+  template <class T>
+  std::vector<T> GetVector(const std::string &b, const std::string &n) {
+    std::vector<T> out;
+    std::stringstream ss(GetString(b, n));
+    std::string tok;
+    while (std::getline(ss, tok, ',')) out.push_back((T)std::stod(tok));
+    return out;
+  }
 };
 
 template <class T>
@@ -282,6 +357,13 @@ class SparsePackShim {
   template <class V, class = decltype(V::name())>
   Real &operator()(int b, const V &v, int k, int j, int i) const {
     return (*this)(b, type_off[shim_type_id<V>()] + v.idx, k, j, i);
+  }
+  struct VarHandle {
+    int sparse_id;
+  };
+  template <class V, class = decltype(V::name())>
+  VarHandle operator()(int, const V &v) const {
+    return VarHandle{v.idx};  // sparse pools are registered with ids 0..nspecies-1
   }
   template <class V, class = decltype(V::name())>
   Real &operator()(int b, TopologicalElement el, const V &v, int k, int j, int i) const {

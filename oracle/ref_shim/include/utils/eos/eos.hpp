@@ -33,6 +33,10 @@ class EOS {
     return _Cv;
   }
   template <class L = Real *>
+  Real GruneisenParamFromDensityInternalEnergy(const Real, const Real, L && = nullptr) const {
+    return _gm1;  // eos_ideal.hpp:150-154
+  }
+  template <class L = Real *>
   Real GruneisenParamFromDensityTemperature(const Real, const Real, L && = nullptr) const {
     return _gm1;
   }

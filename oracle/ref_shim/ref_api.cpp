@@ -24,6 +24,8 @@
 #include "utils/diffusion/diffusion.hpp"
 #include "utils/diffusion/momentum_diffusion.hpp"
 #include "utils/diffusion/thermal_diffusion.hpp"
+// Drag::Initialize + Drag::DragSource<GEOM> with SelfDragSourceImpl / SimpleDragSourceImpl
+#include "drag/drag.cpp"
 
 #include "../artemis_oracle.h"
 
@@ -587,5 +589,82 @@ double ar_diffusion_dt(const ao_grid *g, const ao_fluid *gas, double *gprim,
       cond_dt = Diffusion::EstimateTimestep<GG, Fluid::gas, DiffType::thermaldiff_plaw>(md, cp, gas_pkg, eos_d, vmesh);
   });
   return std::min(visc_dt, cond_dt);
+}
+// ---- drag: the reference's own Drag::Initialize (parameter parsing from an input deck) and
+// Drag::DragSource<GEOM> (dispatch + SelfDragSourceImpl / SimpleDragSourceImpl), src/drag/drag.cpp
+// and drag.hpp, driven from a ParameterInput the harness fills like the deck would.
+void ar_drag_source(const ao_grid *g, const ao_fluid *gas, double *gcons, const ao_fluid *dust,
+                    double *dcons, const ao_drag *dp, const ao_diffusion *dd, double dt) {
+  Ctx c;
+  SetGrid(c, g);
+  if (dd) g_cv = dd->cv;
+  if (gas) {
+    SetFluidPkg(c, g, gas);
+    AddSlab(c, g, gas, false, gcons, nullptr, nullptr, nullptr);
+  }
+  g_cv = 1.0;
+  if (dust) {
+    SetFluidPkg(c, g, dust);
+    AddSlab(c, g, dust, false, dcons, nullptr, nullptr, nullptr);
+  }
+  parthenon::ParameterInput pin;
+  pin.Set("drag", "type", dp->coupling == AO_DRAG_SELF ? "self" : "simple_dust");
+  const char *xn[3] = {"x1", "x2", "x3"};
+  for (int d = 0; d < 3; ++d) {
+    pin.Set("parthenon/mesh", std::string(xn[d]) + "min", dp->xmin[d]);
+    pin.Set("parthenon/mesh", std::string(xn[d]) + "max", dp->xmax[d]);
+  }
+  pin.Set("physics", "gas", gas ? "true" : "false");
+  pin.Set("physics", "dust", dust ? "true" : "false");
+  auto damping = [&](const char *blk, const double *ix, const double *ox, const double *ir,
+                     const double *orr, int to_visc) {
+    for (int d = 0; d < 3; ++d) {
+      pin.Set(blk, "inner_" + std::string(xn[d]), ix[d]);
+      pin.Set(blk, "outer_" + std::string(xn[d]), ox[d]);
+      pin.Set(blk, "inner_" + std::string(xn[d]) + "_rate", ir[d]);
+      pin.Set(blk, "outer_" + std::string(xn[d]) + "_rate", orr[d]);
+    }
+    pin.Set(blk, "damp_to_visc", to_visc ? "true" : "false");
+  };
+  if (gas) damping("gas/damping", dp->g_ix, dp->g_ox, dp->g_irate, dp->g_orate, dp->g_damp_to_visc);
+  if (dust) damping("dust/damping", dp->d_ix, dp->d_ox, dp->d_irate, dp->d_orate, 0);
+  if (dust) {
+    const int nd = dust->nspecies;
+    pin.Set("dust", "nspecies", (Real)nd);
+    pin.Set("dust/stopping_time", "type", dp->model == AO_DRAG_STOKES ? "stokes" : "constant");
+    pin.Set("dust/stopping_time", "scale", dp->scale);
+    std::ostringstream o;
+    o.precision(17);
+    for (int n = 0; n < nd; ++n) o << (n ? "," : "") << dp->tau[n];
+    pin.Set("dust/stopping_time", "tau", o.str());
+    // <dust> sizes / grain_density as Dust::Initialize stores them (src/dust/dust.cpp:102-140)
+    auto dpk = std::make_shared<StateDescriptor>(*c.mesh.packages.Get("dust"));
+    parthenon::ParArray1D<Real> sizes("sizes", nd);
+    for (int n = 0; n < nd; ++n) sizes(n) = dp->sizes[n];
+    dpk->AddParam<parthenon::ParArray1D<Real>>("sizes", sizes);
+    dpk->AddParam<Real>("grain_density", dp->grain_density);
+    c.mesh.packages.pkgs["dust"] = dpk;
+  }
+  if (gas && dd) {
+    Diffusion::DiffCoeffParams vp, cp;
+    double *none[3] = {nullptr, nullptr, nullptr};
+    (void)none;
+    using Diffusion::DiffType;
+    vp.type = dd->visc_type == AO_VISC_PLAW ? DiffType::viscosity_plaw
+              : dd->visc_type == AO_VISC_ALPHA ? DiffType::viscosity_alpha : DiffType::null;
+    vp.avg = Diffusion::DiffAvg::arithmetic;
+    vp.nu_s = dd->nu; vp.eta = dd->eta; vp.R0 = dd->r0; vp.r_exp = dd->r_exp;
+    vp.alpha = dd->alpha; vp.Omega0 = dd->omega0;
+    auto gpk = std::make_shared<StateDescriptor>(*c.mesh.packages.Get("gas"));
+    gpk->AddParam<Diffusion::DiffCoeffParams>("visc_params", vp);
+    c.mesh.packages.pkgs["gas"] = gpk;
+  }
+  c.mesh.packages.pkgs["drag"] = Drag::Initialize(&pin);
+  auto art = std::make_shared<StateDescriptor>(*c.mesh.packages.Get("artemis"));
+  art->AddParam<Coordinates>("coords", static_cast<Coordinates>(g->geom));
+  c.mesh.packages.pkgs["artemis"] = art;
+  GeomDispatch(g->geom, [&](auto G) {
+    Drag::DragSource<decltype(G)::value>(&c.md, 0.0, dt);
+  });
 }
 }  // extern "C"

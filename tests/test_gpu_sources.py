@@ -9,7 +9,8 @@ import pytest
 from artemis_b200.driver import ArtemisDriver
 from artemis_b200.enums import BoundaryFlag, Coordinates
 from artemis_b200.meshdata import MeshData
-from oracle.oracle_py import OracleSim
+from artemis_b200 import capi
+from oracle.oracle_py import OracleSim, make_diffusion, make_drag
 from tests.helpers import dust_params, gas_params, make_mesh, random_prim, zone_rel_err
 
 pytestmark = pytest.mark.gpu
@@ -37,22 +38,64 @@ CASES = [
 NDIM = {Coordinates.axisymmetric: 2}
 
 
-def _run(coords, sources, integ, mode, variant, ncyc=2):
+def _zones(mesh):
+    lo, hi = np.array(mesh.xmin, float), np.array(mesh.xmax, float)
+    w = hi - lo
+    return dict(inner=tuple(lo + 0.3 * w), outer=tuple(hi - 0.3 * w), inner_rate=(3.0, 2.0, 1.5),
+                outer_rate=(2.5, 0.0, 4.0))
+
+
+# Drag::DragSource in full: (coordinates, make_drag keywords as a function of the mesh, viscosity)
+DRAG_CASES = [
+    (Coordinates.cartesian, lambda m: dict(model="stokes", scale=0.4, grain_density=2.5,
+                                           sizes=(1e-3, 0.4)), None),
+    (Coordinates.cylindrical, lambda m: dict(tau=(1e-2, 5.0), scale=0.7, gas_damping=_zones(m),
+                                             dust_damping=_zones(m)), None),
+    (Coordinates.spherical3D, lambda m: dict(model="stokes", scale=0.4, grain_density=2.5,
+                                             sizes=(1e-3, 0.4), gas_damping=_zones(m),
+                                             dust_damping=_zones(m), damp_to_visc=True),
+     dict(visc=("constant", 3e-3))),
+    (Coordinates.axisymmetric, lambda m: dict(coupling="self", gas_damping=_zones(m),
+                                              dust_damping=_zones(m)), None),
+    (Coordinates.spherical2D, lambda m: dict(coupling="self", gas_damping=_zones(m),
+                                             dust_damping=_zones(m), damp_to_visc=True),
+     dict(visc=("constant", 2e-3))),
+]
+
+
+def _to_gpu_sources(sources):
+    out = []
+    for src in sources:
+        if src[0] == "drag_model":   # oracle ao_drag and ab200_drag_desc share their layout
+            out.append(("drag_model", capi.DragDesc.from_buffer_copy(bytes(src[1]))))
+        else:
+            out.append(src)
+    return out
+
+
+def _run(coords, sources, integ, mode, variant, ncyc=2, diffusion=None):
     bcs = (BoundaryFlag.outflow,) * 6 if coords != Coordinates.cartesian else None
     mesh = make_mesh(coords, NDIM.get(coords, 3), bcs=bcs)
+    if callable(sources):
+        sources = sources(mesh)
     gp, dp = gas_params(coords, "ppm", "hllc"), dust_params(coords, "plm", "hlle", S=2)
     prim, dprim = random_prim(mesh, gp, seed=71), random_prim(mesh, dp, seed=72)
     osim = OracleSim(mesh, gas=gp, dust=dp, integrator=integ)
     osim.gas.prim[:] = prim
     osim.dust.prim[:] = dprim
     osim.sources = list(sources)
+    gdiff = None
+    if diffusion:
+        osim.diffusion = make_diffusion(**diffusion)
+        gdiff = capi.DiffusionDesc.from_buffer_copy(bytes(osim.diffusion))
     osim.nlim = ncyc
     osim.initialize()
     osim.run()
     md = MeshData(mesh, gas=gp, dust=dp, variant=variant, materialize_fluxes=(mode == "tasks"))
     md.gas.prim.set(prim)
     md.dust.prim.set(dprim)
-    drv = ArtemisDriver(md, integ, mode=mode, nlim=ncyc, sources=sources)
+    drv = ArtemisDriver(md, integ, mode=mode, nlim=ncyc, sources=_to_gpu_sources(sources),
+                        diffusion=gdiff)
     drv.Initialize()
     drv.Execute()
     out = [(f.u0.get(), f.prim.get(), of.u0, of.prim, of.fp) for f, of in zip(md.fluids, osim.fluids)]
@@ -73,6 +116,26 @@ def test_tasks_with_sources_strict_bit_identical(coords, sources, integ):
 def test_split_fused_stage_with_sources_within_1e12(coords, sources, integ):
     """fast build, fused passes + deferred C2P, two cycles"""
     out, drv, osim = _run(coords, sources, integ, "fused", "fast", ncyc=1)
+    for u0, w, ou0, ow, fp in out:
+        assert zone_rel_err(u0, ou0, fp, "cons") <= 1e-12
+        assert zone_rel_err(w, ow, fp, "prim") <= 1e-12
+
+
+@pytest.mark.parametrize("coords,drag_kw,visc", DRAG_CASES)
+def test_full_drag_source_strict_bit_identical(coords, drag_kw, visc):
+    """ab200_drag_source (Stokes / constant stopping times, damping zones, viscous target, self
+    coupling) against the oracle, which is pinned to the reference's own drag.cpp"""
+    out, drv, osim = _run(coords, lambda m: [("drag_model", make_drag(m, **drag_kw(m)))], "rk2",
+                          "tasks", "strict", diffusion=visc)
+    assert drv.dt == osim.dt
+    for u0, w, ou0, ow, _ in out:
+        assert np.array_equal(u0, ou0) and np.array_equal(w, ow)
+
+
+@pytest.mark.parametrize("coords,drag_kw,visc", DRAG_CASES)
+def test_full_drag_source_fused_within_1e12(coords, drag_kw, visc):
+    out, drv, osim = _run(coords, lambda m: [("drag_model", make_drag(m, **drag_kw(m)))], "rk2",
+                          "fused", "fast", ncyc=1, diffusion=visc)
     for u0, w, ou0, ow, fp in out:
         assert zone_rel_err(u0, ou0, fp, "cons") <= 1e-12
         assert zone_rel_err(w, ow, fp, "prim") <= 1e-12

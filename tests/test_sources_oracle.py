@@ -10,7 +10,7 @@ import pytest
 
 from artemis_b200.enums import BoundaryFlag, Coordinates
 from oracle import ref_py
-from oracle.oracle_py import OracleSim
+from oracle.oracle_py import OracleSim, make_diffusion, make_drag
 from tests.helpers import dust_params, gas_params, make_mesh, random_prim
 
 needs_ref = pytest.mark.skipif(not ref_py.available(), reason="oracle/_ref not built")
@@ -86,6 +86,72 @@ def test_rotating_frame_restatement_is_bit_identical_to_reference_code(coords, n
         assert np.array_equal(fo.u0, fr.u0) and np.array_equal(fo.prim, fr.prim)
     base, _ = _pair(coords, src[1:], integ="vl2", ncyc=2, ndim=ndim)
     assert not np.array_equal(base.gas.u0, o.gas.u0)
+
+
+def _drag_pair(coords, ndim, drag_kw, diffusion=None, integ="rk2", ncyc=2):
+    bcs = (BoundaryFlag.outflow,) * 6 if coords != Coordinates.cartesian else None
+    mesh = make_mesh(coords, ndim, bcs=bcs)
+    gp, dp = gas_params(coords, "plm", "hlle"), dust_params(coords, "plm", "hlle", S=3)
+    sims = []
+    for cls in (OracleSim, ref_py.RefSim):
+        sim = cls(mesh, gas=gp, dust=dp, integrator=integ)
+        sim.gas.prim[:] = random_prim(mesh, gp, seed=61)
+        sim.dust.prim[:] = random_prim(mesh, dp, seed=62)
+        if diffusion:
+            sim.diffusion = make_diffusion(**diffusion)
+        sim.sources = [("drag_model", make_drag(mesh, **drag_kw))]
+        sim.nlim = ncyc
+        sim.initialize()
+        sim.run()
+        sims.append(sim)
+    return sims
+
+
+def _zones(mesh):
+    """damping zones covering the inner / outer ~third of every direction"""
+    lo, hi = np.array(mesh.xmin, float), np.array(mesh.xmax, float)
+    w = hi - lo
+    return dict(inner=tuple(lo + 0.3 * w), outer=tuple(hi - 0.3 * w), inner_rate=(3.0, 2.0, 1.5),
+                outer_rate=(2.5, 0.0, 4.0))
+
+
+DRAG_CASES = {
+    "constant_tau": lambda m: dict(tau=(1e-3, 0.2, 5.0), scale=0.7),
+    "constant_tau_with_an_instantly_coupled_species": lambda m: dict(tau=(0.0, 0.2, 5.0)),
+    "stokes": lambda m: dict(model="stokes", scale=0.4, grain_density=2.5, sizes=(1e-3, 3e-2, 0.4)),
+    "constant_tau_with_damping_zones": lambda m: dict(tau=(1e-2, 0.2, 5.0), gas_damping=_zones(m),
+                                                      dust_damping=_zones(m)),
+    "stokes_with_damping_to_the_viscous_inflow": lambda m: dict(
+        model="stokes", scale=0.4, grain_density=2.5, sizes=(1e-3, 3e-2, 0.4),
+        gas_damping=_zones(m), dust_damping=_zones(m), damp_to_visc=True),
+    "self_damping": lambda m: dict(coupling="self", gas_damping=_zones(m), dust_damping=_zones(m)),
+    "self_damping_to_the_viscous_inflow": lambda m: dict(
+        coupling="self", gas_damping=_zones(m), dust_damping=_zones(m), damp_to_visc=True),
+}
+
+
+@needs_ref
+@pytest.mark.parametrize("coords,ndim", ALL_GEOMS)
+@pytest.mark.parametrize("case", sorted(DRAG_CASES))
+def test_drag_restatement_is_bit_identical_to_reference_code(coords, ndim, case):
+    """Drag::Initialize + Drag::DragSource<GEOM> (src/drag/drag.cpp, drag.hpp) run from the
+    reference's own sources on a parsed parameter set: simple_dust and self coupling, constant and
+    Stokes stopping times, damping zones, damping towards the viscous inflow velocity."""
+    mesh = make_mesh(coords, ndim)
+    kw = DRAG_CASES[case](mesh)
+    visc = dict(visc=("constant", 3e-3)) if kw.get("damp_to_visc") else None
+    o, r = _drag_pair(coords, ndim, kw, diffusion=visc)
+    for fo, fr in zip(o.fluids, r.fluids):
+        assert np.array_equal(fo.u0, fr.u0) and np.array_equal(fo.prim, fr.prim)
+
+
+@needs_ref
+def test_legacy_constant_drag_entry_is_the_reference_drag():
+    """("drag", [tau]) -- what the GPU's ab200_drag_simple is checked against -- now runs the
+    reference's own DragSource on the reference side."""
+    o, r = _pair(Coordinates.cylindrical, [("drag", [0.05, 2.0])], integ="rk3", ncyc=2)
+    for fo, fr in zip(o.fluids, r.fluids):
+        assert np.array_equal(fo.u0, fr.u0) and np.array_equal(fo.prim, fr.prim)
 
 
 def test_drag_conserves_total_momentum_and_relaxes_to_the_common_velocity():
