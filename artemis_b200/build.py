@@ -25,7 +25,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 # (source, extra defines, object suffix)
 UNITS = [("api.cu", [], ""), ("tasks.cu", [], ""), ("halo.cu", [], ""),
          ("fused_dispatch.cu", [], ""), ("host_path.cu", [], ""), ("tma_maps.cu", [], "")]
-UNITS += [("sweep_host.cu", [], ""), ("refine.cu", [], ""), ("comm.cu", [], ""), ("sources.cu", [], ""), ("history.cu", [], ""), ("diffusion.cu", [], "")]
+UNITS += [("sweep_host.cu", [], ""), ("refine.cu", [], ""), ("comm.cu", [], ""), ("sources.cu", [], ""), ("history.cu", [], ""), ("diffusion.cu", [], ""), ("multilevel.cu", [], "")]
 UNITS += [("sweep.cu", [f"-DAB_RS={r}"], f"_r{r}") for r in range(3)]
 UNITS += [("trio.cu", [f"-DAB_RS={r}"], f"_r{r}") for r in range(3)]
 UNITS += [("fused.cu", [f"-DAB_GEOM={g}"], f"_g{g}") for g in range(6)]

@@ -204,6 +204,8 @@ int run_stage(ab200_ctx *c, double g0, double g1, double beta, int pcm, int firs
 int launch_halo(ab200_ctx *c, const ab200_bnd_desc *bnd, int n, int unpack);
 int launch_set_global_dt(ab200_ctx *c, double tlim, int advance_time);
 int ensure_scratch(ab200_ctx *c, int fluid, bool need_flux, bool need_u1);
+// refine.cu: geometry (GridDev gc + metric tables) of the blocks' coarse buffers, built once
+int ensure_coarse_grid(ab200_ctx *c);
 // diffusion.cu
 int launch_diffusion_flux(ab200_ctx *c);
 int launch_diffusion_update(ab200_ctx *c, double dt, const double *dt_dev, double beta);

@@ -1,0 +1,213 @@
+// multilevel.cu -- the data movement of the multilevel ghost exchange that the same-level
+// kernels (halo.cu) and the operators of refine.cu do not cover:
+//
+//   ab200_box_copy    SendBoundBufs + SetBounds for blocks on the same GPU
+//                     (P:bvals/comms/boundary_communication.cpp:48-140, 263-352) as ONE launch
+//                     over a descriptor list: every descriptor copies a box of `ncomp` pack
+//                     entries from a block's fine arrays or its coarse buffer (Parthenon's
+//                     `coarse_s`) into another block's fine arrays or coarse buffer -- the
+//                     three cases of BndInfo (bnd_info.cpp:273-304): same level (fine -> fine),
+//                     to a coarser block (restricted coarse buffer -> fine ghosts) and to a
+//                     finer block (fine interior -> the receiver's coarse-buffer ghosts).
+//                     Index boxes are CalcIndices' (bnd_info.cpp:105-252), supplied by the host
+//                     from Parthenon's own boundary cache.  Every box read is interior data,
+//                     every box written is a ghost region, so one launch is race-free.
+//   ab200_block_bcs   ApplyBoundaryConditionsOnCoarseOrFineMD: GenericBC outflow / reflect
+//                     (P:bvals/boundary_conditions_generic.hpp:178-256) on named faces of named
+//                     blocks, on the fine arrays or on the coarse buffers, over the full
+//                     transverse extent, x1 faces first, then x2, then x3 (one launch each).
+//
+// Both are pure copies: HBM-bound streaming over thin slabs, launch-latency bound in practice.
+#include <cstring>
+
+#include "ab200_ctx.cuh"
+#include "tasks.cuh"
+
+namespace ab200 {
+
+struct BoxDev {
+  int fluid, ncomp;
+  int src_block, src_var0, dst_block, dst_var0;
+  const double *src_coarse;
+  double *dst_coarse;
+  int ssi, ssj, ssk, dsi, dsj, dsk, ni, nj, nk;
+};
+
+// one thread per (descriptor = blockIdx.y, component, cell of the box), i fastest
+__global__ void __launch_bounds__(kThreads)
+k_box_copy(GridDev g, GridDev gc, FluidDev f0, FluidDev f1, const BoxDev *__restrict__ bx) {
+  const BoxDev d = bx[blockIdx.y];
+  const FluidDev &f = d.fluid == AB200_GAS ? f0 : f1;
+  const long long cells = (long long)d.ni * d.nj * d.nk;
+  const long long total = cells * d.ncomp;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int comp = (int)(t / cells);
+    long long r = t - comp * cells;
+    const int i = (int)(r % d.ni); r /= d.ni;
+    const int j = (int)(r % d.nj);
+    const int k = (int)(r / d.nj);
+    double v;
+    if (d.src_coarse)
+      v = d.src_coarse[(((size_t)comp * gc.nk + (d.ssk + k)) * gc.nj + (d.ssj + j)) * gc.ni + (d.ssi + i)];
+    else
+      v = f.prim[(size_t)d.src_block * f.nvar + d.src_var0 + comp]
+                [((size_t)(d.ssk + k) * g.nj + (d.ssj + j)) * g.ni + (d.ssi + i)];
+    if (d.dst_coarse)
+      d.dst_coarse[(((size_t)comp * gc.nk + (d.dsk + k)) * gc.nj + (d.dsj + j)) * gc.ni + (d.dsi + i)] = v;
+    else
+      f.prim[(size_t)d.dst_block * f.nvar + d.dst_var0 + comp]
+            [((size_t)(d.dsk + k) * g.nj + (d.dsj + j)) * g.ni + (d.dsi + i)] = v;
+  }
+}
+
+struct BcDev {
+  int fluid, block, var0, ncomp, face, type;
+  double *coarse;
+};
+
+// GenericBC of one direction: thread per (descriptor, component, transverse cell, ghost layer)
+__global__ void __launch_bounds__(kThreads)
+k_block_bcs(GridDev g, GridDev gc, FluidDev f0, FluidDev f1, const BcDev *__restrict__ bc, int dir) {
+  const BcDev d = bc[blockIdx.y];
+  if (d.face / 2 != dir) return;
+  const FluidDev &f = d.fluid == AB200_GAS ? f0 : f1;
+  const GridDev &a = d.coarse ? gc : g;  // the index space the face lives in
+  const int n[3] = {a.ni, a.nj, a.nk};
+  const int lo[3] = {a.is, a.js, a.ks}, hi[3] = {a.ie, a.je, a.ke};
+  const int ng = lo[dir];                 // ghost depth of this direction
+  const int t1 = (dir + 1) % 3, t2 = (dir + 2) % 3;
+  const long long plane = (long long)n[t1] * n[t2];
+  const long long total = plane * ng * d.ncomp;
+  const bool inner = (d.face % 2) == 0;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    long long r = t;
+    int idx[3];
+    // enumerate so that consecutive threads walk i (direction 0) whenever it is transverse
+    const int a1 = dir == 0 ? 1 : 0, a2 = dir == 2 ? 1 : 2;  // the two transverse axes, low first
+    idx[a1] = (int)(r % n[a1]); r /= n[a1];
+    idx[a2] = (int)(r % n[a2]); r /= n[a2];
+    const int gl = (int)(r % ng);
+    const int comp = (int)(r / ng);
+    (void)t1; (void)t2;
+    int src;
+    if (inner) {
+      idx[dir] = lo[dir] - 1 - gl;
+      src = d.type == AB200_BC_REFLECT ? lo[dir] + gl : lo[dir];
+    } else {
+      idx[dir] = hi[dir] + 1 + gl;
+      src = d.type == AB200_BC_REFLECT ? hi[dir] - gl : hi[dir];
+    }
+    int sidx[3] = {idx[0], idx[1], idx[2]};
+    sidx[dir] = src;
+    const int var = d.var0 + comp;
+    // the velocity component normal to the face flips under reflection
+    // (boundary_conditions_generic.hpp:229-246): pack entries S + 3 n + dir
+    double sgn = 1.0;
+    if (d.type == AB200_BC_REFLECT && var >= f.S && var < 4 * f.S && (var - f.S) % 3 == dir) sgn = -1.0;
+    double *base = d.coarse ? d.coarse + (size_t)comp * n[0] * n[1] * n[2]
+                            : f.prim[(size_t)d.block * f.nvar + var];
+    const double v = base[((size_t)sidx[2] * n[1] + sidx[1]) * n[0] + sidx[0]];
+    base[((size_t)idx[2] * n[1] + idx[1]) * n[0] + idx[0]] = sgn * v;
+  }
+}
+
+}  // namespace ab200
+
+using namespace ab200;
+
+extern "C" {
+
+int ab200_box_copy(ab200_ctx *c, const ab200_box_desc *bx, int nd) {
+  AB_REQUIRE(c && c->grid_set, AB200_ESTATE, "ab200_box_copy: no grid bound");
+  if (nd == 0) return AB200_OK;
+  AB_REQUIRE(bx && nd > 0, AB200_EINVAL, "ab200_box_copy: bad descriptor list");
+  AB_CUDA(cudaSetDevice(c->device));
+  AB_TRY(ensure_coarse_grid(c));
+  const GridDev &g = c->g, &gc = c->gc;
+  std::vector<BoxDev> h(nd);
+  long long maxcells = 1;
+  for (int q = 0; q < nd; ++q) {
+    const ab200_box_desc &s = bx[q];
+    AB_REQUIRE(s.fluid == AB200_GAS || s.fluid == AB200_DUST, AB200_EINVAL, "ab200_box_copy: bad fluid");
+    AB_REQUIRE(c->fl[s.fluid].bound, AB200_ESTATE, "ab200_box_copy: fluid not bound");
+    const FluidDev &f = c->fl[s.fluid].d;
+    AB_REQUIRE(s.ncomp >= 1 && s.ni >= 1 && s.nj >= 1 && s.nk >= 1, AB200_EINVAL, "ab200_box_copy: empty box");
+    const GridDev &sg = s.src_coarse ? gc : g, &dg = s.dst_coarse ? gc : g;
+    AB_REQUIRE(s.ssi >= 0 && s.ssj >= 0 && s.ssk >= 0 && s.ssi + s.ni <= sg.ni &&
+                   s.ssj + s.nj <= sg.nj && s.ssk + s.nk <= sg.nk,
+               AB200_EINVAL, "ab200_box_copy: source box outside the array");
+    AB_REQUIRE(s.dsi >= 0 && s.dsj >= 0 && s.dsk >= 0 && s.dsi + s.ni <= dg.ni &&
+                   s.dsj + s.nj <= dg.nj && s.dsk + s.nk <= dg.nk,
+               AB200_EINVAL, "ab200_box_copy: destination box outside the array");
+    AB_REQUIRE(s.src_coarse || (s.src_block >= 0 && s.src_block < g.nb && s.src_var0 >= 0 &&
+                                s.src_var0 + s.ncomp <= f.nvar),
+               AB200_EINVAL, "ab200_box_copy: bad source entries");
+    AB_REQUIRE(s.dst_coarse || (s.dst_block >= 0 && s.dst_block < g.nb && s.dst_var0 >= 0 &&
+                                s.dst_var0 + s.ncomp <= f.nvar),
+               AB200_EINVAL, "ab200_box_copy: bad destination entries");
+    BoxDev &d = h[q];
+    std::memset(&d, 0, sizeof d);
+    d.fluid = s.fluid; d.ncomp = s.ncomp;
+    d.src_block = s.src_block; d.src_var0 = s.src_var0; d.src_coarse = s.src_coarse;
+    d.dst_block = s.dst_block; d.dst_var0 = s.dst_var0; d.dst_coarse = s.dst_coarse;
+    d.ssi = s.ssi; d.ssj = s.ssj; d.ssk = s.ssk; d.dsi = s.dsi; d.dsj = s.dsj; d.dsk = s.dsk;
+    d.ni = s.ni; d.nj = s.nj; d.nk = s.nk;
+    maxcells = std::max(maxcells, (long long)s.ni * s.nj * s.nk * s.ncomp);
+  }
+  void *dev = nullptr;
+  AB_TRY(cached_descriptors(c, h.data(), sizeof(BoxDev) * (size_t)nd, nd, &dev));
+  for (int f = 0; f < 2; ++f)
+    if (c->fl[f].bound) AB_TRY(sync_prim_home(c, f, 0));
+  NvtxRange nvtx_("SendBoundBufs + SetBounds [multilevel, same GPU]");
+  dim3 grid((unsigned)std::min<long long>((maxcells + kThreads - 1) / kThreads, 64), (unsigned)nd);
+  k_box_copy<<<grid, kThreads, 0, c->stream>>>(g, gc, c->fl[0].d, c->fl[1].d, (const BoxDev *)dev);
+  c->launches++;
+  AB_CUDA(cudaGetLastError());
+  return AB200_OK;
+}
+
+int ab200_block_bcs(ab200_ctx *c, const ab200_block_bc_desc *bc, int nd) {
+  AB_REQUIRE(c && c->grid_set, AB200_ESTATE, "ab200_block_bcs: no grid bound");
+  if (nd == 0) return AB200_OK;
+  AB_REQUIRE(bc && nd > 0, AB200_EINVAL, "ab200_block_bcs: bad descriptor list");
+  AB_CUDA(cudaSetDevice(c->device));
+  AB_TRY(ensure_coarse_grid(c));
+  const GridDev &g = c->g, &gc = c->gc;
+  std::vector<BcDev> h(nd);
+  bool has_dir[3] = {false, false, false};
+  for (int q = 0; q < nd; ++q) {
+    const ab200_block_bc_desc &s = bc[q];
+    AB_REQUIRE(s.fluid == AB200_GAS || s.fluid == AB200_DUST, AB200_EINVAL, "ab200_block_bcs: bad fluid");
+    AB_REQUIRE(c->fl[s.fluid].bound, AB200_ESTATE, "ab200_block_bcs: fluid not bound");
+    const FluidDev &f = c->fl[s.fluid].d;
+    AB_REQUIRE(s.face >= 0 && s.face < 2 * g.ndim, AB200_EINVAL, "ab200_block_bcs: bad face");
+    AB_REQUIRE(s.type == AB200_BC_OUTFLOW || s.type == AB200_BC_REFLECT, AB200_EINVAL,
+               "ab200_block_bcs: outflow or reflect");
+    AB_REQUIRE(s.block >= 0 && s.block < g.nb && s.var0 >= 0 && s.ncomp >= 1 &&
+                   s.var0 + s.ncomp <= f.nvar,
+               AB200_EINVAL, "ab200_block_bcs: bad entries");
+    BcDev &d = h[q];
+    std::memset(&d, 0, sizeof d);
+    d.fluid = s.fluid; d.block = s.block; d.var0 = s.var0; d.ncomp = s.ncomp;
+    d.face = s.face; d.type = s.type; d.coarse = s.coarse;
+    has_dir[s.face / 2] = true;
+  }
+  void *dev = nullptr;
+  AB_TRY(cached_descriptors(c, h.data(), sizeof(BcDev) * (size_t)nd, nd, &dev));
+  for (int f = 0; f < 2; ++f)
+    if (c->fl[f].bound) AB_TRY(sync_prim_home(c, f, 0));
+  NvtxRange nvtx_("ApplyBoundaryConditionsOnCoarseOrFineMD [per block]");
+  const long long plane = (long long)std::max(g.ni * g.nj, std::max(g.nj * g.nk, g.ni * g.nk));
+  dim3 grid((unsigned)std::min<long long>((plane * g.ng * 6 + kThreads - 1) / kThreads, 64), (unsigned)nd);
+  for (int dir = 0; dir < g.ndim; ++dir) {
+    if (!has_dir[dir]) continue;
+    k_block_bcs<<<grid, kThreads, 0, c->stream>>>(g, gc, c->fl[0].d, c->fl[1].d, (const BcDev *)dev, dir);
+    c->launches++;
+  }
+  AB_CUDA(cudaGetLastError());
+  return AB200_OK;
+}
+
+}  // extern "C"

@@ -29,7 +29,7 @@ struct RefineDev {
   double *coarse;
 };
 
-static int ensure_coarse(ab200_ctx *c) {
+int ensure_coarse_grid(ab200_ctx *c) {
   if (c->coarse_ready) return AB200_OK;
   const GridDev &g = c->g;
   GridDev &gc = c->gc;
@@ -210,7 +210,7 @@ static int launch_refine(ab200_ctx *c, const ab200_refine_desc *descs, int n, bo
   AB_REQUIRE(c->grid_set, AB200_ESTATE, "no grid bound: call ab200_set_grid");
   if (n == 0) return AB200_OK;
   AB_CUDA(cudaSetDevice(c->device));
-  AB_TRY(ensure_coarse(c));
+  AB_TRY(ensure_coarse_grid(c));
   for (int f = 0; f < 2; ++f) AB_TRY(sync_prim_home(c, f, 0));  // operators use the caller's arrays
   const GridDev &g = c->g, &gc = c->gc;
   const int act[3] = {1, g.ndim > 1, g.ndim > 2};
@@ -286,7 +286,7 @@ int ab200_coarse_shape(ab200_ctx *c, int *dims6) {
   AB_REQUIRE(c && dims6, AB200_EINVAL, "ab200_coarse_shape: null argument");
   AB_REQUIRE(c->grid_set, AB200_ESTATE, "no grid bound: call ab200_set_grid");
   AB_CUDA(cudaSetDevice(c->device));
-  AB_TRY(ensure_coarse(c));
+  AB_TRY(ensure_coarse_grid(c));
   dims6[0] = c->gc.ni; dims6[1] = c->gc.nj; dims6[2] = c->gc.nk;
   dims6[3] = c->gc.is; dims6[4] = c->gc.js; dims6[5] = c->gc.ks;
   return AB200_OK;

@@ -118,6 +118,10 @@ class MultilevelMesh:
         if ng % 2:
             raise ValueError("Parthenon requires an even nghost with mesh refinement "
                              "(P:mesh/mesh_refinement.cpp:61)")
+        for d in range(self.ndim):
+            if self.block_nx[d] % 2 or self.block_nx[d] < 2 * ng:
+                raise ValueError("multilevel MeshBlocks need an even nx >= 2 nghost per active "
+                                 "direction (the coarse buffer must hold nghost interior zones)")
         self.ngd = tuple(ng if self.block_nx[d] > 1 else 0 for d in range(3))
         self.ni, self.nj, self.nk = (self.block_nx[d] + 2 * self.ngd[d] for d in range(3))
         self.is_, self.js, self.ks = self.ngd
@@ -172,7 +176,7 @@ class MultilevelMesh:
                 self.blk_xmin[b, d] = lo - self.ngd[d] * dx
         self.neighbors = [self._find_neighbors(b) for b in range(self.nb)]
 
-    # ---- duck-typing of UniformMesh for MeshData / the oracle -----------------------------
+    # ---- duck-typing of UniformMesh (what MeshData reads) ------------------------------------
     @property
     def interior_zones(self):
         return self.nb * self.block_nx[0] * self.block_nx[1] * self.block_nx[2]
@@ -182,6 +186,14 @@ class MultilevelMesh:
 
     def coarse_shape(self, nvar):
         return (self.nb, nvar, self.cn[2], self.cn[1], self.cn[0])
+
+    def face_shape(self, ns):
+        return (self.nb, ns, self.fnk, self.fnj, self.fni)
+
+    @property
+    def lattice_n(self):
+        # the uniform-lattice exchange of the library is never used on a multilevel mesh
+        return (self.nb, 1, 1)
 
     def interior(self):
         return (slice(self.ks, self.ke + 1), slice(self.js, self.je + 1),
@@ -324,3 +336,92 @@ def exchange_plan(mesh: MultilevelMesh) -> ExchangePlan:
             if has_coarser:
                 plan.coarse_bcs.append((b, face))
     return plan
+
+
+def fill_ghost_ranges(fp):
+    """contiguous (var0, ncomp) ranges of the FillGhost primitive pack entries: gas density +
+    velocity and sie (the pressure entry is Derived, src/gas/gas.cpp:236-270), dust density +
+    velocity"""
+    from .enums import Fluid
+    S = fp.nspecies
+    if fp.fluid_type == Fluid.gas:
+        return [(0, 4 * S), (5 * S, S)]
+    return [(0, 4 * S)]
+
+
+class MultilevelExchange:
+    """AddBoundaryExchangeTasks on a MultilevelMesh whose blocks live on one GPU: descriptor
+    lists built once from `exchange_plan`, executed through the C ABI in Parthenon's order."""
+
+    def __init__(self, md, plan: ExchangePlan | None = None):
+        import ctypes as C
+
+        from . import capi
+        self.md, self.C, self.capi = md, C, capi
+        m = md.mesh
+        self.plan = plan or exchange_plan(m)
+        shape6 = (C.c_int * 6)()
+        md.call("ab200_coarse_shape", shape6)
+        assert tuple(shape6[:3]) == tuple(m.cn), (tuple(shape6), m.cn)
+        ccells = m.cn[0] * m.cn[1] * m.cn[2]
+        kinds = {int(BoundaryFlag.outflow): 1, int(BoundaryFlag.reflect): 2}
+        self.coarse = {}
+        rs, cp, rt, cb, pr, fb = [], [], [], [], [], []
+        for ff in md.fluids:
+            fl, nv = int(ff.fp.fluid_type), ff.fp.nvar
+            buf = md._alloc(m.coarse_shape(nv))
+            self.coarse[fl] = buf
+
+            def cptr(b, var0, buf=buf, nv=nv):
+                return buf.ptr + ((b * nv + var0) * ccells) * 8
+
+            for var0, nc in fill_ghost_ranges(ff.fp):
+                def refine(lst, b, box):
+                    lst.append(capi.RefineDesc(fl, b, var0, nc, 0, box[0][0], box[0][1], box[1][0],
+                                               box[1][1], box[2][0], box[2][1], cptr(b, var0)))
+                for b, box in self.plan.restrict_send:
+                    refine(rs, b, box)
+                for b, box in self.plan.restrict_set:
+                    refine(rt, b, box)
+                for b, box in self.plan.prolongate:
+                    refine(pr, b, box)
+                for sb, sc, sbox, db, dc, dbox in self.plan.copies:
+                    cp.append(capi.BoxDesc(fl, nc, sb, var0, cptr(sb, var0) if sc else None, db, var0,
+                                           cptr(db, var0) if dc else None, sbox[0][0], sbox[1][0],
+                                           sbox[2][0], dbox[0][0], dbox[1][0], dbox[2][0],
+                                           sbox[0][1] - sbox[0][0] + 1, sbox[1][1] - sbox[1][0] + 1,
+                                           sbox[2][1] - sbox[2][0] + 1))
+                for b, face in self.plan.coarse_bcs:
+                    cb.append(capi.BlockBcDesc(fl, b, var0, nc, face, kinds[int(m.bcs[face])],
+                                               cptr(b, var0)))
+                for b, face in self.plan.fine_bcs:
+                    fb.append(capi.BlockBcDesc(fl, b, var0, nc, face, kinds[int(m.bcs[face])], None))
+
+        def arr(T, lst):
+            return (T * len(lst))(*lst) if lst else None
+
+        self._rs, self._rt, self._pr = arr(capi.RefineDesc, rs), arr(capi.RefineDesc, rt), arr(capi.RefineDesc, pr)
+        self._cp = arr(capi.BoxDesc, cp)
+        self._cb, self._fb = arr(capi.BlockBcDesc, cb), arr(capi.BlockBcDesc, fb)
+        self.n = dict(rs=len(rs), rt=len(rt), pr=len(pr), cp=len(cp), cb=len(cb), fb=len(fb))
+
+    def exchange(self):
+        """SendBoundBufs -> SetBounds -> coarse BCs -> ProlongateBounds -> fine BCs"""
+        md, n = self.md, self.n
+        if n["rs"]:
+            md.call("ab200_restrict", self._rs, n["rs"])
+        if n["cp"]:
+            md.call("ab200_box_copy", self._cp, n["cp"])
+        if n["rt"]:
+            md.call("ab200_restrict", self._rt, n["rt"])
+        if n["cb"]:
+            md.call("ab200_block_bcs", self._cb, n["cb"])
+        if n["pr"]:
+            md.call("ab200_prolongate", self._pr, n["pr"])
+        if n["fb"]:
+            md.call("ab200_block_bcs", self._fb, n["fb"])
+
+    def close(self):
+        for buf in self.coarse.values():
+            buf.free()
+        self.coarse = {}

@@ -368,6 +368,43 @@ int ab200_coarse_shape(ab200_ctx *ctx, int *dims6);
 int ab200_restrict(ab200_ctx *ctx, const ab200_refine_desc *descs, int n);
 int ab200_prolongate(ab200_ctx *ctx, const ab200_refine_desc *descs, int n);
 
+/* ---- multilevel ghost exchange: data movement (config 5) ------------------------------------
+ * With ab200_restrict / ab200_prolongate above these execute Parthenon's multilevel
+ * AddBoundaryExchangeTasks (P:bvals/comms/boundary_communication.cpp:406-445) for blocks on one
+ * GPU: SendBoundBufs (ab200_restrict over ProResInfo::GetSend ranges, then the copies),
+ * SetBounds (the copies; ab200_restrict over ProResInfo::GetSet ranges), physical BCs on the
+ * coarse buffers (ab200_block_bcs), ProlongateBounds (ab200_prolongate), physical BCs on the
+ * fine arrays (ab200_block_bcs).  The host supplies the index boxes from Parthenon's boundary
+ * cache (BndInfo::idxer = CalcIndices, P:bvals/comms/bnd_info.cpp:105-252);
+ * artemis_b200/multilevel.py restates that bookkeeping for hosts without Parthenon.
+ *
+ * ab200_box_desc: copy the box of extents (ni, nj, nk) with origin (ssi, ssj, ssk) of `ncomp`
+ * consecutive PRIMITIVE pack entries from src_var0 of block src_block -- or, when src_coarse is
+ * not NULL, from that coarse buffer ([ncomp][cnk][cnj][cni], ab200_coarse_shape) -- to origin
+ * (dsi, dsj, dsk) of entries from dst_var0 of block dst_block or of the coarse buffer dst_coarse.
+ * The three cases of BndInfo (bnd_info.cpp:273-304): same level fine -> fine, to a coarser
+ * neighbour coarse -> fine, to a finer neighbour fine -> coarse.  A whole list is ONE launch; all
+ * sources must be interior data and all destinations ghost regions (true of CalcIndices' boxes). */
+typedef struct ab200_box_desc {
+  int fluid, ncomp;
+  int src_block, src_var0;
+  const double *src_coarse; /* DEVICE or NULL */
+  int dst_block, dst_var0;
+  double *dst_coarse;       /* DEVICE or NULL */
+  int ssi, ssj, ssk, dsi, dsj, dsk, ni, nj, nk;
+} ab200_box_desc;
+int ab200_box_copy(ab200_ctx *ctx, const ab200_box_desc *boxes, int n);
+/* GenericBC outflow / reflect (P:bvals/boundary_conditions_generic.hpp:178-256) on face
+ * (0..5 = ix1, ox1, ix2, ox2, ix3, ox3) of `ncomp` primitive pack entries from var0 of one block:
+ * on its fine arrays, or on its coarse buffer when `coarse` is not NULL (the buffer slab of those
+ * entries).  Applied over the full transverse extent, x1 faces of the whole list first, then
+ * x2, then x3 (ApplyBoundaryConditionsOnCoarseOrFineMD). */
+typedef struct ab200_block_bc_desc {
+  int fluid, block, var0, ncomp, face, type; /* type: AB200_BC_OUTFLOW | AB200_BC_REFLECT */
+  double *coarse;                            /* DEVICE or NULL */
+} ab200_block_bc_desc;
+int ab200_block_bcs(ab200_ctx *ctx, const ab200_block_bc_desc *bcs, int n);
+
 /* ---- timestep on the device (replaces the per-cycle host round trip of
  *      P:driver/driver.cpp:210-269 + MPI_Allreduce :237) ------------------------------------ */
 /* min over all bound fluids of cfl*min_dt -> device scalar new_dt (no sync) */

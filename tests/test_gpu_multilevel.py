@@ -1,0 +1,109 @@
+"""GPU execution of the multilevel ghost exchange: the plan of
+artemis_b200.multilevel (CalcIndices pinned to the reference, tests/test_multilevel_plan.py)
+run through ab200_restrict / ab200_box_copy / ab200_block_bcs / ab200_prolongate must equal the
+CPU executor (oracle restriction / prolongation pinned to the reference's operators) BIT FOR BIT
+in the strict build -- random gas + dust states with jumps, Cartesian and curvilinear meshes,
+periodic / outflow / reflecting boundaries -- and to rounding in the default build."""
+import numpy as np
+import pytest
+
+from artemis_b200.enums import BoundaryFlag, Coordinates
+from artemis_b200.meshdata import MeshData
+from artemis_b200.multilevel import (MultilevelExchange, MultilevelMesh, exchange_plan,
+                                     fill_ghost_ranges)
+from oracle import multilevel_py
+from tests.helpers import GEOM_DOMAINS, dust_params, gas_params, random_prim
+
+pytestmark = pytest.mark.gpu
+
+B = BoundaryFlag
+CASES = [
+    (Coordinates.cartesian, 3, (B.periodic,) * 6, [(1, 1, 1), (2, 1, 1), (1, 2, 2)]),
+    (Coordinates.cartesian, 3, (B.reflect, B.outflow, B.outflow, B.reflect, B.periodic, B.periodic),
+     [(0, 0, 0), (3, 3, 1), (1, 2, 0)]),
+    (Coordinates.cartesian, 2, (B.outflow, B.reflect, B.reflect, B.outflow, B.periodic, B.periodic),
+     [(0, 1, 0), (3, 3, 0), (2, 2, 0)]),
+    (Coordinates.cartesian, 1, (B.reflect, B.outflow) + (B.periodic,) * 4, [(1, 0, 0), (3, 0, 0)]),
+    (Coordinates.cylindrical, 3, (B.outflow, B.outflow, B.periodic, B.periodic, B.reflect, B.outflow),
+     [(1, 1, 1), (0, 2, 0)]),
+    (Coordinates.spherical3D, 3, (B.reflect, B.outflow, B.outflow, B.outflow, B.periodic, B.periodic),
+     [(1, 1, 1), (3, 0, 2)]),
+    (Coordinates.axisymmetric, 2, (B.outflow,) * 4 + (B.periodic,) * 2, [(1, 1, 0), (2, 2, 0)]),
+    (Coordinates.spherical2D, 2, (B.outflow,) * 4 + (B.periodic,) * 2, [(0, 0, 0), (2, 1, 0)]),
+]
+
+
+def _mesh(coords, ndim, bcs, refine):
+    root = tuple(4 if d < ndim else 1 for d in range(3))
+    bnx = tuple(8 if d < ndim else 1 for d in range(3))
+    xmin, xmax = GEOM_DOMAINS[coords]
+    return MultilevelMesh(root_blocks=root, block_nx=bnx, xmin=xmin, xmax=xmax,
+                          refine=tuple(tuple(r) for r in refine), nghost=4, bcs=bcs, coords=coords)
+
+
+def _vdir(fp):
+    S = fp.nspecies
+    out = []
+    for var0, nc in fill_ghost_ranges(fp):
+        out += [((v - S) % 3 + 1) if S <= v < 4 * S else 0 for v in range(var0, var0 + nc)]
+    return out
+
+
+def _vars(fp):
+    return [v for var0, nc in fill_ghost_ranges(fp) for v in range(var0, var0 + nc)]
+
+
+@pytest.mark.parametrize("coords,ndim,bcs,refine", CASES)
+@pytest.mark.parametrize("variant", ["strict", "fast"])
+def test_multilevel_exchange_equals_cpu_executor(coords, ndim, bcs, refine, variant):
+    m = _mesh(coords, ndim, bcs, refine)
+    plan = exchange_plan(m)
+    gp, dp = gas_params(coords, "plm", "hlle", S=2), dust_params(coords, "plm", "hlle", S=2)
+    md = MeshData(m, gas=gp, dust=dp, variant=variant, materialize_fluxes=False)
+    ex = MultilevelExchange(md, plan)
+    kinds = {B.periodic: "periodic", B.outflow: "outflow", B.reflect: "reflect"}
+    for ff, seed in zip(md.fluids, (11, 12)):
+        prim = random_prim(m, ff.fp, seed=seed)
+        # poison every ghost zone: whatever the exchange does not fill shows up
+        mask = np.ones(prim.shape[2:], dtype=bool)
+        mask[m.interior()] = False
+        prim[:, :, mask] = -777.0
+        ff.prim.set(prim)
+        ff._host = prim
+        # the same poison in the coarse buffers on both sides: the comparison then covers every
+        # coarse zone, including what the boundary conditions copy out of never-restricted ones
+        ex.coarse[int(ff.fp.fluid_type)].set(np.full(m.coarse_shape(ff.fp.nvar), -555.0))
+    ex.exchange()
+    for ff in md.fluids:
+        fine = ff._host.copy()
+        coarse = np.full(m.coarse_shape(ff.fp.nvar), -555.0)
+        multilevel_py.run_plan(m, plan, fine, coarse, _vars(ff.fp), _vdir(ff.fp),
+                               [kinds[b] for b in bcs])
+        got = ff.prim.get()
+        vs = _vars(ff.fp)
+        assert not (got[:, vs] == -777.0).any(), "a ghost zone was never filled"
+        if variant == "strict":
+            assert np.array_equal(got, fine)
+        else:
+            assert np.max(np.abs(got - fine)) <= 1e-13 * np.max(np.abs(fine))
+        cgot = ex.coarse[int(ff.fp.fluid_type)].get()
+        if variant == "strict":
+            assert np.array_equal(cgot, coarse)
+    assert md.launch_count() > 0
+    ex.close()
+    md.close()
+
+
+def test_box_copy_and_block_bcs_reject_bad_descriptors():
+    import ctypes as C
+    from artemis_b200 import capi
+    m = _mesh(Coordinates.cartesian, 2, (B.outflow,) * 4 + (B.periodic,) * 2, [(1, 1, 0)])
+    gp = gas_params(Coordinates.cartesian, "plm", "hlle")
+    md = MeshData(m, gas=gp, materialize_fluxes=False)
+    bad = (capi.BoxDesc * 1)(capi.BoxDesc(0, 4, 0, 0, None, 1, 0, None, 0, 0, 0, 0, 0, 0, m.ni + 1, 1, 1))
+    with pytest.raises(capi.AB200Error, match="outside the array"):
+        md.call("ab200_box_copy", bad, 1)
+    badbc = (capi.BlockBcDesc * 1)(capi.BlockBcDesc(0, 0, 0, 4, 5, 1, None))   # x3 face in 2-D
+    with pytest.raises(capi.AB200Error, match="bad face"):
+        md.call("ab200_block_bcs", badbc, 1)
+    md.close()
