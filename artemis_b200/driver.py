@@ -115,7 +115,16 @@ class ArtemisDerived:
 
 def AddBoundaryExchangeTasks(md: MeshData, comm=None) -> TaskStatus:
     """parthenon::AddBoundaryExchangeTasks (P:bvals/comms/boundary_communication.cpp:433-444):
-    same-GPU neighbours in one kernel, remote neighbours through `comm`, then physical BCs."""
+    same-GPU neighbours in one kernel, remote neighbours through `comm`, then physical BCs.
+    On a multilevel mesh `comm` is a multilevel.MultilevelExchange, which runs the whole
+    sequence (restrict / copy / restrict / coarse BCs / prolongate / fine BCs)."""
+    if getattr(comm, "multilevel", False):
+        try:
+            comm.exchange()
+        except capi.AB200Error as e:
+            md.last_error = str(e)
+            return TaskStatus.fail
+        return TaskStatus.complete
     st = _task(md, "ab200_exchange_ghosts")
     if st != TaskStatus.complete:
         return st

@@ -352,6 +352,11 @@ def fill_ghost_ranges(fp):
 class MultilevelExchange:
     """AddBoundaryExchangeTasks on a MultilevelMesh whose blocks live on one GPU: descriptor
     lists built once from `exchange_plan`, executed through the C ABI in Parthenon's order."""
+    multilevel = True
+
+    @staticmethod
+    def allreduce_min(x):     # one rank: the driver's dt all-reduce is the identity
+        return x
 
     def __init__(self, md, plan: ExchangePlan | None = None):
         import ctypes as C

@@ -322,6 +322,20 @@ class OracleSim:
 
     def ExchangeGhosts(self, fs):
         m = self.mesh
+        if hasattr(m, "leaves"):     # multilevel mesh: Parthenon's multilevel exchange sequence
+            from artemis_b200.multilevel import exchange_plan   # plain index bookkeeping
+            from . import multilevel_py
+            if getattr(self, "_ml_plan", None) is None:
+                self._ml_plan = exchange_plan(m)
+                self._ml_coarse = {}
+            key = id(fs)
+            if key not in self._ml_coarse:
+                self._ml_coarse[key] = np.zeros(m.coarse_shape(fs.fp.nvar))
+            kinds = ["periodic" if int(b) == 0 else ("outflow" if int(b) == 1 else "reflect")
+                     for b in m.bcs]
+            multilevel_py.run_plan(m, self._ml_plan, fs.prim, self._ml_coarse[key], fs.ghost_vars,
+                                   fs.vec_dir, kinds)
+            return
         vars_ = np.array(fs.ghost_vars, dtype=np.int32)
         vdir = np.array(fs.vec_dir, dtype=np.int32)
         bc = m.bc_ints()

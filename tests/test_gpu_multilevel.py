@@ -94,6 +94,61 @@ def test_multilevel_exchange_equals_cpu_executor(coords, ndim, bcs, refine, vari
     md.close()
 
 
+CYCLE_CASES = [
+    (Coordinates.cartesian, 3, (B.periodic,) * 6, [(1, 1, 1), (2, 2, 1)]),
+    (Coordinates.cartesian, 2, (B.reflect, B.outflow, B.outflow, B.reflect, B.periodic, B.periodic),
+     [(0, 1, 0), (2, 2, 0)]),
+    (Coordinates.spherical3D, 3, (B.reflect, B.outflow, B.outflow, B.outflow, B.periodic, B.periodic),
+     [(1, 1, 1)]),
+]
+
+
+def _cycle_pair(coords, ndim, bcs, refine, mode, variant, ncyc, integ="rk2"):
+    from artemis_b200.driver import ArtemisDriver
+    from oracle.oracle_py import OracleSim
+    m = _mesh(coords, ndim, bcs, refine)
+    gp, dp = gas_params(coords, "ppm", "hllc"), dust_params(coords, "plm", "hlle", S=1)
+    prim, dprim = random_prim(m, gp, seed=41), random_prim(m, dp, seed=42)
+    osim = OracleSim(m, gas=gp, dust=dp, integrator=integ)
+    osim.gas.prim[:] = prim
+    osim.dust.prim[:] = dprim
+    osim.nlim = ncyc
+    osim.initialize()
+    osim.run()
+    md = MeshData(m, gas=gp, dust=dp, variant=variant, materialize_fluxes=(mode == "tasks"))
+    md.gas.prim.set(prim)
+    md.dust.prim.set(dprim)
+    ex = MultilevelExchange(md)
+    drv = ArtemisDriver(md, integ, mode=mode, nlim=ncyc, comm=ex)
+    drv.Initialize()
+    drv.Execute()
+    return m, osim, md, drv, ex
+
+
+@pytest.mark.parametrize("coords,ndim,bcs,refine", CYCLE_CASES)
+def test_multilevel_task_cycles_strict_bit_identical(coords, ndim, bcs, refine):
+    """whole rk2 cycles on a refined mesh (fine and coarse blocks advance with the same global
+    dt, ghost zones through the multilevel exchange; no flux correction on either side)"""
+    m, osim, md, drv, ex = _cycle_pair(coords, ndim, bcs, refine, "tasks", "strict", 2)
+    assert drv.ncycle == osim.ncycle == 2 and drv.dt == osim.dt and drv.time == osim.time
+    for ff, of in zip(md.fluids, osim.fluids):
+        assert np.array_equal(ff.u0.get(), of.u0)
+        assert np.array_equal(ff.prim.get(), of.prim)
+    ex.close()
+    md.close()
+
+
+@pytest.mark.parametrize("coords,ndim,bcs,refine", CYCLE_CASES[:2])
+def test_multilevel_fused_cycle_within_1e12(coords, ndim, bcs, refine):
+    from tests.helpers import zone_rel_err
+    m, osim, md, drv, ex = _cycle_pair(coords, ndim, bcs, refine, "fused", "fast", 1)
+    for ff, of in zip(md.fluids, osim.fluids):
+        assert zone_rel_err(ff.u0.get(), of.u0, of.fp, "cons") <= 1e-12
+        assert zone_rel_err(ff.prim.get(), of.prim, of.fp, "prim") <= 1e-12
+    ex.close()
+    md.close()
+
+
 def test_box_copy_and_block_bcs_reject_bad_descriptors():
     import ctypes as C
     from artemis_b200 import capi
