@@ -17,7 +17,14 @@
 //                     blocks, on the fine arrays or on the coarse buffers, over the full
 //                     transverse extent, x1 faces first, then x2, then x3 (one launch each).
 //
-// Both are pure copies: HBM-bound streaming over thin slabs, launch-latency bound in practice.
+//   ab200_flux_correct   AddFluxCorrectionTasks (boundary_communication.cpp:454-461): the fluxes
+//                     through every coarse face shared with finer blocks are replaced by the
+//                     area-weighted average of the fine fluxes -- RestrictAverage<GEOM> on face
+//                     elements (src/utils/refinement/restriction.hpp:41-114) fused with the
+//                     send / set copies into ONE launch over all fine-coarse faces, all
+//                     Metadata::Flux fields of a fluid (conserved fluxes + interface pressure).
+//
+// All are thin-slab streaming kernels: HBM-bound by nature, launch-latency bound in practice.
 #include <cstring>
 
 #include "ab200_ctx.cuh"
@@ -113,11 +120,124 @@ k_block_bcs(GridDev g, GridDev gc, FluidDev f0, FluidDev f1, const BcDev *__rest
   }
 }
 
+struct FluxCorDev {
+  int fluid, fine_block, coarse_block, dir;
+  int cis, cie, cjs, cje, cks, cke;  // coarse-index box of the fine block's face
+  int dsi, dsj, dsk;                 // origin of the same cells in the coarse block
+};
+
+// one thread per (descriptor, flux entry, coarse face cell)
+template <int GEOM>
+__global__ void __launch_bounds__(kThreads)
+k_flux_correct(GridDev g, GridDev gc, FluidDev f0, FluidDev f1, const FluxCorDev *__restrict__ fc) {
+  const FluxCorDev d = fc[blockIdx.y];
+  const FluidDev &f = d.fluid == AB200_GAS ? f0 : f1;
+  const int nent = f.nvar + (d.fluid == AB200_GAS ? f.S : 0);  // conserved fluxes + pressure flux
+  const int nci = d.cie - d.cis + 1, ncj = d.cje - d.cjs + 1, nck = d.cke - d.cks + 1;
+  const long long total = (long long)nent * nck * ncj * nci;
+  const int el = d.dir + 1;
+  const bool inc1 = el != 1, inc2 = g.ndim > 1 && el != 2, inc3 = g.ndim > 2 && el != 3;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    long long r = t;
+    const int ci = (int)(r % nci) + d.cis; r /= nci;
+    const int cj = (int)(r % ncj) + d.cjs; r /= ncj;
+    const int ck = (int)(r % nck) + d.cks; r /= nck;
+    const int n = (int)r;
+    const int i = (ci - gc.is) * 2 + g.is;
+    const int j = g.ndim > 1 ? (cj - gc.js) * 2 + g.js : g.js;
+    const int k = g.ndim > 2 ? (ck - gc.ks) * 2 + g.ks : g.ks;
+    double *const *tab = n < f.nvar ? f.flux[d.dir] : f.pflux[d.dir];
+    const int ent = n < f.nvar ? n : n - f.nvar;
+    const int stride = n < f.nvar ? f.nvar : f.S;
+    const double *fine = tab[(size_t)d.fine_block * stride + ent];
+    double vol[2][2][2], terms[2][2][2];
+#pragma unroll
+    for (int ok = 0; ok < 2; ++ok)
+#pragma unroll
+      for (int oj = 0; oj < 2; ++oj)
+#pragma unroll
+        for (int oi = 0; oi < 2; ++oi) {
+          vol[ok][oj][oi] = 0.0;
+          terms[ok][oj][oi] = 0.0;
+          if ((ok == 0 || inc3) && (oj == 0 || inc2) && (oi == 0 || inc1)) {
+            Coords<GEOM> cc(g, d.fine_block, k + ok, j + oj, i + oi);
+            vol[ok][oj][oi] = el == 1 ? cc.area1(cc.x1[0]) : (el == 2 ? cc.area2(0) : cc.area3());
+            terms[ok][oj][oi] =
+                vol[ok][oj][oi] * fine[((size_t)(k + ok) * g.nj + (j + oj)) * g.ni + (i + oi)];
+          }
+        }
+    // restriction.hpp:103-111: off-centred terms first (FP symmetry)
+    const double tvol = ((vol[0][0][0] + vol[0][1][0]) + (vol[0][0][1] + vol[0][1][1])) +
+                        ((vol[1][0][0] + vol[1][1][0]) + (vol[1][0][1] + vol[1][1][1]));
+    const double v =
+        ddiv((((terms[0][0][0] + terms[0][1][0]) + (terms[0][0][1] + terms[0][1][1])) +
+              ((terms[1][0][0] + terms[1][1][0]) + (terms[1][0][1] + terms[1][1][1]))),
+             tvol);
+    double *dst = tab[(size_t)d.coarse_block * stride + ent];
+    dst[((size_t)(d.dsk + (ck - d.cks)) * g.nj + (d.dsj + (cj - d.cjs))) * g.ni +
+        (d.dsi + (ci - d.cis))] = v;
+  }
+}
+
 }  // namespace ab200
 
 using namespace ab200;
 
 extern "C" {
+
+int ab200_flux_correct(ab200_ctx *c, const ab200_fluxcor_desc *fc, int nd) {
+  AB_REQUIRE(c && c->grid_set, AB200_ESTATE, "ab200_flux_correct: no grid bound");
+  if (nd == 0) return AB200_OK;
+  AB_REQUIRE(fc && nd > 0, AB200_EINVAL, "ab200_flux_correct: bad descriptor list");
+  AB_CUDA(cudaSetDevice(c->device));
+  AB_TRY(ensure_coarse_grid(c));
+  const GridDev &g = c->g, &gc = c->gc;
+  std::vector<FluxCorDev> h(nd);
+  long long maxcells = 1;
+  for (int q = 0; q < nd; ++q) {
+    const ab200_fluxcor_desc &s = fc[q];
+    AB_REQUIRE(s.fluid == AB200_GAS || s.fluid == AB200_DUST, AB200_EINVAL, "ab200_flux_correct: bad fluid");
+    const FluidHost &fh = c->fl[s.fluid];
+    AB_REQUIRE(fh.bound, AB200_ESTATE, "ab200_flux_correct: fluid not bound");
+    AB_REQUIRE(s.dir >= 0 && s.dir < g.ndim, AB200_EINVAL, "ab200_flux_correct: bad direction");
+    AB_REQUIRE(fh.d.flux[s.dir] && (s.fluid == AB200_DUST || fh.d.pflux[s.dir]), AB200_ESTATE,
+               "ab200_flux_correct: no flux arrays (call ab200_calculate_fluxes first)");
+    AB_REQUIRE(s.fine_block >= 0 && s.fine_block < g.nb && s.coarse_block >= 0 &&
+                   s.coarse_block < g.nb,
+               AB200_EINVAL, "ab200_flux_correct: bad block");
+    AB_REQUIRE(s.cis >= 0 && s.cie < gc.ni + 1 && s.cjs >= 0 && s.cje < gc.nj + 1 && s.cks >= 0 &&
+                   s.cke < gc.nk + 1 && s.cis <= s.cie && s.cjs <= s.cje && s.cks <= s.cke,
+               AB200_EINVAL, "ab200_flux_correct: bad coarse box");
+    AB_REQUIRE(s.dsi >= 0 && s.dsi + (s.cie - s.cis) < g.ni && s.dsj >= 0 &&
+                   s.dsj + (s.cje - s.cjs) < g.nj && s.dsk >= 0 && s.dsk + (s.cke - s.cks) < g.nk,
+               AB200_EINVAL, "ab200_flux_correct: destination outside the array");
+    FluxCorDev &d = h[q];
+    std::memset(&d, 0, sizeof d);
+    d.fluid = s.fluid; d.fine_block = s.fine_block; d.coarse_block = s.coarse_block; d.dir = s.dir;
+    d.cis = s.cis; d.cie = s.cie; d.cjs = s.cjs; d.cje = s.cje; d.cks = s.cks; d.cke = s.cke;
+    d.dsi = s.dsi; d.dsj = s.dsj; d.dsk = s.dsk;
+    maxcells = std::max(maxcells, (long long)(s.cie - s.cis + 1) * (s.cje - s.cjs + 1) *
+                                      (s.cke - s.cks + 1) * (fh.d.nvar + fh.d.S));
+  }
+  void *dev = nullptr;
+  AB_TRY(cached_descriptors(c, h.data(), sizeof(FluxCorDev) * (size_t)nd, nd, &dev));
+  NvtxRange nvtx_("SendBoundBufs<flxcor_send> + SetBounds<flxcor_recv> [fused with restriction]");
+  dim3 grid((unsigned)std::min<long long>((maxcells + kThreads - 1) / kThreads, 64), (unsigned)nd);
+  const FluxCorDev *dd = (const FluxCorDev *)dev;
+#define AB_LAUNCH(G)                                                                          \
+  case G: k_flux_correct<G><<<grid, kThreads, 0, c->stream>>>(g, gc, c->fl[0].d, c->fl[1].d, dd); break;
+  switch (g.geom) {
+    AB_LAUNCH(0) AB_LAUNCH(1) AB_LAUNCH(2) AB_LAUNCH(3) AB_LAUNCH(4) AB_LAUNCH(5)
+  default:
+    set_error("Coordinate type not recognized!");
+    return AB200_EINVAL;
+  }
+#undef AB_LAUNCH
+  c->launches++;
+  AB_CUDA(cudaGetLastError());
+  return AB200_OK;
+}
 
 int ab200_box_copy(ab200_ctx *c, const ab200_box_desc *bx, int nd) {
   AB_REQUIRE(c && c->grid_set, AB200_ESTATE, "ab200_box_copy: no grid bound");

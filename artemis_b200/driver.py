@@ -141,7 +141,8 @@ class ArtemisDriver:
     """
 
     def __init__(self, md: MeshData, integrator: str = "rk2", mode: str = "tasks",
-                 tlim: float = np.inf, nlim: int = -1, comm=None, sources=(), diffusion=None):
+                 tlim: float = np.inf, nlim: int = -1, comm=None, sources=(), diffusion=None,
+                 flux_correction: bool = True):
         self.md = md
         # gas diffusion (physics/viscosity, physics/conduction): a capi.DiffusionDesc; the
         # operators run every stage as in src/artemis_driver.cpp:188-196, 217-221
@@ -162,6 +163,14 @@ class ArtemisDriver:
         self.nlim = nlim
         self.do_gas = md.gas is not None
         self.do_dust = md.dust is not None
+        # AddFluxCorrectionTasks on refined meshes (src/artemis_driver.cpp:198-202).  The fused
+        # path never stores fluxes, so it cannot correct them: on a refined mesh it is only
+        # available as the explicitly non-conservative variant (flux_correction=False).
+        self.flux_correction = flux_correction
+        if getattr(comm, "multilevel", False) and flux_correction and mode != "tasks":
+            raise ValueError("refined mesh: the fused stage path stores no fluxes and cannot apply "
+                             "Parthenon's flux correction -- use mode='tasks', or pass "
+                             "flux_correction=False for the non-conservative variant")
 
     @staticmethod
     def _require(st: TaskStatus, md, what):
@@ -242,6 +251,8 @@ class ArtemisDriver:
                     req(Dust.CalculateFluxes(md, do_pcm), md, "Dust::CalculateFluxes")
                 if self.diffusion is not None:
                     req(_task(md, "ab200_diffusion_flux"), md, "Gas::ViscousFlux/ThermalFlux")
+                if getattr(self.comm, "multilevel", False) and self.flux_correction:
+                    self.comm.flux_correct()     # AddFluxCorrectionTasks, artemis_driver.cpp:198-202
                 req(ArtemisUtils.ApplyUpdate(md, stage, integ), md, "ApplyUpdate")
                 if self.do_gas:
                     req(Gas.FluxSource(md, bdt), md, "Gas::FluxSource")

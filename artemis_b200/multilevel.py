@@ -34,19 +34,23 @@ from .mesh import _symm_coord
 BOUNDARY_INTERIOR_SEND, BOUNDARY_EXTERIOR_RECV, INTERIOR_SEND, INTERIOR_RECV = range(4)
 
 
-def calc_indices(ng, nx, my_level, my_l, nb_level, nb_l, offsets, ir_type, prores):
-    """CalcIndices (bnd_info.cpp:105-252) for a cell-centred, non-flux, non-fine field.
+def calc_indices(ng, nx, my_level, my_l, nb_level, nb_l, offsets, ir_type, prores, flux_el=0):
+    """CalcIndices (bnd_info.cpp:105-252) for a cell-centred field (flux_el = 0) or for the flux
+    of one on the x1 / x2 / x3 faces (flux_el = 1..3: a Metadata::Flux field, element F1..F3).
     Returns ((si, ei), (sj, ej), (sk, ek)) in the fine index space of the block or -- for
     prolongation / restriction ranges and whenever the neighbour is coarser -- in the index space
     of its coarse buffer."""
-    def interior(n):
+    flux = flux_el != 0
+    top = [int(flux_el == d + 1) for d in range(3)]
+
+    def interior(n, d):
         g = ng if n > 1 else 0
-        return g, g + n - 1
+        return g, g + n - 1 + top[d]
 
     use_coarse = prores or nb_level < my_level
-    bounds = [interior((nx[d] // 2 if nx[d] > 1 else 1) if use_coarse else nx[d]) for d in range(3)]
+    bounds = [interior((nx[d] // 2 if nx[d] > 1 else 1) if use_coarse else nx[d], d) for d in range(3)]
     coarse_fac = 2 if nb_level > my_level else 1
-    nbounds = [interior(nx[d] // coarse_fac) for d in range(3)]
+    nbounds = [interior(nx[d] // coarse_fac, d) for d in range(3)]
     not_symmetry = [nx[d] > 1 for d in range(3)]
     interior_offset = ng if ir_type == BOUNDARY_INTERIOR_SEND else 0
     exterior_offset = ng if ir_type == BOUNDARY_EXTERIOR_RECV else 0
@@ -76,12 +80,12 @@ def calc_indices(ng, nx, my_level, my_l, nb_level, nb_l, offsets, ir_type, prore
             if prores and not_symmetry[d] and ir_type == INTERIOR_RECV:
                 s -= ng // 2
                 e += ng // 2
-        elif offsets[d] > 0:
-            s = bounds[d][1] - interior_offset + 1
-            e = bounds[d][1] + exterior_offset
+        elif offsets[d] > 0:      # fluxes are only communicated on shared elements
+            s = bounds[d][1] + (0 if flux else -interior_offset + 1 - top[d])
+            e = bounds[d][1] + (0 if flux else exterior_offset)
         else:
-            s = bounds[d][0] - exterior_offset
-            e = bounds[d][0] + interior_offset - 1
+            s = bounds[d][0] + (0 if flux else -exterior_offset)
+            e = bounds[d][0] + (0 if flux else interior_offset - 1 + top[d])
         out.append((s, e))
     return tuple(out)
 
@@ -284,6 +288,35 @@ class MultilevelMesh:
         return faces
 
 
+def flux_correction_plan(mesh) -> list:
+    """AddFluxCorrectionTasks (boundary_communication.cpp:454-461): every fine block sends the
+    fluxes through each face it shares with a COARSER block (loop_utils.hpp:146-159: face
+    neighbours one level down), restricted to the coarse face (ProResInfo::GetSend), and the
+    coarse block overwrites its own flux there (SetBounds<flxcor_recv>).  Entries:
+    (fine block, coarse block, dir 0..2, restrict box in the fine block's coarse index space,
+    destination box in the coarse block's index space)."""
+    ng, nx = mesh.nghost, mesh.block_nx
+    out = []
+    for b in range(mesh.nb):
+        lev, l = mesh.leaves[b]
+        for nb in mesh.neighbors[b]:
+            if nb.level != lev - 1 or sum(abs(o) for o in nb.offsets) != 1:
+                continue
+            d = [abs(o) for o in nb.offsets].index(1)
+            rbox = calc_indices(ng, nx, lev, l, nb.level, nb.origin_loc, nb.offsets,
+                                BOUNDARY_INTERIOR_SEND, True, flux_el=d + 1)
+            back = [m for m in mesh.neighbors[nb.gid]
+                    if m.gid == b and m.offsets == tuple(-o for o in nb.offsets)]
+            m = back[0]
+            clev, cl = mesh.leaves[nb.gid]
+            dbox = calc_indices(ng, nx, clev, cl, m.level, m.origin_loc, m.offsets,
+                                BOUNDARY_EXTERIOR_RECV, False, flux_el=d + 1)
+            if any(rbox[q][1] - rbox[q][0] != dbox[q][1] - dbox[q][0] for q in range(3)):
+                raise RuntimeError(f"flux-correction shapes differ: {b} -> {nb.gid}: {rbox} {dbox}")
+            out.append((b, nb.gid, d, rbox, dbox))
+    return out
+
+
 @dataclass
 class ExchangePlan:
     """Index boxes of one multilevel ghost exchange; boxes are ((si, ei), (sj, ej), (sk, ek))."""
@@ -408,7 +441,15 @@ class MultilevelExchange:
         self._rs, self._rt, self._pr = arr(capi.RefineDesc, rs), arr(capi.RefineDesc, rt), arr(capi.RefineDesc, pr)
         self._cp = arr(capi.BoxDesc, cp)
         self._cb, self._fb = arr(capi.BlockBcDesc, cb), arr(capi.BlockBcDesc, fb)
-        self.n = dict(rs=len(rs), rt=len(rt), pr=len(pr), cp=len(cp), cb=len(cb), fb=len(fb))
+        fcs = []
+        for ff in md.fluids:
+            for fbk, cbk, d, rbox, dbox in flux_correction_plan(m):
+                fcs.append(capi.FluxCorDesc(int(ff.fp.fluid_type), fbk, cbk, d, rbox[0][0], rbox[0][1],
+                                            rbox[1][0], rbox[1][1], rbox[2][0], rbox[2][1],
+                                            dbox[0][0], dbox[1][0], dbox[2][0]))
+        self._fc = arr(capi.FluxCorDesc, fcs)
+        self.n = dict(rs=len(rs), rt=len(rt), pr=len(pr), cp=len(cp), cb=len(cb), fb=len(fb),
+                      fc=len(fcs))
 
     def exchange(self):
         """SendBoundBufs -> SetBounds -> coarse BCs -> ProlongateBounds -> fine BCs"""
@@ -425,6 +466,11 @@ class MultilevelExchange:
             md.call("ab200_prolongate", self._pr, n["pr"])
         if n["fb"]:
             md.call("ab200_block_bcs", self._fb, n["fb"])
+
+    def flux_correct(self):
+        """AddFluxCorrectionTasks: between CalculateFluxes and ApplyUpdate (task path)"""
+        if self.n["fc"]:
+            self.md.call("ab200_flux_correct", self._fc, self.n["fc"])
 
     def close(self):
         for buf in self.coarse.values():

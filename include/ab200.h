@@ -405,6 +405,22 @@ typedef struct ab200_block_bc_desc {
 } ab200_block_bc_desc;
 int ab200_block_bcs(ab200_ctx *ctx, const ab200_block_bc_desc *bcs, int n);
 
+/* Flux correction (AddFluxCorrectionTasks, P:bvals/comms/boundary_communication.cpp:454-461;
+ * src/artemis_driver.cpp:198-202): between ab200_calculate_fluxes and ab200_apply_update on a
+ * multilevel mesh.  One descriptor per face a fine block shares with a coarser block: the box
+ * [cis..cie][cjs..cje][cks..cke] of the fine block's coarse index space that covers the face
+ * (CalcIndices with the flux element, prores = true), and the origin of the same cells in the
+ * coarse block's own index space (CalcIndices, BoundaryExteriorRecv).  Every Metadata::Flux
+ * field of the fluid (conserved fluxes; for the gas also the interface pressure) is restricted
+ * with RestrictAverage<GEOM> on face elements (src/utils/refinement/restriction.hpp:41-114) and
+ * written over the coarse block's flux.  The list is ONE launch. */
+typedef struct ab200_fluxcor_desc {
+  int fluid, fine_block, coarse_block, dir; /* dir 0..2 */
+  int cis, cie, cjs, cje, cks, cke;
+  int dsi, dsj, dsk;
+} ab200_fluxcor_desc;
+int ab200_flux_correct(ab200_ctx *ctx, const ab200_fluxcor_desc *faces, int n);
+
 /* ---- timestep on the device (replaces the per-cycle host round trip of
  *      P:driver/driver.cpp:210-269 + MPI_Allreduce :237) ------------------------------------ */
 /* min over all bound fluids of cfl*min_dt -> device scalar new_dt (no sync) */

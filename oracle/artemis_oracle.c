@@ -1095,6 +1095,43 @@ static void coarse_coords(const ao_refine_geom *r, double cxmin[3], double cdx[3
 
 /* restriction.hpp:41-114 (el = CC): coarse = sum(vol * fine) / sum(vol) over the 2^ndim fine
  * cells, both sums in the reference's pairing ((000+010)+(001+011))+((100+110)+(101+111)). */
+/* the same operator on a face-centred (flux) field, el = 1..3 = x1 / x2 / x3 faces: the
+ * average runs over the 2^(ndim-1) fine faces of the coarse face, weighted by the LOWER face
+ * area of the fine cell (restriction.hpp:57-63, 88-95) */
+void ao_restrict_average_face(const ao_refine_geom *r, int nvar, const double *fine,
+                              double *coarse, const int *box, int el) {
+  const int inc1 = r->ndim > 0 && el != 1, inc2 = r->ndim > 1 && el != 2,
+            inc3 = r->ndim > 2 && el != 3;
+  for (int n = 0; n < nvar; ++n)
+    for (int ck = box[4]; ck <= box[5]; ++ck)
+      for (int cj = box[2]; cj <= box[3]; ++cj)
+        for (int ci = box[0]; ci <= box[1]; ++ci) {
+          const int i = (r->ndim > 0) ? (ci - r->cib_s) * 2 + r->ib_s : r->ib_s;
+          const int j = (r->ndim > 1) ? (cj - r->cjb_s) * 2 + r->jb_s : r->jb_s;
+          const int k = (r->ndim > 2) ? (ck - r->ckb_s) * 2 + r->kb_s : r->kb_s;
+          double vol[2][2][2], terms[2][2][2];
+          for (int ok = 0; ok < 2; ++ok)
+            for (int oj = 0; oj < 2; ++oj)
+              for (int oi = 0; oi < 2; ++oi) vol[ok][oj][oi] = terms[ok][oj][oi] = 0;
+          for (int ok = 0; ok < 1 + inc3; ++ok)
+            for (int oj = 0; oj < 1 + inc2; ++oj)
+              for (int oi = 0; oi < 1 + inc1; ++oi) {
+                const bbox_t b = make_bbox(r->xmin, r->dx, k + ok, j + oj, i + oi);
+                vol[ok][oj][oi] = el == 1 ? g_area1(r->geom, &b, b.x1[0])
+                                  : el == 2 ? g_area2(r->geom, &b, b.x2[0])
+                                            : g_area3(r->geom, &b, b.x3[0]);
+                terms[ok][oj][oi] =
+                    vol[ok][oj][oi] * fine[RIDX(r->nk, r->nj, r->ni, n, k + ok, j + oj, i + oi)];
+              }
+          const double tvol = ((vol[0][0][0] + vol[0][1][0]) + (vol[0][0][1] + vol[0][1][1])) +
+                              ((vol[1][0][0] + vol[1][1][0]) + (vol[1][0][1] + vol[1][1][1]));
+          coarse[RIDX(r->cnk, r->cnj, r->cni, n, ck, cj, ci)] =
+              (((terms[0][0][0] + terms[0][1][0]) + (terms[0][0][1] + terms[0][1][1])) +
+               ((terms[1][0][0] + terms[1][1][0]) + (terms[1][0][1] + terms[1][1][1]))) /
+              tvol;
+        }
+}
+
 void ao_restrict_average(const ao_refine_geom *r, int nvar, const double *fine, double *coarse,
                          const int *box) {
   const int inc1 = r->ndim > 0, inc2 = r->ndim > 1, inc3 = r->ndim > 2;

@@ -121,6 +121,10 @@ typedef struct {
 /* restriction.hpp:41-114: volume-weighted average of the 2^ndim fine cells */
 void ao_restrict_average(const ao_refine_geom *r, int nvar, const double *fine, double *coarse,
                          const int *box);
+/* the same on a face-centred (flux) field, el = 1..3 (flux correction): area-weighted average
+ * of the 2^(ndim-1) fine faces */
+void ao_restrict_average_face(const ao_refine_geom *r, int nvar, const double *fine,
+                              double *coarse, const int *box, int el);
 /* prolongation.hpp:82-184: minmod-limited linear interpolation onto the 2^ndim fine cells */
 void ao_prolongate_minmod(const ao_refine_geom *r, int nvar, const double *coarse, double *fine,
                           const int *box);

@@ -99,3 +99,21 @@ def run_plan(mesh, plan, fine, coarse, vars_, vdir, bc_kinds):
                 a = fine[b, vars_]
                 apply_bc(a, face, bc_kinds[face], nx[face_dir], mesh.nghost, vdir)
                 fine[b, vars_] = a
+
+
+def flux_correct(mesh, fc_plan, flux):
+    """SetFluxCorrections on the CPU: flux = [F1, F2, F3] arrays [nb][nvar][nk][nj][ni] (flux
+    through the LOWER face of every zone); every coarse face shared with finer blocks receives
+    the area-weighted average of the fine fluxes (RestrictAverage on face elements)."""
+    L = oracle_py.lib()
+    geoms = {}
+    for fb, cb, d, rbox, dbox in fc_plan:
+        if fb not in geoms:
+            geoms[fb] = block_geom(mesh, fb)
+        f = np.ascontiguousarray(flux[d][fb])
+        nvar = f.shape[0]
+        c = np.zeros((nvar, mesh.cn[2], mesh.cn[1], mesh.cn[0]))
+        flat = (C.c_int * 6)(rbox[0][0], rbox[0][1], rbox[1][0], rbox[1][1], rbox[2][0], rbox[2][1])
+        L.ao_restrict_average_face(C.byref(geoms[fb]), nvar, oracle_py._p(f), oracle_py._p(c), flat,
+                                   d + 1)
+        flux[d][cb][(slice(None),) + _sl(dbox)] = c[(slice(None),) + _sl(rbox)]

@@ -379,6 +379,17 @@ class OracleSim:
             self.CalculateFluxes(fs, pcm)
         if self.diffusion is not None:
             self.DiffusionFlux()
+        if hasattr(self.mesh, "leaves") and getattr(self, "flux_correction", True):
+            # AddFluxCorrectionTasks (artemis_driver.cpp:198-202): every Metadata::Flux field --
+            # the conserved fluxes and the interface pressure (gas.prim.pressure WithFluxes)
+            from artemis_b200.multilevel import flux_correction_plan
+            from . import multilevel_py
+            if getattr(self, "_fc_plan", None) is None:
+                self._fc_plan = flux_correction_plan(self.mesh)
+            for fs in self.fluids:
+                multilevel_py.flux_correct(self.mesh, self._fc_plan, fs.flux)
+                if fs.pflux[0] is not None:
+                    multilevel_py.flux_correct(self.mesh, self._fc_plan, fs.pflux)
         for fs in self.fluids:
             self.ApplyUpdate(fs, gam0, gam1, bdt)
         for fs in self.fluids:
@@ -446,6 +457,12 @@ def restrict_average(L, r, fine, coarse, box, prefix="ao"):
     """coarse[box] <- volume-weighted average of fine; fine [nvar][nk][nj][ni]."""
     getattr(L, prefix + "_restrict_average")(C.byref(r), fine.shape[0], _p(fine), _p(coarse),
                                              _box(box))
+
+
+def restrict_average_face(L, r, fine, coarse, box, el, prefix="ao"):
+    """the same operator on a flux field living on x1 / x2 / x3 faces (el = 1..3)"""
+    getattr(L, prefix + "_restrict_average_face")(C.byref(r), fine.shape[0], _p(fine), _p(coarse),
+                                                  _box(box), el)
 
 
 def prolongate_minmod(L, r, coarse, fine, box, prefix="ao"):

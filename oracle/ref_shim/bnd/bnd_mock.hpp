@@ -17,9 +17,10 @@ namespace parthenon {
 using Real = double;
 enum CoordinateDirection { NODIR = -1, X0DIR = 0, X1DIR = 1, X2DIR = 2, X3DIR = 3 };
 enum class TopologicalElement : std::size_t { CC = 0, F1 = 3, F2 = 4, F3 = 5 };
-inline int TopologicalOffsetI(TopologicalElement) { return 0; }  // cell-centred fields only
-inline int TopologicalOffsetJ(TopologicalElement) { return 0; }
-inline int TopologicalOffsetK(TopologicalElement) { return 0; }
+// P:basic_types.hpp: a face element adds one index along its own direction
+inline int TopologicalOffsetI(TopologicalElement el) { return el == TopologicalElement::F1; }
+inline int TopologicalOffsetJ(TopologicalElement el) { return el == TopologicalElement::F2; }
+inline int TopologicalOffsetK(TopologicalElement el) { return el == TopologicalElement::F3; }
 enum class IndexDomain { entire, interior };
 enum class IndexRangeType { BoundaryInteriorSend, BoundaryExteriorRecv, InteriorSend, InteriorRecv };
 struct IndexRange { int s = 0, e = 0; };
@@ -30,14 +31,14 @@ class IndexShape {
  public:
   IndexShape() = default;
   IndexShape(int nx3, int nx2, int nx1, int ng) : n_{nx1, nx2, nx3}, ng_(ng) {}
-  IndexRange GetBoundsI(IndexDomain, TopologicalElement) const { return b(0); }
-  IndexRange GetBoundsJ(IndexDomain, TopologicalElement) const { return b(1); }
-  IndexRange GetBoundsK(IndexDomain, TopologicalElement) const { return b(2); }
+  IndexRange GetBoundsI(IndexDomain, TopologicalElement el) const { return b(0, TopologicalOffsetI(el)); }
+  IndexRange GetBoundsJ(IndexDomain, TopologicalElement el) const { return b(1, TopologicalOffsetJ(el)); }
+  IndexRange GetBoundsK(IndexDomain, TopologicalElement el) const { return b(2, TopologicalOffsetK(el)); }
 
  private:
-  IndexRange b(int d) const {
+  IndexRange b(int d, int top) const {  // P:mesh/domain.hpp:296-318
     const int g = n_[d] > 1 ? ng_ : 0;
-    return IndexRange{g, g + n_[d] - 1};
+    return IndexRange{g, g + n_[d] - 1 + top};
   }
   int n_[3] = {1, 1, 1}, ng_ = 0;
 };
@@ -95,8 +96,9 @@ struct Metadata {
 };
 template <class T>
 struct Variable {
+  bool flux = false;
   int GetDim(int) const { return 1; }
-  bool IsSet(Metadata::Flag) const { return false; }
+  bool IsSet(Metadata::Flag f) const { return f == Metadata::Flux && flux; }
 };
 
 struct SpatiallyMaskedIndexer6D {

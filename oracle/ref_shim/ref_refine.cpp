@@ -64,6 +64,27 @@ void Loop(const ao_refine_geom *r, int nvar, double *coarse, double *fine, const
                                                   s.jb, s.ib, s.fine, s.coarse, &pc, &pf);
 }
 
+// restriction of a face-centred (flux) field: RestrictAverage<GEOM>::Do<DIM, F1|F2|F3>
+template <int DIM, Coordinates G, TE EL>
+void LoopFace(const ao_refine_geom *r, int nvar, double *coarse, double *fine, const int *box) {
+  Setup s = MakeSetup(r);
+  ParArrayND<Real, VariableState> pc{coarse, nvar, r->cnk, r->cnj, r->cni};
+  ParArrayND<Real, VariableState> pf{fine, nvar, r->nk, r->nj, r->ni};
+  for (int n = 0; n < nvar; ++n)
+    for (int k = box[4]; k <= box[5]; ++k)
+      for (int j = box[2]; j <= box[3]; ++j)
+        for (int i = box[0]; i <= box[1]; ++i)
+          ArtemisUtils::RestrictAverage<G>::template Do<DIM, EL, EL>(
+              0, 0, n, k, j, i, s.ckb, s.cjb, s.cib, s.kb, s.jb, s.ib, s.fine, s.coarse, &pc, &pf);
+}
+template <int DIM, Coordinates G>
+void RunFace(const ao_refine_geom *r, int nvar, double *coarse, double *fine, const int *box,
+             int el) {
+  if (el == 1) LoopFace<DIM, G, TE::F1>(r, nvar, coarse, fine, box);
+  else if (el == 2) LoopFace<DIM, G, TE::F2>(r, nvar, coarse, fine, box);
+  else LoopFace<DIM, G, TE::F3>(r, nvar, coarse, fine, box);
+}
+
 template <template <Coordinates> class Op>
 void Run(const ao_refine_geom *r, int nvar, double *coarse, double *fine, const int *box) {
   GeomDispatchR(r->geom, [&](auto G) {
@@ -79,6 +100,17 @@ extern "C" {
 void ar_restrict_average(const ao_refine_geom *r, int nvar, const double *fine, double *coarse,
                          const int *box) {
   Run<ArtemisUtils::RestrictAverage>(r, nvar, coarse, const_cast<double *>(fine), box);
+}
+// el = 1..3: the field lives on x1 / x2 / x3 faces (flux correction, SetFluxCorrections)
+void ar_restrict_average_face(const ao_refine_geom *r, int nvar, const double *fine,
+                              double *coarse, const int *box, int el) {
+  GeomDispatchR(r->geom, [&](auto G) {
+    constexpr Coordinates C = decltype(G)::value;
+    double *f = const_cast<double *>(fine);
+    if (r->ndim == 1) RunFace<1, C>(r, nvar, coarse, f, box, el);
+    else if (r->ndim == 2) RunFace<2, C>(r, nvar, coarse, f, box, el);
+    else RunFace<3, C>(r, nvar, coarse, f, box, el);
+  });
 }
 void ar_prolongate_minmod(const ao_refine_geom *r, int nvar, const double *coarse, double *fine,
                           const int *box) {

@@ -103,13 +103,14 @@ CYCLE_CASES = [
 ]
 
 
-def _cycle_pair(coords, ndim, bcs, refine, mode, variant, ncyc, integ="rk2"):
+def _cycle_pair(coords, ndim, bcs, refine, mode, variant, ncyc, integ="rk2", flux_correction=True):
     from artemis_b200.driver import ArtemisDriver
     from oracle.oracle_py import OracleSim
     m = _mesh(coords, ndim, bcs, refine)
     gp, dp = gas_params(coords, "ppm", "hllc"), dust_params(coords, "plm", "hlle", S=1)
     prim, dprim = random_prim(m, gp, seed=41), random_prim(m, dp, seed=42)
     osim = OracleSim(m, gas=gp, dust=dp, integrator=integ)
+    osim.flux_correction = flux_correction
     osim.gas.prim[:] = prim
     osim.dust.prim[:] = dprim
     osim.nlim = ncyc
@@ -119,7 +120,7 @@ def _cycle_pair(coords, ndim, bcs, refine, mode, variant, ncyc, integ="rk2"):
     md.gas.prim.set(prim)
     md.dust.prim.set(dprim)
     ex = MultilevelExchange(md)
-    drv = ArtemisDriver(md, integ, mode=mode, nlim=ncyc, comm=ex)
+    drv = ArtemisDriver(md, integ, mode=mode, nlim=ncyc, comm=ex, flux_correction=flux_correction)
     drv.Initialize()
     drv.Execute()
     return m, osim, md, drv, ex
@@ -127,9 +128,11 @@ def _cycle_pair(coords, ndim, bcs, refine, mode, variant, ncyc, integ="rk2"):
 
 @pytest.mark.parametrize("coords,ndim,bcs,refine", CYCLE_CASES)
 def test_multilevel_task_cycles_strict_bit_identical(coords, ndim, bcs, refine):
-    """whole rk2 cycles on a refined mesh (fine and coarse blocks advance with the same global
-    dt, ghost zones through the multilevel exchange; no flux correction on either side)"""
+    """whole rk2 cycles on a refined mesh as the reference runs them: fine and coarse blocks
+    advance with the same global dt, ghost zones through the multilevel exchange, fluxes
+    corrected on every fine-coarse face between CalculateFluxes and ApplyUpdate"""
     m, osim, md, drv, ex = _cycle_pair(coords, ndim, bcs, refine, "tasks", "strict", 2)
+    assert ex.n["fc"] > 0
     assert drv.ncycle == osim.ncycle == 2 and drv.dt == osim.dt and drv.time == osim.time
     for ff, of in zip(md.fluids, osim.fluids):
         assert np.array_equal(ff.u0.get(), of.u0)
@@ -141,10 +144,89 @@ def test_multilevel_task_cycles_strict_bit_identical(coords, ndim, bcs, refine):
 @pytest.mark.parametrize("coords,ndim,bcs,refine", CYCLE_CASES[:2])
 def test_multilevel_fused_cycle_within_1e12(coords, ndim, bcs, refine):
     from tests.helpers import zone_rel_err
-    m, osim, md, drv, ex = _cycle_pair(coords, ndim, bcs, refine, "fused", "fast", 1)
+    # the fused path stores no fluxes: on a refined mesh it exists only as the explicitly
+    # non-conservative variant, compared with the oracle run the same way
+    m, osim, md, drv, ex = _cycle_pair(coords, ndim, bcs, refine, "fused", "fast", 1,
+                                       flux_correction=False)
     for ff, of in zip(md.fluids, osim.fluids):
         assert zone_rel_err(ff.u0.get(), of.u0, of.fp, "cons") <= 1e-12
         assert zone_rel_err(ff.prim.get(), of.prim, of.fp, "prim") <= 1e-12
+    ex.close()
+    md.close()
+
+
+def test_fused_path_refuses_a_refined_mesh_with_flux_correction():
+    from artemis_b200.driver import ArtemisDriver
+    m = _mesh(Coordinates.cartesian, 2, (B.outflow,) * 4 + (B.periodic,) * 2, [(1, 1, 0)])
+    md = MeshData(m, gas=gas_params(Coordinates.cartesian, "plm", "hlle"), materialize_fluxes=False)
+    ex = MultilevelExchange(md)
+    with pytest.raises(ValueError, match="flux correction"):
+        ArtemisDriver(md, "rk2", mode="fused", comm=ex)
+    ex.close()
+    md.close()
+
+
+FC_CASES = [CASES[0], CASES[1], CASES[2], CASES[3], CASES[4], CASES[5], CASES[6]]
+
+
+@pytest.mark.parametrize("coords,ndim,bcs,refine", FC_CASES)
+@pytest.mark.parametrize("variant", ["strict", "fast"])
+def test_flux_correct_equals_cpu_restriction(coords, ndim, bcs, refine, variant):
+    """ab200_flux_correct on random flux fields == SetFluxCorrections on the CPU (the oracle's
+    face restriction is pinned to RestrictAverage<GEOM>::Do<DIM, F1|F2|F3> of the reference):
+    bit for bit in the strict build; faces that no finer block touches stay untouched"""
+    from artemis_b200.multilevel import flux_correction_plan
+    m = _mesh(coords, ndim, bcs, refine)
+    gp, dp = gas_params(coords, "plm", "hlle", S=2), dust_params(coords, "plm", "hlle", S=2)
+    md = MeshData(m, gas=gp, dust=dp, variant=variant, materialize_fluxes=True)
+    ex = MultilevelExchange(md)
+    plan = flux_correction_plan(m)
+    assert ex.n["fc"] == 2 * len(plan) > 0
+    rng = np.random.default_rng(77)
+    host = []
+    for ff in md.fluids:
+        fl = [rng.standard_normal(m.shape(ff.fp.nvar)) if d < ndim else None for d in range(3)]
+        pf = [rng.standard_normal(m.shape(ff.fp.nspecies))
+              if (d < ndim and ff.pflux[d] is not None) else None for d in range(3)]
+        for d in range(ndim):
+            ff.flux[d].set(fl[d])
+            if pf[d] is not None:
+                ff.pflux[d].set(pf[d])
+        host.append((fl, pf))
+    ex.flux_correct()
+    for ff, (fl, pf) in zip(md.fluids, host):
+        want = [a.copy() if a is not None else None for a in fl]
+        multilevel_py.flux_correct(m, plan, want)
+        wantp = [a.copy() if a is not None else None for a in pf]
+        if any(a is not None for a in pf):
+            multilevel_py.flux_correct(m, plan, wantp)
+        for d in range(ndim):
+            got = ff.flux[d].get()
+            assert not np.array_equal(got, fl[d])
+            if variant == "strict":
+                assert np.array_equal(got, want[d])
+            else:
+                assert np.max(np.abs(got - want[d])) <= 1e-13 * np.max(np.abs(want[d]))
+            if pf[d] is not None:
+                gotp = ff.pflux[d].get()
+                if variant == "strict":
+                    assert np.array_equal(gotp, wantp[d])
+                else:
+                    assert np.max(np.abs(gotp - wantp[d])) <= 1e-13 * np.max(np.abs(wantp[d]))
+    ex.close()
+    md.close()
+
+
+def test_multilevel_task_cycles_conserve_mass_on_the_gpu():
+    """the GPU's own conservation check (periodic refined mesh, 3 rk2 cycles, task path)"""
+    m, osim, md, drv, ex = _cycle_pair(Coordinates.cartesian, 3, (B.periodic,) * 6,
+                                       [(1, 1, 1), (2, 2, 1)], "tasks", "fast", 3)
+    vol = np.prod(m.blk_dx, axis=1)
+    for ff, of in zip(md.fluids, osim.fluids):
+        u = ff.u0.get()
+        for v in range(min(5, ff.fp.nvar)):
+            tot = lambda a: sum(vol[b] * a[(b, v) + m.interior()].sum() for b in range(m.nb))
+            assert abs(tot(u) - tot(of.u0)) <= 1e-13 * tot(np.abs(of.u0))
     ex.close()
     md.close()
 

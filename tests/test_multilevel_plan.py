@@ -42,14 +42,21 @@ def test_calc_indices_equals_parthenons_own_function(nx, ng):
                     nb_l = tuple(6 + p for p in nb_par)
                     for ir in (BOUNDARY_INTERIOR_SEND, BOUNDARY_EXTERIOR_RECV, INTERIOR_SEND, INTERIOR_RECV):
                         for prores in (0, 1):
-                            out = (C.c_int * 6)()
-                            L.ar_calc_indices(ng, (C.c_int * 3)(*nx), 2, (C.c_longlong * 3)(*my_l),
-                                              2 + dlev, (C.c_longlong * 3)(*nb_l),
-                                              (C.c_int * 3)(*o), ir, prores, out)
-                            want = tuple((out[2 * d], out[2 * d + 1]) for d in range(3))
-                            got = calc_indices(ng, nx, 2, my_l, 2 + dlev, nb_l, o, ir, bool(prores))
-                            assert got == want, (o, dlev, my_l, nb_l, ir, prores)
-                            n += 1
+                            # cell-centred field, and the flux of one on the face normal to a
+                            # face offset (GetFluxCorrectionElements, bnd_info.cpp:72-84)
+                            els = [0]
+                            if sum(abs(v) for v in o) == 1:
+                                els.append([abs(v) for v in o].index(1) + 1)
+                            for el in els:
+                                out = (C.c_int * 6)()
+                                L.ar_calc_indices(ng, (C.c_int * 3)(*nx), 2, (C.c_longlong * 3)(*my_l),
+                                                  2 + dlev, (C.c_longlong * 3)(*nb_l),
+                                                  (C.c_int * 3)(*o), ir, prores, el, out)
+                                want = tuple((out[2 * d], out[2 * d + 1]) for d in range(3))
+                                got = calc_indices(ng, nx, 2, my_l, 2 + dlev, nb_l, o, ir,
+                                                   bool(prores), flux_el=el)
+                                assert got == want, (o, dlev, my_l, nb_l, ir, prores, el)
+                                n += 1
     assert n >= 288
 
 
@@ -149,3 +156,62 @@ def test_linear_field_is_reproduced_in_every_ghost_zone(ndim, bcs, refine):
                     sl[3 - d] = slice(m.ngd[d] + m.block_nx[d] - 2, None)
                     diff[tuple(sl)] = 0.0
         assert diff.max() <= 1e-13, (b, m.leaves[b], diff.max())
+
+
+# ---- flux correction (AddFluxCorrectionTasks, boundary_communication.cpp:454-461) ---------------
+def _total(mesh, u, var=0):
+    """volume integral of one conserved variable over all leaf blocks (Cartesian)"""
+    vol = np.prod(mesh.blk_dx[:, :mesh.ndim], axis=1)
+    return float(sum(vol[b] * u[(b, var) + mesh.interior()].sum() for b in range(mesh.nb)))
+
+
+@pytest.mark.parametrize("ndim,refine", [(3, [(1, 1, 1), (2, 1, 1)]), (2, [(1, 1, 0), (2, 2, 0)]),
+                                         (1, [(1, 0, 0)])])
+def test_flux_correction_makes_the_refined_mesh_conservative(ndim, refine):
+    """periodic refined mesh, random gas + dust state with jumps: with the fine fluxes restricted
+    onto every shared coarse face the volume integrals of mass, momentum and energy are
+    conserved to rounding over whole rk2 cycles; without the correction they are not"""
+    from artemis_b200.enums import Coordinates
+    from oracle.oracle_py import OracleSim
+    from tests.helpers import dust_params, gas_params, random_prim
+    drift = {}
+    for fc in (True, False):
+        m = _mesh(ndim, PER, refine)
+        gp = gas_params(Coordinates.cartesian, "plm", "hlle")
+        dp = dust_params(Coordinates.cartesian, "plm", "hlle", S=1)
+        sim = OracleSim(m, gas=gp, dust=dp)
+        sim.flux_correction = fc
+        sim.gas.prim[:] = random_prim(m, gp, seed=5)
+        sim.dust.prim[:] = random_prim(m, dp, seed=6)
+        sim.nlim = 3
+        sim.initialize()
+        # mass, momentum, total energy (the gas's internal-energy entry is not a conservation law)
+        nv = [5, dp.nvar]
+        before = [[_total(m, f.u0, v) for v in range(n)] for f, n in zip(sim.fluids, nv)]
+        scale = [[_total(m, np.abs(f.u0), v) for v in range(n)] for f, n in zip(sim.fluids, nv)]
+        sim.run()
+        after = [[_total(m, f.u0, v) for v in range(n)] for f, n in zip(sim.fluids, nv)]
+        drift[fc] = max(abs(a - b) / s for fa, fb, fs in zip(after, before, scale)
+                        for a, b, s in zip(fa, fb, fs))
+    assert drift[True] <= 5e-15, drift
+    assert drift[False] >= 1e-8, drift
+
+
+def test_flux_correction_plan_covers_every_fine_coarse_face_once():
+    m = _mesh(3, PER, [(1, 1, 1), (2, 1, 1), (1, 2, 2)])
+    from artemis_b200.multilevel import flux_correction_plan
+    plan = flux_correction_plan(m)
+    # every fine block has 3 outward faces of its parent; those shared with another refined
+    # root block are same-level and need no correction
+    n_face = sum(1 for b in range(m.nb) for nb in m.neighbors[b]
+                 if nb.level == m.leaves[b][0] - 1 and sum(map(abs, nb.offsets)) == 1)
+    assert len(plan) == n_face > 0
+    h = [m.block_nx[d] // 2 for d in range(3)]
+    seen = set()
+    for fb, cb, d, rbox, dbox in plan:
+        ext = [rbox[q][1] - rbox[q][0] + 1 for q in range(3)]
+        assert ext == [1 if q == d else h[q] for q in range(3)]          # one coarse face layer
+        assert [dbox[q][1] - dbox[q][0] + 1 for q in range(3)] == ext
+        key = (cb, d) + tuple(dbox[q][0] for q in range(3))
+        assert key not in seen                                           # written exactly once
+        seen.add(key)

@@ -51,6 +51,23 @@ def test_restriction_restatement_is_bit_identical_to_reference_code(coords):
 
 
 @needs_ref
+@pytest.mark.parametrize("el", [1, 2, 3])
+@pytest.mark.parametrize("coords", ALL)
+def test_face_restriction_restatement_is_bit_identical_to_reference_code(coords, el):
+    """flux correction restricts Metadata::Flux fields: RestrictAverage<GEOM>::Do<DIM, F1|F2|F3>"""
+    mesh, r, fine, coarse = _setup(coords, seed=4 + el)
+    if el > mesh.ndim:
+        pytest.skip("no faces in a collapsed direction")
+    box = _interior_box(r, mesh)
+    box[2 * (el - 1) + 1] += 1          # a face field has one more element along its direction
+    a, b = coarse.copy(), coarse.copy()
+    oracle_py.restrict_average_face(oracle_py.lib(), r, fine, a, box, el)
+    oracle_py.restrict_average_face(ref_py.lib(), r, fine, b, box, el, prefix="ar")
+    assert np.array_equal(a, b)
+    assert not np.array_equal(a, coarse)
+
+
+@needs_ref
 @pytest.mark.parametrize("coords", ALL)
 def test_prolongation_restatement_is_bit_identical_to_reference_code(coords):
     mesh, r, fine, coarse = _setup(coords, seed=2)
