@@ -672,8 +672,18 @@ int ab200_set_topology(ab200_ctx *c, int nbx, int nby, int nbz, const int bc[6])
   AB_REQUIRE(nbx > 0 && nby > 0 && nbz > 0 && nbx * nby * nbz == c->g.nb, AB200_EINVAL,
              "ab200_set_topology: lattice does not match the number of bound blocks");
   for (int i = 0; i < 6; ++i)
-    AB_REQUIRE(bc[i] >= AB200_BC_PERIODIC && bc[i] <= AB200_BC_NONE, AB200_EINVAL,
+    AB_REQUIRE(bc[i] >= AB200_BC_PERIODIC && bc[i] <= AB200_BC_FIXED, AB200_EINVAL,
                "ab200_set_topology: unknown boundary flag");
+  {
+    bool fixed = false, remote = false;
+    for (int i = 0; i < 6; ++i) {
+      fixed = fixed || bc[i] == AB200_BC_FIXED;
+      remote = remote || bc[i] == AB200_BC_NONE;
+    }
+    AB_REQUIRE(!(fixed && remote), AB200_EINVAL,
+               "ab200_set_topology: AB200_BC_FIXED faces need a single-rank topology "
+               "(no AB200_BC_NONE face)");
+  }
   c->topo.set = true;
   c->topo.nbx = nbx; c->topo.nby = nby; c->topo.nbz = nbz;
   for (int i = 0; i < 6; ++i) c->topo.bc[i] = bc[i];

@@ -120,8 +120,44 @@ k_fill_ghosts(GridDev g, FluidDev f, int nbx, int nby, int nbz, int bc0, int bc1
   // and only the remaining directions are resolved; cells with no remote direction were
   // already finished by the first pass.
   bool remote = false, local_move = false;
+  // AB200_BC_FIXED (position-only user conditions, Disk::DiskBoundaryIC): Parthenon applies the
+  // physical conditions face by face in x1 -> x2 -> x3 order over the full transverse extent,
+  // after the neighbour exchange (which never reaches zones outside the domain).  A zone
+  // beyond a FIXED face therefore ends with its own stored value unless a LATER axis puts it
+  // beyond an outflow / reflecting face, which then copies the (equally fixed) zone at the
+  // clamped / mirrored position of the same block.
+  int fixed_axis = -1;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
+    const int o = src[d] < s[d] ? -1 : (src[d] > e[d] ? 1 : 0);
+    const int ln = l[d] + o;
+    if (o && (ln < 0 || ln >= nbd[d]) && bc[2 * d + (o > 0)] == AB200_BC_FIXED) fixed_axis = d;
+  }
+  if (fixed_axis >= 0) {
+    if (remote_pass) return;
+    bool moved = false;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (d <= fixed_axis) continue;
+      const int o = src[d] < s[d] ? -1 : (src[d] > e[d] ? 1 : 0);
+      const int ln = l[d] + o;
+      if (!o || (ln >= 0 && ln < nbd[d])) continue;
+      const int type = bc[2 * d + (o > 0)];
+      if (type == AB200_BC_OUTFLOW) {
+        src[d] = o > 0 ? e[d] : s[d];
+        moved = true;
+      } else if (type == AB200_BC_REFLECT) {
+        const int ref = o > 0 ? e[d] : s[d];
+        src[d] = 2 * ref + (o > 0 ? 1 : -1) - src[d];
+        flip[d] = true;
+        moved = true;
+      }
+    }
+    if (!moved) return;  // the zone keeps the value the caller's condition put there
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    if (fixed_axis >= 0) break;
     const int o = src[d] < s[d] ? -1 : (src[d] > e[d] ? 1 : 0);
     if (!o) continue;
     const int ln = l[d] + o;
@@ -247,7 +283,7 @@ int launch_fill_ghosts(ab200_ctx *c, int fluid, int remote_pass) {
 // *entire* index range so corners inherit the previous faces' fills.
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-k_physical_bc(GridDev g, FluidDev f, int nbx, int nby, int nbz, int face, int type,
+k_physical_bc(GridDev g, FluidDev f, int nbx, int nby, int nbz, int face, int type, int fixed_mask,
               const int *__restrict__ gvars, const int *__restrict__ gvdir, int ngv) {
   const int d = face >> 1, outer = face & 1;
   const int nt[3] = {g.ni, g.nj, g.nk};
@@ -275,6 +311,14 @@ k_physical_bc(GridDev g, FluidDev f, int nbx, int nby, int nbz, int face, int ty
   lb[d] = outer ? nbd[d] - 1 : 0;
   const int b = lb[0] + nbx * (lb[1] + nby * lb[2]);
   cidx[d] += outer ? e[d] + 1 : 0;
+  // zones beyond an AB200_BC_FIXED face of a LATER axis belong to that face (Parthenon would
+  // overwrite them with the user's profile when it reaches that axis): leave them alone
+#pragma unroll
+  for (int d2 = 0; d2 < 3; ++d2) {
+    if (d2 <= d) continue;
+    if (cidx[d2] < s[d2] && lb[d2] == 0 && (fixed_mask >> (2 * d2)) & 1) return;
+    if (cidx[d2] > e[d2] && lb[d2] == nbd[d2] - 1 && (fixed_mask >> (2 * d2 + 1)) & 1) return;
+  }
   const int ref = outer ? e[d] : s[d];
   const int offset = 2 * ref + (outer ? 1 : -1);
   int sidx[3] = {cidx[0], cidx[1], cidx[2]};
@@ -306,8 +350,11 @@ int launch_physical_bcs(ab200_ctx *c, int fluid) {
     long long nbf = (long long)nbd[0] * nbd[1] * nbd[2] / nbd[d];
     const long long total = ext[0] * ext[1] * ext[2] * nbf;
     const unsigned grid = (unsigned)((total + kThreads - 1) / kThreads);
+    int fixed_mask = 0;
+    for (int q = 0; q < 6; ++q) fixed_mask |= (tp.bc[q] == AB200_BC_FIXED) << q;
     k_physical_bc<<<grid, kThreads, 0, c->stream>>>(g, fh.d, tp.nbx, tp.nby, tp.nbz, face, type,
-                                                    fh.ghost_vars, fh.ghost_vdir, fh.n_ghost);
+                                                    fixed_mask, fh.ghost_vars, fh.ghost_vdir,
+                                                    fh.n_ghost);
     c->launches++;
   }
   AB_CUDA(cudaGetLastError());

@@ -1,7 +1,11 @@
 // host_path.cu -- ab200_cycles_host: the entry point for callers whose state lives in HOST
 // memory (a Kokkos-OpenMP Parthenon build; bench.py's end-to-end leg).  Uploads primitives,
 // runs full integrator cycles on the device with the fused path, downloads the result.
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "ab200_ctx.cuh"
 
@@ -14,7 +18,130 @@ const Stage kRK1[] = {{0.0, 1.0, 1.0}};
 const Stage kRK2[] = {{0.0, 1.0, 1.0}, {0.5, 0.5, 0.5}};
 const Stage kVL2[] = {{0.0, 1.0, 0.5}, {0.0, 1.0, 1.0}};
 const Stage kRK3[] = {{0.0, 1.0, 1.0}, {0.25, 0.75, 0.25}, {2.0 / 3.0, 1.0 / 3.0, 2.0 / 3.0}};
+
+// ---- interior-only transfers (ab200_set_host_transfer) ---------------------------------------
+// Zero-copy variant: one warp moves one interior row [is..ie] of one (block, entry) array
+// between the pinned host array (addressed in place over PCIe) and the device array.  Rows are
+// 512 B at BASELINE's 64^3 MeshBlocks; every lane keeps kRowsPerWarp independent 8-byte
+// accesses in flight so the PCIe round trip is covered by memory-level parallelism, not by
+// occupancy.  `skip0..skip1` = pack entries that do not travel (gas pressure on the way in).
+constexpr int kXferThreads = 256;
+constexpr int kRowsPerWarp = 4;
+template <bool TO_DEVICE, typename T>
+__global__ void __launch_bounds__(kXferThreads)
+k_host_rows(GridDev g, double *const *__restrict__ tab, int nvar, double *host, int skip0,
+            int skip1) {
+  constexpr int W = sizeof(T) / sizeof(double);  // doubles per access (1, or 2 when rows are 16-byte aligned)
+  const int nir = (g.ie - g.is + 1) / W, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
+  const int e = blockIdx.y;  // (block, entry)
+  const int n = e % nvar;
+  if (n >= skip0 && n < skip1) return;
+  const size_t cells = (size_t)g.ni * g.nj * g.nk;
+  T *dev = reinterpret_cast<T *>(tab[e]);
+  T *hst = reinterpret_cast<T *>(host + (size_t)e * cells);
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nrows = njr * nkr;
+  const int pitch = g.ni / W, i_s = g.is / W;
+  for (int r0 = warp * kRowsPerWarp; r0 < nrows; r0 += nwarps * kRowsPerWarp) {
+    for (int i0 = lane; i0 < nir; i0 += 32) {
+      T v[kRowsPerWarp];
+#pragma unroll
+      for (int q = 0; q < kRowsPerWarp; ++q) {
+        const int r = r0 + q;
+        if (r < nrows) {
+          const size_t off = ((size_t)(g.ks + r / njr) * g.nj + (g.js + r % njr)) * pitch + i_s + i0;
+          v[q] = TO_DEVICE ? __ldcs(hst + off) : __ldcs(dev + off);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kRowsPerWarp; ++q) {
+        const int r = r0 + q;
+        if (r < nrows) {
+          const size_t off = ((size_t)(g.ks + r / njr) * g.nj + (g.js + r % njr)) * pitch + i_s + i0;
+          if (TO_DEVICE) dev[off] = v[q];
+          else __stcs(hst + off, v[q]);
+        }
+      }
+    }
+  }
+}
+
+// device-visible alias of a pinned host array (UVA: normally the same address)
+int host_alias(double *h, double **out) {
+  cudaPointerAttributes at;
+  std::memset(&at, 0, sizeof at);
+  cudaError_t e = cudaPointerGetAttributes(&at, h);
+  if (e != cudaSuccess) (void)cudaGetLastError();
+  AB_REQUIRE(e == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer, AB200_EINVAL,
+             "ab200_cycles_host: AB200_HOST_ZERO_COPY needs pinned host arrays "
+             "(cudaHostAlloc / cudaHostRegister)");
+  *out = (double *)at.devicePointer;
+  return AB200_OK;
+}
+
+// interior zones of every (block, entry) array of one fluid, host <-> device
+int interior_transfer(ab200_ctx *c, int fl, double *host, bool to_device,
+                      const std::vector<double *> &tab) {
+  const GridDev &g = c->g;
+  const FluidDev &f = c->fl[fl].d;
+  const size_t cells = (size_t)g.ni * g.nj * g.nk;
+  const int skip0 = (to_device && fl == AB200_GAS) ? 4 * f.S : 0;
+  const int skip1 = (to_device && fl == AB200_GAS) ? 5 * f.S : 0;
+  const int nir = g.ie - g.is + 1, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
+  if (c->host_transfer & (to_device ? AB200_HOST_ZERO_COPY_IN : AB200_HOST_ZERO_COPY_OUT)) {
+    double *alias = nullptr;
+    AB_TRY(host_alias(host, &alias));
+    const int nrows = njr * nkr;
+    const int warps = (nrows + kRowsPerWarp - 1) / kRowsPerWarp;
+    const unsigned gx = (unsigned)std::max(1, std::min((warps * 32 + kXferThreads - 1) / kXferThreads, 64));
+    const size_t nent = tab.size();
+    // 16-byte accesses when every interior row starts and ends on a 16-byte boundary
+    bool wide = (nir % 2 == 0) && (g.is % 2 == 0) && (g.ni % 2 == 0) && (cells % 2 == 0) &&
+                ((uintptr_t)alias % 16 == 0) && !getenv("AB200_XFER_SCALAR");
+    for (size_t e = 0; e < tab.size() && wide; ++e) wide = ((uintptr_t)tab[e] % 16 == 0);
+    for (size_t e0 = 0; e0 < nent; e0 += 65535) {  // grid.y limit
+      const unsigned ny = (unsigned)std::min<size_t>(65535, nent - e0);
+      dim3 grid(gx, ny);
+#define AB_XFER(TD, T)                                                                            \
+  k_host_rows<TD, T><<<grid, kXferThreads, 0, c->stream>>>(g, f.prim + e0, f.nvar,                 \
+                                                          alias + e0 * cells, skip0, skip1)
+      if (to_device) { if (wide) AB_XFER(true, double2); else AB_XFER(true, double); }
+      else { if (wide) AB_XFER(false, double2); else AB_XFER(false, double); }
+#undef AB_XFER
+      c->launches++;
+    }
+    AB_CUDA(cudaGetLastError());
+    return AB200_OK;
+  }
+  // strided DMA: one 3-D copy per array (rows of nir doubles, pitch ni)
+  for (size_t e = 0; e < tab.size(); ++e) {
+    const int n = (int)(e % f.nvar);
+    if (n >= skip0 && n < skip1) continue;
+    cudaMemcpy3DParms p;
+    std::memset(&p, 0, sizeof p);
+    double *h = host + e * cells;
+    const cudaPitchedPtr hp = make_cudaPitchedPtr(h, (size_t)g.ni * sizeof(double), g.ni, g.nj);
+    const cudaPitchedPtr dp = make_cudaPitchedPtr(tab[e], (size_t)g.ni * sizeof(double), g.ni, g.nj);
+    p.srcPtr = to_device ? hp : dp;
+    p.dstPtr = to_device ? dp : hp;
+    p.srcPos = p.dstPos = make_cudaPos((size_t)g.is * sizeof(double), g.js, g.ks);
+    p.extent = make_cudaExtent((size_t)nir * sizeof(double), njr, nkr);
+    p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    AB_CUDA(cudaMemcpy3DAsync(&p, c->stream));
+  }
+  return AB200_OK;
+}
 }  // namespace
+
+extern "C" int ab200_set_host_transfer(ab200_ctx *c, int flags) {
+  AB_REQUIRE(c, AB200_EINVAL, "ab200_set_host_transfer: null context");
+  AB_REQUIRE((flags & ~(AB200_HOST_INTERIOR_IN | AB200_HOST_INTERIOR_OUT | AB200_HOST_ZERO_COPY)) == 0,
+             AB200_EINVAL, "ab200_set_host_transfer: unknown flag");
+  c->host_transfer = flags;
+  return AB200_OK;
+}
 
 extern "C" int ab200_run_cycles(ab200_ctx *c, int integrator, int ncycles, double tlim) {
   AB_REQUIRE(c && c->grid_set, AB200_ESTATE, "ab200_run_cycles: no grid bound");
@@ -85,12 +212,27 @@ extern "C" int ab200_cycles_host(ab200_ctx *c, int integrator, int ncycles, doub
     AB_CUDA(cudaMemcpyAsync(tab.data(), f.prim, tab.size() * sizeof(double *),
                             cudaMemcpyDeviceToHost, c->stream));
     AB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->host_transfer & AB200_HOST_INTERIOR_IN) {
+      AB_TRY(interior_transfer(c, fl, hp[fl], true, tab));
+      continue;
+    }
     for (size_t e = 0; e < tab.size(); ++e) {
       const int n = (int)(e % f.nvar);
       if (fl == AB200_GAS && n >= 4 * f.S && n < 5 * f.S) continue;  // pressure: derived
       AB_CUDA(cudaMemcpyAsync(tab[e], hp[fl] + e * cells, cells * sizeof(double),
                               cudaMemcpyHostToDevice, c->stream));
     }
+  }
+  if (c->host_transfer & AB200_HOST_INTERIOR_IN) {
+    // ghost primitives from the just-uploaded interior zones: same-GPU exchange + physical
+    // boundaries (what the end of the previous stage did on the caller's side); the pressure
+    // entries they copy are stale, PrimToCons below recomputes P over the entire domain
+    const bool lazy = c->ghost_cons_lazy;
+    c->ghost_cons_lazy = true;
+    const int rc_fill = ab200_fill_ghosts(c);
+    c->ghost_cons_lazy = lazy;
+    AB_TRY(rc_fill);
+    for (int fl = 0; fl < 2; ++fl) c->fl[fl].ghost_cons_stale = false;  // full PrimToCons follows
   }
   AB_TRY(ab200_prim_to_cons(c));  // cons == PrimToCons(prim) at every cycle boundary
   double ts[4] = {0, 0, 0, 0};
@@ -121,6 +263,13 @@ extern "C" int ab200_cycles_host(ab200_ctx *c, int integrator, int ncycles, doub
     AB_CUDA(cudaMemcpyAsync(tc.data(), f.u0, tc.size() * sizeof(double *),
                             cudaMemcpyDeviceToHost, c->stream));
     AB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->host_transfer & AB200_HOST_INTERIOR_OUT) {
+      AB_REQUIRE(!hc[fl], AB200_EINVAL,
+                 "ab200_cycles_host: AB200_HOST_INTERIOR_OUT returns primitives only "
+                 "(pass NULL for the conserved arrays)");
+      AB_TRY(interior_transfer(c, fl, hp[fl], false, tp));
+      continue;
+    }
     for (size_t e = 0; e < tp.size(); ++e) {
       AB_CUDA(cudaMemcpyAsync(hp[fl] + e * cells, tp[e], cells * sizeof(double),
                               cudaMemcpyDeviceToHost, c->stream));

@@ -35,6 +35,9 @@ class BoundaryFlag(IntEnum):
     periodic = 0
     outflow = 1
     reflect = 2
+    # user condition that depends on position only (`ic` of src/pgen/disk.hpp, strat.hpp):
+    # AB200_BC_FIXED -- the ghost zones keep the problem generator's profile
+    fixed = 4
 
 
 def CoordSelect(sys: str, ndim: int) -> Coordinates:

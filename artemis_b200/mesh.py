@@ -129,6 +129,8 @@ class UniformMesh:
         for d in (1, 2, 3):
             for side in ("i", "o"):
                 name = pin.GetOrAddString("parthenon/mesh", f"{side}x{d}_bc", "outflow")
+                if name == "ic":     # Disk / Strat `ic` user condition: position-only profile
+                    name = "fixed"
                 if name not in BoundaryFlag.__members__:
                     raise ValueError(f"boundary flag {name!r} is outside the hot-path scope")
                 bcs.append(BoundaryFlag[name])

@@ -45,6 +45,12 @@ def parse():
     ap.add_argument("--cpu-cycles", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-transfer", default="interior",
+                    choices=["full", "interior", "interior_zc", "interior_dma"],
+                    help="N=1 e2e leg: which zones of the pinned host arrays cross PCIe "
+                         "(ab200_set_host_transfer): whole arrays; interior zones, in by a copy "
+                         "kernel on the pinned array and out by strided DMA (the measured best); "
+                         "copy kernels both ways; strided DMA both ways")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
                     help="BASELINE.json config: 2 = the headline (3-D blast, PPM+HLLC, 256^3 per "
                          "GPU, weak scaling); 3 = gas + 4 dust species, PLM+HLLE, periodic, "
@@ -620,6 +626,9 @@ def main():
         # function of it and are not requested (cons pointer NULL); the input's pressure entries
         # are never uploaded (recomputed by PrimToCons)
         del phc, hc
+        xfer = {"full": 0, "interior": 1 | 2 | 4, "interior_zc": 1 | 2 | 4 | 8,
+                "interior_dma": 1 | 2}[args.e2e_transfer]
+        md.call("ab200_set_host_transfer", xfer)
         md.call("ab200_cycles_host", integ, 1, C.byref(dt_io), php, None, None, None)  # warm-up
         md.synchronize()
         t0 = time.perf_counter()
@@ -627,12 +636,18 @@ def main():
             md.call("ab200_cycles_host", integ, 1, C.byref(dt_io), php, None, None, None)
         md.synchronize()
         te = (time.perf_counter() - t0) / args.e2e_steps
-        nbytes = int(np.prod(shape)) * 8
+        md.call("ab200_set_host_transfer", 0)
+        # bytes that crossed PCIe: whole arrays (ghost zones included) or interior zones only
+        nbytes = (int(np.prod(shape)) if xfer == 0 else mesh.interior_zones * nv) * 8
         e2e = {"value": mesh.interior_zones / te, "unit": "zone-cycles/s",
                "h2d_bytes_per_step": nbytes * 5 // 6, "d2h_bytes_per_step": nbytes,
-               "ms_per_step": te * 1e3,
+               "ms_per_step": te * 1e3, "transfer": args.e2e_transfer,
                "api": "ab200_cycles_host (pinned host primitives in, pressure not uploaded; "
-                      "primitives out, cons not requested)"}
+                      "primitives out, cons not requested)" +
+                      ("" if xfer == 0 else "; ab200_set_host_transfer: interior zones only, ghost "
+                       "zones rebuilt on the device" +
+                       {7: " (in: copy kernel on the pinned array, out: strided DMA)",
+                        15: " (copy kernels on the pinned arrays)", 3: " (strided DMA)"}[xfer])}
     elif not args.no_e2e:
         # N > 1: the same end-to-end step through the public entry points every rank calls --
         # pinned host primitives in, ab200_prim_to_cons, one device-resident cycle with the NCCL

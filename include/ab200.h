@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AB200_ABI_VERSION 9
+#define AB200_ABI_VERSION 10
 
 /* src/artemis.hpp:78-105 */
 enum { AB200_CARTESIAN = 0, AB200_CYLINDRICAL = 1, AB200_SPHERICAL1D = 2,
@@ -52,7 +52,17 @@ enum { AB200_HLLC = 0, AB200_HLLE = 1, AB200_LLF = 2 };
 enum { AB200_PCM = 0, AB200_PLM = 1, AB200_PPM = 2 };
 enum { AB200_GAS = 0, AB200_DUST = 1 };
 enum { AB200_BC_PERIODIC = 0, AB200_BC_OUTFLOW = 1, AB200_BC_REFLECT = 2,
-       AB200_BC_NONE = 3 /* face handled by the caller (remote rank / user BC) */ };
+       AB200_BC_NONE = 3 /* face handled by the caller (remote rank / user BC) */,
+       /* User boundary condition that is a function of POSITION only -- `ic` of the disk and
+        * strat problem generators (Disk::DiskBoundaryIC, src/pgen/disk.hpp:595-633: every ghost
+        * zone of the face, over the full transverse extent, receives the initial-condition
+        * profile at its own position; inputs/disk/disk_sph.in uses it on four faces).  Such
+        * ghost zones never change after Mesh::Initialize applied the condition once, so the
+        * library keeps them resident: zones beyond a FIXED face are never written, except
+        * where a LATER face in Parthenon's x1 -> x2 -> x3 order (outflow / reflect) covers
+        * them, which then copies from the fixed zones as the reference does.  Single-rank
+        * topologies (no AB200_BC_NONE face). */
+       AB200_BC_FIXED = 4 };
 
 enum { AB200_OK = 0, AB200_EINVAL = 1, AB200_ECUDA = 2, AB200_ESTATE = 3, AB200_ENOMEM = 4 };
 
@@ -484,6 +494,34 @@ int ab200_finish_remote_ghosts(ab200_ctx *ctx);
 int ab200_cycles_host(ab200_ctx *ctx, int integrator, int ncycles, double *dt_io,
                       double *gas_prim_host, double *gas_cons_host, double *dust_prim_host,
                       double *dust_cons_host);
+/* Which zones of the host arrays cross PCIe in ab200_cycles_host (default 0: whole arrays).
+ * Ghost zones are redundant at a cycle boundary -- the reference refills them from interior
+ * zones at the end of every stage (src/artemis_driver.cpp:258-261) -- and they are 30 % of a
+ * 64^3 MeshBlock with nghost = 4:
+ *   AB200_HOST_INTERIOR_IN   upload interior zones only and rebuild the ghost zones on the device
+ *                            with the library's exchange + physical boundaries before
+ *                            PrimToCons.  Identical results whenever the caller's ghost zones
+ *                            were consistent (any state a stage driver or Mesh::Initialize
+ *                            left behind); the caller's ghost values are never read.
+ *   AB200_HOST_INTERIOR_OUT  download interior zones only; the ghost zones of the host arrays
+ *                            keep their old contents (the next call with _IN does not read
+ *                            them; a host consumer that needs them refills them itself).
+ *   AB200_HOST_ZERO_COPY_IN / _OUT   the interior rows of that direction are moved by copy
+ *                            kernels that read / write the PINNED host arrays in place over PCIe
+ *                            (cudaHostAlloc / cudaHostRegister memory; AB200_EINVAL otherwise)
+ *                            instead of strided DMA (cudaMemcpy3DAsync, which also accepts
+ *                            pageable memory).  Measured on B200 / PCIe 5 (256^3 zones in 64^3
+ *                            MeshBlocks, profiles/r02_e2e_transfer_ab.json): strided DMA is the
+ *                            better engine on the way out, the copy kernel by far on the way in
+ *                            (host-to-device DMA of 512-byte rows runs at a fraction of the link
+ *                            rate), so AB200_HOST_INTERIOR_IN | _OUT | AB200_HOST_ZERO_COPY_IN is
+ *                            the combination bench.py's end-to-end leg uses. */
+#define AB200_HOST_INTERIOR_IN 1
+#define AB200_HOST_INTERIOR_OUT 2
+#define AB200_HOST_ZERO_COPY_IN 4
+#define AB200_HOST_ZERO_COPY_OUT 8
+#define AB200_HOST_ZERO_COPY (AB200_HOST_ZERO_COPY_IN | AB200_HOST_ZERO_COPY_OUT)
+int ab200_set_host_transfer(ab200_ctx *ctx, int flags);
 
 /* Device-resident driver loop: `ncycles` cycles of {per stage: ab200_fused_stage ->
  * ab200_exchange_ghosts -> ab200_apply_physical_bcs -> ab200_prim_to_cons_ghosts} followed by

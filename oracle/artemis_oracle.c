@@ -998,6 +998,12 @@ static void range_recv(int off, int s, int e, int ng, int *lo, int *hi) {
 void ao_exchange_ghosts_phase(const ao_grid *g, int nbx, int nby, int nbz, const int *bc,
                               int nvar, double *a, int nv, const int *vars,
                               const int *vec_dir, int phases) {
+  ao_exchange_ghosts_ic(g, nbx, nby, nbz, bc, nvar, a, nv, vars, vec_dir, phases, 0);
+}
+
+void ao_exchange_ghosts_ic(const ao_grid *g, int nbx, int nby, int nbz, const int *bc, int nvar,
+                           double *a, int nv, const int *vars, const int *vec_dir, int phases,
+                           const double *ic) {
   const int ng = g->ng;
   const int nbd[3] = {nbx, nby, nbz};
   const int ox3 = g->ndim > 2 ? 1 : 0, ox2 = g->ndim > 1 ? 1 : 0;
@@ -1055,6 +1061,14 @@ void ao_exchange_ghosts_phase(const ao_grid *g, int nbx, int nby, int nbz, const
       int lo[3] = {0, 0, 0}, hi[3] = {nt[0] - 1, nt[1] - 1, nt[2] - 1};
       if (outer) { lo[d] = e[d] + 1; hi[d] = nt[d] - 1; }
       else { lo[d] = 0; hi[d] = s[d] - 1; }
+      if (bc[face] == AO_BC_IC) { /* src/pgen/disk.hpp:595-633: profile at the zone itself */
+        for (int v = 0; v < (ic ? nv : 0); ++v)
+          for (int k = lo[2]; k <= hi[2]; ++k)
+            for (int j = lo[1]; j <= hi[1]; ++j)
+              for (int i = lo[0]; i <= hi[0]; ++i)
+                a[IDX(g, nvar, b, vars[v], k, j, i)] = ic[IDX(g, nvar, b, vars[v], k, j, i)];
+        continue;
+      }
       for (int v = 0; v < nv; ++v) {
         const double sgn = (bc[face] == AO_BC_REFLECT && vec_dir[v] == d + 1) ? -1.0 : 1.0;
         for (int k = lo[2]; k <= hi[2]; ++k)

@@ -39,7 +39,8 @@ enum { AO_CARTESIAN = 0, AO_CYLINDRICAL = 1, AO_SPHERICAL1D = 2, AO_SPHERICAL2D 
 enum { AO_HLLC = 0, AO_HLLE = 1, AO_LLF = 2 };
 enum { AO_PCM = 0, AO_PLM = 1, AO_PPM = 2 };
 enum { AO_GAS = 0, AO_DUST = 1 };
-enum { AO_BC_PERIODIC = 0, AO_BC_OUTFLOW = 1, AO_BC_REFLECT = 2, AO_BC_NONE = 3 };
+enum { AO_BC_PERIODIC = 0, AO_BC_OUTFLOW = 1, AO_BC_REFLECT = 2, AO_BC_NONE = 3,
+       AO_BC_IC = 4 /* user condition `ic`: the initial-condition profile (src/pgen/disk.hpp:595-633) */ };
 
 typedef struct {
   int geom, ndim, ng, nb;
@@ -87,6 +88,12 @@ void ao_exchange_ghosts(const ao_grid *g, int nbx, int nby, int nbz, const int *
 void ao_exchange_ghosts_phase(const ao_grid *g, int nbx, int nby, int nbz, const int *bc,
                               int nvar, double *a, int nv, const int *vars,
                               const int *vec_dir, int phases);
+/* the same with user `ic` faces (AO_BC_IC): `ic` holds the initial-condition profile in every
+ * zone (same shape as `a`); an ic face sets all its ghost zones, over the full transverse extent,
+ * to the profile at their own position -- Disk::DiskBoundaryIC's par_for_bndry */
+void ao_exchange_ghosts_ic(const ao_grid *g, int nbx, int nby, int nbz, const int *bc, int nvar,
+                           double *a, int nv, const int *vars, const int *vec_dir, int phases,
+                           const double *ic);
 
 /* Geometry probes (used by tests to compare against oracle/_ref and the CUDA tables) */
 void ao_geom_cell(int geom, const double *xmin, const double *dx, int k, int j, int i,

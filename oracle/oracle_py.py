@@ -339,9 +339,15 @@ class OracleSim:
         vars_ = np.array(fs.ghost_vars, dtype=np.int32)
         vdir = np.array(fs.vec_dir, dtype=np.int32)
         bc = m.bc_ints()
-        self.L.ao_exchange_ghosts(C.byref(self.g), *[int(v) for v in m.lattice_n],
-                                  bc.ctypes.data_as(_IP), fs.fp.nvar, _p(fs.prim), len(vars_),
-                                  vars_.ctypes.data_as(_IP), vdir.ctypes.data_as(_IP))
+        if (bc == 4).any() and getattr(fs, "ic", None) is None:
+            # user `ic` faces: the problem generator's profile = the state the run starts from
+            # (ghost zones included), kept for Disk::DiskBoundaryIC
+            fs.ic = fs.prim.copy()
+        ic = getattr(fs, "ic", None)
+        self.L.ao_exchange_ghosts_ic(C.byref(self.g), *[int(v) for v in m.lattice_n],
+                                     bc.ctypes.data_as(_IP), fs.fp.nvar, _p(fs.prim), len(vars_),
+                                     vars_.ctypes.data_as(_IP), vdir.ctypes.data_as(_IP), 3,
+                                     _p(ic) if ic is not None else None)
 
     def EstimateTimestep(self):
         dts = []

@@ -113,3 +113,34 @@ def test_sub_lattice_partition_reproduces_global_block_geometry():
         gb = int(l[0] + 4 * (l[1] + 4 * l[2]))
         assert np.array_equal(t.blk_xmin[b], g.blk_xmin[gb])
         assert np.array_equal(t.blk_dx[b], g.blk_dx[gb])
+
+
+def test_oracle_ic_boundary_keeps_the_profile_and_later_faces_copy_from_it():
+    """AO_BC_IC (Disk::DiskBoundaryIC): every ghost zone of an ic face holds the generator's
+    profile at its own position; a later outflow face copies the (fixed) zones of the corner"""
+    import ctypes as C
+    import numpy as np
+    from artemis_b200.enums import BoundaryFlag as B, Coordinates
+    from oracle import oracle_py
+    from tests.helpers import gas_params, make_mesh, random_prim
+    mesh = make_mesh(Coordinates.cartesian, 3, bcs=(B.fixed, B.fixed, B.outflow, B.outflow, B.periodic, B.periodic))
+    gp = gas_params(Coordinates.cartesian, "plm", "hlle")
+    sim = oracle_py.OracleSim(mesh, gas=gp)
+    prim = random_prim(mesh, gp, seed=3)
+    sim.gas.prim[:] = prim
+    sim.nlim = 2
+    sim.initialize()
+    sim.run()
+    ng = mesh.nghost
+    inner = mesh.interior()
+    lo = [b for b in range(mesh.nb) if b % mesh.lattice_n[0] == 0]
+    vs = [0, 1, 2, 3, 5]   # FillGhost fields (pressure is derived)
+    got, ic = sim.gas.prim[lo][:, vs], prim[lo][:, vs]
+    assert np.array_equal(got[:, :, inner[0], inner[1], :ng], ic[:, :, inner[0], inner[1], :ng])
+    # x2 outflow is applied after x1: the corner zones copy the first interior row of the slab
+    lo2 = [b for b in lo if (b // mesh.lattice_n[0]) % mesh.lattice_n[1] == 0]
+    g2 = sim.gas.prim[lo2][:, vs]
+    for j in range(ng):
+        assert np.array_equal(g2[:, :, inner[0], j, :ng], g2[:, :, inner[0], ng, :ng])
+    assert not np.array_equal(sim.gas.prim[(slice(None), slice(None)) + inner],
+                              prim[(slice(None), slice(None)) + inner])
