@@ -29,12 +29,12 @@ constexpr int kXferThreads = 256;
 constexpr int kRowsPerWarp = 4;
 template <bool TO_DEVICE, typename T>
 __global__ void __launch_bounds__(kXferThreads)
-k_host_rows(GridDev g, double *const *__restrict__ tab, int nvar, double *host, int skip0,
-            int skip1) {
+k_host_rows(GridDev g, double *const *__restrict__ tab, int nvar, int e0, double *host,
+            int skip0, int skip1) {
   constexpr int W = sizeof(T) / sizeof(double);  // doubles per access (1, or 2 when rows are 16-byte aligned)
   const int nir = (g.ie - g.is + 1) / W, njr = g.je - g.js + 1, nkr = g.ke - g.ks + 1;
-  const int e = blockIdx.y;  // (block, entry)
-  const int n = e % nvar;
+  const int e = blockIdx.y;  // (block, entry) relative to the launch's first entry e0
+  const int n = (e0 + e) % nvar;
   if (n >= skip0 && n < skip1) return;
   const size_t cells = (size_t)g.ni * g.nj * g.nk;
   T *dev = reinterpret_cast<T *>(tab[e]);
@@ -105,7 +105,7 @@ int interior_transfer(ab200_ctx *c, int fl, double *host, bool to_device,
       const unsigned ny = (unsigned)std::min<size_t>(65535, nent - e0);
       dim3 grid(gx, ny);
 #define AB_XFER(TD, T)                                                                            \
-  k_host_rows<TD, T><<<grid, kXferThreads, 0, c->stream>>>(g, f.prim + e0, f.nvar,                 \
+  k_host_rows<TD, T><<<grid, kXferThreads, 0, c->stream>>>(g, f.prim + e0, f.nvar, (int)(e0 % f.nvar), \
                                                           alias + e0 * cells, skip0, skip1)
       if (to_device) { if (wide) AB_XFER(true, double2); else AB_XFER(true, double); }
       else { if (wide) AB_XFER(false, double2); else AB_XFER(false, double); }

@@ -120,6 +120,8 @@ k_block_bcs(GridDev g, GridDev gc, FluidDev f0, FluidDev f1, const BcDev *__rest
   }
 }
 
+constexpr int kMaxGridY = 65535;
+
 struct FluxCorDev {
   int fluid, fine_block, coarse_block, dir;
   int cis, cie, cjs, cje, cks, cke;  // coarse-index box of the fine block's face
@@ -223,18 +225,21 @@ int ab200_flux_correct(ab200_ctx *c, const ab200_fluxcor_desc *fc, int nd) {
   void *dev = nullptr;
   AB_TRY(cached_descriptors(c, h.data(), sizeof(FluxCorDev) * (size_t)nd, nd, &dev));
   NvtxRange nvtx_("SendBoundBufs<flxcor_send> + SetBounds<flxcor_recv> [fused with restriction]");
-  dim3 grid((unsigned)std::min<long long>((maxcells + kThreads - 1) / kThreads, 64), (unsigned)nd);
-  const FluxCorDev *dd = (const FluxCorDev *)dev;
+  const unsigned gx = (unsigned)std::min<long long>((maxcells + kThreads - 1) / kThreads, 64);
+  for (int q0 = 0; q0 < nd; q0 += kMaxGridY) {  // grid.y is a 16-bit dimension
+    dim3 grid(gx, (unsigned)std::min(kMaxGridY, nd - q0));
+    const FluxCorDev *dd = (const FluxCorDev *)dev + q0;
 #define AB_LAUNCH(G)                                                                          \
   case G: k_flux_correct<G><<<grid, kThreads, 0, c->stream>>>(g, gc, c->fl[0].d, c->fl[1].d, dd); break;
-  switch (g.geom) {
-    AB_LAUNCH(0) AB_LAUNCH(1) AB_LAUNCH(2) AB_LAUNCH(3) AB_LAUNCH(4) AB_LAUNCH(5)
-  default:
-    set_error("Coordinate type not recognized!");
-    return AB200_EINVAL;
-  }
+    switch (g.geom) {
+      AB_LAUNCH(0) AB_LAUNCH(1) AB_LAUNCH(2) AB_LAUNCH(3) AB_LAUNCH(4) AB_LAUNCH(5)
+    default:
+      set_error("Coordinate type not recognized!");
+      return AB200_EINVAL;
+    }
 #undef AB_LAUNCH
-  c->launches++;
+    c->launches++;
+  }
   AB_CUDA(cudaGetLastError());
   return AB200_OK;
 }
@@ -281,9 +286,13 @@ int ab200_box_copy(ab200_ctx *c, const ab200_box_desc *bx, int nd) {
   for (int f = 0; f < 2; ++f)
     if (c->fl[f].bound) AB_TRY(sync_prim_home(c, f, 0));
   NvtxRange nvtx_("SendBoundBufs + SetBounds [multilevel, same GPU]");
-  dim3 grid((unsigned)std::min<long long>((maxcells + kThreads - 1) / kThreads, 64), (unsigned)nd);
-  k_box_copy<<<grid, kThreads, 0, c->stream>>>(g, gc, c->fl[0].d, c->fl[1].d, (const BoxDev *)dev);
-  c->launches++;
+  const unsigned gx = (unsigned)std::min<long long>((maxcells + kThreads - 1) / kThreads, 64);
+  for (int q0 = 0; q0 < nd; q0 += kMaxGridY) {  // grid.y is a 16-bit dimension
+    dim3 grid(gx, (unsigned)std::min(kMaxGridY, nd - q0));
+    k_box_copy<<<grid, kThreads, 0, c->stream>>>(g, gc, c->fl[0].d, c->fl[1].d,
+                                                 (const BoxDev *)dev + q0);
+    c->launches++;
+  }
   AB_CUDA(cudaGetLastError());
   return AB200_OK;
 }
@@ -320,11 +329,15 @@ int ab200_block_bcs(ab200_ctx *c, const ab200_block_bc_desc *bc, int nd) {
     if (c->fl[f].bound) AB_TRY(sync_prim_home(c, f, 0));
   NvtxRange nvtx_("ApplyBoundaryConditionsOnCoarseOrFineMD [per block]");
   const long long plane = (long long)std::max(g.ni * g.nj, std::max(g.nj * g.nk, g.ni * g.nk));
-  dim3 grid((unsigned)std::min<long long>((plane * g.ng * 6 + kThreads - 1) / kThreads, 64), (unsigned)nd);
+  const unsigned gx = (unsigned)std::min<long long>((plane * g.ng * 6 + kThreads - 1) / kThreads, 64);
   for (int dir = 0; dir < g.ndim; ++dir) {
     if (!has_dir[dir]) continue;
-    k_block_bcs<<<grid, kThreads, 0, c->stream>>>(g, gc, c->fl[0].d, c->fl[1].d, (const BcDev *)dev, dir);
-    c->launches++;
+    for (int q0 = 0; q0 < nd; q0 += kMaxGridY) {  // grid.y is a 16-bit dimension
+      dim3 grid(gx, (unsigned)std::min(kMaxGridY, nd - q0));
+      k_block_bcs<<<grid, kThreads, 0, c->stream>>>(g, gc, c->fl[0].d, c->fl[1].d,
+                                                    (const BcDev *)dev + q0, dir);
+      c->launches++;
+    }
   }
   AB_CUDA(cudaGetLastError());
   return AB200_OK;

@@ -283,7 +283,10 @@ def main_config3(args):
         Cc = Coordinates.spherical3D
         mesh = UniformMesh(nx=(M, M, M), xmin=(0.4, 1.0707963267948966, 0.0),
                            xmax=(2.5, 2.0707963267948966, 6.283185307179586), block_nx=(B, B, B),
-                           nghost=4, bcs=(BoundaryFlag.outflow,) * 4 + (BoundaryFlag.periodic,) * 2,
+                           # the deck's `ic` user condition on r and theta (AB200_BC_FIXED: resident
+                           # ghost zones, single-rank topologies); outflow when the mesh is split
+                           nghost=4, bcs=((BoundaryFlag.fixed if world == 1 else BoundaryFlag.outflow),) * 4
+                           + (BoundaryFlag.periodic,) * 2,
                            coords=Cc, lattice_lo=tuple(rl[d] * nbt[d] for d in range(3)), lattice_n=nbt)
         recon, per = ReconstructionMethod.ppm, (False, False, True)
     else:
@@ -412,14 +415,15 @@ def main_config3(args):
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
                "config": {"workload": (f"config 4: spherical 3-D Keplerian disk, gas + 1 dust species, "
-                                       f"PPM+HLLE (WENO5 absent upstream), rk2, outflow r/theta + periodic "
+                                       f"PPM+HLLE (WENO5 absent upstream), rk2, "
+                                       f"{'ic user BCs (AB200_BC_FIXED)' if world == 1 else 'outflow'} in r/theta + periodic "
                                        f"phi, {M}^3 zones in TOTAL in {B}^3 MeshBlocks over {world} GPU(s); "
                                        "curvilinear fluxes, PLM_G-free PPM, geometric source terms; "
                                        + ("no source terms" if args.no_sources else
                                           "point-mass gravity (gm 1) + rotating frame (omega 1, mass-flux "
                                           "tap) + alpha viscosity (1e-3) every stage as in disk_sph.in, "
                                           "split stage")
-                                       + "; the disk user BCs stay on the reference path" if cfg4 else
+                                       if cfg4 else
                                        f"config 3: gas + {S} dust species (inputs/drag state + seeded "
                                        f"perturbation), PLM+HLLE, rk2, periodic, {M}^3 zones in TOTAL in "
                                        f"{B}^3 MeshBlocks split over {world} GPU(s) (strong scaling); "
@@ -650,14 +654,14 @@ def main():
                         15: " (copy kernels on the pinned arrays)", 3: " (strided DMA)"}[xfer])}
     elif not args.no_e2e:
         # N > 1: the same end-to-end step through the public entry points every rank calls --
-        # pinned host primitives in, ab200_prim_to_cons, one device-resident cycle with the NCCL
-        # halo sweeps and the dt all-reduce, primitives + conserved state back to pinned host
-        # memory; wall clock between barriers, max over ranks
+        # pinned host primitives in, ab200_prim_to_cons, one device-resident cycle with the
+        # remote halo exchange and the dt all-reduce, the new primitives back to pinned host
+        # memory (as in the N = 1 leg the conserved arrays are not requested: they are a pure
+        # function of the primitives); wall clock between barriers, max over ranks
         nv = gp.nvar
         shape = mesh.shape(nv)
         nbytes = int(np.prod(shape)) * 8
         hp = torch.empty(shape, dtype=torch.float64).pin_memory()
-        hc = torch.empty(shape, dtype=torch.float64).pin_memory()
         hp.numpy()[:] = md.gas.prim.get()
 
         def e2e_step():
@@ -668,7 +672,6 @@ def main():
             else:
                 drv.StepDevice()
             capi_check(md.L.ab200_memcpy_d2h(md.ctx, hp.data_ptr(), md.gas.prim.ptr, nbytes))
-            capi_check(md.L.ab200_memcpy_d2h(md.ctx, hc.data_ptr(), md.gas.u0.ptr, nbytes))
 
         def capi_check(rc):
             if rc != 0:
@@ -685,10 +688,10 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         te = float(tt.item())
         e2e = {"value": zones / te, "unit": "zone-cycles/s", "h2d_bytes_per_step": nbytes * world,
-               "d2h_bytes_per_step": 2 * nbytes * world, "ms_per_step": te * 1e3,
+               "d2h_bytes_per_step": nbytes * world, "ms_per_step": te * 1e3,
                "api": "per rank: ab200_memcpy_h2d (pinned prim) -> ab200_prim_to_cons -> "
-                      "device-resident cycle (NCCL halo sweeps, dt all-reduce) -> "
-                      "ab200_memcpy_d2h (prim + cons)"}
+                      "device-resident cycle (remote halo exchange, dt all-reduce) -> "
+                      "ab200_memcpy_d2h (prim)"}
     else:
         e2e = None
 

