@@ -51,7 +51,7 @@ def parse():
                          "(ab200_set_host_transfer): whole arrays; interior zones, in by a copy "
                          "kernel on the pinned array and out by strided DMA (the measured best); "
                          "copy kernels both ways; strided DMA both ways")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE.json config: 2 = the headline (3-D blast, PPM+HLLC, 256^3 per "
                          "GPU, weak scaling); 3 = gas + 4 dust species, PLM+HLLE, periodic, "
                          "--mesh^3 zones IN TOTAL split over the GPUs (strong scaling); 4 = spherical "
@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--dust-species", type=int, default=4)
     ap.add_argument("--no-sources", action="store_true",
                     help="config 4: without the deck's point-mass gravity and rotating frame")
+    ap.add_argument("--no-flux-correction", action="store_true",
+                    help="config 5: fused stage kernels without Parthenon's flux correction")
     ap.add_argument("--no-drag", action="store_true",
                     help="config 3: leave Drag::DragSource out (it then stays on the reference path)")
     ap.add_argument("--state", default="blast", choices=["blast", "shocked"],
@@ -444,6 +446,135 @@ def main_config3(args):
         dist.destroy_process_group()
 
 
+def main_config5(args):
+    """config 5: 3-D shearing sheet with static mesh refinement on ONE GPU -- the root lattice
+    of 4^3 MeshBlocks with its central 2^3 blocks refined (the core has the resolution of a
+    uniform mesh twice as fine per direction), gas PLM+HLLC, rk2, shearing box (Omega 1, q 1.5)
+    + point-mass gravity as in inputs/ssheet/ssheet.in.  Every stage runs the reference's task
+    list: CalculateFluxes -> flux correction on the fine-coarse faces -> ApplyUpdate ->
+    FluxSource -> sources -> SetAux / C2P -> multilevel ghost exchange (restrict, copies,
+    coarse BCs, prolongate, fine BCs) -> P2C.  `--no-flux-correction` runs the fused stage
+    kernels instead (the non-conservative variant)."""
+    import ctypes as C
+
+    import torch
+
+    from artemis_b200.driver import ArtemisDriver
+    from artemis_b200.enums import BoundaryFlag, Coordinates, Fluid, ReconstructionMethod, RSolver
+    from artemis_b200.meshdata import MeshData
+    from artemis_b200.multilevel import MultilevelExchange, MultilevelMesh
+    from artemis_b200.params import FluidParams
+
+    if int(os.environ.get("WORLD_SIZE", "1")) != 1 or args.gpus != 1:
+        raise SystemExit("bench.py --config 5: refined meshes are single-GPU (DESIGN.md 6)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(0)
+    B = args.block
+    O, P = BoundaryFlag.outflow, BoundaryFlag.periodic
+    mesh = MultilevelMesh(root_blocks=(4, 4, 4), block_nx=(B, B, B), xmin=(-1.0, -1.0, -1.0),
+                          xmax=(1.0, 1.0, 1.0),
+                          refine=tuple((i, j, k) for k in (1, 2) for j in (1, 2) for i in (1, 2)),
+                          nghost=4, bcs=(O, O, P, P, O, O))
+    gp = FluidParams(Fluid.gas, Coordinates.cartesian, ReconstructionMethod.plm, RSolver.hllc,
+                     cfl=0.3, nspecies=1, dfloor=1e-10, gamma=1.000001, siefloor=1e-10)
+    fused = args.no_flux_correction
+    md = MeshData(mesh, gas=gp, device=0, materialize_fluxes=not fused)
+    rng = np.random.default_rng(1234)
+    prim = np.zeros(mesh.shape(6))
+    for b in range(mesh.nb):
+        x = [mesh.blk_lo[b, d] + (np.arange((mesh.ni, mesh.nj, mesh.nk)[d]) - mesh.ngd[d] + 0.5)
+             * mesh.blk_dx[b, d] for d in range(3)]
+        X, Y, Z = x[0][None, None, :], x[1][None, :, None], x[2][:, None, None]
+        prim[b, 0] = np.exp(-0.5 * (Z / 0.4) ** 2) * (1 + 0.05 * np.sin(3 * np.pi * X) * np.cos(2 * np.pi * Y))
+        prim[b, 1] = 1e-3 * np.sin(2 * np.pi * Y) + 0 * X + 0 * Z
+        prim[b, 2] = -1.5 * X + 0 * Y + 0 * Z          # background shear, q Omega x
+        prim[b, 3] = 1e-3 * rng.standard_normal(1)[0] * np.cos(np.pi * X) + 0 * Y + 0 * Z
+        prim[b, 5] = 0.05 ** 2 / gp.gm1                 # isothermal-like, c_s = h Omega = 0.05
+    prim[:, 4] = gp.gm1 * prim[:, 0] * prim[:, 5]
+    md.gas.prim.set(prim)
+    del prim
+    ex = MultilevelExchange(md)
+    # <gravity/point> mass = 1e-5, soft = 0.03 at the origin; <rotating_frame> omega 1, qshear 1.5
+    drv = ArtemisDriver(md, "rk2", mode="fused" if fused else "tasks", comm=ex,
+                        sources=[("point_mass", 1.0e-5, 0.0, 0.0, 0.0, 0.03, 0.0, 0.0),
+                                 ("shearing_box", 1.0, 1.5)],
+                        flux_correction=not fused)
+    drv.Initialize()
+
+    def sync_all():
+        md.synchronize()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        drv.Step()
+    sync_all()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = md.launch_count()
+    # the cycle is host-driven (dt comes back every cycle, like the reference's driver): wall
+    # clock between synchronisations is the honest number; device time is reported beside it
+    md.call("ab200_timer_begin")
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        drv.Step()
+    ms = C.c_float()
+    md.call("ab200_timer_end", C.byref(ms))
+    sync_all()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = md.launch_count() - l0
+    clocks = sampler.finish()
+    # the multilevel exchange on its own (device time of 10 calls)
+    md.call("ab200_timer_begin")
+    for _ in range(10):
+        ex.exchange()
+    ems = C.c_float()
+    md.call("ab200_timer_end", C.byref(ems))
+    fcms = C.c_float(0.0)
+    if not fused:
+        md.call("ab200_timer_begin")
+        for _ in range(10):
+            ex.flux_correct()
+        md.call("ab200_timer_end", C.byref(fcms))
+    sync_all()
+    zones = mesh.interior_zones
+    t_ms = max(float(ms.value), wall_ms)
+    value = zones * args.steps / (t_ms * 1e-3)
+    peak, peak_src = measured_peaks()
+    alg = 240.0 * 2
+    _emit({"metric": METRIC, "value": value, "unit": "zone-cycles/s", "n_gpus": 1,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": (f"config 5: 3-D shearing sheet with static mesh refinement, gas PLM+HLLC, "
+                                   f"rk2, gamma 1.000001, shearing box (Omega 1, q 1.5) + point-mass "
+                                   f"gravity every stage; root lattice 4^3 MeshBlocks of {B}^3 with the "
+                                   f"central 2^3 refined: {mesh.nb} MeshBlocks, {zones} zones, the core "
+                                   f"at the resolution of a uniform {8 * B}^3 mesh; outflow x1/x3 (the "
+                                   f"deck's extrap / inflow user BCs are state-dependent and stay with "
+                                   f"the caller), periodic x2"),
+                      "zones_total": zones, "blocks": mesh.nb,
+                      "path": ("fused stage kernels, NO flux correction (non-conservative variant)"
+                               if fused else
+                               "reference task list per stage incl. flux correction on every "
+                               "fine-coarse face (AddFluxCorrectionTasks)"),
+                      "multilevel_exchange_ms": float(ems.value) / 10,
+                      "flux_correction_ms": float(fcms.value) / 10,
+                      "exchange_descriptors": ex.n,
+                      "device_ms_per_step": float(ms.value) / args.steps,
+                      "wall_ms_per_step": wall_ms / args.steps,
+                      "l2": "state >> 126 MB L2, no flush needed"},
+           "roofline": {"bound": "hbm", "achieved": value * alg / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": value * alg / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_zone_cycle": alg,
+                        "note": "whole cycle (task kernels materialise fluxes: the algorithmic "
+                                "bytes are those of the fused stage, SURVEY 8d)"},
+           "cpu_baseline": None, "e2e": None, "gpu_launches": launches, "clocks": clocks})
+    ex.close()
+    md.close()
+
+
 def main():
     args = parse()
     _claim_stdout()
@@ -452,6 +583,9 @@ def main():
         return
     if args.config in (3, 4):
         main_config3(args)
+        return
+    if args.config == 5:
+        main_config5(args)
         return
     import torch
     import torch.distributed as dist
