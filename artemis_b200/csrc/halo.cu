@@ -193,29 +193,47 @@ k_fill_ghosts(GridDev g, FluidDev f, int nbx, int nby, int nbz, int bc0, int bc1
   const double hx[3] = {cc.hx1v(), cc.hx2v(), cc.hx3v()};
   const int S = f.S;
   const size_t ed = (size_t)b * f.nvar, es = (size_t)nbr * f.nvar;
+  // Every load of a species is issued BEFORE its first store (a store through double* may alias
+  // any later load, so interleaving them serialises one memory round trip per variable); the
+  // pointer tables are constant and go through the read-only path.
+  auto tabp = [](double *const *tab, size_t e) {
+    return reinterpret_cast<double *>(__ldg(reinterpret_cast<const unsigned long long *>(tab + e)));
+  };
   for (int n = 0; n < S; ++n) {
     // the FillGhost fields (src/gas/gas.cpp:243-270, src/dust/dust.cpp:200-212) ...
-    double w_d = f.prim[es + n][soff];
+    double *pd = tabp(f.prim, ed + n), *pv[3], *pp = nullptr, *ps = nullptr;
+    const double *qd = tabp(f.prim, es + n), *qv[3], *qs = nullptr;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      pv[d] = tabp(f.prim, ed + S + 3 * n + d);
+      qv[d] = tabp(f.prim, es + S + 3 * n + d);
+    }
+    if (gas) {
+      pp = tabp(f.prim, ed + 4 * S + n);
+      ps = tabp(f.prim, ed + 5 * S + n);
+      qs = tabp(f.prim, es + 5 * S + n);
+    }
+    double w_d = qd[soff];
     double vel[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      const double v = f.prim[es + S + 3 * n + d][soff];
+      const double v = qv[d][soff];
       vel[d] = flip[d] ? -1.0 * v : v;
     }
+    double w_s = gas ? qs[soff] : 0.0;
     // ... then PrimToCons on the ghost cell (fill_derived.cpp:217-274)
     w_d = (w_d > f.dfloor) ? w_d : f.dfloor;
-    f.prim[ed + n][doff] = w_d;
+    pd[doff] = w_d;
     if (CONS) f.u0[ed + n][doff] = w_d;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      f.prim[ed + S + 3 * n + d][doff] = vel[d];
+      pv[d][doff] = vel[d];
       if (CONS) f.u0[ed + S + 3 * n + d][doff] = w_d * vel[d] * hx[d];
     }
     if (gas) {
-      double w_s = f.prim[es + 5 * S + n][soff];
       w_s = (w_s > f.siefloor) ? w_s : f.siefloor;
-      f.prim[ed + 5 * S + n][doff] = w_s;
-      f.prim[ed + 4 * S + n][doff] = dmax(0.0, f.gm1 * w_d * w_s);
+      ps[doff] = w_s;
+      pp[doff] = dmax(0.0, f.gm1 * w_d * w_s);
       if (CONS) {
         const double u_u = w_s * w_d;
         f.u0[ed + 5 * S + n][doff] = u_u;

@@ -24,7 +24,10 @@
 
 namespace ab200 {
 
-constexpr int kMarchThreads = 128;
+#ifndef AB200_MARCH_THREADS
+#define AB200_MARCH_THREADS 128
+#endif
+constexpr int kMarchThreads = AB200_MARCH_THREADS;
 #ifndef AB200_MARCH_PREFETCH
 #define AB200_MARCH_PREFETCH 6
 #endif
@@ -61,8 +64,15 @@ AB_D void ppm_mono(double qlv, double q_i, double qrv, double &ql_ip1, double &q
   qr_i = qlv;
 }
 
+// AB200_MARCH_MAXNREG (experiments): cap the registers directly instead of through the
+// occupancy hint (ptxas maps both (160, 2) and (96, 3) launch bounds to 168 registers)
+#ifdef AB200_MARCH_MAXNREG
+#define AB200_MARCH_BOUNDS __maxnreg__(AB200_MARCH_MAXNREG)
+#else
+#define AB200_MARCH_BOUNDS __launch_bounds__(kMarchThreads, AB200_MARCH_MIN_BLOCKS)
+#endif
 template <int GEOM, int FLUID, int RS, int RC, int DIR, bool LAST>
-__global__ void __launch_bounds__(kMarchThreads, AB200_MARCH_MIN_BLOCKS)
+__global__ void AB200_MARCH_BOUNDS
 k_march_pass(GridDev g, FluidDev f, FusedArgs a) {
   static_assert(DIR == 2 || DIR == 3, "marching passes cover x2 and x3");
   constexpr bool gas = (FLUID == AB200_GAS);
