@@ -300,8 +300,23 @@ k_drag(GridDev g, TwoFluids tf, double dt_host, const double *dt_dev, double bet
   Coords<GEOM> cc(g, c.b, c.k, c.j, c.i);
   const double xv[3] = {cc.x1v(), cc.x2v(), cc.x3v()};
   const double hx[3] = {cc.hx1v(), cc.hx2v(), cc.hx3v()};
-  double xcyl0, e[3][3];
-  if (GEOM == AB200_CARTESIAN) {  // geometry.hpp:284-302
+  const bool use_visc = dp.damp_to_visc && dd.visc_type != AB200_VISC_NONE;
+#ifdef AB200_FAST_MATH
+  // default build: the cylindrical basis only feeds the viscous target velocity, and the six
+  // damping ramps (two IEEE divisions each) are identically zero without a damping zone --
+  // both are uniform over the launch
+  const bool need_basis = use_visc;
+  bool damp = false;
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    damp = damp || dp.g_irate[d] != 0.0 || dp.g_orate[d] != 0.0 || dp.d_irate[d] != 0.0 ||
+           dp.d_orate[d] != 0.0;
+#else
+  const bool need_basis = true, damp = true;
+#endif
+  double xcyl0 = 1.0, e[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+  if (!need_basis) {
+  } else if (GEOM == AB200_CARTESIAN) {  // geometry.hpp:284-302
     const double R = sqrt(xv[0] * xv[0] + xv[1] * xv[1]);
     const double cp = xv[0] / (R + 1e-99), sp = xv[1] / (R + 1e-99);
     e[0][0] = cp;  e[0][1] = -sp; e[0][2] = 0.0;
@@ -317,9 +332,10 @@ k_drag(GridDev g, TwoFluids tf, double dt_host, const double *dt_dev, double bet
   const size_t eg = (size_t)c.b * fg.nvar, ed = (size_t)c.b * fd_.nvar;
   const double big = 1.79769313486231570815e+308;
   const double dsc[3] = {1.0, g.ndim >= 2 ? 1.0 : 0.0, g.ndim == 3 ? 1.0 : 0.0};
-  double bg[3], bd[3];
+  double bg[3] = {0.0, 0.0, 0.0}, bd[3] = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
+    if (!damp) break;
     const double rg = damp_ramp(dt, xv[d], dp.g_ix[d], dp.g_ox[d], dp.g_irate[d], dp.g_orate[d],
                                 dp.xmin[d], dp.xmax[d]);
     const double rd = damp_ramp(dt, xv[d], dp.d_ix[d], dp.d_ox[d], dp.d_irate[d], dp.d_orate[d],
@@ -327,7 +343,6 @@ k_drag(GridDev g, TwoFluids tf, double dt_host, const double *dt_dev, double bet
     bg[d] = (d == 0) ? rg : dsc[d] * rg;
     bd[d] = (d == 0) ? rd : dsc[d] * rd;
   }
-  const bool use_visc = dp.damp_to_visc && dd.visc_type != AB200_VISC_NONE;
   // ArtemisUtils::GetSpecificInternalEnergy of gas species n (artemis_utils.hpp:42-62)
   auto cons_sie = [&](int n) {
     const double u_d = dmax(fg.u0[eg + n][off], fg.dfloor);
@@ -371,6 +386,118 @@ k_drag(GridDev g, TwoFluids tf, double dt_host, const double *dt_dev, double bet
     }
     return;
   }
+#ifdef AB200_FAST_MATH
+  // Default build, up to 4 dust species: the same implicit update with every operand loaded
+  // ONCE before the first store (a store through double* may alias any later load, so the
+  // statement order of the reference serialises one memory round trip per momentum component:
+  // 1.0 TB/s measured on the 512^3 gas + 4 dust mesh), one reciprocal per density and per
+  // implicit denominator instead of ~25 IEEE divisions per species, and the dust state kept in
+  // registers between the two passes (4 slots, statically unrolled).  Agrees with the
+  // reference's statement order (the strict build below) to a few ulp; the parity tests hold it
+  // to 1e-12 per zone.
+  auto drag_fast = [&](auto NSc) {
+    constexpr int NS = decltype(NSc)::value;
+    const bool cart = (GEOM == AB200_CARTESIAN);
+    double rho[NS], mom[NS][3];
+#pragma unroll
+    for (int n = 0; n < NS; ++n) {
+      rho[n] = 1.0;
+      mom[n][0] = mom[n][1] = mom[n][2] = 0.0;
+      if (n < Sd) {
+        rho[n] = fd_.u0[ed + n][off];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) mom[n][d] = fd_.u0[ed + Sd + 3 * n + d][off];
+      }
+    }
+    const double dg = fg.u0[eg][off];
+    double mg[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) mg[d] = fg.u0[eg + Sg + d][off];
+    const double eg0 = fg.u0[eg + 4 * Sg][off];
+    const bool need_sie = use_visc || dp.model == AB200_DRAG_STOKES;
+    const double sieg = need_sie ? cons_sie(0) : 0.0;
+    double ihx[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) ihx[d] = cart ? 1.0 : drcp(hx[d]);
+    const double rdg = drcp(dg);
+    double vg[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) vg[d] = mg[d] * ihx[d] * rdg;
+    const double mu = use_visc ? visc_mu_val<GEOM>(cc, dd, fg.gm1, dg, sieg) : 0.0;
+    const double vR = use_visc ? -1.5 * mu * drcp(xcyl0 * dg) : 0.0;
+    const double vt[3] = {e[0][0] * vR, e[1][0] * vR, e[2][0] * vR};
+    const double rvth = (dp.model == AB200_DRAG_STOKES)
+                            ? drsqrt(8.0 / 3.14159265358979323846 * fg.gm1 * sieg) : 0.0;
+    const bool bd_uniform = (bd[0] == bd[1]) && (bd[1] == bd[2]);
+    double al[NS], rrho[NS], rden0[NS];
+    double fd[3] = {0.0, 0.0, 0.0}, fvd[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int n = 0; n < NS; ++n) {
+      al[n] = rrho[n] = rden0[n] = 0.0;
+      if (n < Sd) {
+        // alpha = dt / t_stop (drag.hpp:356-366); t_stop <= 0 couples instantly
+        const double tc = (dp.model == AB200_DRAG_STOKES)
+                              ? dp.scale * dp.grain_density * rdg * dp.sizes[n] * rvth
+                              : dp.scale * dp.tau[n];
+        al[n] = dt * ((tc <= 0.0) ? big : drcp(tc));
+        rrho[n] = drcp(rho[n]);
+        rden0[n] = drcp(1.0 + al[n] + bd[0]);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const double rden = (d == 0 || bd_uniform) ? rden0[n] : drcp(1.0 + al[n] + bd[d]);
+          const double vd = mom[n][d] * ihx[d] * rrho[n];
+          const double rhop = rho[n] * al[n] * rden;
+          fd[d] += rhop * (1.0 + bd[d]);
+          fvd[d] += rhop * vd;
+        }
+      }
+    }
+    double vgp[3], delta_g[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      vgp[d] = (dg * (vg[d] + bg[d] * vt[d]) + fvd[d]) * drcp(dg * (1.0 + bg[d]) + fd[d]);
+      fvd[d] = 0.0;
+    }
+#pragma unroll
+    for (int n = 0; n < NS; ++n) {
+      if (n < Sd) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const double rden = (d == 0 || bd_uniform) ? rden0[n] : drcp(1.0 + al[n] + bd[d]);
+          const double vd = mom[n][d] * ihx[d] * rrho[n];
+          const double rhop = rho[n] * al[n] * rden;
+          const double delta = rhop * ((vgp[d] - vd) + bd[d] * vgp[d]);
+          delta_g[d] -= delta;
+          const double delta_d = delta - bd[d] * rho[n] * rden * (vd + al[n] * vgp[d]);
+          fvd[d] += rhop * ((vd - vt[d]) - bd[d] * vt[d]);
+          mom[n][d] += hx[d] * delta_d;
+        }
+      }
+    }
+    double eadd = 0.0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double prefac = dg * bg[d] * drcp(1.0 + bg[d] + fd[d]);
+      delta_g[d] -= prefac * (dg * (vg[d] - vt[d]) + fvd[d]);
+      mg[d] += hx[d] * delta_g[d];
+      eadd += 0.5 * (vg[d] + vgp[d]) * delta_g[d];
+    }
+#pragma unroll
+    for (int n = 0; n < NS; ++n) {
+      if (n < Sd) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) fd_.u0[ed + Sd + 3 * n + d][off] = mom[n][d];
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) fg.u0[eg + Sg + d][off] = mg[d];
+    fg.u0[eg + 4 * Sg][off] = eg0 + eadd;
+  };
+  if (Sd <= 4) {   // more species take the generic statement order below
+    drag_fast(std::integral_constant<int, 4>{});
+    return;
+  }
+#endif
   // SimpleDragSourceImpl, drag.hpp:296-482 (gas species 0 couples to every dust species)
   const double dg = fg.u0[eg][off];
   double vg[3], fd[3] = {0.0, 0.0, 0.0}, fvd[3] = {0.0, 0.0, 0.0};
