@@ -192,8 +192,9 @@ extern "C" int ab200_cycles_host(ab200_ctx *c, int integrator, int ncycles, doub
                                  double *dust_prim_host, double *dust_cons_host) {
   AB_REQUIRE(c && c->grid_set, AB200_ESTATE, "ab200_cycles_host: no grid bound");
   AB_REQUIRE(c->topo.set, AB200_ESTATE, "ab200_cycles_host: call ab200_set_topology first");
-  AB_REQUIRE(topology_is_local(c), AB200_ESTATE,
-             "ab200_cycles_host: single-rank entry point (topology has AB200_BC_NONE faces)");
+  // faces owned by another rank (AB200_BC_NONE): every rank calls this collectively and the
+  // cycles run through ab200_run_cycles_mr (needs ab200_comm_init + ab200_comm_set_layout)
+  const bool local = topology_is_local(c);
   AB_REQUIRE(dt_io, AB200_EINVAL, "ab200_cycles_host: null dt");
   AB_CUDA(cudaSetDevice(c->device));
   const GridDev &g = c->g;
@@ -229,7 +230,15 @@ extern "C" int ab200_cycles_host(ab200_ctx *c, int integrator, int ncycles, doub
     // entries they copy are stale, PrimToCons below recomputes P over the entire domain
     const bool lazy = c->ghost_cons_lazy;
     c->ghost_cons_lazy = true;
-    const int rc_fill = ab200_fill_ghosts(c);
+    int rc_fill;
+    if (local) {
+      rc_fill = ab200_fill_ghosts(c);
+    } else {  // the same fill with the remote round between its two halves
+      rc_fill = ab200_comm_exchange_begin(c);
+      if (rc_fill == AB200_OK) rc_fill = ab200_fill_ghosts_local(c);
+      if (rc_fill == AB200_OK) rc_fill = ab200_comm_exchange_end(c);
+      if (rc_fill == AB200_OK) rc_fill = ab200_finish_remote_ghosts(c);
+    }
     c->ghost_cons_lazy = lazy;
     AB_TRY(rc_fill);
     for (int fl = 0; fl < 2; ++fl) c->fl[fl].ghost_cons_stale = false;  // full PrimToCons follows
@@ -243,6 +252,7 @@ extern "C" int ab200_cycles_host(ab200_ctx *c, int integrator, int ncycles, doub
     ts[0] = 1.79769313486231570815e+308;
     AB_TRY(ab200_write_time_state(c, ts));
     AB_TRY(ab200_estimate_timestep_device(c));
+    if (!local) AB_TRY(ab200_allreduce_min(c, c->d_time + 1));
     AB_TRY(ab200_set_global_timestep_device(c, 1.79769313486231570815e+308, 0));
   }
   // Conserved arrays are optional on the way back (cons is a pure function of prim: the host
@@ -251,7 +261,8 @@ extern "C" int ab200_cycles_host(ab200_ctx *c, int integrator, int ncycles, doub
   const bool want_cons = (hc[0] != nullptr) || (hc[1] != nullptr);
   const bool lazy_before = c->ghost_cons_lazy;
   if (!want_cons) c->ghost_cons_lazy = true;
-  const int rc_run = ab200_run_cycles(c, integrator, ncycles, 1.79769313486231570815e+308);
+  const int rc_run = local ? ab200_run_cycles(c, integrator, ncycles, 1.79769313486231570815e+308)
+                           : ab200_run_cycles_mr(c, integrator, ncycles, 1.79769313486231570815e+308);
   c->ghost_cons_lazy = lazy_before;
   AB_TRY(rc_run);
   for (int fl = 0; fl < 2; ++fl) {

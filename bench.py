@@ -798,19 +798,27 @@ def main():
         hp = torch.empty(shape, dtype=torch.float64).pin_memory()
         hp.numpy()[:] = md.gas.prim.get()
 
+        xfer = {"full": 0, "interior": 1 | 2 | 4, "interior_zc": 1 | 2 | 4 | 8,
+                "interior_dma": 1 | 2}[args.e2e_transfer]
+        use_host_entry = native is not None     # ab200_cycles_host is collective over the ranks
+        php = C.cast(hp.data_ptr(), C.POINTER(C.c_double))
+        dt_io = C.c_double(drv.dt)
+
         def e2e_step():
+            if use_host_entry:
+                md.call("ab200_cycles_host", integ, 1, C.byref(dt_io), php, None, None, None)
+                return
             capi_check(md.L.ab200_memcpy_h2d(md.ctx, md.gas.prim.ptr, hp.data_ptr(), nbytes))
             md.call("ab200_prim_to_cons")
-            if native is not None:
-                md.call("ab200_run_cycles_mr", integ, 1, float(np.finfo(np.float64).max))
-            else:
-                drv.StepDevice()
+            drv.StepDevice()
             capi_check(md.L.ab200_memcpy_d2h(md.ctx, hp.data_ptr(), md.gas.prim.ptr, nbytes))
 
         def capi_check(rc):
             if rc != 0:
                 raise SystemExit(f"bench.py: host<->device copy failed ({rc})")
 
+        if use_host_entry:
+            md.call("ab200_set_host_transfer", xfer)
         e2e_step()  # warm-up
         sync_all()
         t0 = time.perf_counter()
@@ -818,14 +826,23 @@ def main():
             e2e_step()
         sync_all()
         te = (time.perf_counter() - t0) / args.e2e_steps
+        if use_host_entry:
+            md.call("ab200_set_host_transfer", 0)
+            if xfer:
+                nbytes = mesh.interior_zones * nv * 8
         tt = torch.tensor([te], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         te = float(tt.item())
-        e2e = {"value": zones / te, "unit": "zone-cycles/s", "h2d_bytes_per_step": nbytes * world,
+        e2e = {"value": zones / te, "unit": "zone-cycles/s",
+               "h2d_bytes_per_step": (nbytes * 5 // 6 if use_host_entry else nbytes) * world,
                "d2h_bytes_per_step": nbytes * world, "ms_per_step": te * 1e3,
-               "api": "per rank: ab200_memcpy_h2d (pinned prim) -> ab200_prim_to_cons -> "
-                      "device-resident cycle (remote halo exchange, dt all-reduce) -> "
-                      "ab200_memcpy_d2h (prim)"}
+               "transfer": args.e2e_transfer if use_host_entry else "full",
+               "api": ("per rank, collectively: ab200_cycles_host (pinned host primitives in, "
+                       "pressure not uploaded; ghost zones rebuilt on the device incl. the remote "
+                       "round; ab200_run_cycles_mr; primitives out)" if use_host_entry else
+                       "per rank: ab200_memcpy_h2d (pinned prim) -> ab200_prim_to_cons -> "
+                       "device-resident cycle (remote halo exchange, dt all-reduce) -> "
+                       "ab200_memcpy_d2h (prim)")}
     else:
         e2e = None
 

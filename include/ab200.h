@@ -490,7 +490,10 @@ int ab200_finish_remote_ghosts(ab200_ctx *ctx);
  * Bytes that need not cross PCIe do not: the gas PRESSURE entries of the input are ignored
  * (PrimToCons recomputes P = EOS(rho, sie) over the entire domain, fill_derived.cpp:247) and
  * are not uploaded; *_cons_host may be NULL (cons is a pure function of prim), which halves
- * the download and skips the ghost PrimToCons. */
+ * the download and skips the ghost PrimToCons.
+ * Multi-rank (faces flagged AB200_BC_NONE, ab200_comm_set_layout done): every rank calls it
+ * collectively on its own partition; the cycles run through ab200_run_cycles_mr and an estimated
+ * first dt is all-reduced. */
 int ab200_cycles_host(ab200_ctx *ctx, int integrator, int ncycles, double *dt_io,
                       double *gas_prim_host, double *gas_cons_host, double *dust_prim_host,
                       double *dust_cons_host);

@@ -98,6 +98,7 @@ configure_physics(tmd)
 tdrv = ArtemisDriver(tmd, "rk2", mode="fused", comm=comm)
 tdrv.Initialize()
 assert tdrv.dt == dt0, (tdrv.dt, dt0)
+host0 = [f.prim.get() for f in tmd.fluids]   # this rank's tile with consistent ghost zones
 tmd.set_time_state(tdrv.dt)
 if args.transport == "native":
     ncomm = NativeComm(tmd, lay, rank, world)
@@ -113,14 +114,43 @@ ts = tmd.time_state()
 ok = bool(ts[3] == args.cycles and ts[0] == want_ts[0] and ts[2] == want_ts[2])
 for f, (wp, wu) in zip(tmd.fluids, want):
     ok = ok and np.array_equal(f.prim.get(), wp[gid]) and np.array_equal(f.u0.get(), wu[gid])
+host_ok = None
+if args.transport == "native":
+    # the host-buffer entry point on the split mesh: every rank uploads the INTERIOR zones of its
+    # tile from pinned memory (ghost zones poisoned: rebuilt on the device, remote faces through
+    # the library's transport), runs the same cycles, downloads interior zones only
+    import ctypes as C
+    DP = C.POINTER(C.c_double)
+    ghost = np.ones(host0[0].shape[2:], dtype=bool)
+    ghost[tm.interior()] = False
+    bufs = []
+    for a in host0:
+        t = torch.empty(a.shape, dtype=torch.float64).pin_memory()
+        t.numpy()[:] = a
+        t.numpy()[:, :, ghost] = -9.0e9
+        bufs.append(t)
+    tmd.call("ab200_set_host_transfer", 1 | 2 | 4)
+    dt_io = C.c_double(dt0)
+    tmd.call("ab200_cycles_host", 1, args.cycles, C.byref(dt_io), C.cast(bufs[0].data_ptr(), DP),
+             None, C.cast(bufs[1].data_ptr(), DP), None)
+    tmd.synchronize()
+    tmd.call("ab200_set_host_transfer", 0)
+    inner = (slice(None), slice(None)) + tm.interior()
+    host_ok = bool(dt_io.value == want_ts[0])
+    for t, (wp, wu) in zip(bufs, want):
+        host_ok = host_ok and np.array_equal(t.numpy()[inner], wp[gid][inner])
+        host_ok = host_ok and bool(np.all(t.numpy()[:, :, ghost] == -9.0e9))
+    ok = ok and host_ok
 flag = torch.tensor([1.0 if ok else 0.0], device=f"cuda:{local}")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     direct = int(tmd.L.ab200_comm_is_direct(tmd.ctx)) if args.transport == "native" else 0
     print("check_multigpu: world %d lattice %s cycles %d transport %s physics %s (peer-write over "
-          "CUDA IPC: %s, overlap: %s) -> %s" % (world, lay, args.cycles, args.transport,
+          "CUDA IPC: %s, overlap: %s; ab200_cycles_host on the split mesh, interior-only "
+          "transfers: %s) -> %s" % (world, lay, args.cycles, args.transport,
                                   "gravity+drag+viscosity+conduction" if args.physics else "hydro",
                                   bool(direct), bool(os.environ.get("AB200_OVERLAP")),
+                                  "not run" if host_ok is None else ("ok" if host_ok else "MISMATCH on rank 0"),
                                   "BIT-IDENTICAL" if flag.item() == 1.0 else "MISMATCH"))
 tmd.close()
 dist.destroy_process_group()
