@@ -100,6 +100,8 @@ struct ab200_ctx {
   int stage_path = 0;  // AB200_PATH_*
   bool ghost_cons_lazy = false;  // ghost fills skip PrimToCons until ab200_sync_ghost_cons
   int host_transfer = 0;         // ab200_set_host_transfer flags (ab200_cycles_host)
+  bool graph_replay = false;     // ab200_run_cycles captures one cycle into a CUDA graph (opt-in)
+  long long graph_replays = 0;   // cycles executed as cudaGraphLaunch so far
   double *d_time = nullptr;     // device double[4]: dt, new_dt, time, ncycle
   double *d_red = nullptr;      // reduction scratch
   double *h_pinned = nullptr;   // pinned host scratch (8 doubles)

@@ -532,6 +532,19 @@ int ab200_set_host_transfer(ab200_ctx *ctx, int flags);
  * ArtemisDriver::Step (src/artemis_driver.cpp:101-121) for a single-rank uniform mesh with
  * no host round trip.  State must already be bound; dt/time live in ab200_dt_device(). */
 int ab200_run_cycles(ab200_ctx *ctx, int integrator, int ncycles, double tlim);
+/* Opt-in: ab200_run_cycles replays a CUDA graph of one cycle when it can (no finite tlim, at
+ * least three cycles, a launch sequence that is periodic over one cycle): the first cycle runs
+ * eagerly, the second is captured (on a private stream when the context runs on the legacy
+ * default stream, which cannot be captured), the rest are one cudaGraphLaunch each on the
+ * context's stream.  Results are identical to the eager loop, bit for bit (tested).  Measured
+ * on B200 (profiles/r02b_graph_ab.log): config 1's 8192-zone mesh 137 -> 127 us per cycle, a
+ * 64^3 mesh 254 -> 239 us; nothing at BASELINE's 256^3, where a cycle is 4 ms of kernels.  The
+ * eager loop never waits for the host either (every input of a cycle lives on the device), so
+ * the gain is only the inter-kernel gap.  Off by default; AB200_GRAPH=1 in the environment
+ * turns it on for every context. */
+int ab200_set_graph_replay(ab200_ctx *ctx, int on);
+/* cycles this context has executed as a graph launch so far */
+int ab200_graph_replay_count(ab200_ctx *ctx, long long *count);
 
 /* ---- multi-rank transport (one process per GPU; NCCL over NVLink / NVSwitch) ----------------
  * Replaces, for blocks whose neighbour lives on another rank, the MPI path of

@@ -171,6 +171,64 @@ def test_config1_linwave_2d_deck_default(variant):
         assert zone_rel_err(u0, osim.gas.u0, gp, "cons") <= 1e-13
 
 
+def _linwave_gpu(res, recon, variant, wave_flag=0, rs="hllc", mode="fused"):
+    """the reference's regression geometry (tst/scripts/hydro/linwave.py): 3.0 x 1.5 x 1.5,
+    res x res/2 x res/2 zones, amp 1e-6, rk2, cfl 0.9, nghost 4"""
+    mesh = UniformMesh(nx=(res, res // 2, res // 2), xmin=(0, 0, 0), xmax=(3.0, 1.5, 1.5),
+                       block_nx=(res // 4,) * 3, nghost=4)
+    gp = FluidParams(Fluid.gas, Coordinates.cartesian, ReconstructionMethod[recon], RSolver[rs],
+                     cfl=0.9, nspecies=1, dfloor=1e-20, gamma=1.66666666667)
+    prim, lw = pgen.linear_wave(mesh, gp.gamma, wave_flag, 1e-6, 0.0)
+    md = MeshData(mesh, gas=gp, variant=variant, materialize_fluxes=(mode == "tasks"))
+    md.gas.prim.set(prim)
+    drv = ArtemisDriver(md, "rk2", mode=mode, tlim=lw.tlim, nlim=100000)
+    drv.Initialize()
+    drv.Execute()
+    u0 = md.gas.u0.get()
+    md.close()
+    rms, l1 = pgen.linear_wave_errors(mesh, lw, u0)
+    return rms, l1, drv.ncycle
+
+
+@pytest.mark.parametrize("variant", ["fast", "strict"])
+@pytest.mark.parametrize("recon", ["plm", "ppm"])
+def test_linwave_l1_errors_and_convergence_order_on_the_gpu(recon, variant):
+    """north_star: "the linwave L1 error and convergence order must match".  The reference's own
+    regression (tst/scripts/hydro/linwave.py:96-143) on the GPU: L-going sound wave at 16 and 32
+    zones per wavelength; RMS-L1 errors equal to the real reference build's printed digits
+    (tests/golden/reference_linwave.json), the same number of cycles, the same convergence
+    ratio, both under the reference's thresholds."""
+    g = GOLDEN["test_geometry"][recon]
+    errs = {}
+    for res in (16, 32):
+        rms, l1, ncycle = _linwave_gpu(res, recon, variant)
+        assert ncycle == g[str(res)]["ncycles"]
+        assert abs(rms - g[str(res)]["rms_l1"]) <= 5e-7 * g[str(res)]["rms_l1"]   # 7 printed digits
+        if "l1_per_variable" in g[str(res)]:
+            for got, w in zip(l1, g[str(res)]["l1_per_variable"]):
+                assert abs(got - w) <= 5e-7 * w
+        errs[res] = rms
+    ratio = errs[32] / errs[16]
+    assert abs(ratio - g["ratio"]) < 1e-4
+    thr = GOLDEN["reference_test_thresholds"][recon]
+    assert errs[32] <= thr["err_max_sound"] and ratio <= thr["ratio_max_sound"]
+
+
+@pytest.mark.parametrize("recon", ["plm", "ppm"])
+def test_linwave_left_and_right_going_waves_have_identical_errors_on_the_gpu(recon):
+    """tst/scripts/hydro/linwave.py:135-143 requires l1_rms_l == l1_rms_r EXACTLY: mirrored
+    waves must give mirrored bits.  That is a property of the reference's operation order (the
+    flux divergence summed over the three directions before the update), which the strict build's
+    task kernels reproduce; the directional passes of the default path round once per direction
+    and agree to rounding instead."""
+    l = _linwave_gpu(16, recon, "strict", wave_flag=0, mode="tasks")[0]
+    r = _linwave_gpu(16, recon, "strict", wave_flag=4, mode="tasks")[0]
+    assert l == r
+    lf = _linwave_gpu(16, recon, "fast", wave_flag=0)[0]
+    rf = _linwave_gpu(16, recon, "fast", wave_flag=4)[0]
+    assert abs(lf - rf) <= 1e-9 * l and abs(lf - l) <= 1e-9 * l
+
+
 # ------------------------------------------------------------------------------------------
 # config 3: gas + 4 dust species, PLM + HLLE, periodic, 32^3 blocks
 # ------------------------------------------------------------------------------------------
