@@ -281,6 +281,20 @@ extern "C" int ab200_cycles_host(ab200_ctx *c, int integrator, int ncycles, doub
   const size_t cells = (size_t)g.ni * g.nj * g.nk;
   double *hp[2] = {gas_prim_host, dust_prim_host};
   double *hc[2] = {gas_cons_host, dust_cons_host};
+  // everything that can be refused is refused before the first byte moves
+  AB_REQUIRE(!(c->host_transfer & AB200_HOST_INTERIOR_OUT) || (!hc[0] && !hc[1]), AB200_EINVAL,
+             "ab200_cycles_host: AB200_HOST_INTERIOR_OUT returns primitives only "
+             "(pass NULL for the conserved arrays)");
+  for (int fl = 0; fl < 2; ++fl) {
+    if (!c->fl[fl].bound) continue;
+    AB_REQUIRE(hp[fl], AB200_EINVAL, "ab200_cycles_host: null host array for a bound fluid");
+    const int ht = c->host_transfer;
+    if (((ht & AB200_HOST_INTERIOR_IN) && (ht & AB200_HOST_ZERO_COPY_IN)) ||
+        ((ht & AB200_HOST_INTERIOR_OUT) && (ht & AB200_HOST_ZERO_COPY_OUT))) {
+      double *alias = nullptr;
+      AB_TRY(host_alias(hp[fl], &alias));
+    }
+  }
   // Upload the primitives, [nblocks][nvar][nk][nj][ni].  The gas pressure entries are NOT
   // uploaded: PrimToCons recomputes P = EOS(rho, sie) over the entire domain
   // (fill_derived.cpp:247) before anything reads it, so those bytes never need to cross PCIe.
@@ -355,9 +369,6 @@ extern "C" int ab200_cycles_host(ab200_ctx *c, int integrator, int ncycles, doub
                             cudaMemcpyDeviceToHost, c->stream));
     AB_CUDA(cudaStreamSynchronize(c->stream));
     if (c->host_transfer & AB200_HOST_INTERIOR_OUT) {
-      AB_REQUIRE(!hc[fl], AB200_EINVAL,
-                 "ab200_cycles_host: AB200_HOST_INTERIOR_OUT returns primitives only "
-                 "(pass NULL for the conserved arrays)");
       AB_TRY(interior_transfer(c, fl, hp[fl], false, tp));
       continue;
     }
