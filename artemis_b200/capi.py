@@ -116,7 +116,7 @@ SYMBOLS = [
     "ab200_launch_count", "ab200_timer_begin", "ab200_timer_end",
     "ab200_history_volume_integrals", "ab200_configure_sources", "ab200_finish_stage", "ab200_uniform_gravity", "ab200_shearing_box", "ab200_drag_simple",
     "ab200_point_mass_gravity", "ab200_rotating_frame", "ab200_drag_source",
-    "ab200_box_copy", "ab200_block_bcs", "ab200_flux_correct", "ab200_set_host_transfer", "ab200_set_graph_replay", "ab200_graph_replay_count",
+    "ab200_box_copy", "ab200_block_bcs", "ab200_set_shear_bc_params", "ab200_flux_correct", "ab200_set_host_transfer", "ab200_set_graph_replay", "ab200_graph_replay_count",
     "ab200_configure_diffusion", "ab200_diffusion_flux", "ab200_diffusion_update",
     "ab200_diffusion_timestep", "ab200_diffusion_flux_array",
     "ab200_comm_unique_id", "ab200_comm_init", "ab200_comm_destroy", "ab200_comm_set_layout",
@@ -190,6 +190,7 @@ def load(variant: str | None = None) -> C.CDLL:
         "ab200_set_host_transfer": [vp, i], "ab200_set_graph_replay": [vp, i],
         "ab200_graph_replay_count": [vp, C.POINTER(C.c_longlong)],
         "ab200_box_copy": [vp, C.POINTER(BoxDesc), i], "ab200_block_bcs": [vp, C.POINTER(BlockBcDesc), i],
+        "ab200_set_shear_bc_params": [vp, d, d],
         "ab200_configure_diffusion": [vp, C.POINTER(DiffusionDesc)], "ab200_diffusion_flux": [vp],
         "ab200_diffusion_update": [vp, d], "ab200_diffusion_timestep": [vp, _DP],
         "ab200_diffusion_flux_array": [vp, i, C.POINTER(_DP), C.POINTER(C.c_size_t)],

@@ -92,6 +92,9 @@ struct ab200_ctx {
   ab200::GridDev g{};
   ab200::GridDev gc{};          // coarse buffers of the multilevel operators (refine.cu)
   bool coarse_ready = false;
+  // ab200_set_shear_bc_params: q and Omega_0 of the shearing-box `inflow` user condition
+  double shear_q = 0.0, shear_om0 = 0.0;
+  bool shear_bc_set = false;
   std::vector<void *> grid_allocs;
   std::vector<double> h_xmin, h_dx;
   ab200::FluidHost fl[2];

@@ -15,7 +15,10 @@
 //   ab200_block_bcs   ApplyBoundaryConditionsOnCoarseOrFineMD: GenericBC outflow / reflect
 //                     (P:bvals/boundary_conditions_generic.hpp:178-256) on named faces of named
 //                     blocks, on the fine arrays or on the coarse buffers, over the full
-//                     transverse extent, x1 faces first, then x2, then x3 (one launch each).
+//                     transverse extent, x1 faces first, then x2, then x3 (one launch each);
+//                     plus the state-dependent user conditions of the shearing-box problem
+//                     generators (`extrap`, `inflow`: src/pgen/strat.hpp:154-666) in the same
+//                     list and the same order (k_block_user_bcs).
 //
 //   ab200_flux_correct   AddFluxCorrectionTasks (boundary_communication.cpp:454-461): the fluxes
 //                     through every coarse face shared with finer blocks are replaced by the
@@ -117,6 +120,89 @@ k_block_bcs(GridDev g, GridDev gc, FluidDev f0, FluidDev f1, const BcDev *__rest
                             : f.prim[(size_t)d.block * f.nvar + var];
     const double v = base[((size_t)sidx[2] * n[1] + sidx[1]) * n[0] + sidx[0]];
     base[((size_t)idx[2] * n[1] + idx[1]) * n[0] + idx[0]] = sgn * v;
+  }
+}
+
+// The shearing-box user conditions of the strat / ssheet problem generators
+// (src/pgen/strat.hpp:154-666; inputs/ssheet/ssheet.in: `extrap` on x1 and x3, `inflow` on x2).
+// They are functions of the STATE next to the face, so unlike AB200_BC_FIXED they run every
+// exchange.  One thread per (transverse cell, ghost layer, species); the gas condition touches
+// species 0 only (the reference writes gas::prim::*(0)), the dust condition every species.
+//   AB200_BC_EXTRAP, x1 faces  (ExtrapInnerX1 / ExtrapOuterX1): density, v3, sie copied from the
+//       last interior cell, v1 copied with inflow clipped to zero, v2 extrapolated linearly in x1
+//   AB200_BC_INFLOW, x2 faces  (ShearInnerX2 / ShearOuterX2): copy; v2 = -q Om0 x on the half
+//       of the face where the background shear flows INTO the box, outflow-only on the other
+//   AB200_BC_EXTRAP, x3 faces  (ExtrapInnerX3 / ExtrapOuterX3): copy, v3 with inflow clipped,
+//       density extrapolated as a power law in x3 (hydrostatic stratification)
+// Positions come from the metric tables of the index space the face lives in (fine arrays or
+// coarse buffers), i.e. geometry::Coords<GEOM>::x1v / x3v / bnds.x1[0] of the reference.
+__global__ void __launch_bounds__(kThreads)
+k_block_user_bcs(GridDev g, GridDev gc, FluidDev f0, FluidDev f1, const BcDev *__restrict__ bc,
+                 int dir, double shear_q, double shear_om0) {
+  const BcDev d = bc[blockIdx.y];
+  if (d.face / 2 != dir || (d.type != AB200_BC_EXTRAP && d.type != AB200_BC_INFLOW)) return;
+  const FluidDev &f = d.fluid == AB200_GAS ? f0 : f1;
+  const bool gas = d.fluid == AB200_GAS;
+  const GridDev &a = d.coarse ? gc : g;
+  const int n[3] = {a.ni, a.nj, a.nk};
+  const int lo[3] = {a.is, a.js, a.ks}, hi[3] = {a.ie, a.je, a.ke};
+  const int ng = lo[dir];
+  const int a1 = dir == 0 ? 1 : 0, a2 = dir == 2 ? 1 : 2;
+  const int nsp = gas ? 1 : f.S;
+  const long long total = (long long)n[a1] * n[a2] * ng * nsp;
+  const bool inner = (d.face % 2) == 0;
+  const int ref = inner ? lo[dir] : hi[dir];     // last interior cell (is / ie of the reference)
+  const int ref1 = inner ? ref + 1 : ref - 1;    // its interior neighbour (is + 1 / ie - 1)
+  const size_t cells = (size_t)n[0] * n[1] * n[2];
+  const double *x1v = a.t.x1v + (size_t)d.block * n[0];
+  const double *x3v = a.t.x3v + (size_t)d.block * n[2];
+  const double *x1f = a.t.x1f + (size_t)d.block * (n[0] + 1);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    long long r = t;
+    int idx[3];
+    idx[a1] = (int)(r % n[a1]); r /= n[a1];
+    idx[a2] = (int)(r % n[a2]); r /= n[a2];
+    const int gl = (int)(r % ng);
+    const int sp = (int)(r / ng);
+    idx[dir] = inner ? lo[dir] - 1 - gl : hi[dir] + 1 + gl;
+    int s0[3] = {idx[0], idx[1], idx[2]}, s1[3] = {idx[0], idx[1], idx[2]};
+    s0[dir] = ref; s1[dir] = ref1;
+    const size_t o = ((size_t)idx[2] * n[1] + idx[1]) * n[0] + idx[0];
+    const size_t o0 = ((size_t)s0[2] * n[1] + s0[1]) * n[0] + s0[0];
+    const size_t o1 = ((size_t)s1[2] * n[1] + s1[1]) * n[0] + s1[0];
+    // pack entries: density n, velocity S + 3 n + dir, sie 5 S + n (hllc.hpp:66-73; the
+    // pressure at 4 S + n is not a FillGhost field, PrimToCons recomputes it)
+    const int vd = sp, vv = f.S + 3 * sp, ve = 5 * f.S + sp;
+    auto ptr = [&](int var) -> double * {
+      return d.coarse ? d.coarse + (size_t)var * cells : f.prim[(size_t)d.block * f.nvar + var];
+    };
+    double *pd = ptr(vd), *p1 = ptr(vv), *p2 = ptr(vv + 1), *p3 = ptr(vv + 2);
+    const double dens = pd[o0], v1 = p1[o0], v2 = p2[o0], v3 = p3[o0];
+    double od = dens, o_v1 = v1, o_v2 = v2, o_v3 = v3;
+    if (d.type == AB200_BC_EXTRAP && dir == 0) {
+      const double x0 = x1v[ref], xn = x1v[ref1];
+      const double dx = inner ? xn - x0 : x0 - xn;
+      const double x = x1v[idx[0]];
+      const double v2n = p2[o1];
+      o_v1 = inner ? ((v1 > 0.0) ? 0.0 : v1) : ((v1 < 0.0) ? 0.0 : v1);
+      o_v2 = inner ? v2 + (v2n - v2) * (x - x0) / dx : v2 + (v2 - v2n) * (x - x0) / dx;
+    } else if (d.type == AB200_BC_EXTRAP) {  // dir == 2
+      const double z0 = x3v[ref], zn = x3v[ref1];
+      const double dz = inner ? zn - z0 : z0 - zn;
+      const double z = x3v[idx[2]];
+      const double dn = pd[o1];
+      o_v3 = inner ? ((v3 > 0.0) ? 0.0 : v3) : ((v3 < 0.0) ? 0.0 : v3);
+      const double drho = inner ? dn / dens : dens / dn;
+      od = dens * pow(drho, (z - z0) / dz);
+    } else {  // AB200_BC_INFLOW, dir == 1
+      const double x = x1v[idx[0]], xf = x1f[idx[0]];
+      const double vy0 = -shear_q * shear_om0 * x;
+      if (inner) o_v2 = (xf >= 0) ? ((v2 > 0.0) ? 0.0 : v2) : vy0;
+      else o_v2 = (xf < 0) ? ((v2 < 0.0) ? 0.0 : v2) : vy0;
+    }
+    p1[o] = o_v1; p2[o] = o_v2; p3[o] = o_v3; pd[o] = od;
+    if (gas) { double *pe = ptr(ve); pe[o] = pe[o0]; }
   }
 }
 
@@ -302,18 +388,33 @@ int ab200_block_bcs(ab200_ctx *c, const ab200_block_bc_desc *bc, int nd) {
   if (nd == 0) return AB200_OK;
   AB_REQUIRE(bc && nd > 0, AB200_EINVAL, "ab200_block_bcs: bad descriptor list");
   AB_CUDA(cudaSetDevice(c->device));
-  AB_TRY(ensure_coarse_grid(c));
+  // the coarse index space (and its even-block-size requirement) matters only to descriptors
+  // that name a coarse buffer; a uniform mesh applies its user conditions on fine arrays alone
+  for (int q = 0; q < nd; ++q)
+    if (bc[q].coarse) { AB_TRY(ensure_coarse_grid(c)); break; }
   const GridDev &g = c->g, &gc = c->gc;
   std::vector<BcDev> h(nd);
-  bool has_dir[3] = {false, false, false};
+  bool has_dir[3] = {false, false, false}, user_dir[3] = {false, false, false},
+       generic_dir[3] = {false, false, false};
   for (int q = 0; q < nd; ++q) {
     const ab200_block_bc_desc &s = bc[q];
     AB_REQUIRE(s.fluid == AB200_GAS || s.fluid == AB200_DUST, AB200_EINVAL, "ab200_block_bcs: bad fluid");
     AB_REQUIRE(c->fl[s.fluid].bound, AB200_ESTATE, "ab200_block_bcs: fluid not bound");
     const FluidDev &f = c->fl[s.fluid].d;
     AB_REQUIRE(s.face >= 0 && s.face < 2 * g.ndim, AB200_EINVAL, "ab200_block_bcs: bad face");
-    AB_REQUIRE(s.type == AB200_BC_OUTFLOW || s.type == AB200_BC_REFLECT, AB200_EINVAL,
-               "ab200_block_bcs: outflow or reflect");
+    const bool user = s.type == AB200_BC_EXTRAP || s.type == AB200_BC_INFLOW;
+    AB_REQUIRE(s.type == AB200_BC_OUTFLOW || s.type == AB200_BC_REFLECT || user, AB200_EINVAL,
+               "ab200_block_bcs: outflow, reflect, extrap or inflow");
+    // strat.hpp registers `extrap` on the x1 and x3 faces and `inflow` on the x2 faces only
+    // (src/pgen/problem_modifier.hpp:114-127); both act on the whole fluid at once
+    AB_REQUIRE(s.type != AB200_BC_EXTRAP || s.face / 2 != 1, AB200_EINVAL,
+               "ab200_block_bcs: AB200_BC_EXTRAP exists on x1 and x3 faces only");
+    AB_REQUIRE(s.type != AB200_BC_INFLOW || s.face / 2 == 1, AB200_EINVAL,
+               "ab200_block_bcs: AB200_BC_INFLOW exists on x2 faces only");
+    AB_REQUIRE(!user || (s.var0 == 0 && s.ncomp == f.nvar), AB200_EINVAL,
+               "ab200_block_bcs: a user condition takes every pack entry of the fluid");
+    AB_REQUIRE(s.type != AB200_BC_INFLOW || c->shear_bc_set, AB200_ESTATE,
+               "ab200_block_bcs: call ab200_set_shear_bc_params before AB200_BC_INFLOW");
     AB_REQUIRE(s.block >= 0 && s.block < g.nb && s.var0 >= 0 && s.ncomp >= 1 &&
                    s.var0 + s.ncomp <= f.nvar,
                AB200_EINVAL, "ab200_block_bcs: bad entries");
@@ -322,6 +423,7 @@ int ab200_block_bcs(ab200_ctx *c, const ab200_block_bc_desc *bc, int nd) {
     d.fluid = s.fluid; d.block = s.block; d.var0 = s.var0; d.ncomp = s.ncomp;
     d.face = s.face; d.type = s.type; d.coarse = s.coarse;
     has_dir[s.face / 2] = true;
+    (user ? user_dir : generic_dir)[s.face / 2] = true;
   }
   void *dev = nullptr;
   AB_TRY(cached_descriptors(c, h.data(), sizeof(BcDev) * (size_t)nd, nd, &dev));
@@ -334,13 +436,30 @@ int ab200_block_bcs(ab200_ctx *c, const ab200_block_bc_desc *bc, int nd) {
     if (!has_dir[dir]) continue;
     for (int q0 = 0; q0 < nd; q0 += kMaxGridY) {  // grid.y is a 16-bit dimension
       dim3 grid(gx, (unsigned)std::min(kMaxGridY, nd - q0));
-      k_block_bcs<<<grid, kThreads, 0, c->stream>>>(g, gc, c->fl[0].d, c->fl[1].d,
-                                                    (const BcDev *)dev + q0, dir);
-      c->launches++;
+      // faces of one direction never overlap, so the two kernels of a direction commute
+      if (generic_dir[dir]) {
+        k_block_bcs<<<grid, kThreads, 0, c->stream>>>(g, gc, c->fl[0].d, c->fl[1].d,
+                                                      (const BcDev *)dev + q0, dir);
+        c->launches++;
+      }
+      if (user_dir[dir]) {
+        k_block_user_bcs<<<grid, kThreads, 0, c->stream>>>(g, gc, c->fl[0].d, c->fl[1].d,
+                                                           (const BcDev *)dev + q0, dir,
+                                                           c->shear_q, c->shear_om0);
+        c->launches++;
+      }
     }
   }
   AB_CUDA(cudaGetLastError());
   return AB200_OK;
 }
 
+
+int ab200_set_shear_bc_params(ab200_ctx *c, double q, double om0) {
+  AB_REQUIRE(c, AB200_EINVAL, "ab200_set_shear_bc_params: null context");
+  c->shear_q = q;
+  c->shear_om0 = om0;
+  c->shear_bc_set = true;
+  return AB200_OK;
+}
 }  // extern "C"

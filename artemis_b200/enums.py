@@ -38,6 +38,11 @@ class BoundaryFlag(IntEnum):
     # user condition that depends on position only (`ic` of src/pgen/disk.hpp, strat.hpp):
     # AB200_BC_FIXED -- the ghost zones keep the problem generator's profile
     fixed = 4
+    # state-dependent user conditions of the shearing-box problem generators
+    # (src/pgen/strat.hpp:154-666, inputs/ssheet/ssheet.in): AB200_BC_EXTRAP on x1 / x3 faces,
+    # AB200_BC_INFLOW on x2 faces; applied per block through ab200_block_bcs
+    extrap = 5
+    inflow = 6
 
 
 def CoordSelect(sys: str, ndim: int) -> Coordinates:

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AB200_ABI_VERSION 10
+#define AB200_ABI_VERSION 11
 
 /* src/artemis.hpp:78-105 */
 enum { AB200_CARTESIAN = 0, AB200_CYLINDRICAL = 1, AB200_SPHERICAL1D = 2,
@@ -62,7 +62,16 @@ enum { AB200_BC_PERIODIC = 0, AB200_BC_OUTFLOW = 1, AB200_BC_REFLECT = 2,
         * where a LATER face in Parthenon's x1 -> x2 -> x3 order (outflow / reflect) covers
         * them, which then copies from the fixed zones as the reference does.  Single-rank
         * topologies (no AB200_BC_NONE face). */
-       AB200_BC_FIXED = 4 };
+       AB200_BC_FIXED = 4,
+       /* State-dependent user conditions of the shearing-box problem generators
+        * (src/pgen/strat.hpp, registered in src/pgen/problem_modifier.hpp:114-127;
+        * inputs/ssheet/ssheet.in uses all six).  They exist as ab200_block_bc_desc types only
+        * (ab200_block_bcs applies them per block, on fine arrays or coarse buffers); in
+        * ab200_set_topology such a face is AB200_BC_NONE, i.e. the caller's.
+        *   EXTRAP on x1 faces: strat::ExtrapInnerX1 / ExtrapOuterX1 (strat.hpp:154-297)
+        *   EXTRAP on x3 faces: strat::ExtrapInnerX3 / ExtrapOuterX3 (strat.hpp:487-663)
+        *   INFLOW on x2 faces: strat::ShearInnerX2 / ShearOuterX2   (strat.hpp:299-485) */
+       AB200_BC_EXTRAP = 5, AB200_BC_INFLOW = 6 };
 
 enum { AB200_OK = 0, AB200_EINVAL = 1, AB200_ECUDA = 2, AB200_ESTATE = 3, AB200_ENOMEM = 4 };
 
@@ -410,10 +419,17 @@ int ab200_box_copy(ab200_ctx *ctx, const ab200_box_desc *boxes, int n);
  * entries).  Applied over the full transverse extent, x1 faces of the whole list first, then
  * x2, then x3 (ApplyBoundaryConditionsOnCoarseOrFineMD). */
 typedef struct ab200_block_bc_desc {
-  int fluid, block, var0, ncomp, face, type; /* type: AB200_BC_OUTFLOW | AB200_BC_REFLECT */
+  int fluid, block, var0, ncomp, face, type; /* type: AB200_BC_OUTFLOW | AB200_BC_REFLECT, or a
+                                              * user condition AB200_BC_EXTRAP | AB200_BC_INFLOW,
+                                              * which takes the whole fluid (var0 = 0, ncomp =
+                                              * every pack entry): the gas condition writes
+                                              * species 0, the dust condition every species */
   double *coarse;                            /* DEVICE or NULL */
 } ab200_block_bc_desc;
 int ab200_block_bcs(ab200_ctx *ctx, const ab200_block_bc_desc *bcs, int n);
+/* StratParams::q and ::Om0 (src/pgen/strat.hpp:36-44, <rotating_frame> qshear / omega of the
+ * deck) for AB200_BC_INFLOW: the background shear v2 = -q Om0 x1 imposed where it enters. */
+int ab200_set_shear_bc_params(ab200_ctx *ctx, double q, double om0);
 
 /* Flux correction (AddFluxCorrectionTasks, P:bvals/comms/boundary_communication.cpp:454-461;
  * src/artemis_driver.cpp:198-202): between ab200_calculate_fluxes and ab200_apply_update on a

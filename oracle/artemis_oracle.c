@@ -1054,7 +1054,7 @@ void ao_exchange_ghosts_ic(const ao_grid *g, int nbx, int nby, int nbz, const in
     const int nt[3] = {g->ni, g->nj, g->nk};
     for (int face = 0; face < 2 * g->ndim; ++face) {
       const int d = face / 2, outer = face % 2;
-      if (bc[face] == AO_BC_PERIODIC || bc[face] == AO_BC_NONE) continue;
+      if (bc[face] == AO_BC_PERIODIC || bc[face] == AO_BC_NONE || bc[face] > AO_BC_IC) continue;
       if (outer ? (lb[d] != nbd[d] - 1) : (lb[d] != 0)) continue;
       const int ref = outer ? e[d] : s[d];
       const int offset = 2 * ref + (outer ? 1 : -1);
@@ -1080,6 +1080,112 @@ void ao_exchange_ghosts_ic(const ao_grid *g, int nbx, int nby, int nbz, const in
                   sgn * a[IDX(g, nvar, b, vars[v], c[2], c[1], c[0])];
             }
       }
+    }
+  }
+}
+
+/* The shearing-box user boundary conditions of the strat / ssheet problem generators, applied to
+ * ONE block array a[nvar][nk][nj][ni] (fine arrays or a coarse buffer; xmin / dx are those of
+ * the index space, UniformCartesian::Xf(idx) = xmin + idx * dx).  s / e: interior bounds of the
+ * three directions.  Every ghost zone of `face` over the FULL transverse extent, like
+ * MeshBlock::par_for_bndry over IndexDomain::inner_x1 ... outer_x3.
+ *   type AO_BC_EXTRAP, x1 faces: strat::ExtrapInnerX1 / ExtrapOuterX1  src/pgen/strat.hpp:154-297
+ *   type AO_BC_INFLOW, x2 faces: strat::ShearInnerX2 / ShearOuterX2    src/pgen/strat.hpp:299-485
+ *   type AO_BC_EXTRAP, x3 faces: strat::ExtrapInnerX3 / ExtrapOuterX3  src/pgen/strat.hpp:487-663
+ * The gas branch writes gas::prim::{density, velocity, sie}(0) only; the dust branch every
+ * species.  Returns 0, or 1 for a (type, face) pair the reference does not register
+ * (src/pgen/problem_modifier.hpp:114-127). */
+int ao_strat_bc(int geom, const double *xmin, const double *dx, int ni, int nj, int nk,
+                const int *s, const int *e, int fluid, int S, double *a, int face, int type,
+                double q, double om0) {
+  const int d = face / 2, outer = face % 2;
+  if (type == AO_BC_EXTRAP ? d == 1 : (type != AO_BC_INFLOW || d != 1)) return 1;
+  const int nt[3] = {ni, nj, nk};
+  int lo[3] = {0, 0, 0}, hi[3] = {ni - 1, nj - 1, nk - 1};
+  if (outer) lo[d] = e[d] + 1; else hi[d] = s[d] - 1;
+  const int ref = outer ? e[d] : s[d];        /* is / ie, js / je, ks / ke */
+  const int ref1 = outer ? ref - 1 : ref + 1; /* is + 1 / ie - 1, ...       */
+  const size_t cells = (size_t)ni * nj * nk;
+  const int nsp = fluid == AO_GAS ? 1 : S;
+  (void)nt;
+#define SA(var, k, j, i) a[(size_t)(var) * cells + ((size_t)(k) * nj + (j)) * ni + (i)]
+  for (int n = 0; n < nsp; ++n) {
+    const int vd = n, v1 = S + 3 * n, v2 = v1 + 1, v3 = v1 + 2, ve = 5 * S + n;
+    for (int k = lo[2]; k <= hi[2]; ++k)
+      for (int j = lo[1]; j <= hi[1]; ++j)
+        for (int i = lo[0]; i <= hi[0]; ++i) {
+          int c0[3] = {i, j, k}, c1[3] = {i, j, k};
+          c0[d] = ref; c1[d] = ref1;
+          const bbox_t bb = make_bbox(xmin, dx, k, j, i);
+          const bbox_t b0 = make_bbox(xmin, dx, c0[2], c0[1], c0[0]);
+          const bbox_t b1 = make_bbox(xmin, dx, c1[2], c1[1], c1[0]);
+          const double gv1 = SA(v1, c0[2], c0[1], c0[0]);
+          const double gv2 = SA(v2, c0[2], c0[1], c0[0]);
+          const double gv3 = SA(v3, c0[2], c0[1], c0[0]);
+          const double gd = SA(vd, c0[2], c0[1], c0[0]);
+          double vx1 = gv1, vx2 = gv2, vx3 = gv3, dens = gd;
+          if (type == AO_BC_EXTRAP && d == 0) {
+            const double x0 = g_x1v(geom, &b0), x1 = g_x1v(geom, &b1);
+            const double ddx = outer ? x0 - x1 : x1 - x0;
+            const double x = g_x1v(geom, &bb);
+            const double gv2n = SA(v2, c1[2], c1[1], c1[0]);
+            if (outer) {
+              vx1 = (gv1 < 0.0) ? 0.0 : gv1;
+              vx2 = gv2 + (gv2 - gv2n) * (x - x0) / ddx;
+            } else {
+              vx1 = (gv1 > 0.0) ? 0.0 : gv1;
+              vx2 = gv2 + (gv2n - gv2) * (x - x0) / ddx;
+            }
+          } else if (type == AO_BC_EXTRAP) { /* x3 */
+            const double z = g_x3v(geom, &bb);
+            const double z0 = g_x3v(geom, &b0), z1 = g_x3v(geom, &b1);
+            const double dz = outer ? z0 - z1 : z1 - z0;
+            const double gdn = SA(vd, c1[2], c1[1], c1[0]);
+            const double drho = outer ? gd / gdn : gdn / gd;
+            vx3 = outer ? ((gv3 < 0.0) ? 0.0 : gv3) : ((gv3 > 0.0) ? 0.0 : gv3);
+            dens = gd * pow(drho, (z - z0) / dz);
+          } else { /* inflow, x2 */
+            const double x = g_x1v(geom, &bb);
+            const double xf = bb.x1[0];
+            const double vy0 = -q * om0 * x;
+            if (outer) vx2 = (xf < 0) ? ((gv2 < 0.0) ? 0.0 : gv2) : vy0;
+            else vx2 = (xf >= 0) ? ((gv2 > 0.) ? 0.0 : gv2) : vy0;
+          }
+          const double sie = fluid == AO_GAS ? SA(ve, c0[2], c0[1], c0[0]) : 0.0;
+          SA(v1, k, j, i) = vx1;
+          SA(v2, k, j, i) = vx2;
+          SA(v3, k, j, i) = vx3;
+          SA(vd, k, j, i) = dens;
+          if (fluid == AO_GAS) SA(ve, k, j, i) = sie;
+        }
+  }
+#undef SA
+  return 0;
+}
+
+/* ao_exchange_ghosts_ic with the shearing-box user conditions: faces flagged AO_BC_EXTRAP /
+ * AO_BC_INFLOW run ao_strat_bc on the whole fluid (a = its primitive pack, S species), every
+ * other face the generic condition, all in Parthenon's x1 -> x2 -> x3 face order. */
+void ao_exchange_ghosts_user(const ao_grid *g, int nbx, int nby, int nbz, const int *bc, int nvar,
+                             double *a, int nv, const int *vars, const int *vec_dir,
+                             const double *ic, int fluid, int S, double q, double om0) {
+  ao_exchange_ghosts_ic(g, nbx, nby, nbz, bc, nvar, a, nv, vars, vec_dir, 1, ic);
+  const int nbd[3] = {nbx, nby, nbz};
+  const int s[3] = {g->is, g->js, g->ks}, e[3] = {g->ie, g->je, g->ke};
+  for (int face = 0; face < 2 * g->ndim; ++face) {
+    const int d = face / 2, outer = face % 2;
+    if (bc[face] == AO_BC_EXTRAP || bc[face] == AO_BC_INFLOW) {
+#pragma omp parallel for schedule(static)
+      for (int b = 0; b < g->nb; ++b) {
+        const int lb[3] = {b % nbx, (b / nbx) % nby, b / (nbx * nby)};
+        if (outer ? (lb[d] != nbd[d] - 1) : (lb[d] != 0)) continue;
+        ao_strat_bc(g->geom, g->xmin + 3 * b, g->dx + 3 * b, g->ni, g->nj, g->nk, s, e, fluid, S,
+                    a + (size_t)b * nvar * g->ni * g->nj * g->nk, face, bc[face], q, om0);
+      }
+    } else { /* one generic face at a time keeps the order */
+      int one[6] = {AO_BC_NONE, AO_BC_NONE, AO_BC_NONE, AO_BC_NONE, AO_BC_NONE, AO_BC_NONE};
+      one[face] = bc[face];
+      ao_exchange_ghosts_ic(g, nbx, nby, nbz, one, nvar, a, nv, vars, vec_dir, 2, ic);
     }
   }
 }

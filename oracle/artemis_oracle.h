@@ -40,7 +40,9 @@ enum { AO_HLLC = 0, AO_HLLE = 1, AO_LLF = 2 };
 enum { AO_PCM = 0, AO_PLM = 1, AO_PPM = 2 };
 enum { AO_GAS = 0, AO_DUST = 1 };
 enum { AO_BC_PERIODIC = 0, AO_BC_OUTFLOW = 1, AO_BC_REFLECT = 2, AO_BC_NONE = 3,
-       AO_BC_IC = 4 /* user condition `ic`: the initial-condition profile (src/pgen/disk.hpp:595-633) */ };
+       AO_BC_IC = 4 /* user condition `ic`: the initial-condition profile (src/pgen/disk.hpp:595-633) */,
+       /* shearing-box user conditions of src/pgen/strat.hpp (inputs/ssheet/ssheet.in) */
+       AO_BC_EXTRAP = 5, AO_BC_INFLOW = 6 };
 
 typedef struct {
   int geom, ndim, ng, nb;
@@ -94,6 +96,15 @@ void ao_exchange_ghosts_phase(const ao_grid *g, int nbx, int nby, int nbz, const
 void ao_exchange_ghosts_ic(const ao_grid *g, int nbx, int nby, int nbz, const int *bc, int nvar,
                            double *a, int nv, const int *vars, const int *vec_dir, int phases,
                            const double *ic);
+
+/* strat.hpp:154-666 on one block array (see artemis_oracle.c); 0 = applied */
+int ao_strat_bc(int geom, const double *xmin, const double *dx, int ni, int nj, int nk,
+                const int *s, const int *e, int fluid, int S, double *a, int face, int type,
+                double q, double om0);
+/* neighbour copies + every physical face in x1 -> x2 -> x3 order, user faces included */
+void ao_exchange_ghosts_user(const ao_grid *g, int nbx, int nby, int nbz, const int *bc, int nvar,
+                             double *a, int nv, const int *vars, const int *vec_dir,
+                             const double *ic, int fluid, int S, double q, double om0);
 
 /* Geometry probes (used by tests to compare against oracle/_ref and the CUDA tables) */
 void ao_geom_cell(int geom, const double *xmin, const double *dx, int k, int j, int i,

@@ -51,10 +51,41 @@ def apply_bc(arr, face, kind, n_int, ng_d, vdir):
         arr[tuple(dst)] = vals
 
 
-def run_plan(mesh, plan, fine, coarse, vars_, vdir, bc_kinds):
+def coarse_coords(mesh, b):
+    """UniformCartesian(src, coarsen = 2) of block b (P:coordinates/uniform_cartesian.hpp:41-55;
+    the same arithmetic as the oracle's coarse_coords)"""
+    act = (True, mesh.ndim > 1, mesh.ndim > 2)
+    cx, cd = [], []
+    for d in range(3):
+        istart = mesh.nghost if act[d] else 0
+        dx = float(mesh.blk_dx[b, d])
+        xm = float(mesh.blk_xmin[b, d])
+        xm += istart * dx * (1 - 2)
+        dx *= 2 if (d == 0 or istart > 0) else 1
+        cx.append(xm)
+        cd.append(dx)
+    return cx, cd
+
+
+def apply_user_bc(mesh, b, arr, face, kind, is_coarse, user):
+    """strat.hpp user condition on the FULL pack array of one block (fine or coarse), in place"""
+    code = {"extrap": 5, "inflow": 6}[kind]
+    if is_coarse:
+        xmin, dx = coarse_coords(mesh, b)
+        s, e = mesh.cs, mesh.ce
+    else:
+        xmin, dx = mesh.blk_xmin[b], mesh.blk_dx[b]
+        s = (mesh.is_, mesh.js, mesh.ks)
+        e = (mesh.ie, mesh.je, mesh.ke)
+    oracle_py.strat_bc(arr, int(mesh.coords), xmin, dx, s, e, user["fluid"], user["S"], face, code,
+                       user["q"], user["om0"])
+
+
+def run_plan(mesh, plan, fine, coarse, vars_, vdir, bc_kinds, user=None):
     """fine [nb][nvar][nk][nj][ni], coarse [nb][nvar][cnk][cnj][cni] (both updated in place);
     vars_: pack entries that are exchanged (FillGhost), vdir: per ENTRY OF vars_ the vector
-    direction 1..3 or 0; bc_kinds: 6 names ('outflow' | 'reflect' | 'periodic')."""
+    direction 1..3 or 0; bc_kinds: 6 names ('outflow' | 'reflect' | 'periodic' | 'extrap' | 'inflow');
+    user: fluid / S / q / om0 of the strat.hpp user conditions."""
     L = oracle_py.lib()
     vars_ = list(vars_)
     geoms = [block_geom(mesh, b) for b in range(mesh.nb)]
@@ -88,6 +119,9 @@ def run_plan(mesh, plan, fine, coarse, vars_, vdir, bc_kinds):
     for face_dir in range(3):                            # x1 faces, then x2, then x3
         for b, face in plan.coarse_bcs:
             if face // 2 == face_dir:
+                if bc_kinds[face] in ("extrap", "inflow"):
+                    apply_user_bc(mesh, b, coarse[b], face, bc_kinds[face], True, user)
+                    continue
                 a = coarse[b, vars_]
                 apply_bc(a, face, bc_kinds[face], nx[face_dir] // 2, mesh.nghost, vdir)
                 coarse[b, vars_] = a
@@ -96,6 +130,9 @@ def run_plan(mesh, plan, fine, coarse, vars_, vdir, bc_kinds):
     for face_dir in range(3):
         for b, face in plan.fine_bcs:
             if face // 2 == face_dir:
+                if bc_kinds[face] in ("extrap", "inflow"):
+                    apply_user_bc(mesh, b, fine[b], face, bc_kinds[face], False, user)
+                    continue
                 a = fine[b, vars_]
                 apply_bc(a, face, bc_kinds[face], nx[face_dir], mesh.nghost, vdir)
                 fine[b, vars_] = a

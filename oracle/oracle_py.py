@@ -208,6 +208,8 @@ class OracleSim:
         # physics/conduction off
         self.diffusion = None
         self.dflx = None
+        # StratParams q, Om0 of the shearing-box `inflow` user condition (strat.hpp:36-44)
+        self.shear_bc = (0.0, 0.0)
 
     def _diff_lib(self):
         return self.L, "ao"
@@ -331,10 +333,12 @@ class OracleSim:
             key = id(fs)
             if key not in self._ml_coarse:
                 self._ml_coarse[key] = np.zeros(m.coarse_shape(fs.fp.nvar))
-            kinds = ["periodic" if int(b) == 0 else ("outflow" if int(b) == 1 else "reflect")
-                     for b in m.bcs]
+            names = {0: "periodic", 1: "outflow", 2: "reflect", 5: "extrap", 6: "inflow"}
+            kinds = [names[int(b)] for b in m.bcs]
+            user = dict(fluid=int(fs.fp.fluid_type), S=fs.fp.nspecies, q=self.shear_bc[0],
+                        om0=self.shear_bc[1])
             multilevel_py.run_plan(m, self._ml_plan, fs.prim, self._ml_coarse[key], fs.ghost_vars,
-                                   fs.vec_dir, kinds)
+                                   fs.vec_dir, kinds, user=user)
             return
         vars_ = np.array(fs.ghost_vars, dtype=np.int32)
         vdir = np.array(fs.vec_dir, dtype=np.int32)
@@ -344,6 +348,14 @@ class OracleSim:
             # (ghost zones included), kept for Disk::DiskBoundaryIC
             fs.ic = fs.prim.copy()
         ic = getattr(fs, "ic", None)
+        if (bc >= 5).any():   # shearing-box user conditions (strat.hpp), Parthenon's face order
+            self.L.ao_exchange_ghosts_user(
+                C.byref(self.g), *[int(v) for v in m.lattice_n], bc.ctypes.data_as(_IP),
+                fs.fp.nvar, _p(fs.prim), len(vars_), vars_.ctypes.data_as(_IP),
+                vdir.ctypes.data_as(_IP), _p(ic) if ic is not None else None,
+                int(fs.fp.fluid_type), fs.fp.nspecies, C.c_double(self.shear_bc[0]),
+                C.c_double(self.shear_bc[1]))
+            return
         self.L.ao_exchange_ghosts_ic(C.byref(self.g), *[int(v) for v in m.lattice_n],
                                      bc.ctypes.data_as(_IP), fs.fp.nvar, _p(fs.prim), len(vars_),
                                      vars_.ctypes.data_as(_IP), vdir.ctypes.data_as(_IP), 3,
@@ -474,3 +486,17 @@ def restrict_average_face(L, r, fine, coarse, box, el, prefix="ao"):
 def prolongate_minmod(L, r, coarse, fine, box, prefix="ao"):
     getattr(L, prefix + "_prolongate_minmod")(C.byref(r), coarse.shape[0], _p(coarse), _p(fine),
                                               _box(box))
+
+
+def strat_bc(arr, geom, xmin, dx, s, e, fluid, S, face, kind, q=0.0, om0=0.0):
+    """ao_strat_bc on one block array [nvar][nk][nj][ni] in place (strat.hpp:154-666);
+    kind 5 = extrap (x1 / x3 faces), 6 = inflow (x2 faces)."""
+    assert arr.flags["C_CONTIGUOUS"] and arr.dtype == np.float64
+    nk, nj, ni = arr.shape[1:]
+    D3, I3 = C.c_double * 3, C.c_int * 3
+    rc = lib().ao_strat_bc(int(geom), D3(*[float(v) for v in xmin]), D3(*[float(v) for v in dx]),
+                           ni, nj, nk, I3(*[int(v) for v in s]), I3(*[int(v) for v in e]),
+                           int(fluid), int(S), _p(arr), int(face), int(kind), C.c_double(q),
+                           C.c_double(om0))
+    if rc != 0:
+        raise ValueError(f"strat.hpp registers no condition of kind {kind} on face {face}")
