@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(kThreads)
 k_block_bcs(GridDev g, GridDev gc, FluidDev f0, FluidDev f1, const BcDev *__restrict__ bc, int dir) {
   const BcDev d = bc[blockIdx.y];
   if (d.face / 2 != dir) return;
+  if (d.type != AB200_BC_OUTFLOW && d.type != AB200_BC_REFLECT) return;  // k_block_user_bcs
   const FluidDev &f = d.fluid == AB200_GAS ? f0 : f1;
   const GridDev &a = d.coarse ? gc : g;  // the index space the face lives in
   const int n[3] = {a.ni, a.nj, a.nk};

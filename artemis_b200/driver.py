@@ -130,6 +130,15 @@ def AddBoundaryExchangeTasks(md: MeshData, comm=None) -> TaskStatus:
         return st
     if comm is not None:
         comm.exchange(md)
+    if getattr(md, "user_bcs", False):
+        # state-dependent user conditions (strat.hpp extrap / inflow): every physical face of
+        # the mesh goes through the per-block list, in Parthenon's x1 -> x2 -> x3 order
+        try:
+            md.apply_physical_bcs()
+        except capi.AB200Error as e:
+            md.last_error = str(e)
+            return TaskStatus.fail
+        return TaskStatus.complete
     return _task(md, "ab200_apply_physical_bcs")
 
 
@@ -305,6 +314,10 @@ class ArtemisDriver:
         single-round remote exchange (pack / NCCL / unpack on a second stream) concurrent with
         the local ghost fill -> finish."""
         md, integ = self.md, self.integrator
+        if getattr(md, "user_bcs", False):
+            raise capi.AB200Error("the device-resident cycle fills ghost zones with the fused "
+                                  "kernel, which has no state-dependent user conditions "
+                                  "(extrap / inflow): use Step()")
         for stage in range(1, integ.nstages + 1):
             do_pcm = (stage == 1) and (integ.GetName() == "vl2")
             # DEVICE_DT | PINGPONG (primitives may stay in the alternate set) | REDUCE_DT

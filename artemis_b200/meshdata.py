@@ -15,6 +15,7 @@ import numpy as np
 
 from . import capi
 from .enums import Fluid
+from .enums import BoundaryFlag
 from .mesh import UniformMesh
 from .params import FluidParams
 
@@ -97,7 +98,7 @@ class MeshData:
     def __init__(self, mesh: UniformMesh, gas: FluidParams | None = None,
                  dust: FluidParams | None = None, device: int = 0, variant: str | None = None,
                  stream: int | None = None, materialize_fluxes: bool = True,
-                 use_torch: bool = False, bcs=None):
+                 use_torch: bool = False, bcs=None, shear_bc=None):
         self.mesh = mesh
         self.L = capi.load(variant)
         self.ctx = C.c_void_p()
@@ -118,9 +119,51 @@ class MeshData:
         self.fluids = [f for f in (self.gas, self.dust) if f is not None]
         bc = np.array([int(v) for v in (bcs if bcs is not None else mesh.bcs)], dtype=np.int32)
         self.bc = bc
+        # State-dependent user conditions (strat.hpp `extrap` / `inflow`): the library's fused
+        # ghost fill knows position-independent faces only, so every physical face of such a
+        # mesh is the caller's (AB200_BC_NONE in the topology) and AddBoundaryExchangeTasks
+        # applies them per block through ab200_block_bcs, in Parthenon's x1 -> x2 -> x3 order.
+        self.user_bcs = bool((bc >= int(BoundaryFlag.extrap)).any())
+        self._phys_bcs = None
+        topo = bc
+        if self.user_bcs:
+            if (bc == int(BoundaryFlag.fixed)).any():
+                raise ValueError("`ic` faces cannot be combined with extrap / inflow faces")
+            topo = np.where(bc == int(BoundaryFlag.periodic), 0, 3).astype(np.int32)
+        if shear_bc is not None:     # StratParams q, Om0 of the `inflow` condition
+            self.call("ab200_set_shear_bc_params", float(shear_bc[0]), float(shear_bc[1]))
         capi.check(self.L, self.L.ab200_set_topology(
-            self.ctx, *[int(v) for v in mesh.lattice_n], bc.ctypes.data_as(C.POINTER(C.c_int))),
+            self.ctx, *[int(v) for v in mesh.lattice_n], topo.ctypes.data_as(C.POINTER(C.c_int))),
             "ab200_set_topology")
+        if self.user_bcs and not hasattr(mesh, "leaves"):
+            self._phys_bcs = self._physical_bc_list(bc)
+
+    def _physical_bc_list(self, bc):
+        """ab200_block_bc_desc of every (fluid, block on the lattice boundary, non-periodic face)
+        of a uniform mesh -- what ApplyBoundaryConditionsOnCoarseOrFineMD walks"""
+        from .multilevel import fill_ghost_ranges
+        nbd = [int(v) for v in self.mesh.lattice_n]
+        out = []
+        for ff in self.fluids:
+            fl = int(ff.fp.fluid_type)
+            for b in range(self.mesh.nb):
+                lb = (b % nbd[0], (b // nbd[0]) % nbd[1], b // (nbd[0] * nbd[1]))
+                for face in range(2 * self.mesh.ndim):
+                    d, outer = face // 2, face % 2
+                    t = int(bc[face])
+                    if t == int(BoundaryFlag.periodic) or lb[d] != (nbd[d] - 1 if outer else 0):
+                        continue
+                    if t >= int(BoundaryFlag.extrap):
+                        out.append(capi.BlockBcDesc(fl, b, 0, ff.fp.nvar, face, t, None))
+                    else:
+                        out += [capi.BlockBcDesc(fl, b, v0, nc, face, t, None)
+                                for v0, nc in fill_ghost_ranges(ff.fp)]
+        return (capi.BlockBcDesc * len(out))(*out) if out else None
+
+    def apply_physical_bcs(self):
+        """the per-block boundary list of a mesh with user conditions (ab200_block_bcs)"""
+        if self._phys_bcs is not None:
+            self.call("ab200_block_bcs", self._phys_bcs, len(self._phys_bcs))
 
     # ---- allocation / binding ----------------------------------------------------------
     def _alloc(self, shape):

@@ -403,6 +403,8 @@ class MultilevelExchange:
         assert tuple(shape6[:3]) == tuple(m.cn), (tuple(shape6), m.cn)
         ccells = m.cn[0] * m.cn[1] * m.cn[2]
         kinds = {int(BoundaryFlag.outflow): 1, int(BoundaryFlag.reflect): 2}
+        # strat.hpp user conditions take the whole fluid: one descriptor per (block, face)
+        user = (int(BoundaryFlag.extrap), int(BoundaryFlag.inflow))
         self.coarse = {}
         rs, cp, rt, cb, pr, fb = [], [], [], [], [], []
         for ff in md.fluids:
@@ -430,10 +432,18 @@ class MultilevelExchange:
                                            sbox[0][1] - sbox[0][0] + 1, sbox[1][1] - sbox[1][0] + 1,
                                            sbox[2][1] - sbox[2][0] + 1))
                 for b, face in self.plan.coarse_bcs:
-                    cb.append(capi.BlockBcDesc(fl, b, var0, nc, face, kinds[int(m.bcs[face])],
-                                               cptr(b, var0)))
+                    if int(m.bcs[face]) not in user:
+                        cb.append(capi.BlockBcDesc(fl, b, var0, nc, face, kinds[int(m.bcs[face])],
+                                                   cptr(b, var0)))
                 for b, face in self.plan.fine_bcs:
-                    fb.append(capi.BlockBcDesc(fl, b, var0, nc, face, kinds[int(m.bcs[face])], None))
+                    if int(m.bcs[face]) not in user:
+                        fb.append(capi.BlockBcDesc(fl, b, var0, nc, face, kinds[int(m.bcs[face])], None))
+            for b, face in self.plan.coarse_bcs:
+                if int(m.bcs[face]) in user:
+                    cb.append(capi.BlockBcDesc(fl, b, 0, nv, face, int(m.bcs[face]), cptr(b, 0)))
+            for b, face in self.plan.fine_bcs:
+                if int(m.bcs[face]) in user:
+                    fb.append(capi.BlockBcDesc(fl, b, 0, nv, face, int(m.bcs[face]), None))
 
         def arr(T, lst):
             return (T * len(lst))(*lst) if lst else None

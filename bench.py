@@ -63,6 +63,10 @@ def parse():
                     help="config 4: without the deck's point-mass gravity and rotating frame")
     ap.add_argument("--no-flux-correction", action="store_true",
                     help="config 5: fused stage kernels without Parthenon's flux correction")
+    ap.add_argument("--bcs", default="generic", choices=["generic", "deck"],
+                    help="config 5: 'deck' = inputs/ssheet/ssheet.in's own user conditions (extrap on "
+                         "x1 / x3, inflow on x2: strat.hpp) on fine arrays and coarse buffers; "
+                         "'generic' = outflow x1 / x3, periodic x2")
     ap.add_argument("--no-drag", action="store_true",
                     help="config 3: leave Drag::DragSource out (it then stays on the reference path)")
     ap.add_argument("--state", default="blast", choices=["blast", "shocked"],
@@ -475,11 +479,15 @@ def main_config5(args):
     mesh = MultilevelMesh(root_blocks=(4, 4, 4), block_nx=(B, B, B), xmin=(-1.0, -1.0, -1.0),
                           xmax=(1.0, 1.0, 1.0),
                           refine=tuple((i, j, k) for k in (1, 2) for j in (1, 2) for i in (1, 2)),
-                          nghost=4, bcs=(O, O, P, P, O, O))
+                          nghost=4,
+                          bcs=((BoundaryFlag.extrap, BoundaryFlag.extrap, BoundaryFlag.inflow,
+                                BoundaryFlag.inflow, BoundaryFlag.extrap, BoundaryFlag.extrap)
+                               if args.bcs == "deck" else (O, O, P, P, O, O)))
     gp = FluidParams(Fluid.gas, Coordinates.cartesian, ReconstructionMethod.plm, RSolver.hllc,
                      cfl=0.3, nspecies=1, dfloor=1e-10, gamma=1.000001, siefloor=1e-10)
     fused = args.no_flux_correction
-    md = MeshData(mesh, gas=gp, device=0, materialize_fluxes=not fused)
+    # StratParams of the deck's `inflow` faces: <rotating_frame> qshear 1.5, omega 1
+    md = MeshData(mesh, gas=gp, device=0, materialize_fluxes=not fused, shear_bc=(1.5, 1.0))
     rng = np.random.default_rng(1234)
     prim = np.zeros(mesh.shape(6))
     for b in range(mesh.nb):
@@ -551,9 +559,11 @@ def main_config5(args):
                                    f"rk2, gamma 1.000001, shearing box (Omega 1, q 1.5) + point-mass "
                                    f"gravity every stage; root lattice 4^3 MeshBlocks of {B}^3 with the "
                                    f"central 2^3 refined: {mesh.nb} MeshBlocks, {zones} zones, the core "
-                                   f"at the resolution of a uniform {8 * B}^3 mesh; outflow x1/x3 (the "
-                                   f"deck's extrap / inflow user BCs are state-dependent and stay with "
-                                   f"the caller), periodic x2"),
+                                   f"at the resolution of a uniform {8 * B}^3 mesh; " +
+                                   ("the deck's own user BCs: extrap x1 / x3, inflow x2 (strat.hpp) on "
+                                    "fine arrays and coarse buffers" if args.bcs == "deck" else
+                                    "outflow x1/x3, periodic x2 (--bcs deck runs the deck's extrap / "
+                                    "inflow user conditions)")),
                       "zones_total": zones, "blocks": mesh.nb,
                       "path": ("fused stage kernels, NO flux correction (non-conservative variant)"
                                if fused else

@@ -1,0 +1,99 @@
+"""Shearing-box user boundary conditions, host logic (no GPU): the two CPU executors that check
+the GPU path -- ao_exchange_ghosts_user on a uniform block lattice and oracle/multilevel_py's
+run_plan on the same lattice expressed as an unrefined MultilevelMesh -- must agree bit for bit
+(face order x1 -> x2 -> x3, full transverse extent, fluid-wide conditions), every ghost zone of
+every FillGhost entry must be filled on uniform and refined meshes, and the host mirror's
+descriptor lists must name every physical face once."""
+import numpy as np
+import pytest
+
+from artemis_b200.enums import BoundaryFlag as B, Coordinates
+from artemis_b200.mesh import UniformMesh
+from artemis_b200.multilevel import MultilevelMesh, exchange_plan
+from oracle.oracle_py import OracleSim
+from tests.helpers import dust_params, gas_params, random_prim
+
+STRAT = (B.extrap, B.extrap, B.inflow, B.inflow, B.extrap, B.extrap)
+CART = Coordinates.cartesian
+XMIN, XMAX = (-0.5, -0.4, -0.3), (0.5, 0.4, 0.3)
+
+
+def _fluids():
+    return gas_params(CART, "plm", "hlle"), dust_params(CART, "plm", "hlle", S=2)
+
+
+def _poisoned(mesh, of, seed):
+    p = random_prim(mesh, of.fp, seed=seed)
+    mask = np.ones(p.shape[2:], dtype=bool)
+    mask[mesh.interior()] = False
+    for v in of.ghost_vars:
+        p[:, v][:, mask] = -777.0
+    return p
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_uniform_and_multilevel_executors_agree(ndim):
+    bcs = STRAT if ndim == 3 else STRAT[:4] + (B.periodic,) * 2
+    root = tuple(2 if d < ndim else 1 for d in range(3))
+    bnx = tuple(8 if d < ndim else 1 for d in range(3))
+    mm = MultilevelMesh(root_blocks=root, block_nx=bnx, xmin=XMIN, xmax=XMAX, refine=(), nghost=4,
+                        bcs=bcs, coords=CART)
+    mu = UniformMesh(nx=tuple(r * n for r, n in zip(root, bnx)), xmin=XMIN, xmax=XMAX, block_nx=bnx,
+                     nghost=4, bcs=bcs, coords=CART)
+    gp, dp = _fluids()
+    o1, o2 = OracleSim(mu, gas=gp, dust=dp), OracleSim(mm, gas=gp, dust=dp)
+    o1.shear_bc = o2.shear_bc = (1.5, 0.8)
+    order = [int(np.argmin(np.abs(mu.blk_xmin - mm.blk_xmin[b]).sum(1))) for b in range(mm.nb)]
+    assert sorted(order) == list(range(mu.nb))
+    for f1, f2, seed in zip(o1.fluids, o2.fluids, (3, 4)):
+        p = _poisoned(mm, f2, seed)
+        f2.prim[:] = p
+        f1.prim[order] = p
+        o1.ExchangeGhosts(f1)
+        o2.ExchangeGhosts(f2)
+        assert not (f1.prim[:, f1.ghost_vars] == -777.0).any()
+        assert np.array_equal(f1.prim[order], f2.prim)
+
+
+@pytest.mark.parametrize("ndim,refine", [(3, ((1, 1, 1), (0, 0, 0))), (2, ((1, 1, 0), (3, 0, 0)))])
+def test_refined_mesh_fills_every_ghost_zone(ndim, refine):
+    bcs = STRAT if ndim == 3 else STRAT[:4] + (B.periodic,) * 2
+    root = tuple(4 if d < ndim else 1 for d in range(3))
+    bnx = tuple(8 if d < ndim else 1 for d in range(3))
+    mm = MultilevelMesh(root_blocks=root, block_nx=bnx, xmin=XMIN, xmax=XMAX, refine=refine,
+                        nghost=4, bcs=bcs, coords=CART)
+    plan = exchange_plan(mm)
+    assert plan.coarse_bcs and plan.fine_bcs
+    gp, dp = _fluids()
+    o = OracleSim(mm, gas=gp, dust=dp)
+    o.shear_bc = (1.5, 0.8)
+    for of, seed in zip(o.fluids, (5, 6)):
+        of.prim[:] = _poisoned(mm, of, seed)
+        o.ExchangeGhosts(of)
+        assert not (of.prim[:, of.ghost_vars] == -777.0).any()
+        assert np.isfinite(of.prim).all()
+
+
+def test_two_cycles_with_the_decks_boundaries_stay_finite():
+    mu = UniformMesh(nx=(16, 16, 16), xmin=XMIN, xmax=XMAX, block_nx=(8, 8, 8), nghost=4, bcs=STRAT,
+                     coords=CART)
+    gp, dp = gas_params(CART, "ppm", "hllc"), dust_params(CART, "plm", "hlle", S=1)
+    o = OracleSim(mu, gas=gp, dust=dp)
+    o.shear_bc = (1.5, 0.8)
+    o.gas.prim[:] = random_prim(mu, gp, seed=51)
+    o.dust.prim[:] = random_prim(mu, dp, seed=52)
+    o.nlim = 2
+    o.initialize()
+    o.run()
+    assert o.ncycle == 2 and np.isfinite(o.gas.u0).all() and np.isfinite(o.dust.u0).all()
+
+
+def test_input_deck_names_map_to_the_user_flags():
+    from artemis_b200.params import ParameterInput
+    deck = "\n".join(["<parthenon/mesh>", "nx1 = 16", "nx2 = 16", "nx3 = 16", "nghost = 4",
+                      "ix1_bc = extrap", "ox1_bc = extrap", "ix2_bc = inflow", "ox2_bc = inflow",
+                      "ix3_bc = extrap", "ox3_bc = extrap", "<parthenon/meshblock>", "nx1 = 8",
+                      "nx2 = 8", "nx3 = 8", "<artemis>", "coordinates = cartesian"])
+    pin = ParameterInput(deck)
+    m = UniformMesh.from_input(pin)
+    assert tuple(m.bcs) == STRAT
