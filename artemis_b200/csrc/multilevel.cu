@@ -215,17 +215,58 @@ struct FluxCorDev {
   int dsi, dsj, dsk;                 // origin of the same cells in the coarse block
 };
 
-// one thread per (descriptor, flux entry, coarse face cell)
+// RestrictAverage<GEOM> on the face element el (1..3) of one coarse face cell whose lower-corner
+// fine cell is (k, j, i) of `block`: the area-weighted mean of the 2^(ndim-1) fine faces
+// (src/utils/refinement/restriction.hpp:41-114).  `fine` is one [..][snj][sni] array.
 template <int GEOM>
+AB_D double restrict_face(const GridDev &g, int block, int el, int k, int j, int i,
+                          const double *__restrict__ fine, int snj, int sni) {
+  const bool inc1 = el != 1, inc2 = g.ndim > 1 && el != 2, inc3 = g.ndim > 2 && el != 3;
+  double vol[2][2][2], terms[2][2][2];
+#pragma unroll
+  for (int ok = 0; ok < 2; ++ok)
+#pragma unroll
+    for (int oj = 0; oj < 2; ++oj)
+#pragma unroll
+      for (int oi = 0; oi < 2; ++oi) {
+        vol[ok][oj][oi] = 0.0;
+        terms[ok][oj][oi] = 0.0;
+        if ((ok == 0 || inc3) && (oj == 0 || inc2) && (oi == 0 || inc1)) {
+          Coords<GEOM> cc(g, block, k + ok, j + oj, i + oi);
+          vol[ok][oj][oi] = el == 1 ? cc.area1(cc.x1[0]) : (el == 2 ? cc.area2(0) : cc.area3());
+          terms[ok][oj][oi] =
+              vol[ok][oj][oi] * fine[((size_t)(k + ok) * snj + (j + oj)) * sni + (i + oi)];
+        }
+      }
+  // restriction.hpp:103-111: off-centred terms first (FP symmetry)
+  const double tvol = ((vol[0][0][0] + vol[0][1][0]) + (vol[0][0][1] + vol[0][1][1])) +
+                      ((vol[1][0][0] + vol[1][1][0]) + (vol[1][0][1] + vol[1][1][1]));
+  return ddiv((((terms[0][0][0] + terms[0][1][0]) + (terms[0][0][1] + terms[0][1][1])) +
+               ((terms[1][0][0] + terms[1][1][0]) + (terms[1][0][1] + terms[1][1][1]))),
+              tvol);
+}
+
+// one thread per (descriptor, flux entry, coarse face cell).  DIFF = false: the hydrodynamic
+// Metadata::Flux fields of the descriptor's fluid (conserved fluxes + the gas's interface
+// pressure, cell-shaped arrays of the bound pack).  DIFF = true: the gas diffusion fluxes
+// gas.diff.momentum / gas.diff.energy (src/gas/gas.cpp:277-285, also Metadata::WithFluxes and
+// therefore corrected by the same Parthenon task), library-owned face-shaped arrays
+// dflx[nb][4 S][fnk][fnj][fni] of the descriptor's direction; dust descriptors have none.
+template <int GEOM, bool DIFF>
 __global__ void __launch_bounds__(kThreads)
-k_flux_correct(GridDev g, GridDev gc, FluidDev f0, FluidDev f1, const FluxCorDev *__restrict__ fc) {
+k_flux_correct(GridDev g, GridDev gc, FluidDev f0, FluidDev f1, const FluxCorDev *__restrict__ fc,
+               double *__restrict__ dflx0, double *__restrict__ dflx1, double *__restrict__ dflx2) {
   const FluxCorDev d = fc[blockIdx.y];
+  if (DIFF && d.fluid != AB200_GAS) return;
   const FluidDev &f = d.fluid == AB200_GAS ? f0 : f1;
-  const int nent = f.nvar + (d.fluid == AB200_GAS ? f.S : 0);  // conserved fluxes + pressure flux
+  // conserved fluxes + pressure flux | momentum + energy diffusion fluxes
+  const int nent = DIFF ? 4 * f.S : f.nvar + (d.fluid == AB200_GAS ? f.S : 0);
   const int nci = d.cie - d.cis + 1, ncj = d.cje - d.cjs + 1, nck = d.cke - d.cks + 1;
   const long long total = (long long)nent * nck * ncj * nci;
   const int el = d.dir + 1;
-  const bool inc1 = el != 1, inc2 = g.ndim > 1 && el != 2, inc3 = g.ndim > 2 && el != 3;
+  const int snj = DIFF ? g.fnj : g.nj, sni = DIFF ? g.fni : g.ni;
+  double *dflx = d.dir == 0 ? dflx0 : (d.dir == 1 ? dflx1 : dflx2);
+  const size_t fcells = (size_t)g.fnk * g.fnj * g.fni;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
     long long r = t;
@@ -236,35 +277,20 @@ k_flux_correct(GridDev g, GridDev gc, FluidDev f0, FluidDev f1, const FluxCorDev
     const int i = (ci - gc.is) * 2 + g.is;
     const int j = g.ndim > 1 ? (cj - gc.js) * 2 + g.js : g.js;
     const int k = g.ndim > 2 ? (ck - gc.ks) * 2 + g.ks : g.ks;
-    double *const *tab = n < f.nvar ? f.flux[d.dir] : f.pflux[d.dir];
-    const int ent = n < f.nvar ? n : n - f.nvar;
-    const int stride = n < f.nvar ? f.nvar : f.S;
-    const double *fine = tab[(size_t)d.fine_block * stride + ent];
-    double vol[2][2][2], terms[2][2][2];
-#pragma unroll
-    for (int ok = 0; ok < 2; ++ok)
-#pragma unroll
-      for (int oj = 0; oj < 2; ++oj)
-#pragma unroll
-        for (int oi = 0; oi < 2; ++oi) {
-          vol[ok][oj][oi] = 0.0;
-          terms[ok][oj][oi] = 0.0;
-          if ((ok == 0 || inc3) && (oj == 0 || inc2) && (oi == 0 || inc1)) {
-            Coords<GEOM> cc(g, d.fine_block, k + ok, j + oj, i + oi);
-            vol[ok][oj][oi] = el == 1 ? cc.area1(cc.x1[0]) : (el == 2 ? cc.area2(0) : cc.area3());
-            terms[ok][oj][oi] =
-                vol[ok][oj][oi] * fine[((size_t)(k + ok) * g.nj + (j + oj)) * g.ni + (i + oi)];
-          }
-        }
-    // restriction.hpp:103-111: off-centred terms first (FP symmetry)
-    const double tvol = ((vol[0][0][0] + vol[0][1][0]) + (vol[0][0][1] + vol[0][1][1])) +
-                        ((vol[1][0][0] + vol[1][1][0]) + (vol[1][0][1] + vol[1][1][1]));
-    const double v =
-        ddiv((((terms[0][0][0] + terms[0][1][0]) + (terms[0][0][1] + terms[0][1][1])) +
-              ((terms[1][0][0] + terms[1][1][0]) + (terms[1][0][1] + terms[1][1][1]))),
-             tvol);
-    double *dst = tab[(size_t)d.coarse_block * stride + ent];
-    dst[((size_t)(d.dsk + (ck - d.cks)) * g.nj + (d.dsj + (cj - d.cjs))) * g.ni +
+    const double *fine;
+    double *dst;
+    if (DIFF) {
+      fine = dflx + ((size_t)d.fine_block * nent + n) * fcells;
+      dst = dflx + ((size_t)d.coarse_block * nent + n) * fcells;
+    } else {
+      double *const *tab = n < f.nvar ? f.flux[d.dir] : f.pflux[d.dir];
+      const int ent = n < f.nvar ? n : n - f.nvar;
+      const int stride = n < f.nvar ? f.nvar : f.S;
+      fine = tab[(size_t)d.fine_block * stride + ent];
+      dst = tab[(size_t)d.coarse_block * stride + ent];
+    }
+    const double v = restrict_face<GEOM>(g, d.fine_block, el, k, j, i, fine, snj, sni);
+    dst[((size_t)(d.dsk + (ck - d.cks)) * snj + (d.dsj + (cj - d.cjs))) * sni +
         (d.dsi + (ci - d.cis))] = v;
   }
 }
@@ -316,8 +342,17 @@ int ab200_flux_correct(ab200_ctx *c, const ab200_fluxcor_desc *fc, int nd) {
   for (int q0 = 0; q0 < nd; q0 += kMaxGridY) {  // grid.y is a 16-bit dimension
     dim3 grid(gx, (unsigned)std::min(kMaxGridY, nd - q0));
     const FluxCorDev *dd = (const FluxCorDev *)dev + q0;
+    // gas.diff.* are Metadata::WithFluxes fields too: once the diffusion operators are
+    // configured and their flux arrays exist, the same task corrects them
+    const bool diff = c->has_diffusion && c->d_dflx[0] && c->fl[AB200_GAS].bound;
 #define AB_LAUNCH(G)                                                                          \
-  case G: k_flux_correct<G><<<grid, kThreads, 0, c->stream>>>(g, gc, c->fl[0].d, c->fl[1].d, dd); break;
+  case G:                                                                                     \
+    k_flux_correct<G, false><<<grid, kThreads, 0, c->stream>>>(g, gc, c->fl[0].d, c->fl[1].d, \
+                                                               dd, nullptr, nullptr, nullptr); \
+    if (diff)                                                                                 \
+      k_flux_correct<G, true><<<grid, kThreads, 0, c->stream>>>(                              \
+          g, gc, c->fl[0].d, c->fl[1].d, dd, c->d_dflx[0], c->d_dflx[1], c->d_dflx[2]);       \
+    break;
     switch (g.geom) {
       AB_LAUNCH(0) AB_LAUNCH(1) AB_LAUNCH(2) AB_LAUNCH(3) AB_LAUNCH(4) AB_LAUNCH(5)
     default:
@@ -325,7 +360,7 @@ int ab200_flux_correct(ab200_ctx *c, const ab200_fluxcor_desc *fc, int nd) {
       return AB200_EINVAL;
     }
 #undef AB_LAUNCH
-    c->launches++;
+    c->launches += diff ? 2 : 1;
   }
   AB_CUDA(cudaGetLastError());
   return AB200_OK;
