@@ -439,7 +439,10 @@ int ab200_set_shear_bc_params(ab200_ctx *ctx, double q, double om0);
  * coarse block's own index space (CalcIndices, BoundaryExteriorRecv).  Every Metadata::Flux
  * field of the fluid (conserved fluxes; for the gas also the interface pressure) is restricted
  * with RestrictAverage<GEOM> on face elements (src/utils/refinement/restriction.hpp:41-114) and
- * written over the coarse block's flux.  The list is ONE launch. */
+ * written over the coarse block's flux.  The list is ONE launch.  With the diffusion operators
+ * configured (ab200_configure_diffusion) and their fluxes computed, the gas descriptors also
+ * correct gas.diff.momentum / gas.diff.energy -- Metadata::WithFluxes fields like the others
+ * (src/gas/gas.cpp:277-285) -- in a second launch over the same list. */
 typedef struct ab200_fluxcor_desc {
   int fluid, fine_block, coarse_block, dir; /* dir 0..2 */
   int cis, cie, cjs, cje, cks, cke;

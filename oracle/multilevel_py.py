@@ -147,7 +147,9 @@ def flux_correct(mesh, fc_plan, flux):
     for fb, cb, d, rbox, dbox in fc_plan:
         if fb not in geoms:
             geoms[fb] = block_geom(mesh, fb)
-        f = np.ascontiguousarray(flux[d][fb])
+        # face-shaped arrays (the diffusion fluxes, [nvar][fnk][fnj][fni]) address the same
+        # (k, j, i) = lower face of zone (k, j, i): restrict their cell-shaped corner
+        f = np.ascontiguousarray(flux[d][fb][:, :mesh.nk, :mesh.nj, :mesh.ni])
         nvar = f.shape[0]
         c = np.zeros((nvar, mesh.cn[2], mesh.cn[1], mesh.cn[0]))
         flat = (C.c_int * 6)(rbox[0][0], rbox[0][1], rbox[1][0], rbox[1][1], rbox[2][0], rbox[2][1])

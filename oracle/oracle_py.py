@@ -408,6 +408,10 @@ class OracleSim:
                 multilevel_py.flux_correct(self.mesh, self._fc_plan, fs.flux)
                 if fs.pflux[0] is not None:
                     multilevel_py.flux_correct(self.mesh, self._fc_plan, fs.pflux)
+            if self.diffusion is not None and self.dflx is not None:
+                # gas.diff.momentum / gas.diff.energy are Metadata::WithFluxes fields too
+                # (src/gas/gas.cpp:277-285): the same task corrects them
+                multilevel_py.flux_correct(self.mesh, self._fc_plan, self.dflx)
         for fs in self.fluids:
             self.ApplyUpdate(fs, gam0, gam1, bdt)
         for fs in self.fluids:

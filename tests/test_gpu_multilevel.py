@@ -244,3 +244,42 @@ def test_box_copy_and_block_bcs_reject_bad_descriptors():
     with pytest.raises(capi.AB200Error, match="bad face"):
         md.call("ab200_block_bcs", badbc, 1)
     md.close()
+
+
+@pytest.mark.parametrize("ndim,refine", [(3, [(1, 1, 1), (2, 2, 1)]), (2, [(0, 1, 0), (2, 2, 0)])])
+def test_flux_correction_of_the_diffusion_fluxes_strict_bit_identical(ndim, refine):
+    """gas.diff.momentum / gas.diff.energy are Metadata::WithFluxes fields
+    (src/gas/gas.cpp:277-285): ab200_flux_correct restricts them onto every fine-coarse face
+    together with the hydrodynamic fluxes.  rk2 cycles with constant viscosity + conduction on a
+    periodic refined mesh: bit-identical to the oracle (whose corrected run conserves momentum
+    and energy to rounding, tests/test_multilevel_plan.py), and the corrected face values
+    themselves are compared"""
+    from artemis_b200.driver import ArtemisDriver
+    from oracle.oracle_py import OracleSim, make_diffusion
+    from tests.test_gpu_diffusion import _flux, desc_of
+    bcs = (B.periodic,) * 6
+    m = _mesh(Coordinates.cartesian, ndim, bcs, refine)
+    gp = gas_params(Coordinates.cartesian, "plm", "hlle")
+    prim = random_prim(m, gp, seed=61)
+    osim = OracleSim(m, gas=gp)
+    osim.diffusion = make_diffusion(visc=("constant", 2e-2), cond=("conductivity", 3e-2))
+    osim.gas.prim[:] = prim
+    osim.nlim = 2
+    osim.initialize()
+    osim.run()
+    md = MeshData(m, gas=gp, variant="strict", materialize_fluxes=True)
+    md.gas.prim.set(prim)
+    ex = MultilevelExchange(md)
+    drv = ArtemisDriver(md, "rk2", mode="tasks", nlim=2, comm=ex,
+                        diffusion=desc_of(osim.diffusion))
+    drv.Initialize()
+    drv.Execute()
+    assert ex.n["fc"] > 0 and drv.ncycle == osim.ncycle == 2
+    assert drv.dt == osim.dt and drv.time == osim.time
+    assert np.array_equal(md.gas.u0.get(), osim.gas.u0)
+    assert np.array_equal(md.gas.prim.get(), osim.gas.prim)
+    # the diffusion flux arrays of the last stage, corrected faces included
+    for d in range(ndim):
+        assert np.array_equal(_flux(md, d, osim.dflx[d].shape), osim.dflx[d])
+    ex.close()
+    md.close()

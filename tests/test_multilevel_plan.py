@@ -197,6 +197,42 @@ def test_flux_correction_makes_the_refined_mesh_conservative(ndim, refine):
     assert drift[False] >= 1e-8, drift
 
 
+@pytest.mark.parametrize("ndim,refine", [(3, [(1, 1, 1)]), (2, [(1, 1, 0), (2, 2, 0)])])
+def test_flux_correction_covers_the_diffusion_fluxes(ndim, refine):
+    """gas.diff.momentum / gas.diff.energy carry Metadata::WithFluxes (src/gas/gas.cpp:277-285),
+    so AddFluxCorrectionTasks restricts them onto the shared coarse faces as well: with viscosity
+    and conduction on, a periodic refined mesh conserves momentum and total energy to rounding
+    only if the diffusion fluxes are corrected together with the hydrodynamic ones"""
+    from artemis_b200.enums import Coordinates
+    from oracle import multilevel_py
+    from oracle.oracle_py import OracleSim, make_diffusion
+    from tests.helpers import gas_params, random_prim
+    drift = {}
+    for with_diff_fc in (True, False):
+        m = _mesh(ndim, PER, refine)
+        gp = gas_params(Coordinates.cartesian, "plm", "hlle")
+        sim = OracleSim(m, gas=gp)
+        sim.diffusion = make_diffusion(visc=("constant", 2e-2), cond=("conductivity", 3e-2))
+        sim.gas.prim[:] = random_prim(m, gp, seed=9)
+        sim.nlim = 3
+        sim.initialize()
+        if not with_diff_fc:   # hydrodynamic fluxes corrected, diffusion fluxes left alone
+            orig = multilevel_py.flux_correct
+            multilevel_py.flux_correct = (
+                lambda mesh, plan, flux, _o=orig: None if flux is sim.dflx else _o(mesh, plan, flux))
+        try:
+            before = [_total(m, sim.gas.u0, v) for v in range(5)]
+            scale = [_total(m, np.abs(sim.gas.u0), v) for v in range(5)]
+            sim.run()
+        finally:
+            if not with_diff_fc:
+                multilevel_py.flux_correct = orig
+        after = [_total(m, sim.gas.u0, v) for v in range(5)]
+        drift[with_diff_fc] = max(abs(a - b) / s for a, b, s in zip(after, before, scale))
+    assert drift[True] <= 5e-15, drift
+    assert drift[False] >= 1e-10, drift
+
+
 def test_flux_correction_plan_covers_every_fine_coarse_face_once():
     m = _mesh(3, PER, [(1, 1, 1), (2, 1, 1), (1, 2, 2)])
     from artemis_b200.multilevel import flux_correction_plan
