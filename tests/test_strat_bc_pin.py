@@ -17,7 +17,7 @@ from oracle import oracle_py
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "oracle", "_ref", "libstrat_ref.so")
-pytestmark = pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libstrat_ref.so not built")
+needs_ref = pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libstrat_ref.so not built")
 _DP = C.POINTER(C.c_double)
 KIND = {0: 5, 1: 5, 2: 6, 3: 6, 4: 5, 5: 5}   # strat: extrap on x1 / x3, inflow on x2
 
@@ -28,6 +28,7 @@ def _state(rng, nvar, shape, S):
     return a
 
 
+@needs_ref
 @pytest.mark.parametrize("coarse", [0, 1])
 @pytest.mark.parametrize("ng", [2, 4])
 @pytest.mark.parametrize("nx,xmin", [((8, 12, 1), (-0.3, -0.5, 0.0)), ((8, 6, 10), (-0.2, -0.5, -0.4)),
@@ -72,3 +73,27 @@ def test_strat_registers_extrap_on_x1_x3_and_inflow_on_x2_only():
     for face, kind in ((2, 5), (3, 5), (0, 6), (1, 6), (4, 6), (5, 6)):
         with pytest.raises(ValueError):
             oracle_py.strat_bc(a, 0, (0, 0, 0), (1, 1, 1), (2, 2, 2), (3, 3, 3), 0, 1, face, kind)
+
+
+def test_oracle_reproduces_the_golden_vectors():
+    """tests/golden/strat_bc_vectors.npz = outputs of the reference's own functions
+    (tests/golden/make_strat_bc_vectors.py): the pin that survives where neither
+    /root/reference nor oracle/_ref exists"""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location(
+        "make_strat_bc_vectors", os.path.join(here, "golden", "make_strat_bc_vectors.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    gold = np.load(os.path.join(here, "golden", "strat_bc_vectors.npz"))
+    assert int(gold["ncases"]) == len(gen.CASES)
+    for c, case in enumerate(gen.CASES):
+        ndim, n, s, e, dx, x0 = gen.geometry(case)
+        gas, dust = gold[f"gas_in_{c}"].copy(), gold[f"dust_in_{c}"].copy()
+        for face in range(2 * ndim):
+            oracle_py.strat_bc(gas, 0, x0, dx, s, e, 0, 1, face, KIND[face], float(gold["q"]),
+                               float(gold["om0"]))
+            oracle_py.strat_bc(dust, 0, x0, dx, s, e, 1, gen.SD, face, KIND[face], float(gold["q"]),
+                               float(gold["om0"]))
+        assert np.array_equal(gas, gold[f"gas_out_{c}"])
+        assert np.array_equal(dust, gold[f"dust_out_{c}"])
