@@ -72,7 +72,7 @@ class FluxCorDesc(C.Structure):
 class BlockBcDesc(C.Structure):
     """ab200_block_bc_desc"""
     _fields_ = [(n, C.c_int) for n in ("fluid", "block", "var0", "ncomp", "face", "type")] + [
-        ("coarse", C.c_void_p)]
+        ("coarse", C.c_void_p), ("coarse_entries", C.c_void_p)]
 
 
 class DragDesc(C.Structure):

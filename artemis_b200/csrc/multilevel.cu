@@ -74,6 +74,7 @@ k_box_copy(GridDev g, GridDev gc, FluidDev f0, FluidDev f1, const BoxDev *__rest
 struct BcDev {
   int fluid, block, var0, ncomp, face, type;
   double *coarse;
+  double *const *ctab;  // user conditions: per-entry coarse arrays (one per Parthenon Variable)
 };
 
 // GenericBC of one direction: thread per (descriptor, component, transverse cell, ghost layer)
@@ -144,7 +145,7 @@ k_block_user_bcs(GridDev g, GridDev gc, FluidDev f0, FluidDev f1, const BcDev *_
   if (d.face / 2 != dir || (d.type != AB200_BC_EXTRAP && d.type != AB200_BC_INFLOW)) return;
   const FluidDev &f = d.fluid == AB200_GAS ? f0 : f1;
   const bool gas = d.fluid == AB200_GAS;
-  const GridDev &a = d.coarse ? gc : g;
+  const GridDev &a = (d.coarse || d.ctab) ? gc : g;
   const int n[3] = {a.ni, a.nj, a.nk};
   const int lo[3] = {a.is, a.js, a.ks}, hi[3] = {a.ie, a.je, a.ke};
   const int ng = lo[dir];
@@ -176,6 +177,7 @@ k_block_user_bcs(GridDev g, GridDev gc, FluidDev f0, FluidDev f1, const BcDev *_
     // pressure at 4 S + n is not a FillGhost field, PrimToCons recomputes it)
     const int vd = sp, vv = f.S + 3 * sp, ve = 5 * f.S + sp;
     auto ptr = [&](int var) -> double * {
+      if (d.ctab) return d.ctab[var];
       return d.coarse ? d.coarse + (size_t)var * cells : f.prim[(size_t)d.block * f.nvar + var];
     };
     double *pd = ptr(vd), *p1 = ptr(vv), *p2 = ptr(vv + 1), *p3 = ptr(vv + 2);
@@ -427,7 +429,7 @@ int ab200_block_bcs(ab200_ctx *c, const ab200_block_bc_desc *bc, int nd) {
   // the coarse index space (and its even-block-size requirement) matters only to descriptors
   // that name a coarse buffer; a uniform mesh applies its user conditions on fine arrays alone
   for (int q = 0; q < nd; ++q)
-    if (bc[q].coarse) { AB_TRY(ensure_coarse_grid(c)); break; }
+    if (bc[q].coarse || bc[q].coarse_entries) { AB_TRY(ensure_coarse_grid(c)); break; }
   const GridDev &g = c->g, &gc = c->gc;
   std::vector<BcDev> h(nd);
   bool has_dir[3] = {false, false, false}, user_dir[3] = {false, false, false},
@@ -449,6 +451,9 @@ int ab200_block_bcs(ab200_ctx *c, const ab200_block_bc_desc *bc, int nd) {
                "ab200_block_bcs: AB200_BC_INFLOW exists on x2 faces only");
     AB_REQUIRE(!user || (s.var0 == 0 && s.ncomp == f.nvar), AB200_EINVAL,
                "ab200_block_bcs: a user condition takes every pack entry of the fluid");
+    AB_REQUIRE(user || !s.coarse_entries, AB200_EINVAL,
+               "ab200_block_bcs: coarse_entries is for user conditions (outflow / reflect take one "
+               "descriptor per Variable)");
     AB_REQUIRE(s.type != AB200_BC_INFLOW || c->shear_bc_set, AB200_ESTATE,
                "ab200_block_bcs: call ab200_set_shear_bc_params before AB200_BC_INFLOW");
     AB_REQUIRE(s.block >= 0 && s.block < g.nb && s.var0 >= 0 && s.ncomp >= 1 &&
@@ -457,7 +462,7 @@ int ab200_block_bcs(ab200_ctx *c, const ab200_block_bc_desc *bc, int nd) {
     BcDev &d = h[q];
     std::memset(&d, 0, sizeof d);
     d.fluid = s.fluid; d.block = s.block; d.var0 = s.var0; d.ncomp = s.ncomp;
-    d.face = s.face; d.type = s.type; d.coarse = s.coarse;
+    d.face = s.face; d.type = s.type; d.coarse = s.coarse; d.ctab = s.coarse_entries;
     has_dir[s.face / 2] = true;
     (user ? user_dir : generic_dir)[s.face / 2] = true;
   }

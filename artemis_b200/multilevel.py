@@ -391,7 +391,10 @@ class MultilevelExchange:
     def allreduce_min(x):     # one rank: the driver's dt all-reduce is the identity
         return x
 
-    def __init__(self, md, plan: ExchangePlan | None = None):
+    def __init__(self, md, plan: ExchangePlan | None = None, entry_tables: bool = False):
+        """entry_tables: hand the user conditions their coarse arrays the way a Parthenon host
+        has them -- one device pointer per pack entry (ab200_block_bc_desc.coarse_entries; one
+        coarse buffer per Variable) -- instead of one slab per fluid"""
         import ctypes as C
 
         from . import capi
@@ -438,9 +441,19 @@ class MultilevelExchange:
                 for b, face in self.plan.fine_bcs:
                     if int(m.bcs[face]) not in user:
                         fb.append(capi.BlockBcDesc(fl, b, var0, nc, face, kinds[int(m.bcs[face])], None))
+            if entry_tables and any(int(m.bcs[f]) in user for _, f in self.plan.coarse_bcs):
+                # [block][entry] -> that entry's coarse array, as 64-bit words on the device
+                ptrs = np.array([cptr(b, v) for b in range(m.nb) for v in range(nv)], dtype=np.uint64)
+                tab = md._alloc((m.nb * nv,))
+                tab.set(ptrs.view(np.float64))
+                self._entry_tabs = getattr(self, "_entry_tabs", []) + [tab]
             for b, face in self.plan.coarse_bcs:
                 if int(m.bcs[face]) in user:
-                    cb.append(capi.BlockBcDesc(fl, b, 0, nv, face, int(m.bcs[face]), cptr(b, 0)))
+                    if entry_tables:
+                        cb.append(capi.BlockBcDesc(fl, b, 0, nv, face, int(m.bcs[face]), None,
+                                                   tab.ptr + b * nv * 8))
+                    else:
+                        cb.append(capi.BlockBcDesc(fl, b, 0, nv, face, int(m.bcs[face]), cptr(b, 0)))
             for b, face in self.plan.fine_bcs:
                 if int(m.bcs[face]) in user:
                     fb.append(capi.BlockBcDesc(fl, b, 0, nv, face, int(m.bcs[face]), None))
@@ -483,6 +496,7 @@ class MultilevelExchange:
             self.md.call("ab200_flux_correct", self._fc, self.n["fc"])
 
     def close(self):
-        for buf in self.coarse.values():
+        for buf in list(self.coarse.values()) + getattr(self, "_entry_tabs", []):
             buf.free()
         self.coarse = {}
+        self._entry_tabs = []

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define AB200_ABI_VERSION 11
+#define AB200_ABI_VERSION 12
 
 /* src/artemis.hpp:78-105 */
 enum { AB200_CARTESIAN = 0, AB200_CYLINDRICAL = 1, AB200_SPHERICAL1D = 2,
@@ -425,6 +425,13 @@ typedef struct ab200_block_bc_desc {
                                               * every pack entry): the gas condition writes
                                               * species 0, the dust condition every species */
   double *coarse;                            /* DEVICE or NULL */
+  /* User conditions only, optional: DEVICE table of ncomp pointers, the block's coarse array
+   * of every pack entry.  Parthenon keeps ONE coarse buffer per Variable
+   * (Variable::coarse_s, P:interface/variable.hpp:142), so the entries a user condition
+   * couples (density, velocity, sie) are not one slab there; with this table set, `coarse`
+   * is ignored and the face lives in the coarse index space.  NULL: entries contiguous from
+   * `coarse` (or the fine arrays when that is NULL too). */
+  double *const *coarse_entries;
 } ab200_block_bc_desc;
 int ab200_block_bcs(ab200_ctx *ctx, const ab200_block_bc_desc *bcs, int n);
 /* StratParams::q and ::Om0 (src/pgen/strat.hpp:36-44, <rotating_frame> qshear / omega of the

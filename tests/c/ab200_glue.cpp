@@ -147,4 +147,83 @@ Real EstimateTimestepMesh(MeshData<Real> *md, int dev, void *stream) {
   Check(ab200_estimate_timestep(Bind(md, md, dev, stream).ctx, AB200_GAS, &dt));
   return dt;
 }
+
+// ---- user boundary conditions of the strat / ssheet generators ---------------------------------
+// Registered in place of strat::ExtrapInnerX1 ... strat::ExtrapOuterX3
+// (src/pgen/problem_modifier.hpp:114-127), e.g.
+//   pman->app_input->RegisterBoundaryCondition(BF::inner_x1, "extrap",
+//                                              AB200Glue::UserBc<0, AB200_BC_EXTRAP>);
+// Parthenon calls the functions block by block and face by face
+// (ApplyBoundaryConditionsOnCoarseOrFine, P:bvals/boundary_conditions.cpp); each call only APPENDS
+// a descriptor, FlushUserBcs hands the list to the library, which applies the x1 faces of the
+// whole list first, then x2, then x3 -- Parthenon's order within every block.
+struct UserBcQueue {
+  ab200_ctx *ctx = nullptr;
+  int nspecies = 1;
+  std::map<const parthenon::MeshBlock *, int> block_of;  // position of a block in the bound pack
+  std::vector<ab200_block_bc_desc> pending;
+  // per pending descriptor: the block's per-entry coarse arrays [6 S] (empty = fine arrays);
+  // FlushUserBcs uploads them as DEVICE tables (ab200_malloc + ab200_memcpy_h2d)
+  std::vector<std::vector<double *>> coarse_entries_host;
+  std::vector<void *> device_tables;
+};
+inline UserBcQueue &Queue() { static UserBcQueue q; return q; }
+
+template <int FACE, int TYPE>
+void UserBc(std::shared_ptr<parthenon::MeshBlockData<Real>> &mbd, bool coarse) {
+  UserBcQueue &Q = Queue();
+  const int S = Q.nspecies;
+  ab200_block_bc_desc d{};
+  d.fluid = AB200_GAS; d.block = Q.block_of[mbd->GetBlockPointer()];
+  d.var0 = 0; d.ncomp = 6 * S; d.face = FACE; d.type = TYPE;
+  d.coarse = nullptr; d.coarse_entries = nullptr;
+  std::vector<double *> ent;
+  if (coarse) {
+    // one coarse buffer per Variable (P:interface/variable.hpp:139): the pack entries of the
+    // gas primitives in pack order (hllc.hpp:66-73), component c of a Variable at
+    // coarse_s.data() + c * (cells of the coarse index space)
+    for (const char *name : {"gas.prim.density", "gas.prim.velocity", "gas.prim.pressure", "gas.prim.sie"}) {
+      const auto &cs = mbd->Get(name).coarse_s;
+      const size_t ccells = (size_t)cs.GetDim(1) * cs.GetDim(2) * cs.GetDim(3);
+      for (int c = 0; c < cs.GetDim(4); ++c) ent.push_back(cs.data() + c * ccells);
+    }
+  }
+  Q.coarse_entries_host.push_back(ent);
+  Q.pending.push_back(d);
+}
+
+// after ApplyBoundaryConditionsOnCoarseOrFineMD has walked the blocks of the partition
+inline TaskStatus FlushUserBcs(Real qshear, Real omega) {
+  UserBcQueue &Q = Queue();
+  if (Q.pending.empty()) return TaskStatus::complete;
+  Check(ab200_set_shear_bc_params(Q.ctx, qshear, omega));  // StratParams, strat.hpp:36-66
+  for (size_t q = 0; q < Q.pending.size(); ++q) {
+    const auto &ent = Q.coarse_entries_host[q];
+    if (ent.empty()) continue;
+    ab200_block_bc_desc &d = Q.pending[q];
+    void *dev = nullptr;
+    Check(ab200_malloc(Q.ctx, &dev, ent.size() * sizeof(double *)));
+    Check(ab200_memcpy_h2d(Q.ctx, dev, ent.data(), ent.size() * sizeof(double *)));
+    Q.device_tables.push_back(dev);
+    d.coarse_entries = static_cast<double *const *>(dev);
+  }
+  const int rc = ab200_block_bcs(Q.ctx, Q.pending.data(), (int)Q.pending.size());
+  Check(ab200_synchronize(Q.ctx));
+  for (void *dev : Q.device_tables) Check(ab200_free(Q.ctx, dev));
+  Q.device_tables.clear();
+  Q.coarse_entries_host.clear();
+  Q.pending.clear();
+  return Status(rc);
+}
+// the six registrations of the strat problem, as the reference spells them
+inline void RegisterStratBoundaries(
+    void (*reg)(int face, const char *name,
+                void (*fn)(std::shared_ptr<parthenon::MeshBlockData<Real>> &, bool))) {
+  reg(0, "extrap", UserBc<0, AB200_BC_EXTRAP>);
+  reg(1, "extrap", UserBc<1, AB200_BC_EXTRAP>);
+  reg(2, "inflow", UserBc<2, AB200_BC_INFLOW>);
+  reg(3, "inflow", UserBc<3, AB200_BC_INFLOW>);
+  reg(4, "extrap", UserBc<4, AB200_BC_EXTRAP>);
+  reg(5, "extrap", UserBc<5, AB200_BC_EXTRAP>);
+}
 }  // namespace AB200Glue

@@ -26,9 +26,11 @@ struct ParArrayND {
   int GetDim(int i) const { return dim[i - 1]; }
 };
 // P:interface/variable.hpp:138: `ParArrayND<T, VariableState> data;`
+// :139: `ParArrayND<T, VariableState> coarse_s;` (the coarse buffer of the multilevel exchange)
 template <class T>
 struct Variable {
   ParArrayND<T> data;
+  ParArrayND<T> coarse_s;
 };
 // P:coordinates/uniform_cartesian.hpp:84-88 (Dxf), :117-126 (Xf: xmin_[dir-1] + idx * dx_[dir-1])
 struct UniformCartesian {

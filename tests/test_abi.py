@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(variant):
     for n in names:
         assert hasattr(L, n), f"{n} declared in ab200.h but not exported by the {variant} library"
     assert sorted(capi.SYMBOLS) == names, "capi.SYMBOLS is out of sync with include/ab200.h"
-    assert L.ab200_abi_version() == 11
+    assert L.ab200_abi_version() == 12
 
 
 def test_header_is_plain_c():

@@ -117,8 +117,11 @@ def test_rk2_cycles_with_the_ssheet_decks_boundaries(mode, variant, ncyc):
 
 
 @pytest.mark.parametrize("ndim,refine", [(3, [(0, 0, 0), (3, 3, 3), (1, 2, 0)]), (2, [(0, 3, 0), (2, 1, 0)])])
-@pytest.mark.parametrize("variant", ["strict", "fast"])
-def test_refined_mesh_user_bcs_on_fine_arrays_and_coarse_buffers(ndim, refine, variant):
+@pytest.mark.parametrize("variant,entry_tables", [("strict", False), ("fast", False), ("strict", True)])
+def test_refined_mesh_user_bcs_on_fine_arrays_and_coarse_buffers(ndim, refine, variant, entry_tables):
+    """entry_tables: the coarse arrays of the entries reach the user conditions as one device
+    pointer per pack entry (ab200_block_bc_desc.coarse_entries), the way a Parthenon host holds
+    them (one coarse buffer per Variable), instead of one slab per fluid -- same bits"""
     from artemis_b200.multilevel import exchange_plan
     root = tuple(4 if d < ndim else 1 for d in range(3))
     bnx = tuple(8 if d < ndim else 1 for d in range(3))
@@ -131,7 +134,8 @@ def test_refined_mesh_user_bcs_on_fine_arrays_and_coarse_buffers(ndim, refine, v
     osim = OracleSim(m, gas=gp, dust=dp)
     osim.shear_bc = (Q, OM0)
     md = MeshData(m, gas=gp, dust=dp, variant=variant, materialize_fluxes=False, shear_bc=(Q, OM0))
-    ex = MultilevelExchange(md, plan)
+    ex = MultilevelExchange(md, plan, entry_tables=entry_tables)
+    assert bool(getattr(ex, "_entry_tabs", [])) == entry_tables
     for ff, of, seed in zip(md.fluids, osim.fluids, (21, 22)):
         prim = random_prim(m, ff.fp, seed=seed)
         ff.prim.set(prim)
@@ -162,6 +166,10 @@ def test_user_bc_error_behaviour():
                  capi.BlockBcDesc(0, 0, 0, 4, 0, int(B.extrap), None)):
         with pytest.raises(capi.AB200Error):
             md.call("ab200_block_bcs", (capi.BlockBcDesc * 1)(desc), 1)
+    # per-entry coarse tables belong to the user conditions
+    with pytest.raises(capi.AB200Error):
+        md.call("ab200_block_bcs", (capi.BlockBcDesc * 1)(
+            capi.BlockBcDesc(0, 0, 0, 4, 0, int(B.outflow), None, md.gas.prim.ptr)), 1)
     # the device-resident cycle has no state-dependent conditions in its fused ghost fill
     drv = ArtemisDriver(md, "rk2", mode="fused", nlim=1)
     with pytest.raises(capi.AB200Error):
