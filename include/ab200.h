@@ -427,7 +427,7 @@ typedef struct ab200_block_bc_desc {
   double *coarse;                            /* DEVICE or NULL */
   /* User conditions only, optional: DEVICE table of ncomp pointers, the block's coarse array
    * of every pack entry.  Parthenon keeps ONE coarse buffer per Variable
-   * (Variable::coarse_s, P:interface/variable.hpp:142), so the entries a user condition
+   * (Variable::coarse_s, P:interface/variable.hpp:139), so the entries a user condition
    * couples (density, velocity, sie) are not one slab there; with this table set, `coarse`
    * is ignored and the face lives in the coarse index space.  NULL: entries contiguous from
    * `coarse` (or the fine arrays when that is NULL too). */
