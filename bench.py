@@ -63,7 +63,7 @@ def parse():
                     help="config 4: without the deck's point-mass gravity and rotating frame")
     ap.add_argument("--no-flux-correction", action="store_true",
                     help="config 5: fused stage kernels without Parthenon's flux correction")
-    ap.add_argument("--bcs", default="generic", choices=["generic", "deck"],
+    ap.add_argument("--bcs", default="deck", choices=["generic", "deck"],
                     help="config 5: 'deck' = inputs/ssheet/ssheet.in's own user conditions (extrap on "
                          "x1 / x3, inflow on x2: strat.hpp) on fine arrays and coarse buffers; "
                          "'generic' = outflow x1 / x3, periodic x2")

@@ -97,3 +97,39 @@ def test_input_deck_names_map_to_the_user_flags():
     pin = ParameterInput(deck)
     m = UniformMesh.from_input(pin)
     assert tuple(m.bcs) == STRAT
+
+
+def test_host_mirror_names_every_physical_face_once():
+    """MeshData._physical_bc_list (no GPU needed: it only reads the mesh and the fluids): one
+    descriptor per (fluid, boundary block, non-periodic face) for a user condition -- the whole
+    fluid -- and one per FillGhost range for a generic condition; interior blocks get none"""
+    import types
+
+    from artemis_b200.meshdata import MeshData
+    bcs = (B.outflow, B.extrap, B.inflow, B.reflect, B.periodic, B.periodic)
+    mu = UniformMesh(nx=(24, 16, 8), xmin=XMIN, xmax=XMAX, block_nx=(8, 8, 8), nghost=4, bcs=bcs,
+                     coords=CART)
+    gp, dp = _fluids()
+    fake = types.SimpleNamespace(mesh=mu, fluids=[types.SimpleNamespace(fp=gp),
+                                                  types.SimpleNamespace(fp=dp)])
+    lst = MeshData._physical_bc_list(fake, mu.bc_ints())
+    nbx, nby, nbz = mu.lattice_n
+    seen = {}
+    for d in lst:
+        lb = (d.block % nbx, (d.block // nbx) % nby, d.block // (nbx * nby))
+        axis, outer = d.face // 2, d.face % 2
+        assert lb[axis] == ((nbx, nby, nbz)[axis] - 1 if outer else 0)
+        assert d.type == int(bcs[d.face]) and not d.coarse and not d.coarse_entries
+        nvar = (gp if d.fluid == 0 else dp).nvar
+        if d.type >= int(B.extrap):
+            assert (d.var0, d.ncomp) == (0, nvar)
+        seen.setdefault((d.fluid, d.block, d.face), []).append((d.var0, d.ncomp))
+    # x3 is periodic: faces 4 and 5 never appear; every boundary (block, face) appears
+    assert all(k[2] < 4 for k in seen)
+    per_face = {0: nby * nbz, 1: nby * nbz, 2: nbx * nbz, 3: nbx * nbz}
+    for fluid in (0, 1):
+        for face, n in per_face.items():
+            assert sum(1 for k in seen if k[0] == fluid and k[2] == face) == n
+    # generic faces: gas = (density + velocity) and sie, dust = one range
+    assert sorted(seen[(0, 0, 0)]) == [(0, 4), (5, 1)]
+    assert seen[(1, 0, 0)] == [(0, 8)]
