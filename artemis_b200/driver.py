@@ -125,6 +125,12 @@ def AddBoundaryExchangeTasks(md: MeshData, comm=None) -> TaskStatus:
             md.last_error = str(e)
             return TaskStatus.fail
         return TaskStatus.complete
+    if comm is not None and getattr(md, "user_bcs", False):
+        # a face flagged AB200_BC_NONE means "another rank" to the transport and "user condition"
+        # to this mirror: the two are not told apart yet, so refuse instead of exchanging wrongly
+        md.last_error = ("extrap / inflow user conditions on a mesh split across ranks are not "
+                         "supported by the host mirror")
+        return TaskStatus.fail
     st = _task(md, "ab200_exchange_ghosts")
     if st != TaskStatus.complete:
         return st

@@ -133,3 +133,15 @@ def test_host_mirror_names_every_physical_face_once():
     # generic faces: gas = (density + velocity) and sie, dust = one range
     assert sorted(seen[(0, 0, 0)]) == [(0, 4), (5, 1)]
     assert seen[(1, 0, 0)] == [(0, 8)]
+
+
+def test_user_conditions_on_a_split_mesh_are_refused_not_mis_exchanged():
+    """AB200_BC_NONE means "another rank" to the transport and "user condition" to the host
+    mirror; until the two are told apart the exchange task fails loudly (TaskStatus.fail with a
+    reason) instead of exchanging across a physical boundary"""
+    import types
+
+    from artemis_b200.driver import AddBoundaryExchangeTasks, TaskStatus
+    md = types.SimpleNamespace(user_bcs=True)
+    assert AddBoundaryExchangeTasks(md, comm=object()) == TaskStatus.fail
+    assert "split across ranks" in md.last_error
