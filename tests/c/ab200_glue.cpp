@@ -159,7 +159,7 @@ Real EstimateTimestepMesh(MeshData<Real> *md, int dev, void *stream) {
 // whole list first, then x2, then x3 -- Parthenon's order within every block.
 struct UserBcQueue {
   ab200_ctx *ctx = nullptr;
-  int nspecies = 1;
+  int nspecies = 1, dust_species = 0;  // gas / dust nspecies of the bound packs (0: no dust)
   std::map<const parthenon::MeshBlock *, int> block_of;  // position of a block in the bound pack
   std::vector<ab200_block_bc_desc> pending;
   // per pending descriptor: the block's per-entry coarse arrays [6 S] (empty = fine arrays);
@@ -172,24 +172,33 @@ inline UserBcQueue &Queue() { static UserBcQueue q; return q; }
 template <int FACE, int TYPE>
 void UserBc(std::shared_ptr<parthenon::MeshBlockData<Real>> &mbd, bool coarse) {
   UserBcQueue &Q = Queue();
-  const int S = Q.nspecies;
-  ab200_block_bc_desc d{};
-  d.fluid = AB200_GAS; d.block = Q.block_of[mbd->GetBlockPointer()];
-  d.var0 = 0; d.ncomp = 6 * S; d.face = FACE; d.type = TYPE;
-  d.coarse = nullptr; d.coarse_entries = nullptr;
-  std::vector<double *> ent;
-  if (coarse) {
-    // one coarse buffer per Variable (P:interface/variable.hpp:139): the pack entries of the
-    // gas primitives in pack order (hllc.hpp:66-73), component c of a Variable at
-    // coarse_s.data() + c * (cells of the coarse index space)
-    for (const char *name : {"gas.prim.density", "gas.prim.velocity", "gas.prim.pressure", "gas.prim.sie"}) {
-      const auto &cs = mbd->Get(name).coarse_s;
-      const size_t ccells = (size_t)cs.GetDim(1) * cs.GetDim(2) * cs.GetDim(3);
-      for (int c = 0; c < cs.GetDim(4); ++c) ent.push_back(cs.data() + c * ccells);
+  // the reference's functions set the gas and, when do_dust, every dust species in one call
+  // (strat.hpp:183-218); here that is one descriptor per bound fluid
+  const char *const gas_fields[] = {"gas.prim.density", "gas.prim.velocity", "gas.prim.pressure",
+                                    "gas.prim.sie"};
+  const char *const dust_fields[] = {"dust.prim.density", "dust.prim.velocity"};
+  for (int fluid = AB200_GAS; fluid <= (Q.dust_species > 0 ? AB200_DUST : AB200_GAS); ++fluid) {
+    ab200_block_bc_desc d{};
+    d.fluid = fluid; d.block = Q.block_of[mbd->GetBlockPointer()];
+    d.var0 = 0; d.ncomp = fluid == AB200_GAS ? 6 * Q.nspecies : 4 * Q.dust_species;
+    d.face = FACE; d.type = TYPE;
+    d.coarse = nullptr; d.coarse_entries = nullptr;
+    std::vector<double *> ent;
+    if (coarse) {
+      // one coarse buffer per Variable (P:interface/variable.hpp:139): the pack entries of the
+      // fluid's primitives in pack order (hllc.hpp:66-73), component c of a Variable at
+      // coarse_s.data() + c * (cells of the coarse index space)
+      const char *const *names = fluid == AB200_GAS ? gas_fields : dust_fields;
+      const int nnames = fluid == AB200_GAS ? 4 : 2;
+      for (int f = 0; f < nnames; ++f) {
+        const auto &cs = mbd->Get(names[f]).coarse_s;
+        const size_t ccells = (size_t)cs.GetDim(1) * cs.GetDim(2) * cs.GetDim(3);
+        for (int c = 0; c < cs.GetDim(4); ++c) ent.push_back(cs.data() + c * ccells);
+      }
     }
+    Q.coarse_entries_host.push_back(ent);
+    Q.pending.push_back(d);
   }
-  Q.coarse_entries_host.push_back(ent);
-  Q.pending.push_back(d);
 }
 
 // after ApplyBoundaryConditionsOnCoarseOrFineMD has walked the blocks of the partition
